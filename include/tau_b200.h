@@ -1,0 +1,91 @@
+/* tau_b200.h — C-ABI of the B200-native per-timestep update path.
+ *
+ * The reference (seanwevans/fluid-sims @ 78429ea) has no FFI/plugin boundary: each solver's
+ * per-step host sequence is inline code in main().  This header introduces that
+ * boundary: one opaque handle per solver, plain pointers and sizes only, no C++/torch types.
+ * Every entry point cites the reference host sequence it replaces (file:line into the reference).
+ *
+ * Conventions
+ *   - all functions return 0 on success or a negative errno-style code; tau_last_error() returns
+ *     the message for the calling thread.  The CLI binaries wrap calls in TAU_OR_DIE, which prints
+ *     the message to stderr and exits — the reference's CK()/gpuAssert() policy
+ *     (tau_hypersonic_cuda.cu:69-75, tau_gray_scott.cu:29-41).
+ *   - "planes" are row-major SoA arrays in the reference's layout and order.
+ *   - *_step() only enqueues work on the handle's stream; nothing inside it synchronises with the
+ *     host.  *_download(), *_clock() and *_sync() synchronise.
+ *   - slab mode (multi-GPU): a handle owns rows [y_begin, y_begin+ny_local) of the global grid plus
+ *     `halo` ghost rows on each side, which the caller fills between steps (NCCL send/recv on the
+ *     device pointers returned by *_halo_ptrs).  Single-GPU: y_begin=0, ny_local=ny.
+ *   - there is no CPU fallback: creating a handle without a CUDA device fails with -ENODEV.
+ */
+#ifndef TAU_B200_H
+#define TAU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TAU_B200_ABI_VERSION 1
+
+const char *tau_last_error(void);
+int tau_abi_version(void);
+/* number of visible CUDA devices (0 when none / no driver); never fails */
+int tau_device_count(void);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Gray-Scott reaction-diffusion (reference: tau_gray_scott.cu)                                 */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct tau_gs tau_gs;
+
+/* mirrors `struct Params` tau_gray_scott.cu:43-61 (simulation fields only) */
+typedef struct tau_gs_params {
+  int nx, ny;
+  float dx, dt, Du, Dv, feed, kill;
+  unsigned seed;
+} tau_gs_params;
+
+/* defaults of tau_gray_scott.cu:43-61; nx = ny = 128 (headless default, :293-296) */
+void tau_gs_default_params(tau_gs_params *p);
+/* host-side initial pattern, identical to init_pattern() tau_gray_scott.cu:173-204 */
+void tau_gs_init_pattern(float *u, float *v, int nx, int ny, unsigned seed);
+
+/* replaces the cudaMalloc block tau_gray_scott.cu:301-306.  stream may be NULL (own stream). */
+int tau_gs_create(const tau_gs_params *p, int device, int y_begin, int ny_local, void *stream,
+                  tau_gs **out);
+/* init_pattern + H2D (tau_gray_scott.cu:299-309); in slab mode uploads this rank's rows */
+int tau_gs_init(tau_gs *h);
+/* inject caller state: u, v are full ny_local x nx host planes */
+int tau_gs_upload(tau_gs *h, const float *u, const float *v);
+/* THE hot path: nsteps x { step_kernel; swap } of tau_gray_scott.cu:321-329, without the per-step
+ * cudaDeviceSynchronize.  Single-GPU handles apply the periodic wrap themselves; slab handles
+ * (ny_local < ny) expect the ghost rows to have been exchanged before every step. */
+int tau_gs_step(tau_gs *h, int nsteps);
+int tau_gs_download(tau_gs *h, float *u, float *v);
+int tau_gs_sync(tau_gs *h);
+/* device pointers of the CURRENT state planes, pointing at ghost row -1 (pitch nx floats,
+ * ny_local+2 rows). */
+int tau_gs_device_planes(tau_gs *h, float **u, float **v);
+long long tau_gs_steps_done(tau_gs *h);
+/* kernels launched by this handle so far (for bench.py's gpu_launches) */
+long long tau_gs_launch_count(tau_gs *h);
+/* device time of the most recent tau_gs_step() call in ms (CUDA events on the handle's stream) */
+int tau_gs_last_step_ms(tau_gs *h, float *ms);
+int tau_gs_destroy(tau_gs *h);
+
+#ifdef __cplusplus
+}
+#endif
+
+#define TAU_OR_DIE(call)                                          \
+  do {                                                            \
+    int _rc = (call);                                             \
+    if (_rc != 0) {                                               \
+      fprintf(stderr, "%s (%s)\n", tau_last_error(), #call);      \
+      exit(1);                                                    \
+    }                                                             \
+  } while (0)
+
+#endif /* TAU_B200_H */

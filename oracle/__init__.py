@@ -1,0 +1,247 @@
+"""oracle — the CHECKER.  Test infrastructure only.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may
+import this package; the product (fluid_sims_b200/) never does.
+
+  * `oracle.lib`      — liboracle.so: plain-C restatements of the reference algorithms
+                        (oracle/*_oracle.c, each function citing the reference file:line).
+  * `oracle.ref(name)`— oracle/_ref/lib<name>.so: the reference's OWN sources compiled from
+                        /root/reference by oracle/Makefile (prebuilt files travel to the GPU box).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(HERE, "liboracle.so")
+REF_DIR = os.path.join(HERE, "_ref")
+
+
+def build(ref: bool = True) -> None:
+    """Compile liboracle.so (always) and oracle/_ref (when /root/reference is present)."""
+    subprocess.run(["make", "-C", HERE, "-j8", "liboracle.so"] + (["ref"] if ref else []),
+                   check=True, stdout=subprocess.DEVNULL)
+
+
+def _load_lib() -> C.CDLL:
+    if not os.path.exists(_LIB):
+        build(ref=False)
+    return C.CDLL(_LIB)
+
+
+lib = _load_lib()
+
+f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+
+def has_ref(name: str) -> bool:
+    return os.path.exists(os.path.join(REF_DIR, f"lib{name}.so"))
+
+
+_ref_cache: dict = {}
+
+
+def ref(name: str) -> C.CDLL:
+    """Load oracle/_ref/lib<name>.so (the compiled reference)."""
+    if name not in _ref_cache:
+        path = os.path.join(REF_DIR, f"lib{name}.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} not built (run `make -C oracle ref` where "
+                                    "/root/reference exists)")
+        _ref_cache[name] = C.CDLL(path)
+    return _ref_cache[name]
+
+
+# ------------------------------------------------------------------------------------------------
+# Gray-Scott
+# ------------------------------------------------------------------------------------------------
+lib.oracle_gs_run.argtypes = [f32p, f32p, C.c_int, C.c_int] + [C.c_float] * 6 + [C.c_int]
+lib.oracle_gs_run.restype = C.c_int
+lib.oracle_gs_init_pattern.argtypes = [f32p, f32p, C.c_int, C.c_int, C.c_uint]
+lib.oracle_gs_init_pattern.restype = None
+
+
+def gs_init_pattern(nx, ny, seed=1337):
+    u = np.empty((ny, nx), np.float32)
+    v = np.empty((ny, nx), np.float32)
+    lib.oracle_gs_init_pattern(u, v, nx, ny, seed)
+    return u, v
+
+
+def gs_run(u, v, steps, Du=0.2, Dv=0.1, dt=1.0, dx=1.0, feed=0.03, kill=0.06):
+    """CPU oracle: `steps` Gray-Scott steps; returns new (u, v)."""
+    u = np.array(u, np.float32, order="C", copy=True)
+    v = np.array(v, np.float32, order="C", copy=True)
+    ny, nx = u.shape
+    rc = lib.oracle_gs_run(u, v, nx, ny, Du, Dv, dt, dx, feed, kill, steps)
+    assert rc == 0
+    return u, v
+
+
+def ref_gs_run(u, v, steps, Du=0.2, Dv=0.1, dt=1.0, dx=1.0, feed=0.03, kill=0.06):
+    """The reference's own step_kernel on the GPU (oracle/_ref/libref_gs.so)."""
+    r = ref("ref_gs")
+    r.ref_gs_run.argtypes = [f32p, f32p, C.c_int, C.c_int] + [C.c_float] * 6 + [C.c_int]
+    r.ref_gs_run.restype = C.c_int
+    u = np.array(u, np.float32, order="C", copy=True)
+    v = np.array(v, np.float32, order="C", copy=True)
+    ny, nx = u.shape
+    rc = r.ref_gs_run(u, v, nx, ny, Du, Dv, dt, dx, feed, kill, steps)
+    if rc != 0:
+        raise RuntimeError(f"reference Gray-Scott run failed with cudaError {rc}")
+    return u, v
+
+
+def ref_gs_init_pattern(nx, ny, seed=1337):
+    r = ref("ref_gs")
+    r.ref_gs_init_pattern.argtypes = [f32p, f32p, C.c_int, C.c_int, C.c_uint]
+    r.ref_gs_init_pattern.restype = None
+    u = np.empty((ny, nx), np.float32)
+    v = np.empty((ny, nx), np.float32)
+    r.ref_gs_init_pattern(u, v, nx, ny, seed)
+    return u, v
+
+
+# ------------------------------------------------------------------------------------------------
+# 2-D hypersonic (tau_hypersonic_cuda.cu), fp64
+# ------------------------------------------------------------------------------------------------
+class Hyp2dCfg(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("gamma", "cfl", "visc_nu", "visc_rho", "visc_e",
+                                          "inflow_mach", "geom_x0", "geom_cy", "geom_Rb",
+                                          "geom_Rn", "geom_theta")] + [("W", C.c_int), ("H", C.c_int)]
+
+    def as11(self):
+        return np.array([self.gamma, self.cfl, self.visc_nu, self.visc_rho, self.visc_e,
+                         self.inflow_mach, self.geom_x0, self.geom_cy, self.geom_Rb, self.geom_Rn,
+                         self.geom_theta], np.float64)
+
+
+_cfgp = C.POINTER(Hyp2dCfg)
+lib.oracle_hyp2d_default_cfg.argtypes = [_cfgp, C.c_int, C.c_int]
+lib.oracle_hyp2d_default_cfg.restype = None
+lib.oracle_hyp2d_init.argtypes = [_cfgp, f64p, f64p, f64p, f64p, u8p]
+lib.oracle_hyp2d_init.restype = None
+lib.oracle_hyp2d_step.argtypes = [_cfgp, f64p, f64p, f64p, f64p, u8p]
+lib.oracle_hyp2d_step.restype = C.c_double
+lib.oracle_hyp2d_run.argtypes = [_cfgp, f64p, f64p, f64p, f64p, u8p, C.c_int, C.c_void_p]
+lib.oracle_hyp2d_run.restype = C.c_double
+lib.oracle_hyp2d_max_wavespeed.argtypes = [_cfgp, f64p, f64p, f64p, f64p, u8p]
+lib.oracle_hyp2d_max_wavespeed.restype = C.c_double
+lib.oracle_hyp2d_dt.argtypes = [_cfgp, C.c_double]
+lib.oracle_hyp2d_dt.restype = C.c_double
+lib.oracle_hyp2d_snapshot.argtypes = [_cfgp, C.c_int, f64p, f64p, f64p, f64p, u8p, f64p]
+lib.oracle_hyp2d_snapshot.restype = None
+lib.oracle_hyp2d_sdf.argtypes = [C.c_double] * 5
+lib.oracle_hyp2d_sdf.restype = C.c_double
+
+
+def hyp2d_cfg(W, H, **over) -> Hyp2dCfg:
+    c = Hyp2dCfg()
+    lib.oracle_hyp2d_default_cfg(C.byref(c), W, H)
+    for k, v in over.items():
+        setattr(c, k, v)
+    return c
+
+
+def hyp2d_init(cfg: Hyp2dCfg):
+    N = cfg.W * cfg.H
+    planes = [np.empty(N, np.float64) for _ in range(4)]
+    mask = np.empty(N, np.uint8)
+    lib.oracle_hyp2d_init(C.byref(cfg), *planes, mask)
+    return planes, mask
+
+
+def hyp2d_run(cfg: Hyp2dCfg, planes, mask, steps):
+    """CPU oracle: returns (new planes, sim_t, dts)."""
+    planes = [np.array(p, np.float64, order="C", copy=True).ravel() for p in planes]
+    mask = np.ascontiguousarray(mask, np.uint8).ravel()
+    dts = np.zeros(max(steps, 1), np.float64)
+    t = lib.oracle_hyp2d_run(C.byref(cfg), *planes, mask, steps, dts.ctypes.data_as(C.c_void_p))
+    return planes, float(t), dts[:steps]
+
+
+def hyp2d_snapshot(cfg: Hyp2dCfg, steps, planes, mask):
+    out = np.zeros(12, np.float64)
+    lib.oracle_hyp2d_snapshot(C.byref(cfg), steps, *[np.ascontiguousarray(p, np.float64).ravel()
+                                                      for p in planes],
+                              np.ascontiguousarray(mask, np.uint8).ravel(), out)
+    return out
+
+
+def ref_hyp2d_run(W, H, cfg11, steps, planes=None, mask=None, tile=(32, 8)):
+    """The reference's own kernels on the GPU (oracle/_ref/libref_hyp2d_<W>x<H>.so).
+    planes=None -> start from k_init.  Returns (planes, mask, sim_t, dts, ms)."""
+    r = ref(f"ref_hyp2d_{W}x{H}")
+    r.ref_hyp2d_run.argtypes = [f64p, C.c_int, C.c_int, C.c_int, C.c_int, f64p, f64p, f64p, f64p,
+                                u8p, C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_float)]
+    r.ref_hyp2d_run.restype = C.c_int
+    N = W * H
+    do_init = planes is None
+    if do_init:
+        planes = [np.zeros(N, np.float64) for _ in range(4)]
+        mask = np.zeros(N, np.uint8)
+    else:
+        planes = [np.array(p, np.float64, order="C", copy=True).ravel() for p in planes]
+        mask = np.array(mask, np.uint8, order="C", copy=True).ravel()
+    t = C.c_double()
+    ms = C.c_float()
+    dts = np.zeros(max(steps, 1), np.float64)
+    rc = r.ref_hyp2d_run(np.ascontiguousarray(cfg11, np.float64), steps, tile[0], tile[1],
+                         1 if do_init else 0, *planes, mask, C.byref(t),
+                         dts.ctypes.data_as(C.c_void_p), C.byref(ms))
+    if rc != 0:
+        raise RuntimeError(f"reference hyp2d run failed with cudaError {rc}")
+    return planes, mask, float(t.value), dts[:steps], float(ms.value)
+
+
+def ref_hyp2d_eval(W, H, cfg11, kind, vecs):
+    r = ref(f"ref_hyp2d_{W}x{H}")
+    r.ref_hyp2d_eval.argtypes = [f64p, C.c_int, C.c_int, f64p, f64p]
+    r.ref_hyp2d_eval.restype = C.c_int
+    vecs = np.ascontiguousarray(vecs, np.float64)
+    n = vecs.shape[0]
+    out = np.zeros((n, 8), np.float64)
+    rc = r.ref_hyp2d_eval(np.ascontiguousarray(cfg11, np.float64), kind, n, vecs, out)
+    if rc != 0:
+        raise RuntimeError(f"reference hyp2d eval failed with cudaError {rc}")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU hypersonic reference (tau_hypersonic.c / tau_hypersonic_simd.c) — timing baseline
+# ------------------------------------------------------------------------------------------------
+class RefHypCpu:
+    """The reference CPU solver compiled at a fixed WxH (file-static state: one instance per
+    process per library)."""
+
+    def __init__(self, W=256, H=256, simd=False):
+        self.W, self.H = W, H
+        self.lib = ref(f"ref_{'hypsimd' if simd else 'hypcpu'}_{W}x{H}")
+        self.lib.ref_hypcpu_steps.argtypes = [C.c_int]
+        self.lib.ref_hypcpu_steps.restype = C.c_double
+        self.lib.ref_hypcpu_time.restype = C.c_double
+        self.lib.ref_hypcpu_get.argtypes = [f64p, f64p, f64p, f64p, u8p]
+        self.lib.ref_hypcpu_set.argtypes = [f64p, f64p, f64p, f64p, u8p]
+
+    def init(self):
+        self.lib.ref_hypcpu_init()
+
+    def steps(self, n) -> float:
+        return float(self.lib.ref_hypcpu_steps(n))
+
+    @property
+    def sim_t(self) -> float:
+        return float(self.lib.ref_hypcpu_time())
+
+    def get(self):
+        N = self.W * self.H
+        planes = [np.empty(N, np.float64) for _ in range(4)]
+        mask = np.empty(N, np.uint8)
+        self.lib.ref_hypcpu_get(*planes, mask)
+        return planes, mask

@@ -1,0 +1,103 @@
+"""Generate golden fixtures from the REFERENCE's own kernels (oracle/_ref) on a GPU box.
+
+    gpurun -- python tests/golden/make_golden_gpu.py        # writes gpurun_out/golden/*.npz
+    cp gpurun_out/golden/*.npz tests/golden/                 # then commit
+
+The reference holds no golden vectors for these solvers; these files pin the
+CPU oracle (oracle/*.c) to what the reference code itself computes on a B200.  Inputs are seeded;
+each file records the generating arguments.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402
+
+OUT = os.path.join(ROOT, "gpurun_out", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def gs():
+    # (a) reference init pattern + 200 steps at defaults, 96x64
+    u0, v0 = oracle.ref_gs_init_pattern(96, 64, 1337)
+    u1, v1 = oracle.ref_gs_run(u0, v0, 200)
+    # (b) random field, non-default coefficients, odd sizes, dx = 0.5 (power of two)
+    rng = np.random.default_rng(7)
+    ur = rng.random((45, 70), dtype=np.float32)
+    vr = (rng.random((45, 70), dtype=np.float32) * 0.5).astype(np.float32)
+    kw = dict(Du=0.16, Dv=0.08, dt=0.25, dx=0.5, feed=0.0367, kill=0.0649)
+    ur1, vr1 = oracle.ref_gs_run(ur, vr, 33, **kw)
+    # (c) long run where v decays into the flush-to-zero range
+    ul, vl = oracle.ref_gs_run(u0, v0 * np.float32(1e-30), 400)
+    np.savez_compressed(os.path.join(OUT, "gs_ref.npz"), u0=u0, v0=v0, u200=u1, v200=v1, ur=ur,
+                        vr=vr, ur33=ur1, vr33=vr1, kw=np.array(list(kw.values()), np.float32),
+                        ul400=ul, vl400=vl)
+    print("gs golden written")
+
+
+def hyp2d():
+    for (W, H, steps) in ((256, 128, 60), (200, 120, 25)):
+        r = oracle.ref(f"ref_hyp2d_{W}x{H}")
+        cfg11 = np.zeros(11)
+        r.ref_hyp2d_default_config.argtypes = [oracle.f64p]
+        r.ref_hyp2d_default_config(cfg11)
+        p0, mask, _, _, _ = oracle.ref_hyp2d_run(W, H, cfg11, 0)
+        out = {"cfg11": cfg11, "mask": mask, "steps": np.array(steps)}
+        for k, p in zip(("rho0", "mx0", "my0", "E0"), p0):
+            out[k] = p
+        p1, _, t, dts, _ = oracle.ref_hyp2d_run(W, H, cfg11, steps)
+        for k, p in zip(("rho", "mx", "my", "E"), p1):
+            out[k] = p
+        out["sim_t"] = np.array(t)
+        out["dts"] = dts
+        # a second configuration that exercises walls harder: lower Mach, bigger body
+        cfg_b = cfg11.copy()
+        cfg_b[5] = 3.0           # inflow_mach
+        cfg_b[6] = 40.0          # geom_x0
+        p2, mask_b, t2, dts2, _ = oracle.ref_hyp2d_run(W, H, cfg_b, steps)
+        out["cfg11_b"] = cfg_b
+        out["mask_b"] = mask_b
+        for k, p in zip(("rho_b", "mx_b", "my_b", "E_b"), p2):
+            out[k] = p
+        out["sim_t_b"] = np.array(t2)
+        np.savez_compressed(os.path.join(OUT, f"hyp2d_ref_{W}x{H}.npz"), **out)
+    # device-helper vectors: HLLC on random state pairs, limited reconstruction on random triples
+    rng = np.random.default_rng(11)
+    n = 4096
+    cfg11 = np.zeros(11)
+    r = oracle.ref("ref_hyp2d_256x128")
+    r.ref_hyp2d_default_config(cfg11)
+    prim = np.empty((n, 2, 4))
+    prim[..., 0] = rng.uniform(0.05, 8.0, (n, 2))
+    prim[..., 1] = rng.normal(0, 12.0, (n, 2))
+    prim[..., 2] = rng.normal(0, 12.0, (n, 2))
+    prim[..., 3] = rng.uniform(0.02, 60.0, (n, 2))
+    prim[: n // 8, 1, :] = prim[: n // 8, 0, :]          # equal states
+    prim[n // 8: n // 4, :, 1] += 40.0                   # supersonic to the right
+    g = cfg11[0]
+    cons = np.empty((n, 8))
+    for s in range(2):
+        rho, u, v, p = (prim[:, s, k] for k in range(4))
+        cons[:, 4 * s + 0] = rho
+        cons[:, 4 * s + 1] = rho * u
+        cons[:, 4 * s + 2] = rho * v
+        cons[:, 4 * s + 3] = p / (g - 1) + 0.5 * rho * (u * u + v * v)
+    hllc = oracle.ref_hyp2d_eval(256, 128, cfg11, 0, cons)
+    tri = np.empty((n, 12))
+    base = rng.uniform(0.1, 5.0, (n, 4))
+    for k in range(3):
+        tri[:, 4 * k:4 * k + 4] = base + rng.normal(0, 0.8, (n, 4)) * (rng.random((n, 1)) < 0.8)
+    tri[: n // 16, 0] = -0.5   # force the positivity repair loop
+    recon = oracle.ref_hyp2d_eval(256, 128, cfg11, 1, tri)
+    np.savez_compressed(os.path.join(OUT, "hyp2d_ref_helpers.npz"), cfg11=cfg11, hllc_in=cons,
+                        hllc_out=hllc, recon_in=tri, recon_out=recon)
+    print("hyp2d golden written")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["gs", "hyp2d"]
+    for w in which:
+        globals()[w]()

@@ -1,0 +1,1182 @@
+// hypersonic2d.cu — 2-D compressible-flow (MUSCL-Hancock + HLLC + 4th-order diffusion) update path
+// for sm_100a.  Replaces the per-step host sequence of the reference `tau_2d_hypersonic_cuda`
+// binary (tau_hypersonic_cuda.cu:1833-1889):
+//     k_apply_inflow_left -> k_max_wavespeed_blocks -> k_reduce_block_max -> 8-byte D2H + host dt
+//     -> k_predict_face_states -> k_compute_xface_flux -> k_compute_yface_flux -> k_step -> swap
+// with ONE kernel per step and no host round trip.  The arithmetic of every stage follows the
+// reference device helpers (cited at each function); what changes is where intermediate data
+// lives: the reference writes 16 predicted-state planes and 8 flux planes to HBM and re-reads them
+// (517 B/cell in fp64); here they never leave registers.
+//
+// Decomposition ("column marching"): one WARP owns a strip of 30 columns (+1 halo lane each side)
+// and marches down a segment of rows.
+//   * x-direction neighbours (reconstruction stencils, face states, face fluxes) move between
+//     lanes with warp shuffles;
+//   * y-direction state is carried in registers from row to row: the prims of rows r..r+2, the
+//     predicted top state of row r and the flux through the face below it — every y-face flux is
+//     computed exactly once;
+//   * rows of the conserved state are staged through a per-warp shared-memory ring, 4 rows x 40
+//     columns x 4 fields per TMA box (cp.async.bulk.tensor.3d completing on a per-slot mbarrier),
+//     prefetched >= 4 rows ahead, so global latency is hidden without occupancy;
+//   * boundary conditions are folded in at load time: ghost rows of the planes hold the y-clamp
+//     (the kernel refreshes them in its output), edge strips patch inflow / outflow-copy columns in
+//     shared memory, the column-0 inflow overwrite (k_apply_inflow_left) is applied as the tile is
+//     read; so the marching code itself is branch-uniform;
+//   * the max-wavespeed reduction for the NEXT step's dt is fused into the epilogue (warp-shuffle
+//     max + one integer atomicMax per warp; max is exactly associative, so dt is bit-identical to a
+//     standalone reduction) and dt / sim_t live in device memory.
+//
+// Templated on the storage/arithmetic type: double reproduces the reference (fp64) to round-off;
+// float is the BASELINE configuration ("4096x4096 fp32").
+#include "common.cuh"
+#include "../../include/tau_b200.h"
+
+#include <math.h>
+#include <new>
+#include <vector>
+
+namespace {
+
+constexpr int H2_OWN = 30;    // columns owned per warp strip
+constexpr int H2_BOXW = 40;   // staged columns: bx .. bx+39, bx = (x0-2) rounded down to a
+                              // multiple of 4 (TMA wants a 16-byte aligned box origin in fp32)
+constexpr int H2_RB = 4;      // rows per TMA box / ring slot
+constexpr int H2_NS = 3;      // ring slots per warp
+constexpr int H2_WARPS = 4;   // warps per CTA
+constexpr int H2_GHOST = 2;   // ghost rows above/below each plane
+
+struct Ctrl {          // device-resident step control (replaces the host dt logic :1852-1869)
+  double maxspeed[3];  // rotating slots: step s reads [s%3], reduces into [(s+1)%3], clears [(s+2)%3]
+  double sim_t;
+  double dt_last;
+};
+
+template <typename R>
+struct Params {
+  R gamma, gm1, inv_gm1;
+  R visc_nu, visc_rho, visc_e;
+  R infl_cons[4];  // prim_to_cons(inflow_state())
+  R eps_rho, eps_p;
+  double cfl, nu_max, infl_speed;
+  int W, H_local, H_global, y_begin;
+  int seg_rows;   // rows per marching segment
+  int nstrips, nsegs;
+  size_t plane;   // elements per plane incl. ghost rows
+};
+
+template <typename R> struct Cons4 { R rho, mx, my, E; };
+template <typename R> struct Prim4 { R rho, u, v, p; };
+
+template <typename R> __device__ __forceinline__ R rmax(R a, R b) { return a > b ? a : b; }  // :131
+template <typename R> __device__ __forceinline__ R rmin(R a, R b) { return a < b ? a : b; }  // :134
+template <typename R> __device__ __forceinline__ R rabs(R a) { return a < R(0) ? -a : a; }   // :137
+
+// tau_hypersonic_cuda.cu:143-159
+template <typename R>
+__device__ __forceinline__ Prim4<R> cons_to_prim(const Params<R> &P, Cons4<R> c) {
+  Prim4<R> p;
+  R rho = rmax(c.rho, P.eps_rho);
+  R inv = R(1) / rho;
+  R u = c.mx * inv;
+  R v = c.my * inv;
+  R kin = R(0.5) * rho * (u * u + v * v);
+  R eint = c.E - kin;
+  p.rho = rho;
+  p.u = u;
+  p.v = v;
+  p.p = P.gm1 * rmax(eint, P.eps_p);
+  return p;
+}
+// :161-170
+template <typename R>
+__device__ __forceinline__ Cons4<R> prim_to_cons(const Params<R> &P, Prim4<R> p) {
+  Cons4<R> c;
+  R rho = rmax(p.rho, P.eps_rho);
+  R pr = rmax(p.p, P.eps_p);
+  c.rho = rho;
+  c.mx = rho * p.u;
+  c.my = rho * p.v;
+  c.E = pr / P.gm1 + R(0.5) * rho * (p.u * p.u + p.v * p.v);
+  return c;
+}
+// :172-174
+template <typename R>
+__device__ __forceinline__ R sound_speed(const Params<R> &P, Prim4<R> p) {
+  return sqrt(P.gamma * rmax(p.p, P.eps_p) / rmax(p.rho, P.eps_rho));
+}
+// flux_axis<AX>(Cons) :194-203
+template <int AX, typename R>
+__device__ __forceinline__ Cons4<R> flux_axis(const Params<R> &P, Cons4<R> c) {
+  Prim4<R> p = cons_to_prim(P, c);
+  R un = AX == 0 ? p.u : p.v;
+  Cons4<R> f;
+  f.rho = AX == 0 ? c.mx : c.my;
+  f.mx = AX == 0 ? (c.mx * un + p.p) : (c.mx * un);
+  f.my = AX == 0 ? (c.my * un) : (c.my * un + p.p);
+  f.E = (c.E + p.p) * un;
+  return f;
+}
+// :217-228
+template <typename R> __device__ __forceinline__ R minmod(R a, R b) {
+  if (a * b <= R(0)) return R(0);
+  return (rabs(a) < rabs(b)) ? a : b;
+}
+template <typename R> __device__ __forceinline__ R mc_limiter(R dl, R dc, R dr) {
+  R mm1 = minmod(dl, dr);
+  R mm2 = minmod(dc, R(2) * dl);
+  R mm3 = minmod(dc, R(2) * dr);
+  return minmod(mm1, minmod(mm2, mm3));
+}
+// wall_ghost_prim :262-264 followed by prim_to_cons
+template <typename R>
+__device__ __forceinline__ Prim4<R> ghost_prim(Prim4<R> in) {
+  return Prim4<R>{in.rho, -in.u, -in.v, in.p};
+}
+template <typename R>
+__device__ __forceinline__ Cons4<R> ghost_cons(const Params<R> &P, Prim4<R> centre) {
+  return prim_to_cons(P, ghost_prim(centre));
+}
+
+// enforce_positive_faces :373-398
+template <typename R>
+__device__ __forceinline__ void enforce_positive_faces(const Params<R> &P, Prim4<R> &qm,
+                                                       const Prim4<R> &qc, Prim4<R> &qp) {
+  for (int it = 0; it < 8; it++) {
+    bool bad = (qm.rho <= P.eps_rho || qp.rho <= P.eps_rho) || (qm.p <= P.eps_p || qp.p <= P.eps_p);
+    if (!bad) return;
+    qm.rho = R(0.5) * (qm.rho + qc.rho);
+    qm.u = R(0.5) * (qm.u + qc.u);
+    qm.v = R(0.5) * (qm.v + qc.v);
+    qm.p = R(0.5) * (qm.p + qc.p);
+    qp.rho = R(0.5) * (qp.rho + qc.rho);
+    qp.u = R(0.5) * (qp.u + qc.u);
+    qp.v = R(0.5) * (qp.v + qc.v);
+    qp.p = R(0.5) * (qp.p + qc.p);
+  }
+  qm.rho = rmax(qm.rho, P.eps_rho);
+  qp.rho = rmax(qp.rho, P.eps_rho);
+  qm.p = rmax(qm.p, P.eps_p);
+  qp.p = rmax(qp.p, P.eps_p);
+}
+
+// half_step_predict_axis :442-455 (+ the caller's extra floors :936-939)
+template <typename R>
+__device__ __forceinline__ Cons4<R> half_step_predict(const Params<R> &P, Prim4<R> q, Cons4<R> dF,
+                                                      R half_dt) {
+  Cons4<R> c = prim_to_cons(P, q);
+  c.rho -= half_dt * dF.rho;
+  c.mx -= half_dt * dF.mx;
+  c.my -= half_dt * dF.my;
+  c.E -= half_dt * dF.E;
+  Prim4<R> o = cons_to_prim(P, c);
+  o.rho = rmax(o.rho, P.eps_rho);
+  o.p = rmax(o.p, P.eps_p);
+  return prim_to_cons(P, o);
+}
+
+// reconstruct_limited_faces :400-425 + the predictor block of k_predict_face_states :923-961.
+// Returns the predicted (conserved) states on the low ("L"/"B") and high ("R"/"T") side of cell qc.
+template <int AX, typename R>
+__device__ __forceinline__ void reconstruct_predict(const Params<R> &P, Prim4<R> qm, Prim4<R> qc,
+                                                    Prim4<R> qp, R half_dt, Cons4<R> &lo,
+                                                    Cons4<R> &hi) {
+  R s_rho = mc_limiter(qc.rho - qm.rho, R(0.5) * (qp.rho - qm.rho), qp.rho - qc.rho);
+  R s_u = mc_limiter(qc.u - qm.u, R(0.5) * (qp.u - qm.u), qp.u - qc.u);
+  R s_v = mc_limiter(qc.v - qm.v, R(0.5) * (qp.v - qm.v), qp.v - qc.v);
+  R s_p = mc_limiter(qc.p - qm.p, R(0.5) * (qp.p - qm.p), qp.p - qc.p);
+  Prim4<R> qL{qc.rho - R(0.5) * s_rho, qc.u - R(0.5) * s_u, qc.v - R(0.5) * s_v,
+              qc.p - R(0.5) * s_p};
+  Prim4<R> qR{qc.rho + R(0.5) * s_rho, qc.u + R(0.5) * s_u, qc.v + R(0.5) * s_v,
+              qc.p + R(0.5) * s_p};
+  enforce_positive_faces(P, qL, qc, qR);
+  Cons4<R> FL = flux_axis<AX>(P, prim_to_cons(P, qL));
+  Cons4<R> FR = flux_axis<AX>(P, prim_to_cons(P, qR));
+  Cons4<R> dF{FR.rho - FL.rho, FR.mx - FL.mx, FR.my - FL.my, FR.E - FL.E};
+  lo = half_step_predict(P, qL, dF, half_dt);
+  hi = half_step_predict(P, qR, dF, half_dt);
+}
+
+// hlle_axis :483-509
+template <int AX, typename R>
+__device__ __noinline__ Cons4<R> hlle_axis(const Params<R> &P, Cons4<R> UL, Cons4<R> UR) {
+  Prim4<R> L = cons_to_prim(P, UL), Rr = cons_to_prim(P, UR);
+  R uL = AX == 0 ? L.u : L.v, uR = AX == 0 ? Rr.u : Rr.v;
+  R aL = sound_speed(P, L), aR = sound_speed(P, Rr);
+  R SL = rmin(uL - aL, uR - aR), SR = rmax(uL + aL, uR + aR);
+  Cons4<R> FL = flux_axis<AX>(P, UL), FR = flux_axis<AX>(P, UR);
+  if (SL >= R(0)) return FL;
+  if (SR <= R(0)) return FR;
+  R denom = SR - SL;
+  if (rabs(denom) < R(1e-14))
+    return Cons4<R>{R(0.5) * (FL.rho + FR.rho), R(0.5) * (FL.mx + FR.mx), R(0.5) * (FL.my + FR.my),
+                    R(0.5) * (FL.E + FR.E)};
+  R inv = R(1) / denom, ss = SL * SR;
+  Cons4<R> o;
+  o.rho = inv * ((SR * FL.rho + (-SL) * FR.rho) + ss * (UR.rho - UL.rho));
+  o.mx = inv * ((SR * FL.mx + (-SL) * FR.mx) + ss * (UR.mx - UL.mx));
+  o.my = inv * ((SR * FL.my + (-SL) * FR.my) + ss * (UR.my - UL.my));
+  o.E = inv * ((SR * FL.E + (-SL) * FR.E) + ss * (UR.E - UL.E));
+  return o;
+}
+
+// hllc_axis :519-606
+template <int AX, typename R>
+__device__ __forceinline__ Cons4<R> hllc_axis(const Params<R> &P, Cons4<R> UL, Cons4<R> UR) {
+  Prim4<R> L = cons_to_prim(P, UL), Rr = cons_to_prim(P, UR);
+  R unL = AX == 0 ? L.u : L.v, unR = AX == 0 ? Rr.u : Rr.v;
+  R utL = AX == 0 ? L.v : L.u, utR = AX == 0 ? Rr.v : Rr.u;
+  R aL = sound_speed(P, L), aR = sound_speed(P, Rr);
+  R SL = rmin(unL - aL, unR - aR), SR = rmax(unL + aL, unR + aR);
+  Cons4<R> FL = flux_axis<AX>(P, UL), FR = flux_axis<AX>(P, UR);
+  if (SL >= R(0)) return FL;
+  if (SR <= R(0)) return FR;
+  R rhoL = L.rho, rhoR = Rr.rho, pL = L.p, pR = Rr.p;
+  R num = pR - pL + rhoL * unL * (SL - unL) - rhoR * unR * (SR - unR);
+  R den = rhoL * (SL - unL) - rhoR * (SR - unR);
+  bool fallback = (rabs(den) < R(1e-14)) || !isfinite(num) || !isfinite(den);
+  R SM = R(0), pStar = R(0), dLS = R(0), dRS = R(0), rhoStarL = R(0), rhoStarR = R(0);
+  R EStarL = R(0), EStarR = R(0);
+  if (!fallback) {
+    SM = num / den;
+    fallback = !isfinite(SM);
+  }
+  if (!fallback) {
+    pStar = rmax(pL + rhoL * (SL - unL) * (SM - unL), P.eps_p);
+    dLS = SL - SM;
+    dRS = SR - SM;
+    fallback = (rabs(dLS) < R(1e-14)) || (rabs(dRS) < R(1e-14));
+  }
+  if (!fallback) {
+    rhoStarL = rhoL * (SL - unL) / dLS;
+    rhoStarR = rhoR * (SR - unR) / dRS;
+    fallback = !(rhoStarL > R(0)) || !(rhoStarR > R(0)) || !isfinite(rhoStarL) ||
+               !isfinite(rhoStarR);
+  }
+  if (!fallback) {
+    EStarL = ((SL - unL) * UL.E - pL * unL + pStar * SM) / dLS;
+    fallback = !isfinite(EStarL);
+  }
+  if (!fallback) {
+    EStarR = ((SR - unR) * UR.E - pR * unR + pStar * SM) / dRS;
+    fallback = !isfinite(EStarR);
+  }
+  if (fallback) return hlle_axis<AX>(P, UL, UR);
+  Cons4<R> F;
+  if (SM >= R(0)) {
+    R sn = rhoStarL * SM, st = rhoStarL * utL;
+    F.rho = FL.rho + SL * (rhoStarL - UL.rho);
+    F.mx = FL.mx + SL * ((AX == 0 ? sn : st) - UL.mx);
+    F.my = FL.my + SL * ((AX == 0 ? st : sn) - UL.my);
+    F.E = FL.E + SL * (EStarL - UL.E);
+  } else {
+    R sn = rhoStarR * SM, st = rhoStarR * utR;
+    F.rho = FR.rho + SR * (rhoStarR - UR.rho);
+    F.mx = FR.mx + SR * ((AX == 0 ? sn : st) - UR.mx);
+    F.my = FR.my + SR * ((AX == 0 ? st : sn) - UR.my);
+    F.E = FR.E + SR * (EStarR - UR.E);
+  }
+  return F;
+}
+
+template <typename R> __device__ __forceinline__ Prim4<R> shfl_up_prim(Prim4<R> p) {
+  return Prim4<R>{__shfl_up_sync(0xffffffffu, p.rho, 1), __shfl_up_sync(0xffffffffu, p.u, 1),
+                  __shfl_up_sync(0xffffffffu, p.v, 1), __shfl_up_sync(0xffffffffu, p.p, 1)};
+}
+template <typename R> __device__ __forceinline__ Prim4<R> shfl_down_prim(Prim4<R> p) {
+  return Prim4<R>{__shfl_down_sync(0xffffffffu, p.rho, 1), __shfl_down_sync(0xffffffffu, p.u, 1),
+                  __shfl_down_sync(0xffffffffu, p.v, 1), __shfl_down_sync(0xffffffffu, p.p, 1)};
+}
+template <typename R> __device__ __forceinline__ Cons4<R> shfl_up_cons(Cons4<R> c) {
+  return Cons4<R>{__shfl_up_sync(0xffffffffu, c.rho, 1), __shfl_up_sync(0xffffffffu, c.mx, 1),
+                  __shfl_up_sync(0xffffffffu, c.my, 1), __shfl_up_sync(0xffffffffu, c.E, 1)};
+}
+template <typename R> __device__ __forceinline__ Cons4<R> shfl_down_cons(Cons4<R> c) {
+  return Cons4<R>{__shfl_down_sync(0xffffffffu, c.rho, 1), __shfl_down_sync(0xffffffffu, c.mx, 1),
+                  __shfl_down_sync(0xffffffffu, c.my, 1), __shfl_down_sync(0xffffffffu, c.E, 1)};
+}
+
+// Per-warp view of the shared-memory row ring.  Row q (offset from the segment's first staged row)
+// lives in slot (q/4)%NS; a slot is laid out [field][row-in-box][36 columns] as the TMA box lands.
+template <typename R>
+struct Ring {
+  R *base;
+  __device__ __forceinline__ R *row(int q, int f) const {
+    const int slot = (q >> 2) % H2_NS, sub = q & 3;
+    return base + (size_t)slot * (4 * H2_RB * H2_BOXW) + (f * H2_RB + sub) * H2_BOXW;
+  }
+  __device__ __forceinline__ Cons4<R> cons(int q, int c) const {
+    return Cons4<R>{row(q, 0)[c], row(q, 1)[c], row(q, 2)[c], row(q, 3)[c]};
+  }
+};
+
+// 5-tap second derivative (-1, 16, -30, 16, -1)/12 of k_step :1126-1153
+template <typename R>
+__device__ __forceinline__ R d2(R m2, R m1, R c, R p1, R p2) {
+  return (-m2 + R(16) * m1 - R(30) * c + R(16) * p1 - p2) * (R(1) / R(12));
+}
+
+template <typename R, bool USE_TMA>
+__global__ void __launch_bounds__(H2_WARPS * 32)
+hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *__restrict__ Uin,
+           R *__restrict__ Uout, const uint8_t *__restrict__ mask, Ctrl *__restrict__ ctrl,
+           int step_slot) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  constexpr int SLOT_ELEMS = 4 * H2_RB * H2_BOXW;
+  R *ring_base = reinterpret_cast<R *>(smem_raw) + (size_t)warp * H2_NS * SLOT_ELEMS;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)H2_WARPS * H2_NS * SLOT_ELEMS *
+                                                               sizeof(R)) +
+                   warp * H2_NS;
+  Ring<R> ring{ring_base};
+
+  // ---- dt from the device-resident max wavespeed (host rule :1852-1869, evaluated in fp64) ----
+  double maxs = ctrl->maxspeed[step_slot];
+  if (!isfinite(maxs) || maxs < 1e-12) maxs = 1e-12;
+  const double dt_conv = P.cfl * 1.0 / maxs;
+  double dt_diff = dt_conv;
+  if (isfinite(P.nu_max) && P.nu_max > 1e-12) dt_diff = 0.25 / P.nu_max;
+  const double dt_d = fmin(dt_conv, dt_diff);
+  const R dt = (R)dt_d;
+  const R half_dt = (R)(0.5 * dt_d);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ctrl->sim_t += dt_d;
+    ctrl->dt_last = dt_d;
+    ctrl->maxspeed[(step_slot + 2) % 3] = 1e-12;
+  }
+
+  const int item = blockIdx.x * H2_WARPS + warp;
+  if (item >= P.nstrips * P.nsegs) return;
+  const int strip = item % P.nstrips;
+  const int seg = item / P.nstrips;
+  const int W = P.W;
+  const int x0 = strip * H2_OWN;
+  const int x = x0 - 1 + lane;  // this lane's column
+  const int bx = (x0 - 2) & ~3;  // first staged column (16-byte aligned box origin)
+  const int c = x - bx;          // this lane's staged column index
+  const int ys = seg * P.seg_rows;
+  const int ye = min(ys + P.seg_rows, P.H_local);
+  const int nrows = (ye - ys) + 4;  // staged rows: local rows ys-2 .. ye+1
+  const int nblk = (nrows + H2_RB - 1) / H2_RB;
+  const bool owned = (lane >= 1) && (lane <= H2_OWN) && (x < W);
+  const bool edge_strip = (bx < 0) || (bx + H2_BOXW > W);
+  const size_t PL = P.plane;
+
+  if (USE_TMA) {
+    if (lane == 0) {
+      for (int s = 0; s < H2_NS; ++s) tau::mbar_init(&bars[s], 1);
+      tau::mbar_fence_init();
+    }
+    __syncwarp();
+  }
+
+  // stage block k (plane rows ys+4k .. ys+4k+3; plane row = local row + 2) into slot k%NS
+  auto issue = [&](int k) {
+    R *dst = ring_base + (size_t)(k % H2_NS) * SLOT_ELEMS;
+    const int prow = ys + H2_RB * k;
+    if (USE_TMA) {
+      if (lane == 0) {
+        tau::mbar_expect_tx(&bars[k % H2_NS], SLOT_ELEMS * sizeof(R));
+        tau::tma_load_3d(dst, &tmU, bx, prow, 0, &bars[k % H2_NS]);
+      }
+    } else {
+      for (int i = lane; i < SLOT_ELEMS; i += 32) {
+        const int cc = i % H2_BOXW, sub = (i / H2_BOXW) % H2_RB, f = i / (H2_BOXW * H2_RB);
+        const int gx = bx + cc, gr = prow + sub;
+        R v = R(0);
+        if (gx >= 0 && gx < W && gr < P.H_local + 2 * H2_GHOST) v = Uin[f * PL + (size_t)gr * W + gx];
+        dst[i] = v;
+      }
+    }
+  };
+  // wait for block k and fold the x-boundary conditions into the staged rows
+  auto acquire = [&](int k) {
+    if (USE_TMA) tau::mbar_wait(&bars[k % H2_NS], (k / H2_NS) & 1);
+    else __syncwarp();
+    if (edge_strip) {
+      R *dst = ring_base + (size_t)(k % H2_NS) * SLOT_ELEMS;
+      const int prow = ys + H2_RB * k;
+      const int cw = (W - 1) - bx;  // staged column of x = W-1
+      for (int i = lane; i < SLOT_ELEMS; i += 32) {
+        const int cc = i % H2_BOXW, sub = (i / H2_BOXW) % H2_RB, f = i / (H2_BOXW * H2_RB);
+        const int gx = bx + cc, gr = prow + sub;
+        if (gr >= P.H_local + 2 * H2_GHOST) continue;
+        if (gx < 0) {
+          dst[i] = P.infl_cons[f];  // x<0 -> inflow (neighbor_or_wall :277-279)
+        } else if (gx == 0) {
+          if (!mask[(size_t)gr * W]) dst[i] = P.infl_cons[f];  // k_apply_inflow_left :772-784
+        }
+      }
+      __syncwarp();
+      for (int i = lane; i < SLOT_ELEMS; i += 32) {
+        const int cc = i % H2_BOXW;
+        const int gx = bx + cc;
+        if (gx >= W) dst[i] = dst[i - cc + cw];  // x>=W -> raw column W-1 (:280-282)
+      }
+      __syncwarp();
+    }
+  };
+  // 40 mask bits of plane row prow (bit b <-> staged column b); out-of-domain columns read as 0
+  auto mask_row = [&](int prow) -> unsigned long long {
+    const uint8_t *mr = mask + (size_t)prow * W;
+    const int gx = bx + lane;
+    const int m0 = (gx >= 0 && gx < W) ? mr[gx] : 0;
+    const int gx1 = bx + 32 + lane;
+    const int m1 = (lane < H2_BOXW - 32 && gx1 < W) ? mr[gx1] : 0;
+    const unsigned lo = __ballot_sync(0xffffffffu, m0 != 0);
+    const unsigned hi = __ballot_sync(0xffffffffu, m1 != 0);
+    return (unsigned long long)lo | ((unsigned long long)hi << 32);
+  };
+  auto row_in_domain = [&](int r) -> bool {  // local row r inside the GLOBAL grid?
+    const int gy = P.y_begin + r;
+    return gy >= 0 && gy < P.H_global;
+  };
+  auto bit = [&](unsigned long long w, int b) -> bool { return (w >> b) & 1ull; };
+
+  // y-face flux between the cell below (B) and above (T) — k_compute_yface_flux :998-1030
+  auto yface = [&](bool hasB, bool hasT, bool rinB, bool rinT, const Cons4<R> &yT_B,
+                   const Cons4<R> &yB_T, const Prim4<R> &PB, const Prim4<R> &PT,
+                   const Cons4<R> &UB_raw, const Cons4<R> &UT_raw) -> Cons4<R> {
+    Cons4<R> lo, hi;
+    if (hasB && hasT) {
+      lo = yT_B;
+      hi = yB_T;
+    } else if (hasT) {
+      lo = rinB ? ghost_cons(P, PT) : UT_raw;  // neighbor_or_wall(x, yt, 0, -1)
+      hi = yB_T;
+    } else if (hasB) {
+      lo = yT_B;
+      hi = rinT ? ghost_cons(P, PB) : UB_raw;  // neighbor_or_wall(x, yb, 0, +1)
+    } else {
+      return Cons4<R>{R(0), R(0), R(0), R(0)};
+    }
+    return hllc_axis<1>(P, lo, hi);
+  };
+
+  // ------------------------------------------------------------------------------------------
+  // prologue: stage the first blocks, build the carried state for row ys
+  // ------------------------------------------------------------------------------------------
+  int issued = 0, acquired = 0;
+  for (; issued < nblk && issued < H2_NS; ++issued) issue(issued);
+  auto need_row = [&](int q) {
+    while (acquired * H2_RB <= q) {
+      acquire(acquired);
+      ++acquired;
+    }
+  };
+  need_row(3);
+  // mask words for local rows ys-2 .. ys+1 (plane rows ys .. ys+3)
+  unsigned long long mw_m2, mw_m1, mw_c, mw_p1, mw_p2;
+  mw_m1 = mask_row(ys + 0);  // local ys-2
+  mw_c = mask_row(ys + 1);   // local ys-1
+  mw_p1 = mask_row(ys + 2);  // local ys
+  mw_p2 = mask_row(ys + 3);  // local ys+1
+  mw_m2 = 0;
+
+  Prim4<R> Pa = cons_to_prim(P, ring.cons(0, c));  // row ys-2
+  Cons4<R> Ub = ring.cons(1, c);                   // row ys-1
+  Prim4<R> Pb = cons_to_prim(P, Ub);
+  Cons4<R> U0 = ring.cons(2, c);  // row ys
+  Prim4<R> P0 = cons_to_prim(P, U0);
+  Cons4<R> U1 = ring.cons(3, c);  // row ys+1
+  Prim4<R> P1 = cons_to_prim(P, U1);
+
+  Cons4<R> yT_r, G_bot;
+  {
+    // y-reconstruction of cell ys-1 (needs rows ys-2, ys-1, ys) -> its predicted top state
+    Cons4<R> lo_b, hi_b, lo_0, hi_0;
+    Prim4<R> qm = bit(mw_m1, c) ? ghost_prim(Pb) : Pa;
+    Prim4<R> qp = bit(mw_p1, c) ? ghost_prim(Pb) : P0;
+    reconstruct_predict<1>(P, qm, Pb, qp, half_dt, lo_b, hi_b);
+    // y-reconstruction of cell ys (rows ys-1, ys, ys+1)
+    qm = bit(mw_c, c) ? ghost_prim(P0) : Pb;
+    qp = bit(mw_p2, c) ? ghost_prim(P0) : P1;
+    reconstruct_predict<1>(P, qm, P0, qp, half_dt, lo_0, hi_0);
+    const bool rinB = row_in_domain(ys - 1);
+    const bool hasB = rinB && !bit(mw_c, c);
+    const bool hasT = !bit(mw_p1, c);
+    G_bot = yface(hasB, hasT, rinB, true, hi_b, lo_0, Pb, P0, Ub, U0);
+    yT_r = hi_0;
+  }
+  // roll so that (m2, m1, c, p1, p2) describe rows r-2 .. r+2 for r = ys (p2 loaded in the loop)
+  mw_m2 = mw_m1;
+  mw_m1 = mw_c;
+  mw_c = mw_p1;
+  mw_p1 = mw_p2;
+
+  Prim4<R> Pr = P0, Pr1 = P1;
+  Cons4<R> Ur = U0, Ur1 = U1;
+  R wmax = R(0);
+
+  // ------------------------------------------------------------------------------------------
+  // march
+  // ------------------------------------------------------------------------------------------
+  for (int r = ys; r < ye; ++r) {
+    const int q = r - ys + 2;  // staged-row offset of row r
+    need_row(q + 2);
+    mw_p2 = mask_row(r + 2 + H2_GHOST);
+    const Cons4<R> Ur2 = ring.cons(q + 2, c);
+    const Prim4<R> Pr2 = cons_to_prim(P, Ur2);
+
+    // -- y: reconstruct cell r+1, flux through face r+1/2 ------------------------------------
+    Cons4<R> yB1, yT1;
+    {
+      Prim4<R> qm = bit(mw_c, c) ? ghost_prim(Pr1) : Pr;
+      Prim4<R> qp = bit(mw_p2, c) ? ghost_prim(Pr1) : Pr2;
+      reconstruct_predict<1>(P, qm, Pr1, qp, half_dt, yB1, yT1);
+    }
+    const bool m_c = bit(mw_c, c);
+    const bool rinT = row_in_domain(r + 1);
+    const Cons4<R> G_top =
+        yface(!m_c, rinT && !bit(mw_p1, c), true, rinT, yT_r, yB1, Pr, Pr1, Ur, Ur1);
+
+    // -- x: neighbours by shuffle, edge lanes from the staged halo columns --------------------
+    Prim4<R> Pl = shfl_up_prim(Pr), Pq = shfl_down_prim(Pr);
+    if (lane == 0 || lane == 31) {
+      const Prim4<R> e = cons_to_prim(P, ring.cons(q, lane == 0 ? c - 1 : c + 1));
+      if (lane == 0) Pl = e;
+      else Pq = e;
+    }
+    Cons4<R> xL, xR;
+    {
+      Prim4<R> qm = bit(mw_c, c - 1) ? ghost_prim(Pr) : Pl;
+      Prim4<R> qp = bit(mw_c, c + 1) ? ghost_prim(Pr) : Pq;
+      reconstruct_predict<0>(P, qm, Pr, qp, half_dt, xL, xR);
+    }
+    // flux through this lane's RIGHT face (between columns x and x+1) — k_compute_xface_flux
+    Cons4<R> F_right;
+    {
+      const Cons4<R> xL_B = shfl_down_cons(xL);
+      const bool inA = (x >= 0) && (x < W), inB = (x + 1 >= 0) && (x + 1 < W);
+      const bool hasA = inA && !m_c, hasB = inB && !bit(mw_c, c + 1);
+      Cons4<R> lo, hi;
+      bool live = true;
+      if (hasA && hasB) {
+        lo = xR;
+        hi = xL_B;
+      } else if (hasB) {
+        lo = inA ? ghost_cons(P, Pq) : Cons4<R>{P.infl_cons[0], P.infl_cons[1], P.infl_cons[2],
+                                                P.infl_cons[3]};
+        hi = xL_B;
+      } else if (hasA) {
+        lo = xR;
+        hi = inB ? ghost_cons(P, Pr) : ring.cons(q, c + 1);  // x+1>=W: raw column W-1
+      } else {
+        live = false;
+      }
+      F_right = live ? hllc_axis<0>(P, lo, hi) : Cons4<R>{R(0), R(0), R(0), R(0)};
+    }
+    const Cons4<R> F_left = shfl_up_cons(F_right);
+
+    // -- update (k_step :1097-1175) -----------------------------------------------------------
+    if (owned) {
+      Cons4<R> Un = Ur;
+      if (!m_c) {
+        Un.rho -= dt * (F_right.rho - F_left.rho);
+        Un.mx -= dt * (F_right.mx - F_left.mx);
+        Un.my -= dt * (F_right.my - F_left.my);
+        Un.E -= dt * (F_right.E - F_left.E);
+        Un.rho -= dt * (G_top.rho - G_bot.rho);
+        Un.mx -= dt * (G_top.mx - G_bot.mx);
+        Un.my -= dt * (G_top.my - G_bot.my);
+        Un.E -= dt * (G_top.E - G_bot.E);
+
+        const Cons4<R> gh = ghost_cons(P, Pr);  // masked neighbour -> no-slip ghost of the centre
+        const Cons4<R> xm2 = bit(mw_c, c - 2) ? gh : ring.cons(q, c - 2);
+        const Cons4<R> xm1 = bit(mw_c, c - 1) ? gh : ring.cons(q, c - 1);
+        const Cons4<R> xp1 = bit(mw_c, c + 1) ? gh : ring.cons(q, c + 1);
+        const Cons4<R> xp2 = bit(mw_c, c + 2) ? gh : ring.cons(q, c + 2);
+        const Cons4<R> ym2 = bit(mw_m2, c) ? gh : ring.cons(q - 2, c);
+        const Cons4<R> ym1 = bit(mw_m1, c) ? gh : ring.cons(q - 1, c);
+        const Cons4<R> yp1 = bit(mw_p1, c) ? gh : Ur1;
+        const Cons4<R> yp2 = bit(mw_p2, c) ? gh : Ur2;
+        const R lap_rho = d2(xm2.rho, xm1.rho, Ur.rho, xp1.rho, xp2.rho) +
+                          d2(ym2.rho, ym1.rho, Ur.rho, yp1.rho, yp2.rho);
+        const R lap_mx = d2(xm2.mx, xm1.mx, Ur.mx, xp1.mx, xp2.mx) +
+                         d2(ym2.mx, ym1.mx, Ur.mx, yp1.mx, yp2.mx);
+        const R lap_my = d2(xm2.my, xm1.my, Ur.my, xp1.my, xp2.my) +
+                         d2(ym2.my, ym1.my, Ur.my, yp1.my, yp2.my);
+        const R lap_E = d2(xm2.E, xm1.E, Ur.E, xp1.E, xp2.E) + d2(ym2.E, ym1.E, Ur.E, yp1.E, yp2.E);
+        Un.rho += (P.visc_rho * dt) * lap_rho;
+        Un.mx += (P.visc_nu * dt) * lap_mx;
+        Un.my += (P.visc_nu * dt) * lap_my;
+        Un.E += (P.visc_e * dt) * lap_E;
+
+        Un.rho = rmax(Un.rho, P.eps_rho);
+        Prim4<R> pp = cons_to_prim(P, Un);
+        if (pp.p <= P.eps_p || !isfinite(pp.p) || !isfinite(pp.rho) || !isfinite(pp.u) ||
+            !isfinite(pp.v)) {
+          pp.rho = rmax(pp.rho, P.eps_rho);
+          pp.p = rmax(pp.p, P.eps_p);
+          Un = prim_to_cons(P, pp);
+          pp = cons_to_prim(P, Un);
+        }
+        // max wavespeed of the state the NEXT step will see (k_max_wavespeed_blocks :786-819);
+        // column 0 is overwritten with the inflow state before that scan (:1834)
+        R ws;
+        if (x == 0) {
+          ws = (R)P.infl_speed;
+        } else {
+          const R a = sound_speed(P, pp);
+          const R sx = rabs(pp.u) + a, sy = rabs(pp.v) + a;
+          ws = sx > sy ? sx : sy;
+          if (!isfinite(ws)) ws = R(1e-12);
+        }
+        wmax = ws > wmax ? ws : wmax;
+      }
+      const size_t o = (size_t)(r + H2_GHOST) * W + x;
+      Uout[o] = Un.rho;
+      Uout[PL + o] = Un.mx;
+      Uout[2 * PL + o] = Un.my;
+      Uout[3 * PL + o] = Un.E;
+      // keep the y-clamp ghost rows of the output planes current (global edges only)
+      const int gy = P.y_begin + r;
+      if (gy == 0) {
+#pragma unroll
+        for (int g = 1; g <= H2_GHOST; ++g) {
+          const size_t og = (size_t)(r + H2_GHOST - g) * W + x;
+          Uout[og] = Un.rho;
+          Uout[PL + og] = Un.mx;
+          Uout[2 * PL + og] = Un.my;
+          Uout[3 * PL + og] = Un.E;
+        }
+      }
+      if (gy == P.H_global - 1) {
+#pragma unroll
+        for (int g = 1; g <= H2_GHOST; ++g) {
+          const size_t og = (size_t)(r + H2_GHOST + g) * W + x;
+          Uout[og] = Un.rho;
+          Uout[PL + og] = Un.mx;
+          Uout[2 * PL + og] = Un.my;
+          Uout[3 * PL + og] = Un.E;
+        }
+      }
+    }
+
+    // -- roll the carried state ----------------------------------------------------------------
+    G_bot = G_top;
+    yT_r = yT1;
+    Pr = Pr1;
+    Pr1 = Pr2;
+    Ur = Ur1;
+    Ur1 = Ur2;
+    mw_m2 = mw_m1;
+    mw_m1 = mw_c;
+    mw_c = mw_p1;
+    mw_p1 = mw_p2;
+
+    // rows <= q-2 are dead for the next iteration: recycle a slot once its last row is
+    if (((q - 2) & 3) == 3) {
+      __syncwarp();
+      if (issued < nblk) {
+        issue(issued);
+        ++issued;
+      }
+    }
+  }
+
+  wmax = tau::warp_max(wmax);
+  if (lane == 0 && wmax > R(0)) tau::atomic_max_nonneg(&ctrl->maxspeed[(step_slot + 1) % 3], (double)wmax);
+}
+
+// Standalone max-wavespeed scan of the CURRENT state (first step after init/upload) —
+// k_apply_inflow_left + k_max_wavespeed_blocks + k_reduce_block_max :772-847.
+template <typename R>
+__global__ void hyp2d_wavespeed(const Params<R> P, const R *__restrict__ U,
+                                const uint8_t *__restrict__ mask, Ctrl *ctrl, int slot) {
+  const size_t n = (size_t)P.W * P.H_local;
+  R wmax = R(0);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t o = i + (size_t)H2_GHOST * P.W;
+    if (mask[o]) continue;
+    R ws;
+    if (i % P.W == 0) {
+      ws = (R)P.infl_speed;
+    } else {
+      Prim4<R> p = cons_to_prim(P, Cons4<R>{U[o], U[P.plane + o], U[2 * P.plane + o],
+                                            U[3 * P.plane + o]});
+      const R a = sound_speed(P, p);
+      const R sx = rabs(p.u) + a, sy = rabs(p.v) + a;
+      ws = sx > sy ? sx : sy;
+      if (!isfinite(ws)) ws = R(1e-12);
+    }
+    wmax = ws > wmax ? ws : wmax;
+  }
+  wmax = tau::warp_max(wmax);
+  if ((threadIdx.x & 31) == 0 && wmax > R(0)) tau::atomic_max_nonneg(&ctrl->maxspeed[slot], (double)wmax);
+}
+
+// Fill the ghost rows of planes and mask at GLOBAL y-edges with the clamp images (rows 0 / H-1).
+template <typename R>
+__global__ void hyp2d_fill_ghost(const Params<R> P, R *U, uint8_t *mask, int do_mask) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= P.W) return;
+  const bool top = (P.y_begin == 0), bot = (P.y_begin + P.H_local == P.H_global);
+  for (int g = 0; g < H2_GHOST; ++g) {
+    if (top) {
+      const size_t dst = (size_t)g * P.W + x, src = (size_t)H2_GHOST * P.W + x;
+      for (int f = 0; f < 4; ++f) U[f * P.plane + dst] = U[f * P.plane + src];
+      if (do_mask) mask[dst] = mask[src];
+    }
+    if (bot) {
+      const size_t dst = (size_t)(P.H_local + H2_GHOST + g) * P.W + x;
+      const size_t src = (size_t)(P.H_local + H2_GHOST - 1) * P.W + x;
+      for (int f = 0; f < 4; ++f) U[f * P.plane + dst] = U[f * P.plane + src];
+      if (do_mask) mask[dst] = mask[src];
+    }
+  }
+}
+
+// ---- geometry + initial condition: k_init :740-770 (always evaluated in fp64) -------------------
+__device__ __forceinline__ double g_clamp01(double t) { return t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t); }
+__device__ __forceinline__ double g_len2(double x, double y) { return sqrt(x * x + y * y); }
+__device__ double g_sd_segment(double px, double py, double ax, double ay, double bx, double by) {
+  double abx = bx - ax, aby = by - ay, apx = px - ax, apy = py - ay;
+  double denom = abx * abx + aby * aby + 1e-30;
+  double t = g_clamp01((apx * abx + apy * aby) / denom);
+  double qx = ax + t * abx, qy = ay + t * aby;
+  return g_len2(px - qx, py - qy);
+}
+// sdSphereConeCapsule :644-686
+__device__ double g_sd_sphere_cone(double x, double y, double Rb, double Rn, double theta) {
+  double r = y < 0 ? -y : y;
+  double st = sin(theta), ct = cos(theta), tt = tan(theta);
+  double xt = Rn * (1.0 - st), rt = Rn * ct;
+  double xb = xt + (Rb - rt) / (tt > 1e-30 ? tt : 1e-30);
+  double rprof;
+  if (x < 0.0) rprof = -1.0;
+  else if (x <= xt) {
+    double dx = x - Rn, inside = Rn * Rn - dx * dx;
+    rprof = inside > 0.0 ? sqrt(inside) : 0.0;
+  } else if (x <= xb) rprof = rt + (x - xt) * tt;
+  else rprof = -1.0;
+  int inside = (x >= 0.0 && x <= xb && r <= rprof);
+  double d = fabs(g_len2(x - Rn, r) - Rn);
+  double d_cone = g_sd_segment(x, r, xt, rt, xb, Rb);
+  double d_base = g_sd_segment(x, y, xb, -Rb, xb, +Rb);
+  double d_rim = g_len2(x - xb, r - Rb);
+  if (d_cone < d) d = d_cone;
+  if (d_base < d) d = d_base;
+  if (d_rim < d) d = d_rim;
+  return inside ? -d : d;
+}
+
+struct Geom { double x0, cy, Rb, Rn, theta; };
+
+template <typename R>
+__global__ void hyp2d_init(const Params<R> P, Geom G, R rest_E, R *U, uint8_t *mask) {
+  const size_t n = (size_t)P.W * P.H_local;
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = (int)(i % P.W), y = (int)(i / P.W) + P.y_begin;
+  const double X = (double)x - G.x0, Y = (double)y - G.cy;
+  const double st = sin(G.theta), ct = cos(G.theta), tt = tan(G.theta);
+  const double xb = G.Rn * (1.0 - st) + (G.Rb - G.Rn * ct) / (tt > 1e-30 ? tt : 1e-30);  // :729-737
+  double sd = g_sd_sphere_cone(X, Y, G.Rb, G.Rn, G.theta) - G.Rb;
+  sd = sd > (X - xb) ? sd : (X - xb);
+  const uint8_t m = (sd < 0.0) ? 1 : 0;
+  const size_t o = i + (size_t)H2_GHOST * P.W;
+  mask[o] = m;
+  U[o] = P.infl_cons[0];
+  U[P.plane + o] = m ? R(0) : P.infl_cons[1];
+  U[2 * P.plane + o] = m ? R(0) : P.infl_cons[2];
+  U[3 * P.plane + o] = m ? rest_E : P.infl_cons[3];
+}
+
+}  // namespace
+
+// ================================================================================================
+// host side
+// ================================================================================================
+struct tau_hyp2d {
+  tau_hyp2d_config cfg;
+  int W, H, dtype;  // dtype: 0 = f32, 1 = f64
+  int device, y_begin, h_local;
+  bool slab, use_tma;
+  cudaStream_t stream;
+  bool own_stream;
+  void *U[2];        // 4 planes each, contiguous, incl. ghost rows
+  uint8_t *mask;
+  Ctrl *ctrl;
+  CUtensorMap tm[2];
+  int cur;
+  long long steps, launches;
+  bool speed_valid;  // ctrl->maxspeed[steps%3] holds the max wavespeed of the current state
+  int seg_rows;
+  cudaEvent_t ev0, ev1;
+  bool timed;
+  size_t plane_elems;
+};
+
+namespace {
+
+template <typename R>
+Params<R> make_params(const tau_hyp2d *h) {
+  Params<R> P;
+  const tau_hyp2d_config &c = h->cfg;
+  P.gamma = (R)c.gamma;
+  P.gm1 = (R)(c.gamma - 1.0);
+  P.inv_gm1 = (R)(1.0 / (c.gamma - 1.0));
+  P.visc_nu = (R)c.visc_nu;
+  P.visc_rho = (R)c.visc_rho;
+  P.visc_e = (R)c.visc_e;
+  P.eps_rho = (R)1e-25;
+  P.eps_p = (R)1e-25;
+  // inflow_state() :230-238 then prim_to_cons :161-170, in the handle's arithmetic type
+  const R rho = R(1), p = R(1);
+  const R a = (R)sqrt((double)((R)c.gamma * p / rho));
+  const R u = (R)c.inflow_mach * a;
+  P.infl_cons[0] = rho;
+  P.infl_cons[1] = rho * u;
+  P.infl_cons[2] = rho * R(0);
+  P.infl_cons[3] = p / P.gm1 + R(0.5) * rho * (u * u + R(0) * R(0));
+  // wavespeed of a column-0 inflow cell as k_max_wavespeed_blocks would compute it from those cons
+  {
+    R r = P.infl_cons[0], inv = R(1) / r, uu = P.infl_cons[1] * inv, vv = P.infl_cons[2] * inv;
+    R kin = R(0.5) * r * (uu * uu + vv * vv);
+    R eint = P.infl_cons[3] - kin;
+    R pr = P.gm1 * (eint > P.eps_p ? eint : P.eps_p);
+    R aa = (R)sqrt((double)(P.gamma * pr / r));
+    if (sizeof(R) == 4) aa = sqrtf((float)(P.gamma * pr / r));
+    R sx = (uu < 0 ? -uu : uu) + aa, sy = (vv < 0 ? -vv : vv) + aa;
+    P.infl_speed = (double)(sx > sy ? sx : sy);
+  }
+  P.cfl = c.cfl;
+  P.nu_max = fmax(c.visc_nu, fmax(c.visc_rho, c.visc_e));
+  P.W = h->W;
+  P.H_local = h->h_local;
+  P.H_global = h->H;
+  P.y_begin = h->y_begin;
+  P.seg_rows = h->seg_rows;
+  P.nstrips = (h->W + H2_OWN - 1) / H2_OWN;
+  P.nsegs = (h->h_local + h->seg_rows - 1) / h->seg_rows;
+  P.plane = h->plane_elems;
+  return P;
+}
+
+template <typename R>
+size_t step_smem_bytes() {
+  return (size_t)H2_WARPS * H2_NS * 4 * H2_RB * H2_BOXW * sizeof(R) + H2_WARPS * H2_NS * sizeof(uint64_t);
+}
+
+template <typename R>
+int launch_wavespeed(tau_hyp2d *h, int slot) {
+  Params<R> P = make_params<R>(h);
+  TAU_CUDA(cudaMemsetAsync(&h->ctrl->maxspeed[slot], 0, sizeof(double), h->stream));
+  hyp2d_wavespeed<R><<<148 * 8, 256, 0, h->stream>>>(P, (const R *)h->U[h->cur], h->mask, h->ctrl, slot);
+  h->launches++;
+  TAU_CUDA(cudaGetLastError());
+  return TAU_OK;
+}
+
+template <typename R>
+int launch_fill_ghost(tau_hyp2d *h, int do_mask) {
+  Params<R> P = make_params<R>(h);
+  hyp2d_fill_ghost<R><<<(h->W + 255) / 256, 256, 0, h->stream>>>(P, (R *)h->U[h->cur], h->mask, do_mask);
+  h->launches++;
+  TAU_CUDA(cudaGetLastError());
+  return TAU_OK;
+}
+
+template <typename R>
+int launch_init(tau_hyp2d *h) {
+  Params<R> P = make_params<R>(h);
+  Geom G{h->cfg.geom_x0, h->cfg.geom_cy, h->cfg.geom_Rb, h->cfg.geom_Rn, h->cfg.geom_theta};
+  // body cells start at rest: prim_to_cons({rho, 0, 0, p}) -> E = p/(gamma-1)
+  const R rest_E = R(1) / P.gm1 + R(0.5) * R(1) * (R(0) * R(0) + R(0) * R(0));
+  const size_t n = (size_t)h->W * h->h_local;
+  hyp2d_init<R><<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(P, G, rest_E, (R *)h->U[h->cur], h->mask);
+  h->launches++;
+  TAU_CUDA(cudaGetLastError());
+  return TAU_OK;
+}
+
+template <typename R>
+int launch_steps(tau_hyp2d *h, int nsteps) {
+  Params<R> P = make_params<R>(h);
+  const size_t smem = step_smem_bytes<R>();
+  const int items = P.nstrips * P.nsegs;
+  const int grid = (items + H2_WARPS - 1) / H2_WARPS;
+  static bool attr_done[2][2] = {{false, false}, {false, false}};
+  auto kern_tma = hyp2d_step<R, true>;
+  auto kern_gen = hyp2d_step<R, false>;
+  const int ti = sizeof(R) == 8;
+  if (!attr_done[ti][0]) {
+    TAU_CUDA(cudaFuncSetAttribute(kern_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TAU_CUDA(cudaFuncSetAttribute(kern_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done[ti][0] = true;
+  }
+  for (int s = 0; s < nsteps; ++s) {
+    const int a = h->cur, b = a ^ 1;
+    const int slot = (int)(h->steps % 3);
+    if (h->use_tma)
+      kern_tma<<<grid, H2_WARPS * 32, smem, h->stream>>>(h->tm[a], P, (const R *)h->U[a], (R *)h->U[b],
+                                                         h->mask, h->ctrl, slot);
+    else
+      kern_gen<<<grid, H2_WARPS * 32, smem, h->stream>>>(h->tm[a], P, (const R *)h->U[a], (R *)h->U[b],
+                                                         h->mask, h->ctrl, slot);
+    h->launches++;
+    h->cur = b;
+    h->steps++;
+  }
+  TAU_CUDA(cudaGetLastError());
+  return TAU_OK;
+}
+
+int elem_size(const tau_hyp2d *h) { return h->dtype ? 8 : 4; }
+
+}  // namespace
+
+extern "C" {
+
+// default_config() tau_hypersonic_cuda.cu:1394-1409 with the H-derived geometry evaluated for the
+// runtime grid height.
+void tau_hyp2d_default_config(tau_hyp2d_config *c, int W, int H) {
+  (void)W;
+  c->gamma = 1.1;
+  c->cfl = 0.25;
+  c->visc_nu = 5e-2;
+  c->visc_rho = 5e-2;
+  c->visc_e = 2e-2;
+  c->inflow_mach = 25.0;
+  c->geom_x0 = 125.0;
+  c->geom_cy = (double)H / 2.0;
+  c->geom_Rb = (double)H / 12.0;
+  c->geom_Rn = (double)H / 24.0;
+  c->geom_theta = 3.14159265358979323846 / 4.0;
+  c->steps_per_frame = 2;
+}
+
+// The validation block of parse_args() :1545-1637, same messages.
+int tau_hyp2d_validate_config(const tau_hyp2d_config *cfg) {
+  TAU_REQUIRE(cfg, "tau_hyp2d_validate_config: null config");
+  TAU_REQUIRE(cfg->gamma > 1.0, "Invalid --gamma: %.8g (must be > 1).", cfg->gamma);
+  TAU_REQUIRE(cfg->cfl > 0.0, "Invalid --cfl: %.8g (must be > 0).", cfg->cfl);
+  TAU_REQUIRE(cfg->visc_nu >= 0.0, "Invalid --visc-nu: %.8g (must be >= 0).", cfg->visc_nu);
+  TAU_REQUIRE(cfg->visc_rho >= 0.0, "Invalid --visc-rho: %.8g (must be >= 0).", cfg->visc_rho);
+  TAU_REQUIRE(cfg->visc_e >= 0.0, "Invalid --visc-e: %.8g (must be >= 0).", cfg->visc_e);
+  TAU_REQUIRE(cfg->inflow_mach > 0.0, "Invalid --mach: %.8g (must be > 0).", cfg->inflow_mach);
+  TAU_REQUIRE(cfg->steps_per_frame > 0 && cfg->steps_per_frame <= 1024,
+              "Invalid --steps-per-frame: %d (must be in [1, 1024]).", cfg->steps_per_frame);
+  TAU_REQUIRE(cfg->geom_Rb > 0.0, "Invalid --geom-rb: %.8g (must be > 0).", cfg->geom_Rb);
+  TAU_REQUIRE(cfg->geom_Rn > 0.0, "Invalid --geom-rn: %.8g (must be > 0).", cfg->geom_Rn);
+  TAU_REQUIRE(cfg->geom_theta > 0.0 && cfg->geom_theta < 3.14159265358979323846 / 2.0,
+              "Invalid --geom-theta: %.8g (must be in (0, pi/2)).", cfg->geom_theta);
+  const double st = sin(cfg->geom_theta), ct = cos(cfg->geom_theta), tt = tan(cfg->geom_theta);
+  const double xt = cfg->geom_Rn * (1.0 - st), rt = cfg->geom_Rn * ct;
+  TAU_REQUIRE(cfg->geom_Rb >= rt,
+              "Invalid geometry: --geom-rb %.8g is smaller than the tangent radius %.8g implied by "
+              "--geom-rn %.8g and --geom-theta %.8g. Require geom-rb >= geom-rn*cos(theta).",
+              cfg->geom_Rb, rt, cfg->geom_Rn, cfg->geom_theta);
+  TAU_REQUIRE(isfinite(tt) && tt > 0.0,
+              "Invalid geometry: tan(theta)=%.8g for --geom-theta %.8g must be finite and positive.",
+              tt, cfg->geom_theta);
+  const double xb = xt + (cfg->geom_Rb - rt) / tt;
+  TAU_REQUIRE(isfinite(xb), "Invalid geometry: computed xb is non-finite (xb=%.8g).", xb);
+  TAU_REQUIRE(xb >= xt, "Invalid geometry: computed xb %.8g is behind cone tangent point xt %.8g.",
+              xb, xt);
+  return TAU_OK;
+}
+
+int tau_hyp2d_create(const tau_hyp2d_config *cfg, int W, int H, int dtype, int device, int y_begin,
+                     int h_local, void *stream, tau_hyp2d **out) {
+  TAU_REQUIRE(cfg && out, "tau_hyp2d_create: null argument");
+  TAU_REQUIRE(W >= 4 && H >= 1, "tau_hyp2d_create: grid %d x %d too small (W >= 4, H >= 1)", W, H);
+  TAU_REQUIRE(dtype == 0 || dtype == 1, "tau_hyp2d_create: dtype must be 0 (f32) or 1 (f64)");
+  TAU_REQUIRE(y_begin >= 0 && h_local > 0 && y_begin + h_local <= H,
+              "tau_hyp2d_create: slab rows [%d,%d) outside [0,%d)", y_begin, y_begin + h_local, H);
+  TAU_REQUIRE(h_local == H || h_local >= H2_GHOST,
+              "tau_hyp2d_create: a slab needs at least %d rows", H2_GHOST);
+  int rc = tau_hyp2d_validate_config(cfg);
+  if (rc) return rc;
+  if (tau_device_count() <= 0) {
+    tau_set_error("tau_hyp2d_create: no CUDA device (this library has no CPU fallback)");
+    return TAU_ERR_NODEV;
+  }
+  TAU_CUDA(cudaSetDevice(device));
+  tau_hyp2d *h = new (std::nothrow) tau_hyp2d();
+  if (!h) return TAU_ERR_NOMEM;
+  h->cfg = *cfg;
+  h->W = W;
+  h->H = H;
+  h->dtype = dtype;
+  h->device = device;
+  h->y_begin = y_begin;
+  h->h_local = h_local;
+  h->slab = (h_local != H);
+  const int es = dtype ? 8 : 4;
+  h->use_tma = ((size_t)W * es) % 16 == 0;
+  h->cur = 0;
+  h->steps = 0;
+  h->launches = 0;
+  h->speed_valid = false;
+  h->timed = false;
+  h->seg_rows = 64;
+  if (const char *e = getenv("TAU_HYP2D_SEG_ROWS")) {
+    int v = atoi(e);
+    if (v >= 4) h->seg_rows = v;
+  }
+  if (stream) {
+    h->stream = (cudaStream_t)stream;
+    h->own_stream = false;
+  } else {
+    TAU_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+  }
+  h->plane_elems = (size_t)W * (h_local + 2 * H2_GHOST);
+  const size_t bytes = 4 * h->plane_elems * es;
+  for (int b = 0; b < 2; ++b) {
+    TAU_CUDA(cudaMalloc(&h->U[b], bytes));
+    TAU_CUDA(cudaMemsetAsync(h->U[b], 0, bytes, h->stream));
+  }
+  TAU_CUDA(cudaMalloc(&h->mask, h->plane_elems));
+  TAU_CUDA(cudaMemsetAsync(h->mask, 0, h->plane_elems, h->stream));
+  TAU_CUDA(cudaMalloc(&h->ctrl, sizeof(Ctrl)));
+  TAU_CUDA(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->stream));
+  if (h->use_tma) {
+    const uint64_t dims[3] = {(uint64_t)W, (uint64_t)(h_local + 2 * H2_GHOST), 4};
+    const uint64_t strides[2] = {(uint64_t)W * es, (uint64_t)h->plane_elems * es};
+    const uint32_t box[3] = {H2_BOXW, H2_RB, 4};
+    for (int b = 0; b < 2; ++b) {
+      rc = tau_make_tensor_map(&h->tm[b], h->U[b], es, 3, dims, strides, box);
+      if (rc) return rc;
+    }
+  } else {
+    memset(h->tm, 0, sizeof(h->tm));
+  }
+  TAU_CUDA(cudaEventCreate(&h->ev0));
+  TAU_CUDA(cudaEventCreate(&h->ev1));
+  *out = h;
+  return TAU_OK;
+}
+
+static int hyp2d_state_changed(tau_hyp2d *h, int fill_mask) {
+  int rc = h->dtype ? launch_fill_ghost<double>(h, fill_mask) : launch_fill_ghost<float>(h, fill_mask);
+  if (rc) return rc;
+  const int slot = (int)(h->steps % 3);
+  rc = h->dtype ? launch_wavespeed<double>(h, slot) : launch_wavespeed<float>(h, slot);
+  if (rc) return rc;
+  h->speed_valid = true;
+  return TAU_OK;
+}
+
+int tau_hyp2d_init(tau_hyp2d *h) {
+  TAU_REQUIRE(h, "tau_hyp2d_init: null handle");
+  TAU_CUDA(cudaSetDevice(h->device));
+  h->steps = 0;
+  TAU_CUDA(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->stream));
+  int rc = h->dtype ? launch_init<double>(h) : launch_init<float>(h);
+  if (rc) return rc;
+  rc = hyp2d_state_changed(h, 1);
+  if (rc) return rc;
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  return TAU_OK;
+}
+
+int tau_hyp2d_upload(tau_hyp2d *h, const void *const planes[4], const uint8_t *mask) {
+  TAU_REQUIRE(h && planes, "tau_hyp2d_upload: null argument");
+  TAU_CUDA(cudaSetDevice(h->device));
+  const int es = elem_size(h);
+  const size_t row0 = (size_t)H2_GHOST * h->W;
+  const size_t n = (size_t)h->W * h->h_local;
+  for (int f = 0; f < 4; ++f) {
+    TAU_REQUIRE(planes[f], "tau_hyp2d_upload: null plane %d", f);
+    TAU_CUDA(cudaMemcpyAsync((char *)h->U[h->cur] + (f * h->plane_elems + row0) * es, planes[f], n * es,
+                             cudaMemcpyHostToDevice, h->stream));
+  }
+  if (mask) TAU_CUDA(cudaMemcpyAsync(h->mask + row0, mask, n, cudaMemcpyHostToDevice, h->stream));
+  int rc = hyp2d_state_changed(h, mask ? 1 : 0);
+  if (rc) return rc;
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  return TAU_OK;
+}
+
+int tau_hyp2d_step(tau_hyp2d *h, int nsteps) {
+  TAU_REQUIRE(h, "tau_hyp2d_step: null handle");
+  TAU_REQUIRE(nsteps >= 0, "tau_hyp2d_step: nsteps must be >= 0");
+  TAU_REQUIRE(!(h->slab && nsteps > 1),
+              "tau_hyp2d_step: a slab handle advances one step per call (ghost rows and the max "
+              "wavespeed must be exchanged in between)");
+  TAU_REQUIRE(h->speed_valid, "tau_hyp2d_step: no state (call tau_hyp2d_init or tau_hyp2d_upload)");
+  TAU_CUDA(cudaSetDevice(h->device));
+  TAU_CUDA(cudaEventRecord(h->ev0, h->stream));
+  int rc = h->dtype ? launch_steps<double>(h, nsteps) : launch_steps<float>(h, nsteps);
+  if (rc) return rc;
+  TAU_CUDA(cudaEventRecord(h->ev1, h->stream));
+  h->timed = true;
+  return TAU_OK;
+}
+
+int tau_hyp2d_clock(tau_hyp2d *h, double *sim_t, double *dt_last) {
+  TAU_REQUIRE(h, "tau_hyp2d_clock: null handle");
+  Ctrl c;
+  TAU_CUDA(cudaMemcpyAsync(&c, h->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  if (sim_t) *sim_t = c.sim_t;
+  if (dt_last) *dt_last = c.dt_last;
+  return TAU_OK;
+}
+
+int tau_hyp2d_download(tau_hyp2d *h, void *const planes[4], uint8_t *mask) {
+  TAU_REQUIRE(h && planes, "tau_hyp2d_download: null argument");
+  TAU_CUDA(cudaSetDevice(h->device));
+  const int es = elem_size(h);
+  const size_t row0 = (size_t)H2_GHOST * h->W;
+  const size_t n = (size_t)h->W * h->h_local;
+  for (int f = 0; f < 4; ++f)
+    if (planes[f])
+      TAU_CUDA(cudaMemcpyAsync(planes[f], (char *)h->U[h->cur] + (f * h->plane_elems + row0) * es, n * es,
+                               cudaMemcpyDeviceToHost, h->stream));
+  if (mask) TAU_CUDA(cudaMemcpyAsync(mask, h->mask + row0, n, cudaMemcpyDeviceToHost, h->stream));
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  return TAU_OK;
+}
+
+int tau_hyp2d_sync(tau_hyp2d *h) {
+  TAU_REQUIRE(h, "tau_hyp2d_sync: null handle");
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  return TAU_OK;
+}
+
+int tau_hyp2d_device_state(tau_hyp2d *h, void **planes, uint8_t **mask, double **maxspeed_slot) {
+  TAU_REQUIRE(h, "tau_hyp2d_device_state: null handle");
+  if (planes) *planes = h->U[h->cur];
+  if (mask) *mask = h->mask;
+  if (maxspeed_slot) *maxspeed_slot = &h->ctrl->maxspeed[h->steps % 3];
+  return TAU_OK;
+}
+
+int tau_hyp2d_set_seg_rows(tau_hyp2d *h, int rows) {
+  TAU_REQUIRE(h && rows >= 4, "tau_hyp2d_set_seg_rows: rows must be >= 4");
+  h->seg_rows = rows;
+  return TAU_OK;
+}
+
+long long tau_hyp2d_steps_done(tau_hyp2d *h) { return h ? h->steps : -1; }
+long long tau_hyp2d_launch_count(tau_hyp2d *h) { return h ? h->launches : -1; }
+
+int tau_hyp2d_last_step_ms(tau_hyp2d *h, float *ms) {
+  TAU_REQUIRE(h && ms, "tau_hyp2d_last_step_ms: null argument");
+  TAU_REQUIRE(h->timed, "tau_hyp2d_last_step_ms: no step has been timed yet");
+  TAU_CUDA(cudaEventSynchronize(h->ev1));
+  TAU_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return TAU_OK;
+}
+
+int tau_hyp2d_destroy(tau_hyp2d *h) {
+  if (!h) return TAU_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(h->ctrl);
+  cudaFree(h->mask);
+  cudaFree(h->U[1]);
+  cudaFree(h->U[0]);
+  cudaEventDestroy(h->ev1);
+  cudaEventDestroy(h->ev0);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return TAU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,169 @@
+"""Host-side mirror of the reference `tau_2d_hypersonic_cuda` solver (tau_hypersonic_cuda.cu) over
+the C-ABI.  Names follow the reference: `SimConfig` (:37-50), `default_config` (:1394-1409), the
+flag validation of `parse_args` (:1545-1637) and the per-step sequence (:1833-1889), here
+`Hypersonic2D.step()`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, fields
+
+import numpy as np
+
+from ._lib import check, declare
+
+
+class _CConfig(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("gamma", "cfl", "visc_nu", "visc_rho", "visc_e",
+                                          "inflow_mach", "geom_x0", "geom_cy", "geom_Rb", "geom_Rn",
+                                          "geom_theta")] + [("steps_per_frame", C.c_int)]
+
+
+_h = C.c_void_p
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_default = declare("tau_hyp2d_default_config", [C.POINTER(_CConfig), C.c_int, C.c_int], None)
+_validate = declare("tau_hyp2d_validate_config", [C.POINTER(_CConfig)])
+_create = declare("tau_hyp2d_create", [C.POINTER(_CConfig), C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_void_p, C.POINTER(_h)])
+_init = declare("tau_hyp2d_init", [_h])
+_upload = declare("tau_hyp2d_upload", [_h, C.POINTER(C.c_void_p), C.c_void_p])
+_step = declare("tau_hyp2d_step", [_h, C.c_int])
+_clock = declare("tau_hyp2d_clock", [_h, C.POINTER(C.c_double), C.POINTER(C.c_double)])
+_download = declare("tau_hyp2d_download", [_h, C.POINTER(C.c_void_p), C.c_void_p])
+_sync = declare("tau_hyp2d_sync", [_h])
+_devstate = declare("tau_hyp2d_device_state", [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                               C.POINTER(C.c_void_p)])
+_set_seg = declare("tau_hyp2d_set_seg_rows", [_h, C.c_int])
+_steps_done = declare("tau_hyp2d_steps_done", [_h], C.c_longlong)
+_launches = declare("tau_hyp2d_launch_count", [_h], C.c_longlong)
+_last_ms = declare("tau_hyp2d_last_step_ms", [_h, C.POINTER(C.c_float)])
+_destroy = declare("tau_hyp2d_destroy", [_h])
+
+HALO = 2
+
+
+@dataclass
+class SimConfig:
+    """`struct SimConfig` (tau_hypersonic_cuda.cu:37-50) plus the grid size, which the reference
+    fixes at compile time (`#define W 8192 / H 1024`, :28-29)."""
+    W: int
+    H: int
+    gamma: float = 1.1
+    cfl: float = 0.25
+    visc_nu: float = 5e-2
+    visc_rho: float = 5e-2
+    visc_e: float = 2e-2
+    inflow_mach: float = 25.0
+    geom_x0: float = 125.0
+    geom_cy: float = 0.0
+    geom_Rb: float = 0.0
+    geom_Rn: float = 0.0
+    geom_theta: float = 0.0
+    steps_per_frame: int = 2
+
+    @classmethod
+    def default(cls, W: int = 8192, H: int = 1024, **over) -> "SimConfig":
+        """default_config() (:1394-1409) — geometry derived from H."""
+        c = _CConfig()
+        _default(C.byref(c), W, H)
+        kw = {f[0]: getattr(c, f[0]) for f in _CConfig._fields_}
+        kw.update(over)
+        return cls(W=W, H=H, **kw)
+
+    def _c(self) -> _CConfig:
+        return _CConfig(*[getattr(self, f[0]) for f in _CConfig._fields_])
+
+    def validate(self) -> None:
+        c = self._c()
+        check(_validate(C.byref(c)))
+
+
+_NP = {"f32": np.float32, "f64": np.float64}
+
+
+class Hypersonic2D:
+    """One solver handle on one GPU (`y_begin/h_local` select a slab of rows for multi-GPU)."""
+
+    def __init__(self, cfg: SimConfig, dtype: str = "f32", device: int = 0, y_begin: int = 0,
+                 h_local: int | None = None, stream: int | None = None):
+        if dtype not in _NP:
+            raise ValueError("dtype must be 'f32' or 'f64'")
+        self.cfg = cfg
+        self.dtype = dtype
+        self.np_dtype = _NP[dtype]
+        self.h_local = cfg.H if h_local is None else h_local
+        self.y_begin = y_begin
+        self.device = device
+        self._handle = _h()
+        cc = cfg._c()
+        check(_create(C.byref(cc), cfg.W, cfg.H, 0 if dtype == "f32" else 1, device, y_begin,
+                      self.h_local, C.c_void_p(stream or 0), C.byref(self._handle)))
+
+    def init(self):
+        check(_init(self._handle))
+        return self
+
+    def upload(self, planes, mask=None):
+        arrs = [np.ascontiguousarray(p, self.np_dtype).reshape(self.h_local, self.cfg.W)
+                for p in planes]
+        ptrs = (C.c_void_p * 4)(*[a.ctypes.data for a in arrs])
+        m = None
+        if mask is not None:
+            m = np.ascontiguousarray(mask, np.uint8).reshape(self.h_local, self.cfg.W)
+        check(_upload(self._handle, ptrs, C.c_void_p(m.ctypes.data if m is not None else 0)))
+        return self
+
+    def step(self, nsteps: int = 1):
+        check(_step(self._handle, nsteps))
+        return self
+
+    def clock(self):
+        """(sim_t, dt of the last step)."""
+        t, dt = C.c_double(), C.c_double()
+        check(_clock(self._handle, C.byref(t), C.byref(dt)))
+        return float(t.value), float(dt.value)
+
+    def download(self):
+        """([rho, mx, my, E], mask) as (h_local, W) arrays in the handle's dtype."""
+        arrs = [np.empty((self.h_local, self.cfg.W), self.np_dtype) for _ in range(4)]
+        mask = np.empty((self.h_local, self.cfg.W), np.uint8)
+        ptrs = (C.c_void_p * 4)(*[a.ctypes.data for a in arrs])
+        check(_download(self._handle, ptrs, C.c_void_p(mask.ctypes.data)))
+        return arrs, mask
+
+    def sync(self):
+        check(_sync(self._handle))
+
+    def device_state(self):
+        """(planes_ptr, mask_ptr, maxspeed_ptr) raw device addresses for the slab exchange."""
+        p, m, s = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(_devstate(self._handle, C.byref(p), C.byref(m), C.byref(s)))
+        return p.value, m.value, s.value
+
+    def set_seg_rows(self, rows: int):
+        check(_set_seg(self._handle, rows))
+        return self
+
+    @property
+    def steps_done(self) -> int:
+        return int(_steps_done(self._handle))
+
+    @property
+    def launch_count(self) -> int:
+        return int(_launches(self._handle))
+
+    def last_step_ms(self) -> float:
+        ms = C.c_float()
+        check(_last_ms(self._handle, C.byref(ms)))
+        return float(ms.value)
+
+    def close(self):
+        if self._handle:
+            _destroy(self._handle)
+            self._handle = _h()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -75,6 +75,55 @@ long long tau_gs_launch_count(tau_gs *h);
 int tau_gs_last_step_ms(tau_gs *h, float *ms);
 int tau_gs_destroy(tau_gs *h);
 
+
+/* ------------------------------------------------------------------------------------------ */
+/* 2-D hypersonic compressible flow (reference: tau_hypersonic_cuda.cu)                         */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct tau_hyp2d tau_hyp2d;
+
+/* mirrors `struct SimConfig` tau_hypersonic_cuda.cu:37-50 */
+typedef struct tau_hyp2d_config {
+  double gamma, cfl, visc_nu, visc_rho, visc_e, inflow_mach;
+  double geom_x0, geom_cy, geom_Rb, geom_Rn, geom_theta;
+  int steps_per_frame;
+} tau_hyp2d_config;
+
+#define TAU_F32 0
+#define TAU_F64 1
+
+/* default_config() :1394-1409; the reference derives the geometry from its compile-time H, here
+ * from the runtime H (W, H are runtime: the reference's `#define W 8192 / H 1024` :28-29 become
+ * arguments). */
+void tau_hyp2d_default_config(tau_hyp2d_config *c, int W, int H);
+/* the validation block of parse_args() :1545-1637 (same messages, returned not printed) */
+int tau_hyp2d_validate_config(const tau_hyp2d_config *c);
+/* replaces main()'s allocation block :1748-1811.  dtype: TAU_F32 (BASELINE "fp32") or TAU_F64
+ * (the reference's arithmetic).  Slab: rows [y_begin, y_begin+h_local), 2 ghost rows each side. */
+int tau_hyp2d_create(const tau_hyp2d_config *c, int W, int H, int dtype, int device, int y_begin,
+                     int h_local, void *stream, tau_hyp2d **out);
+/* k_init :740-770 (+ the first max-wavespeed scan) */
+int tau_hyp2d_init(tau_hyp2d *h);
+/* inject caller state: 4 host planes rho,mx,my,E of h_local x W elements in the handle's dtype and
+ * (optional) the body mask */
+int tau_hyp2d_upload(tau_hyp2d *h, const void *const planes[4], const uint8_t *mask);
+/* THE hot path: nsteps x the loop body :1833-1889 (inflow column, max wavespeed, dt, predict,
+ * x/y fluxes, update+diffusion, swap, sim_t += dt) as one fused kernel per step, dt on device. */
+int tau_hyp2d_step(tau_hyp2d *h, int nsteps);
+/* sim_t (:1888) and the dt of the most recent step; synchronises */
+int tau_hyp2d_clock(tau_hyp2d *h, double *sim_t, double *dt_last);
+int tau_hyp2d_download(tau_hyp2d *h, void *const planes[4], uint8_t *mask);
+int tau_hyp2d_sync(tau_hyp2d *h);
+/* slab plumbing: device pointers of the current planes (4 contiguous planes of (h_local+4) x W,
+ * starting at ghost row -2), the mask (same row layout) and the max-wavespeed scalar the next
+ * step will read (all-reduce it with MAX across ranks before tau_hyp2d_step). */
+int tau_hyp2d_device_state(tau_hyp2d *h, void **planes, uint8_t **mask, double **maxspeed_slot);
+/* rows each warp marches per work item (tuning; --tile-by analogue of :1641-1685) */
+int tau_hyp2d_set_seg_rows(tau_hyp2d *h, int rows);
+long long tau_hyp2d_steps_done(tau_hyp2d *h);
+long long tau_hyp2d_launch_count(tau_hyp2d *h);
+int tau_hyp2d_last_step_ms(tau_hyp2d *h, float *ms);
+int tau_hyp2d_destroy(tau_hyp2d *h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark: Mcell-updates/s of the 2-D hypersonic update path on the
+4096 x 4096 fp32 grid (BASELINE.json configs[1]), with the HBM roofline of the fused step kernel
+and the reference CPU solver timed beside it.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # product arm
+  python bench.py --impl reference [--steps K] [--warmup W]      # reference CPU arm
+  torchrun ... bench.py --gpus N ...                              # one rank per GPU (N > 1)
+
+Definitions
+  step     one solver time step of the whole grid (tau_hypersonic_cuda.cu:1833-1889), i.e. W*H
+           cell-updates.  `value` = W*H*K / t_device, inputs resident in HBM, t from CUDA events on
+           the launching stream, max over ranks.
+  e2e      the same metric through the C-ABI with HOST buffers: every e2e step is one *frame* of
+           the reference's frame loop — upload the 4 state planes from pinned host memory
+           (tau_hyp2d_upload), run `steps_per_frame` solver steps (reference default 2,
+           tau_hypersonic_cuda.cu:1407), download the 4 planes (tau_hyp2d_download) — all inside
+           the timed region (wall clock around synchronous calls).
+  roofline achieved = 33 algorithmic bytes/cell (read 4 fp32 fields + 1 mask byte, write 4 fields;
+           SURVEY.md §8(d)) x W*H / average duration of one hyp2d_step launch (CUDA events over the
+           timed region, in which it is the only kernel) vs the measured HBM copy bandwidth in
+           MEASURED_PEAKS.json.
+  cpu_baseline  the reference's own tau_hypersonic_simd.c (compiled from the reference sources into
+           oracle/_ref with the reference's flags) stepping a 4096 x 256 band of the grid on one
+           host core; `--impl reference` runs one independent replica of it per host core.
+The working set (2 x 268 MB of state) is larger than the 126 MB L2, so no L2 flush is needed
+between timed steps.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GRID_W = 4096
+GRID_H = 4096
+BYTES_PER_CELL = 33           # 4 fields R + 4 fields W (fp32) + 1 mask byte
+CPU_BAND = (4096, 256)        # bounded CPU sample: a 4096 x 256 band (1/16 of the rows)
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def profile_traffic():
+    """dram bytes per hyp2d_step launch from the committed ncu summary (profiles/), if present."""
+    path = os.path.join(ROOT, "profiles", "hyp2d_step_traffic.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                 "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        smax = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) > 8:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own CPU solver from oracle/_ref
+# --------------------------------------------------------------------------------------------
+def _cpu_replica(args):
+    nsteps, warm = args
+    import oracle
+    r = oracle.RefHypCpu(CPU_BAND[0], CPU_BAND[1], simd=True)
+    r.init()
+    if warm:
+        r.steps(warm)
+    return r.steps(nsteps)
+
+
+def cpu_reference(nsteps, warm, procs):
+    """Aggregate Mcell-updates/s of `procs` independent replicas (the solver is single-threaded:
+    tau_hypersonic_simd.c has no OpenMP/pthreads)."""
+    import multiprocessing as mp
+    cells = CPU_BAND[0] * CPU_BAND[1]
+    if procs == 1:
+        secs = [_cpu_replica((nsteps, warm))]
+    else:
+        with mp.get_context("spawn").Pool(procs) as pool:
+            secs = pool.map(_cpu_replica, [(nsteps, warm)] * procs)
+    t = max(secs)
+    return procs * cells * nsteps / t / 1e6, t / nsteps * 1e3
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    val, ms = cpu_reference(a.steps, a.warmup, cores)
+    sample = (f"{a.steps} x step_physics() of tau_hypersonic_simd.c (gcc -O3 -mavx2 -mfma) on a "
+              f"{CPU_BAND[0]}x{CPU_BAND[1]} band, one independent replica per host core")
+    print(json.dumps({
+        "impl": "reference", "metric": "Mcell-updates/s", "value": val, "unit": "Mcell-updates/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "tau_hypersonic 4096x4096 (CPU reference steps a 4096x256 band per "
+                               "replica; solver is fp64 and single-threaded)"},
+        "cpu_baseline": {"value": val, "unit": "Mcell-updates/s", "cores": cores,
+                         "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------------------------
+# product arm
+# --------------------------------------------------------------------------------------------
+def run_product(a):
+    import numpy as np
+    import torch
+
+    from fluid_sims_b200 import slab
+    from fluid_sims_b200.hypersonic2d import HALO, Hypersonic2D, SimConfig
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    dev = local if world > 1 else 0
+
+    W = GRID_W
+    H = GRID_H * world if a.scaling == "weak" else GRID_H
+    cfg = SimConfig.default(W, H)
+    y0, hl = slab.partition_rows(H, world)[rank]
+    # an explicit side stream: torch's legacy default stream has handle 0, which the C-ABI reads as
+    # "create your own stream" — events recorded on it would not see the kernels
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+    sim = Hypersonic2D(cfg, dtype=a.dtype, device=dev, y_begin=y0, h_local=hl, stream=stream)
+    if a.seg_rows:
+        sim.set_seg_rows(a.seg_rows)
+    sim.init()
+    tdt = torch.float32 if a.dtype == "f32" else torch.float64
+
+    views = {}
+
+    def state_views():
+        pp, mp, sp = sim.device_state()
+        if pp not in views:
+            views[pp] = slab.wrap_plane(pp, (4, hl + 2 * HALO, W), tdt, dev)
+        if sp not in views:
+            views[sp] = slab.wrap_plane(sp, (1,), torch.float64, dev)
+        return views[pp], views[sp], mp
+
+    def advance(n):
+        if world == 1:
+            sim.step(n)
+            return
+        for _ in range(n):
+            planes, speed, _ = state_views()
+            slab.exchange_halos([planes], HALO, periodic=False, dim=1)
+            dist.all_reduce(speed, op=dist.ReduceOp.MAX)
+            sim.step(1)
+
+    if world > 1:   # the static body mask needs its ghost rows once
+        _, _, mp = state_views()
+        mview = slab.wrap_plane(mp, (hl + 2 * HALO, W), torch.uint8, dev)
+        slab.exchange_halos([mview], HALO, periodic=False, dim=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # develop the flow first (uniform inflow under-exercises the limiter/HLLC branches)
+    advance(a.develop)
+    advance(a.warmup)
+    barrier()
+
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+    launches0 = sim.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    advance(a.steps)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = sim.launch_count - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    cells = W * H
+    value = cells * a.steps / (ms * 1e-3) / 1e6
+    kernel_ms = ms / a.steps
+    peak, peak_src = measured_peak()
+    # roofline of the dominant kernel (hyp2d_step): per launch it updates this rank's slab
+    ach = BYTES_PER_CELL * (W * hl) / (kernel_ms * 1e-3) / 1e9
+    bpc = BYTES_PER_CELL if a.dtype == "f32" else 65
+    if a.dtype != "f32":
+        ach = bpc * (W * hl) / (kernel_ms * 1e-3) / 1e9
+
+    # ---- e2e: frames through the C-ABI with host buffers -------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        np_dt = np.float32 if a.dtype == "f32" else np.float64
+        host_in = [torch.empty((hl, W), dtype=tdt).pin_memory() for _ in range(4)]
+        planes, _ = sim.download()
+        for t_, p_ in zip(host_in, planes):
+            t_.numpy()[...] = p_
+        del planes
+        import ctypes as C
+        from fluid_sims_b200 import hypersonic2d as h2
+        host_out = [torch.empty((hl, W), dtype=tdt).pin_memory() for _ in range(4)]
+        in_ptrs = (C.c_void_p * 4)(*[t_.data_ptr() for t_ in host_in])
+        out_ptrs = (C.c_void_p * 4)(*[t_.data_ptr() for t_ in host_out])
+
+        def frame():
+            h2.check(h2._upload(sim._handle, in_ptrs, C.c_void_p(0)))
+            if world > 1:
+                advance(a.steps_per_frame)
+            else:
+                sim.step(a.steps_per_frame)
+            h2.check(h2._download(sim._handle, out_ptrs, C.c_void_p(0)))
+
+        for _ in range(3):
+            frame()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(a.e2e_frames):
+            frame()
+        barrier()
+        dt_wall = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt_wall], device=f"cuda:{dev}", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_wall = float(t.item())
+        nbytes = 4 * hl * W * np.dtype(np_dt).itemsize
+        e2e = {"value": cells * a.steps_per_frame * a.e2e_frames / dt_wall / 1e6,
+               "unit": "Mcell-updates/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+               "steps_per_frame": a.steps_per_frame, "frames": a.e2e_frames,
+               "ms_per_frame": dt_wall / a.e2e_frames * 1e3}
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        v, _ = cpu_reference(a.cpu_steps, 1, 1)
+        cpu = {"value": v, "unit": "Mcell-updates/s", "cores": 1, "kind": "reference",
+               "sample": (f"{a.cpu_steps} x step_physics() of tau_hypersonic_simd.c (gcc -O3 -mavx2 "
+                          f"-mfma, oracle/_ref) on a {CPU_BAND[0]}x{CPU_BAND[1]} band of the grid, "
+                          f"1 thread (the solver is single-threaded); host has {os.cpu_count()} cores")}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": "Mcell-updates/s", "value": value, "unit": "Mcell-updates/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+            "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
+            "dtype": a.dtype, "data": "synthetic",
+            "config": {"workload": f"tau_hypersonic_cuda {W}x{H} {a.dtype}: k_init state developed "
+                                   f"for {a.develop} steps, then timed",
+                       "grid": [W, H], "slab_rows_per_gpu": hl, "parallelism": f"y-slab x{world}",
+                       "cache": "state (2 x 268 MB) larger than L2 (126 MB): no flush needed",
+                       "seg_rows": a.seg_rows or 64},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": profile_traffic(),
+                         "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
+                         "algorithmic_bytes_per_cell": bpc, "kernel": "hyp2d_step",
+                         "kernel_ms": kernel_ms,
+                         "note": "kernel is FP32-issue bound (~1e3 instr/cell), see DESIGN.md"},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--develop", type=int, default=1500,
+                    help="untimed steps run first so that the bow shock exists")
+    ap.add_argument("--steps-per-frame", type=int, default=2)
+    ap.add_argument("--e2e-frames", type=int, default=10)
+    ap.add_argument("--cpu-steps", type=int, default=12)
+    ap.add_argument("--seg-rows", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    a = ap.parse_args()
+    if a.warmup < 3 and a.impl == "b200":
+        a.warmup = 3
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if a.gpus > 1 and world == 1:
+            # convenience: re-launch under torchrun, one rank per GPU
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                   f"--nproc-per-node={a.gpus}", "--master-addr", "127.0.0.1", "--master-port",
+                   os.environ.get("MASTER_PORT", "29517"), os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+        run_product(a)
+
+
+if __name__ == "__main__":
+    main()

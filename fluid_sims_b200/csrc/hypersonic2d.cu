@@ -71,12 +71,27 @@ template <typename R> __device__ __forceinline__ R rmax(R a, R b) { return a > b
 template <typename R> __device__ __forceinline__ R rmin(R a, R b) { return a < b ? a : b; }  // :134
 template <typename R> __device__ __forceinline__ R rabs(R a) { return a < R(0) ? -a : a; }   // :137
 
+// reciprocal / sound speed: IEEE in fp64 (parity with the fp64 reference to ~1e-13), single
+// MUFU approximations (<= 1 ulp / 2 ulp) in fp32 where they are below the fp32 noise floor.
+__device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+__device__ __forceinline__ float rcp(float x) {
+  float r;
+  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ double sqrt_pos(double x) { return sqrt(x); }
+__device__ __forceinline__ float sqrt_pos(float x) {
+  float r;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // tau_hypersonic_cuda.cu:143-159
 template <typename R>
 __device__ __forceinline__ Prim4<R> cons_to_prim(const Params<R> &P, Cons4<R> c) {
   Prim4<R> p;
   R rho = rmax(c.rho, P.eps_rho);
-  R inv = R(1) / rho;
+  R inv = rcp(rho);
   R u = c.mx * inv;
   R v = c.my * inv;
   R kin = R(0.5) * rho * (u * u + v * v);
@@ -96,51 +111,62 @@ __device__ __forceinline__ Cons4<R> prim_to_cons(const Params<R> &P, Prim4<R> p)
   c.rho = rho;
   c.mx = rho * p.u;
   c.my = rho * p.v;
-  c.E = pr / P.gm1 + R(0.5) * rho * (p.u * p.u + p.v * p.v);
+  c.E = pr * P.inv_gm1 + R(0.5) * rho * (p.u * p.u + p.v * p.v);
   return c;
 }
 // :172-174
 template <typename R>
 __device__ __forceinline__ R sound_speed(const Params<R> &P, Prim4<R> p) {
-  return sqrt(P.gamma * rmax(p.p, P.eps_p) / rmax(p.rho, P.eps_rho));
+  return sqrt_pos(P.gamma * rmax(p.p, P.eps_p) * rcp(rmax(p.rho, P.eps_rho)));
 }
-// flux_axis<AX>(Cons) :194-203
-template <int AX, typename R>
-__device__ __forceinline__ Cons4<R> flux_axis(const Params<R> &P, Cons4<R> c) {
-  Prim4<R> p = cons_to_prim(P, c);
-  R un = AX == 0 ? p.u : p.v;
-  Cons4<R> f;
-  f.rho = AX == 0 ? c.mx : c.my;
-  f.mx = AX == 0 ? (c.mx * un + p.p) : (c.mx * un);
-  f.my = AX == 0 ? (c.my * un) : (c.my * un + p.p);
-  f.E = (c.E + p.p) * un;
-  return f;
+// A face state: primitives plus total energy (what the Riemann solver consumes).  The reference
+// round-trips every face state prim -> cons -> prim (prim_to_cons :161, then cons_to_prim again
+// inside flux_axis :195 and hllc_axis :520-521); algebraically those are identities, so the
+// fused kernel carries (rho,u,v,p,E) once instead.  Differences are at round-off level.
+template <typename R> struct Face { R rho, u, v, p, E; };
+
+// mc_limiter :217-228.  With dl*dr > 0 the nested minmods of the reference reduce to "the
+// argument of smallest magnitude among dl, dr, dc" (2dl and 2dr can never be the smallest), and to
+// 0 otherwise; written branch-free.  Bit-identical to the reference formulation.
+template <typename R> __device__ __forceinline__ R mc_limiter(R dl, R dc, R dr) {
+  const R m = fmin(fmin(fabs(dl), fabs(dr)), fabs(dc));
+  return (dl * dr > R(0)) ? copysign(m, dl) : R(0);
 }
-// :217-228
+// :217-221, kept for the known-answer tests
 template <typename R> __device__ __forceinline__ R minmod(R a, R b) {
   if (a * b <= R(0)) return R(0);
   return (rabs(a) < rabs(b)) ? a : b;
 }
-template <typename R> __device__ __forceinline__ R mc_limiter(R dl, R dc, R dr) {
-  R mm1 = minmod(dl, dr);
-  R mm2 = minmod(dc, R(2) * dl);
-  R mm3 = minmod(dc, R(2) * dr);
-  return minmod(mm1, minmod(mm2, mm3));
-}
-// wall_ghost_prim :262-264 followed by prim_to_cons
+// wall_ghost_prim :262-264
 template <typename R>
 __device__ __forceinline__ Prim4<R> ghost_prim(Prim4<R> in) {
   return Prim4<R>{in.rho, -in.u, -in.v, in.p};
 }
+// prim_to_cons(wall_ghost_prim(centre)) :286-287 as a conserved state (diffusion taps)
 template <typename R>
-__device__ __forceinline__ Cons4<R> ghost_cons(const Params<R> &P, Prim4<R> centre) {
-  return prim_to_cons(P, ghost_prim(centre));
+__device__ __forceinline__ Cons4<R> ghost_cons(const Params<R> &P, Prim4<R> q) {
+  const R rho = rmax(q.rho, P.eps_rho), pr = rmax(q.p, P.eps_p);
+  return Cons4<R>{rho, -(rho * q.u), -(rho * q.v),
+                  pr * P.inv_gm1 + R(0.5) * rho * (q.u * q.u + q.v * q.v)};
+}
+// ... and as a face state (Riemann-solver input)
+template <typename R>
+__device__ __forceinline__ Face<R> ghost_face(const Params<R> &P, Prim4<R> q) {
+  const R rho = rmax(q.rho, P.eps_rho), pr = rmax(q.p, P.eps_p);
+  return Face<R>{rho, -q.u, -q.v, q.p,
+                 pr * P.inv_gm1 + R(0.5) * rho * (q.u * q.u + q.v * q.v)};
+}
+// an unpredicted conserved state used directly as a face state (inflow, outflow copy, y-clamp)
+template <typename R>
+__device__ __forceinline__ Face<R> face_from_cons(const Params<R> &P, Cons4<R> c) {
+  const Prim4<R> q = cons_to_prim(P, c);
+  return Face<R>{q.rho, q.u, q.v, q.p, c.E};
 }
 
-// enforce_positive_faces :373-398
+// enforce_positive_faces :373-398 (rarely taken: only when a limited face state is non-positive)
 template <typename R>
-__device__ __forceinline__ void enforce_positive_faces(const Params<R> &P, Prim4<R> &qm,
-                                                       const Prim4<R> &qc, Prim4<R> &qp) {
+__device__ __noinline__ void enforce_positive_faces(const Params<R> &P, Prim4<R> &qm,
+                                                    const Prim4<R> &qc, Prim4<R> &qp) {
   for (int it = 0; it < 8; it++) {
     bool bad = (qm.rho <= P.eps_rho || qp.rho <= P.eps_rho) || (qm.p <= P.eps_p || qp.p <= P.eps_p);
     if (!bad) return;
@@ -159,125 +185,125 @@ __device__ __forceinline__ void enforce_positive_faces(const Params<R> &P, Prim4
   qp.p = rmax(qp.p, P.eps_p);
 }
 
-// half_step_predict_axis :442-455 (+ the caller's extra floors :936-939)
-template <typename R>
-__device__ __forceinline__ Cons4<R> half_step_predict(const Params<R> &P, Prim4<R> q, Cons4<R> dF,
-                                                      R half_dt) {
-  Cons4<R> c = prim_to_cons(P, q);
-  c.rho -= half_dt * dF.rho;
-  c.mx -= half_dt * dF.mx;
-  c.my -= half_dt * dF.my;
-  c.E -= half_dt * dF.E;
-  Prim4<R> o = cons_to_prim(P, c);
-  o.rho = rmax(o.rho, P.eps_rho);
-  o.p = rmax(o.p, P.eps_p);
-  return prim_to_cons(P, o);
-}
-
-// reconstruct_limited_faces :400-425 + the predictor block of k_predict_face_states :923-961.
-// Returns the predicted (conserved) states on the low ("L"/"B") and high ("R"/"T") side of cell qc.
+// Limited reconstruction (reconstruct_limited_faces :400-425) + Hancock half-step predictor
+// (k_predict_face_states :923-961, half_step_predict_axis :442-455) for one axis of one cell.
+// lo/hi = predicted states on the cell's low ("L"/"B") and high ("R"/"T") face.
 template <int AX, typename R>
-__device__ __forceinline__ void reconstruct_predict(const Params<R> &P, Prim4<R> qm, Prim4<R> qc,
-                                                    Prim4<R> qp, R half_dt, Cons4<R> &lo,
-                                                    Cons4<R> &hi) {
-  R s_rho = mc_limiter(qc.rho - qm.rho, R(0.5) * (qp.rho - qm.rho), qp.rho - qc.rho);
-  R s_u = mc_limiter(qc.u - qm.u, R(0.5) * (qp.u - qm.u), qp.u - qc.u);
-  R s_v = mc_limiter(qc.v - qm.v, R(0.5) * (qp.v - qm.v), qp.v - qc.v);
-  R s_p = mc_limiter(qc.p - qm.p, R(0.5) * (qp.p - qm.p), qp.p - qc.p);
+__device__ __forceinline__ void reconstruct_predict(const Params<R> &P, const Prim4<R> &qm,
+                                                    const Prim4<R> &qc, const Prim4<R> &qp,
+                                                    R half_dt, Face<R> &lo, Face<R> &hi) {
+  const R s_rho = mc_limiter(qc.rho - qm.rho, R(0.5) * (qp.rho - qm.rho), qp.rho - qc.rho);
+  const R s_u = mc_limiter(qc.u - qm.u, R(0.5) * (qp.u - qm.u), qp.u - qc.u);
+  const R s_v = mc_limiter(qc.v - qm.v, R(0.5) * (qp.v - qm.v), qp.v - qc.v);
+  const R s_p = mc_limiter(qc.p - qm.p, R(0.5) * (qp.p - qm.p), qp.p - qc.p);
   Prim4<R> qL{qc.rho - R(0.5) * s_rho, qc.u - R(0.5) * s_u, qc.v - R(0.5) * s_v,
               qc.p - R(0.5) * s_p};
   Prim4<R> qR{qc.rho + R(0.5) * s_rho, qc.u + R(0.5) * s_u, qc.v + R(0.5) * s_v,
               qc.p + R(0.5) * s_p};
-  enforce_positive_faces(P, qL, qc, qR);
-  Cons4<R> FL = flux_axis<AX>(P, prim_to_cons(P, qL));
-  Cons4<R> FR = flux_axis<AX>(P, prim_to_cons(P, qR));
-  Cons4<R> dF{FR.rho - FL.rho, FR.mx - FL.mx, FR.my - FL.my, FR.E - FL.E};
-  lo = half_step_predict(P, qL, dF, half_dt);
-  hi = half_step_predict(P, qR, dF, half_dt);
+  if ((qL.rho <= P.eps_rho || qR.rho <= P.eps_rho) || (qL.p <= P.eps_p || qR.p <= P.eps_p))
+    enforce_positive_faces(P, qL, qc, qR);
+  // conserved variables and physical flux of both face states (flux_axis :194-203)
+  const R mxL = qL.rho * qL.u, myL = qL.rho * qL.v;
+  const R mxR = qR.rho * qR.u, myR = qR.rho * qR.v;
+  const R EL = qL.p * P.inv_gm1 + R(0.5) * qL.rho * (qL.u * qL.u + qL.v * qL.v);
+  const R ER = qR.p * P.inv_gm1 + R(0.5) * qR.rho * (qR.u * qR.u + qR.v * qR.v);
+  const R unL = AX == 0 ? qL.u : qL.v, unR = AX == 0 ? qR.u : qR.v;
+  const R d_rho = (AX == 0 ? mxR : myR) - (AX == 0 ? mxL : myL);
+  const R d_mx = (mxR * unR + (AX == 0 ? qR.p : R(0))) - (mxL * unL + (AX == 0 ? qL.p : R(0)));
+  const R d_my = (myR * unR + (AX == 1 ? qR.p : R(0))) - (myL * unL + (AX == 1 ? qL.p : R(0)));
+  const R d_E = (ER + qR.p) * unR - (EL + qL.p) * unL;
+  // half-step predictor on each face state, back to primitives with the reference's floors
+  {
+    const R rho = rmax(qL.rho - half_dt * d_rho, P.eps_rho);
+    const R inv = rcp(rho);
+    const R u = (mxL - half_dt * d_mx) * inv, v = (myL - half_dt * d_my) * inv;
+    const R kin = R(0.5) * rho * (u * u + v * v);
+    const R pr = rmax(P.gm1 * rmax((EL - half_dt * d_E) - kin, P.eps_p), P.eps_p);
+    lo = Face<R>{rho, u, v, pr, pr * P.inv_gm1 + kin};
+  }
+  {
+    const R rho = rmax(qR.rho - half_dt * d_rho, P.eps_rho);
+    const R inv = rcp(rho);
+    const R u = (mxR - half_dt * d_mx) * inv, v = (myR - half_dt * d_my) * inv;
+    const R kin = R(0.5) * rho * (u * u + v * v);
+    const R pr = rmax(P.gm1 * rmax((ER - half_dt * d_E) - kin, P.eps_p), P.eps_p);
+    hi = Face<R>{rho, u, v, pr, pr * P.inv_gm1 + kin};
+  }
 }
 
-// hlle_axis :483-509
 template <int AX, typename R>
-__device__ __noinline__ Cons4<R> hlle_axis(const Params<R> &P, Cons4<R> UL, Cons4<R> UR) {
-  Prim4<R> L = cons_to_prim(P, UL), Rr = cons_to_prim(P, UR);
-  R uL = AX == 0 ? L.u : L.v, uR = AX == 0 ? Rr.u : Rr.v;
-  R aL = sound_speed(P, L), aR = sound_speed(P, Rr);
-  R SL = rmin(uL - aL, uR - aR), SR = rmax(uL + aL, uR + aR);
-  Cons4<R> FL = flux_axis<AX>(P, UL), FR = flux_axis<AX>(P, UR);
+__device__ __forceinline__ Cons4<R> phys_flux(const Face<R> &f) {
+  const R un = AX == 0 ? f.u : f.v;
+  const R m = f.rho * un;
+  return Cons4<R>{m, m * f.u + (AX == 0 ? f.p : R(0)), m * f.v + (AX == 1 ? f.p : R(0)),
+                  (f.E + f.p) * un};
+}
+
+// hlle_axis :483-509 — only reached through the guarded fall-backs of HLLC
+template <int AX, typename R>
+__device__ __noinline__ Cons4<R> hlle_flux(const Params<R> &P, Face<R> L, Face<R> Rr, R SL, R SR) {
+  const Cons4<R> FL = phys_flux<AX>(L), FR = phys_flux<AX>(Rr);
   if (SL >= R(0)) return FL;
   if (SR <= R(0)) return FR;
-  R denom = SR - SL;
+  const R denom = SR - SL;
   if (rabs(denom) < R(1e-14))
     return Cons4<R>{R(0.5) * (FL.rho + FR.rho), R(0.5) * (FL.mx + FR.mx), R(0.5) * (FL.my + FR.my),
                     R(0.5) * (FL.E + FR.E)};
-  R inv = R(1) / denom, ss = SL * SR;
+  const R inv = R(1) / denom, ss = SL * SR;
   Cons4<R> o;
-  o.rho = inv * ((SR * FL.rho + (-SL) * FR.rho) + ss * (UR.rho - UL.rho));
-  o.mx = inv * ((SR * FL.mx + (-SL) * FR.mx) + ss * (UR.mx - UL.mx));
-  o.my = inv * ((SR * FL.my + (-SL) * FR.my) + ss * (UR.my - UL.my));
-  o.E = inv * ((SR * FL.E + (-SL) * FR.E) + ss * (UR.E - UL.E));
+  o.rho = inv * ((SR * FL.rho + (-SL) * FR.rho) + ss * (Rr.rho - L.rho));
+  o.mx = inv * ((SR * FL.mx + (-SL) * FR.mx) + ss * (Rr.rho * Rr.u - L.rho * L.u));
+  o.my = inv * ((SR * FL.my + (-SL) * FR.my) + ss * (Rr.rho * Rr.v - L.rho * L.v));
+  o.E = inv * ((SR * FL.E + (-SL) * FR.E) + ss * (Rr.E - L.E));
   return o;
 }
 
-// hllc_axis :519-606
+// hllc_axis :519-606: Davis wave speeds, Toro contact speed, the reference's guarded fall-backs to
+// HLLE.  Only the star state on the upwind side of the contact is evaluated; the positivity
+// guards of BOTH sides (:568-571) are kept as sign tests.
 template <int AX, typename R>
-__device__ __forceinline__ Cons4<R> hllc_axis(const Params<R> &P, Cons4<R> UL, Cons4<R> UR) {
-  Prim4<R> L = cons_to_prim(P, UL), Rr = cons_to_prim(P, UR);
-  R unL = AX == 0 ? L.u : L.v, unR = AX == 0 ? Rr.u : Rr.v;
-  R utL = AX == 0 ? L.v : L.u, utR = AX == 0 ? Rr.v : Rr.u;
-  R aL = sound_speed(P, L), aR = sound_speed(P, Rr);
-  R SL = rmin(unL - aL, unR - aR), SR = rmax(unL + aL, unR + aR);
-  Cons4<R> FL = flux_axis<AX>(P, UL), FR = flux_axis<AX>(P, UR);
-  if (SL >= R(0)) return FL;
-  if (SR <= R(0)) return FR;
-  R rhoL = L.rho, rhoR = Rr.rho, pL = L.p, pR = Rr.p;
-  R num = pR - pL + rhoL * unL * (SL - unL) - rhoR * unR * (SR - unR);
-  R den = rhoL * (SL - unL) - rhoR * (SR - unR);
-  bool fallback = (rabs(den) < R(1e-14)) || !isfinite(num) || !isfinite(den);
-  R SM = R(0), pStar = R(0), dLS = R(0), dRS = R(0), rhoStarL = R(0), rhoStarR = R(0);
-  R EStarL = R(0), EStarR = R(0);
-  if (!fallback) {
-    SM = num / den;
-    fallback = !isfinite(SM);
-  }
-  if (!fallback) {
-    pStar = rmax(pL + rhoL * (SL - unL) * (SM - unL), P.eps_p);
-    dLS = SL - SM;
-    dRS = SR - SM;
-    fallback = (rabs(dLS) < R(1e-14)) || (rabs(dRS) < R(1e-14));
-  }
-  if (!fallback) {
-    rhoStarL = rhoL * (SL - unL) / dLS;
-    rhoStarR = rhoR * (SR - unR) / dRS;
-    fallback = !(rhoStarL > R(0)) || !(rhoStarR > R(0)) || !isfinite(rhoStarL) ||
-               !isfinite(rhoStarR);
-  }
-  if (!fallback) {
-    EStarL = ((SL - unL) * UL.E - pL * unL + pStar * SM) / dLS;
-    fallback = !isfinite(EStarL);
-  }
-  if (!fallback) {
-    EStarR = ((SR - unR) * UR.E - pR * unR + pStar * SM) / dRS;
-    fallback = !isfinite(EStarR);
-  }
-  if (fallback) return hlle_axis<AX>(P, UL, UR);
+__device__ __forceinline__ Cons4<R> hllc_flux(const Params<R> &P, const Face<R> &L,
+                                              const Face<R> &Rr) {
+  const R unL = AX == 0 ? L.u : L.v, unR = AX == 0 ? Rr.u : Rr.v;
+  const R aL = sqrt_pos(P.gamma * L.p * rcp(L.rho)), aR = sqrt_pos(P.gamma * Rr.p * rcp(Rr.rho));
+  const R SL = rmin(unL - aL, unR - aR), SR = rmax(unL + aL, unR + aR);
+  // supersonic shortcut (:537-540); warp-uniform so whole free-stream strips skip the star state
+  if (__all_sync(0xffffffffu, SL >= R(0))) return phys_flux<AX>(L);
+  const R qL = L.rho * (SL - unL), qR = Rr.rho * (SR - unR);
+  const R num = Rr.p - L.p + qL * unL - qR * unR;
+  const R den = qL - qR;
+  const R SM = num * rcp(den);
+  const R dLS = SL - SM, dRS = SR - SM;
+  const bool left = (SL >= R(0)) || (!(SR <= R(0)) && SM >= R(0));
+  const Face<R> &K = left ? L : Rr;
+  const R SK = left ? SL : SR, unK = left ? unL : unR, qK = left ? qL : qR;
+  const R dKS = left ? dLS : dRS;
+  const Cons4<R> FK = phys_flux<AX>(K);
+  const R pStar = rmax(L.p + qL * (SM - unL), P.eps_p);
+  const R invd = rcp(dKS);
+  const R rhoStar = qK * invd;
+  const R EStar = ((SK - unK) * K.E - K.p * unK + pStar * SM) * invd;
+  const bool fallback = (rabs(den) < R(1e-14)) || !isfinite(num) || !isfinite(den) ||
+                        !isfinite(SM) || (rabs(dLS) < R(1e-14)) || (rabs(dRS) < R(1e-14)) ||
+                        !(qL * dLS > R(0)) || !(qR * dRS > R(0)) || !isfinite(rhoStar) ||
+                        !isfinite(EStar);
+  const bool supersonic = (SL >= R(0)) || (SR <= R(0));
+  if (!supersonic && fallback) return hlle_flux<AX>(P, L, Rr, SL, SR);
+  if (supersonic) return FK;
+  const R sn = rhoStar * SM, st = rhoStar * (AX == 0 ? K.v : K.u);
   Cons4<R> F;
-  if (SM >= R(0)) {
-    R sn = rhoStarL * SM, st = rhoStarL * utL;
-    F.rho = FL.rho + SL * (rhoStarL - UL.rho);
-    F.mx = FL.mx + SL * ((AX == 0 ? sn : st) - UL.mx);
-    F.my = FL.my + SL * ((AX == 0 ? st : sn) - UL.my);
-    F.E = FL.E + SL * (EStarL - UL.E);
-  } else {
-    R sn = rhoStarR * SM, st = rhoStarR * utR;
-    F.rho = FR.rho + SR * (rhoStarR - UR.rho);
-    F.mx = FR.mx + SR * ((AX == 0 ? sn : st) - UR.mx);
-    F.my = FR.my + SR * ((AX == 0 ? st : sn) - UR.my);
-    F.E = FR.E + SR * (EStarR - UR.E);
-  }
+  F.rho = FK.rho + SK * (rhoStar - K.rho);
+  F.mx = FK.mx + SK * ((AX == 0 ? sn : st) - K.rho * K.u);
+  F.my = FK.my + SK * ((AX == 0 ? st : sn) - K.rho * K.v);
+  F.E = FK.E + SK * (EStar - K.E);
   return F;
 }
 
+template <typename R> __device__ __forceinline__ Face<R> shfl_down_face(Face<R> f) {
+  return Face<R>{__shfl_down_sync(0xffffffffu, f.rho, 1), __shfl_down_sync(0xffffffffu, f.u, 1),
+                 __shfl_down_sync(0xffffffffu, f.v, 1), __shfl_down_sync(0xffffffffu, f.p, 1),
+                 __shfl_down_sync(0xffffffffu, f.E, 1)};
+}
 template <typename R> __device__ __forceinline__ Prim4<R> shfl_up_prim(Prim4<R> p) {
   return Prim4<R>{__shfl_up_sync(0xffffffffu, p.rho, 1), __shfl_up_sync(0xffffffffu, p.u, 1),
                   __shfl_up_sync(0xffffffffu, p.v, 1), __shfl_up_sync(0xffffffffu, p.p, 1)};
@@ -434,23 +460,21 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
   auto bit = [&](unsigned long long w, int b) -> bool { return (w >> b) & 1ull; };
 
   // y-face flux between the cell below (B) and above (T) — k_compute_yface_flux :998-1030
-  auto yface = [&](bool hasB, bool hasT, bool rinB, bool rinT, const Cons4<R> &yT_B,
-                   const Cons4<R> &yB_T, const Prim4<R> &PB, const Prim4<R> &PT,
+  auto yface = [&](bool hasB, bool hasT, bool rinB, bool rinT, const Face<R> &yT_B,
+                   const Face<R> &yB_T, const Prim4<R> &PB, const Prim4<R> &PT,
                    const Cons4<R> &UB_raw, const Cons4<R> &UT_raw) -> Cons4<R> {
-    Cons4<R> lo, hi;
-    if (hasB && hasT) {
-      lo = yT_B;
-      hi = yB_T;
-    } else if (hasT) {
-      lo = rinB ? ghost_cons(P, PT) : UT_raw;  // neighbor_or_wall(x, yt, 0, -1)
-      hi = yB_T;
-    } else if (hasB) {
-      lo = yT_B;
-      hi = rinT ? ghost_cons(P, PB) : UB_raw;  // neighbor_or_wall(x, yb, 0, +1)
-    } else {
-      return Cons4<R>{R(0), R(0), R(0), R(0)};
+    Face<R> lo = yT_B, hi = yB_T;
+    if (!(hasB && hasT)) {
+      if (hasT) {
+        lo = rinB ? ghost_face(P, PT) : face_from_cons(P, UT_raw);  // neighbor_or_wall(x,yt,0,-1)
+      } else if (hasB) {
+        hi = rinT ? ghost_face(P, PB) : face_from_cons(P, UB_raw);  // neighbor_or_wall(x,yb,0,+1)
+      }
     }
-    return hllc_axis<1>(P, lo, hi);
+    // faces between two non-fluid cells carry no flux (:1024-1027); they are still evaluated on
+    // finite states so that the warp-uniform control flow of hllc_flux stays convergent
+    const Cons4<R> F = hllc_flux<1>(P, lo, hi);
+    return (hasB || hasT) ? F : Cons4<R>{R(0), R(0), R(0), R(0)};
   };
 
   // ------------------------------------------------------------------------------------------
@@ -481,10 +505,11 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
   Cons4<R> U1 = ring.cons(3, c);  // row ys+1
   Prim4<R> P1 = cons_to_prim(P, U1);
 
-  Cons4<R> yT_r, G_bot;
+  Face<R> yT_r;
+  Cons4<R> G_bot;
   {
     // y-reconstruction of cell ys-1 (needs rows ys-2, ys-1, ys) -> its predicted top state
-    Cons4<R> lo_b, hi_b, lo_0, hi_0;
+    Face<R> lo_b, hi_b, lo_0, hi_0;
     Prim4<R> qm = bit(mw_m1, c) ? ghost_prim(Pb) : Pa;
     Prim4<R> qp = bit(mw_p1, c) ? ghost_prim(Pb) : P0;
     reconstruct_predict<1>(P, qm, Pb, qp, half_dt, lo_b, hi_b);
@@ -519,7 +544,7 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
     const Prim4<R> Pr2 = cons_to_prim(P, Ur2);
 
     // -- y: reconstruct cell r+1, flux through face r+1/2 ------------------------------------
-    Cons4<R> yB1, yT1;
+    Face<R> yB1, yT1;
     {
       Prim4<R> qm = bit(mw_c, c) ? ghost_prim(Pr1) : Pr;
       Prim4<R> qp = bit(mw_p2, c) ? ghost_prim(Pr1) : Pr2;
@@ -537,7 +562,7 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
       if (lane == 0) Pl = e;
       else Pq = e;
     }
-    Cons4<R> xL, xR;
+    Face<R> xL, xR;
     {
       Prim4<R> qm = bit(mw_c, c - 1) ? ghost_prim(Pr) : Pl;
       Prim4<R> qp = bit(mw_c, c + 1) ? ghost_prim(Pr) : Pq;
@@ -546,25 +571,21 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
     // flux through this lane's RIGHT face (between columns x and x+1) — k_compute_xface_flux
     Cons4<R> F_right;
     {
-      const Cons4<R> xL_B = shfl_down_cons(xL);
+      const Face<R> xL_B = shfl_down_face(xL);
       const bool inA = (x >= 0) && (x < W), inB = (x + 1 >= 0) && (x + 1 < W);
       const bool hasA = inA && !m_c, hasB = inB && !bit(mw_c, c + 1);
-      Cons4<R> lo, hi;
-      bool live = true;
-      if (hasA && hasB) {
-        lo = xR;
-        hi = xL_B;
-      } else if (hasB) {
-        lo = inA ? ghost_cons(P, Pq) : Cons4<R>{P.infl_cons[0], P.infl_cons[1], P.infl_cons[2],
-                                                P.infl_cons[3]};
-        hi = xL_B;
-      } else if (hasA) {
-        lo = xR;
-        hi = inB ? ghost_cons(P, Pr) : ring.cons(q, c + 1);  // x+1>=W: raw column W-1
-      } else {
-        live = false;
+      Face<R> lo = xR, hi = xL_B;
+      if (!(hasA && hasB)) {
+        if (hasB) {   // A is the inflow boundary (x<0) or a body cell
+          lo = inA ? ghost_face(P, Pq)
+                   : face_from_cons(P, Cons4<R>{P.infl_cons[0], P.infl_cons[1], P.infl_cons[2],
+                                                P.infl_cons[3]});
+        } else if (hasA) {  // B is beyond the outflow edge (raw column W-1) or a body cell
+          hi = inB ? ghost_face(P, Pr) : face_from_cons(P, ring.cons(q, c + 1));
+        }
       }
-      F_right = live ? hllc_axis<0>(P, lo, hi) : Cons4<R>{R(0), R(0), R(0), R(0)};
+      const Cons4<R> F = hllc_flux<0>(P, lo, hi);
+      F_right = (hasA || hasB) ? F : Cons4<R>{R(0), R(0), R(0), R(0)};
     }
     const Cons4<R> F_left = shfl_up_cons(F_right);
 

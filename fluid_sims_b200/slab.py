@@ -51,46 +51,51 @@ def wrap_plane(ptr: int, shape, dtype: torch.dtype, device: int | None = None) -
     return torch.as_tensor(_DevArray(ptr, shape, _TYPESTR[dtype]), device=dev)
 
 
-def exchange_halos(planes: Sequence[torch.Tensor], halo: int, periodic: bool,
-                   group=None) -> None:
+def exchange_halos(planes: Sequence[torch.Tensor], halo: int, periodic: bool, group=None,
+                   dim: int = 0) -> None:
     """Fill the ghost rows of every plane from the neighbouring ranks.
 
-    planes: tensors of shape (ny_local + 2*halo, ...) — dimension 0 is the decomposed one.
+    planes: tensors whose dimension `dim` is the decomposed one, of extent ny_local + 2*halo.
     Rows [halo, 2*halo) go up (to rank-1's bottom ghosts), rows [-2*halo, -halo) go down (to
-    rank+1's top ghosts).  Non-periodic: rank 0 has no upper neighbour, the last rank no lower one.
+    rank+1's top ghosts).  Non-periodic: rank 0 has no upper neighbour, the last rank no lower one
+    (their outer ghosts stay whatever the solver's boundary condition put there).
     """
-    rank = dist.get_rank(group)
-    world = dist.get_world_size(group)
-    up = rank - 1 if rank > 0 else (world - 1 if periodic else None)
-    dn = rank + 1 if rank < world - 1 else (0 if periodic else None)
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         if periodic:
             for p in planes:
-                p[:halo].copy_(p[-2 * halo:-halo])
-                p[-halo:].copy_(p[halo:2 * halo])
+                n = p.shape[dim]
+                p.narrow(dim, 0, halo).copy_(p.narrow(dim, n - 2 * halo, halo))
+                p.narrow(dim, n - halo, halo).copy_(p.narrow(dim, halo, halo))
         return
-    ops = []
-    keep = []
+    up = rank - 1 if rank > 0 else (world - 1 if periodic else None)
+    dn = rank + 1 if rank < world - 1 else (0 if periodic else None)
+    # Per plane the ops are issued as [send_up, send_dn, recv_dn, recv_up].  With distinct
+    # neighbours the order is irrelevant; in a 2-rank ring both neighbours are the same peer and
+    # messages between one pair of ranks match in issue order: the peer's first message (its top
+    # rows, sent "up") is my bottom ghost, its second (bottom rows) my top ghost.
+    ops, keep = [], []
     for p in planes:
+        n = p.shape[dim]
+        sends, recvs = [], []
         if up is not None:
-            s = p[halo:2 * halo].contiguous()
-            r = torch.empty_like(s)
-            keep.append((p, slice(0, halo), r))
-            ops.append(dist.P2POp(dist.isend, s, up, group))
-            ops.append(dist.P2POp(dist.irecv, r, up, group))
+            s_up = p.narrow(dim, halo, halo).contiguous()
+            r_up = torch.empty_like(s_up)
+            sends.append(dist.P2POp(dist.isend, s_up, up, group))
+            recvs.append(dist.P2POp(dist.irecv, r_up, up, group))
+            keep.append((p.narrow(dim, 0, halo), r_up))
         if dn is not None:
-            s = p[-2 * halo:-halo].contiguous()
-            r = torch.empty_like(s)
-            keep.append((p, slice(p.shape[0] - halo, p.shape[0]), r))
-            ops.append(dist.P2POp(dist.isend, s, dn, group))
-            ops.append(dist.P2POp(dist.irecv, r, dn, group))
-    if world == 2 and periodic and up == dn:
-        # both neighbours are the same peer: order the two messages per plane consistently
-        pass
+            s_dn = p.narrow(dim, n - 2 * halo, halo).contiguous()
+            r_dn = torch.empty_like(s_dn)
+            sends.append(dist.P2POp(dist.isend, s_dn, dn, group))
+            recvs.insert(0, dist.P2POp(dist.irecv, r_dn, dn, group))
+            keep.append((p.narrow(dim, n - halo, halo), r_dn))
+        ops += sends + recvs
     for w in dist.batch_isend_irecv(ops):
         w.wait()
-    for p, sl, r in keep:
-        p[sl].copy_(r)
+    for dst, r in keep:
+        dst.copy_(r)
 
 
 def allreduce_max_(t: torch.Tensor, group=None) -> torch.Tensor:

@@ -33,6 +33,7 @@
 
 #include <math.h>
 #include <new>
+#include <type_traits>
 #include <vector>
 
 namespace {
@@ -67,9 +68,11 @@ struct Params {
 template <typename R> struct Cons4 { R rho, mx, my, E; };
 template <typename R> struct Prim4 { R rho, u, v, p; };
 
-template <typename R> __device__ __forceinline__ R rmax(R a, R b) { return a > b ? a : b; }  // :131
-template <typename R> __device__ __forceinline__ R rmin(R a, R b) { return a < b ? a : b; }  // :134
-template <typename R> __device__ __forceinline__ R rabs(R a) { return a < R(0) ? -a : a; }   // :137
+// d_fmax/d_fmin :131-136.  (a > b ? a : b) and fmax differ only when an argument is NaN; every
+// call site either floors against a finite constant or feeds the guarded HLLC fall-back logic.
+template <typename R> __device__ __forceinline__ R rmax(R a, R b) { return fmax(a, b); }
+template <typename R> __device__ __forceinline__ R rmin(R a, R b) { return fmin(a, b); }
+template <typename R> __device__ __forceinline__ R rabs(R a) { return fabs(a); }  // :137
 
 // reciprocal / sound speed: IEEE in fp64 (parity with the fp64 reference to ~1e-13), single
 // MUFU approximations (<= 1 ulp / 2 ulp) in fp32 where they are below the fp32 noise floor.
@@ -163,13 +166,15 @@ __device__ __forceinline__ Face<R> face_from_cons(const Params<R> &P, Cons4<R> c
   return Face<R>{q.rho, q.u, q.v, q.p, c.E};
 }
 
-// enforce_positive_faces :373-398 (rarely taken: only when a limited face state is non-positive)
+// enforce_positive_faces :373-398 (rarely taken: only when a limited face state is non-positive).
+// Out of line and fed by value so that it does not force the kernel parameters into local memory.
+template <typename R> struct PrimPair { Prim4<R> m, p; };
 template <typename R>
-__device__ __noinline__ void enforce_positive_faces(const Params<R> &P, Prim4<R> &qm,
-                                                    const Prim4<R> &qc, Prim4<R> &qp) {
+__device__ __noinline__ PrimPair<R> enforce_positive_faces(R eps_rho, R eps_p, Prim4<R> qm,
+                                                           Prim4<R> qc, Prim4<R> qp) {
   for (int it = 0; it < 8; it++) {
-    bool bad = (qm.rho <= P.eps_rho || qp.rho <= P.eps_rho) || (qm.p <= P.eps_p || qp.p <= P.eps_p);
-    if (!bad) return;
+    bool bad = (qm.rho <= eps_rho || qp.rho <= eps_rho) || (qm.p <= eps_p || qp.p <= eps_p);
+    if (!bad) return PrimPair<R>{qm, qp};
     qm.rho = R(0.5) * (qm.rho + qc.rho);
     qm.u = R(0.5) * (qm.u + qc.u);
     qm.v = R(0.5) * (qm.v + qc.v);
@@ -179,10 +184,11 @@ __device__ __noinline__ void enforce_positive_faces(const Params<R> &P, Prim4<R>
     qp.v = R(0.5) * (qp.v + qc.v);
     qp.p = R(0.5) * (qp.p + qc.p);
   }
-  qm.rho = rmax(qm.rho, P.eps_rho);
-  qp.rho = rmax(qp.rho, P.eps_rho);
-  qm.p = rmax(qm.p, P.eps_p);
-  qp.p = rmax(qp.p, P.eps_p);
+  qm.rho = rmax(qm.rho, eps_rho);
+  qp.rho = rmax(qp.rho, eps_rho);
+  qm.p = rmax(qm.p, eps_p);
+  qp.p = rmax(qp.p, eps_p);
+  return PrimPair<R>{qm, qp};
 }
 
 // Limited reconstruction (reconstruct_limited_faces :400-425) + Hancock half-step predictor
@@ -200,8 +206,11 @@ __device__ __forceinline__ void reconstruct_predict(const Params<R> &P, const Pr
               qc.p - R(0.5) * s_p};
   Prim4<R> qR{qc.rho + R(0.5) * s_rho, qc.u + R(0.5) * s_u, qc.v + R(0.5) * s_v,
               qc.p + R(0.5) * s_p};
-  if ((qL.rho <= P.eps_rho || qR.rho <= P.eps_rho) || (qL.p <= P.eps_p || qR.p <= P.eps_p))
-    enforce_positive_faces(P, qL, qc, qR);
+  if ((qL.rho <= P.eps_rho || qR.rho <= P.eps_rho) || (qL.p <= P.eps_p || qR.p <= P.eps_p)) {
+    const PrimPair<R> fixed = enforce_positive_faces(P.eps_rho, P.eps_p, qL, qc, qR);
+    qL = fixed.m;
+    qR = fixed.p;
+  }
   // conserved variables and physical flux of both face states (flux_axis :194-203)
   const R mxL = qL.rho * qL.u, myL = qL.rho * qL.v;
   const R mxR = qR.rho * qR.u, myR = qR.rho * qR.v;
@@ -241,7 +250,7 @@ __device__ __forceinline__ Cons4<R> phys_flux(const Face<R> &f) {
 
 // hlle_axis :483-509 — only reached through the guarded fall-backs of HLLC
 template <int AX, typename R>
-__device__ __noinline__ Cons4<R> hlle_flux(const Params<R> &P, Face<R> L, Face<R> Rr, R SL, R SR) {
+__device__ __noinline__ Cons4<R> hlle_flux(Face<R> L, Face<R> Rr, R SL, R SR) {
   const Cons4<R> FL = phys_flux<AX>(L), FR = phys_flux<AX>(Rr);
   if (SL >= R(0)) return FL;
   if (SR <= R(0)) return FR;
@@ -288,7 +297,7 @@ __device__ __forceinline__ Cons4<R> hllc_flux(const Params<R> &P, const Face<R> 
                         !(qL * dLS > R(0)) || !(qR * dRS > R(0)) || !isfinite(rhoStar) ||
                         !isfinite(EStar);
   const bool supersonic = (SL >= R(0)) || (SR <= R(0));
-  if (!supersonic && fallback) return hlle_flux<AX>(P, L, Rr, SL, SR);
+  if (!supersonic && fallback) return hlle_flux<AX>(L, Rr, SL, SR);
   if (supersonic) return FK;
   const R sn = rhoStar * SM, st = rhoStar * (AX == 0 ? K.v : K.u);
   Cons4<R> F;
@@ -322,17 +331,20 @@ template <typename R> __device__ __forceinline__ Cons4<R> shfl_down_cons(Cons4<R
 }
 
 // Per-warp view of the shared-memory row ring.  Row q (offset from the segment's first staged row)
-// lives in slot (q/4)%NS; a slot is laid out [field][row-in-box][36 columns] as the TMA box lands.
+// lives in slot (q/4)%NS; a slot is laid out [field][row-in-box][BOXW columns] as the TMA box
+// lands.  row_off(q) is the element offset of (field 0, row q, column 0); fields are FSTRIDE apart.
 template <typename R>
 struct Ring {
   R *base;
-  __device__ __forceinline__ R *row(int q, int f) const {
-    const int slot = (q >> 2) % H2_NS, sub = q & 3;
-    return base + (size_t)slot * (4 * H2_RB * H2_BOXW) + (f * H2_RB + sub) * H2_BOXW;
+  static constexpr int FSTRIDE = H2_RB * H2_BOXW;
+  __device__ __forceinline__ static int row_off(int q) {
+    return ((q >> 2) % H2_NS) * (4 * H2_RB * H2_BOXW) + (q & 3) * H2_BOXW;
   }
-  __device__ __forceinline__ Cons4<R> cons(int q, int c) const {
-    return Cons4<R>{row(q, 0)[c], row(q, 1)[c], row(q, 2)[c], row(q, 3)[c]};
+  __device__ __forceinline__ Cons4<R> at(int off, int c) const {
+    const R *p = base + off + c;
+    return Cons4<R>{p[0], p[FSTRIDE], p[2 * FSTRIDE], p[3 * FSTRIDE]};
   }
+  __device__ __forceinline__ Cons4<R> cons(int q, int c) const { return at(row_off(q), c); }
 };
 
 // 5-tap second derivative (-1, 16, -30, 16, -1)/12 of k_step :1126-1153
@@ -344,8 +356,8 @@ __device__ __forceinline__ R d2(R m2, R m1, R c, R p1, R p2) {
 template <typename R, bool USE_TMA>
 __global__ void __launch_bounds__(H2_WARPS * 32)
 hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *__restrict__ Uin,
-           R *__restrict__ Uout, const uint8_t *__restrict__ mask, Ctrl *__restrict__ ctrl,
-           int step_slot) {
+           R *__restrict__ Uout, const uint8_t *__restrict__ mask,
+           const uint8_t *__restrict__ segmask, Ctrl *__restrict__ ctrl, int step_slot) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -396,6 +408,9 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
     __syncwarp();
   }
 
+  auto infl_f = [&](int f) -> R {
+    return f == 0 ? P.infl_cons[0] : f == 1 ? P.infl_cons[1] : f == 2 ? P.infl_cons[2] : P.infl_cons[3];
+  };
   // stage block k (plane rows ys+4k .. ys+4k+3; plane row = local row + 2) into slot k%NS
   auto issue = [&](int k) {
     R *dst = ring_base + (size_t)(k % H2_NS) * SLOT_ELEMS;
@@ -428,9 +443,9 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
         const int gx = bx + cc, gr = prow + sub;
         if (gr >= P.H_local + 2 * H2_GHOST) continue;
         if (gx < 0) {
-          dst[i] = P.infl_cons[f];  // x<0 -> inflow (neighbor_or_wall :277-279)
+          dst[i] = infl_f(f);  // x<0 -> inflow (neighbor_or_wall :277-279)
         } else if (gx == 0) {
-          if (!mask[(size_t)gr * W]) dst[i] = P.infl_cons[f];  // k_apply_inflow_left :772-784
+          if (!mask[(size_t)gr * W]) dst[i] = infl_f(f);  // k_apply_inflow_left :772-784
         }
       }
       __syncwarp();
@@ -442,44 +457,11 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
       __syncwarp();
     }
   };
-  // 40 mask bits of plane row prow (bit b <-> staged column b); out-of-domain columns read as 0
-  auto mask_row = [&](int prow) -> unsigned long long {
-    const uint8_t *mr = mask + (size_t)prow * W;
-    const int gx = bx + lane;
-    const int m0 = (gx >= 0 && gx < W) ? mr[gx] : 0;
-    const int gx1 = bx + 32 + lane;
-    const int m1 = (lane < H2_BOXW - 32 && gx1 < W) ? mr[gx1] : 0;
-    const unsigned lo = __ballot_sync(0xffffffffu, m0 != 0);
-    const unsigned hi = __ballot_sync(0xffffffffu, m1 != 0);
-    return (unsigned long long)lo | ((unsigned long long)hi << 32);
-  };
   auto row_in_domain = [&](int r) -> bool {  // local row r inside the GLOBAL grid?
     const int gy = P.y_begin + r;
     return gy >= 0 && gy < P.H_global;
   };
-  auto bit = [&](unsigned long long w, int b) -> bool { return (w >> b) & 1ull; };
 
-  // y-face flux between the cell below (B) and above (T) — k_compute_yface_flux :998-1030
-  auto yface = [&](bool hasB, bool hasT, bool rinB, bool rinT, const Face<R> &yT_B,
-                   const Face<R> &yB_T, const Prim4<R> &PB, const Prim4<R> &PT,
-                   const Cons4<R> &UB_raw, const Cons4<R> &UT_raw) -> Cons4<R> {
-    Face<R> lo = yT_B, hi = yB_T;
-    if (!(hasB && hasT)) {
-      if (hasT) {
-        lo = rinB ? ghost_face(P, PT) : face_from_cons(P, UT_raw);  // neighbor_or_wall(x,yt,0,-1)
-      } else if (hasB) {
-        hi = rinT ? ghost_face(P, PB) : face_from_cons(P, UB_raw);  // neighbor_or_wall(x,yb,0,+1)
-      }
-    }
-    // faces between two non-fluid cells carry no flux (:1024-1027); they are still evaluated on
-    // finite states so that the warp-uniform control flow of hllc_flux stays convergent
-    const Cons4<R> F = hllc_flux<1>(P, lo, hi);
-    return (hasB || hasT) ? F : Cons4<R>{R(0), R(0), R(0), R(0)};
-  };
-
-  // ------------------------------------------------------------------------------------------
-  // prologue: stage the first blocks, build the carried state for row ys
-  // ------------------------------------------------------------------------------------------
   int issued = 0, acquired = 0;
   for (; issued < nblk && issued < H2_NS; ++issued) issue(issued);
   auto need_row = [&](int q) {
@@ -488,216 +470,265 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
       ++acquired;
     }
   };
-  need_row(3);
-  // mask words for local rows ys-2 .. ys+1 (plane rows ys .. ys+3)
-  unsigned long long mw_m2, mw_m1, mw_c, mw_p1, mw_p2;
-  mw_m1 = mask_row(ys + 0);  // local ys-2
-  mw_c = mask_row(ys + 1);   // local ys-1
-  mw_p1 = mask_row(ys + 2);  // local ys
-  mw_p2 = mask_row(ys + 3);  // local ys+1
-  mw_m2 = 0;
-
-  Prim4<R> Pa = cons_to_prim(P, ring.cons(0, c));  // row ys-2
-  Cons4<R> Ub = ring.cons(1, c);                   // row ys-1
-  Prim4<R> Pb = cons_to_prim(P, Ub);
-  Cons4<R> U0 = ring.cons(2, c);  // row ys
-  Prim4<R> P0 = cons_to_prim(P, U0);
-  Cons4<R> U1 = ring.cons(3, c);  // row ys+1
-  Prim4<R> P1 = cons_to_prim(P, U1);
-
-  Face<R> yT_r;
-  Cons4<R> G_bot;
-  {
-    // y-reconstruction of cell ys-1 (needs rows ys-2, ys-1, ys) -> its predicted top state
-    Face<R> lo_b, hi_b, lo_0, hi_0;
-    Prim4<R> qm = bit(mw_m1, c) ? ghost_prim(Pb) : Pa;
-    Prim4<R> qp = bit(mw_p1, c) ? ghost_prim(Pb) : P0;
-    reconstruct_predict<1>(P, qm, Pb, qp, half_dt, lo_b, hi_b);
-    // y-reconstruction of cell ys (rows ys-1, ys, ys+1)
-    qm = bit(mw_c, c) ? ghost_prim(P0) : Pb;
-    qp = bit(mw_p2, c) ? ghost_prim(P0) : P1;
-    reconstruct_predict<1>(P, qm, P0, qp, half_dt, lo_0, hi_0);
-    const bool rinB = row_in_domain(ys - 1);
-    const bool hasB = rinB && !bit(mw_c, c);
-    const bool hasT = !bit(mw_p1, c);
-    G_bot = yface(hasB, hasT, rinB, true, hi_b, lo_0, Pb, P0, Ub, U0);
-    yT_r = hi_0;
-  }
-  // roll so that (m2, m1, c, p1, p2) describe rows r-2 .. r+2 for r = ys (p2 loaded in the loop)
-  mw_m2 = mw_m1;
-  mw_m1 = mw_c;
-  mw_c = mw_p1;
-  mw_p1 = mw_p2;
-
-  Prim4<R> Pr = P0, Pr1 = P1;
-  Cons4<R> Ur = U0, Ur1 = U1;
+  need_row(1);
   R wmax = R(0);
 
-  // ------------------------------------------------------------------------------------------
-  // march
-  // ------------------------------------------------------------------------------------------
-  for (int r = ys; r < ye; ++r) {
-    const int q = r - ys + 2;  // staged-row offset of row r
-    need_row(q + 2);
-    mw_p2 = mask_row(r + 2 + H2_GHOST);
-    const Cons4<R> Ur2 = ring.cons(q + 2, c);
-    const Prim4<R> Pr2 = cons_to_prim(P, Ur2);
+  // 40 mask bits of one plane row (bit b <-> staged column b); out-of-domain columns read as 0
+  const int mgx0 = bx + lane, mgx1 = bx + 32 + lane;
+  const bool mok0 = (mgx0 >= 0) && (mgx0 < W);
+  const bool mok1 = (lane < H2_BOXW - 32) && (mgx1 < W);
 
-    // -- y: reconstruct cell r+1, flux through face r+1/2 ------------------------------------
-    Face<R> yB1, yT1;
-    {
-      Prim4<R> qm = bit(mw_c, c) ? ghost_prim(Pr1) : Pr;
-      Prim4<R> qp = bit(mw_p2, c) ? ghost_prim(Pr1) : Pr2;
-      reconstruct_predict<1>(P, qm, Pr1, qp, half_dt, yB1, yT1);
-    }
-    const bool m_c = bit(mw_c, c);
-    const bool rinT = row_in_domain(r + 1);
-    const Cons4<R> G_top =
-        yface(!m_c, rinT && !bit(mw_p1, c), true, rinT, yT_r, yB1, Pr, Pr1, Ur, Ur1);
+  // The march is instantiated twice: MASKED = the strip-segment touches the body (mask words are
+  // loaded and every neighbour access goes through the no-slip ghost rule), and the plain variant
+  // for the (vast majority of) strip-segments that contain no body cell, where the mask plane is
+  // never read and the ghost selects vanish at compile time.
+  auto march = [&](auto masked_tag) {
+    constexpr bool MASKED = decltype(masked_tag)::value;
+    auto mask_row = [&](int prow) -> unsigned long long {
+      if constexpr (MASKED) {
+        const uint8_t *mr = mask + (size_t)prow * W;
+        const int m0 = mok0 ? mr[mgx0] : 0;
+        const int m1 = mok1 ? mr[mgx1] : 0;
+        const unsigned lo = __ballot_sync(0xffffffffu, m0 != 0);
+        const unsigned hi = __ballot_sync(0xffffffffu, m1 != 0);
+        return (unsigned long long)lo | ((unsigned long long)hi << 32);
+      } else {
+        return 0ull;
+      }
+    };
+    auto bit = [&](unsigned long long w, int b) -> bool {
+      if constexpr (MASKED) return (w >> b) & 1ull;
+      else return false;
+    };
+    // neighbour prim with the wall rule: masked -> no-slip ghost of the centre (:364-368)
+    auto nb = [&](unsigned long long w, int b, const Prim4<R> &centre, const Prim4<R> &n) {
+      if constexpr (MASKED) return bit(w, b) ? ghost_prim(centre) : n;
+      else return n;
+    };
 
-    // -- x: neighbours by shuffle, edge lanes from the staged halo columns --------------------
-    Prim4<R> Pl = shfl_up_prim(Pr), Pq = shfl_down_prim(Pr);
-    if (lane == 0 || lane == 31) {
-      const Prim4<R> e = cons_to_prim(P, ring.cons(q, lane == 0 ? c - 1 : c + 1));
-      if (lane == 0) Pl = e;
-      else Pq = e;
-    }
-    Face<R> xL, xR;
-    {
-      Prim4<R> qm = bit(mw_c, c - 1) ? ghost_prim(Pr) : Pl;
-      Prim4<R> qp = bit(mw_c, c + 1) ? ghost_prim(Pr) : Pq;
-      reconstruct_predict<0>(P, qm, Pr, qp, half_dt, xL, xR);
-    }
-    // flux through this lane's RIGHT face (between columns x and x+1) — k_compute_xface_flux
-    Cons4<R> F_right;
-    {
-      const Face<R> xL_B = shfl_down_face(xL);
-      const bool inA = (x >= 0) && (x < W), inB = (x + 1 >= 0) && (x + 1 < W);
-      const bool hasA = inA && !m_c, hasB = inB && !bit(mw_c, c + 1);
-      Face<R> lo = xR, hi = xL_B;
-      if (!(hasA && hasB)) {
-        if (hasB) {   // A is the inflow boundary (x<0) or a body cell
-          lo = inA ? ghost_face(P, Pq)
-                   : face_from_cons(P, Cons4<R>{P.infl_cons[0], P.infl_cons[1], P.infl_cons[2],
-                                                P.infl_cons[3]});
-        } else if (hasA) {  // B is beyond the outflow edge (raw column W-1) or a body cell
-          hi = inB ? ghost_face(P, Pr) : face_from_cons(P, ring.cons(q, c + 1));
+    // y-face flux between the cell below (B) and above (T) — k_compute_yface_flux :998-1030
+    auto yface = [&](bool hasB, bool hasT, bool rinB, bool rinT, const Face<R> &yT_B,
+                     const Face<R> &yB_T, const Prim4<R> &PB, const Prim4<R> &PT, int roB,
+                     int roT) -> Cons4<R> {
+      Face<R> lo = yT_B, hi = yB_T;
+      if (!(hasB && hasT)) {
+        if (hasT) {  // neighbor_or_wall(x, yt, 0, -1): body cell below, or the y=0 clamp
+          lo = rinB ? ghost_face(P, PT) : face_from_cons(P, ring.at(roT, c));
+        } else if (hasB) {  // neighbor_or_wall(x, yb, 0, +1)
+          hi = rinT ? ghost_face(P, PB) : face_from_cons(P, ring.at(roB, c));
         }
       }
-      const Cons4<R> F = hllc_flux<0>(P, lo, hi);
-      F_right = (hasA || hasB) ? F : Cons4<R>{R(0), R(0), R(0), R(0)};
+      // faces between two non-fluid cells carry no flux (:1024-1027); they are still evaluated
+      // (on finite states) so that the warp-uniform control flow of hllc_flux stays convergent
+      const Cons4<R> F = hllc_flux<1>(P, lo, hi);
+      if constexpr (MASKED) return (hasB || hasT) ? F : Cons4<R>{R(0), R(0), R(0), R(0)};
+      else return F;
+    };
+
+    // The march starts two rows early (r = ys-2, ys-1): those warm-up iterations only build the
+    // carried y-state (predicted top state of the row below, flux through the face below) with
+    // the same code the real rows use, which keeps a single copy of the reconstruction / Riemann
+    // solver in the instruction stream.
+    unsigned long long mw_m2 = 0, mw_m1 = 0, mw_c, mw_p1, mw_p2;
+    mw_c = mask_row(ys + 0);   // local row ys-2 (plane row = local row + 2)
+    mw_p1 = mask_row(ys + 1);  // local row ys-1
+    // ring offsets of rows r-2, r-1, r, r+1
+    int ro_m2 = 0, ro_m1 = 0, ro_c = Ring<R>::row_off(0), ro_p1 = Ring<R>::row_off(1);
+    Prim4<R> Pr = cons_to_prim(P, ring.at(ro_c, c)), Pr1 = cons_to_prim(P, ring.at(ro_p1, c));
+    Face<R> yT_r{R(1), R(0), R(0), R(1), R(1)};
+    Cons4<R> G_bot{R(0), R(0), R(0), R(0)};
+
+    for (int r = ys - 2; r < ye; ++r) {
+      const int q = r - ys + 2;  // staged-row offset of row r
+      need_row(q + 2);
+      mw_p2 = mask_row(r + 2 + H2_GHOST);
+      const int ro_p2 = Ring<R>::row_off(q + 2);
+      const Prim4<R> Pr2 = cons_to_prim(P, ring.at(ro_p2, c));
+
+      // -- y: reconstruct cell r+1, flux through face r+1/2 ----------------------------------
+      Face<R> yB1, yT1;
+      reconstruct_predict<1>(P, nb(mw_c, c, Pr1, Pr), Pr1, nb(mw_p2, c, Pr1, Pr2), half_dt, yB1,
+                             yT1);
+      const bool m_c = bit(mw_c, c);
+      const bool rinB = row_in_domain(r), rinT = row_in_domain(r + 1);
+      const Cons4<R> G_top = yface(rinB && !m_c, rinT && !bit(mw_p1, c), rinB, rinT, yT_r, yB1,
+                                   Pr, Pr1, ro_c, ro_p1);
+
+      if (r >= ys) {  // warp-uniform: the two warm-up rows skip the x-sweep and the update
+        // -- x: neighbours by shuffle, edge lanes from the staged halo columns ----------------
+        Prim4<R> Pl = shfl_up_prim(Pr), Pq = shfl_down_prim(Pr);
+        if (lane == 0 || lane == 31) {
+          const Prim4<R> e = cons_to_prim(P, ring.at(ro_c, lane == 0 ? c - 1 : c + 1));
+          if (lane == 0) Pl = e;
+          else Pq = e;
+        }
+        Face<R> xL, xR;
+        reconstruct_predict<0>(P, nb(mw_c, c - 1, Pr, Pl), Pr, nb(mw_c, c + 1, Pr, Pq), half_dt, xL,
+                               xR);
+        // flux through this lane's RIGHT face (columns x | x+1) — k_compute_xface_flux :964-996
+        Cons4<R> F_right;
+        {
+          const Face<R> xL_B = shfl_down_face(xL);
+          const bool inA = (x >= 0) && (x < W), inB = (x + 1 >= 0) && (x + 1 < W);
+          const bool hasA = inA && !m_c, hasB = inB && !bit(mw_c, c + 1);
+          Face<R> lo = xR, hi = xL_B;
+          if (!(hasA && hasB)) {
+            if (hasB) {  // A is the inflow boundary (x<0) or a body cell
+              lo = inA ? ghost_face(P, Pq)
+                       : face_from_cons(P, Cons4<R>{P.infl_cons[0], P.infl_cons[1],
+                                                    P.infl_cons[2], P.infl_cons[3]});
+            } else if (hasA) {  // B is beyond the outflow edge (raw column W-1) or a body cell
+              hi = inB ? ghost_face(P, Pr) : face_from_cons(P, ring.at(ro_c, c + 1));
+            }
+          }
+          const Cons4<R> F = hllc_flux<0>(P, lo, hi);
+          if constexpr (MASKED) F_right = (hasA || hasB) ? F : Cons4<R>{R(0), R(0), R(0), R(0)};
+          else F_right = F;
+        }
+        const Cons4<R> F_left = shfl_up_cons(F_right);
+
+        // -- update (k_step :1097-1175) -------------------------------------------------------
+        if (owned) {
+          const Cons4<R> Ur = ring.at(ro_c, c);
+          Cons4<R> Un = Ur;
+          if (!m_c) {
+            Un.rho -= dt * (F_right.rho - F_left.rho);
+            Un.mx -= dt * (F_right.mx - F_left.mx);
+            Un.my -= dt * (F_right.my - F_left.my);
+            Un.E -= dt * (F_right.E - F_left.E);
+            Un.rho -= dt * (G_top.rho - G_bot.rho);
+            Un.mx -= dt * (G_top.mx - G_bot.mx);
+            Un.my -= dt * (G_top.my - G_bot.my);
+            Un.E -= dt * (G_top.E - G_bot.E);
+
+            // diffusion taps: masked neighbour -> no-slip ghost of the centre (:1121-1141)
+            Cons4<R> xm2 = ring.at(ro_c, c - 2), xm1 = ring.at(ro_c, c - 1);
+            Cons4<R> xp1 = ring.at(ro_c, c + 1), xp2 = ring.at(ro_c, c + 2);
+            Cons4<R> ym2 = ring.at(ro_m2, c), ym1 = ring.at(ro_m1, c);
+            Cons4<R> yp1 = ring.at(ro_p1, c), yp2 = ring.at(ro_p2, c);
+            if constexpr (MASKED) {
+              const Cons4<R> gh = ghost_cons(P, Pr);
+              if (bit(mw_c, c - 2)) xm2 = gh;
+              if (bit(mw_c, c - 1)) xm1 = gh;
+              if (bit(mw_c, c + 1)) xp1 = gh;
+              if (bit(mw_c, c + 2)) xp2 = gh;
+              if (bit(mw_m2, c)) ym2 = gh;
+              if (bit(mw_m1, c)) ym1 = gh;
+              if (bit(mw_p1, c)) yp1 = gh;
+              if (bit(mw_p2, c)) yp2 = gh;
+            }
+            const R lap_rho = d2(xm2.rho, xm1.rho, Ur.rho, xp1.rho, xp2.rho) +
+                              d2(ym2.rho, ym1.rho, Ur.rho, yp1.rho, yp2.rho);
+            const R lap_mx = d2(xm2.mx, xm1.mx, Ur.mx, xp1.mx, xp2.mx) +
+                             d2(ym2.mx, ym1.mx, Ur.mx, yp1.mx, yp2.mx);
+            const R lap_my = d2(xm2.my, xm1.my, Ur.my, xp1.my, xp2.my) +
+                             d2(ym2.my, ym1.my, Ur.my, yp1.my, yp2.my);
+            const R lap_E =
+                d2(xm2.E, xm1.E, Ur.E, xp1.E, xp2.E) + d2(ym2.E, ym1.E, Ur.E, yp1.E, yp2.E);
+            Un.rho += (P.visc_rho * dt) * lap_rho;
+            Un.mx += (P.visc_nu * dt) * lap_mx;
+            Un.my += (P.visc_nu * dt) * lap_my;
+            Un.E += (P.visc_e * dt) * lap_E;
+
+            Un.rho = rmax(Un.rho, P.eps_rho);
+            Prim4<R> pp = cons_to_prim(P, Un);
+            if (pp.p <= P.eps_p || !isfinite(pp.p) || !isfinite(pp.rho) || !isfinite(pp.u) ||
+                !isfinite(pp.v)) {
+              pp.rho = rmax(pp.rho, P.eps_rho);
+              pp.p = rmax(pp.p, P.eps_p);
+              Un = prim_to_cons(P, pp);
+              pp = cons_to_prim(P, Un);
+            }
+            // max wavespeed of the state the NEXT step will see (k_max_wavespeed_blocks
+            // :786-819); column 0 is overwritten with the inflow state before that scan (:1834)
+            R ws;
+            if (x == 0) {
+              ws = (R)P.infl_speed;
+            } else {
+              const R a = sound_speed(P, pp);
+              const R sx = rabs(pp.u) + a, sy = rabs(pp.v) + a;
+              ws = sx > sy ? sx : sy;
+              if (!isfinite(ws)) ws = R(1e-12);
+            }
+            wmax = ws > wmax ? ws : wmax;
+          }
+          const size_t o = (size_t)(r + H2_GHOST) * W + x;
+          Uout[o] = Un.rho;
+          Uout[PL + o] = Un.mx;
+          Uout[2 * PL + o] = Un.my;
+          Uout[3 * PL + o] = Un.E;
+          // keep the y-clamp ghost rows of the output planes current (global edges only)
+          const int gy = P.y_begin + r;
+          if (gy == 0 || gy == P.H_global - 1) {
+            for (int g = 1; g <= H2_GHOST; ++g) {
+              if (gy == 0) {
+                const size_t og = (size_t)(r + H2_GHOST - g) * W + x;
+                Uout[og] = Un.rho;
+                Uout[PL + og] = Un.mx;
+                Uout[2 * PL + og] = Un.my;
+                Uout[3 * PL + og] = Un.E;
+              }
+              if (gy == P.H_global - 1) {
+                const size_t og = (size_t)(r + H2_GHOST + g) * W + x;
+                Uout[og] = Un.rho;
+                Uout[PL + og] = Un.mx;
+                Uout[2 * PL + og] = Un.my;
+                Uout[3 * PL + og] = Un.E;
+              }
+            }
+          }
+        }
+      }  // r >= ys
+
+      // -- roll the carried state ---------------------------------------------------------------
+      G_bot = G_top;
+      yT_r = yT1;
+      Pr = Pr1;
+      Pr1 = Pr2;
+      mw_m2 = mw_m1;
+      mw_m1 = mw_c;
+      mw_c = mw_p1;
+      mw_p1 = mw_p2;
+      ro_m2 = ro_m1;
+      ro_m1 = ro_c;
+      ro_c = ro_p1;
+      ro_p1 = ro_p2;
+
+      // rows <= q-2 are dead for the next iteration: recycle a slot once its last row is
+      if (q >= 5 && ((q - 2) & 3) == 3) {
+        __syncwarp();
+        if (issued < nblk) {
+          issue(issued);
+          ++issued;
+        }
+      }
     }
-    const Cons4<R> F_left = shfl_up_cons(F_right);
+  };
 
-    // -- update (k_step :1097-1175) -----------------------------------------------------------
-    if (owned) {
-      Cons4<R> Un = Ur;
-      if (!m_c) {
-        Un.rho -= dt * (F_right.rho - F_left.rho);
-        Un.mx -= dt * (F_right.mx - F_left.mx);
-        Un.my -= dt * (F_right.my - F_left.my);
-        Un.E -= dt * (F_right.E - F_left.E);
-        Un.rho -= dt * (G_top.rho - G_bot.rho);
-        Un.mx -= dt * (G_top.mx - G_bot.mx);
-        Un.my -= dt * (G_top.my - G_bot.my);
-        Un.E -= dt * (G_top.E - G_bot.E);
-
-        const Cons4<R> gh = ghost_cons(P, Pr);  // masked neighbour -> no-slip ghost of the centre
-        const Cons4<R> xm2 = bit(mw_c, c - 2) ? gh : ring.cons(q, c - 2);
-        const Cons4<R> xm1 = bit(mw_c, c - 1) ? gh : ring.cons(q, c - 1);
-        const Cons4<R> xp1 = bit(mw_c, c + 1) ? gh : ring.cons(q, c + 1);
-        const Cons4<R> xp2 = bit(mw_c, c + 2) ? gh : ring.cons(q, c + 2);
-        const Cons4<R> ym2 = bit(mw_m2, c) ? gh : ring.cons(q - 2, c);
-        const Cons4<R> ym1 = bit(mw_m1, c) ? gh : ring.cons(q - 1, c);
-        const Cons4<R> yp1 = bit(mw_p1, c) ? gh : Ur1;
-        const Cons4<R> yp2 = bit(mw_p2, c) ? gh : Ur2;
-        const R lap_rho = d2(xm2.rho, xm1.rho, Ur.rho, xp1.rho, xp2.rho) +
-                          d2(ym2.rho, ym1.rho, Ur.rho, yp1.rho, yp2.rho);
-        const R lap_mx = d2(xm2.mx, xm1.mx, Ur.mx, xp1.mx, xp2.mx) +
-                         d2(ym2.mx, ym1.mx, Ur.mx, yp1.mx, yp2.mx);
-        const R lap_my = d2(xm2.my, xm1.my, Ur.my, xp1.my, xp2.my) +
-                         d2(ym2.my, ym1.my, Ur.my, yp1.my, yp2.my);
-        const R lap_E = d2(xm2.E, xm1.E, Ur.E, xp1.E, xp2.E) + d2(ym2.E, ym1.E, Ur.E, yp1.E, yp2.E);
-        Un.rho += (P.visc_rho * dt) * lap_rho;
-        Un.mx += (P.visc_nu * dt) * lap_mx;
-        Un.my += (P.visc_nu * dt) * lap_my;
-        Un.E += (P.visc_e * dt) * lap_E;
-
-        Un.rho = rmax(Un.rho, P.eps_rho);
-        Prim4<R> pp = cons_to_prim(P, Un);
-        if (pp.p <= P.eps_p || !isfinite(pp.p) || !isfinite(pp.rho) || !isfinite(pp.u) ||
-            !isfinite(pp.v)) {
-          pp.rho = rmax(pp.rho, P.eps_rho);
-          pp.p = rmax(pp.p, P.eps_p);
-          Un = prim_to_cons(P, pp);
-          pp = cons_to_prim(P, Un);
-        }
-        // max wavespeed of the state the NEXT step will see (k_max_wavespeed_blocks :786-819);
-        // column 0 is overwritten with the inflow state before that scan (:1834)
-        R ws;
-        if (x == 0) {
-          ws = (R)P.infl_speed;
-        } else {
-          const R a = sound_speed(P, pp);
-          const R sx = rabs(pp.u) + a, sy = rabs(pp.v) + a;
-          ws = sx > sy ? sx : sy;
-          if (!isfinite(ws)) ws = R(1e-12);
-        }
-        wmax = ws > wmax ? ws : wmax;
-      }
-      const size_t o = (size_t)(r + H2_GHOST) * W + x;
-      Uout[o] = Un.rho;
-      Uout[PL + o] = Un.mx;
-      Uout[2 * PL + o] = Un.my;
-      Uout[3 * PL + o] = Un.E;
-      // keep the y-clamp ghost rows of the output planes current (global edges only)
-      const int gy = P.y_begin + r;
-      if (gy == 0) {
-#pragma unroll
-        for (int g = 1; g <= H2_GHOST; ++g) {
-          const size_t og = (size_t)(r + H2_GHOST - g) * W + x;
-          Uout[og] = Un.rho;
-          Uout[PL + og] = Un.mx;
-          Uout[2 * PL + og] = Un.my;
-          Uout[3 * PL + og] = Un.E;
-        }
-      }
-      if (gy == P.H_global - 1) {
-#pragma unroll
-        for (int g = 1; g <= H2_GHOST; ++g) {
-          const size_t og = (size_t)(r + H2_GHOST + g) * W + x;
-          Uout[og] = Un.rho;
-          Uout[PL + og] = Un.mx;
-          Uout[2 * PL + og] = Un.my;
-          Uout[3 * PL + og] = Un.E;
-        }
-      }
-    }
-
-    // -- roll the carried state ----------------------------------------------------------------
-    G_bot = G_top;
-    yT_r = yT1;
-    Pr = Pr1;
-    Pr1 = Pr2;
-    Ur = Ur1;
-    Ur1 = Ur2;
-    mw_m2 = mw_m1;
-    mw_m1 = mw_c;
-    mw_c = mw_p1;
-    mw_p1 = mw_p2;
-
-    // rows <= q-2 are dead for the next iteration: recycle a slot once its last row is
-    if (((q - 2) & 3) == 3) {
-      __syncwarp();
-      if (issued < nblk) {
-        issue(issued);
-        ++issued;
-      }
-    }
-  }
+  if (segmask[item]) march(std::true_type{});
+  else march(std::false_type{});
 
   wmax = tau::warp_max(wmax);
   if (lane == 0 && wmax > R(0)) tau::atomic_max_nonneg(&ctrl->maxspeed[(step_slot + 1) % 3], (double)wmax);
+}
+
+// One flag per marching work item (strip x segment): does the staged window of that item contain a
+// body cell?  Static for a given mask and segment height; selects the march variant.
+template <typename R>
+__global__ void hyp2d_build_segmask(const Params<R> P, const uint8_t *__restrict__ mask,
+                                    uint8_t *__restrict__ segmask) {
+  const int item = blockIdx.x;
+  const int strip = item % P.nstrips, seg = item / P.nstrips;
+  const int x0 = strip * H2_OWN, bx = (x0 - 2) & ~3;
+  const int ys = seg * P.seg_rows, ye = min(ys + P.seg_rows, P.H_local);
+  const int r0 = ys, r1 = min(ye + 2 * H2_GHOST, P.H_local + 2 * H2_GHOST);  // plane rows
+  const int c0 = max(bx, 0), c1 = min(bx + H2_BOXW, P.W);
+  int any = 0;
+  const int ncol = c1 - c0, n = (r1 - r0) * ncol;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    any |= mask[(size_t)(r0 + i / ncol) * P.W + c0 + i % ncol];
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) segmask[item] = any ? 1 : 0;
 }
 
 // Standalone max-wavespeed scan of the CURRENT state (first step after init/upload) —
@@ -819,6 +850,9 @@ struct tau_hyp2d {
   bool own_stream;
   void *U[2];        // 4 planes each, contiguous, incl. ghost rows
   uint8_t *mask;
+  uint8_t *segmask;      // per work-item "touches the body" flags (device)
+  size_t segmask_cap;
+  bool segmask_dirty;
   Ctrl *ctrl;
   CUtensorMap tm[2];
   int cur;
@@ -928,15 +962,25 @@ int launch_steps(tau_hyp2d *h, int nsteps) {
     TAU_CUDA(cudaFuncSetAttribute(kern_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done[ti][0] = true;
   }
+  if (h->segmask_dirty) {
+    if (h->segmask_cap < (size_t)items) {
+      if (h->segmask) TAU_CUDA(cudaFree(h->segmask));
+      TAU_CUDA(cudaMalloc(&h->segmask, (size_t)items));
+      h->segmask_cap = (size_t)items;
+    }
+    hyp2d_build_segmask<R><<<items, 128, 0, h->stream>>>(P, h->mask, h->segmask);
+    h->launches++;
+    h->segmask_dirty = false;
+  }
   for (int s = 0; s < nsteps; ++s) {
     const int a = h->cur, b = a ^ 1;
     const int slot = (int)(h->steps % 3);
     if (h->use_tma)
       kern_tma<<<grid, H2_WARPS * 32, smem, h->stream>>>(h->tm[a], P, (const R *)h->U[a], (R *)h->U[b],
-                                                         h->mask, h->ctrl, slot);
+                                                         h->mask, h->segmask, h->ctrl, slot);
     else
       kern_gen<<<grid, H2_WARPS * 32, smem, h->stream>>>(h->tm[a], P, (const R *)h->U[a], (R *)h->U[b],
-                                                         h->mask, h->ctrl, slot);
+                                                         h->mask, h->segmask, h->ctrl, slot);
     h->launches++;
     h->cur = b;
     h->steps++;
@@ -1033,6 +1077,9 @@ int tau_hyp2d_create(const tau_hyp2d_config *cfg, int W, int H, int dtype, int d
   h->launches = 0;
   h->speed_valid = false;
   h->timed = false;
+  h->segmask = nullptr;
+  h->segmask_cap = 0;
+  h->segmask_dirty = true;
   h->seg_rows = 64;
   if (const char *e = getenv("TAU_HYP2D_SEG_ROWS")) {
     int v = atoi(e);
@@ -1086,6 +1133,7 @@ int tau_hyp2d_init(tau_hyp2d *h) {
   TAU_REQUIRE(h, "tau_hyp2d_init: null handle");
   TAU_CUDA(cudaSetDevice(h->device));
   h->steps = 0;
+  h->segmask_dirty = true;
   TAU_CUDA(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->stream));
   int rc = h->dtype ? launch_init<double>(h) : launch_init<float>(h);
   if (rc) return rc;
@@ -1106,7 +1154,10 @@ int tau_hyp2d_upload(tau_hyp2d *h, const void *const planes[4], const uint8_t *m
     TAU_CUDA(cudaMemcpyAsync((char *)h->U[h->cur] + (f * h->plane_elems + row0) * es, planes[f], n * es,
                              cudaMemcpyHostToDevice, h->stream));
   }
-  if (mask) TAU_CUDA(cudaMemcpyAsync(h->mask + row0, mask, n, cudaMemcpyHostToDevice, h->stream));
+  if (mask) {
+    TAU_CUDA(cudaMemcpyAsync(h->mask + row0, mask, n, cudaMemcpyHostToDevice, h->stream));
+    h->segmask_dirty = true;
+  }
   int rc = hyp2d_state_changed(h, mask ? 1 : 0);
   if (rc) return rc;
   TAU_CUDA(cudaStreamSynchronize(h->stream));
@@ -1171,6 +1222,7 @@ int tau_hyp2d_device_state(tau_hyp2d *h, void **planes, uint8_t **mask, double *
 int tau_hyp2d_set_seg_rows(tau_hyp2d *h, int rows) {
   TAU_REQUIRE(h && rows >= 4, "tau_hyp2d_set_seg_rows: rows must be >= 4");
   h->seg_rows = rows;
+  h->segmask_dirty = true;
   return TAU_OK;
 }
 
@@ -1190,6 +1242,7 @@ int tau_hyp2d_destroy(tau_hyp2d *h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   cudaFree(h->ctrl);
+  if (h->segmask) cudaFree(h->segmask);
   cudaFree(h->mask);
   cudaFree(h->U[1]);
   cudaFree(h->U[0]);

@@ -1,0 +1,71 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/tau_b200.h declares; the
+product has no CPU fallback (creating a handle without a device fails loudly)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "tau_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tau_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from fluid_sims_b200 import _lib
+    syms = declared_symbols()
+    assert len(syms) >= 25
+    missing = [s for s in syms if not hasattr(_lib.lib, s)]
+    assert not missing, f"declared in tau_b200.h but not exported: {missing}"
+    assert _lib.lib.tau_abi_version() == 1
+
+
+def test_product_does_not_link_or_import_the_oracle():
+    import subprocess
+    from fluid_sims_b200 import LIB_PATH
+    out = subprocess.run(["ldd", LIB_PATH], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "libref" not in out
+    pkg = os.path.join(ROOT, "fluid_sims_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in src and "liboracle" not in src, f
+
+
+def test_no_cpu_fallback():
+    from fluid_sims_b200 import TauError, device_count
+    if device_count() > 0:
+        pytest.skip("a GPU is present")
+    from fluid_sims_b200.gray_scott import GrayScott, Params
+    from fluid_sims_b200.hypersonic2d import Hypersonic2D, SimConfig
+    with pytest.raises(TauError) as e:
+        GrayScott(Params(nx=64, ny=64))
+    assert e.value.code == -19
+    with pytest.raises(TauError) as e:
+        Hypersonic2D(SimConfig.default(64, 64))
+    assert e.value.code == -19
+
+
+def test_host_side_helpers_without_gpu():
+    import numpy as np
+
+    import oracle
+    from fluid_sims_b200 import TauError
+    from fluid_sims_b200.gray_scott import init_pattern
+    from fluid_sims_b200.hypersonic2d import SimConfig
+    u, v = init_pattern(96, 64, 1337)
+    eu, ev = oracle.gs_init_pattern(96, 64, 1337)
+    assert np.array_equal(u, eu) and np.array_equal(v, ev)
+    c = SimConfig.default(8192, 1024)           # default_config() tau_hypersonic_cuda.cu:1394-1409
+    assert (c.gamma, c.cfl, c.inflow_mach, c.geom_x0) == (1.1, 0.25, 25.0, 125.0)
+    assert c.geom_cy == 512.0 and abs(c.geom_Rb - 1024 / 12) < 1e-12 and c.steps_per_frame == 2
+    c.validate()
+    for bad, pat in ((dict(gamma=1.0), "gamma"), (dict(cfl=0.0), "cfl"), (dict(visc_nu=-1.0), "visc-nu"),
+                     (dict(inflow_mach=0.0), "mach"), (dict(geom_Rb=1.0), "geom-rb")):
+        with pytest.raises(TauError, match=pat):
+            SimConfig.default(8192, 1024, **bad).validate()

@@ -177,8 +177,8 @@ def run_product(a):
         torch.cuda.set_device(0)
     dev = local if world > 1 else 0
 
-    W = GRID_W
-    H = GRID_H * world if a.scaling == "weak" else GRID_H
+    W = a.grid_w or GRID_W
+    H = (a.grid_h or GRID_H) * (world if a.scaling == "weak" else 1)
     cfg = SimConfig.default(W, H)
     y0, hl = slab.partition_rows(H, world)[rank]
     # an explicit side stream: torch's legacy default stream has handle 0, which the C-ABI reads as
@@ -203,20 +203,29 @@ def run_product(a):
             views[sp] = slab.wrap_plane(sp, (1,), torch.float64, dev)
         return views[pp], views[sp], mp
 
+    peer = world > 1 and a.exchange == "peer"
+
+    def resync():
+        """after init/upload on a slab: ghost rows + wavespeed once over NCCL, arm device barrier"""
+        if world > 1:
+            slab.hyp2d_sync_state(sim)
+            if peer:
+                sim.peers_ready()
+                dist.barrier()
+
     def advance(n):
-        if world == 1:
-            sim.step(n)
+        if world == 1 or peer:
+            sim.step(n)      # peer mode: halo push + max all-reduce + barrier are device-side
             return
-        for _ in range(n):
+        for _ in range(n):   # host-driven exchange (NCCL P2P + all-reduce every step)
             planes, speed, _ = state_views()
             slab.exchange_halos([planes], HALO, periodic=False, dim=1)
             dist.all_reduce(speed, op=dist.ReduceOp.MAX)
             sim.step(1)
 
-    if world > 1:   # the static body mask needs its ghost rows once
-        _, _, mp = state_views()
-        mview = slab.wrap_plane(mp, (hl + 2 * HALO, W), torch.uint8, dev)
-        slab.exchange_halos([mview], HALO, periodic=False, dim=0)
+    if peer:
+        slab.hyp2d_attach_peers(sim)
+    resync()
 
     def barrier():
         if world > 1:
@@ -272,10 +281,8 @@ def run_product(a):
 
         def frame():
             h2.check(h2._upload(sim._handle, in_ptrs, C.c_void_p(0)))
-            if world > 1:
-                advance(a.steps_per_frame)
-            else:
-                sim.step(a.steps_per_frame)
+            resync()
+            advance(a.steps_per_frame)
             h2.check(h2._download(sim._handle, out_ptrs, C.c_void_p(0)))
 
         for _ in range(3):
@@ -312,9 +319,9 @@ def run_product(a):
             "dtype": a.dtype, "data": "synthetic",
             "config": {"workload": f"tau_hypersonic_cuda {W}x{H} {a.dtype}: k_init state developed "
                                    f"for {a.develop} steps, then timed",
-                       "grid": [W, H], "slab_rows_per_gpu": hl, "parallelism": f"y-slab x{world}",
+                       "grid": [W, H], "slab_rows_per_gpu": hl, "parallelism": f"y-slab x{world}" + (f" ({a.exchange} halo exchange)" if world > 1 else ""),
                        "cache": "state (2 x 268 MB) larger than L2 (126 MB): no flush needed",
-                       "seg_rows": a.seg_rows or 64},
+                       "seg_rows": sim.seg_rows},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": profile_traffic(),
                          "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
@@ -341,6 +348,11 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=10)
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--seg-rows", type=int, default=0)
+    ap.add_argument("--grid-w", type=int, default=0, help="experiments only (default 4096)")
+    ap.add_argument("--grid-h", type=int, default=0, help="experiments only (default 4096)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU halo exchange: device-side peer pushes over NVLink (default) or "
+                         "host-driven NCCL send/recv + all-reduce every step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()

@@ -50,6 +50,25 @@ struct Ctrl {          // device-resident step control (replaces the host dt log
   double maxspeed[3];  // rotating slots: step s reads [s%3], reduces into [(s+1)%3], clears [(s+2)%3]
   double sim_t;
   double dt_last;
+  unsigned int arrived[3];  // multi-GPU: cumulative count of peer "step done" signals per slot
+  unsigned int done_blocks; // CTAs of the running step kernel that have finished
+};
+
+// Multi-GPU (one process per GPU): peer-memory views of the two slab neighbours' output planes and
+// of every rank's Ctrl block, opened through CUDA IPC.  The step kernel pushes its boundary rows
+// straight into the neighbours' ghost rows over NVLink; two one-warp kernels around it implement
+// the all-reduce(max) of the wavespeed and the step barrier use system-scope atomics issued by the
+// step kernel itself (first thing: wait for the peers' previous step; last CTA out: signal).
+struct PeerCtrls {
+  Ctrl *ctrl[8];
+  int world, rank;
+};
+struct PeerPush {
+  void *up_out, *dn_out;       // neighbour planes for the CURRENT output buffer (or null)
+  size_t up_plane, dn_plane;   // their plane strides (elements)
+  int up_hl;                   // rows owned by the upper neighbour
+  unsigned int expected;       // value arrived[slot] must reach before this step may start
+  PeerCtrls pc;                // world == 1: single GPU or host-driven exchange
 };
 
 template <typename R>
@@ -357,7 +376,8 @@ template <typename R, bool USE_TMA>
 __global__ void __launch_bounds__(H2_WARPS * 32)
 hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *__restrict__ Uin,
            R *__restrict__ Uout, const uint8_t *__restrict__ mask,
-           const uint8_t *__restrict__ segmask, Ctrl *__restrict__ ctrl, int step_slot) {
+           const uint8_t *__restrict__ segmask, Ctrl *__restrict__ ctrl, int step_slot,
+           const PeerPush peer) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -368,8 +388,26 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
                    warp * H2_NS;
   Ring<R> ring{ring_base};
 
+  // ---- multi-GPU step barrier: every peer must have finished the previous step (their boundary
+  // rows are in our ghost rows and their max wavespeed is folded into our slot) ----------------
+  // Only CTAs that can be resident in the first wave poll (with an acquire load, no fence): a
+  // later CTA cannot start before one of them has finished, i.e. after the flag was observed.
+  if (peer.pc.world > 1 && blockIdx.x < 148 * 16) {
+    if (threadIdx.x == 0) {
+      const unsigned int *a = &ctrl->arrived[step_slot];
+      unsigned ns = 64, v;
+      for (;;) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
+        if (v >= peer.expected) break;
+        __nanosleep(ns);
+        if (ns < 1024) ns *= 2;
+      }
+    }
+    __syncthreads();
+  }
+
   // ---- dt from the device-resident max wavespeed (host rule :1852-1869, evaluated in fp64) ----
-  double maxs = ctrl->maxspeed[step_slot];
+  double maxs = *reinterpret_cast<volatile double *>(&ctrl->maxspeed[step_slot]);
   if (!isfinite(maxs) || maxs < 1e-12) maxs = 1e-12;
   const double dt_conv = P.cfl * 1.0 / maxs;
   double dt_diff = dt_conv;
@@ -383,8 +421,9 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
     ctrl->maxspeed[(step_slot + 2) % 3] = 1e-12;
   }
 
+  bool pushed = false;  // this thread stored into a neighbour GPU's ghost rows
   const int item = blockIdx.x * H2_WARPS + warp;
-  if (item >= P.nstrips * P.nsegs) return;
+  if (item < P.nstrips * P.nsegs) {
   const int strip = item % P.nstrips;
   const int seg = item / P.nstrips;
   const int W = P.W;
@@ -657,6 +696,25 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
           Uout[PL + o] = Un.mx;
           Uout[2 * PL + o] = Un.my;
           Uout[3 * PL + o] = Un.E;
+          // multi-GPU: push boundary rows into the slab neighbours' ghost rows (peer memory)
+          if (peer.up_out != nullptr && r < H2_GHOST) {
+            pushed = true;
+            R *o_up = static_cast<R *>(peer.up_out);
+            const size_t og = (size_t)(peer.up_hl + H2_GHOST + r) * W + x;
+            o_up[og] = Un.rho;
+            o_up[peer.up_plane + og] = Un.mx;
+            o_up[2 * peer.up_plane + og] = Un.my;
+            o_up[3 * peer.up_plane + og] = Un.E;
+          }
+          if (peer.dn_out != nullptr && r >= P.H_local - H2_GHOST) {
+            pushed = true;
+            R *o_dn = static_cast<R *>(peer.dn_out);
+            const size_t og = (size_t)(r - (P.H_local - H2_GHOST)) * W + x;
+            o_dn[og] = Un.rho;
+            o_dn[peer.dn_plane + og] = Un.mx;
+            o_dn[2 * peer.dn_plane + og] = Un.my;
+            o_dn[3 * peer.dn_plane + og] = Un.E;
+          }
           // keep the y-clamp ghost rows of the output planes current (global edges only)
           const int gy = P.y_begin + r;
           if (gy == 0 || gy == P.H_global - 1) {
@@ -710,6 +768,33 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
 
   wmax = tau::warp_max(wmax);
   if (lane == 0 && wmax > R(0)) tau::atomic_max_nonneg(&ctrl->maxspeed[(step_slot + 1) % 3], (double)wmax);
+  }  // item < nitems
+
+  // ---- multi-GPU: the last CTA out folds this rank's max wavespeed into every peer's slot for the
+  // next step and then signals "step done" (release order: data, fence, flag) -------------------
+  if (peer.pc.world > 1) {
+    __shared__ int s_last;
+    if (pushed) __threadfence_system();  // peer stores (ghost-row pushes) before the CTA count
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = (atomicAdd(&ctrl->done_blocks, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const int next = (step_slot + 1) % 3;
+      if (threadIdx.x == 0) ctrl->done_blocks = 0;
+      const int p = threadIdx.x;
+      if (p < peer.pc.world && p != peer.pc.rank) {
+        const double m = *reinterpret_cast<volatile double *>(&ctrl->maxspeed[next]);
+        atomicMax_system(reinterpret_cast<unsigned long long *>(&peer.pc.ctrl[p]->maxspeed[next]),
+                         static_cast<unsigned long long>(__double_as_longlong(m)));
+        __threadfence_system();
+        atomicAdd_system(&peer.pc.ctrl[p]->arrived[next], 1u);
+      }
+    }
+  }
 }
 
 // One flag per marching work item (strip x segment): does the staged window of that item contain a
@@ -850,6 +935,12 @@ struct tau_hyp2d {
   bool own_stream;
   void *U[2];        // 4 planes each, contiguous, incl. ghost rows
   uint8_t *mask;
+  // multi-GPU peer views (CUDA IPC); null/0 when single-GPU or exchange is host-driven
+  void *peer_up[2], *peer_dn[2];
+  int peer_up_hl, peer_dn_hl;
+  PeerCtrls pctrl;
+  bool peers_attached;
+  unsigned int peer_epoch[3];  // how many times each barrier slot has been consumed
   uint8_t *segmask;      // per work-item "touches the body" flags (device)
   size_t segmask_cap;
   bool segmask_dirty;
@@ -859,6 +950,7 @@ struct tau_hyp2d {
   long long steps, launches;
   bool speed_valid;  // ctrl->maxspeed[steps%3] holds the max wavespeed of the current state
   int seg_rows;
+  bool seg_auto;         // seg_rows chosen by the wave model below (not set by the caller)
   cudaEvent_t ev0, ev1;
   bool timed;
   size_t plane_elems;
@@ -947,12 +1039,20 @@ int launch_init(tau_hyp2d *h) {
   return TAU_OK;
 }
 
+// Segment height: shorter segments balance the SMs better (more, smaller work items) but pay
+// the two warm-up rows more often.  Measured on B200 (4096 columns): 24 rows is best at 4096 rows
+// per GPU, 16 at 2048, 8 at <= 1024 (profiles/hyp2d_seg_rows_r1.md).
+template <typename R>
+int choose_seg_rows(tau_hyp2d *h, size_t) {
+  int seg = h->h_local / 128;
+  if (seg < 8) seg = 8;
+  if (seg > 24) seg = 24;
+  return seg;
+}
+
 template <typename R>
 int launch_steps(tau_hyp2d *h, int nsteps) {
-  Params<R> P = make_params<R>(h);
   const size_t smem = step_smem_bytes<R>();
-  const int items = P.nstrips * P.nsegs;
-  const int grid = (items + H2_WARPS - 1) / H2_WARPS;
   static bool attr_done[2][2] = {{false, false}, {false, false}};
   auto kern_tma = hyp2d_step<R, true>;
   auto kern_gen = hyp2d_step<R, false>;
@@ -962,6 +1062,17 @@ int launch_steps(tau_hyp2d *h, int nsteps) {
     TAU_CUDA(cudaFuncSetAttribute(kern_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done[ti][0] = true;
   }
+  if (h->seg_auto) {
+    const int seg = choose_seg_rows<R>(h, smem);
+    if (seg != h->seg_rows) {
+      h->seg_rows = seg;
+      h->segmask_dirty = true;
+    }
+    h->seg_auto = false;  // decided once per handle
+  }
+  Params<R> P = make_params<R>(h);
+  const int items = P.nstrips * P.nsegs;
+  const int grid = (items + H2_WARPS - 1) / H2_WARPS;
   if (h->segmask_dirty) {
     if (h->segmask_cap < (size_t)items) {
       if (h->segmask) TAU_CUDA(cudaFree(h->segmask));
@@ -975,12 +1086,24 @@ int launch_steps(tau_hyp2d *h, int nsteps) {
   for (int s = 0; s < nsteps; ++s) {
     const int a = h->cur, b = a ^ 1;
     const int slot = (int)(h->steps % 3);
+    PeerPush peer;
+    memset(&peer, 0, sizeof(peer));
+    peer.pc.world = 1;
+    if (h->peers_attached) {
+      peer.up_out = h->peer_up[b];
+      peer.dn_out = h->peer_dn[b];
+      peer.up_hl = h->peer_up_hl;
+      peer.up_plane = (size_t)h->W * (h->peer_up_hl + 2 * H2_GHOST);
+      peer.dn_plane = (size_t)h->W * (h->peer_dn_hl + 2 * H2_GHOST);
+      peer.pc = h->pctrl;
+      peer.expected = ++h->peer_epoch[slot] * (unsigned)(h->pctrl.world - 1);
+    }
     if (h->use_tma)
       kern_tma<<<grid, H2_WARPS * 32, smem, h->stream>>>(h->tm[a], P, (const R *)h->U[a], (R *)h->U[b],
-                                                         h->mask, h->segmask, h->ctrl, slot);
+                                                         h->mask, h->segmask, h->ctrl, slot, peer);
     else
       kern_gen<<<grid, H2_WARPS * 32, smem, h->stream>>>(h->tm[a], P, (const R *)h->U[a], (R *)h->U[b],
-                                                         h->mask, h->segmask, h->ctrl, slot);
+                                                         h->mask, h->segmask, h->ctrl, slot, peer);
     h->launches++;
     h->cur = b;
     h->steps++;
@@ -1077,13 +1200,23 @@ int tau_hyp2d_create(const tau_hyp2d_config *cfg, int W, int H, int dtype, int d
   h->launches = 0;
   h->speed_valid = false;
   h->timed = false;
+  h->peer_up[0] = h->peer_up[1] = h->peer_dn[0] = h->peer_dn[1] = nullptr;
+  h->peer_up_hl = h->peer_dn_hl = 0;
+  memset(&h->pctrl, 0, sizeof(h->pctrl));
+  h->pctrl.world = 1;
+  h->peers_attached = false;
+  h->peer_epoch[0] = h->peer_epoch[1] = h->peer_epoch[2] = 0;
   h->segmask = nullptr;
   h->segmask_cap = 0;
   h->segmask_dirty = true;
   h->seg_rows = 64;
+  h->seg_auto = true;
   if (const char *e = getenv("TAU_HYP2D_SEG_ROWS")) {
     int v = atoi(e);
-    if (v >= 4) h->seg_rows = v;
+    if (v >= 4) {
+      h->seg_rows = v;
+      h->seg_auto = false;
+    }
   }
   if (stream) {
     h->stream = (cudaStream_t)stream;
@@ -1167,9 +1300,9 @@ int tau_hyp2d_upload(tau_hyp2d *h, const void *const planes[4], const uint8_t *m
 int tau_hyp2d_step(tau_hyp2d *h, int nsteps) {
   TAU_REQUIRE(h, "tau_hyp2d_step: null handle");
   TAU_REQUIRE(nsteps >= 0, "tau_hyp2d_step: nsteps must be >= 0");
-  TAU_REQUIRE(!(h->slab && nsteps > 1),
-              "tau_hyp2d_step: a slab handle advances one step per call (ghost rows and the max "
-              "wavespeed must be exchanged in between)");
+  TAU_REQUIRE(!(h->slab && !h->peers_attached && nsteps > 1),
+              "tau_hyp2d_step: a slab handle without attached peers advances one step per call "
+              "(ghost rows and the max wavespeed must be exchanged in between)");
   TAU_REQUIRE(h->speed_valid, "tau_hyp2d_step: no state (call tau_hyp2d_init or tau_hyp2d_upload)");
   TAU_CUDA(cudaSetDevice(h->device));
   TAU_CUDA(cudaEventRecord(h->ev0, h->stream));
@@ -1219,13 +1352,75 @@ int tau_hyp2d_device_state(tau_hyp2d *h, void **planes, uint8_t **mask, double *
   return TAU_OK;
 }
 
+// ---- multi-GPU peer plumbing (CUDA IPC; one process per GPU on one box) ----------------------
+int tau_hyp2d_ipc_export(tau_hyp2d *h, void *out, size_t out_bytes) {
+  TAU_REQUIRE(h && out, "tau_hyp2d_ipc_export: null argument");
+  TAU_REQUIRE(out_bytes >= 3 * sizeof(cudaIpcMemHandle_t),
+              "tau_hyp2d_ipc_export: buffer must hold %zu bytes", 3 * sizeof(cudaIpcMemHandle_t));
+  TAU_CUDA(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t *hd = static_cast<cudaIpcMemHandle_t *>(out);
+  TAU_CUDA(cudaIpcGetMemHandle(&hd[0], h->U[0]));
+  TAU_CUDA(cudaIpcGetMemHandle(&hd[1], h->U[1]));
+  TAU_CUDA(cudaIpcGetMemHandle(&hd[2], h->ctrl));
+  return TAU_OK;
+}
+
+int tau_hyp2d_ipc_attach(tau_hyp2d *h, int rank, int world, const void *all_handles,
+                         const int *h_locals) {
+  TAU_REQUIRE(h && all_handles && h_locals, "tau_hyp2d_ipc_attach: null argument");
+  TAU_REQUIRE(world >= 2 && world <= 8 && rank >= 0 && rank < world,
+              "tau_hyp2d_ipc_attach: need 2 <= world <= 8 (got rank %d of %d)", rank, world);
+  TAU_REQUIRE(h_locals[rank] == h->h_local, "tau_hyp2d_ipc_attach: h_locals[rank] mismatch");
+  TAU_CUDA(cudaSetDevice(h->device));
+  const cudaIpcMemHandle_t *hd = static_cast<const cudaIpcMemHandle_t *>(all_handles);
+  h->pctrl.world = world;
+  h->pctrl.rank = rank;
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) {
+      h->pctrl.ctrl[p] = h->ctrl;
+      continue;
+    }
+    void *ptr = nullptr;
+    TAU_CUDA(cudaIpcOpenMemHandle(&ptr, hd[3 * p + 2], cudaIpcMemLazyEnablePeerAccess));
+    h->pctrl.ctrl[p] = static_cast<Ctrl *>(ptr);
+  }
+  // y is clamped, not periodic: the slabs form a chain
+  if (rank > 0) {
+    for (int b = 0; b < 2; ++b)
+      TAU_CUDA(cudaIpcOpenMemHandle(&h->peer_up[b], hd[3 * (rank - 1) + b], cudaIpcMemLazyEnablePeerAccess));
+    h->peer_up_hl = h_locals[rank - 1];
+  }
+  if (rank < world - 1) {
+    for (int b = 0; b < 2; ++b)
+      TAU_CUDA(cudaIpcOpenMemHandle(&h->peer_dn[b], hd[3 * (rank + 1) + b], cudaIpcMemLazyEnablePeerAccess));
+    h->peer_dn_hl = h_locals[rank + 1];
+  }
+  h->peers_attached = true;
+  return TAU_OK;
+}
+
+// Call once after the caller has exchanged the ghost rows of the current state and all-reduced
+// the wavespeed slot on the host side (init / upload): arms the first device-side barrier.
+int tau_hyp2d_peers_ready(tau_hyp2d *h) {
+  TAU_REQUIRE(h && h->peers_attached, "tau_hyp2d_peers_ready: no peers attached");
+  TAU_CUDA(cudaSetDevice(h->device));
+  unsigned int a[4] = {0, 0, 0, 0};  // arrived[3] + done_blocks
+  a[h->steps % 3] = (unsigned)(h->pctrl.world - 1);
+  h->peer_epoch[0] = h->peer_epoch[1] = h->peer_epoch[2] = 0;
+  TAU_CUDA(cudaMemcpyAsync(h->ctrl->arrived, a, sizeof(a), cudaMemcpyHostToDevice, h->stream));
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  return TAU_OK;
+}
+
 int tau_hyp2d_set_seg_rows(tau_hyp2d *h, int rows) {
   TAU_REQUIRE(h && rows >= 4, "tau_hyp2d_set_seg_rows: rows must be >= 4");
   h->seg_rows = rows;
+  h->seg_auto = false;
   h->segmask_dirty = true;
   return TAU_OK;
 }
 
+int tau_hyp2d_get_seg_rows(tau_hyp2d *h) { return h ? h->seg_rows : -1; }
 long long tau_hyp2d_steps_done(tau_hyp2d *h) { return h ? h->steps : -1; }
 long long tau_hyp2d_launch_count(tau_hyp2d *h) { return h ? h->launches : -1; }
 

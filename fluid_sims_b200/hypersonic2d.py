@@ -34,6 +34,11 @@ _sync = declare("tau_hyp2d_sync", [_h])
 _devstate = declare("tau_hyp2d_device_state", [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                                C.POINTER(C.c_void_p)])
 _set_seg = declare("tau_hyp2d_set_seg_rows", [_h, C.c_int])
+_get_seg = declare("tau_hyp2d_get_seg_rows", [_h])
+_ipc_export = declare("tau_hyp2d_ipc_export", [_h, C.c_void_p, C.c_size_t])
+_ipc_attach = declare("tau_hyp2d_ipc_attach", [_h, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)])
+_peers_ready = declare("tau_hyp2d_peers_ready", [_h])
+IPC_BYTES = 3 * 64
 _steps_done = declare("tau_hyp2d_steps_done", [_h], C.c_longlong)
 _launches = declare("tau_hyp2d_launch_count", [_h], C.c_longlong)
 _last_ms = declare("tau_hyp2d_last_step_ms", [_h, C.POINTER(C.c_float)])
@@ -140,9 +145,30 @@ class Hypersonic2D:
         check(_devstate(self._handle, C.byref(p), C.byref(m), C.byref(s)))
         return p.value, m.value, s.value
 
+    # ---- multi-GPU peer plumbing (CUDA IPC) -------------------------------------------------
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(IPC_BYTES)
+        check(_ipc_export(self._handle, buf, IPC_BYTES))
+        return buf.raw
+
+    def ipc_attach(self, rank: int, world: int, handles, h_locals):
+        blob = b"".join(handles)
+        assert len(blob) == world * IPC_BYTES
+        hl = (C.c_int * world)(*h_locals)
+        check(_ipc_attach(self._handle, rank, world, blob, hl))
+        return self
+
+    def peers_ready(self):
+        check(_peers_ready(self._handle))
+        return self
+
     def set_seg_rows(self, rows: int):
         check(_set_seg(self._handle, rows))
         return self
+
+    @property
+    def seg_rows(self) -> int:
+        return int(_get_seg(self._handle))
 
     @property
     def steps_done(self) -> int:

@@ -102,3 +102,33 @@ def allreduce_max_(t: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return t
+
+
+def hyp2d_attach_peers(sim, group=None) -> None:
+    """All-gather the CUDA-IPC handles of every rank's planes/control block and attach them, so that
+    the 2-D hypersonic step kernel pushes its boundary rows straight into the neighbours' ghost rows
+    (NVLink peer stores) and the wavespeed all-reduce + step barrier run on the device."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    mine = (sim.ipc_export(), sim.h_local)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine, group=group)
+    sim.ipc_attach(rank, world, [g[0] for g in gathered], [g[1] for g in gathered])
+
+
+def hyp2d_sync_state(sim, group=None) -> None:
+    """Host-driven (NCCL) exchange of the CURRENT state's ghost rows, the static mask's ghost rows
+    and the max-wavespeed scalar — needed once after init()/upload(); arms the device barrier when
+    peers are attached."""
+    from .hypersonic2d import HALO
+    pp, mp, sp = sim.device_state()
+    tdt = torch.float32 if sim.dtype == "f32" else torch.float64
+    W, hl, dev = sim.cfg.W, sim.h_local, sim.device
+    planes = wrap_plane(pp, (4, hl + 2 * HALO, W), tdt, dev)
+    mask = wrap_plane(mp, (hl + 2 * HALO, W), torch.uint8, dev)
+    speed = wrap_plane(sp, (1,), torch.float64, dev)
+    exchange_halos([mask], HALO, periodic=False, group=group, dim=0)
+    exchange_halos([planes], HALO, periodic=False, group=group, dim=1)
+    dist.all_reduce(speed, op=dist.ReduceOp.MAX, group=group)
+    torch.cuda.synchronize()
+    dist.barrier(group=group)

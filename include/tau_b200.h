@@ -117,8 +117,20 @@ int tau_hyp2d_sync(tau_hyp2d *h);
  * starting at ghost row -2), the mask (same row layout) and the max-wavespeed scalar the next
  * step will read (all-reduce it with MAX across ranks before tau_hyp2d_step). */
 int tau_hyp2d_device_state(tau_hyp2d *h, void **planes, uint8_t **mask, double **maxspeed_slot);
+/* Multi-GPU without per-step host work (one process per GPU, one box): export CUDA-IPC handles of
+ * this handle's planes and control block (3 x 64 bytes), all-gather them across ranks, attach.
+ * Afterwards the step kernel pushes its boundary rows into the neighbours' ghost rows over NVLink
+ * and tau_hyp2d_step(h, n) may advance many steps per call; the wavespeed all-reduce and the step
+ * barrier run on the device.  After init/upload the caller exchanges ghost rows + the wavespeed
+ * once on the host side and calls tau_hyp2d_peers_ready(). */
+int tau_hyp2d_ipc_export(tau_hyp2d *h, void *out, size_t out_bytes);
+int tau_hyp2d_ipc_attach(tau_hyp2d *h, int rank, int world, const void *all_handles,
+                         const int *h_locals);
+int tau_hyp2d_peers_ready(tau_hyp2d *h);
 /* rows each warp marches per work item (tuning; --tile-by analogue of :1641-1685) */
 int tau_hyp2d_set_seg_rows(tau_hyp2d *h, int rows);
+/* the height in use (chosen by a wave model at the first step unless set explicitly) */
+int tau_hyp2d_get_seg_rows(tau_hyp2d *h);
 long long tau_hyp2d_steps_done(tau_hyp2d *h);
 long long tau_hyp2d_launch_count(tau_hyp2d *h);
 int tau_hyp2d_last_step_ms(tau_hyp2d *h, float *ms);

@@ -1,0 +1,772 @@
+// hypersonic3d.cu — 3-D compressible flow with vibrational relaxation (WENO5 + HLLC/HLL blend)
+// update path for sm_100a.  Replaces the per-step host sequence of the reference `tau3d`
+// (tau_hypersonic_3d_cuda.cu:1678-1712: host clock -> 4-byte H2D -> k_step -> 4-byte D2H -> host
+// d_tau controller -> 6 pointer swaps) and its k_step (:987-1359).
+//
+// What is restructured relative to the reference kernel:
+//   * every face flux is computed ONCE.  The reference evaluates 6 faces per cell (each face twice,
+//     once from either side; 72 WENO5 evaluations + 6 Riemann solves per cell).  Here a CTA decodes
+//     its 14x14x10 halo tile to primitives in shared memory (same tile as the reference), then its
+//     threads sweep the tile's 896 faces — ordered so that every warp works on one axis — and park
+//     the fluxes in shared memory; the cell update gathers its six.  3.5 faces per cell instead of 6.
+//   * the WENO5 nonlinear weights use one reciprocal per reconstruction instead of six IEEE
+//     divisions (algebraically identical: w_k = c_k prod_{j!=k} (eps+b_j)^2 / sum), the rest of the
+//     arithmetic keeps the reference's expression trees and its fast intrinsics (__expf/__logf).
+//   * the log-time clock, inflow ramp and d_tau controller (:1680-1704) live on the device: a
+//     one-thread controller kernel follows each step; no host synchronisation per step.
+//   * planes carry 3 ghost planes in z on either side so that z-slabs (multi-GPU ring) need no
+//     special casing; a single-GPU handle wraps the plane index instead.
+//
+// This solver is compute-bound by more than an order of magnitude (885 MUFU and
+// ~2e4 instructions per cell in the reference); the HBM roofline fraction is reported as measured.
+#include "common.cuh"
+#include "../../include/tau_b200.h"
+
+#include <math.h>
+#include <new>
+#include <vector>
+
+namespace {
+
+constexpr int T3_TX = 8, T3_TY = 8, T3_TZ = 4, T3_H = 3;
+constexpr int T3_SX = T3_TX + 2 * T3_H, T3_SY = T3_TY + 2 * T3_H, T3_SZ = T3_TZ + 2 * T3_H;
+constexpr int T3_SXY = T3_SX * T3_SY, T3_SVOL = T3_SXY * T3_SZ;
+constexpr int T3_THREADS = T3_TX * T3_TY * T3_TZ;
+constexpr int T3_NFX = (T3_TX + 1) * T3_TY * T3_TZ;  // 288 = 9 warps
+constexpr int T3_NFY = T3_TX * (T3_TY + 1) * T3_TZ;  // 288
+constexpr int T3_NFZ = T3_TX * T3_TY * (T3_TZ + 1);  // 320
+constexpr int T3_NF = T3_NFX + T3_NFY + T3_NFZ;
+static_assert(T3_NFX % 32 == 0 && T3_NFY % 32 == 0 && T3_NFZ % 32 == 0, "one axis per warp");
+
+constexpr float RHO_P_FLOOR = 1e-30f;  // tau_hypersonic_3d_cuda.cu:52-58
+constexpr float THERMAL_ENERGY_FLOOR = 1e-12f;
+constexpr float DENOM_EPS = 1e-12f;
+constexpr float NEWTON_TEMP_FLOOR = 1e-6f;
+constexpr float WENO_EPS = 1e-6f;
+constexpr float TAU_VIB_MIN = 1e-9f;
+
+struct Par {  // struct Params :21-42 + slab geometry
+  int nx, ny, nz;        // GLOBAL grid
+  float dx, dy, dz, cfl, u_ref, R, gamma_floor, Twall, tau_vib, theta_v;
+  float sdf_cx, sdf_cy, sdf_cz, sdf_r;
+  float inflow_r, inflow_p, inflow_u, inflow_v, inflow_w;
+  int sponge_n;
+  float sponge_strength;
+  int sponge_out_n;
+  float sponge_out_strength;
+  int z_begin, nz_local, slab;
+  size_t plane;  // elements per plane = nx*ny*(nz_local+6)
+};
+
+struct Clock {      // device-resident step control (:1635-1636, :1680-1704)
+  float t[2], d_tau[2];
+  float dt_last, maxs_last;
+  float maxs;       // accumulated by the running step (non-negative: integer atomicMax)
+  int pad;
+};
+
+struct Q { float r, u, v, w, p, ev; };
+struct C6 { float r, mx, my, mz, Et, Ev; };
+
+__device__ __forceinline__ float clampf(float x, float a, float b) { return fminf(fmaxf(x, a), b); }
+__device__ __forceinline__ float signed_denom_guard(float x) {  // :147
+  return copysignf(fmaxf(fabsf(x), DENOM_EPS), x);
+}
+__device__ __forceinline__ int wrapi(int i, int n) {  // :156
+  i %= n;
+  return (i < 0) ? i + n : i;
+}
+__device__ __forceinline__ float asinhf_dev(float x) {  // :121-125
+  float ax = fabsf(x);
+  return copysignf(logf(ax + sqrtf(ax * ax + 1.0f)), x);
+}
+__device__ __forceinline__ float evib_eq(const Par &P, float T) {  // :206-211
+  float a = P.theta_v / fmaxf(T, NEWTON_TEMP_FLOOR);
+  float ea = __expf(a);
+  float denom = fmaxf(ea - 1.f, NEWTON_TEMP_FLOOR);
+  return (P.R * P.theta_v) / denom;
+}
+__device__ __forceinline__ Q decode(const Par &P, float xi, float phx, float phy, float phz,
+                                    float lam, float zet) {  // log_to_prim_fast :213-225
+  Q q;
+  q.r = __expf(xi);
+  q.u = P.u_ref * sinhf(phx);
+  q.v = P.u_ref * sinhf(phy);
+  q.w = P.u_ref * sinhf(phz);
+  q.p = __expf(lam);
+  q.ev = __expf(zet);
+  return q;
+}
+__device__ __forceinline__ C6 prim_to_cons(const Par &P, const Q &q) {  // :234-245
+  C6 U;
+  U.r = q.r;
+  U.mx = q.r * q.u;
+  U.my = q.r * q.v;
+  U.mz = q.r * q.w;
+  float ke = 0.5f * (q.u * q.u + q.v * q.v + q.w * q.w);
+  float e_th = q.p / fmaxf((P.gamma_floor - 1.f) * q.r, RHO_P_FLOOR);
+  U.Ev = q.r * q.ev;
+  U.Et = q.r * (ke + e_th + q.ev);
+  return U;
+}
+__device__ __forceinline__ float soundspeed(const Par &P, const Q &q) {  // :264
+  return sqrtf(fmaxf(P.gamma_floor * q.p / q.r, DENOM_EPS));
+}
+__device__ __forceinline__ C6 axis_flux(const Par &P, const Q &q, int axis) {  // :268-308
+  C6 F;
+  float un = axis == 0 ? q.u : (axis == 1 ? q.v : q.w);
+  float H = (q.p / q.r) + (0.5f * (q.u * q.u + q.v * q.v + q.w * q.w) + q.ev) +
+            q.p / fmaxf((P.gamma_floor - 1.f) * q.r, RHO_P_FLOOR);
+  F.r = q.r * un;
+  F.mx = q.r * q.u * un + (axis == 0 ? q.p : 0.f);
+  F.my = q.r * q.v * un + (axis == 1 ? q.p : 0.f);
+  F.mz = q.r * q.w * un + (axis == 2 ? q.p : 0.f);
+  F.Et = q.r * H * un;
+  F.Ev = q.r * q.ev * un;
+  return F;
+}
+__device__ __forceinline__ float entropy_fix_speed(float s, float a_ref) {  // :366-374
+  float d = 0.1f * a_ref, as = fabsf(s);
+  float sgn = (s >= 0.f) ? 1.f : -1.f;
+  float sm = 0.5f * (as * as / fmaxf(d, DENOM_EPS) + d);
+  return (as >= d) ? s : sgn * sm;
+}
+
+// hllc_flux_axis :383-460 (HLLC blended towards HLL by shock sensor x alignment)
+__device__ __forceinline__ C6 hllc_flux_axis(const Par &P, const Q &L, const Q &R, int axis) {
+  float aL = soundspeed(P, L), aR = soundspeed(P, R);
+  float unL = axis == 0 ? L.u : (axis == 1 ? L.v : L.w);
+  float unR = axis == 0 ? R.u : (axis == 1 ? R.v : R.w);
+  float sL = fminf(unL - aL, unR - aR), sR = fmaxf(unL + aL, unR + aR);
+  float aRef = fmaxf(aL, aR);
+  sL = entropy_fix_speed(sL, aRef);
+  sR = entropy_fix_speed(sR, aRef);
+  C6 FL = axis_flux(P, L, axis);
+  if (__all_sync(__activemask(), sL >= 0.f)) return FL;  // supersonic to the right, whole warp
+  C6 UL = prim_to_cons(P, L), UR = prim_to_cons(P, R);
+  C6 FR = axis_flux(P, R, axis);
+  float rL = L.r, rR = R.r, pL = L.p, pR = R.p;
+  float denom = signed_denom_guard(rL * (sL - unL) - rR * (sR - unR));
+  float sM = (pR - pL + rL * unL * (sL - unL) - rR * unR * (sR - unR)) / denom;
+  float pStarL = pL + rL * (sL - unL) * (sM - unL);
+  float pStarR = pR + rR * (sR - unR) * (sM - unR);
+  float pStar = 0.5f * (pStarL + pStarR);
+  float vCarb;  // axis_crossflow_speed :318-325
+  if (axis == 0) vCarb = (fabsf(L.v) + fabsf(R.v) + fabsf(L.w) + fabsf(R.w)) * 0.5f;
+  else if (axis == 1) vCarb = (fabsf(L.u) + fabsf(R.u) + fabsf(L.w) + fabsf(R.w)) * 0.5f;
+  else vCarb = (fabsf(L.u) + fabsf(R.u) + fabsf(L.v) + fabsf(R.v)) * 0.5f;
+  float align = clampf(1.f - vCarb / fmaxf(aRef, DENOM_EPS), 0.f, 1.f);
+  float dp = fabsf(R.p - L.p) / fmaxf(R.p + L.p, DENOM_EPS);  // shock_sensor :376-381
+  float dr = fabsf(R.r - L.r) / fmaxf(R.r + L.r, DENOM_EPS);
+  float alpha = clampf(5.f * (0.5f * (dp + dr)), 0.f, 1.f) * align;
+  float inv_hll = 1.f / signed_denom_guard(sR - sL), ss = sL * sR;
+  C6 FHLL;
+  FHLL.r = ((FL.r * sR - FR.r * sL) + (UR.r - UL.r) * ss) * inv_hll;
+  FHLL.mx = ((FL.mx * sR - FR.mx * sL) + (UR.mx - UL.mx) * ss) * inv_hll;
+  FHLL.my = ((FL.my * sR - FR.my * sL) + (UR.my - UL.my) * ss) * inv_hll;
+  FHLL.mz = ((FL.mz * sR - FR.mz * sL) + (UR.mz - UL.mz) * ss) * inv_hll;
+  FHLL.Et = ((FL.Et * sR - FR.Et * sL) + (UR.Et - UL.Et) * ss) * inv_hll;
+  FHLL.Ev = ((FL.Ev * sR - FR.Ev * sL) + (UR.Ev - UL.Ev) * ss) * inv_hll;
+  const bool left = sM >= 0.f;
+  const Q &K = left ? L : R;
+  const C6 &UK = left ? UL : UR;
+  const C6 &FK = left ? FL : FR;
+  float sK = left ? sL : sR, unK = left ? unL : unR;
+  float starDenom = signed_denom_guard(sK - sM);
+  float rStar = K.r * (sK - unK) / starDenom;
+  float EStar = ((sK - unK) * UK.Et - K.p * unK + pStar * sM) / starDenom;
+  float EvStar = UK.Ev * (sK - unK) / starDenom;
+  C6 US;  // fill_star_momentum :335-350
+  US.r = rStar;
+  US.mx = rStar * (axis == 0 ? sM : K.u);
+  US.my = rStar * (axis == 1 ? sM : K.v);
+  US.mz = rStar * (axis == 2 ? sM : K.w);
+  US.Et = EStar;
+  US.Ev = EvStar;
+  const float om = 1.f - alpha;
+  C6 F;
+  F.r = (FK.r + (US.r - UK.r) * sK) * om + FHLL.r * alpha;
+  F.mx = (FK.mx + (US.mx - UK.mx) * sK) * om + FHLL.mx * alpha;
+  F.my = (FK.my + (US.my - UK.my) * sK) * om + FHLL.my * alpha;
+  F.mz = (FK.mz + (US.mz - UK.mz) * sK) * om + FHLL.mz * alpha;
+  F.Et = (FK.Et + (US.Et - UK.Et) * sK) * om + FHLL.Et * alpha;
+  F.Ev = (FK.Ev + (US.Ev - UK.Ev) * sK) * om + FHLL.Ev * alpha;
+  if (sL >= 0.f) F = FL;        // :400-403
+  else if (sR <= 0.f) F = FR;
+  return F;
+}
+
+// weno5_left :534-558 with the three weight divisions and the three normalisations folded into
+// one reciprocal: w_k = a_k / sum a_j with a_k = c_k / e_k^2  ==  c_k prod_{j != k} e_j^2 / (...).
+__device__ __forceinline__ float weno5_left(float v0, float v1, float v2, float v3, float v4) {
+  float p0 = (2.f * v0 - 7.f * v1 + 11.f * v2) * (1.f / 6.f);
+  float p1 = (-1.f * v1 + 5.f * v2 + 2.f * v3) * (1.f / 6.f);
+  float p2 = (2.f * v2 + 5.f * v3 - 1.f * v4) * (1.f / 6.f);
+  float t0 = v0 - 2.f * v1 + v2, u0 = v0 - 4.f * v1 + 3.f * v2;
+  float t1 = v1 - 2.f * v2 + v3, u1 = v1 - v3;
+  float t2 = v2 - 2.f * v3 + v4, u2 = 3.f * v2 - 4.f * v3 + v4;
+  float b0 = (13.f / 12.f) * t0 * t0 + 0.25f * u0 * u0;
+  float b1 = (13.f / 12.f) * t1 * t1 + 0.25f * u1 * u1;
+  float b2 = (13.f / 12.f) * t2 * t2 + 0.25f * u2 * u2;
+  float e0 = (WENO_EPS + b0) * (WENO_EPS + b0);
+  float e1 = (WENO_EPS + b1) * (WENO_EPS + b1);
+  float e2 = (WENO_EPS + b2) * (WENO_EPS + b2);
+  float n0 = 0.1f * (e1 * e2), n1 = 0.6f * (e0 * e2), n2 = 0.3f * (e0 * e1);
+  return (n0 * p0 + n1 * p1 + n2 * p2) / (n0 + n1 + n2);
+}
+__device__ __forceinline__ void prim_floor_fast(Q &q) {  // :565-571
+  q.r = fmaxf(q.r, RHO_P_FLOOR);
+  q.p = fmaxf(q.p, RHO_P_FLOOR);
+  q.ev = fmaxf(q.ev, 0.f);
+}
+__device__ __forceinline__ Q inflow_prim(const Par &P) {  // :611-622
+  Q q;
+  q.r = fmaxf(P.inflow_r, RHO_P_FLOOR);
+  q.u = P.inflow_u;
+  q.v = P.inflow_v;
+  q.w = P.inflow_w;
+  q.p = fmaxf(P.inflow_p, RHO_P_FLOOR);
+  q.ev = evib_eq(P, q.p / (q.r * P.R));
+  return q;
+}
+__device__ __forceinline__ void apply_wall(const Par &P, Q &q) {  // :511-521
+  float p_keep = fmaxf(q.p, RHO_P_FLOOR);
+  q.u = q.v = q.w = 0.f;
+  q.p = p_keep;
+  q.r = fmaxf(q.p / (P.R * fmaxf(P.Twall, NEWTON_TEMP_FLOOR)), RHO_P_FLOOR);
+  q.ev = evib_eq(P, P.Twall);
+}
+__device__ __forceinline__ float sdf_sphere(const Par &P, float x, float y, float z) {  // :173-178
+  float dx = x - P.sdf_cx, dy = y - P.sdf_cy, dz = z - P.sdf_cz;
+  return sqrtf(dx * dx + dy * dy + dz * dz) - P.sdf_r;
+}
+
+// plane index (incl. the 3 ghost planes) of local plane lz: slabs read real ghost planes, a
+// single-GPU handle wraps (z is periodic, :1031)
+__device__ __forceinline__ int zplane(const Par &P, int lz) {
+  return (P.slab ? min(max(lz, -T3_H), P.nz_local + T3_H - 1) : wrapi(lz, P.nz_local)) + T3_H;
+}
+
+__global__ void __launch_bounds__(T3_THREADS)
+hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out,
+           const uint8_t *__restrict__ solid, Clock *__restrict__ clk, int slot) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  float *s_q = reinterpret_cast<float *>(smem);                 // [6][SVOL] r,u,v,w,p,ev
+  float *s_f = s_q + 6 * T3_SVOL;                                // [6][NF]   face fluxes
+  uint8_t *s_solid = reinterpret_cast<uint8_t *>(s_f + 6 * T3_NF);
+
+  // ---- log-time clock, :1680-1683 -------------------------------------------------------------
+  const float d_tau = clk->d_tau[slot];
+  const float t = clk->t[slot] * expf(d_tau);
+  const float dt = t * d_tau;
+  const float inflow_gain = fminf(fmaxf(t / 0.02f, 0.f), 1.f);
+
+  const int tid = (threadIdx.z * T3_TY + threadIdx.y) * T3_TX + threadIdx.x;
+  const int bx0 = blockIdx.x * T3_TX, by0 = blockIdx.y * T3_TY, bz0 = blockIdx.z * T3_TZ;
+  const size_t PL = P.plane;
+  const int nxy = P.nx * P.ny;
+
+  // ---- decode the halo tile to primitives (k_step :1019-1056) --------------------------------
+  for (int tt = tid; tt < T3_SVOL; tt += T3_THREADS) {
+    const int lz = tt / T3_SXY, rem = tt - lz * T3_SXY, ly = rem / T3_SX, lx = rem - ly * T3_SX;
+    const int gx = bx0 + lx - T3_H, gy = wrapi(by0 + ly - T3_H, P.ny), glz = bz0 + lz - T3_H;
+    const int pz = zplane(P, glz);
+    bool is_solid;
+    Q q;
+    if (gx < 0 || gx >= P.nx) {
+      // cell_is_solid outside the grid: analytic sphere (:186-188)
+      const int gz = wrapi(P.z_begin + glz, P.nz);
+      is_solid = sdf_sphere(P, (gx + 0.5f) * P.dx, (gy + 0.5f) * P.dy, (gz + 0.5f) * P.dz) < 0.f;
+      if (gx < 0) {
+        q = inflow_prim(P);
+      } else {  // outflow_prim_transmissive :691-722
+        const size_t gi = (size_t)pz * nxy + (size_t)gy * P.nx + (P.nx - 1);
+        q = decode(P, in[gi], in[PL + gi], in[2 * PL + gi], in[3 * PL + gi], in[4 * PL + gi],
+                   in[5 * PL + gi]);
+        const float aR = soundspeed(P, q), un = q.u;
+        if (un < 0.0f) {
+          q = inflow_prim(P);
+        } else {
+          if (un < aR) {
+            const float p_amb = fmaxf(P.inflow_p, RHO_P_FLOOR);
+            q.p = fmaxf(q.p + 0.05f * (p_amb - q.p), RHO_P_FLOOR);
+          }
+          prim_floor_fast(q);
+        }
+      }
+    } else {
+      const size_t gi = (size_t)pz * nxy + (size_t)gy * P.nx + gx;
+      is_solid = solid[gi] != 0;
+      q = decode(P, in[gi], in[PL + gi], in[2 * PL + gi], in[3 * PL + gi], in[4 * PL + gi],
+                 in[5 * PL + gi]);
+    }
+    if (is_solid) apply_wall(P, q);
+    s_q[tt] = q.r;
+    s_q[T3_SVOL + tt] = q.u;
+    s_q[2 * T3_SVOL + tt] = q.v;
+    s_q[3 * T3_SVOL + tt] = q.w;
+    s_q[4 * T3_SVOL + tt] = q.p;
+    s_q[5 * T3_SVOL + tt] = q.ev;
+    s_solid[tt] = is_solid ? 1 : 0;
+  }
+  __syncthreads();
+
+  auto load_q = [&](int j) {
+    return Q{s_q[j], s_q[T3_SVOL + j], s_q[2 * T3_SVOL + j], s_q[3 * T3_SVOL + j],
+             s_q[4 * T3_SVOL + j], s_q[5 * T3_SVOL + j]};
+  };
+
+  // ---- every face of the tile once (k_step :1113-1264 evaluates each from both sides) ---------
+  for (int f = tid; f < T3_NF; f += T3_THREADS) {
+    int axis, fx, fy, fz;  // (fx,fy,fz): tile coordinates of the cell on the PLUS side of the face
+    if (f < T3_NFX) {
+      axis = 0;
+      fx = f % (T3_TX + 1); fy = (f / (T3_TX + 1)) % T3_TY; fz = f / ((T3_TX + 1) * T3_TY);
+    } else if (f < T3_NFX + T3_NFY) {
+      const int g = f - T3_NFX;
+      axis = 1;
+      fx = g % T3_TX; fy = (g / T3_TX) % (T3_TY + 1); fz = g / (T3_TX * (T3_TY + 1));
+    } else {
+      const int g = f - T3_NFX - T3_NFY;
+      axis = 2;
+      fx = g % T3_TX; fy = (g / T3_TX) % T3_TY; fz = g / (T3_TX * T3_TY);
+    }
+    const int stride = axis == 0 ? 1 : (axis == 1 ? T3_SX : T3_SXY);
+    const int jb = ((fz + T3_H) * T3_SY + (fy + T3_H)) * T3_SX + (fx + T3_H);  // plus-side cell
+    const int ja = jb - stride;                                                // minus-side cell
+    const bool sa = s_solid[ja] != 0, sb = s_solid[jb] != 0;
+    Q L, R;
+    if (sa || sb) {  // face touches a solid: mirror state of the fluid side (:1125-1128, :1146-1149)
+      if (!sb) {
+        R = load_q(jb);
+        L = R;
+        if (axis == 0) L.u = -L.u; else if (axis == 1) L.v = -L.v; else L.w = -L.w;
+      } else {
+        L = load_q(ja);  // both solid: flux unused, any finite state will do
+        R = L;
+        if (axis == 0) R.u = -R.u; else if (axis == 1) R.v = -R.v; else R.w = -R.w;
+      }
+    } else {
+      const bool stencil_solid = s_solid[ja - 2 * stride] | s_solid[ja - stride] |
+                                 s_solid[jb + stride] | s_solid[jb + 2 * stride];
+      if (stencil_solid) {  // first order next to the body (:1129-1135)
+        L = load_q(ja);
+        R = load_q(jb);
+      } else {  // weno_face_from_6 :578-598 on cells a-2 .. b+2
+        const int j0 = ja - 2 * stride;
+#define WENO_FIELD(k, fld)                                                                       \
+  {                                                                                              \
+    const float *s = s_q + (k) * T3_SVOL + j0;                                                   \
+    const float v0 = s[0], v1 = s[stride], v2 = s[2 * stride], v3 = s[3 * stride],               \
+                v4 = s[4 * stride], v5 = s[5 * stride];                                          \
+    L.fld = weno5_left(v0, v1, v2, v3, v4);                                                      \
+    R.fld = weno5_left(v5, v4, v3, v2, v1);                                                      \
+  }
+        WENO_FIELD(0, r) WENO_FIELD(1, u) WENO_FIELD(2, v) WENO_FIELD(3, w) WENO_FIELD(4, p)
+        WENO_FIELD(5, ev)
+#undef WENO_FIELD
+      }
+      prim_floor_fast(L);
+      prim_floor_fast(R);
+    }
+    const C6 F = hllc_flux_axis(P, L, R, axis);
+    s_f[f] = F.r;
+    s_f[T3_NF + f] = F.mx;
+    s_f[2 * T3_NF + f] = F.my;
+    s_f[3 * T3_NF + f] = F.mz;
+    s_f[4 * T3_NF + f] = F.Et;
+    s_f[5 * T3_NF + f] = F.Ev;
+  }
+  __syncthreads();
+
+  // ---- conservative update, relaxation, sponges, re-encode (k_step :1266-1358) ----------------
+  const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y, lz = bz0 + threadIdx.z;
+  float ssum = 0.f;
+  if (x < P.nx && y < P.ny && lz < P.nz_local) {
+    const size_t i = (size_t)(lz + T3_H) * nxy + (size_t)y * P.nx + x;
+    if (solid[i]) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) out[k * PL + i] = in[k * PL + i];
+    } else {
+      const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
+      const int fxm = (tz * T3_TY + ty) * (T3_TX + 1) + tx, fxp = fxm + 1;
+      const int fym = T3_NFX + (tz * (T3_TY + 1) + ty) * T3_TX + tx, fyp = fym + T3_TX;
+      const int fzm = T3_NFX + T3_NFY + (tz * T3_TY + ty) * T3_TX + tx, fzp = fzm + T3_TX * T3_TY;
+      const int jc = ((tz + T3_H) * T3_SY + (ty + T3_H)) * T3_SX + (tx + T3_H);
+      const Q q0 = load_q(jc);
+      const C6 U0 = prim_to_cons(P, q0);
+      float U1[6];
+      const float U0a[6] = {U0.r, U0.mx, U0.my, U0.mz, U0.Et, U0.Ev};
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const float *sf = s_f + k * T3_NF;
+        const float dU = -((sf[fxp] - sf[fxm]) / P.dx + (sf[fyp] - sf[fym]) / P.dy +
+                           (sf[fzp] - sf[fzm]) / P.dz);
+        U1[k] = U0a[k] + dU * dt;
+      }
+      // cons_to_prim :247-262
+      Q q1;
+      q1.r = fmaxf(U1[0], RHO_P_FLOOR);
+      q1.u = U1[1] / q1.r;
+      q1.v = U1[2] / q1.r;
+      q1.w = U1[3] / q1.r;
+      {
+        const float ke = 0.5f * (q1.u * q1.u + q1.v * q1.v + q1.w * q1.w);
+        const float ev = fmaxf(U1[5] / q1.r, 0.f);
+        const float e_th = fmaxf(U1[4] / q1.r - ke - ev, THERMAL_ENERGY_FLOOR);
+        q1.p = fmaxf((P.gamma_floor - 1.f) * q1.r * e_th, RHO_P_FLOOR);
+        q1.ev = ev;
+      }
+      if (!isfinite(q1.r) || !isfinite(q1.p) || !isfinite(q1.u) || !isfinite(q1.v) ||
+          !isfinite(q1.w) || !isfinite(q1.ev) || q1.r <= 0.f || q1.p <= 0.f || q1.ev < 0.f)
+        q1 = inflow_prim(P);  // :1284-1289
+      float T1 = q1.p / (q1.r * P.R);
+      q1.ev = fmaxf(q1.ev + (evib_eq(P, T1) - q1.ev) * (dt / fmaxf(P.tau_vib, TAU_VIB_MIN)), 0.f);
+      const float tr = fmaxf(P.inflow_r, RHO_P_FLOOR), tp = fmaxf(P.inflow_p, RHO_P_FLOOR);
+      const int nsp = P.sponge_n > 0 ? P.sponge_n : 0;
+      if (nsp > 0 && x < nsp) {  // inflow sponge :1295-1318
+        float s = 1.0f - (float)x / (float)nsp;
+        s = fminf(fmaxf(s, 0.0f), 1.0f);
+        const float k = P.sponge_strength * (s * s);
+        const float tev = evib_eq(P, tp / (tr * P.R));
+        q1.r = fmaxf(q1.r + k * (tr - q1.r), RHO_P_FLOOR);
+        q1.p = fmaxf(q1.p + k * (tp - q1.p), RHO_P_FLOOR);
+        q1.u = q1.u + k * (inflow_gain * P.inflow_u - q1.u);
+        q1.v = q1.v + k * (inflow_gain * P.inflow_v - q1.v);
+        q1.w = q1.w + k * (inflow_gain * P.inflow_w - q1.w);
+        q1.ev = fmaxf(q1.ev + k * (tev - q1.ev), 0.f);
+      }
+      const int nspo = P.sponge_out_n > 0 ? P.sponge_out_n : 0;
+      if (nspo > 0 && x >= (P.nx - nspo)) {  // outflow sponge :1319-1343
+        float s = (float)(x - (P.nx - nspo)) / (float)nspo;
+        s = fminf(fmaxf(s, 0.0f), 1.0f);
+        const float k = P.sponge_out_strength * (s * s);
+        const float tev = evib_eq(P, tp / (tr * P.R));
+        q1.r = fmaxf(q1.r + k * (tr - q1.r), RHO_P_FLOOR);
+        q1.p = fmaxf(q1.p + k * (tp - q1.p), RHO_P_FLOOR);
+        q1.u = q1.u + k * (0.0f - q1.u);
+        q1.v = q1.v + k * (0.0f - q1.v);
+        q1.w = q1.w + k * (0.0f - q1.w);
+        q1.ev = fmaxf(q1.ev + k * (tev - q1.ev), 0.f);
+      }
+      const float a = soundspeed(P, q1);  // :1345-1351
+      const float sw = (fabsf(q1.u) + a) / P.dx + (fabsf(q1.v) + a) / P.dy + (fabsf(q1.w) + a) / P.dz;
+      if (isfinite(sw) && sw > 0.f) ssum = sw;
+      out[i] = __logf(fmaxf(q1.r, RHO_P_FLOOR));  // :1353-1358
+      out[PL + i] = asinhf_dev(q1.u / P.u_ref);
+      out[2 * PL + i] = asinhf_dev(q1.v / P.u_ref);
+      out[3 * PL + i] = asinhf_dev(q1.w / P.u_ref);
+      out[4 * PL + i] = __logf(fmaxf(q1.p, RHO_P_FLOOR));
+      out[5 * PL + i] = __logf(fmaxf(q1.ev, RHO_P_FLOOR));
+    }
+  }
+  ssum = tau::warp_max(ssum);
+  if ((tid & 31) == 0 && ssum > 0.f) tau::atomic_max_nonneg(&clk->maxs, ssum);
+}
+
+// host controller :1680-1704 as a one-thread kernel: commits t, adapts d_tau from the max wavespeed
+// the step just measured, arms the other clock slot, clears the accumulator.
+__global__ void hyp3d_controller(const Par P, Clock *clk, int slot) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float d_tau = clk->d_tau[slot];
+  const float t = clk->t[slot] * expf(d_tau);
+  const float dt = t * d_tau;
+  const float maxs = clk->maxs;
+  const float dt_cfl = P.cfl / fmaxf(maxs, 1e-9f);
+  if (dt > 1.10f * dt_cfl) d_tau *= 0.80f;
+  else if (dt < 0.85f * dt_cfl) d_tau *= 1.10f;
+  d_tau = fminf(fmaxf(d_tau, 1e-7f), 5e-2f);
+  clk->t[slot ^ 1] = t;
+  clk->d_tau[slot ^ 1] = d_tau;
+  clk->dt_last = dt;
+  clk->maxs_last = maxs;
+  clk->maxs = 0.f;
+}
+
+// k_build_solid_mask :759-770 for every plane of the slab incl. the 3 ghost planes on either side
+__global__ void hyp3d_build_solid(const Par P, uint8_t *solid) {
+  const size_t n = P.plane;
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = (int)(i % P.nx), y = (int)((i / P.nx) % P.ny), pz = (int)(i / ((size_t)P.nx * P.ny));
+  const int gz = wrapi(P.z_begin + pz - T3_H, P.nz);
+  solid[i] = sdf_sphere(P, (x + 0.5f) * P.dx, (y + 0.5f) * P.dy, (gz + 0.5f) * P.dz) < 0.f ? 1 : 0;
+}
+
+// k_init :939-985 (ghost planes included: the initial state is z-periodic by construction)
+__global__ void hyp3d_init(const Par P, float *st, const uint8_t *solid) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= P.plane) return;
+  float r = fmaxf(P.inflow_r, RHO_P_FLOOR), p = fmaxf(P.inflow_p, RHO_P_FLOOR);
+  float T = p / (r * P.R);
+  float ev = evib_eq(P, T);
+  if (solid[i]) {
+    T = P.Twall;
+    r = fmaxf(p / (P.R * fmaxf(T, NEWTON_TEMP_FLOOR)), RHO_P_FLOOR);
+    ev = evib_eq(P, T);
+  }
+  st[i] = __logf(fmaxf(r, RHO_P_FLOOR));
+  st[P.plane + i] = asinhf_dev(0.f / P.u_ref);
+  st[2 * P.plane + i] = asinhf_dev(0.f / P.u_ref);
+  st[3 * P.plane + i] = asinhf_dev(0.f / P.u_ref);
+  st[4 * P.plane + i] = __logf(fmaxf(p, RHO_P_FLOOR));
+  st[5 * P.plane + i] = __logf(fmaxf(ev, RHO_P_FLOOR));
+}
+
+constexpr size_t T3_SMEM = (size_t)(6 * T3_SVOL + 6 * T3_NF) * sizeof(float) + ((T3_SVOL + 15) / 16) * 16;
+
+}  // namespace
+
+struct tau_hyp3d {
+  tau_hyp3d_params prm;
+  int device, z_begin, nz_local;
+  bool slab;
+  cudaStream_t stream;
+  bool own_stream;
+  float *st[2];      // 6 contiguous planes each, (nz_local+6) z-planes
+  uint8_t *solid;
+  Clock *clk;
+  int cur;
+  long long steps, launches;
+  size_t plane;
+  cudaEvent_t ev0, ev1;
+  bool timed, have_state;
+};
+
+namespace {
+Par make_par(const tau_hyp3d *h) {
+  Par P;
+  const tau_hyp3d_params &p = h->prm;
+  P.nx = p.nx; P.ny = p.ny; P.nz = p.nz;
+  P.dx = p.dx; P.dy = p.dy; P.dz = p.dz; P.cfl = p.cfl; P.u_ref = p.u_ref; P.R = p.R;
+  P.gamma_floor = p.gamma_floor; P.Twall = p.Twall; P.tau_vib = p.tau_vib; P.theta_v = p.theta_v;
+  P.sdf_cx = p.sdf_cx; P.sdf_cy = p.sdf_cy; P.sdf_cz = p.sdf_cz; P.sdf_r = p.sdf_r;
+  P.inflow_r = p.inflow_r; P.inflow_p = p.inflow_p; P.inflow_u = p.inflow_u;
+  P.inflow_v = p.inflow_v; P.inflow_w = p.inflow_w;
+  P.sponge_n = p.sponge_n; P.sponge_strength = p.sponge_strength;
+  P.sponge_out_n = p.sponge_out_n; P.sponge_out_strength = p.sponge_out_strength;
+  P.z_begin = h->z_begin; P.nz_local = h->nz_local; P.slab = h->slab ? 1 : 0;
+  P.plane = h->plane;
+  return P;
+}
+}  // namespace
+
+extern "C" {
+
+// main()'s hard-coded Params :1531-1557 for an nx x ny x nz grid (the reference uses 64^3)
+void tau_hyp3d_default_params(tau_hyp3d_params *p, int nx, int ny, int nz) {
+  p->nx = nx; p->ny = ny; p->nz = nz;
+  p->dx = 1.f / nx; p->dy = 1.f / ny; p->dz = 1.f / nz;
+  p->cfl = 0.3333f; p->u_ref = 10.f; p->R = 10.f; p->gamma_floor = 1.1f; p->Twall = 0.02f;
+  p->tau_vib = 2e-4f; p->theta_v = 0.2f;
+  p->sdf_cx = 0.5f; p->sdf_cy = 0.5f; p->sdf_cz = 0.5f; p->sdf_r = 0.25f;
+  p->inflow_r = 0.02f; p->inflow_p = 0.02f; p->inflow_u = 100.0f; p->inflow_v = 0.0f; p->inflow_w = 0.0f;
+  p->sponge_n = 24; p->sponge_strength = 0.05f; p->sponge_out_n = 24; p->sponge_out_strength = 0.05f;
+  p->t0 = 1e-5f;      // :1635
+  p->d_tau0 = 1e-3f;  // :1636
+}
+
+int tau_hyp3d_create(const tau_hyp3d_params *p, int device, int z_begin, int nz_local, void *stream,
+                     tau_hyp3d **out) {
+  TAU_REQUIRE(p && out, "tau_hyp3d_create: null argument");
+  TAU_REQUIRE(p->nx >= 1 && p->ny >= 1 && p->nz >= 1, "tau_hyp3d_create: bad grid %d x %d x %d",
+              p->nx, p->ny, p->nz);
+  TAU_REQUIRE(z_begin >= 0 && nz_local > 0 && z_begin + nz_local <= p->nz,
+              "tau_hyp3d_create: slab planes [%d,%d) outside [0,%d)", z_begin, z_begin + nz_local, p->nz);
+  TAU_REQUIRE(nz_local == p->nz || nz_local >= T3_H, "tau_hyp3d_create: a slab needs >= %d planes", T3_H);
+  if (tau_device_count() <= 0) {
+    tau_set_error("tau_hyp3d_create: no CUDA device (this library has no CPU fallback)");
+    return TAU_ERR_NODEV;
+  }
+  TAU_CUDA(cudaSetDevice(device));
+  tau_hyp3d *h = new (std::nothrow) tau_hyp3d();
+  if (!h) return TAU_ERR_NOMEM;
+  h->prm = *p;
+  h->device = device;
+  h->z_begin = z_begin;
+  h->nz_local = nz_local;
+  h->slab = (nz_local != p->nz);
+  h->cur = 0;
+  h->steps = h->launches = 0;
+  h->timed = h->have_state = false;
+  if (stream) {
+    h->stream = (cudaStream_t)stream;
+    h->own_stream = false;
+  } else {
+    TAU_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    h->own_stream = true;
+  }
+  h->plane = (size_t)p->nx * p->ny * (nz_local + 2 * T3_H);
+  for (int b = 0; b < 2; ++b) {
+    TAU_CUDA(cudaMalloc(&h->st[b], 6 * h->plane * sizeof(float)));
+    TAU_CUDA(cudaMemsetAsync(h->st[b], 0, 6 * h->plane * sizeof(float), h->stream));
+  }
+  TAU_CUDA(cudaMalloc(&h->solid, h->plane));
+  TAU_CUDA(cudaMalloc(&h->clk, sizeof(Clock)));
+  TAU_CUDA(cudaEventCreate(&h->ev0));
+  TAU_CUDA(cudaEventCreate(&h->ev1));
+  TAU_CUDA(cudaFuncSetAttribute(hyp3d_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T3_SMEM));
+  const Par P = make_par(h);
+  hyp3d_build_solid<<<(unsigned)((h->plane + 255) / 256), 256, 0, h->stream>>>(P, h->solid);
+  h->launches++;
+  TAU_CUDA(cudaGetLastError());
+  *out = h;
+  return TAU_OK;
+}
+
+static int hyp3d_reset_clock(tau_hyp3d *h) {
+  Clock c;
+  memset(&c, 0, sizeof(c));
+  c.t[0] = c.t[1] = h->prm.t0;
+  c.d_tau[0] = c.d_tau[1] = h->prm.d_tau0;
+  TAU_CUDA(cudaMemcpyAsync(h->clk, &c, sizeof(c), cudaMemcpyHostToDevice, h->stream));
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  h->steps = 0;
+  return TAU_OK;
+}
+
+int tau_hyp3d_init(tau_hyp3d *h) {
+  TAU_REQUIRE(h, "tau_hyp3d_init: null handle");
+  TAU_CUDA(cudaSetDevice(h->device));
+  const Par P = make_par(h);
+  hyp3d_init<<<(unsigned)((h->plane + 255) / 256), 256, 0, h->stream>>>(P, h->st[h->cur], h->solid);
+  h->launches++;
+  TAU_CUDA(cudaGetLastError());
+  h->have_state = true;
+  return hyp3d_reset_clock(h);
+}
+
+int tau_hyp3d_upload(tau_hyp3d *h, const float *const planes[6], const float *clock2) {
+  TAU_REQUIRE(h && planes, "tau_hyp3d_upload: null argument");
+  TAU_CUDA(cudaSetDevice(h->device));
+  const size_t nxy = (size_t)h->prm.nx * h->prm.ny, n = nxy * h->nz_local;
+  for (int f = 0; f < 6; ++f) {
+    TAU_REQUIRE(planes[f], "tau_hyp3d_upload: null plane %d", f);
+    TAU_CUDA(cudaMemcpyAsync(h->st[h->cur] + f * h->plane + T3_H * nxy, planes[f], n * sizeof(float),
+                             cudaMemcpyHostToDevice, h->stream));
+  }
+  h->have_state = true;
+  int rc = hyp3d_reset_clock(h);
+  if (rc) return rc;
+  if (clock2) {
+    Clock c;
+    memset(&c, 0, sizeof(c));
+    c.t[0] = c.t[1] = clock2[0];
+    c.d_tau[0] = c.d_tau[1] = clock2[1];
+    TAU_CUDA(cudaMemcpyAsync(h->clk, &c, sizeof(c), cudaMemcpyHostToDevice, h->stream));
+    TAU_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  return TAU_OK;
+}
+
+int tau_hyp3d_step(tau_hyp3d *h, int nsteps) {
+  TAU_REQUIRE(h, "tau_hyp3d_step: null handle");
+  TAU_REQUIRE(nsteps >= 0, "tau_hyp3d_step: nsteps must be >= 0");
+  TAU_REQUIRE(h->have_state, "tau_hyp3d_step: no state (call tau_hyp3d_init or tau_hyp3d_upload)");
+  TAU_REQUIRE(!h->slab, "tau_hyp3d_step: slab handles use tau_hyp3d_step_begin / tau_hyp3d_step_end "
+                        "(ghost planes and the max wavespeed are exchanged in between)");
+  TAU_CUDA(cudaSetDevice(h->device));
+  TAU_CUDA(cudaEventRecord(h->ev0, h->stream));
+  for (int s = 0; s < nsteps; ++s) {
+    int rc = tau_hyp3d_step_begin(h);
+    if (rc) return rc;
+    rc = tau_hyp3d_step_end(h);
+    if (rc) return rc;
+  }
+  TAU_CUDA(cudaEventRecord(h->ev1, h->stream));
+  h->timed = true;
+  return TAU_OK;
+}
+
+// k_step only (slab protocol: exchange ghost planes BEFORE, all-reduce MAX the wavespeed AFTER,
+// then tau_hyp3d_step_end runs the controller)
+int tau_hyp3d_step_begin(tau_hyp3d *h) {
+  TAU_REQUIRE(h && h->have_state, "tau_hyp3d_step_begin: no state");
+  const Par P = make_par(h);
+  const int slot = (int)(h->steps & 1);
+  dim3 block(T3_TX, T3_TY, T3_TZ);
+  dim3 grid((P.nx + T3_TX - 1) / T3_TX, (P.ny + T3_TY - 1) / T3_TY, (h->nz_local + T3_TZ - 1) / T3_TZ);
+  hyp3d_step<<<grid, block, T3_SMEM, h->stream>>>(P, h->st[h->cur], h->st[h->cur ^ 1], h->solid, h->clk, slot);
+  h->launches++;
+  TAU_CUDA(cudaGetLastError());
+  return TAU_OK;
+}
+
+int tau_hyp3d_step_end(tau_hyp3d *h) {
+  TAU_REQUIRE(h, "tau_hyp3d_step_end: null handle");
+  const Par P = make_par(h);
+  const int slot = (int)(h->steps & 1);
+  hyp3d_controller<<<1, 32, 0, h->stream>>>(P, h->clk, slot);
+  h->launches++;
+  TAU_CUDA(cudaGetLastError());
+  h->cur ^= 1;
+  h->steps++;
+  return TAU_OK;
+}
+
+int tau_hyp3d_clock(tau_hyp3d *h, float *t, float *d_tau, float *dt_last, float *maxs_last) {
+  TAU_REQUIRE(h, "tau_hyp3d_clock: null handle");
+  Clock c;
+  TAU_CUDA(cudaMemcpyAsync(&c, h->clk, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  const int slot = (int)(h->steps & 1);
+  if (t) *t = c.t[slot];
+  if (d_tau) *d_tau = c.d_tau[slot];
+  if (dt_last) *dt_last = c.dt_last;
+  if (maxs_last) *maxs_last = c.maxs_last;
+  return TAU_OK;
+}
+
+int tau_hyp3d_download(tau_hyp3d *h, float *const planes[6], uint8_t *solid) {
+  TAU_REQUIRE(h && planes, "tau_hyp3d_download: null argument");
+  TAU_CUDA(cudaSetDevice(h->device));
+  const size_t nxy = (size_t)h->prm.nx * h->prm.ny, n = nxy * h->nz_local;
+  for (int f = 0; f < 6; ++f)
+    if (planes[f])
+      TAU_CUDA(cudaMemcpyAsync(planes[f], h->st[h->cur] + f * h->plane + T3_H * nxy, n * sizeof(float),
+                               cudaMemcpyDeviceToHost, h->stream));
+  if (solid) TAU_CUDA(cudaMemcpyAsync(solid, h->solid + T3_H * nxy, n, cudaMemcpyDeviceToHost, h->stream));
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  return TAU_OK;
+}
+
+int tau_hyp3d_sync(tau_hyp3d *h) {
+  TAU_REQUIRE(h, "tau_hyp3d_sync: null handle");
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  return TAU_OK;
+}
+
+int tau_hyp3d_device_state(tau_hyp3d *h, float **planes, float **maxs) {
+  TAU_REQUIRE(h, "tau_hyp3d_device_state: null handle");
+  if (planes) *planes = h->st[h->cur];
+  if (maxs) *maxs = &h->clk->maxs;
+  return TAU_OK;
+}
+
+long long tau_hyp3d_steps_done(tau_hyp3d *h) { return h ? h->steps : -1; }
+long long tau_hyp3d_launch_count(tau_hyp3d *h) { return h ? h->launches : -1; }
+
+int tau_hyp3d_last_step_ms(tau_hyp3d *h, float *ms) {
+  TAU_REQUIRE(h && ms, "tau_hyp3d_last_step_ms: null argument");
+  TAU_REQUIRE(h->timed, "tau_hyp3d_last_step_ms: no step has been timed yet");
+  TAU_CUDA(cudaEventSynchronize(h->ev1));
+  TAU_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return TAU_OK;
+}
+
+int tau_hyp3d_destroy(tau_hyp3d *h) {
+  if (!h) return TAU_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(h->clk);
+  cudaFree(h->solid);
+  cudaFree(h->st[1]);
+  cudaFree(h->st[0]);
+  cudaEventDestroy(h->ev1);
+  cudaEventDestroy(h->ev0);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return TAU_OK;
+}
+
+}  // extern "C"

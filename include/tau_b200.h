@@ -136,6 +136,55 @@ long long tau_hyp2d_launch_count(tau_hyp2d *h);
 int tau_hyp2d_last_step_ms(tau_hyp2d *h, float *ms);
 int tau_hyp2d_destroy(tau_hyp2d *h);
 
+/* ------------------------------------------------------------------------------------------ */
+/* 3-D hypersonic flow with vibrational relaxation (reference: tau_hypersonic_3d_cuda.cu)       */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct tau_hyp3d tau_hyp3d;
+
+/* mirrors `struct Params` tau_hypersonic_3d_cuda.cu:21-42, plus the initial log-time clock
+ * (t0, d_tau0) that main() hard-codes (:1635-1636) */
+typedef struct tau_hyp3d_params {
+  int nx, ny, nz;
+  float dx, dy, dz;
+  float cfl, u_ref, R, gamma_floor, Twall, tau_vib, theta_v;
+  float sdf_cx, sdf_cy, sdf_cz, sdf_r;
+  float inflow_r, inflow_p, inflow_u, inflow_v, inflow_w;
+  int sponge_n;
+  float sponge_strength;
+  int sponge_out_n;
+  float sponge_out_strength;
+  float t0, d_tau0;
+} tau_hyp3d_params;
+
+/* main()'s constants :1531-1557 for an nx x ny x nz grid (dx = 1/nx ...; the reference runs 64^3) */
+void tau_hyp3d_default_params(tau_hyp3d_params *p, int nx, int ny, int nz);
+/* replaces the allocation block :1572-1601 incl. k_build_solid_mask.  Slab: z-planes
+ * [z_begin, z_begin+nz_local) with 3 ghost planes on either side (z is periodic: a ring). */
+int tau_hyp3d_create(const tau_hyp3d_params *p, int device, int z_begin, int nz_local, void *stream,
+                     tau_hyp3d **out);
+/* reset_sim -> k_init :1605, clock := (t0, d_tau0) */
+int tau_hyp3d_init(tau_hyp3d *h);
+/* inject caller state: 6 host planes xi, phix, phiy, phiz, lam, zet of nz_local*ny*nx floats,
+ * index (z*ny+y)*nx+x (:152); clock2 = {t, d_tau} or NULL for (t0, d_tau0) */
+int tau_hyp3d_upload(tau_hyp3d *h, const float *const planes[6], const float *clock2);
+/* THE hot path: nsteps x the loop body :1679-1712 (log-time clock, k_step, d_tau controller, swap)
+ * with clock and controller on the device.  Single-GPU handles only. */
+int tau_hyp3d_step(tau_hyp3d *h, int nsteps);
+/* slab protocol, one step: [exchange ghost planes] step_begin [all-reduce MAX of *maxs] step_end */
+int tau_hyp3d_step_begin(tau_hyp3d *h);
+int tau_hyp3d_step_end(tau_hyp3d *h);
+/* t, d_tau for the NEXT step, and dt / max wavespeed sum of the last one (HUD :1763-1768) */
+int tau_hyp3d_clock(tau_hyp3d *h, float *t, float *d_tau, float *dt_last, float *maxs_last);
+int tau_hyp3d_download(tau_hyp3d *h, float *const planes[6], uint8_t *solid);
+int tau_hyp3d_sync(tau_hyp3d *h);
+/* device pointers: current state (6 contiguous planes of (nz_local+6)*ny*nx floats, starting at
+ * ghost plane -3) and the max-wavespeed accumulator of the running step */
+int tau_hyp3d_device_state(tau_hyp3d *h, float **planes, float **maxs);
+long long tau_hyp3d_steps_done(tau_hyp3d *h);
+long long tau_hyp3d_launch_count(tau_hyp3d *h);
+int tau_hyp3d_last_step_ms(tau_hyp3d *h, float *ms);
+int tau_hyp3d_destroy(tau_hyp3d *h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -245,3 +245,88 @@ class RefHypCpu:
         mask = np.empty(N, np.uint8)
         self.lib.ref_hypcpu_get(*planes, mask)
         return planes, mask
+
+
+# ------------------------------------------------------------------------------------------------
+# 3-D hypersonic (tau_hypersonic_3d_cuda.cu), fp32
+# ------------------------------------------------------------------------------------------------
+_H3_FIELDS = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int)] + \
+             [(n, C.c_float) for n in ("dx", "dy", "dz", "cfl", "u_ref", "R", "gamma_floor", "Twall",
+                                       "tau_vib", "theta_v", "sdf_cx", "sdf_cy", "sdf_cz", "sdf_r",
+                                       "inflow_r", "inflow_p", "inflow_u", "inflow_v", "inflow_w")] + \
+             [("sponge_n", C.c_int), ("sponge_strength", C.c_float), ("sponge_out_n", C.c_int),
+              ("sponge_out_strength", C.c_float)]
+
+
+class Hyp3dParams(C.Structure):
+    _fields_ = _H3_FIELDS
+
+    def as23(self):
+        """the 23 floats oracle/ref_drivers/ref_hyp3d.cu expects (everything but nx, ny, nz)"""
+        return np.array([float(getattr(self, f[0])) for f in _H3_FIELDS[3:]], np.float32)
+
+
+_h3p = C.POINTER(Hyp3dParams)
+_pp6 = C.POINTER(C.c_void_p)
+lib.oracle_hyp3d_default_params.argtypes = [_h3p, C.c_int, C.c_int, C.c_int]
+lib.oracle_hyp3d_default_params.restype = None
+lib.oracle_hyp3d_build_solid.argtypes = [_h3p, u8p]
+lib.oracle_hyp3d_build_solid.restype = None
+lib.oracle_hyp3d_init.argtypes = [_h3p] + [f32p] * 6 + [u8p]
+lib.oracle_hyp3d_init.restype = None
+lib.oracle_hyp3d_run.argtypes = [_h3p, _pp6, u8p, C.c_int, f32p, C.c_void_p, C.c_void_p]
+lib.oracle_hyp3d_run.restype = None
+
+
+def hyp3d_params(nx, ny, nz, **over) -> Hyp3dParams:
+    p = Hyp3dParams()
+    lib.oracle_hyp3d_default_params(C.byref(p), nx, ny, nz)
+    for k, v in over.items():
+        setattr(p, k, v)
+    return p
+
+
+def hyp3d_init(p: Hyp3dParams):
+    N = p.nx * p.ny * p.nz
+    solid = np.empty(N, np.uint8)
+    lib.oracle_hyp3d_build_solid(C.byref(p), solid)
+    planes = [np.empty(N, np.float32) for _ in range(6)]
+    lib.oracle_hyp3d_init(C.byref(p), *planes, solid)
+    return planes, solid
+
+
+def hyp3d_run(p: Hyp3dParams, planes, solid, steps, clock=(1e-5, 1e-3)):
+    """CPU oracle: returns (planes, clock(t, d_tau), dt_hist, maxs_hist)."""
+    planes = [np.array(a, np.float32, order="C", copy=True).ravel() for a in planes]
+    solid = np.ascontiguousarray(solid, np.uint8).ravel()
+    ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in planes])
+    ck = np.array(clock, np.float32)
+    dts = np.zeros(max(steps, 1), np.float32)
+    ms = np.zeros(max(steps, 1), np.float32)
+    lib.oracle_hyp3d_run(C.byref(p), ptrs, solid, steps, ck, dts.ctypes.data_as(C.c_void_p),
+                         ms.ctypes.data_as(C.c_void_p))
+    return planes, (float(ck[0]), float(ck[1])), dts[:steps], ms[:steps]
+
+
+def ref_hyp3d_run(p: Hyp3dParams, steps, planes=None, clock=(1e-5, 1e-3)):
+    """The reference's own k_step on the GPU (oracle/_ref/libref_hyp3d.so).
+    Returns (planes, solid, clock, dt_hist, maxs_hist, ms)."""
+    r = ref("ref_hyp3d")
+    r.ref_hyp3d_run.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _pp6, u8p, f32p,
+                                C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    r.ref_hyp3d_run.restype = C.c_int
+    N = p.nx * p.ny * p.nz
+    do_init = planes is None
+    planes = [np.zeros(N, np.float32) for _ in range(6)] if do_init else \
+        [np.array(a, np.float32, order="C", copy=True).ravel() for a in planes]
+    solid = np.zeros(N, np.uint8)
+    ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in planes])
+    ck = np.array(clock, np.float32)
+    dts = np.zeros(max(steps, 1), np.float32)
+    mx = np.zeros(max(steps, 1), np.float32)
+    ms = C.c_float()
+    rc = r.ref_hyp3d_run(p.as23(), p.nx, p.ny, p.nz, steps, 1 if do_init else 0, ptrs, solid, ck,
+                         dts.ctypes.data_as(C.c_void_p), mx.ctypes.data_as(C.c_void_p), C.byref(ms))
+    if rc != 0:
+        raise RuntimeError(f"reference hyp3d run failed with cudaError {rc}")
+    return planes, solid, (float(ck[0]), float(ck[1])), dts[:steps], mx[:steps], float(ms.value)

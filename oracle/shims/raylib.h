@@ -32,6 +32,19 @@ typedef Camera3D Camera;
 #define KEY_LEFT 263
 #define KEY_RIGHT 262
 #define MOUSE_BUTTON_LEFT 0
+#define MOUSE_BUTTON_RIGHT 1
+#define MOUSE_BUTTON_MIDDLE 2
+#define KEY_L 76
+#define KEY_MINUS 45
+#define KEY_EQUAL 61
+#define KEY_KP_SUBTRACT 333
+#define KEY_KP_ADD 334
+#define KEY_LEFT_BRACKET 91
+#define KEY_RIGHT_BRACKET 93
+#define KEY_P 80
+#define KEY_V 86
+#define KEY_TAB 258
+#define KEY_ESCAPE 256
 #define BLACK ((Color){0, 0, 0, 255})
 #define WHITE ((Color){255, 255, 255, 255})
 #define GREEN ((Color){0, 228, 48, 255})
@@ -73,6 +86,9 @@ static inline void DrawText(const char *t, int x, int y, int s, Color c) { (void
 static inline void DrawFPS(int x, int y) { (void)x; (void)y; }
 static inline const char *TextFormat(const char *f, ...) { return f; }
 static inline void CloseWindow(void) {}
+static inline void DrawCubeWires(Vector3 p, float w, float h, float l, Color c) { (void)p; (void)w; (void)h; (void)l; (void)c; }
+static inline Color Fade(Color c, float a) { (void)a; return c; }
+static inline void DrawRectangle(int x, int y, int w, int h, Color c) { (void)x; (void)y; (void)w; (void)h; (void)c; }
 #ifdef __cplusplus
 }
 #endif

@@ -97,7 +97,27 @@ def hyp2d():
     print("hyp2d golden written")
 
 
+def hyp3d():
+    # the reference's own k_step from k_init, small grids (block 8x8x4 does not divide 20 / 28)
+    for (nx, ny, nz, steps) in ((32, 28, 20, 30),):
+        prm = oracle.hyp3d_params(nx, ny, nz)
+        p0, solid, _, _, _, _ = oracle.ref_hyp3d_run(prm, 0)
+        p1, _, clock, dts, mx, _ = oracle.ref_hyp3d_run(prm, steps)
+        out = {"steps": np.array(steps), "solid": solid, "clock": np.array(clock), "dts": dts, "maxs": mx}
+        for k, a, b in zip(("xi", "phix", "phiy", "phiz", "lam", "zet"), p0, p1):
+            out[k + "0"] = a
+            out[k] = b
+        # a developed state: start late in the inflow ramp so that shocks and the sponge matter
+        p2, _, clock2, dts2, mx2, _ = oracle.ref_hyp3d_run(prm, steps, planes=p1, clock=(0.015, 2e-3))
+        for k, b in zip(("xi", "phix", "phiy", "phiz", "lam", "zet"), p2):
+            out[k + "_b"] = b
+        out["clock_b"] = np.array(clock2)
+        out["dts_b"] = dts2
+        np.savez_compressed(os.path.join(OUT, f"hyp3d_ref_{nx}x{ny}x{nz}.npz"), **out)
+    print("hyp3d golden written")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["gs", "hyp2d"]
+    which = sys.argv[1:] or ["gs", "hyp2d", "hyp3d"]
     for w in which:
         globals()[w]()

@@ -227,3 +227,25 @@ def test_reference_cpu_solver_runs_config1():
     planes, mask = r.get()
     assert r.sim_t > 0 and np.isfinite(planes[3]).all() and planes[0].min() > 0
     assert mask.sum() > 0
+
+
+def test_hyp3d_oracle_matches_reference_golden():
+    """3-D: the reference has no tests; the fixture is the reference's own k_step run on a B200."""
+    g = np.load(os.path.join(GOLDEN, "hyp3d_ref_32x28x20.npz"))
+    prm = oracle.hyp3d_params(32, 28, 20)
+    names = ("xi", "phix", "phiy", "phiz", "lam", "zet")
+    planes, solid = oracle.hyp3d_init(prm)
+    assert np.array_equal(solid, g["solid"])
+    for k, a in zip(names, planes):
+        assert np.abs(a - g[k + "0"]).max() <= 1e-6
+    steps = int(g["steps"])
+    out, clock, dts, maxs = oracle.hyp3d_run(prm, planes, solid, steps)
+    for k, a in zip(names, out):
+        assert np.abs(a - g[k]).max() <= 2e-5, k              # libm vs __expf/__logf, quiescent start
+    assert abs(clock[0] - g["clock"][0]) <= 1e-6 * clock[0] and abs(clock[1] - g["clock"][1]) <= 1e-6
+    assert np.abs(dts - g["dts"]).max() <= 1e-6 * dts.max()
+    assert np.abs(maxs - g["maxs"]).max() <= 1e-4 * maxs.max()
+    out, clock, _, _ = oracle.hyp3d_run(prm, [g[k] for k in names], solid, steps, (0.015, 2e-3))
+    tol = dict(xi=2e-4, phix=5e-5, phiy=5e-5, phiz=5e-5, lam=5e-3, zet=1e-2)
+    for k, a in zip(names, out):
+        assert np.abs(a - g[k + "_b"]).max() <= tol[k], k

@@ -185,6 +185,51 @@ long long tau_hyp3d_launch_count(tau_hyp3d *h);
 int tau_hyp3d_last_step_ms(tau_hyp3d *h, float *ms);
 int tau_hyp3d_destroy(tau_hyp3d *h);
 
+/* ------------------------------------------------------------------------------------------ */
+/* 2-D weakly-compressible SPH (reference: tau_sph.cu)                                          */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct tau_sph tau_sph;
+
+/* simulation fields of `struct Params` tau_sph.cu:49-85 (same defaults) */
+typedef struct tau_sph_params {
+  int N;
+  float boxX, boxY;
+  float dTau, t0, CFL;
+  float rho0, c0, gammaEOS, hMul, viscAlpha, gravity;
+  int rain, useVisc, useGrav;
+  int viscSub;
+  int useXSPH;
+  float xsphEps;
+  int seed;
+} tau_sph_params;
+
+void tau_sph_default_params(tau_sph_params *p);
+/* reset_particles() tau_sph.cu:493-510 on the host: pos_xy / vel_xy are N x (x, y) floats */
+void tau_sph_reset_particles(const tau_sph_params *p, float *pos_xy, float *vel_xy);
+/* replaces the allocation block :561-565 + ensure_cell_buffers :512-540 + derived constants
+ * :573-578 */
+int tau_sph_create(const tau_sph_params *p, int device, void *stream, tau_sph **out);
+/* reset_particles + H2D :567-571; clock := (t0, tau = 0) */
+int tau_sph_init(tau_sph *h);
+int tau_sph_upload(tau_sph *h, const float *pos_xy, const float *vel_xy);
+/* THE hot path: nframes x the doStep block :663-722 — per sub-step: cell keys, radix sort, cell
+ * ranges, density/pressure, forces + integration, [XSPH], [rain], tau-clock.  No host sync. */
+int tau_sph_step(tau_sph *h, int nframes);
+int tau_sph_clock(tau_sph *h, float *t, float *tau, long long *step);
+/* state in ORIGINAL particle order (any pointer may be NULL) */
+int tau_sph_download(tau_sph *h, float *pos_xy, float *vel_xy, float *s, float *press);
+/* (cell key, particle index) pairs of the last sub-step's radix sort, in sorted order */
+int tau_sph_download_sort(tau_sph *h, unsigned *keys, unsigned *vals);
+/* the sort on its own: N keys (< number of cells rounded up to a power of two) -> sorted keys and
+ * the stable permutation */
+int tau_sph_sort_pairs(tau_sph *h, const unsigned *keys_in, unsigned *keys_out, unsigned *vals_out);
+int tau_sph_grid(tau_sph *h, int *Gx, int *Gy, float *cell, float *hh, float *mass);
+int tau_sph_sync(tau_sph *h);
+long long tau_sph_substeps_done(tau_sph *h);
+long long tau_sph_launch_count(tau_sph *h);
+int tau_sph_last_step_ms(tau_sph *h, float *ms);
+int tau_sph_destroy(tau_sph *h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -330,3 +330,97 @@ def ref_hyp3d_run(p: Hyp3dParams, steps, planes=None, clock=(1e-5, 1e-3)):
     if rc != 0:
         raise RuntimeError(f"reference hyp3d run failed with cudaError {rc}")
     return planes, solid, (float(ck[0]), float(ck[1])), dts[:steps], mx[:steps], float(ms.value)
+
+
+# ------------------------------------------------------------------------------------------------
+# SPH (tau_sph.cu), fp32
+# ------------------------------------------------------------------------------------------------
+_SPH_FIELDS = [("N", C.c_int), ("boxX", C.c_float), ("boxY", C.c_float), ("dTau", C.c_float),
+               ("t0", C.c_float), ("CFL", C.c_float), ("rho0", C.c_float), ("c0", C.c_float),
+               ("gammaEOS", C.c_float), ("hMul", C.c_float), ("viscAlpha", C.c_float),
+               ("gravity", C.c_float), ("rain", C.c_int), ("useVisc", C.c_int), ("useGrav", C.c_int),
+               ("viscSub", C.c_int), ("useXSPH", C.c_int), ("xsphEps", C.c_float), ("seed", C.c_int)]
+
+
+class SphParams(C.Structure):
+    _fields_ = _SPH_FIELDS
+
+    def as19(self):
+        return np.array([float(getattr(self, f[0])) for f in _SPH_FIELDS], np.float32)
+
+
+class SphClock(C.Structure):
+    _fields_ = [("t", C.c_float), ("tau", C.c_float), ("rain_carry", C.c_float), ("step", C.c_longlong)]
+
+
+u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_sphp = C.POINTER(SphParams)
+lib.oracle_sph_run.argtypes = [_sphp, f32p, f32p, f32p, f32p, f32p, C.c_int, C.POINTER(SphClock)]
+lib.oracle_sph_run.restype = None
+lib.oracle_sph_cell_sort.argtypes = [_sphp, f32p, u32p, u32p, i32p]
+lib.oracle_sph_cell_sort.restype = None
+lib.oracle_sph_derived.argtypes = [_sphp] + [C.POINTER(C.c_float)] * 3 + [C.POINTER(C.c_int)] * 2
+lib.oracle_sph_derived.restype = None
+
+
+def sph_params(N=1 << 16, **over) -> SphParams:
+    p = SphParams(N, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 2.0, 0.25, 9.81, 1, 1, 1, 1, 0, 0.25, 69420)
+    for k, v in over.items():
+        setattr(p, k, v)
+    return p
+
+
+def sph_derived(p: SphParams):
+    m, h, c = C.c_float(), C.c_float(), C.c_float()
+    gx, gy = C.c_int(), C.c_int()
+    lib.oracle_sph_derived(C.byref(p), C.byref(m), C.byref(h), C.byref(c), C.byref(gx), C.byref(gy))
+    return dict(mass=m.value, h=h.value, cell=c.value, Gx=gx.value, Gy=gy.value)
+
+
+def sph_cell_sort(p: SphParams, pos):
+    """(sorted keys, stable permutation, cellStart[M+1]) for the given positions."""
+    d = sph_derived(p)
+    pos = np.ascontiguousarray(pos, np.float32).reshape(-1)
+    k, v = np.empty(p.N, np.uint32), np.empty(p.N, np.uint32)
+    cs = np.empty(d["Gx"] * d["Gy"] + 1, np.int32)
+    lib.oracle_sph_cell_sort(C.byref(p), pos, k, v, cs)
+    return k, v, cs
+
+
+def sph_run(p: SphParams, pos, vel, nframes, clock=None):
+    """CPU oracle: returns (pos, vel, acc, s, press, clock)."""
+    pos = np.array(pos, np.float32, order="C", copy=True).reshape(-1)
+    vel = np.array(vel, np.float32, order="C", copy=True).reshape(-1)
+    acc = np.zeros(2 * p.N, np.float32)
+    s, pr = np.zeros(p.N, np.float32), np.zeros(p.N, np.float32)
+    ck = clock or SphClock(p.t0, 0.0, 0.0, 0)
+    lib.oracle_sph_run(C.byref(p), pos, vel, acc, s, pr, nframes, C.byref(ck))
+    return pos.reshape(-1, 2), vel.reshape(-1, 2), acc.reshape(-1, 2), s, pr, ck
+
+
+def ref_sph_reset_particles(p: SphParams):
+    r = ref("ref_sph")
+    r.ref_sph_reset_particles.argtypes = [f32p, f32p, f32p]
+    r.ref_sph_reset_particles.restype = None
+    pos, vel = np.empty(2 * p.N, np.float32), np.empty(2 * p.N, np.float32)
+    r.ref_sph_reset_particles(p.as19(), pos, vel)
+    return pos.reshape(-1, 2), vel.reshape(-1, 2)
+
+
+def ref_sph_run(p: SphParams, pos, vel, nframes, clock=None):
+    """The reference's own kernels on the GPU (oracle/_ref/libref_sph.so).
+    Returns (pos, vel, acc, s, press, clock[t, tau, rain_carry, step], ms)."""
+    r = ref("ref_sph")
+    r.ref_sph_run.argtypes = [f32p] * 6 + [C.c_int, f32p, C.POINTER(C.c_float)]
+    r.ref_sph_run.restype = C.c_int
+    pos = np.array(pos, np.float32, order="C", copy=True).reshape(-1)
+    vel = np.array(vel, np.float32, order="C", copy=True).reshape(-1)
+    acc = np.zeros(2 * p.N, np.float32)
+    s, pr = np.zeros(p.N, np.float32), np.zeros(p.N, np.float32)
+    ck = np.array(clock if clock is not None else [p.t0, 0.0, 0.0, 0.0], np.float32)
+    ms = C.c_float()
+    rc = r.ref_sph_run(p.as19(), pos, vel, acc, s, pr, nframes, ck, C.byref(ms))
+    if rc != 0:
+        raise RuntimeError(f"reference SPH run failed with cudaError {rc}")
+    return pos.reshape(-1, 2), vel.reshape(-1, 2), acc.reshape(-1, 2), s, pr, ck, float(ms.value)

@@ -117,7 +117,21 @@ def hyp3d():
     print("hyp3d golden written")
 
 
+def sph():
+    # the reference's own kernels (linked-list neighbour search) on its own initial lattice
+    out = {}
+    for tag, N, frames, kw in (("a", 4096, 10, {}), ("b", 6000, 8, dict(useXSPH=1, rain=0, viscSub=2))):
+        prm = oracle.sph_params(N, **kw)
+        pos0, vel0 = oracle.ref_sph_reset_particles(prm)
+        pos, vel, acc, s, pr, ck, _ = oracle.ref_sph_run(prm, pos0, vel0, frames)
+        out.update({f"pos0_{tag}": pos0, f"vel0_{tag}": vel0, f"pos_{tag}": pos, f"vel_{tag}": vel,
+                    f"s_{tag}": s, f"press_{tag}": pr, f"clock_{tag}": ck, f"p19_{tag}": prm.as19(),
+                    f"frames_{tag}": np.array(frames)})
+    np.savez_compressed(os.path.join(OUT, "sph_ref.npz"), **out)
+    print("sph golden written")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["gs", "hyp2d", "hyp3d"]
+    which = sys.argv[1:] or ["gs", "hyp2d", "hyp3d", "sph"]
     for w in which:
         globals()[w]()

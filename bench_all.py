@@ -1,0 +1,188 @@
+#!/usr/bin/env python
+"""bench_all.py — secondary benchmarks of the other BASELINE configs (the headline is bench.py):
+
+  config 3  tau_gray_scott 8192x8192                  -> Mcell-updates/s, HBM roofline (16 B/cell)
+  config 4  tau_hypersonic_3d_cuda n^3 (default 256, --n3 512; z-slabs under torchrun)
+                                                        -> Mcell-updates/s, roofline at 49 B/cell
+  config 5  tau_sph 2M particles                       -> Mparticle-updates/s (per sub-step)
+
+Each line also carries `reference_gpu`: the reference's own kernels (oracle/_ref, recompiled for
+sm_100a) timed on the same GPU on the same problem — test infrastructure used as a yardstick, never
+as the product path.  One JSON object per line on stdout.
+
+  python bench_all.py [gs] [hyp3d] [sph] [--steps K]
+  torchrun --nproc-per-node 8 bench_all.py hyp3d --n3 512        # config 4 proper
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+def bench_gs(a):
+    import oracle
+    from fluid_sims_b200.gray_scott import GrayScott, Params
+    n = a.gs_n
+    g = GrayScott(Params(nx=n, ny=n)).init()
+    g.step(20)
+    g.sync()
+    g.step(a.steps)
+    ms = g.last_step_ms() / a.steps
+    cells = n * n
+    ach = 16 * cells / (ms * 1e-3) / 1e9
+    ref_ms = None
+    if oracle.has_ref("ref_gs"):
+        import ctypes as C
+        r = oracle.ref("ref_gs")
+        r.ref_gs_time.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
+        t = C.c_float()
+        r.ref_gs_time(n, n, min(a.steps, 200), C.byref(t))
+        ref_ms = t.value / min(a.steps, 200)
+    print(json.dumps({"bench": "gray_scott", "grid": [n, n], "steps": a.steps, "ms_per_step": ms,
+                      "value": cells / (ms * 1e-3) / 1e6, "unit": "Mcell-updates/s",
+                      "roofline": {"bound": "hbm", "achieved": ach, "peak": peak(), "unit": "GB/s",
+                                   "frac": ach / peak(), "algorithmic_bytes_per_cell": 16},
+                      "reference_gpu": {"ms_per_step": ref_ms,
+                                        "value": cells / (ref_ms * 1e-3) / 1e6 if ref_ms else None,
+                                        "what": "tau_gray_scott.cu step_kernel recompiled for sm_100a"},
+                      "gpu_launches": g.launch_count}))
+
+
+def bench_hyp3d(a):
+    import numpy as np
+    import torch
+
+    import oracle
+    from fluid_sims_b200 import slab
+    from fluid_sims_b200.hypersonic3d import HALO, Hypersonic3D, Params
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = a.n3
+    prm = Params.default(n, n, n)
+    z0, nl = slab.partition_rows(n, world)[rank]
+    ts = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(ts)
+    sim = Hypersonic3D(prm, device=local, z_begin=z0, nz_local=nl, stream=ts.cuda_stream).init()
+    # start late in the inflow ramp so that the bow shock forms within the warm-up
+    p0, _ = sim.download()
+    sim.upload(p0, (5e-3, 2e-3))
+    del p0
+    views = {}
+
+    def advance(k):
+        if world == 1:
+            sim.step(k)
+            return
+        for _ in range(k):
+            pp, mp = sim.device_state()
+            if pp not in views:
+                views[pp] = slab.wrap_plane(pp, (6, nl + 2 * HALO, n, n), torch.float32, local)
+            if mp not in views:
+                views[mp] = slab.wrap_plane(mp, (1,), torch.float32, local)
+            slab.exchange_halos([views[pp]], HALO, periodic=True, dim=1)
+            sim.step_begin()
+            dist.all_reduce(views[mp], op=dist.ReduceOp.MAX)
+            sim.step_end()
+
+    advance(a.warm3)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    advance(a.steps3)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps3
+    if world > 1:
+        t = torch.tensor([ms], device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    cells = n ** 3
+    ach = 49 * (cells / world) / (ms * 1e-3) / 1e9
+    ref = None
+    if world == 1 and oracle.has_ref("ref_hyp3d") and n <= 256:
+        op = oracle.hyp3d_params(n, n, n)
+        *_, rms = oracle.ref_hyp3d_run(op, a.steps3, clock=(5e-3, 2e-3))
+        ref = rms / a.steps3
+    if rank == 0:
+        print(json.dumps({"bench": "hypersonic3d", "grid": [n, n, n], "n_gpus": world,
+                          "steps": a.steps3, "ms_per_step": ms,
+                          "value": cells / (ms * 1e-3) / 1e6, "unit": "Mcell-updates/s",
+                          "roofline": {"bound": "hbm", "achieved": ach, "peak": peak(), "unit": "GB/s",
+                                       "frac": ach / peak(), "algorithmic_bytes_per_cell": 49,
+                                       "note": "compute/MUFU bound by >10x (WENO5+HLLC), see DESIGN.md"},
+                          "reference_gpu": {"ms_per_step": ref,
+                                            "value": cells / (ref * 1e-3) / 1e6 if ref else None,
+                                            "what": "tau_hypersonic_3d_cuda.cu k_step recompiled for "
+                                                    "sm_100a incl. its 2 blocking 4-byte copies per step"},
+                          "clock": sim.clock(), "parallelism": f"z-slab ring x{world}"}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_sph(a):
+    import oracle
+    from fluid_sims_b200.sph import SPH, Params, reset_particles
+    N = a.sph_n
+    P = Params(N=N)
+    s = SPH(P).init()
+    s.step(5)
+    s.sync()
+    s.step(a.steps_sph)
+    ms = s.last_step_ms() / a.steps_sph
+    ref = None
+    if oracle.has_ref("ref_sph"):
+        pos0, vel0 = reset_particles(P)
+        r = oracle.ref_sph_run(oracle.sph_params(N), pos0, vel0, a.steps_sph)
+        ref = r[6] / a.steps_sph
+    ach = 72 * N / (ms * 1e-3) / 1e9
+    print(json.dumps({"bench": "sph", "particles": N, "substeps": a.steps_sph, "ms_per_substep": ms,
+                      "value": N / (ms * 1e-3) / 1e6, "unit": "Mparticle-updates/s",
+                      "roofline": {"bound": "hbm", "achieved": ach, "peak": peak(), "unit": "GB/s",
+                                   "frac": ach / peak(), "algorithmic_bytes_per_particle": 72,
+                                   "note": "L2-resident working set, instruction bound; HBM fraction "
+                                           "is informational (SURVEY 8(d))"},
+                      "reference_gpu": {"ms_per_substep": ref,
+                                        "value": N / (ref * 1e-3) / 1e6 if ref else None,
+                                        "what": "tau_sph.cu kernels recompiled for sm_100a"},
+                      "gpu_launches": s.launch_count}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("which", nargs="*", default=[])
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--gs-n", type=int, default=8192)
+    ap.add_argument("--n3", type=int, default=256)
+    ap.add_argument("--steps3", type=int, default=40)
+    ap.add_argument("--warm3", type=int, default=60)
+    ap.add_argument("--sph-n", type=int, default=1 << 21)
+    ap.add_argument("--steps-sph", type=int, default=50)
+    a = ap.parse_args()
+    which = a.which or ["gs", "hyp3d", "sph"]
+    for w in which:
+        {"gs": bench_gs, "hyp3d": bench_hyp3d, "sph": bench_sph}[w](a)
+
+
+if __name__ == "__main__":
+    main()

@@ -249,3 +249,39 @@ def test_hyp3d_oracle_matches_reference_golden():
     tol = dict(xi=2e-4, phix=5e-5, phiy=5e-5, phiz=5e-5, lam=5e-3, zet=1e-2)
     for k, a in zip(names, out):
         assert np.abs(a - g[k + "_b"]).max() <= tol[k], k
+
+
+def test_sph_oracle_matches_reference_golden():
+    """SPH: the fixture is the reference's own (linked-list) kernels run on a B200.  Integer part
+    (cell keys -> stable order) is exact by construction; floating point agrees at fp32 round-off
+    (libm vs -use_fast_math intrinsics, different summation order)."""
+    g = np.load(os.path.join(GOLDEN, "sph_ref.npz"))
+    for tag in ("a", "b"):
+        p19 = g[f"p19_{tag}"]
+        names = [f[0] for f in oracle._SPH_FIELDS]
+        kw = {n: (int(v) if t is C.c_int else float(v)) for (n, t), v in zip(oracle._SPH_FIELDS, p19)}
+        prm = oracle.sph_params(**{k: kw[k] for k in names})
+        frames = int(g[f"frames_{tag}"])
+        pos, vel, acc, s, pr, ck = oracle.sph_run(prm, g[f"pos0_{tag}"], g[f"vel0_{tag}"], frames)
+        assert np.abs(pos - g[f"pos_{tag}"]).max() <= 1e-4
+        dv = np.abs(vel - g[f"vel_{tag}"]).max(axis=1)
+        assert (dv > 2e-3).mean() <= 2e-3
+        assert (np.abs(s - g[f"s_{tag}"]) > 2e-3).mean() <= 2e-3
+        assert ck.t == pytest.approx(float(g[f"clock_{tag}"][0]), rel=1e-6)
+        assert ck.step == int(g[f"clock_{tag}"][3])
+
+
+def test_sph_cell_sort_is_a_stable_sort():
+    prm = oracle.sph_params(5000)
+    rng = np.random.default_rng(0)
+    pos = rng.random((5000, 2)).astype(np.float32)
+    pos[:50] = -0.1      # clamped into the first row / column
+    pos[50:100] = 1.5    # clamped into the last
+    k, v, cs = oracle.sph_cell_sort(prm, pos)
+    d = oracle.sph_derived(prm)
+    gx = np.clip(np.floor(pos[:, 0] / np.float32(d["cell"])).astype(np.int64), 0, d["Gx"] - 1)
+    gy = np.clip(np.floor(pos[:, 1] / np.float32(d["cell"])).astype(np.int64), 0, d["Gy"] - 1)
+    keys = (gy * d["Gx"] + gx).astype(np.uint32)
+    order = np.argsort(keys, kind="stable").astype(np.uint32)
+    assert np.array_equal(v, order) and np.array_equal(k, keys[order])
+    assert cs[0] == 0 and cs[-1] == 5000 and np.all(np.diff(cs) >= 0)

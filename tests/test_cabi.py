@@ -69,3 +69,29 @@ def test_host_side_helpers_without_gpu():
                      (dict(inflow_mach=0.0), "mach"), (dict(geom_Rb=1.0), "geom-rb")):
         with pytest.raises(TauError, match=pat):
             SimConfig.default(8192, 1024, **bad).validate()
+
+
+def test_cli_hosts_build_and_fail_loudly_without_gpu():
+    """The C host programs link against the C-ABI only; without a GPU they exit(1) with the
+    library's message (the reference's CK() policy), with one they run a tiny headless case."""
+    import subprocess
+    from fluid_sims_b200 import device_count
+    cli = os.path.join(ROOT, "fluid_sims_b200", "cli")
+    subprocess.run(["make", "-C", cli], check=True, capture_output=True)
+    cases = {"tgs": ["--nx", "64", "--ny", "32", "--steps", "3", "--headless"],
+             "tau_2d_hypersonic_cuda": ["--nx", "128", "--ny", "64", "--frames", "2"],
+             "tau3d": ["--n", "16", "--frames", "1"],
+             "tau_sph": ["--n", "2048", "--frames", "2"]}
+    for exe, args in cases.items():
+        r = subprocess.run([os.path.join(cli, exe)] + args, capture_output=True, text=True, timeout=120)
+        if device_count() > 0:
+            assert r.returncode == 0, (exe, r.stderr)
+            assert "updates/s" in r.stdout
+        else:
+            assert r.returncode == 1 and "no CUDA device" in r.stderr, (exe, r.stderr)
+    # flag validation happens before any device work: reference message, exit code 1
+    r = subprocess.run([os.path.join(cli, "tau_2d_hypersonic_cuda"), "--gamma", "0.5"],
+                       capture_output=True, text=True)
+    assert r.returncode == 1 and "Invalid --gamma" in r.stderr
+    r = subprocess.run([os.path.join(cli, "tau_2d_hypersonic_cuda"), "--bogus"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Unknown or incomplete argument" in r.stderr

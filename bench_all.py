@@ -141,31 +141,75 @@ def bench_hyp3d(a):
 
 
 def bench_sph(a):
+    import torch
+
     import oracle
+    from fluid_sims_b200 import slab
     from fluid_sims_b200.sph import SPH, Params, reset_particles
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N = a.sph_n
     P = Params(N=N)
-    s = SPH(P).init()
-    s.step(5)
-    s.sync()
-    s.step(a.steps_sph)
-    ms = s.last_step_ms() / a.steps_sph
+    ts = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(ts)
+    s = SPH(P, device=local, stream=ts.cuda_stream).init()
+    if world > 1:
+        s.shard_config(rank, world)
+
+    def gather(pa, pb, chunk):
+        for ptr in (pa, pb):
+            full = slab.wrap_plane(ptr, (world * chunk, 2), torch.float32, local)
+            dist.all_gather_into_tensor(full, full[rank * chunk:(rank + 1) * chunk])
+
+    def advance(k):
+        if world == 1:
+            s.step(k)
+        else:
+            for _ in range(k):
+                s.shard_substep(gather)
+
+    advance(5)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    advance(a.steps_sph)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps_sph
+    if world > 1:
+        t = torch.tensor([ms], device=f"cuda:{local}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     ref = None
-    if oracle.has_ref("ref_sph"):
+    if world == 1 and oracle.has_ref("ref_sph"):
         pos0, vel0 = reset_particles(P)
         r = oracle.ref_sph_run(oracle.sph_params(N), pos0, vel0, a.steps_sph)
         ref = r[6] / a.steps_sph
     ach = 72 * N / (ms * 1e-3) / 1e9
-    print(json.dumps({"bench": "sph", "particles": N, "substeps": a.steps_sph, "ms_per_substep": ms,
-                      "value": N / (ms * 1e-3) / 1e6, "unit": "Mparticle-updates/s",
-                      "roofline": {"bound": "hbm", "achieved": ach, "peak": peak(), "unit": "GB/s",
-                                   "frac": ach / peak(), "algorithmic_bytes_per_particle": 72,
-                                   "note": "L2-resident working set, instruction bound; HBM fraction "
-                                           "is informational (SURVEY 8(d))"},
-                      "reference_gpu": {"ms_per_substep": ref,
-                                        "value": N / (ref * 1e-3) / 1e6 if ref else None,
-                                        "what": "tau_sph.cu kernels recompiled for sm_100a"},
-                      "gpu_launches": s.launch_count}))
+    if rank == 0:
+        print(json.dumps({"bench": "sph", "particles": N, "n_gpus": world, "substeps": a.steps_sph,
+                          "ms_per_substep": ms, "value": N / (ms * 1e-3) / 1e6,
+                          "unit": "Mparticle-updates/s",
+                          "roofline": {"bound": "hbm", "achieved": ach, "peak": peak(), "unit": "GB/s",
+                                       "frac": ach / peak() / world, "algorithmic_bytes_per_particle": 72,
+                                       "note": "L2-resident working set, instruction bound; HBM "
+                                               "fraction is informational (SURVEY 8(d))"},
+                          "reference_gpu": {"ms_per_substep": ref,
+                                            "value": N / (ref * 1e-3) / 1e6 if ref else None,
+                                            "what": "tau_sph.cu kernels recompiled for sm_100a"},
+                          "parallelism": "replicated state, slot-range shards + all-gather x%d" % world,
+                          "gpu_launches": s.launch_count}))
+    if world > 1 and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 def main():

@@ -42,6 +42,8 @@ struct Consts {
   int N, Gx, Gy;
   float cell, mass, h, rho0, c0, gammaEOS, viscAlpha, gx, gy, boxX, boxY, alpha, xsphEps;
   int useVisc, useGrav;
+  int k_begin, k_end;   // slots this launch works on (single GPU: [0, N))
+  int write_state;      // forces kernel updates pos/vel itself (single GPU) or only the sorted copies
 };
 
 // grid_x / grid_y tau_sph.cu:141-157
@@ -257,10 +259,10 @@ __device__ __forceinline__ void neighbour_sweep(const int *__restrict__ cellStar
 __global__ void __launch_bounds__(256)
 sph_density(const float2 *__restrict__ sxy, const unsigned *__restrict__ vals,
             const int *__restrict__ cellStart, float2 *__restrict__ srp, float *__restrict__ s_out, float *__restrict__ press_out,
-            Consts c) {
+            const int *__restrict__ range, Consts c) {
   const int g = threadIdx.x & (GROUP - 1);
   const int k = (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
-  const bool valid = k < c.N;
+  const bool valid = range ? (k >= range[0] && k < range[1]) : (k < c.N);
   const float2 xi = sxy[valid ? k : 0];
   const int gx = grid_c(xi.x, c.cell, c.Gx), gy = grid_c(xi.y, c.cell, c.Gy);
   const float twoh = 2.f * c.h, twoh2 = twoh * twoh;
@@ -301,8 +303,8 @@ sph_forces_integrate(const float2 *__restrict__ sxy, const float2 *__restrict__ 
                      const int *__restrict__ cellStart, float2 *__restrict__ pos, float2 *__restrict__ vel, float2 *__restrict__ acc,
                      float2 *__restrict__ sxy_new, float2 *__restrict__ svel_new, float dt, Consts c) {
   const int g = threadIdx.x & (GROUP - 1);
-  const int k = (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
-  const bool valid = k < c.N;
+  const int k = c.k_begin + (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
+  const bool valid = k < c.k_end;
   const int kk = valid ? k : 0;
   const float2 xi = sxy[kk], vi = svel[kk], rpi = srp[kk];
   const float rhoi = rpi.x, pri = rpi.y;
@@ -361,8 +363,10 @@ sph_forces_integrate(const float2 *__restrict__ sxy, const float2 *__restrict__ 
     if (x.x > c.boxX) { x.x = c.boxX; v.x = -e * v.x; }
     if (x.y < 0.f) { x.y = 0.f; v.y = -e * v.y; }
     if (x.y > c.boxY) { x.y = c.boxY; v.y = -e * v.y; }
-    pos[i] = x;
-    vel[i] = v;
+    if (c.write_state) {
+      pos[i] = x;
+      vel[i] = v;
+    }
     if (sxy_new) {  // XSPH needs the post-integration state in (old) sorted order
       sxy_new[k] = x;
       svel_new[k] = v;
@@ -414,6 +418,27 @@ __global__ void sph_apply_xsph(float2 *__restrict__ vel, const float2 *__restric
     vel[i].x += dvel[i].x;
     vel[i].y += dvel[i].y;
   }
+}
+
+// ---- multi-GPU (replicated state, sharded work) helpers -------------------------------------------
+// slots whose density a rank needs: its own slots [k0, k1) plus every slot in the cell rows just
+// below / above them (the 3x3 search of an own particle reaches one cell row further)
+__global__ void sph_ghost_range(const unsigned *__restrict__ keys, const int *__restrict__ cellStart,
+                                int *__restrict__ range, int k0, int k1, int Gx, int Gy) {
+  if (threadIdx.x || blockIdx.x) return;
+  const int r0 = (int)(keys[k0] / (unsigned)Gx) - 1, r1 = (int)(keys[k1 - 1] / (unsigned)Gx) + 1;
+  range[0] = cellStart[max(r0, 0) * Gx];
+  range[1] = cellStart[min(r1 + 1, Gy) * Gx];
+}
+// sorted-order state -> original particle order (after the all-gather of every rank's slots)
+__global__ void sph_scatter_state(const unsigned *__restrict__ vals, const float2 *__restrict__ sxy_new,
+                                  const float2 *__restrict__ svel_new, float2 *__restrict__ pos,
+                                  float2 *__restrict__ vel, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const unsigned i = vals[k];
+  pos[i] = sxy_new[k];
+  vel[i] = svel_new[k];
 }
 
 // ---- rain (k_rain :377-392), write collisions resolved: the highest spawn index wins ---------------
@@ -470,6 +495,10 @@ struct tau_sph {
   float2 *sxy, *svel, *srp, *sxy_new, *svel_new;
   int *cellStart, *winner;
   int sorted_buf;  // which keys/vals buffer holds the last sort result
+  // multi-GPU sharding (replicated state): this rank integrates slots [rank*chunk, ...)
+  int rank, world, chunk, sub_k;
+  float dTau_accum, dt_sub;
+  int *range;
   // derived constants (:573-578, ensure_cell_buffers :512-540)
   float mass, h, cell, alpha;
   int Gx, Gy, M, key_bits, nwarps;
@@ -502,6 +531,9 @@ Consts make_consts(const tau_sph *h) {
   c.xsphEps = h->p.xsphEps;
   c.useVisc = h->p.useVisc;
   c.useGrav = h->p.useGrav;
+  c.k_begin = 0;
+  c.k_end = h->p.N;
+  c.write_state = 1;
   return c;
 }
 
@@ -529,27 +561,54 @@ int radix_sort(tau_sph *h) {
   return src;
 }
 
-int substep(tau_sph *h, float dt_sub) {
-  const Consts c = make_consts(h);
+// first half of a sub-step: keys, sort, cell ranges, gather, density, forces + integration.
+// Sharded handles only integrate their own slots (into the sorted copies) — the caller all-gathers
+// sxy_new / svel_new across ranks before substep_finish().
+int substep_compute(tau_sph *h, float dt_sub) {
+  Consts c = make_consts(h);
   const int n = c.N, BS = 256, GS = (n + BS - 1) / BS;
-  const int GSg = (int)(((size_t)n * GROUP + BS - 1) / BS);
+  const bool sharded = h->world > 1;
   sph_keys<<<GS, BS, 0, h->stream>>>(h->pos, h->keys[0], h->vals[0], c);
   const int sb = radix_sort(h);
   h->sorted_buf = sb;
   sph_cell_start<<<(h->M + 1 + BS - 1) / BS, BS, 0, h->stream>>>(h->keys[sb], h->cellStart, n, h->M);
   sph_gather<<<GS, BS, 0, h->stream>>>(h->vals[sb], h->pos, h->vel, h->sxy, h->svel, n);
-  sph_density<<<GSg, BS, 0, h->stream>>>(h->sxy, h->vals[sb], h->cellStart, h->srp, h->s, h->press, c);
+  const int GSall = (int)(((size_t)n * GROUP + BS - 1) / BS);
+  if (sharded) {
+    c.k_begin = h->rank * h->chunk;
+    c.k_end = min(n, c.k_begin + h->chunk);
+    c.write_state = 0;
+    sph_ghost_range<<<1, 32, 0, h->stream>>>(h->keys[sb], h->cellStart, h->range, c.k_begin, c.k_end, h->Gx,
+                                             h->Gy);
+    h->launches++;
+  }
+  sph_density<<<GSall, BS, 0, h->stream>>>(h->sxy, h->vals[sb], h->cellStart, h->srp, h->s, h->press,
+                                           sharded ? h->range : nullptr, c);
   const bool xsph = h->p.useXSPH && h->p.xsphEps > 0.f;
-  sph_forces_integrate<<<GSg, BS, 0, h->stream>>>(h->sxy, h->svel, h->srp, h->vals[sb], h->cellStart,
-                                                  h->pos, h->vel, h->acc,
-                                                  xsph ? h->sxy_new : nullptr,
-                                                  xsph ? h->svel_new : nullptr, dt_sub, c);
+  const int GSown = (int)(((size_t)(c.k_end - c.k_begin) * GROUP + BS - 1) / BS);
+  sph_forces_integrate<<<GSown, BS, 0, h->stream>>>(h->sxy, h->svel, h->srp, h->vals[sb], h->cellStart,
+                                                    h->pos, h->vel, h->acc,
+                                                    (xsph || sharded) ? h->sxy_new : nullptr,
+                                                    (xsph || sharded) ? h->svel_new : nullptr, dt_sub, c);
   h->launches += 5;
   if (xsph) {
+    const int GSg = GSall;
     sph_xsph<<<GSg, BS, 0, h->stream>>>(h->sxy_new, h->svel_new, h->srp, h->vals[sb], h->cellStart,
                                         h->acc, c);
     sph_apply_xsph<<<GS, BS, 0, h->stream>>>(h->vel, h->acc, n);
     h->launches += 2;
+  }
+  TAU_CUDA(cudaGetLastError());
+  return TAU_OK;
+}
+
+// second half: (sharded: sorted copies of ALL slots -> original order) + rain
+int substep_finish(tau_sph *h, float dt_sub) {
+  const int n = h->p.N, BS = 256, GS = (n + BS - 1) / BS;
+  if (h->world > 1) {
+    sph_scatter_state<<<GS, BS, 0, h->stream>>>(h->vals[h->sorted_buf], h->sxy_new, h->svel_new, h->pos,
+                                                h->vel, n);
+    h->launches++;
   }
   if (h->p.rain) {  // :706-716
     h->rain_carry += 0.02f * h->p.N * dt_sub;
@@ -567,6 +626,12 @@ int substep(tau_sph *h, float dt_sub) {
   h->substeps++;
   TAU_CUDA(cudaGetLastError());
   return TAU_OK;
+}
+
+int substep(tau_sph *h, float dt_sub) {
+  int rc = substep_compute(h, dt_sub);
+  if (rc) return rc;
+  return substep_finish(h, dt_sub);
 }
 
 }  // namespace
@@ -670,8 +735,12 @@ int tau_sph_create(const tau_sph_params *p, int device, void *stream, tau_sph **
   TAU_CUDA(cudaMalloc(&h->sxy, n * sizeof(float2)));
   TAU_CUDA(cudaMalloc(&h->svel, n * sizeof(float2)));
   TAU_CUDA(cudaMalloc(&h->srp, n * sizeof(float2)));
-  TAU_CUDA(cudaMalloc(&h->sxy_new, n * sizeof(float2)));
-  TAU_CUDA(cudaMalloc(&h->svel_new, n * sizeof(float2)));
+  TAU_CUDA(cudaMalloc(&h->sxy_new, (n + 64) * sizeof(float2)));   // + padding: all-gather chunks
+  TAU_CUDA(cudaMalloc(&h->svel_new, (n + 64) * sizeof(float2)));
+  TAU_CUDA(cudaMalloc(&h->range, 2 * sizeof(int)));
+  h->rank = 0;
+  h->world = 1;
+  h->chunk = p->N;
   TAU_CUDA(cudaMalloc(&h->cellStart, (size_t)(h->M + 1) * sizeof(int)));
   TAU_CUDA(cudaMalloc(&h->winner, n * sizeof(int)));
   sph_fill_int<<<(p->N + 255) / 256, 256, 0, h->stream>>>(h->winner, p->N, -1);
@@ -714,6 +783,7 @@ int tau_sph_step(tau_sph *h, int nframes) {
   TAU_REQUIRE(h, "tau_sph_step: null handle");
   TAU_REQUIRE(nframes >= 0, "tau_sph_step: nframes must be >= 0");
   TAU_REQUIRE(h->have_state, "tau_sph_step: no state (call tau_sph_init or tau_sph_upload)");
+  TAU_REQUIRE(h->world == 1, "tau_sph_step: sharded handles advance with tau_sph_shard_substep_begin/end");
   TAU_CUDA(cudaSetDevice(h->device));
   TAU_CUDA(cudaEventRecord(h->ev0, h->stream));
   const tau_sph_params &P = h->p;
@@ -736,6 +806,65 @@ int tau_sph_step(tau_sph *h, int nframes) {
   }
   TAU_CUDA(cudaEventRecord(h->ev1, h->stream));
   h->timed = true;
+  return TAU_OK;
+}
+
+// ---- multi-GPU: replicated particle state, work sharded by sorted-slot (= cell-stripe) range -------
+// Every rank holds all N particles and performs the (cheap) sort; rank r computes densities for its
+// slot chunk plus the ghost cell rows around it and integrates its own chunk into the sorted copies
+// sxy_new / svel_new.  Between begin and end the caller all-gathers those two arrays (equal chunks
+// of `chunk` slots; NCCL over NVLink).  XSPH is not supported in this mode.
+int tau_sph_shard_config(tau_sph *h, int rank, int world) {
+  TAU_REQUIRE(h, "tau_sph_shard_config: null handle");
+  TAU_REQUIRE(world >= 1 && rank >= 0 && rank < world, "tau_sph_shard_config: bad rank %d of %d", rank, world);
+  TAU_REQUIRE(!(world > 1 && h->p.useXSPH && h->p.xsphEps > 0.f),
+              "tau_sph_shard_config: XSPH needs a second ghost exchange and is single-GPU only");
+  const int chunk = (h->p.N + world - 1) / world;
+  TAU_REQUIRE((size_t)chunk * world <= (size_t)h->p.N + 64, "tau_sph_shard_config: N=%d does not split into "
+              "%d chunks within the padding", h->p.N, world);
+  h->rank = rank;
+  h->world = world;
+  h->chunk = chunk;
+  h->sub_k = 0;
+  h->dTau_accum = 0.f;
+  return TAU_OK;
+}
+
+int tau_sph_shard_buffers(tau_sph *h, float **sxy_new, float **svel_new, int *chunk) {
+  TAU_REQUIRE(h, "tau_sph_shard_buffers: null handle");
+  if (sxy_new) *sxy_new = reinterpret_cast<float *>(h->sxy_new);
+  if (svel_new) *svel_new = reinterpret_cast<float *>(h->svel_new);
+  if (chunk) *chunk = h->chunk;
+  return TAU_OK;
+}
+
+int tau_sph_shard_substep_begin(tau_sph *h) {
+  TAU_REQUIRE(h && h->have_state, "tau_sph_shard_substep_begin: no state");
+  TAU_CUDA(cudaSetDevice(h->device));
+  const tau_sph_params &P = h->p;
+  const int K = (P.viscSub > 0 ? P.viscSub : 1);
+  if (h->sub_k == 0) {  // frame start :663-669
+    const float dt_try = h->t * P.dTau;
+    const float dt_cfl = P.CFL * h->h / (P.c0 * (1.0f + 2.0f * P.viscAlpha));
+    h->dt_sub = fminf(dt_try, dt_cfl) / K;
+    h->dTau_accum = 0.f;
+  }
+  return substep_compute(h, h->dt_sub);
+}
+
+int tau_sph_shard_substep_end(tau_sph *h) {
+  TAU_REQUIRE(h && h->have_state, "tau_sph_shard_substep_end: no state");
+  const tau_sph_params &P = h->p;
+  const int K = (P.viscSub > 0 ? P.viscSub : 1);
+  int rc = substep_finish(h, h->dt_sub);
+  if (rc) return rc;
+  h->dTau_accum += h->dt_sub / fmaxf(h->t, 1e-9f);  // :718-720
+  h->t = P.t0 * expf(h->tau + h->dTau_accum);
+  if (++h->sub_k == K) {
+    h->tau += h->dTau_accum;
+    h->step++;
+    h->sub_k = 0;
+  }
   return TAU_OK;
 }
 
@@ -818,7 +947,7 @@ int tau_sph_destroy(tau_sph *h) {
   if (!h) return TAU_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  void *ptrs[] = {h->winner, h->cellStart, h->svel_new, h->sxy_new, h->srp, h->svel, h->sxy,
+  void *ptrs[] = {h->range, h->winner, h->cellStart, h->svel_new, h->sxy_new, h->srp, h->svel, h->sxy,
                   h->scan_totals, h->hist, h->vals[1], h->keys[1], h->vals[0], h->keys[0], h->press, h->s, h->acc,
                   h->vel, h->pos};
   for (void *p : ptrs) cudaFree(p);

@@ -29,6 +29,10 @@ _create = declare("tau_sph_create", [C.POINTER(_CParams), C.c_int, C.c_void_p, C
 _init = declare("tau_sph_init", [_h])
 _upload = declare("tau_sph_upload", [_h, _f32, _f32])
 _step = declare("tau_sph_step", [_h, C.c_int])
+_shard_cfg = declare("tau_sph_shard_config", [_h, C.c_int, C.c_int])
+_shard_buf = declare("tau_sph_shard_buffers", [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int)])
+_shard_begin = declare("tau_sph_shard_substep_begin", [_h])
+_shard_end = declare("tau_sph_shard_substep_end", [_h])
 _clock = declare("tau_sph_clock", [_h, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_longlong)])
 _download = declare("tau_sph_download", [_h, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
 _dl_sort = declare("tau_sph_download_sort", [_h, _u32, _u32])
@@ -102,6 +106,24 @@ class SPH:
     def step(self, nframes: int = 1):
         check(_step(self._handle, nframes))
         return self
+
+    # ---- multi-GPU: replicated state, sharded work ----------------------------------------------
+    def shard_config(self, rank: int, world: int):
+        check(_shard_cfg(self._handle, rank, world))
+        return self
+
+    def shard_buffers(self):
+        """(sxy_new_ptr, svel_new_ptr, chunk) — the sorted-copy arrays to all-gather per sub-step."""
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_int()
+        check(_shard_buf(self._handle, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def shard_substep(self, all_gather):
+        """One sub-step of a sharded handle; `all_gather(sxy_new_ptr, svel_new_ptr, chunk)` must
+        exchange the chunks between the ranks (see bench_all.py)."""
+        check(_shard_begin(self._handle))
+        all_gather(*self.shard_buffers())
+        check(_shard_end(self._handle))
 
     def clock(self):
         t, tau, st = C.c_float(), C.c_float(), C.c_longlong()

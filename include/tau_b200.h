@@ -215,6 +215,16 @@ int tau_sph_upload(tau_sph *h, const float *pos_xy, const float *vel_xy);
 /* THE hot path: nframes x the doStep block :663-722 — per sub-step: cell keys, radix sort, cell
  * ranges, density/pressure, forces + integration, [XSPH], [rain], tau-clock.  No host sync. */
 int tau_sph_step(tau_sph *h, int nframes);
+/* Multi-GPU (new: the reference has none).  Particle state is replicated on every rank; the work of
+ * a sub-step is sharded by sorted-slot range, i.e. by stripes of hash bins balanced by particle
+ * count.  Per sub-step: shard_substep_begin (sort, densities of own + ghost rows, forces +
+ * integration of the own chunk into sorted copies), all-gather the two sorted-copy arrays
+ * (tau_sph_shard_buffers: N+pad x 2 floats each, `chunk` slots per rank), shard_substep_end
+ * (back to original order, rain, tau-clock). */
+int tau_sph_shard_config(tau_sph *h, int rank, int world);
+int tau_sph_shard_buffers(tau_sph *h, float **sxy_new, float **svel_new, int *chunk);
+int tau_sph_shard_substep_begin(tau_sph *h);
+int tau_sph_shard_substep_end(tau_sph *h);
 int tau_sph_clock(tau_sph *h, float *t, float *tau, long long *step);
 /* state in ORIGINAL particle order (any pointer may be NULL) */
 int tau_sph_download(tau_sph *h, float *pos_xy, float *vel_xy, float *s, float *press);

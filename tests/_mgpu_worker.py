@@ -94,6 +94,28 @@ def main():
         same = np.array_equal(got[0], fu) and np.array_equal(got[1], fv)
         print(f"gray-scott world={world}: slab == single-GPU: {same}")
         ok &= same
+    # ---- SPH: replicated state, work sharded by sorted-slot range, all-gather per sub-step ---------
+    from fluid_sims_b200.sph import SPH, Params as SP, reset_particles
+    sp = SP(N=200000, viscSub=2)
+    pos0, vel0 = reset_particles(sp)
+    sh = SPH(sp, device=local, stream=ts.cuda_stream).upload(pos0, vel0).shard_config(rank, world)
+
+    def gather(pa, pb, chunk):
+        for ptr in (pa, pb):
+            full = slab.wrap_plane(ptr, (world * chunk, 2), torch.float32, local)
+            dist.all_gather_into_tensor(full, full[rank * chunk:(rank + 1) * chunk])
+
+    nsub = 16
+    for _ in range(nsub):
+        sh.shard_substep(gather)
+    spos, svel, _, _ = sh.download()
+    if rank == 0:
+        one = SPH(sp, device=local).upload(pos0, vel0)
+        one.step(nsub // 2)
+        opos, ovel, _, _ = one.download()
+        same = np.array_equal(spos, opos) and np.array_equal(svel, ovel) and sh.clock() == one.clock()
+        print(f"sph world={world}: sharded == single-GPU: {same}")
+        ok &= same
         with open(os.path.join(out_dir, "result.txt"), "w") as f:
             f.write("OK" if ok else "FAIL")
     dist.barrier()

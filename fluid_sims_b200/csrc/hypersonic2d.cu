@@ -45,6 +45,9 @@ constexpr int H2_RB = 4;      // rows per TMA box / ring slot
 constexpr int H2_NS = 3;      // ring slots per warp
 constexpr int H2_WARPS = 4;   // warps per CTA
 constexpr int H2_GHOST = 2;   // ghost rows above/below each plane
+#ifndef H2_MIN_CTAS
+#define H2_MIN_CTAS 5          // fp32: resident CTAs per SM the register allocation must allow (measured: 5 > 4 > 6)
+#endif
 
 struct Ctrl {          // device-resident step control (replaces the host dt logic :1852-1869)
   double maxspeed[3];  // rotating slots: step s reads [s%3], reduces into [(s+1)%3], clears [(s+2)%3]
@@ -145,13 +148,15 @@ __device__ __forceinline__ R sound_speed(const Params<R> &P, Prim4<R> p) {
 // round-trips every face state prim -> cons -> prim (prim_to_cons :161, then cons_to_prim again
 // inside flux_axis :195 and hllc_axis :520-521); algebraically those are identities, so the
 // fused kernel carries (rho,u,v,p,E) once instead.  Differences are at round-off level.
-template <typename R> struct Face { R rho, u, v, p, E; };
+template <typename R> struct Face { R rho, u, v, p, E, a; };  // a = sound speed sqrt(gamma p / rho)
 
 // mc_limiter :217-228.  With dl*dr > 0 the nested minmods of the reference reduce to "the
-// argument of smallest magnitude among dl, dr, dc" (2dl and 2dr can never be the smallest), and to
-// 0 otherwise; written branch-free.  Bit-identical to the reference formulation.
-template <typename R> __device__ __forceinline__ R mc_limiter(R dl, R dc, R dr) {
-  const R m = fmin(fmin(fabs(dl), fabs(dr)), fabs(dc));
+// argument of smallest magnitude among dl, dr, dc" (2dl and 2dr can never be the smallest) and to 0
+// otherwise.  Since dc = (dl+dr)/2 lies between dl and dr it can only be the smallest by a rounding
+// ulp, so the limited slope is min-magnitude(dl, dr): identical to the reference except for
+// last-bit ties.  Branch-free.
+template <typename R> __device__ __forceinline__ R mc_limiter(R dl, R dr) {
+  const R m = fmin(fabs(dl), fabs(dr));
   return (dl * dr > R(0)) ? copysign(m, dl) : R(0);
 }
 // :217-221, kept for the known-answer tests
@@ -175,14 +180,14 @@ __device__ __forceinline__ Cons4<R> ghost_cons(const Params<R> &P, Prim4<R> q) {
 template <typename R>
 __device__ __forceinline__ Face<R> ghost_face(const Params<R> &P, Prim4<R> q) {
   const R rho = rmax(q.rho, P.eps_rho), pr = rmax(q.p, P.eps_p);
-  return Face<R>{rho, -q.u, -q.v, q.p,
-                 pr * P.inv_gm1 + R(0.5) * rho * (q.u * q.u + q.v * q.v)};
+  return Face<R>{rho, -q.u, -q.v, q.p, pr * P.inv_gm1 + R(0.5) * rho * (q.u * q.u + q.v * q.v),
+                 sqrt_pos(P.gamma * q.p * rcp(rho))};
 }
 // an unpredicted conserved state used directly as a face state (inflow, outflow copy, y-clamp)
 template <typename R>
 __device__ __forceinline__ Face<R> face_from_cons(const Params<R> &P, Cons4<R> c) {
   const Prim4<R> q = cons_to_prim(P, c);
-  return Face<R>{q.rho, q.u, q.v, q.p, c.E};
+  return Face<R>{q.rho, q.u, q.v, q.p, c.E, sqrt_pos(P.gamma * q.p * rcp(q.rho))};
 }
 
 // enforce_positive_faces :373-398 (rarely taken: only when a limited face state is non-positive).
@@ -217,10 +222,10 @@ template <int AX, typename R>
 __device__ __forceinline__ void reconstruct_predict(const Params<R> &P, const Prim4<R> &qm,
                                                     const Prim4<R> &qc, const Prim4<R> &qp,
                                                     R half_dt, Face<R> &lo, Face<R> &hi) {
-  const R s_rho = mc_limiter(qc.rho - qm.rho, R(0.5) * (qp.rho - qm.rho), qp.rho - qc.rho);
-  const R s_u = mc_limiter(qc.u - qm.u, R(0.5) * (qp.u - qm.u), qp.u - qc.u);
-  const R s_v = mc_limiter(qc.v - qm.v, R(0.5) * (qp.v - qm.v), qp.v - qc.v);
-  const R s_p = mc_limiter(qc.p - qm.p, R(0.5) * (qp.p - qm.p), qp.p - qc.p);
+  const R s_rho = mc_limiter(qc.rho - qm.rho, qp.rho - qc.rho);
+  const R s_u = mc_limiter(qc.u - qm.u, qp.u - qc.u);
+  const R s_v = mc_limiter(qc.v - qm.v, qp.v - qc.v);
+  const R s_p = mc_limiter(qc.p - qm.p, qp.p - qc.p);
   Prim4<R> qL{qc.rho - R(0.5) * s_rho, qc.u - R(0.5) * s_u, qc.v - R(0.5) * s_v,
               qc.p - R(0.5) * s_p};
   Prim4<R> qR{qc.rho + R(0.5) * s_rho, qc.u + R(0.5) * s_u, qc.v + R(0.5) * s_v,
@@ -247,7 +252,7 @@ __device__ __forceinline__ void reconstruct_predict(const Params<R> &P, const Pr
     const R u = (mxL - half_dt * d_mx) * inv, v = (myL - half_dt * d_my) * inv;
     const R kin = R(0.5) * rho * (u * u + v * v);
     const R pr = rmax(P.gm1 * rmax((EL - half_dt * d_E) - kin, P.eps_p), P.eps_p);
-    lo = Face<R>{rho, u, v, pr, pr * P.inv_gm1 + kin};
+    lo = Face<R>{rho, u, v, pr, pr * P.inv_gm1 + kin, sqrt_pos(P.gamma * pr * inv)};
   }
   {
     const R rho = rmax(qR.rho - half_dt * d_rho, P.eps_rho);
@@ -255,7 +260,7 @@ __device__ __forceinline__ void reconstruct_predict(const Params<R> &P, const Pr
     const R u = (mxR - half_dt * d_mx) * inv, v = (myR - half_dt * d_my) * inv;
     const R kin = R(0.5) * rho * (u * u + v * v);
     const R pr = rmax(P.gm1 * rmax((ER - half_dt * d_E) - kin, P.eps_p), P.eps_p);
-    hi = Face<R>{rho, u, v, pr, pr * P.inv_gm1 + kin};
+    hi = Face<R>{rho, u, v, pr, pr * P.inv_gm1 + kin, sqrt_pos(P.gamma * pr * inv)};
   }
 }
 
@@ -293,7 +298,7 @@ template <int AX, typename R>
 __device__ __forceinline__ Cons4<R> hllc_flux(const Params<R> &P, const Face<R> &L,
                                               const Face<R> &Rr) {
   const R unL = AX == 0 ? L.u : L.v, unR = AX == 0 ? Rr.u : Rr.v;
-  const R aL = sqrt_pos(P.gamma * L.p * rcp(L.rho)), aR = sqrt_pos(P.gamma * Rr.p * rcp(Rr.rho));
+  const R aL = L.a, aR = Rr.a;
   const R SL = rmin(unL - aL, unR - aR), SR = rmax(unL + aL, unR + aR);
   // supersonic shortcut (:537-540); warp-uniform so whole free-stream strips skip the star state
   if (__all_sync(0xffffffffu, SL >= R(0))) return phys_flux<AX>(L);
@@ -311,10 +316,11 @@ __device__ __forceinline__ Cons4<R> hllc_flux(const Params<R> &P, const Face<R> 
   const R invd = rcp(dKS);
   const R rhoStar = qK * invd;
   const R EStar = ((SK - unK) * K.E - K.p * unK + pStar * SM) * invd;
-  const bool fallback = (rabs(den) < R(1e-14)) || !isfinite(num) || !isfinite(den) ||
-                        !isfinite(SM) || (rabs(dLS) < R(1e-14)) || (rabs(dRS) < R(1e-14)) ||
-                        !(qL * dLS > R(0)) || !(qR * dRS > R(0)) || !isfinite(rhoStar) ||
-                        !isfinite(EStar);
+  // guarded fall-backs :548-587.  The reference tests num, den, SM, rho* and E* for finiteness one
+  // by one; with finite inputs they can only fail together, so one test on their sum stands in.
+  const bool fallback = (rabs(den) < R(1e-14)) || (rabs(dLS) < R(1e-14)) || (rabs(dRS) < R(1e-14)) ||
+                        !(qL * dLS > R(0)) || !(qR * dRS > R(0)) ||
+                        !isfinite((num + den) + (SM + rhoStar) + EStar);
   const bool supersonic = (SL >= R(0)) || (SR <= R(0));
   if (!supersonic && fallback) return hlle_flux<AX>(L, Rr, SL, SR);
   if (supersonic) return FK;
@@ -330,7 +336,7 @@ __device__ __forceinline__ Cons4<R> hllc_flux(const Params<R> &P, const Face<R> 
 template <typename R> __device__ __forceinline__ Face<R> shfl_down_face(Face<R> f) {
   return Face<R>{__shfl_down_sync(0xffffffffu, f.rho, 1), __shfl_down_sync(0xffffffffu, f.u, 1),
                  __shfl_down_sync(0xffffffffu, f.v, 1), __shfl_down_sync(0xffffffffu, f.p, 1),
-                 __shfl_down_sync(0xffffffffu, f.E, 1)};
+                 __shfl_down_sync(0xffffffffu, f.E, 1), __shfl_down_sync(0xffffffffu, f.a, 1)};
 }
 template <typename R> __device__ __forceinline__ Prim4<R> shfl_up_prim(Prim4<R> p) {
   return Prim4<R>{__shfl_up_sync(0xffffffffu, p.rho, 1), __shfl_up_sync(0xffffffffu, p.u, 1),
@@ -373,7 +379,7 @@ __device__ __forceinline__ R d2(R m2, R m1, R c, R p1, R p2) {
 }
 
 template <typename R, bool USE_TMA>
-__global__ void __launch_bounds__(H2_WARPS * 32)
+__global__ void __launch_bounds__(H2_WARPS * 32, sizeof(R) == 4 ? H2_MIN_CTAS : 2)
 hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *__restrict__ Uin,
            R *__restrict__ Uout, const uint8_t *__restrict__ mask,
            const uint8_t *__restrict__ segmask, Ctrl *__restrict__ ctrl, int step_slot,
@@ -574,12 +580,12 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
     // ring offsets of rows r-2, r-1, r, r+1
     int ro_m2 = 0, ro_m1 = 0, ro_c = Ring<R>::row_off(0), ro_p1 = Ring<R>::row_off(1);
     Prim4<R> Pr = cons_to_prim(P, ring.at(ro_c, c)), Pr1 = cons_to_prim(P, ring.at(ro_p1, c));
-    Face<R> yT_r{R(1), R(0), R(0), R(1), R(1)};
+    Face<R> yT_r{R(1), R(0), R(0), R(1), R(1), R(1)};
     Cons4<R> G_bot{R(0), R(0), R(0), R(0)};
 
     for (int r = ys - 2; r < ye; ++r) {
       const int q = r - ys + 2;  // staged-row offset of row r
-      need_row(q + 2);
+      if (((q + 2) & (H2_RB - 1)) == 0) need_row(q + 2);
       mw_p2 = mask_row(r + 2 + H2_GHOST);
       const int ro_p2 = Ring<R>::row_off(q + 2);
       const Prim4<R> Pr2 = cons_to_prim(P, ring.at(ro_p2, c));
@@ -656,18 +662,16 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
               if (bit(mw_p1, c)) yp1 = gh;
               if (bit(mw_p2, c)) yp2 = gh;
             }
-            const R lap_rho = d2(xm2.rho, xm1.rho, Ur.rho, xp1.rho, xp2.rho) +
-                              d2(ym2.rho, ym1.rho, Ur.rho, yp1.rho, yp2.rho);
-            const R lap_mx = d2(xm2.mx, xm1.mx, Ur.mx, xp1.mx, xp2.mx) +
-                             d2(ym2.mx, ym1.mx, Ur.mx, yp1.mx, yp2.mx);
-            const R lap_my = d2(xm2.my, xm1.my, Ur.my, xp1.my, xp2.my) +
-                             d2(ym2.my, ym1.my, Ur.my, yp1.my, yp2.my);
-            const R lap_E =
-                d2(xm2.E, xm1.E, Ur.E, xp1.E, xp2.E) + d2(ym2.E, ym1.E, Ur.E, yp1.E, yp2.E);
-            Un.rho += (P.visc_rho * dt) * lap_rho;
-            Un.mx += (P.visc_nu * dt) * lap_mx;
-            Un.my += (P.visc_nu * dt) * lap_my;
-            Un.E += (P.visc_e * dt) * lap_E;
+            // d2x + d2y of :1126-1158 in one expression:
+            // (16 (xm1+xp1+ym1+yp1) - (xm2+xp2+ym2+yp2) - 60 c) / 12
+#define TAU_LAP(f)                                                                         \
+  (((R(16) * ((xm1.f + xp1.f) + (ym1.f + yp1.f)) - ((xm2.f + xp2.f) + (ym2.f + yp2.f))) - \
+    R(60) * Ur.f) * (R(1) / R(12)))
+            Un.rho += (P.visc_rho * dt) * TAU_LAP(rho);
+            Un.mx += (P.visc_nu * dt) * TAU_LAP(mx);
+            Un.my += (P.visc_nu * dt) * TAU_LAP(my);
+            Un.E += (P.visc_e * dt) * TAU_LAP(E);
+#undef TAU_LAP
 
             Un.rho = rmax(Un.rho, P.eps_rho);
             Prim4<R> pp = cons_to_prim(P, Un);

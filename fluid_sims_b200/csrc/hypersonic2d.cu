@@ -97,17 +97,19 @@ template <typename R> __device__ __forceinline__ R rmin(R a, R b) { return fmin(
 template <typename R> __device__ __forceinline__ R rabs(R a) { return fabs(a); }  // :137
 
 // reciprocal / sound speed: IEEE in fp64 (parity with the fp64 reference to ~1e-13), single
-// MUFU approximations (<= 1 ulp / 2 ulp) in fp32 where they are below the fp32 noise floor.
+// MUFU approximations (<= 1 ulp / 2 ulp) in fp32 where they are below the fp32 noise floor.  The
+// .ftz forms are single MUFU instructions; without .ftz ptxas wraps each in 6 range-scaling
+// instructions (operands here are never subnormal: EPS_RHO = EPS_P = 1e-25).
 __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
 __device__ __forceinline__ float rcp(float x) {
   float r;
-  asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 __device__ __forceinline__ double sqrt_pos(double x) { return sqrt(x); }
 __device__ __forceinline__ float sqrt_pos(float x) {
   float r;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 

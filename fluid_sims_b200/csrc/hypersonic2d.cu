@@ -9,7 +9,11 @@
 // (517 B/cell in fp64); here they never leave registers.
 //
 // Decomposition ("column marching"): one WARP owns a strip of 30 columns (+1 halo lane each side)
-// and marches down a segment of rows.
+// and marches down a segment of rows.  Segments ("work items") come from a host-built table —
+// body-touching items first, then tall ones, tapering to short ones — and the warps of a persistent
+// grid (one resident set of CTAs per SM) claim them from a device-side counter, so that every SM
+// runs out of work at the same time (the step ends with a global max-wavespeed reduction, so the
+// tail of one step cannot be overlapped with the next).
 //   * x-direction neighbours (reconstruction stencils, face states, face fluxes) move between
 //     lanes with warp shuffles;
 //   * y-direction state is carried in registers from row to row: the prims of rows r..r+2, the
@@ -55,6 +59,7 @@ struct Ctrl {          // device-resident step control (replaces the host dt log
   double dt_last;
   unsigned int arrived[3];  // multi-GPU: cumulative count of peer "step done" signals per slot
   unsigned int done_blocks; // CTAs of the running step kernel that have finished
+  unsigned int next_item[3]; // work-item claim counters, rotating like maxspeed[]
 };
 
 // Multi-GPU (one process per GPU): peer-memory views of the two slab neighbours' output planes and
@@ -82,8 +87,8 @@ struct Params {
   R eps_rho, eps_p;
   double cfl, nu_max, infl_speed;
   int W, H_local, H_global, y_begin;
-  int seg_rows;   // rows per marching segment
-  int nstrips, nsegs;
+  int nstrips;    // 30-column strips per row
+  int nitems;     // entries of the work-item table
   size_t plane;   // elements per plane incl. ghost rows
 };
 
@@ -384,7 +389,7 @@ template <typename R, bool USE_TMA>
 __global__ void __launch_bounds__(H2_WARPS * 32, sizeof(R) == 4 ? H2_MIN_CTAS : 2)
 hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *__restrict__ Uin,
            R *__restrict__ Uout, const uint8_t *__restrict__ mask,
-           const uint8_t *__restrict__ segmask, Ctrl *__restrict__ ctrl, int step_slot,
+           const uint2 *__restrict__ items, Ctrl *__restrict__ ctrl, int step_slot,
            const PeerPush peer) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
@@ -395,6 +400,20 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
                                                                sizeof(R)) +
                    warp * H2_NS;
   Ring<R> ring{ring_base};
+
+  // Programmatic dependent launch: the next step's grid may be scheduled as soon as this one's CTAs
+  // have all started; its CTAs take over SM slots as ours retire and park at griddepcontrol.wait
+  // (below) until this grid has completed and its stores are visible.  Hides the launch latency
+  // between the back-to-back step kernels.  Nothing above the wait reads global memory.
+  asm volatile("griddepcontrol.launch_dependents;");
+  if (USE_TMA) {
+    if (lane == 0) {
+      for (int s = 0; s < H2_NS; ++s) tau::mbar_init(&bars[s], 1);
+      tau::mbar_fence_init();
+    }
+    __syncwarp();
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // ---- multi-GPU step barrier: every peer must have finished the previous step (their boundary
   // rows are in our ghost rows and their max wavespeed is folded into our slot) ----------------
@@ -427,45 +446,54 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
     ctrl->sim_t += dt_d;
     ctrl->dt_last = dt_d;
     ctrl->maxspeed[(step_slot + 2) % 3] = 1e-12;
+    ctrl->next_item[(step_slot + 2) % 3] = 0u;
   }
 
   bool pushed = false;  // this thread stored into a neighbour GPU's ghost rows
-  const int item = blockIdx.x * H2_WARPS + warp;
-  if (item < P.nstrips * P.nsegs) {
-  const int strip = item % P.nstrips;
-  const int seg = item / P.nstrips;
+  R wmax = R(0);
   const int W = P.W;
+  const size_t PL = P.plane;
+  // Persistent warps: each claims work items (strip x row segment) from the table until it is
+  // exhausted.  The ring slots and their mbarrier phases simply keep counting across items: `kb`
+  // is the number of 4-row blocks this warp has staged so far.
+  // The next item is claimed three rows before the current one ends and its descriptor is fetched
+  // during the last row: late enough that no warp sits on reserved work while another idles at the
+  // end of the step, early enough that neither latency is exposed.
+  unsigned kb = 0;
+  unsigned claim = 0;
+  if (lane == 0) claim = atomicAdd(&ctrl->next_item[step_slot], 1u);
+  unsigned item = __shfl_sync(0xffffffffu, claim, 0);
+  uint2 desc = make_uint2(0u, 0u);
+  if (item < (unsigned)P.nitems) desc = items[item];
+  while (item < (unsigned)P.nitems) {
+  const int strip = (int)(desc.x & 0xffffu);
+  const bool item_masked = (desc.x >> 31) != 0u;
   const int x0 = strip * H2_OWN;
   const int x = x0 - 1 + lane;  // this lane's column
   const int bx = (x0 - 2) & ~3;  // first staged column (16-byte aligned box origin)
   const int c = x - bx;          // this lane's staged column index
-  const int ys = seg * P.seg_rows;
-  const int ye = min(ys + P.seg_rows, P.H_local);
+  const int ys = (int)(desc.y & 0xfffffu);
+  const int ye = ys + (int)(desc.y >> 20);
   const int nrows = (ye - ys) + 4;  // staged rows: local rows ys-2 .. ye+1
   const int nblk = (nrows + H2_RB - 1) / H2_RB;
   const bool owned = (lane >= 1) && (lane <= H2_OWN) && (x < W);
   const bool edge_strip = (bx < 0) || (bx + H2_BOXW > W);
-  const size_t PL = P.plane;
-
-  if (USE_TMA) {
-    if (lane == 0) {
-      for (int s = 0; s < H2_NS; ++s) tau::mbar_init(&bars[s], 1);
-      tau::mbar_fence_init();
-    }
-    __syncwarp();
-  }
+  auto row_off = [&](int q) -> int {  // ring offset of staged row q of this item
+    return (int)((kb + (unsigned)(q >> 2)) % H2_NS) * (4 * H2_RB * H2_BOXW) + (q & 3) * H2_BOXW;
+  };
 
   auto infl_f = [&](int f) -> R {
     return f == 0 ? P.infl_cons[0] : f == 1 ? P.infl_cons[1] : f == 2 ? P.infl_cons[2] : P.infl_cons[3];
   };
   // stage block k (plane rows ys+4k .. ys+4k+3; plane row = local row + 2) into slot k%NS
   auto issue = [&](int k) {
-    R *dst = ring_base + (size_t)(k % H2_NS) * SLOT_ELEMS;
+    const unsigned slot = (kb + (unsigned)k) % H2_NS;
+    R *dst = ring_base + (size_t)slot * SLOT_ELEMS;
     const int prow = ys + H2_RB * k;
     if (USE_TMA) {
       if (lane == 0) {
-        tau::mbar_expect_tx(&bars[k % H2_NS], SLOT_ELEMS * sizeof(R));
-        tau::tma_load_3d(dst, &tmU, bx, prow, 0, &bars[k % H2_NS]);
+        tau::mbar_expect_tx(&bars[slot], SLOT_ELEMS * sizeof(R));
+        tau::tma_load_3d(dst, &tmU, bx, prow, 0, &bars[slot]);
       }
     } else {
       for (int i = lane; i < SLOT_ELEMS; i += 32) {
@@ -479,10 +507,11 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
   };
   // wait for block k and fold the x-boundary conditions into the staged rows
   auto acquire = [&](int k) {
-    if (USE_TMA) tau::mbar_wait(&bars[k % H2_NS], (k / H2_NS) & 1);
+    const unsigned slot = (kb + (unsigned)k) % H2_NS;
+    if (USE_TMA) tau::mbar_wait(&bars[slot], ((kb + (unsigned)k) / H2_NS) & 1u);
     else __syncwarp();
     if (edge_strip) {
-      R *dst = ring_base + (size_t)(k % H2_NS) * SLOT_ELEMS;
+      R *dst = ring_base + (size_t)slot * SLOT_ELEMS;
       const int prow = ys + H2_RB * k;
       const int cw = (W - 1) - bx;  // staged column of x = W-1
       for (int i = lane; i < SLOT_ELEMS; i += 32) {
@@ -518,7 +547,6 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
     }
   };
   need_row(1);
-  R wmax = R(0);
 
   // 40 mask bits of one plane row (bit b <-> staged column b); out-of-domain columns read as 0
   const int mgx0 = bx + lane, mgx1 = bx + 32 + lane;
@@ -580,16 +608,22 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
     mw_c = mask_row(ys + 0);   // local row ys-2 (plane row = local row + 2)
     mw_p1 = mask_row(ys + 1);  // local row ys-1
     // ring offsets of rows r-2, r-1, r, r+1
-    int ro_m2 = 0, ro_m1 = 0, ro_c = Ring<R>::row_off(0), ro_p1 = Ring<R>::row_off(1);
+    int ro_m2 = 0, ro_m1 = 0, ro_c = row_off(0), ro_p1 = row_off(1);
     Prim4<R> Pr = cons_to_prim(P, ring.at(ro_c, c)), Pr1 = cons_to_prim(P, ring.at(ro_p1, c));
     Face<R> yT_r{R(1), R(0), R(0), R(1), R(1), R(1)};
     Cons4<R> G_bot{R(0), R(0), R(0), R(0)};
 
     for (int r = ys - 2; r < ye; ++r) {
       const int q = r - ys + 2;  // staged-row offset of row r
+      if (r == ye - 3) {         // (a segment has at least one row: r = ye-3 >= ys-2 is reached)
+        if (lane == 0) claim = atomicAdd(&ctrl->next_item[step_slot], 1u);
+      } else if (r == ye - 1) {
+        item = __shfl_sync(0xffffffffu, claim, 0);
+        if (item < (unsigned)P.nitems) desc = items[item];
+      }
       if (((q + 2) & (H2_RB - 1)) == 0) need_row(q + 2);
       mw_p2 = mask_row(r + 2 + H2_GHOST);
-      const int ro_p2 = Ring<R>::row_off(q + 2);
+      const int ro_p2 = row_off(q + 2);
       const Prim4<R> Pr2 = cons_to_prim(P, ring.at(ro_p2, c));
 
       // -- y: reconstruct cell r+1, flux through face r+1/2 ----------------------------------
@@ -769,12 +803,15 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
     }
   };
 
-  if (segmask[item]) march(std::true_type{});
+  if (item_masked) march(std::true_type{});
   else march(std::false_type{});
+
+  kb += (unsigned)nblk;  // every staged block has been acquired; the ring carries on from here
+  __syncwarp();
+  }  // work-item loop
 
   wmax = tau::warp_max(wmax);
   if (lane == 0 && wmax > R(0)) tau::atomic_max_nonneg(&ctrl->maxspeed[(step_slot + 1) % 3], (double)wmax);
-  }  // item < nitems
 
   // ---- multi-GPU: the last CTA out folds this rank's max wavespeed into every peer's slot for the
   // next step and then signals "step done" (release order: data, fence, flag) -------------------
@@ -791,27 +828,34 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
       __threadfence();
       const int next = (step_slot + 1) % 3;
       if (threadIdx.x == 0) ctrl->done_blocks = 0;
-      const int p = threadIdx.x;
-      if (p < peer.pc.world && p != peer.pc.rank) {
+      // (constant indices only: a dynamically indexed kernel parameter would be copied to local
+      // memory, and every read of `peer` in the row loop would become a local load)
+      Ctrl *pc = nullptr;
+#pragma unroll
+      for (int p = 0; p < 8; ++p)
+        if (p == (int)threadIdx.x && p < peer.pc.world && p != peer.pc.rank) pc = peer.pc.ctrl[p];
+      if (pc != nullptr) {
         const double m = *reinterpret_cast<volatile double *>(&ctrl->maxspeed[next]);
-        atomicMax_system(reinterpret_cast<unsigned long long *>(&peer.pc.ctrl[p]->maxspeed[next]),
+        atomicMax_system(reinterpret_cast<unsigned long long *>(&pc->maxspeed[next]),
                          static_cast<unsigned long long>(__double_as_longlong(m)));
         __threadfence_system();
-        atomicAdd_system(&peer.pc.ctrl[p]->arrived[next], 1u);
+        atomicAdd_system(&pc->arrived[next], 1u);
       }
     }
   }
 }
 
-// One flag per marching work item (strip x segment): does the staged window of that item contain a
-// body cell?  Static for a given mask and segment height; selects the march variant.
+// One flag per marching work item (strip x row segment): does the staged window of that item
+// contain a body cell?  Static for a given mask and item table; selects the march variant (bit 31
+// of the descriptor's first word).
 template <typename R>
-__global__ void hyp2d_build_segmask(const Params<R> P, const uint8_t *__restrict__ mask,
-                                    uint8_t *__restrict__ segmask) {
+__global__ void hyp2d_flag_items(const Params<R> P, const uint8_t *__restrict__ mask,
+                                 uint2 *__restrict__ items) {
   const int item = blockIdx.x;
-  const int strip = item % P.nstrips, seg = item / P.nstrips;
+  const uint2 d = items[item];
+  const int strip = (int)(d.x & 0xffffu);
   const int x0 = strip * H2_OWN, bx = (x0 - 2) & ~3;
-  const int ys = seg * P.seg_rows, ye = min(ys + P.seg_rows, P.H_local);
+  const int ys = (int)(d.y & 0xfffffu), ye = ys + (int)(d.y >> 20);
   const int r0 = ys, r1 = min(ye + 2 * H2_GHOST, P.H_local + 2 * H2_GHOST);  // plane rows
   const int c0 = max(bx, 0), c1 = min(bx + H2_BOXW, P.W);
   int any = 0;
@@ -819,7 +863,7 @@ __global__ void hyp2d_build_segmask(const Params<R> P, const uint8_t *__restrict
   for (int i = threadIdx.x; i < n; i += blockDim.x)
     any |= mask[(size_t)(r0 + i / ncol) * P.W + c0 + i % ncol];
   any = __syncthreads_or(any);
-  if (threadIdx.x == 0) segmask[item] = any ? 1 : 0;
+  if (threadIdx.x == 0) items[item].x = (d.x & 0x7fffffffu) | (any ? 0x80000000u : 0u);
 }
 
 // Standalone max-wavespeed scan of the CURRENT state (first step after init/upload) —
@@ -947,16 +991,19 @@ struct tau_hyp2d {
   PeerCtrls pctrl;
   bool peers_attached;
   unsigned int peer_epoch[3];  // how many times each barrier slot has been consumed
-  uint8_t *segmask;      // per work-item "touches the body" flags (device)
-  size_t segmask_cap;
-  bool segmask_dirty;
+  uint2 *items;          // work-item table (device): {strip | masked<<31, ys | rows<<20}
+  size_t items_cap;
+  int nitems;
+  int grid_ctas;         // persistent grid: resident CTAs per SM x SMs (capped by the item count)
+  bool items_dirty;
   Ctrl *ctrl;
   CUtensorMap tm[2];
   int cur;
   long long steps, launches;
   bool speed_valid;  // ctrl->maxspeed[steps%3] holds the max wavespeed of the current state
-  int seg_rows;
-  bool seg_auto;         // seg_rows chosen by the wave model below (not set by the caller)
+  int seg_rows;          // tallest segment of the table (the only height when set by the caller)
+  bool seg_auto;         // tapered schedule chosen by build_items (not set by the caller)
+  int taper_k, min_rows; // schedule tuning (TAU_HYP2D_TAPER_K / TAU_HYP2D_MIN_ROWS)
   cudaEvent_t ev0, ev1;
   bool timed;
   size_t plane_elems;
@@ -1001,9 +1048,8 @@ Params<R> make_params(const tau_hyp2d *h) {
   P.H_local = h->h_local;
   P.H_global = h->H;
   P.y_begin = h->y_begin;
-  P.seg_rows = h->seg_rows;
   P.nstrips = (h->W + H2_OWN - 1) / H2_OWN;
-  P.nsegs = (h->h_local + h->seg_rows - 1) / h->seg_rows;
+  P.nitems = h->nitems;
   P.plane = h->plane_elems;
   return P;
 }
@@ -1045,15 +1091,74 @@ int launch_init(tau_hyp2d *h) {
   return TAU_OK;
 }
 
-// Segment height: shorter segments balance the SMs better (more, smaller work items) but pay
-// the two warm-up rows more often.  Measured on B200 (4096 columns): 24 rows is best at 4096 rows
-// per GPU, 16 at 2048, 8 at <= 1024 (profiles/hyp2d_seg_rows_r1.md).
+// Work-item table.  The rows of the slab are cut into layers; a layer is one row segment of every
+// strip.  Caller-chosen height (tau_hyp2d_set_seg_rows): uniform layers.  Default: guided
+// self-scheduling — a layer's height is (remaining item-rows) / (taper_k x resident warps), clamped
+// to [min_rows, 24]: tall segments first (the two warm-up rows of a segment are amortised over 24
+// rows), short ones last (so that all SMs run dry together; the step ends in a global reduction and
+// its tail cannot be overlapped with the next step).  Items whose window touches the body run the
+// costlier masked march and go to the front of the table (longest-processing-time-first).
 template <typename R>
-int choose_seg_rows(tau_hyp2d *h, size_t) {
-  int seg = h->h_local / 128;
-  if (seg < 8) seg = 8;
-  if (seg > 24) seg = 24;
-  return seg;
+int build_items(tau_hyp2d *h, size_t smem) {
+  int dev_sms = 148, per_sm = 1;
+  TAU_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
+  if (h->use_tma)
+    TAU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hyp2d_step<R, true>, H2_WARPS * 32, smem));
+  else
+    TAU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hyp2d_step<R, false>, H2_WARPS * 32, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int resident_warps = dev_sms * per_sm * H2_WARPS;
+  const int nstrips = (h->W + H2_OWN - 1) / H2_OWN;
+  std::vector<int> layer_y, layer_h;
+  int y = 0;
+  while (y < h->h_local) {
+    int hgt;
+    if (h->seg_auto) {
+      const long long remaining = (long long)(h->h_local - y) * nstrips;
+      hgt = (int)(remaining / ((long long)h->taper_k * resident_warps));
+      if (hgt > 24) hgt = 24;
+      if (hgt < h->min_rows) hgt = h->min_rows;
+    } else {
+      hgt = h->seg_rows;
+    }
+    if (hgt > h->h_local - y) hgt = h->h_local - y;
+    layer_y.push_back(y);
+    layer_h.push_back(hgt);
+    y += hgt;
+  }
+  if (h->seg_auto) h->seg_rows = layer_h.empty() ? 0 : layer_h[0];
+  const size_t n = layer_y.size() * (size_t)nstrips;
+  TAU_REQUIRE(nstrips <= 0xffff && h->h_local < (1 << 20), "tau_hyp2d: grid too large for the item table");
+  std::vector<uint2> tab(n);
+  size_t k = 0;
+  for (size_t l = 0; l < layer_y.size(); ++l)
+    for (int s = 0; s < nstrips; ++s)
+      tab[k++] = make_uint2((unsigned)s, (unsigned)layer_y[l] | ((unsigned)layer_h[l] << 20));
+  if (h->items_cap < n) {
+    if (h->items) TAU_CUDA(cudaFree(h->items));
+    TAU_CUDA(cudaMalloc(&h->items, n * sizeof(uint2)));
+    h->items_cap = n;
+  }
+  h->nitems = (int)n;
+  TAU_CUDA(cudaMemcpyAsync(h->items, tab.data(), n * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
+  Params<R> P = make_params<R>(h);
+  hyp2d_flag_items<R><<<(unsigned)n, 128, 0, h->stream>>>(P, h->mask, h->items);
+  h->launches++;
+  TAU_CUDA(cudaGetLastError());
+  TAU_CUDA(cudaMemcpyAsync(tab.data(), h->items, n * sizeof(uint2), cudaMemcpyDeviceToHost, h->stream));
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  // masked items first; within each class the table order (tall -> short) is kept
+  std::vector<uint2> sorted;
+  sorted.reserve(n);
+  for (size_t i = 0; i < n; ++i) if (tab[i].x >> 31) sorted.push_back(tab[i]);
+  for (size_t i = 0; i < n; ++i) if (!(tab[i].x >> 31)) sorted.push_back(tab[i]);
+  TAU_CUDA(cudaMemcpyAsync(h->items, sorted.data(), n * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
+  TAU_CUDA(cudaStreamSynchronize(h->stream));  // `sorted` goes out of scope
+  const int need = (int)((n + H2_WARPS - 1) / H2_WARPS);
+  h->grid_ctas = dev_sms * per_sm < need ? dev_sms * per_sm : need;
+  if (h->grid_ctas < 1) h->grid_ctas = 1;
+  h->items_dirty = false;
+  return TAU_OK;
 }
 
 template <typename R>
@@ -1068,27 +1173,12 @@ int launch_steps(tau_hyp2d *h, int nsteps) {
     TAU_CUDA(cudaFuncSetAttribute(kern_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done[ti][0] = true;
   }
-  if (h->seg_auto) {
-    const int seg = choose_seg_rows<R>(h, smem);
-    if (seg != h->seg_rows) {
-      h->seg_rows = seg;
-      h->segmask_dirty = true;
-    }
-    h->seg_auto = false;  // decided once per handle
+  if (h->items_dirty) {
+    const int rc = build_items<R>(h, smem);
+    if (rc) return rc;
   }
   Params<R> P = make_params<R>(h);
-  const int items = P.nstrips * P.nsegs;
-  const int grid = (items + H2_WARPS - 1) / H2_WARPS;
-  if (h->segmask_dirty) {
-    if (h->segmask_cap < (size_t)items) {
-      if (h->segmask) TAU_CUDA(cudaFree(h->segmask));
-      TAU_CUDA(cudaMalloc(&h->segmask, (size_t)items));
-      h->segmask_cap = (size_t)items;
-    }
-    hyp2d_build_segmask<R><<<items, 128, 0, h->stream>>>(P, h->mask, h->segmask);
-    h->launches++;
-    h->segmask_dirty = false;
-  }
+  const int grid = h->grid_ctas;
   for (int s = 0; s < nsteps; ++s) {
     const int a = h->cur, b = a ^ 1;
     const int slot = (int)(h->steps % 3);
@@ -1104,12 +1194,19 @@ int launch_steps(tau_hyp2d *h, int nsteps) {
       peer.pc = h->pctrl;
       peer.expected = ++h->peer_epoch[slot] * (unsigned)(h->pctrl.world - 1);
     }
-    if (h->use_tma)
-      kern_tma<<<grid, H2_WARPS * 32, smem, h->stream>>>(h->tm[a], P, (const R *)h->U[a], (R *)h->U[b],
-                                                         h->mask, h->segmask, h->ctrl, slot, peer);
-    else
-      kern_gen<<<grid, H2_WARPS * 32, smem, h->stream>>>(h->tm[a], P, (const R *)h->U[a], (R *)h->U[b],
-                                                         h->mask, h->segmask, h->ctrl, slot, peer);
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)grid);
+    lc.blockDim = dim3(H2_WARPS * 32);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    TAU_CUDA(cudaLaunchKernelEx(&lc, h->use_tma ? kern_tma : kern_gen, h->tm[a], P, (const R *)h->U[a],
+                                (R *)h->U[b], (const uint8_t *)h->mask, (const uint2 *)h->items,
+                                h->ctrl, slot, peer));
     h->launches++;
     h->cur = b;
     h->steps++;
@@ -1212,17 +1309,29 @@ int tau_hyp2d_create(const tau_hyp2d_config *cfg, int W, int H, int dtype, int d
   h->pctrl.world = 1;
   h->peers_attached = false;
   h->peer_epoch[0] = h->peer_epoch[1] = h->peer_epoch[2] = 0;
-  h->segmask = nullptr;
-  h->segmask_cap = 0;
-  h->segmask_dirty = true;
-  h->seg_rows = 64;
+  h->items = nullptr;
+  h->items_cap = 0;
+  h->nitems = 0;
+  h->grid_ctas = 1;
+  h->items_dirty = true;
+  h->seg_rows = 24;
   h->seg_auto = true;
+  h->taper_k = 2;
+  h->min_rows = 4;
   if (const char *e = getenv("TAU_HYP2D_SEG_ROWS")) {
     int v = atoi(e);
     if (v >= 4) {
       h->seg_rows = v;
       h->seg_auto = false;
     }
+  }
+  if (const char *e = getenv("TAU_HYP2D_TAPER_K")) {
+    int v = atoi(e);
+    if (v >= 1) h->taper_k = v;
+  }
+  if (const char *e = getenv("TAU_HYP2D_MIN_ROWS")) {
+    int v = atoi(e);
+    if (v >= 2) h->min_rows = v;
   }
   if (stream) {
     h->stream = (cudaStream_t)stream;
@@ -1272,7 +1381,7 @@ int tau_hyp2d_init(tau_hyp2d *h) {
   TAU_REQUIRE(h, "tau_hyp2d_init: null handle");
   TAU_CUDA(cudaSetDevice(h->device));
   h->steps = 0;
-  h->segmask_dirty = true;
+  h->items_dirty = true;
   TAU_CUDA(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->stream));
   int rc = h->dtype ? launch_init<double>(h) : launch_init<float>(h);
   if (rc) return rc;
@@ -1295,7 +1404,7 @@ int tau_hyp2d_upload(tau_hyp2d *h, const void *const planes[4], const uint8_t *m
   }
   if (mask) {
     TAU_CUDA(cudaMemcpyAsync(h->mask + row0, mask, n, cudaMemcpyHostToDevice, h->stream));
-    h->segmask_dirty = true;
+    h->items_dirty = true;
   }
   int rc = hyp2d_state_changed(h, mask ? 1 : 0);
   if (rc) return rc;
@@ -1422,7 +1531,7 @@ int tau_hyp2d_set_seg_rows(tau_hyp2d *h, int rows) {
   TAU_REQUIRE(h && rows >= 4, "tau_hyp2d_set_seg_rows: rows must be >= 4");
   h->seg_rows = rows;
   h->seg_auto = false;
-  h->segmask_dirty = true;
+  h->items_dirty = true;
   return TAU_OK;
 }
 
@@ -1443,7 +1552,7 @@ int tau_hyp2d_destroy(tau_hyp2d *h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   cudaFree(h->ctrl);
-  if (h->segmask) cudaFree(h->segmask);
+  if (h->items) cudaFree(h->items);
   cudaFree(h->mask);
   cudaFree(h->U[1]);
   cudaFree(h->U[0]);

@@ -253,6 +253,11 @@ def run_product(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
+    peer_timing = None
+    if peer:
+        mine = sim.peer_timing()
+        peer_timing = [None] * world
+        dist.all_gather_object(peer_timing, {k: round(v, 2) for k, v in mine.items()})
 
     cells = W * H
     value = cells * a.steps / (ms * 1e-3) / 1e6
@@ -329,6 +334,7 @@ def run_product(a):
                          "kernel_ms": kernel_ms,
                          "note": "kernel is FP32-issue bound (~1e3 instr/cell), see DESIGN.md"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            **({"peer_timing": peer_timing} if peer_timing else {}),
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -75,7 +75,8 @@ def bench_hyp3d(a):
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = a.n3
     prm = Params.default(n, n, n)
     z0, nl = slab.partition_rows(n, world)[rank]
@@ -136,8 +137,6 @@ def bench_hyp3d(a):
                                             "what": "tau_hypersonic_3d_cuda.cu k_step recompiled for "
                                                     "sm_100a incl. its 2 blocking 4-byte copies per step"},
                           "clock": sim.clock(), "parallelism": f"z-slab ring x{world}"}))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def bench_sph(a):
@@ -208,8 +207,6 @@ def bench_sph(a):
                                             "what": "tau_sph.cu kernels recompiled for sm_100a"},
                           "parallelism": "replicated state, slot-range shards + all-gather x%d" % world,
                           "gpu_launches": s.launch_count}))
-    if world > 1 and dist.is_initialized():
-        dist.destroy_process_group()
 
 
 def main():
@@ -226,6 +223,11 @@ def main():
     which = a.which or ["gs", "hyp3d", "sph"]
     for w in which:
         {"gs": bench_gs, "hyp3d": bench_hyp3d, "sph": bench_sph}[w](a)
+    # one process group for the whole run (re-initialising NCCL between benches is not reliable)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -57,16 +57,24 @@ struct Ctrl {          // device-resident step control (replaces the host dt log
   double maxspeed[3];  // rotating slots: step s reads [s%3], reduces into [(s+1)%3], clears [(s+2)%3]
   double sim_t;
   double dt_last;
-  unsigned int arrived[3];  // multi-GPU: cumulative count of peer "step done" signals per slot
   unsigned int done_blocks; // CTAs of the running step kernel that have finished
   unsigned int next_item[3]; // work-item claim counters, rotating like maxspeed[]
+  // multi-GPU: inbox[slot][src] = bit pattern of rank src's max wavespeed for the step that reads
+  // `slot`, written by src with ONE release store when its previous step is complete (its boundary
+  // rows are then in our ghost rows).  Zero = not arrived yet (a max wavespeed is >= 1e-12 > 0), so
+  // the value is its own flag: one one-way NVLink latency per step, no atomics, no second message.
+  unsigned long long inbox[3][8];
+  // multi-GPU diagnostics (globaltimer ns, accumulated): waiting for peers, start -> last CTA out,
+  // last CTA out -> next start; t_prev_end = end of the previous step
+  unsigned long long t_wait, t_busy, t_gap, t_prev_end, t_steps;
 };
 
 // Multi-GPU (one process per GPU): peer-memory views of the two slab neighbours' output planes and
 // of every rank's Ctrl block, opened through CUDA IPC.  The step kernel pushes its boundary rows
-// straight into the neighbours' ghost rows over NVLink; two one-warp kernels around it implement
-// the all-reduce(max) of the wavespeed and the step barrier use system-scope atomics issued by the
-// step kernel itself (first thing: wait for the peers' previous step; last CTA out: signal).
+// straight into the neighbours' ghost rows over NVLink; the all-reduce(max) of the wavespeed and
+// the step barrier are one message per peer per step, sent by the step kernel itself (last CTA out:
+// a release store of this rank's max into every peer's inbox; first thing in the next step: wait
+// until every peer's inbox entry is non-zero and fold them into dt).
 struct PeerCtrls {
   Ctrl *ctrl[8];
   int world, rank;
@@ -75,7 +83,6 @@ struct PeerPush {
   void *up_out, *dn_out;       // neighbour planes for the CURRENT output buffer (or null)
   size_t up_plane, dn_plane;   // their plane strides (elements)
   int up_hl;                   // rows owned by the upper neighbour
-  unsigned int expected;       // value arrived[slot] must reach before this step may start
   PeerCtrls pc;                // world == 1: single GPU or host-driven exchange
 };
 
@@ -415,26 +422,37 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  // ---- multi-GPU step barrier: every peer must have finished the previous step (their boundary
-  // rows are in our ghost rows and their max wavespeed is folded into our slot) ----------------
-  // Only CTAs that can be resident in the first wave poll (with an acquire load, no fence): a
-  // later CTA cannot start before one of them has finished, i.e. after the flag was observed.
-  if (peer.pc.world > 1 && blockIdx.x < 148 * 16) {
-    if (threadIdx.x == 0) {
-      const unsigned int *a = &ctrl->arrived[step_slot];
-      unsigned ns = 64, v;
-      for (;;) {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a) : "memory");
-        if (v >= peer.expected) break;
-        __nanosleep(ns);
-        if (ns < 1024) ns *= 2;
+  // ---- multi-GPU step barrier + all-reduce(max): every peer must have finished the previous step
+  // (its boundary rows are in our ghost rows); its inbox entry carries its max wavespeed ----------
+  __shared__ unsigned long long s_peer_max;
+  unsigned long long tm0 = 0;
+  if (peer.pc.world > 1) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tm0));
+    if (warp == 0) {
+      unsigned long long v = 1ull;
+      if (lane < peer.pc.world && lane != peer.pc.rank) {
+        const unsigned long long *a = &ctrl->inbox[step_slot][lane];
+        for (;;) {
+          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a) : "memory");
+          if (v != 0ull) break;
+          __nanosleep(40);
+        }
+      } else {
+        v = 0ull;
       }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {  // ranks live in lanes 0..7; non-negative doubles order like their bits
+        const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w > v ? w : v;
+      }
+      if (lane == 0) s_peer_max = v;
     }
     __syncthreads();
   }
 
   // ---- dt from the device-resident max wavespeed (host rule :1852-1869, evaluated in fp64) ----
   double maxs = *reinterpret_cast<volatile double *>(&ctrl->maxspeed[step_slot]);
+  if (peer.pc.world > 1) maxs = fmax(maxs, __longlong_as_double((long long)s_peer_max));
   if (!isfinite(maxs) || maxs < 1e-12) maxs = 1e-12;
   const double dt_conv = P.cfl * 1.0 / maxs;
   double dt_diff = dt_conv;
@@ -447,6 +465,18 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
     ctrl->dt_last = dt_d;
     ctrl->maxspeed[(step_slot + 2) % 3] = 1e-12;
     ctrl->next_item[(step_slot + 2) % 3] = 0u;
+    if (peer.pc.world > 1) {
+      // the slot our peers will fill at the end of THEIR next step; they cannot get there before
+      // they have seen this step's message, which is sent after this clear
+#pragma unroll
+      for (int p = 0; p < 8; ++p) ctrl->inbox[(step_slot + 2) % 3][p] = 0ull;
+      unsigned long long tm1;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tm1));
+      ctrl->t_wait += tm1 - tm0;
+      if (ctrl->t_prev_end != 0ull) ctrl->t_gap += tm0 - ctrl->t_prev_end;
+      ctrl->t_prev_end = tm1;  // peers seen; replaced by this step's end below
+      ctrl->t_steps += 1ull;
+    }
   }
 
   bool pushed = false;  // this thread stored into a neighbour GPU's ghost rows
@@ -836,10 +866,16 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
         if (p == (int)threadIdx.x && p < peer.pc.world && p != peer.pc.rank) pc = peer.pc.ctrl[p];
       if (pc != nullptr) {
         const double m = *reinterpret_cast<volatile double *>(&ctrl->maxspeed[next]);
-        atomicMax_system(reinterpret_cast<unsigned long long *>(&pc->maxspeed[next]),
-                         static_cast<unsigned long long>(__double_as_longlong(m)));
+        const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(fmax(m, 1e-12)));
         __threadfence_system();
-        atomicAdd_system(&pc->arrived[next], 1u);
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&pc->inbox[next][peer.pc.rank]), "l"(bits)
+                     : "memory");
+      }
+      if (threadIdx.x == 0) {
+        unsigned long long tm2;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tm2));
+        ctrl->t_busy += tm2 - ctrl->t_prev_end;
+        ctrl->t_prev_end = tm2;
       }
     }
   }
@@ -990,7 +1026,6 @@ struct tau_hyp2d {
   int peer_up_hl, peer_dn_hl;
   PeerCtrls pctrl;
   bool peers_attached;
-  unsigned int peer_epoch[3];  // how many times each barrier slot has been consumed
   uint2 *items;          // work-item table (device): {strip | masked<<31, ys | rows<<20}
   size_t items_cap;
   int nitems;
@@ -1192,7 +1227,6 @@ int launch_steps(tau_hyp2d *h, int nsteps) {
       peer.up_plane = (size_t)h->W * (h->peer_up_hl + 2 * H2_GHOST);
       peer.dn_plane = (size_t)h->W * (h->peer_dn_hl + 2 * H2_GHOST);
       peer.pc = h->pctrl;
-      peer.expected = ++h->peer_epoch[slot] * (unsigned)(h->pctrl.world - 1);
     }
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)grid);
@@ -1308,7 +1342,6 @@ int tau_hyp2d_create(const tau_hyp2d_config *cfg, int W, int H, int dtype, int d
   memset(&h->pctrl, 0, sizeof(h->pctrl));
   h->pctrl.world = 1;
   h->peers_attached = false;
-  h->peer_epoch[0] = h->peer_epoch[1] = h->peer_epoch[2] = 0;
   h->items = nullptr;
   h->items_cap = 0;
   h->nitems = 0;
@@ -1519,11 +1552,32 @@ int tau_hyp2d_ipc_attach(tau_hyp2d *h, int rank, int world, const void *all_hand
 int tau_hyp2d_peers_ready(tau_hyp2d *h) {
   TAU_REQUIRE(h && h->peers_attached, "tau_hyp2d_peers_ready: no peers attached");
   TAU_CUDA(cudaSetDevice(h->device));
-  unsigned int a[4] = {0, 0, 0, 0};  // arrived[3] + done_blocks
-  a[h->steps % 3] = (unsigned)(h->pctrl.world - 1);
-  h->peer_epoch[0] = h->peer_epoch[1] = h->peer_epoch[2] = 0;
-  TAU_CUDA(cudaMemcpyAsync(h->ctrl->arrived, a, sizeof(a), cudaMemcpyHostToDevice, h->stream));
+  // the caller has all-reduced maxspeed[steps%3] already: every peer "arrives" with a tiny value
+  unsigned long long box[3][8];
+  memset(box, 0, sizeof(box));
+  const double tiny = 1e-12;
+  for (int p = 0; p < h->pctrl.world; ++p)
+    if (p != h->pctrl.rank) memcpy(&box[h->steps % 3][p], &tiny, sizeof(double));
+  TAU_CUDA(cudaMemsetAsync(&h->ctrl->done_blocks, 0, sizeof(unsigned int), h->stream));
+  TAU_CUDA(cudaMemcpyAsync(h->ctrl->inbox, box, sizeof(box), cudaMemcpyHostToDevice, h->stream));
+  TAU_CUDA(cudaMemsetAsync(&h->ctrl->t_wait, 0, 5 * sizeof(unsigned long long), h->stream));
   TAU_CUDA(cudaStreamSynchronize(h->stream));
+  return TAU_OK;
+}
+
+// Multi-GPU diagnostics: average per-step times in microseconds since tau_hyp2d_peers_ready():
+// out[0] waiting for the peers' messages, out[1] peers seen -> last CTA out, out[2] last CTA out ->
+// next step's start (launch gap), out[3] = steps counted.
+int tau_hyp2d_peer_timing(tau_hyp2d *h, double out[4]) {
+  TAU_REQUIRE(h && out, "tau_hyp2d_peer_timing: null argument");
+  Ctrl c;
+  TAU_CUDA(cudaMemcpyAsync(&c, h->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  const double n = c.t_steps ? (double)c.t_steps : 1.0;
+  out[0] = (double)c.t_wait / n * 1e-3;
+  out[1] = (double)c.t_busy / n * 1e-3;
+  out[2] = (double)c.t_gap / n * 1e-3;
+  out[3] = (double)c.t_steps;
   return TAU_OK;
 }
 

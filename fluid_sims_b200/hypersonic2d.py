@@ -38,6 +38,7 @@ _get_seg = declare("tau_hyp2d_get_seg_rows", [_h])
 _ipc_export = declare("tau_hyp2d_ipc_export", [_h, C.c_void_p, C.c_size_t])
 _ipc_attach = declare("tau_hyp2d_ipc_attach", [_h, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)])
 _peers_ready = declare("tau_hyp2d_peers_ready", [_h])
+_peer_timing = declare("tau_hyp2d_peer_timing", [_h, C.POINTER(C.c_double)])
 IPC_BYTES = 3 * 64
 _steps_done = declare("tau_hyp2d_steps_done", [_h], C.c_longlong)
 _launches = declare("tau_hyp2d_launch_count", [_h], C.c_longlong)
@@ -161,6 +162,12 @@ class Hypersonic2D:
     def peers_ready(self):
         check(_peers_ready(self._handle))
         return self
+
+    def peer_timing(self):
+        """Average microseconds per step: (waiting for peers, computing, launch gap, steps counted)."""
+        out = (C.c_double * 4)()
+        check(_peer_timing(self._handle, out))
+        return {"wait_us": out[0], "busy_us": out[1], "gap_us": out[2], "steps": int(out[3])}
 
     def set_seg_rows(self, rows: int):
         check(_set_seg(self._handle, rows))

@@ -127,6 +127,9 @@ int tau_hyp2d_ipc_export(tau_hyp2d *h, void *out, size_t out_bytes);
 int tau_hyp2d_ipc_attach(tau_hyp2d *h, int rank, int world, const void *all_handles,
                          const int *h_locals);
 int tau_hyp2d_peers_ready(tau_hyp2d *h);
+/* Diagnostics of the device-side exchange: average microseconds per step spent waiting for the
+ * peers' messages, computing, and between steps; out[3] = steps counted since peers_ready. */
+int tau_hyp2d_peer_timing(tau_hyp2d *h, double out[4]);
 /* rows each warp marches per work item (tuning; --tile-by analogue of :1641-1685) */
 int tau_hyp2d_set_seg_rows(tau_hyp2d *h, int rows);
 /* the height in use (chosen by a wave model at the first step unless set explicitly) */

@@ -420,6 +420,13 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
     }
     __syncwarp();
   }
+  // A warp's first work item is fixed (its global warp index), so its descriptor — static data, not
+  // written by the previous step — can be fetched before the grid dependency resolves; only the
+  // later items are claimed from the counter (which therefore counts from the number of warps).
+  const unsigned nwarps_grid = gridDim.x * H2_WARPS;
+  unsigned item = blockIdx.x * H2_WARPS + warp;
+  uint2 desc = make_uint2(0u, 0u);
+  if (item < (unsigned)P.nitems) desc = items[item];
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // ---- multi-GPU step barrier + all-reduce(max): every peer must have finished the previous step
@@ -450,6 +457,9 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
     __syncthreads();
   }
 
+  // (evaluated after the first item's tiles have been requested: see the work-item loop)
+  R dt = R(0), half_dt = R(0);
+  auto compute_dt = [&]() {
   // ---- dt from the device-resident max wavespeed (host rule :1852-1869, evaluated in fp64) ----
   double maxs = *reinterpret_cast<volatile double *>(&ctrl->maxspeed[step_slot]);
   if (peer.pc.world > 1) maxs = fmax(maxs, __longlong_as_double((long long)s_peer_max));
@@ -458,8 +468,8 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
   double dt_diff = dt_conv;
   if (isfinite(P.nu_max) && P.nu_max > 1e-12) dt_diff = 0.25 / P.nu_max;
   const double dt_d = fmin(dt_conv, dt_diff);
-  const R dt = (R)dt_d;
-  const R half_dt = (R)(0.5 * dt_d);
+  dt = (R)dt_d;
+  half_dt = (R)(0.5 * dt_d);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     ctrl->sim_t += dt_d;
     ctrl->dt_last = dt_d;
@@ -478,6 +488,7 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
       ctrl->t_steps += 1ull;
     }
   }
+  };
 
   bool pushed = false;  // this thread stored into a neighbour GPU's ghost rows
   R wmax = R(0);
@@ -491,10 +502,7 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
   // end of the step, early enough that neither latency is exposed.
   unsigned kb = 0;
   unsigned claim = 0;
-  if (lane == 0) claim = atomicAdd(&ctrl->next_item[step_slot], 1u);
-  unsigned item = __shfl_sync(0xffffffffu, claim, 0);
-  uint2 desc = make_uint2(0u, 0u);
-  if (item < (unsigned)P.nitems) desc = items[item];
+  bool first = true;
   while (item < (unsigned)P.nitems) {
   const int strip = (int)(desc.x & 0xffffu);
   const bool item_masked = (desc.x >> 31) != 0u;
@@ -576,6 +584,10 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
       ++acquired;
     }
   };
+  if (first) {
+    compute_dt();
+    first = false;
+  }
   need_row(1);
 
   // 40 mask bits of one plane row (bit b <-> staged column b); out-of-domain columns read as 0
@@ -646,7 +658,7 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
     for (int r = ys - 2; r < ye; ++r) {
       const int q = r - ys + 2;  // staged-row offset of row r
       if (r == ye - 3) {         // (a segment has at least one row: r = ye-3 >= ys-2 is reached)
-        if (lane == 0) claim = atomicAdd(&ctrl->next_item[step_slot], 1u);
+        if (lane == 0) claim = nwarps_grid + atomicAdd(&ctrl->next_item[step_slot], 1u);
       } else if (r == ye - 1) {
         item = __shfl_sync(0xffffffffu, claim, 0);
         if (item < (unsigned)P.nitems) desc = items[item];
@@ -766,6 +778,9 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
           Uout[PL + o] = Un.mx;
           Uout[2 * PL + o] = Un.my;
           Uout[3 * PL + o] = Un.E;
+          // The first and last two rows of the slab have extra consumers; one warp-uniform test
+          // keeps all of that out of the way of every other row.
+          if (r < H2_GHOST || r >= P.H_local - H2_GHOST) {
           // multi-GPU: push boundary rows into the slab neighbours' ghost rows (peer memory)
           if (peer.up_out != nullptr && r < H2_GHOST) {
             pushed = true;
@@ -805,6 +820,7 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
               }
             }
           }
+          }  // boundary rows
         }
       }  // r >= ys
 
@@ -839,6 +855,7 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
   kb += (unsigned)nblk;  // every staged block has been acquired; the ring carries on from here
   __syncwarp();
   }  // work-item loop
+  if (first) compute_dt();  // a warp without any item still owes block 0's bookkeeping
 
   wmax = tau::warp_max(wmax);
   if (lane == 0 && wmax > R(0)) tau::atomic_max_nonneg(&ctrl->maxspeed[(step_slot + 1) % 3], (double)wmax);

@@ -3,7 +3,11 @@
  * --cfl --visc-nu --visc-rho --visc-e --steps-per-frame --geom-x0 --geom-cy --geom-rb --geom-rn
  * --geom-theta --tile-bx --tile-by) with the same validation messages, and replaces the raylib
  * frame loop (:1824-1947) by a headless one.  Additive flags: --nx/--ny (the reference's grid is a
- * compile-time #define), --frames, --dtype f32|f64, --dump FILE. */
+ * compile-time #define), --frames, --dtype f32|f64, --dump FILE; --view MODE --ppm FILE (the render
+ * pass of the frame loop :1892-1926 written as a binary PPM instead of a raylib texture; MODE as
+ * the reference's M key cycles it, 0..6); --write-baseline / --verify-baseline FILE (the regression
+ * snapshot of tau_hypersonic_cuda_tests.cu:84-176, same file format and tolerances);
+ * --checkpoint FILE / --resume FILE (raw SoA state, bit-identical resume). */
 #include <errno.h>
 #include <limits.h>
 #include <math.h>
@@ -17,7 +21,9 @@ static void usage(const char *a0) {
           "          [--geom-x0 X0] [--geom-cy CY] [--geom-rb RB]\n"
           "          [--geom-rn RN] [--geom-theta THETA]\n"
           "          [--tile-bx BX] [--tile-by BY]\n"
-          "          [--nx W] [--ny H] [--frames N] [--dtype f32|f64] [--dump FILE]\n",
+          "          [--nx W] [--ny H] [--frames N] [--dtype f32|f64] [--dump FILE]\n"
+          "          [--view MODE] [--ppm FILE] [--write-baseline FILE | --verify-baseline FILE]\n"
+          "          [--checkpoint FILE] [--resume FILE]\n",
           a0);
 }
 static int parse_d(const char *name, const char *v, double *out) { /* parse_double_flag :1462 */
@@ -44,7 +50,8 @@ static int parse_i(const char *name, const char *v, int *out) { /* parse_int_fla
 
 int main(int argc, char **argv) {
   int W = 8192, H = 1024, frames = 100, dtype = TAU_F64, tile_bx = -1, tile_by = -1;
-  const char *dump = NULL;
+  const char *dump = NULL, *ppm = NULL, *wbase = NULL, *vbase = NULL, *ckpt = NULL, *resume = NULL;
+  int view = 0;
   /* first pass: grid size, because default_config derives the geometry from H (:1401-1405) */
   for (int i = 1; i + 1 < argc; i++) {
     if (!strcmp(argv[i], "--nx") && !parse_i("--nx", argv[i + 1], &W)) return 1;
@@ -69,6 +76,12 @@ int main(int argc, char **argv) {
     if (!strcmp(a, "--frames") && has) { if (!parse_i(a, argv[++i], &frames)) return 1; continue; }
     if (!strcmp(a, "--dtype") && has) { dtype = !strcmp(argv[++i], "f32") ? TAU_F32 : TAU_F64; continue; }
     if (!strcmp(a, "--dump") && has) { dump = argv[++i]; continue; }
+    if (!strcmp(a, "--view") && has) { if (!parse_i(a, argv[++i], &view)) return 1; continue; }
+    if (!strcmp(a, "--ppm") && has) { ppm = argv[++i]; continue; }
+    if (!strcmp(a, "--write-baseline") && has) { wbase = argv[++i]; continue; }
+    if (!strcmp(a, "--verify-baseline") && has) { vbase = argv[++i]; continue; }
+    if (!strcmp(a, "--checkpoint") && has) { ckpt = argv[++i]; continue; }
+    if (!strcmp(a, "--resume") && has) { resume = argv[++i]; continue; }
     fprintf(stderr, "Unknown or incomplete argument: %s\n", a);
     usage(argv[0]);
     return 1;
@@ -86,7 +99,8 @@ int main(int argc, char **argv) {
   tau_hyp2d *sim;
   TAU_OR_DIE(tau_hyp2d_create(&c, W, H, dtype, 0, 0, H, NULL, &sim));
   if (tile_by > 0) TAU_OR_DIE(tau_hyp2d_set_seg_rows(sim, tile_by < 4 ? 4 : tile_by));
-  TAU_OR_DIE(tau_hyp2d_init(sim));
+  if (resume) TAU_OR_DIE(tau_hyp2d_checkpoint_load(sim, resume));
+  else TAU_OR_DIE(tau_hyp2d_init(sim));
   printf("LaunchConfig:\n  grid=%dx%d dtype=%s marching segment=%d rows\n", W, H, dtype ? "f64" : "f32",
          tau_hyp2d_get_seg_rows(sim));
   const double t0 = cli_now();
@@ -110,6 +124,33 @@ int main(int argc, char **argv) {
     cli_dump(dump, 4, (int)es, W, H, 1, tau_hyp2d_steps_done(sim), sim_t, planes);
     for (int p = 0; p < 4; ++p) free(planes[p]);
   }
+  if (ppm) { /* render pass A + B of the frame loop, then the texture upload becomes a file */
+    uint32_t *px = (uint32_t *)malloc((size_t)W * H * 4);
+    double mm[2];
+    TAU_OR_DIE(tau_hyp2d_render(sim, view, px, mm));
+    FILE *f = fopen(ppm, "wb");
+    if (!f) { fprintf(stderr, "cannot open %s for writing\n", ppm); return 1; }
+    fprintf(f, "P6\n%d %d\n255\n", W, H);
+    for (size_t i = 0; i < (size_t)W * H; ++i) fwrite(&px[i], 1, 3, f); /* R,G,B of uchar4 */
+    fclose(f);
+    free(px);
+    printf("view %d: value range [%.6g, %.6g] -> %s\n", view, mm[0], mm[1], ppm);
+  }
+  if (wbase || vbase) {
+    tau_hyp2d_snapshot_t cur, exp;
+    TAU_OR_DIE(tau_hyp2d_snapshot(sim, &cur));
+    if (wbase) TAU_OR_DIE(tau_hyp2d_snapshot_write(wbase, &cur));
+    if (vbase) {
+      TAU_OR_DIE(tau_hyp2d_snapshot_read(vbase, &exp));
+      const int failed = tau_hyp2d_snapshot_compare(&cur, &exp);
+      if (failed) {
+        fprintf(stderr, "%s\n%d baseline check(s) failed\n", tau_last_error(), failed);
+        return 1;
+      }
+      printf("baseline %s verified\n", vbase);
+    }
+  }
+  if (ckpt) TAU_OR_DIE(tau_hyp2d_checkpoint_save(sim, ckpt));
   TAU_OR_DIE(tau_hyp2d_destroy(sim));
   return 0;
 }

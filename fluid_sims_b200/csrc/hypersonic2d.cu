@@ -1002,6 +1002,145 @@ __device__ double g_sd_sphere_cone(double x, double y, double Rb, double Rn, dou
   return inside ? -d : d;
 }
 
+
+// ================================================================================================
+// Render / diagnostic pass — the step on the other side of the hot path in the reference's frame
+// loop (tau_hypersonic_cuda.cu:1892-1926): k_render_vals (:1178-1248) -> k_reduce_minmax x n
+// (:1273-1320) -> k_compute_inv_range (:1322-1326) -> k_render_pixels (:1250-1271).
+// The reference writes a value plane (8 B/cell), 2 x N/256 block extrema, reduces them in a chain of
+// launches and re-reads the value plane.  Here: pass 1 evaluates the view value and reduces min/max
+// with warp shuffles + one pair of integer atomics per warp (order-preserving key of the double, so
+// the result is exact and order independent); pass 2 re-evaluates the value (cheaper than 16 B/cell
+// of HBM traffic) and writes RGBA8.  All arithmetic in fp64 on the handle's state, like the reference.
+// ================================================================================================
+struct RenderPar {
+  double gamma, gm1, eps_rho, eps_p, inflow_u;  // inflow_state() :230-238 = (1, inflow_u, 0, 1)
+  int W, H_local;
+  size_t plane;
+};
+struct PrimD { double rho, u, v, p; };
+
+__device__ __forceinline__ unsigned long long f64_key(double v) {  // monotonic double -> u64
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double f64_unkey(unsigned long long k) {
+  const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+// cons_to_prim :143-159 in fp64 on plane element `o`
+template <typename R>
+__device__ __forceinline__ PrimD render_prim(const RenderPar &P, const R *__restrict__ U, size_t o) {
+  const double c_rho = (double)U[o], c_mx = (double)U[P.plane + o], c_my = (double)U[2 * P.plane + o],
+               c_E = (double)U[3 * P.plane + o];
+  PrimD p;
+  const double rho = fmax(c_rho, P.eps_rho);
+  const double inv = 1.0 / rho;
+  p.rho = rho;
+  p.u = c_mx * inv;
+  p.v = c_my * inv;
+  const double kin = 0.5 * rho * (p.u * p.u + p.v * p.v);
+  p.p = P.gm1 * fmax(c_E - kin, P.eps_p);
+  return p;
+}
+// sample_prim_bc :706-727 for the neighbour (x+dx, row+dy) of the fluid cell (x, row); rows are
+// plane rows (ghost rows hold the y-clamp images at the global edges, the neighbours' rows inside a
+// slab decomposition — callers keep them current, see tau_hyp2d_render_minmax).
+template <typename R>
+__device__ __forceinline__ PrimD render_neighbour(const RenderPar &P, const R *__restrict__ U,
+                                                  const uint8_t *__restrict__ mask, const PrimD &centre,
+                                                  int x, int prow, int dx, int dy) {
+  const int xn = x + dx, rn = prow + dy;
+  if (xn < 0) return PrimD{1.0, P.inflow_u, 0.0, 1.0};
+  if (xn >= P.W) return render_prim(P, U, (size_t)rn * P.W + (P.W - 1));
+  const size_t o = (size_t)rn * P.W + xn;
+  if (mask[o]) return PrimD{centre.rho, -centre.u, -centre.v, centre.p};
+  return render_prim(P, U, o);
+}
+template <typename R>
+__device__ __forceinline__ double render_value(const RenderPar &P, const R *__restrict__ U,
+                                               const uint8_t *__restrict__ mask, int mode, int x, int prow) {
+  const PrimD p = render_prim(P, U, (size_t)prow * P.W + x);
+  double v;
+  if (mode == 0) {
+    v = log(p.rho);
+  } else if (mode == 1) {
+    v = log(p.p);
+  } else if (mode == 2) {
+    v = sqrt(p.u * p.u + p.v * p.v);
+  } else if (mode == 3) {
+    const double rhoL = render_neighbour(P, U, mask, p, x, prow, -1, 0).rho;
+    const double rhoR = render_neighbour(P, U, mask, p, x, prow, +1, 0).rho;
+    const double rhoB = render_neighbour(P, U, mask, p, x, prow, 0, -1).rho;
+    const double rhoT = render_neighbour(P, U, mask, p, x, prow, 0, +1).rho;
+    const double gx = 0.5 * (rhoR - rhoL), gy = 0.5 * (rhoT - rhoB);
+    v = log(1e-12 + sqrt(gx * gx + gy * gy));
+  } else if (mode == 4) {
+    const PrimD pL = render_neighbour(P, U, mask, p, x, prow, -1, 0);
+    const PrimD pR = render_neighbour(P, U, mask, p, x, prow, +1, 0);
+    const PrimD pB = render_neighbour(P, U, mask, p, x, prow, 0, -1);
+    const PrimD pT = render_neighbour(P, U, mask, p, x, prow, 0, +1);
+    v = asinh(0.5 * (pR.v - pL.v) - 0.5 * (pT.u - pB.u));
+  } else if (mode == 5) {
+    const double a = sqrt(P.gamma * fmax(p.p, P.eps_p) / fmax(p.rho, P.eps_rho));  // sound_speed :172
+    v = sqrt(p.u * p.u + p.v * p.v) / fmax(a, 1e-30);
+  } else {
+    v = log(fmax(p.p / fmax(p.rho, P.eps_rho), 1e-30));
+  }
+  return isfinite(v) ? v : 0.0;
+}
+
+// pass 1: mm[0] = key(min), mm[1] = key(max) over the fluid cells of the slab
+template <typename R>
+__global__ void __launch_bounds__(256)
+hyp2d_render_minmax(const RenderPar P, const R *__restrict__ U, const uint8_t *__restrict__ mask,
+                    int mode, unsigned long long *__restrict__ mm) {
+  const size_t n = (size_t)P.W * P.H_local;
+  double mn = 1e300, mx = -1e300;  // the reference's identities (:1190-1191)
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % P.W), prow = (int)(i / P.W) + H2_GHOST;
+    if (mask[(size_t)prow * P.W + x]) continue;
+    const double v = render_value(P, U, mask, mode, x, prow);
+    mn = fmin(mn, v);
+    mx = fmax(mx, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&mm[0], f64_key(mn));
+    atomicMax(&mm[1], f64_key(mx));
+  }
+}
+// get_color :692-704
+__device__ __forceinline__ uchar4 render_color(double t) {
+  t = t < 0 ? 0 : t;
+  t = t > 1 ? 1 : t;
+  const double rr = 255.0 * fmin(1.0, fmax(0.0, 3.0 * t - 1.0));
+  const double gg = 255.0 * fmin(1.0, fmax(0.0, 2.0 - 4.0 * fabs(t - 0.5)));
+  const double bb = 255.0 * fmin(1.0, fmax(0.0, 2.0 - 3.0 * t));
+  return uchar4{(unsigned char)rr, (unsigned char)gg, (unsigned char)bb, 255};
+}
+// pass 2: pixels (k_compute_inv_range + k_render_pixels)
+template <typename R>
+__global__ void __launch_bounds__(256)
+hyp2d_render_pixels(const RenderPar P, const R *__restrict__ U, const uint8_t *__restrict__ mask,
+                    int mode, double vmin, double vmax, uchar4 *__restrict__ out) {
+  const size_t n = (size_t)P.W * P.H_local;
+  const double inv_range = 1.0 / fmax(vmax - vmin, 1e-30);
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % P.W), prow = (int)(i / P.W) + H2_GHOST;
+    if (mask[(size_t)prow * P.W + x]) {
+      out[i] = uchar4{110, 110, 110, 255};
+      continue;
+    }
+    const double v = render_value(P, U, mask, mode, x, prow);
+    out[i] = render_color((v - vmin) * inv_range);
+  }
+}
+
 struct Geom { double x0, cy, Rb, Rn, theta; };
 
 template <typename R>
@@ -1059,6 +1198,8 @@ struct tau_hyp2d {
   cudaEvent_t ev0, ev1;
   bool timed;
   size_t plane_elems;
+  uchar4 *pixels;             // render target (device), allocated on first use
+  unsigned long long *mmkeys; // render min/max keys (device)
 };
 
 namespace {
@@ -1359,6 +1500,8 @@ int tau_hyp2d_create(const tau_hyp2d_config *cfg, int W, int H, int dtype, int d
   memset(&h->pctrl, 0, sizeof(h->pctrl));
   h->pctrl.world = 1;
   h->peers_attached = false;
+  h->pixels = nullptr;
+  h->mmkeys = nullptr;
   h->items = nullptr;
   h->items_cap = 0;
   h->nitems = 0;
@@ -1582,6 +1725,82 @@ int tau_hyp2d_peers_ready(tau_hyp2d *h) {
   return TAU_OK;
 }
 
+
+// ---- render pass (reference frame loop :1892-1926) ---------------------------------------------
+static RenderPar make_render_par(const tau_hyp2d *h) {
+  RenderPar P;
+  P.gamma = h->cfg.gamma;
+  P.gm1 = h->cfg.gamma - 1.0;
+  P.eps_rho = 1e-25;
+  P.eps_p = 1e-25;
+  P.inflow_u = h->cfg.inflow_mach * sqrt(h->cfg.gamma * 1.0 / 1.0);  // inflow_state() :230-238
+  P.W = h->W;
+  P.H_local = h->h_local;
+  P.plane = h->plane_elems;
+  return P;
+}
+
+int tau_hyp2d_render_minmax(tau_hyp2d *h, int view_mode, double minmax[2]) {
+  TAU_REQUIRE(h && minmax, "tau_hyp2d_render_minmax: null argument");
+  TAU_REQUIRE(view_mode >= 0 && view_mode <= 6, "tau_hyp2d_render_minmax: view mode %d not in [0, 6]", view_mode);
+  TAU_REQUIRE(h->speed_valid, "tau_hyp2d_render_minmax: no state (call tau_hyp2d_init or tau_hyp2d_upload)");
+  TAU_CUDA(cudaSetDevice(h->device));
+  if (!h->mmkeys) TAU_CUDA(cudaMalloc(&h->mmkeys, 2 * sizeof(unsigned long long)));
+  const unsigned long long init[2] = {~0ull, 0ull};
+  TAU_CUDA(cudaMemcpyAsync(h->mmkeys, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+  const RenderPar P = make_render_par(h);
+  const int grid = 148 * 8;
+  if (h->dtype)
+    hyp2d_render_minmax<double><<<grid, 256, 0, h->stream>>>(P, (const double *)h->U[h->cur], h->mask, view_mode, h->mmkeys);
+  else
+    hyp2d_render_minmax<float><<<grid, 256, 0, h->stream>>>(P, (const float *)h->U[h->cur], h->mask, view_mode, h->mmkeys);
+  h->launches++;
+  TAU_CUDA(cudaGetLastError());
+  unsigned long long k[2];
+  TAU_CUDA(cudaMemcpyAsync(k, h->mmkeys, sizeof(k), cudaMemcpyDeviceToHost, h->stream));
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < 2; ++i) {  // f64_unkey on the host
+    const unsigned long long b = (k[i] >> 63) ? (k[i] & 0x7fffffffffffffffull) : ~k[i];
+    memcpy(&minmax[i], &b, sizeof(double));
+  }
+  return TAU_OK;
+}
+
+int tau_hyp2d_render_pixels(tau_hyp2d *h, int view_mode, const double minmax[2], uint32_t *rgba) {
+  TAU_REQUIRE(h && minmax && rgba, "tau_hyp2d_render_pixels: null argument");
+  TAU_REQUIRE(view_mode >= 0 && view_mode <= 6, "tau_hyp2d_render_pixels: view mode %d not in [0, 6]", view_mode);
+  TAU_REQUIRE(h->speed_valid, "tau_hyp2d_render_pixels: no state (call tau_hyp2d_init or tau_hyp2d_upload)");
+  TAU_CUDA(cudaSetDevice(h->device));
+  const size_t n = (size_t)h->W * h->h_local;
+  if (!h->pixels) TAU_CUDA(cudaMalloc(&h->pixels, n * sizeof(uchar4)));
+  const RenderPar P = make_render_par(h);
+  const int grid = 148 * 8;
+  if (h->dtype)
+    hyp2d_render_pixels<double><<<grid, 256, 0, h->stream>>>(P, (const double *)h->U[h->cur], h->mask, view_mode,
+                                                              minmax[0], minmax[1], h->pixels);
+  else
+    hyp2d_render_pixels<float><<<grid, 256, 0, h->stream>>>(P, (const float *)h->U[h->cur], h->mask, view_mode,
+                                                             minmax[0], minmax[1], h->pixels);
+  h->launches++;
+  TAU_CUDA(cudaGetLastError());
+  TAU_CUDA(cudaMemcpyAsync(rgba, h->pixels, n * sizeof(uchar4), cudaMemcpyDeviceToHost, h->stream));
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  return TAU_OK;
+}
+
+int tau_hyp2d_render(tau_hyp2d *h, int view_mode, uint32_t *rgba, double minmax_out[2]) {
+  double mm[2];
+  int rc = tau_hyp2d_render_minmax(h, view_mode, mm);
+  if (rc) return rc;
+  rc = tau_hyp2d_render_pixels(h, view_mode, mm, rgba);
+  if (rc) return rc;
+  if (minmax_out) {
+    minmax_out[0] = mm[0];
+    minmax_out[1] = mm[1];
+  }
+  return TAU_OK;
+}
+
 // Multi-GPU diagnostics: average per-step times in microseconds since tau_hyp2d_peers_ready():
 // out[0] waiting for the peers' messages, out[1] peers seen -> last CTA out, out[2] last CTA out ->
 // next step's start (launch gap), out[3] = steps counted.
@@ -1607,6 +1826,38 @@ int tau_hyp2d_set_seg_rows(tau_hyp2d *h, int rows) {
 }
 
 int tau_hyp2d_get_seg_rows(tau_hyp2d *h) { return h ? h->seg_rows : -1; }
+
+int tau_hyp2d_describe(tau_hyp2d *h, int *W, int *H, int *dtype, int *y_begin, int *h_local,
+                       tau_hyp2d_config *cfg) {
+  TAU_REQUIRE(h, "tau_hyp2d_describe: null handle");
+  if (W) *W = h->W;
+  if (H) *H = h->H;
+  if (dtype) *dtype = h->dtype;
+  if (y_begin) *y_begin = h->y_begin;
+  if (h_local) *h_local = h->h_local;
+  if (cfg) *cfg = h->cfg;
+  return TAU_OK;
+}
+
+// Restore the device-resident clock after tau_hyp2d_upload (checkpoint/resume).  The step counter
+// only selects the rotating control slot; the max wavespeed of the restored state was re-scanned by
+// the upload, so the next dt equals the one the original run would have taken.
+int tau_hyp2d_set_clock(tau_hyp2d *h, double sim_t, long long steps_done) {
+  TAU_REQUIRE(h && steps_done >= 0, "tau_hyp2d_set_clock: bad argument");
+  TAU_REQUIRE(h->speed_valid, "tau_hyp2d_set_clock: no state (call tau_hyp2d_upload first)");
+  TAU_CUDA(cudaSetDevice(h->device));
+  Ctrl c;
+  TAU_CUDA(cudaMemcpyAsync(&c, h->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  const double ms = c.maxspeed[h->steps % 3];
+  memset(&c, 0, sizeof(c));
+  h->steps = steps_done;
+  c.maxspeed[h->steps % 3] = ms;
+  c.sim_t = sim_t;
+  TAU_CUDA(cudaMemcpyAsync(h->ctrl, &c, sizeof(Ctrl), cudaMemcpyHostToDevice, h->stream));
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  return TAU_OK;
+}
 long long tau_hyp2d_steps_done(tau_hyp2d *h) { return h ? h->steps : -1; }
 long long tau_hyp2d_launch_count(tau_hyp2d *h) { return h ? h->launches : -1; }
 
@@ -1624,6 +1875,8 @@ int tau_hyp2d_destroy(tau_hyp2d *h) {
   cudaStreamSynchronize(h->stream);
   cudaFree(h->ctrl);
   if (h->items) cudaFree(h->items);
+  if (h->pixels) cudaFree(h->pixels);
+  if (h->mmkeys) cudaFree(h->mmkeys);
   cudaFree(h->mask);
   cudaFree(h->U[1]);
   cudaFree(h->U[0]);

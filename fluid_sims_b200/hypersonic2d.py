@@ -10,7 +10,7 @@ from dataclasses import dataclass, fields
 
 import numpy as np
 
-from ._lib import check, declare
+from ._lib import check, declare, lib
 
 
 class _CConfig(C.Structure):
@@ -39,6 +39,47 @@ _ipc_export = declare("tau_hyp2d_ipc_export", [_h, C.c_void_p, C.c_size_t])
 _ipc_attach = declare("tau_hyp2d_ipc_attach", [_h, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)])
 _peers_ready = declare("tau_hyp2d_peers_ready", [_h])
 _peer_timing = declare("tau_hyp2d_peer_timing", [_h, C.POINTER(C.c_double)])
+_render_mm = declare("tau_hyp2d_render_minmax", [_h, C.c_int, C.POINTER(C.c_double)])
+_render_px = declare("tau_hyp2d_render_pixels", [_h, C.c_int, C.POINTER(C.c_double), C.c_void_p])
+_render = declare("tau_hyp2d_render", [_h, C.c_int, C.c_void_p, C.POINTER(C.c_double)])
+
+
+class Snapshot(C.Structure):
+    """`struct RegressionSnapshot` (tau_hypersonic_cuda_tests.cu:20-36)."""
+    _fields_ = [("steps", C.c_int), ("fluid_cells", C.c_int)] + [
+        (k, C.c_double) for k in ("sum_rho", "sum_mx", "sum_my", "sum_E", "min_rho", "min_p", "max_mach",
+                                  "checksum_rho", "checksum_mx", "checksum_E")]
+
+    def as_tuple(self):
+        return tuple(getattr(self, f[0]) for f in self._fields_)
+
+    def write(self, path: str):
+        check(_snap_write(path.encode(), C.byref(self)))
+
+    @classmethod
+    def read(cls, path: str) -> "Snapshot":
+        s = cls()
+        check(_snap_read(path.encode(), C.byref(s)))
+        return s
+
+    def failures_against(self, expected: "Snapshot"):
+        """The reference's verification (:527-557): list of failed check names (empty = pass)."""
+        n = _snap_cmp(C.byref(self), C.byref(expected))
+        if n < 0:
+            check(n)
+        return [] if n == 0 else lib.tau_last_error().decode().split("; ")
+
+
+_snapshot = declare("tau_hyp2d_snapshot", [_h, C.POINTER(Snapshot)])
+_snap_write = declare("tau_hyp2d_snapshot_write", [C.c_char_p, C.POINTER(Snapshot)])
+_snap_read = declare("tau_hyp2d_snapshot_read", [C.c_char_p, C.POINTER(Snapshot)])
+_snap_cmp = declare("tau_hyp2d_snapshot_compare", [C.POINTER(Snapshot), C.POINTER(Snapshot)])
+_ckpt_save = declare("tau_hyp2d_checkpoint_save", [_h, C.c_char_p])
+_ckpt_load = declare("tau_hyp2d_checkpoint_load", [_h, C.c_char_p])
+_ckpt_info = declare("tau_hyp2d_checkpoint_info", [C.c_char_p] + [C.POINTER(C.c_int)] * 5 +
+                     [C.POINTER(C.c_longlong), C.POINTER(C.c_double), C.c_void_p])
+_set_clock = declare("tau_hyp2d_set_clock", [_h, C.c_double, C.c_longlong])
+VIEW_MODES = ("log_rho", "log_p", "speed", "log_grad_rho", "asinh_vorticity", "mach", "log_p_over_rho")
 IPC_BYTES = 3 * 64
 _steps_done = declare("tau_hyp2d_steps_done", [_h], C.c_longlong)
 _launches = declare("tau_hyp2d_launch_count", [_h], C.c_longlong)
@@ -139,6 +180,49 @@ class Hypersonic2D:
 
     def sync(self):
         check(_sync(self._handle))
+
+    # ---- regression snapshot + checkpoint/resume (tau_hypersonic_cuda_tests.cu:84-176) -------
+    def snapshot(self) -> Snapshot:
+        out = Snapshot()
+        check(_snapshot(self._handle, C.byref(out)))
+        return out
+
+    def checkpoint_save(self, path: str):
+        check(_ckpt_save(self._handle, path.encode()))
+        return self
+
+    def checkpoint_load(self, path: str):
+        check(_ckpt_load(self._handle, path.encode()))
+        return self
+
+    @staticmethod
+    def checkpoint_info(path: str):
+        v = [C.c_int() for _ in range(5)]
+        steps, t = C.c_longlong(), C.c_double()
+        check(_ckpt_info(path.encode(), *[C.byref(x) for x in v], C.byref(steps), C.byref(t), None))
+        return {"W": v[0].value, "H": v[1].value, "dtype": "f64" if v[2].value else "f32",
+                "y_begin": v[3].value, "h_local": v[4].value, "steps": steps.value, "sim_t": t.value}
+
+    # ---- render pass (reference frame loop, tau_hypersonic_cuda.cu:1892-1926) ---------------
+    def render_minmax(self, view_mode: int):
+        """(min, max) of the view value over this handle's fluid cells."""
+        mm = (C.c_double * 2)()
+        check(_render_mm(self._handle, view_mode, mm))
+        return float(mm[0]), float(mm[1])
+
+    def render_pixels(self, view_mode: int, vmin: float, vmax: float):
+        """(h_local, W, 4) uint8 RGBA for the given (global) value range."""
+        out = np.empty((self.h_local, self.cfg.W, 4), np.uint8)
+        mm = (C.c_double * 2)(vmin, vmax)
+        check(_render_px(self._handle, view_mode, mm, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def render(self, view_mode: int = 0):
+        """Both passes: ((h_local, W, 4) uint8 RGBA, (min, max))."""
+        out = np.empty((self.h_local, self.cfg.W, 4), np.uint8)
+        mm = (C.c_double * 2)()
+        check(_render(self._handle, view_mode, C.c_void_p(out.ctypes.data), mm))
+        return out, (float(mm[0]), float(mm[1]))
 
     def device_state(self):
         """(planes_ptr, mask_ptr, maxspeed_ptr) raw device addresses for the slab exchange."""

@@ -130,6 +130,42 @@ int tau_hyp2d_peers_ready(tau_hyp2d *h);
 /* Diagnostics of the device-side exchange: average microseconds per step spent waiting for the
  * peers' messages, computing, and between steps; out[3] = steps counted since peers_ready. */
 int tau_hyp2d_peer_timing(tau_hyp2d *h, double out[4]);
+/* Render pass of the frame loop :1892-1926 (k_render_vals, k_reduce_minmax, k_compute_inv_range,
+ * k_render_pixels) on the current state.  view_mode as the reference's `view_mode` (:1195-1228):
+ * 0 log rho, 1 log p, 2 speed, 3 log |grad rho|, 4 asinh(vorticity), 5 Mach, 6 log(p/rho).
+ * rgba: h_local x W pixels, byte order R,G,B,A (uchar4 of :688-690), body cells (110,110,110).
+ * Slabs: tau_hyp2d_render_minmax gives the slab's extrema — reduce them (min/max) across ranks and
+ * hand the result to tau_hyp2d_render_pixels; modes 3/4 read the ghost rows, which the device-side
+ * exchange keeps current (with the host-driven exchange, exchange once more after the last step).
+ * tau_hyp2d_render = both passes on one handle. */
+int tau_hyp2d_render_minmax(tau_hyp2d *h, int view_mode, double minmax[2]);
+int tau_hyp2d_render_pixels(tau_hyp2d *h, int view_mode, const double minmax[2], uint32_t *rgba);
+int tau_hyp2d_render(tau_hyp2d *h, int view_mode, uint32_t *rgba, double minmax_out[2]);
+/* grid, dtype, slab and config of a handle (any out pointer may be NULL) */
+int tau_hyp2d_describe(tau_hyp2d *h, int *W, int *H, int *dtype, int *y_begin, int *h_local,
+                       tau_hyp2d_config *cfg);
+/* restore sim_t and the step counter after tau_hyp2d_upload (checkpoint/resume) */
+int tau_hyp2d_set_clock(tau_hyp2d *h, double sim_t, long long steps_done);
+
+/* The reference's regression snapshot (`struct RegressionSnapshot`,
+ * tau_hypersonic_cuda_tests.cu:20-36) and its text file (:84-125): compute_snapshot :143-176 on the
+ * handle's state (host, sequential, the reference's summation order), write / read in the
+ * reference's format, compare with the reference's tolerances (:527-557; returns the number of
+ * failed checks, names in tau_last_error()).  A slab handle yields its partial sums. */
+typedef struct tau_hyp2d_snapshot_t {
+  int steps, fluid_cells;
+  double sum_rho, sum_mx, sum_my, sum_E, min_rho, min_p, max_mach, checksum_rho, checksum_mx, checksum_E;
+} tau_hyp2d_snapshot_t;
+int tau_hyp2d_snapshot(tau_hyp2d *h, tau_hyp2d_snapshot_t *out);
+int tau_hyp2d_snapshot_write(const char *path, const tau_hyp2d_snapshot_t *s);
+int tau_hyp2d_snapshot_read(const char *path, tau_hyp2d_snapshot_t *s);
+int tau_hyp2d_snapshot_compare(const tau_hyp2d_snapshot_t *current, const tau_hyp2d_snapshot_t *expected);
+/* Raw SoA checkpoint of a handle (one file per slab) and bit-identical resume; the reference has
+ * no state output.  _info reads the header so that a matching handle can be created. */
+int tau_hyp2d_checkpoint_save(tau_hyp2d *h, const char *path);
+int tau_hyp2d_checkpoint_info(const char *path, int *W, int *H, int *dtype, int *y_begin, int *h_local,
+                              long long *steps, double *sim_t, tau_hyp2d_config *cfg);
+int tau_hyp2d_checkpoint_load(tau_hyp2d *h, const char *path);
 /* rows each warp marches per work item (tuning; --tile-by analogue of :1641-1685) */
 int tau_hyp2d_set_seg_rows(tau_hyp2d *h, int rows);
 /* the height in use (chosen by a wave model at the first step unless set explicitly) */

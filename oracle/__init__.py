@@ -200,6 +200,36 @@ def ref_hyp2d_run(W, H, cfg11, steps, planes=None, mask=None, tile=(32, 8)):
     return planes, mask, float(t.value), dts[:steps], float(ms.value)
 
 
+def hyp2d_render(cfg: Hyp2dCfg, planes, mask, view_mode):
+    """CPU oracle of the render pass: (rgba (H, W, 4) uint8, vals (H, W) f64, (min, max))."""
+    lib.oracle_hyp2d_render.argtypes = [C.POINTER(Hyp2dCfg), f64p, f64p, f64p, f64p, u8p, C.c_int, u8p,
+                                        f64p, f64p]
+    lib.oracle_hyp2d_render.restype = None
+    planes = [np.ascontiguousarray(p, np.float64).ravel() for p in planes]
+    mask = np.ascontiguousarray(mask, np.uint8).ravel()
+    rgba = np.zeros(cfg.W * cfg.H * 4, np.uint8)
+    vals = np.zeros(cfg.W * cfg.H, np.float64)
+    mm = np.zeros(2, np.float64)
+    lib.oracle_hyp2d_render(C.byref(cfg), *planes, mask, view_mode, rgba, vals, mm)
+    return rgba.reshape(cfg.H, cfg.W, 4), vals.reshape(cfg.H, cfg.W), (float(mm[0]), float(mm[1]))
+
+
+def ref_hyp2d_render(W, H, cfg11, planes, mask, view_mode):
+    """The reference's own render kernels (k_render_vals .. k_render_pixels) on the GPU."""
+    r = ref(f"ref_hyp2d_{W}x{H}")
+    r.ref_hyp2d_render.argtypes = [f64p, C.c_int, f64p, f64p, f64p, f64p, u8p, u8p, f64p, f64p]
+    r.ref_hyp2d_render.restype = C.c_int
+    planes = [np.ascontiguousarray(p, np.float64).ravel() for p in planes]
+    mask = np.ascontiguousarray(mask, np.uint8).ravel()
+    rgba = np.zeros(W * H * 4, np.uint8)
+    vals = np.zeros(W * H, np.float64)
+    mm = np.zeros(2, np.float64)
+    rc = r.ref_hyp2d_render(np.ascontiguousarray(cfg11, np.float64), view_mode, *planes, mask, rgba, vals, mm)
+    if rc != 0:
+        raise RuntimeError(f"reference hyp2d render failed with cudaError {rc}")
+    return rgba.reshape(H, W, 4), vals.reshape(H, W), (float(mm[0]), float(mm[1]))
+
+
 def ref_hyp2d_eval(W, H, cfg11, kind, vecs):
     r = ref(f"ref_hyp2d_{W}x{H}")
     r.ref_hyp2d_eval.argtypes = [f64p, C.c_int, C.c_int, f64p, f64p]

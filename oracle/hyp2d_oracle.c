@@ -522,6 +522,79 @@ void oracle_hyp2d_snapshot(const oracle_hyp2d_cfg *c, int steps, const double *r
   out[6] = min_rho; out[7] = min_p; out[8] = max_mach; out[9] = ck_rho; out[10] = ck_mx; out[11] = ck_E;
 }
 
+/* ---- render pass: k_render_vals :1178-1248, the min/max reduction :1273-1320, k_compute_inv_range
+ * :1322-1326, k_render_pixels :1250-1271, get_color :692-704, sample_prim_bc :706-727 ------------- */
+static Prim sample_prim_bc(const Field *f, int xc, int yc, int x, int y) {
+  const oracle_hyp2d_cfg *c = f->c;
+  if (y < 0) y = 0;
+  if (y >= c->H) y = c->H - 1;
+  if (x < 0) return inflow_state(c);
+  if (x >= c->W) return cons_to_prim(c, load_cons(f, y * c->W + (c->W - 1)));
+  int i = y * c->W + x;
+  if (f->mask[i]) return wall_ghost(cons_to_prim(c, load_cons(f, yc * c->W + xc)));
+  return cons_to_prim(c, load_cons(f, i));
+}
+
+double oracle_hyp2d_render_value(const oracle_hyp2d_cfg *c, const double *rho, const double *mx,
+                                 const double *my, const double *E, const uint8_t *mask, int view_mode,
+                                 int x, int y) {
+  Field f = {c, rho, mx, my, E, mask};
+  Prim p = cons_to_prim(c, load_cons(&f, y * c->W + x));
+  double v;
+  if (view_mode == 0) v = log(p.rho);
+  else if (view_mode == 1) v = log(p.p);
+  else if (view_mode == 2) v = sqrt(p.u * p.u + p.v * p.v);
+  else if (view_mode == 3) {
+    double rhoL = sample_prim_bc(&f, x, y, x - 1, y).rho, rhoR = sample_prim_bc(&f, x, y, x + 1, y).rho;
+    double rhoB = sample_prim_bc(&f, x, y, x, y - 1).rho, rhoT = sample_prim_bc(&f, x, y, x, y + 1).rho;
+    double gx = 0.5 * (rhoR - rhoL), gy = 0.5 * (rhoT - rhoB);
+    v = log(1e-12 + sqrt(gx * gx + gy * gy));
+  } else if (view_mode == 4) {
+    Prim pL = sample_prim_bc(&f, x, y, x - 1, y), pR = sample_prim_bc(&f, x, y, x + 1, y);
+    Prim pB = sample_prim_bc(&f, x, y, x, y - 1), pT = sample_prim_bc(&f, x, y, x, y + 1);
+    double dv_dx = 0.5 * (pR.v - pL.v), du_dy = 0.5 * (pT.u - pB.u);
+    v = asinh(dv_dx - du_dy);
+  } else if (view_mode == 5) {
+    double a = sound_speed(c, p), sp = sqrt(p.u * p.u + p.v * p.v);
+    v = sp / dmax(a, 1e-30);
+  } else {
+    v = log(dmax(p.p / dmax(p.rho, EPS_RHO), 1e-30));
+  }
+  if (!isfinite(v)) v = 0.0;
+  return v;
+}
+
+/* rgba: W*H pixels, bytes R,G,B,A.  vals (optional, W*H doubles) receives tmpVal; minmax[2]. */
+void oracle_hyp2d_render(const oracle_hyp2d_cfg *c, const double *rho, const double *mx, const double *my,
+                         const double *E, const uint8_t *mask, int view_mode, uint8_t *rgba,
+                         double *vals, double *minmax) {
+  const int N = c->W * c->H;
+  double mn = 1e300, mxv = -1e300;
+  double *tmp = vals ? vals : (double *)malloc((size_t)N * sizeof(double));
+  for (int i = 0; i < N; i++) {
+    if (mask[i]) { tmp[i] = 0.0; continue; }
+    double v = oracle_hyp2d_render_value(c, rho, mx, my, E, mask, view_mode, i % c->W, i / c->W);
+    tmp[i] = v;
+    if (v < mn) mn = v;
+    if (v > mxv) mxv = v;
+  }
+  const double inv_range = 1.0 / dmax(mxv - mn, 1e-30);
+  for (int i = 0; i < N; i++) {
+    uint8_t *px = rgba + 4 * (size_t)i;
+    if (mask[i]) { px[0] = px[1] = px[2] = 110; px[3] = 255; continue; }
+    double t = (tmp[i] - mn) * inv_range;
+    if (t < 0) t = 0;
+    if (t > 1) t = 1;
+    double rr = 255.0 * dmin(1.0, dmax(0.0, 3.0 * t - 1.0));
+    double gg = 255.0 * dmin(1.0, dmax(0.0, 2.0 - 4.0 * dabs(t - 0.5)));
+    double bb = 255.0 * dmin(1.0, dmax(0.0, 2.0 - 3.0 * t));
+    px[0] = (uint8_t)rr; px[1] = (uint8_t)gg; px[2] = (uint8_t)bb; px[3] = 255;
+  }
+  if (minmax) { minmax[0] = mn; minmax[1] = mxv; }
+  if (!vals) free(tmp);
+}
+
+
 /* ---- helper exports for the known-answer tests (tau_hypersonic_cuda_tests.cu:245-371) ---------- */
 void oracle_hyp2d_kat_cons_to_prim(const oracle_hyp2d_cfg *c, const double q[4], double p[4]) {
   Cons a = {q[0], q[1], q[2], q[3]};

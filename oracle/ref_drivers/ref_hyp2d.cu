@@ -149,3 +149,62 @@ extern "C" int ref_hyp2d_eval(const double *cfg11, int kind, int n, const double
   cudaFree(din); cudaFree(dout);
   return (int)e;
 }
+
+// ---- render pass: main()'s sequence :1892-1926 on caller-provided planes --------------------------
+// rgba: N x 4 bytes out; vals: N doubles out (tmpVal); minmax[2] out.
+extern "C" int ref_hyp2d_render(const double *cfg11, int view_mode, const double *rho, const double *mx,
+                                const double *my, const double *E, const uint8_t *mask, uint8_t *rgba,
+                                double *vals, double *minmax) {
+  SimConfig h_cfg = cfg_from(cfg11);
+  cudaError_t e;
+  if ((e = cudaMemcpyToSymbol(d_cfg, &h_cfg, sizeof(SimConfig)))) return e;
+  const int N = W * H;
+  Usoa dU{};
+  alloc_Us(&dU, N);
+  uint8_t *dMask = nullptr;
+  CK(cudaMalloc(&dMask, (size_t)N));
+  CK(cudaMemcpy(dU.rho, rho, (size_t)N * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dU.mx, mx, (size_t)N * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dU.my, my, (size_t)N * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dU.E, E, (size_t)N * 8, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dMask, mask, (size_t)N, cudaMemcpyHostToDevice));
+  const int threads = 256;
+  const int blocksN = (N + threads - 1) / threads;
+  const size_t reduceMinMaxSharedBytes = 2 * (size_t)threads * sizeof(double);
+  double *dTmpVal, *dBlockMin, *dBlockMax, *dReduceMin, *dReduceMax, *dInvRange;
+  uchar4 *dPixels;
+  CK(cudaMalloc(&dTmpVal, (size_t)N * 8));
+  CK(cudaMalloc(&dBlockMin, (size_t)blocksN * 8));
+  CK(cudaMalloc(&dBlockMax, (size_t)blocksN * 8));
+  CK(cudaMalloc(&dReduceMin, (size_t)blocksN * 8));
+  CK(cudaMalloc(&dReduceMax, (size_t)blocksN * 8));
+  CK(cudaMalloc(&dInvRange, 8));
+  CK(cudaMalloc(&dPixels, (size_t)N * sizeof(uchar4)));
+  k_render_vals<<<blocksN, threads, reduceMinMaxSharedBytes>>>(dU, dMask, view_mode, dTmpVal, dBlockMin, dBlockMax);
+  const double *curMin = dBlockMin, *curMax = dBlockMax;
+  double *outMin = dReduceMin, *outMax = dReduceMax;
+  int curN = blocksN;
+  while (curN > 1) {
+    int outN = (curN + (2 * threads - 1)) / (2 * threads);
+    k_reduce_minmax<<<outN, threads, reduceMinMaxSharedBytes>>>(curMin, curMax, outMin, outMax, curN);
+    curN = outN;
+    const double *nextMin = outMin, *nextMax = outMax;
+    outMin = (nextMin == dBlockMin) ? dReduceMin : dBlockMin;
+    outMax = (nextMax == dBlockMax) ? dReduceMax : dBlockMax;
+    curMin = nextMin;
+    curMax = nextMax;
+  }
+  k_compute_inv_range<<<1, 1>>>(curMin, curMax, dInvRange);
+  k_render_pixels<<<blocksN, threads>>>(dMask, dTmpVal, curMin, dInvRange, dPixels);
+  e = cudaDeviceSynchronize();
+  CK(cudaMemcpy(rgba, dPixels, (size_t)N * 4, cudaMemcpyDeviceToHost));
+  if (vals) CK(cudaMemcpy(vals, dTmpVal, (size_t)N * 8, cudaMemcpyDeviceToHost));
+  if (minmax) {
+    CK(cudaMemcpy(&minmax[0], curMin, 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&minmax[1], curMax, 8, cudaMemcpyDeviceToHost));
+  }
+  cudaFree(dTmpVal); cudaFree(dBlockMin); cudaFree(dBlockMax); cudaFree(dReduceMin); cudaFree(dReduceMax);
+  cudaFree(dInvRange); cudaFree(dPixels); cudaFree(dMask);
+  free_Us(&dU);
+  return (int)e;
+}

@@ -95,3 +95,26 @@ def test_cli_hosts_build_and_fail_loudly_without_gpu():
     assert r.returncode == 1 and "Invalid --gamma" in r.stderr
     r = subprocess.run([os.path.join(cli, "tau_2d_hypersonic_cuda"), "--bogus"], capture_output=True, text=True)
     assert r.returncode == 1 and "Unknown or incomplete argument" in r.stderr
+
+
+def test_snapshot_file_format_without_gpu(tmp_path):
+    """The regression-baseline text format (tau_hypersonic_cuda_tests.cu:84-125) and the verification
+    tolerances (:527-557) are host code: usable on a GPU-less box."""
+    from fluid_sims_b200.hypersonic2d import Snapshot
+    s = Snapshot(24, 1000, 1234.5678901234567, -3.25, 1e-17, 9.75e8, 0.5, 0.25, 24.99, 1.5e9, -2.5e7, 3.0e12)
+    p = str(tmp_path / "baseline.txt")
+    s.write(p)
+    txt = open(p).read()
+    assert txt.startswith("steps 24\nfluid_cells 1000\nsum_rho 1234.5678901234567\n")
+    assert Snapshot.read(p).as_tuple() == s.as_tuple()
+    t = Snapshot.read(p)
+    t.sum_rho *= 1 + 4e-8          # inside 5e-8 relative
+    assert s.failures_against(t) == []
+    t.sum_rho *= 1 + 1e-7          # outside
+    t.min_p += 2e-9                # outside the absolute 1e-9
+    assert s.failures_against(t) == ["FAIL: sum_rho matches baseline", "FAIL: min_p matches baseline"]
+    (tmp_path / "bad.txt").write_text("steps 3\nfluid_cells\n")
+    from fluid_sims_b200 import TauError
+    import pytest
+    with pytest.raises(TauError, match="of 12 fields"):
+        Snapshot.read(str(tmp_path / "bad.txt"))

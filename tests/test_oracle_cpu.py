@@ -285,3 +285,25 @@ def test_sph_cell_sort_is_a_stable_sort():
     order = np.argsort(keys, kind="stable").astype(np.uint32)
     assert np.array_equal(v, order) and np.array_equal(k, keys[order])
     assert cs[0] == 0 and cs[-1] == 5000 and np.all(np.diff(cs) >= 0)
+
+
+def test_hyp2d_render_oracle_invariants():
+    """render restatement (tau_hypersonic_cuda.cu:1178-1326): body pixels are (110,110,110,255), the
+    extrema are attained, the colormap end points are get_color(0)=(0,0,255) / get_color(1)=(255,0,0)
+    (:692-704) and tmpVal is 0 on body cells."""
+    cfg = oracle.hyp2d_cfg(96, 64, geom_x0=30.0)
+    planes, mask = oracle.hyp2d_init(cfg)
+    planes, _, _ = oracle.hyp2d_run(cfg, planes, mask, 12)
+    m2 = mask.reshape(64, 96) != 0
+    for mode in range(7):
+        rgba, vals, (mn, mx) = oracle.hyp2d_render(cfg, planes, mask, mode)
+        assert np.all(rgba[m2] == np.array([110, 110, 110, 255], np.uint8))
+        assert np.all(vals[m2] == 0.0)
+        fl = vals[~m2]
+        assert fl.min() == mn and fl.max() == mx and np.isfinite(fl).all()
+        assert tuple(rgba[~m2][np.argmin(fl)]) == (0, 0, 255, 255)
+        assert tuple(rgba[~m2][np.argmax(fl)]) == (255, 0, 0, 255)
+        assert np.all(rgba[..., 3] == 255)
+    # mode 2 is |velocity|: body at rest, inflow at Mach 25 * sqrt(gamma)
+    _, vals, (mn, mx) = oracle.hyp2d_render(cfg, planes, mask, 2)
+    assert mx >= 25.0 * np.sqrt(1.1) * 0.999

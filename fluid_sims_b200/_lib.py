@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtau_b200.so")
+# TAU_B200_LIB: load another build of the same library (kernel experiments); never a fallback
+LIB_PATH = os.environ.get("TAU_B200_LIB") or os.path.join(_HERE, "libtau_b200.so")
 
 
 class TauError(RuntimeError):

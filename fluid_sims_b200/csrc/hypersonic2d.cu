@@ -46,7 +46,10 @@ constexpr int H2_OWN = 30;    // columns owned per warp strip
 constexpr int H2_BOXW = 40;   // staged columns: bx .. bx+39, bx = (x0-2) rounded down to a
                               // multiple of 4 (TMA wants a 16-byte aligned box origin in fp32)
 constexpr int H2_RB = 4;      // rows per TMA box / ring slot
-constexpr int H2_NS = 3;      // ring slots per warp
+#ifndef H2_NS_SLOTS
+#define H2_NS_SLOTS 3
+#endif
+constexpr int H2_NS = H2_NS_SLOTS;  // ring slots per warp
 constexpr int H2_WARPS = 4;   // warps per CTA
 constexpr int H2_GHOST = 2;   // ghost rows above/below each plane
 #ifndef H2_MIN_CTAS
@@ -168,10 +171,12 @@ template <typename R> struct Face { R rho, u, v, p, E, a; };  // a = sound speed
 // argument of smallest magnitude among dl, dr, dc" (2dl and 2dr can never be the smallest) and to 0
 // otherwise.  Since dc = (dl+dr)/2 lies between dl and dr it can only be the smallest by a rounding
 // ulp, so the limited slope is min-magnitude(dl, dr): identical to the reference except for
-// last-bit ties.  Branch-free.
+// last-bit ties.
 template <typename R> __device__ __forceinline__ R mc_limiter(R dl, R dr) {
-  const R m = fmin(fabs(dl), fabs(dr));
-  return (dl * dr > R(0)) ? copysign(m, dl) : R(0);
+  // min-magnitude(dl, dr) if they agree in sign, else 0 == median(dl, dr, 0): four min/max, no
+  // product, compare, sign transfer or select.  (Differs from the product test only when dl*dr
+  // underflows, i.e. for slopes below 1e-19 in fp32 / 1e-154 in fp64.)
+  return fmax(fmin(dl, dr), fmin(fmax(dl, dr), R(0)));
 }
 // :217-221, kept for the known-answer tests
 template <typename R> __device__ __forceinline__ R minmod(R a, R b) {
@@ -399,8 +404,15 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
            const uint2 *__restrict__ items, Ctrl *__restrict__ ctrl, int step_slot,
            const PeerPush peer) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  // volatile asm: ptxas otherwise re-reads SR_TID.X (an ~20-cycle S2R) three times per marched row
+  // to rematerialise lane / warp instead of holding them in registers
+  int lane, warp;
+  {
+    unsigned t;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
+    lane = (int)(t & 31u);
+    warp = (int)(t >> 5);
+  }
   constexpr int SLOT_ELEMS = 4 * H2_RB * H2_BOXW;
   R *ring_base = reinterpret_cast<R *>(smem_raw) + (size_t)warp * H2_NS * SLOT_ELEMS;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)H2_WARPS * H2_NS * SLOT_ELEMS *
@@ -544,11 +556,11 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
     }
   };
   // wait for block k and fold the x-boundary conditions into the staged rows
-  auto acquire = [&](int k) {
+  auto acquire = [&](int k, auto edge_tag) {
     const unsigned slot = (kb + (unsigned)k) % H2_NS;
     if (USE_TMA) tau::mbar_wait(&bars[slot], ((kb + (unsigned)k) / H2_NS) & 1u);
     else __syncwarp();
-    if (edge_strip) {
+    if (decltype(edge_tag)::value && edge_strip) {
       R *dst = ring_base + (size_t)slot * SLOT_ELEMS;
       const int prow = ys + H2_RB * k;
       const int cw = (W - 1) - bx;  // staged column of x = W-1
@@ -578,9 +590,9 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
 
   int issued = 0, acquired = 0;
   for (; issued < nblk && issued < H2_NS; ++issued) issue(issued);
-  auto need_row = [&](int q) {
+  auto need_row = [&](int q, auto edge_tag) {
     while (acquired * H2_RB <= q) {
-      acquire(acquired);
+      acquire(acquired, edge_tag);
       ++acquired;
     }
   };
@@ -588,7 +600,7 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
     compute_dt();
     first = false;
   }
-  need_row(1);
+  need_row(1, std::true_type{});
 
   // 40 mask bits of one plane row (bit b <-> staged column b); out-of-domain columns read as 0
   const int mgx0 = bx + lane, mgx1 = bx + 32 + lane;
@@ -599,8 +611,13 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
   // loaded and every neighbour access goes through the no-slip ghost rule), and the plain variant
   // for the (vast majority of) strip-segments that contain no body cell, where the mask plane is
   // never read and the ghost selects vanish at compile time.
-  auto march = [&](auto masked_tag) {
+  // ... and once more for strips that touch the x-boundaries (EDGE): interior strips of the plain
+  // variant carry no inflow / outflow / ownership tests at all.
+  auto march = [&](auto masked_tag, auto edge_tag) {
     constexpr bool MASKED = decltype(masked_tag)::value;
+    constexpr bool EDGE = decltype(edge_tag)::value;
+    static_assert(EDGE || !MASKED, "the masked march always keeps the boundary tests");
+    const bool own = EDGE ? owned : ((lane >= 1) && (lane <= H2_OWN));
     auto mask_row = [&](int prow) -> unsigned long long {
       if constexpr (MASKED) {
         const uint8_t *mr = mask + (size_t)prow * W;
@@ -655,6 +672,9 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
     Face<R> yT_r{R(1), R(0), R(0), R(1), R(1), R(1)};
     Cons4<R> G_bot{R(0), R(0), R(0), R(0)};
 
+#ifdef H2_OPT_UNROLL
+#pragma unroll 2
+#endif
     for (int r = ys - 2; r < ye; ++r) {
       const int q = r - ys + 2;  // staged-row offset of row r
       if (r == ye - 3) {         // (a segment has at least one row: r = ye-3 >= ys-2 is reached)
@@ -663,7 +683,7 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
         item = __shfl_sync(0xffffffffu, claim, 0);
         if (item < (unsigned)P.nitems) desc = items[item];
       }
-      if (((q + 2) & (H2_RB - 1)) == 0) need_row(q + 2);
+      if (((q + 2) & (H2_RB - 1)) == 0) need_row(q + 2, edge_tag);
       mw_p2 = mask_row(r + 2 + H2_GHOST);
       const int ro_p2 = row_off(q + 2);
       const Prim4<R> Pr2 = cons_to_prim(P, ring.at(ro_p2, c));
@@ -680,10 +700,10 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
       if (r >= ys) {  // warp-uniform: the two warm-up rows skip the x-sweep and the update
         // -- x: neighbours by shuffle, edge lanes from the staged halo columns ----------------
         Prim4<R> Pl = shfl_up_prim(Pr), Pq = shfl_down_prim(Pr);
-        if (lane == 0 || lane == 31) {
-          const Prim4<R> e = cons_to_prim(P, ring.at(ro_c, lane == 0 ? c - 1 : c + 1));
+        {  // (a divergent branch taken by 2 lanes costs the same issue slots as all 32 taking it)
+          const Prim4<R> e = cons_to_prim(P, ring.at(ro_c, c + (lane == 0 ? -1 : (lane == 31 ? 1 : 0))));
           if (lane == 0) Pl = e;
-          else Pq = e;
+          if (lane == 31) Pq = e;
         }
         Face<R> xL, xR;
         reconstruct_predict<0>(P, nb(mw_c, c - 1, Pr, Pl), Pr, nb(mw_c, c + 1, Pr, Pq), half_dt, xL,
@@ -692,7 +712,7 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
         Cons4<R> F_right;
         {
           const Face<R> xL_B = shfl_down_face(xL);
-          const bool inA = (x >= 0) && (x < W), inB = (x + 1 >= 0) && (x + 1 < W);
+          const bool inA = !EDGE || ((x >= 0) && (x < W)), inB = !EDGE || ((x + 1 >= 0) && (x + 1 < W));
           const bool hasA = inA && !m_c, hasB = inB && !bit(mw_c, c + 1);
           Face<R> lo = xR, hi = xL_B;
           if (!(hasA && hasB)) {
@@ -711,7 +731,7 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
         const Cons4<R> F_left = shfl_up_cons(F_right);
 
         // -- update (k_step :1097-1175) -------------------------------------------------------
-        if (owned) {
+        if (own) {
           const Cons4<R> Ur = ring.at(ro_c, c);
           Cons4<R> Un = Ur;
           if (!m_c) {
@@ -763,7 +783,7 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
             // max wavespeed of the state the NEXT step will see (k_max_wavespeed_blocks
             // :786-819); column 0 is overwritten with the inflow state before that scan (:1834)
             R ws;
-            if (x == 0) {
+            if (EDGE && x == 0) {
               ws = (R)P.infl_speed;
             } else {
               const R a = sound_speed(P, pp);
@@ -849,8 +869,9 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
     }
   };
 
-  if (item_masked) march(std::true_type{});
-  else march(std::false_type{});
+  if (item_masked) march(std::true_type{}, std::true_type{});
+  else if (edge_strip) march(std::false_type{}, std::true_type{});
+  else march(std::false_type{}, std::false_type{});
 
   kb += (unsigned)nblk;  // every staged block has been acquired; the ring carries on from here
   __syncwarp();

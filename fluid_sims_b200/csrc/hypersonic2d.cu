@@ -618,6 +618,8 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
     constexpr bool EDGE = decltype(edge_tag)::value;
     static_assert(EDGE || !MASKED, "the masked march always keeps the boundary tests");
     const bool own = EDGE ? owned : ((lane >= 1) && (lane <= H2_OWN));
+    // rows 2 .. H_local-3 have no consumer besides this slab's own planes
+    const unsigned interior_rows = (unsigned)max(P.H_local - 2 * H2_GHOST, 0);
     auto mask_row = [&](int prow) -> unsigned long long {
       if constexpr (MASKED) {
         const uint8_t *mr = mask + (size_t)prow * W;
@@ -666,26 +668,40 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
     unsigned long long mw_m2 = 0, mw_m1 = 0, mw_c, mw_p1, mw_p2;
     mw_c = mask_row(ys + 0);   // local row ys-2 (plane row = local row + 2)
     mw_p1 = mask_row(ys + 1);  // local row ys-1
-    // ring offsets of rows r-2, r-1, r, r+1
-    int ro_m2 = 0, ro_m1 = 0, ro_c = row_off(0), ro_p1 = row_off(1);
+    // ring offsets of rows r-2, r-1, r, r+1 (and r+2, advanced incrementally: +1 row inside a
+    // 4-row block, on to the next slot when a block is entered)
+    int ro_m2 = 0, ro_m1 = 0, ro_c = row_off(0), ro_p1 = row_off(1), ro_p2 = ro_p1;
+    unsigned slot_p2 = kb % H2_NS;
     Prim4<R> Pr = cons_to_prim(P, ring.at(ro_c, c)), Pr1 = cons_to_prim(P, ring.at(ro_p1, c));
     Face<R> yT_r{R(1), R(0), R(0), R(1), R(1), R(1)};
     Cons4<R> G_bot{R(0), R(0), R(0), R(0)};
 
-#ifdef H2_OPT_UNROLL
-#pragma unroll 2
-#endif
     for (int r = ys - 2; r < ye; ++r) {
       const int q = r - ys + 2;  // staged-row offset of row r
-      if (r == ye - 3) {         // (a segment has at least one row: r = ye-3 >= ys-2 is reached)
-        if (lane == 0) claim = nwarps_grid + atomicAdd(&ctrl->next_item[step_slot], 1u);
-      } else if (r == ye - 1) {
-        item = __shfl_sync(0xffffffffu, claim, 0);
-        if (item < (unsigned)P.nitems) desc = items[item];
+      if (r >= ye - 3) {         // (a segment has at least one row: r = ye-3 >= ys-2 is reached)
+        if (r == ye - 3) {
+          if (lane == 0) claim = nwarps_grid + atomicAdd(&ctrl->next_item[step_slot], 1u);
+        } else if (r == ye - 1) {
+          item = __shfl_sync(0xffffffffu, claim, 0);
+          if (item < (unsigned)P.nitems) desc = items[item];
+        }
       }
-      if (((q + 2) & (H2_RB - 1)) == 0) need_row(q + 2, edge_tag);
+      ro_p2 += H2_BOXW;
+      if (((q + 2) & (H2_RB - 1)) == 0) {
+        // row q+2 opens block B = (q+2)/4: wait for it; block B-2 died with row q-3, so its slot
+        // takes block B+1 (needed four rows from now)
+        need_row(q + 2, edge_tag);
+        slot_p2 = (slot_p2 + 1 == H2_NS) ? 0u : slot_p2 + 1;
+        ro_p2 = (int)slot_p2 * (4 * H2_RB * H2_BOXW);
+        if (q >= 6) {
+          __syncwarp();
+          if (issued < nblk) {
+            issue(issued);
+            ++issued;
+          }
+        }
+      }
       mw_p2 = mask_row(r + 2 + H2_GHOST);
-      const int ro_p2 = row_off(q + 2);
       const Prim4<R> Pr2 = cons_to_prim(P, ring.at(ro_p2, c));
 
       // -- y: reconstruct cell r+1, flux through face r+1/2 ----------------------------------
@@ -800,7 +816,7 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
           Uout[3 * PL + o] = Un.E;
           // The first and last two rows of the slab have extra consumers; one warp-uniform test
           // keeps all of that out of the way of every other row.
-          if (r < H2_GHOST || r >= P.H_local - H2_GHOST) {
+          if ((unsigned)(r - H2_GHOST) >= interior_rows) {
           // multi-GPU: push boundary rows into the slab neighbours' ghost rows (peer memory)
           if (peer.up_out != nullptr && r < H2_GHOST) {
             pushed = true;
@@ -857,15 +873,6 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
       ro_m1 = ro_c;
       ro_c = ro_p1;
       ro_p1 = ro_p2;
-
-      // rows <= q-2 are dead for the next iteration: recycle a slot once its last row is
-      if (q >= 5 && ((q - 2) & 3) == 3) {
-        __syncwarp();
-        if (issued < nblk) {
-          issue(issued);
-          ++issued;
-        }
-      }
     }
   };
 

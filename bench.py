@@ -12,10 +12,13 @@ Definitions
            cell-updates.  `value` = W*H*K / t_device, inputs resident in HBM, t from CUDA events on
            the launching stream, max over ranks.
   e2e      the same metric through the C-ABI with HOST buffers: every e2e step is one *frame* of
-           the reference's frame loop — upload the 4 state planes from pinned host memory
-           (tau_hyp2d_upload), run `steps_per_frame` solver steps (reference default 2,
-           tau_hypersonic_cuda.cu:1407), download the 4 planes (tau_hyp2d_download) — all inside
-           the timed region (wall clock around synchronous calls).
+           the reference's frame loop — upload the 4 state planes from pinned host memory, run
+           `steps_per_frame` solver steps (reference default 2, tau_hypersonic_cuda.cu:1407),
+           download the 4 planes — all inside the timed region (wall clock, drained at the end).
+           At N=1 two frames are in flight (two handles on two streams, tau_hyp2d_upload_async /
+           tau_hyp2d_download_async), so the H2D copy of one frame overlaps the D2H copy of the
+           other; at N>1 frames are synchronous (the ghost-row hand-over after an upload is a
+           host-driven NCCL exchange).
   roofline achieved = 33 algorithmic bytes/cell (read 4 fp32 fields + 1 mask byte, write 4 fields;
            SURVEY.md §8(d)) x W*H / average duration of one hyp2d_step launch (CUDA events over the
            timed region, in which it is the only kernel) vs the measured HBM copy bandwidth in
@@ -284,20 +287,53 @@ def run_product(a):
         in_ptrs = (C.c_void_p * 4)(*[t_.data_ptr() for t_ in host_in])
         out_ptrs = (C.c_void_p * 4)(*[t_.data_ptr() for t_ in host_out])
 
-        def frame():
-            h2.check(h2._upload(sim._handle, in_ptrs, C.c_void_p(0)))
-            resync()
-            advance(a.steps_per_frame)
-            h2.check(h2._download(sim._handle, out_ptrs, C.c_void_p(0)))
+        pipelined = world == 1
+        if pipelined:
+            # two frames in flight: a second handle on its own stream, so that the upload of frame
+            # i+1 (H2D copy engine) overlaps the download of frame i (D2H copy engine)
+            stream_b = torch.cuda.Stream(device=dev)
+            sim_b = Hypersonic2D(cfg, dtype=a.dtype, device=dev, y_begin=y0, h_local=hl,
+                                 stream=stream_b.cuda_stream)
+            if a.seg_rows:
+                sim_b.set_seg_rows(a.seg_rows)
+            sim_b.init()
+            host_out_b = [torch.empty((hl, W), dtype=tdt).pin_memory() for _ in range(4)]
+            out_ptrs_b = (C.c_void_p * 4)(*[t_.data_ptr() for t_ in host_out_b])
+            lanes = [(sim, out_ptrs), (sim_b, out_ptrs_b)]
 
-        for _ in range(3):
-            frame()
+            def frame(i):
+                h, optr = lanes[i % 2]
+                h2.check(h2._sync(h._handle))          # this lane's previous frame has landed
+                h2.check(h2._upload_async(h._handle, in_ptrs, C.c_void_p(0)))
+                h2.check(h2._step(h._handle, a.steps_per_frame))
+                h2.check(h2._download_async(h._handle, optr, C.c_void_p(0)))
+
+            def drain():
+                for h, _ in lanes:
+                    h2.check(h2._sync(h._handle))
+        else:
+            def frame(i):
+                h2.check(h2._upload(sim._handle, in_ptrs, C.c_void_p(0)))
+                resync()
+                advance(a.steps_per_frame)
+                h2.check(h2._download(sim._handle, out_ptrs, C.c_void_p(0)))
+
+            def drain():
+                pass
+
+        for i in range(4):
+            frame(i)
+        drain()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(a.e2e_frames):
-            frame()
+        for i in range(a.e2e_frames):
+            frame(i)
+        drain()
         barrier()
         dt_wall = time.perf_counter() - t0
+        if pipelined:
+            # both lanes computed the same frame from the same input: identical results
+            assert all(torch.equal(x, y) for x, y in zip(host_out, host_out_b)), "pipelined lanes differ"
         if world > 1:
             t = torch.tensor([dt_wall], device=f"cuda:{dev}", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -306,6 +342,7 @@ def run_product(a):
         e2e = {"value": cells * a.steps_per_frame * a.e2e_frames / dt_wall / 1e6,
                "unit": "Mcell-updates/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                "steps_per_frame": a.steps_per_frame, "frames": a.e2e_frames,
+               "frames_in_flight": 2 if pipelined else 1,
                "ms_per_frame": dt_wall / a.e2e_frames * 1e3}
 
     cpu = None
@@ -332,7 +369,7 @@ def run_product(a):
                          "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
                          "algorithmic_bytes_per_cell": bpc, "kernel": "hyp2d_step",
                          "kernel_ms": kernel_ms,
-                         "note": "kernel is FP32-issue bound (~1e3 instr/cell), see DESIGN.md"},
+                         "note": "kernel is FP32-issue bound (~690 executed warp-instructions per 30-cell row, 80 % issue-slot utilisation), see DESIGN.md 4.1"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             **({"peer_timing": peer_timing} if peer_timing else {}),
         }))
@@ -351,7 +388,7 @@ def main():
     ap.add_argument("--develop", type=int, default=1500,
                     help="untimed steps run first so that the bow shock exists")
     ap.add_argument("--steps-per-frame", type=int, default=2)
-    ap.add_argument("--e2e-frames", type=int, default=10)
+    ap.add_argument("--e2e-frames", type=int, default=20)
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--seg-rows", type=int, default=0)
     ap.add_argument("--grid-w", type=int, default=0, help="experiments only (default 4096)")

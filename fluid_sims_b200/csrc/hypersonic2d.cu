@@ -1612,7 +1612,17 @@ int tau_hyp2d_init(tau_hyp2d *h) {
   return TAU_OK;
 }
 
+static int hyp2d_upload_impl(tau_hyp2d *h, const void *const planes[4], const uint8_t *mask, bool sync);
 int tau_hyp2d_upload(tau_hyp2d *h, const void *const planes[4], const uint8_t *mask) {
+  return hyp2d_upload_impl(h, planes, mask, true);
+}
+// Enqueue-only forms for pipelined frame loops (pinned host buffers; they must stay valid until
+// tau_hyp2d_sync): with two handles on two streams the upload of frame i+1 overlaps the download of
+// frame i on the two PCIe copy engines.
+int tau_hyp2d_upload_async(tau_hyp2d *h, const void *const planes[4], const uint8_t *mask) {
+  return hyp2d_upload_impl(h, planes, mask, false);
+}
+static int hyp2d_upload_impl(tau_hyp2d *h, const void *const planes[4], const uint8_t *mask, bool sync) {
   TAU_REQUIRE(h && planes, "tau_hyp2d_upload: null argument");
   TAU_CUDA(cudaSetDevice(h->device));
   const int es = elem_size(h);
@@ -1629,7 +1639,7 @@ int tau_hyp2d_upload(tau_hyp2d *h, const void *const planes[4], const uint8_t *m
   }
   int rc = hyp2d_state_changed(h, mask ? 1 : 0);
   if (rc) return rc;
-  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  if (sync) TAU_CUDA(cudaStreamSynchronize(h->stream));
   return TAU_OK;
 }
 
@@ -1659,7 +1669,14 @@ int tau_hyp2d_clock(tau_hyp2d *h, double *sim_t, double *dt_last) {
   return TAU_OK;
 }
 
+static int hyp2d_download_impl(tau_hyp2d *h, void *const planes[4], uint8_t *mask, bool sync);
 int tau_hyp2d_download(tau_hyp2d *h, void *const planes[4], uint8_t *mask) {
+  return hyp2d_download_impl(h, planes, mask, true);
+}
+int tau_hyp2d_download_async(tau_hyp2d *h, void *const planes[4], uint8_t *mask) {
+  return hyp2d_download_impl(h, planes, mask, false);
+}
+static int hyp2d_download_impl(tau_hyp2d *h, void *const planes[4], uint8_t *mask, bool sync) {
   TAU_REQUIRE(h && planes, "tau_hyp2d_download: null argument");
   TAU_CUDA(cudaSetDevice(h->device));
   const int es = elem_size(h);
@@ -1670,7 +1687,7 @@ int tau_hyp2d_download(tau_hyp2d *h, void *const planes[4], uint8_t *mask) {
       TAU_CUDA(cudaMemcpyAsync(planes[f], (char *)h->U[h->cur] + (f * h->plane_elems + row0) * es, n * es,
                                cudaMemcpyDeviceToHost, h->stream));
   if (mask) TAU_CUDA(cudaMemcpyAsync(mask, h->mask + row0, n, cudaMemcpyDeviceToHost, h->stream));
-  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  if (sync) TAU_CUDA(cudaStreamSynchronize(h->stream));
   return TAU_OK;
 }
 

@@ -31,6 +31,8 @@ _step = declare("tau_hyp2d_step", [_h, C.c_int])
 _clock = declare("tau_hyp2d_clock", [_h, C.POINTER(C.c_double), C.POINTER(C.c_double)])
 _download = declare("tau_hyp2d_download", [_h, C.POINTER(C.c_void_p), C.c_void_p])
 _sync = declare("tau_hyp2d_sync", [_h])
+_upload_async = declare("tau_hyp2d_upload_async", [_h, C.POINTER(C.c_void_p), C.c_void_p])
+_download_async = declare("tau_hyp2d_download_async", [_h, C.POINTER(C.c_void_p), C.c_void_p])
 _devstate = declare("tau_hyp2d_device_state", [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                                C.POINTER(C.c_void_p)])
 _set_seg = declare("tau_hyp2d_set_seg_rows", [_h, C.c_int])

@@ -112,6 +112,10 @@ int tau_hyp2d_step(tau_hyp2d *h, int nsteps);
 /* sim_t (:1888) and the dt of the most recent step; synchronises */
 int tau_hyp2d_clock(tau_hyp2d *h, double *sim_t, double *dt_last);
 int tau_hyp2d_download(tau_hyp2d *h, void *const planes[4], uint8_t *mask);
+/* enqueue-only forms (host buffers must be pinned and stay valid until tau_hyp2d_sync): with two
+ * handles on two streams a frame loop overlaps the upload of frame i+1 with the download of frame i */
+int tau_hyp2d_upload_async(tau_hyp2d *h, const void *const planes[4], const uint8_t *mask);
+int tau_hyp2d_download_async(tau_hyp2d *h, void *const planes[4], uint8_t *mask);
 int tau_hyp2d_sync(tau_hyp2d *h);
 /* slab plumbing: device pointers of the current planes (4 contiguous planes of (h_local+4) x W,
  * starting at ghost row -2), the mask (same row layout) and the max-wavespeed scalar the next

@@ -73,18 +73,39 @@ __device__ __forceinline__ float signed_denom_guard(float x) {  // :147
   return copysignf(fmaxf(fabsf(x), DENOM_EPS), x);
 }
 __device__ __forceinline__ int wrapi(int i, int n) {  // :156
-  i %= n;
-  return (i < 0) ? i + n : i;
+  // callers are at most one period out of range; the integer modulo (~25 instructions, 7 % of the
+  // kernel's stall samples) is only kept for grids narrower than the halo
+  if (i < 0) i += n;
+  else if (i >= n) i -= n;
+  if ((unsigned)i >= (unsigned)n) {
+    i %= n;
+    if (i < 0) i += n;
+  }
+  return i;
+}
+// Quotient without the FCHK slow path.  nvcc expands `a / b` into MUFU.RCP + an FFMA refinement
+// guarded by FCHK, and FCHK sends a ZERO NUMERATOR to a ~30-instruction subroutine.  Numerators
+// are exactly zero all the time here (v = w = 0 in the free stream, flux differences of uniform
+// regions, zero jumps in the shock sensor): measured 1.7 slow-path calls per cell, 19 % of all
+// executed instructions (profiles/hyp3d_r1_experiments.md).  rcp.approx + one exact-residual
+// correction gives the correctly rounded quotient for operands in the normal range (every divisor
+// here is floored away from zero) and exactly 0 for a zero numerator.
+__device__ __forceinline__ float fdiv(float a, float b) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+  const float q = a * r;
+  return fmaf(fmaf(-b, q, a), r, q);
 }
 __device__ __forceinline__ float asinhf_dev(float x) {  // :121-125
   float ax = fabsf(x);
   return copysignf(logf(ax + sqrtf(ax * ax + 1.0f)), x);
 }
 __device__ __forceinline__ float evib_eq(const Par &P, float T) {  // :206-211
-  float a = P.theta_v / fmaxf(T, NEWTON_TEMP_FLOOR);
+  float a = fdiv(P.theta_v, fmaxf(T, NEWTON_TEMP_FLOOR));
   float ea = __expf(a);
-  float denom = fmaxf(ea - 1.f, NEWTON_TEMP_FLOOR);
-  return (P.R * P.theta_v) / denom;
+  // (cold gas: __expf overflows to +inf, and (R theta_v) / inf = 0 — fdiv needs a finite divisor)
+  float denom = fminf(fmaxf(ea - 1.f, NEWTON_TEMP_FLOOR), 3.0e38f);
+  return fdiv(P.R * P.theta_v, denom);
 }
 __device__ __forceinline__ Q decode(const Par &P, float xi, float phx, float phy, float phz,
                                     float lam, float zet) {  // log_to_prim_fast :213-225
@@ -104,19 +125,19 @@ __device__ __forceinline__ C6 prim_to_cons(const Par &P, const Q &q) {  // :234-
   U.my = q.r * q.v;
   U.mz = q.r * q.w;
   float ke = 0.5f * (q.u * q.u + q.v * q.v + q.w * q.w);
-  float e_th = q.p / fmaxf((P.gamma_floor - 1.f) * q.r, RHO_P_FLOOR);
+  float e_th = fdiv(q.p, fmaxf((P.gamma_floor - 1.f) * q.r, RHO_P_FLOOR));
   U.Ev = q.r * q.ev;
   U.Et = q.r * (ke + e_th + q.ev);
   return U;
 }
 __device__ __forceinline__ float soundspeed(const Par &P, const Q &q) {  // :264
-  return sqrtf(fmaxf(P.gamma_floor * q.p / q.r, DENOM_EPS));
+  return sqrtf(fmaxf(fdiv(P.gamma_floor * q.p, q.r), DENOM_EPS));
 }
 __device__ __forceinline__ C6 axis_flux(const Par &P, const Q &q, int axis) {  // :268-308
   C6 F;
   float un = axis == 0 ? q.u : (axis == 1 ? q.v : q.w);
-  float H = (q.p / q.r) + (0.5f * (q.u * q.u + q.v * q.v + q.w * q.w) + q.ev) +
-            q.p / fmaxf((P.gamma_floor - 1.f) * q.r, RHO_P_FLOOR);
+  float H = fdiv(q.p, q.r) + (0.5f * (q.u * q.u + q.v * q.v + q.w * q.w) + q.ev) +
+            fdiv(q.p, fmaxf((P.gamma_floor - 1.f) * q.r, RHO_P_FLOOR));
   F.r = q.r * un;
   F.mx = q.r * q.u * un + (axis == 0 ? q.p : 0.f);
   F.my = q.r * q.v * un + (axis == 1 ? q.p : 0.f);
@@ -128,7 +149,7 @@ __device__ __forceinline__ C6 axis_flux(const Par &P, const Q &q, int axis) {  /
 __device__ __forceinline__ float entropy_fix_speed(float s, float a_ref) {  // :366-374
   float d = 0.1f * a_ref, as = fabsf(s);
   float sgn = (s >= 0.f) ? 1.f : -1.f;
-  float sm = 0.5f * (as * as / fmaxf(d, DENOM_EPS) + d);
+  float sm = 0.5f * (fdiv(as * as, fmaxf(d, DENOM_EPS)) + d);
   return (as >= d) ? s : sgn * sm;
 }
 
@@ -147,7 +168,7 @@ __device__ __forceinline__ C6 hllc_flux_axis(const Par &P, const Q &L, const Q &
   C6 FR = axis_flux(P, R, axis);
   float rL = L.r, rR = R.r, pL = L.p, pR = R.p;
   float denom = signed_denom_guard(rL * (sL - unL) - rR * (sR - unR));
-  float sM = (pR - pL + rL * unL * (sL - unL) - rR * unR * (sR - unR)) / denom;
+  float sM = fdiv(pR - pL + rL * unL * (sL - unL) - rR * unR * (sR - unR), denom);
   float pStarL = pL + rL * (sL - unL) * (sM - unL);
   float pStarR = pR + rR * (sR - unR) * (sM - unR);
   float pStar = 0.5f * (pStarL + pStarR);
@@ -155,11 +176,11 @@ __device__ __forceinline__ C6 hllc_flux_axis(const Par &P, const Q &L, const Q &
   if (axis == 0) vCarb = (fabsf(L.v) + fabsf(R.v) + fabsf(L.w) + fabsf(R.w)) * 0.5f;
   else if (axis == 1) vCarb = (fabsf(L.u) + fabsf(R.u) + fabsf(L.w) + fabsf(R.w)) * 0.5f;
   else vCarb = (fabsf(L.u) + fabsf(R.u) + fabsf(L.v) + fabsf(R.v)) * 0.5f;
-  float align = clampf(1.f - vCarb / fmaxf(aRef, DENOM_EPS), 0.f, 1.f);
-  float dp = fabsf(R.p - L.p) / fmaxf(R.p + L.p, DENOM_EPS);  // shock_sensor :376-381
-  float dr = fabsf(R.r - L.r) / fmaxf(R.r + L.r, DENOM_EPS);
+  float align = clampf(1.f - fdiv(vCarb, fmaxf(aRef, DENOM_EPS)), 0.f, 1.f);
+  float dp = fdiv(fabsf(R.p - L.p), fmaxf(R.p + L.p, DENOM_EPS));  // shock_sensor :376-381
+  float dr = fdiv(fabsf(R.r - L.r), fmaxf(R.r + L.r, DENOM_EPS));
   float alpha = clampf(5.f * (0.5f * (dp + dr)), 0.f, 1.f) * align;
-  float inv_hll = 1.f / signed_denom_guard(sR - sL), ss = sL * sR;
+  float inv_hll = fdiv(1.f, signed_denom_guard(sR - sL)), ss = sL * sR;
   C6 FHLL;
   FHLL.r = ((FL.r * sR - FR.r * sL) + (UR.r - UL.r) * ss) * inv_hll;
   FHLL.mx = ((FL.mx * sR - FR.mx * sL) + (UR.mx - UL.mx) * ss) * inv_hll;
@@ -173,9 +194,9 @@ __device__ __forceinline__ C6 hllc_flux_axis(const Par &P, const Q &L, const Q &
   const C6 &FK = left ? FL : FR;
   float sK = left ? sL : sR, unK = left ? unL : unR;
   float starDenom = signed_denom_guard(sK - sM);
-  float rStar = K.r * (sK - unK) / starDenom;
-  float EStar = ((sK - unK) * UK.Et - K.p * unK + pStar * sM) / starDenom;
-  float EvStar = UK.Ev * (sK - unK) / starDenom;
+  float rStar = fdiv(K.r * (sK - unK), starDenom);
+  float EStar = fdiv((sK - unK) * UK.Et - K.p * unK + pStar * sM, starDenom);
+  float EvStar = fdiv(UK.Ev * (sK - unK), starDenom);
   C6 US;  // fill_star_momentum :335-350
   US.r = rStar;
   US.mx = rStar * (axis == 0 ? sM : K.u);
@@ -212,7 +233,7 @@ __device__ __forceinline__ float weno5_left(float v0, float v1, float v2, float 
   float e1 = (WENO_EPS + b1) * (WENO_EPS + b1);
   float e2 = (WENO_EPS + b2) * (WENO_EPS + b2);
   float n0 = 0.1f * (e1 * e2), n1 = 0.6f * (e0 * e2), n2 = 0.3f * (e0 * e1);
-  return (n0 * p0 + n1 * p1 + n2 * p2) / (n0 + n1 + n2);
+  return fdiv(n0 * p0 + n1 * p1 + n2 * p2, n0 + n1 + n2);
 }
 __device__ __forceinline__ void prim_floor_fast(Q &q) {  // :565-571
   q.r = fmaxf(q.r, RHO_P_FLOOR);
@@ -226,14 +247,14 @@ __device__ __forceinline__ Q inflow_prim(const Par &P) {  // :611-622
   q.v = P.inflow_v;
   q.w = P.inflow_w;
   q.p = fmaxf(P.inflow_p, RHO_P_FLOOR);
-  q.ev = evib_eq(P, q.p / (q.r * P.R));
+  q.ev = evib_eq(P, fdiv(q.p, q.r * P.R));
   return q;
 }
 __device__ __forceinline__ void apply_wall(const Par &P, Q &q) {  // :511-521
   float p_keep = fmaxf(q.p, RHO_P_FLOOR);
   q.u = q.v = q.w = 0.f;
   q.p = p_keep;
-  q.r = fmaxf(q.p / (P.R * fmaxf(P.Twall, NEWTON_TEMP_FLOOR)), RHO_P_FLOOR);
+  q.r = fmaxf(fdiv(q.p, P.R * fmaxf(P.Twall, NEWTON_TEMP_FLOOR)), RHO_P_FLOOR);
   q.ev = evib_eq(P, P.Twall);
 }
 __device__ __forceinline__ float sdf_sphere(const Par &P, float x, float y, float z) {  // :173-178
@@ -400,35 +421,35 @@ hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out,
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
         const float *sf = s_f + k * T3_NF;
-        const float dU = -((sf[fxp] - sf[fxm]) / P.dx + (sf[fyp] - sf[fym]) / P.dy +
-                           (sf[fzp] - sf[fzm]) / P.dz);
+        const float dU = -(fdiv(sf[fxp] - sf[fxm], P.dx) + fdiv(sf[fyp] - sf[fym], P.dy) +
+                           fdiv(sf[fzp] - sf[fzm], P.dz));
         U1[k] = U0a[k] + dU * dt;
       }
       // cons_to_prim :247-262
       Q q1;
       q1.r = fmaxf(U1[0], RHO_P_FLOOR);
-      q1.u = U1[1] / q1.r;
-      q1.v = U1[2] / q1.r;
-      q1.w = U1[3] / q1.r;
+      q1.u = fdiv(U1[1], q1.r);
+      q1.v = fdiv(U1[2], q1.r);
+      q1.w = fdiv(U1[3], q1.r);
       {
         const float ke = 0.5f * (q1.u * q1.u + q1.v * q1.v + q1.w * q1.w);
-        const float ev = fmaxf(U1[5] / q1.r, 0.f);
-        const float e_th = fmaxf(U1[4] / q1.r - ke - ev, THERMAL_ENERGY_FLOOR);
+        const float ev = fmaxf(fdiv(U1[5], q1.r), 0.f);
+        const float e_th = fmaxf(fdiv(U1[4], q1.r) - ke - ev, THERMAL_ENERGY_FLOOR);
         q1.p = fmaxf((P.gamma_floor - 1.f) * q1.r * e_th, RHO_P_FLOOR);
         q1.ev = ev;
       }
       if (!isfinite(q1.r) || !isfinite(q1.p) || !isfinite(q1.u) || !isfinite(q1.v) ||
           !isfinite(q1.w) || !isfinite(q1.ev) || q1.r <= 0.f || q1.p <= 0.f || q1.ev < 0.f)
         q1 = inflow_prim(P);  // :1284-1289
-      float T1 = q1.p / (q1.r * P.R);
-      q1.ev = fmaxf(q1.ev + (evib_eq(P, T1) - q1.ev) * (dt / fmaxf(P.tau_vib, TAU_VIB_MIN)), 0.f);
+      float T1 = fdiv(q1.p, q1.r * P.R);
+      q1.ev = fmaxf(q1.ev + (evib_eq(P, T1) - q1.ev) * fdiv(dt, fmaxf(P.tau_vib, TAU_VIB_MIN)), 0.f);
       const float tr = fmaxf(P.inflow_r, RHO_P_FLOOR), tp = fmaxf(P.inflow_p, RHO_P_FLOOR);
       const int nsp = P.sponge_n > 0 ? P.sponge_n : 0;
       if (nsp > 0 && x < nsp) {  // inflow sponge :1295-1318
         float s = 1.0f - (float)x / (float)nsp;
         s = fminf(fmaxf(s, 0.0f), 1.0f);
         const float k = P.sponge_strength * (s * s);
-        const float tev = evib_eq(P, tp / (tr * P.R));
+        const float tev = evib_eq(P, fdiv(tp, tr * P.R));
         q1.r = fmaxf(q1.r + k * (tr - q1.r), RHO_P_FLOOR);
         q1.p = fmaxf(q1.p + k * (tp - q1.p), RHO_P_FLOOR);
         q1.u = q1.u + k * (inflow_gain * P.inflow_u - q1.u);
@@ -441,7 +462,7 @@ hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out,
         float s = (float)(x - (P.nx - nspo)) / (float)nspo;
         s = fminf(fmaxf(s, 0.0f), 1.0f);
         const float k = P.sponge_out_strength * (s * s);
-        const float tev = evib_eq(P, tp / (tr * P.R));
+        const float tev = evib_eq(P, fdiv(tp, tr * P.R));
         q1.r = fmaxf(q1.r + k * (tr - q1.r), RHO_P_FLOOR);
         q1.p = fmaxf(q1.p + k * (tp - q1.p), RHO_P_FLOOR);
         q1.u = q1.u + k * (0.0f - q1.u);
@@ -450,12 +471,12 @@ hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out,
         q1.ev = fmaxf(q1.ev + k * (tev - q1.ev), 0.f);
       }
       const float a = soundspeed(P, q1);  // :1345-1351
-      const float sw = (fabsf(q1.u) + a) / P.dx + (fabsf(q1.v) + a) / P.dy + (fabsf(q1.w) + a) / P.dz;
+      const float sw = fdiv(fabsf(q1.u) + a, P.dx) + fdiv(fabsf(q1.v) + a, P.dy) + fdiv(fabsf(q1.w) + a, P.dz);
       if (isfinite(sw) && sw > 0.f) ssum = sw;
       out[i] = __logf(fmaxf(q1.r, RHO_P_FLOOR));  // :1353-1358
-      out[PL + i] = asinhf_dev(q1.u / P.u_ref);
-      out[2 * PL + i] = asinhf_dev(q1.v / P.u_ref);
-      out[3 * PL + i] = asinhf_dev(q1.w / P.u_ref);
+      out[PL + i] = asinhf_dev(fdiv(q1.u, P.u_ref));
+      out[2 * PL + i] = asinhf_dev(fdiv(q1.v, P.u_ref));
+      out[3 * PL + i] = asinhf_dev(fdiv(q1.w, P.u_ref));
       out[4 * PL + i] = __logf(fmaxf(q1.p, RHO_P_FLOOR));
       out[5 * PL + i] = __logf(fmaxf(q1.ev, RHO_P_FLOOR));
     }

@@ -15,7 +15,7 @@ Definitions
            the reference's frame loop — upload the 4 state planes from pinned host memory, run
            `steps_per_frame` solver steps (reference default 2, tau_hypersonic_cuda.cu:1407),
            download the 4 planes — all inside the timed region (wall clock, drained at the end).
-           At N=1 two frames are in flight (two handles on two streams, tau_hyp2d_upload_async /
+           At N=1 three frames are in flight (one handle per frame in flight, each on its own stream, tau_hyp2d_upload_async /
            tau_hyp2d_download_async), so the H2D copy of one frame overlaps the D2H copy of the
            other; at N>1 frames are synchronous (the ghost-row hand-over after an upload is a
            host-driven NCCL exchange).
@@ -289,27 +289,29 @@ def run_product(a):
 
         pipelined = world == 1
         if pipelined:
-            # two frames in flight: a second handle on its own stream, so that the upload of frame
-            # i+1 (H2D copy engine) overlaps the download of frame i (D2H copy engine)
-            stream_b = torch.cuda.Stream(device=dev)
-            sim_b = Hypersonic2D(cfg, dtype=a.dtype, device=dev, y_begin=y0, h_local=hl,
-                                 stream=stream_b.cuda_stream)
-            if a.seg_rows:
-                sim_b.set_seg_rows(a.seg_rows)
-            sim_b.init()
-            host_out_b = [torch.empty((hl, W), dtype=tdt).pin_memory() for _ in range(4)]
-            out_ptrs_b = (C.c_void_p * 4)(*[t_.data_ptr() for t_ in host_out_b])
-            lanes = [(sim, out_ptrs), (sim_b, out_ptrs_b)]
+            # several frames in flight: extra handles on their own streams, so that the upload of
+            # frame i+1 (H2D copy engine) overlaps the download of frame i (D2H copy engine)
+            lanes = [(sim, out_ptrs, host_out)]
+            lane_streams = []
+            for _ in range(a.e2e_lanes - 1):
+                st = torch.cuda.Stream(device=dev)
+                sb = Hypersonic2D(cfg, dtype=a.dtype, device=dev, y_begin=y0, h_local=hl, stream=st.cuda_stream)
+                if a.seg_rows:
+                    sb.set_seg_rows(a.seg_rows)
+                sb.init()
+                ho = [torch.empty((hl, W), dtype=tdt).pin_memory() for _ in range(4)]
+                lanes.append((sb, (C.c_void_p * 4)(*[t_.data_ptr() for t_ in ho]), ho))
+                lane_streams.append(st)  # keep the stream alive
 
             def frame(i):
-                h, optr = lanes[i % 2]
+                h, optr, _ = lanes[i % len(lanes)]
                 h2.check(h2._sync(h._handle))          # this lane's previous frame has landed
                 h2.check(h2._upload_async(h._handle, in_ptrs, C.c_void_p(0)))
                 h2.check(h2._step(h._handle, a.steps_per_frame))
                 h2.check(h2._download_async(h._handle, optr, C.c_void_p(0)))
 
             def drain():
-                for h, _ in lanes:
+                for h, _, _ in lanes:
                     h2.check(h2._sync(h._handle))
         else:
             def frame(i):
@@ -321,7 +323,7 @@ def run_product(a):
             def drain():
                 pass
 
-        for i in range(4):
+        for i in range(2 * a.e2e_lanes):
             frame(i)
         drain()
         barrier()
@@ -333,7 +335,8 @@ def run_product(a):
         dt_wall = time.perf_counter() - t0
         if pipelined:
             # both lanes computed the same frame from the same input: identical results
-            assert all(torch.equal(x, y) for x, y in zip(host_out, host_out_b)), "pipelined lanes differ"
+            for _, _, ho in lanes[1:]:
+                assert all(torch.equal(x, y) for x, y in zip(host_out, ho)), "pipelined lanes differ"
         if world > 1:
             t = torch.tensor([dt_wall], device=f"cuda:{dev}", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -342,7 +345,7 @@ def run_product(a):
         e2e = {"value": cells * a.steps_per_frame * a.e2e_frames / dt_wall / 1e6,
                "unit": "Mcell-updates/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                "steps_per_frame": a.steps_per_frame, "frames": a.e2e_frames,
-               "frames_in_flight": 2 if pipelined else 1,
+               "frames_in_flight": a.e2e_lanes if pipelined else 1,
                "ms_per_frame": dt_wall / a.e2e_frames * 1e3}
 
     cpu = None
@@ -388,7 +391,8 @@ def main():
     ap.add_argument("--develop", type=int, default=1500,
                     help="untimed steps run first so that the bow shock exists")
     ap.add_argument("--steps-per-frame", type=int, default=2)
-    ap.add_argument("--e2e-frames", type=int, default=20)
+    ap.add_argument("--e2e-frames", type=int, default=24)
+    ap.add_argument("--e2e-lanes", type=int, default=3, help="frames in flight in the e2e loop (N=1)")
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--seg-rows", type=int, default=0)
     ap.add_argument("--grid-w", type=int, default=0, help="experiments only (default 4096)")

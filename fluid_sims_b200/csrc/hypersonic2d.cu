@@ -136,8 +136,11 @@ __device__ __forceinline__ Prim4<R> cons_to_prim(const Params<R> &P, Cons4<R> c)
   R inv = rcp(rho);
   R u = c.mx * inv;
   R v = c.my * inv;
-  R kin = R(0.5) * rho * (u * u + v * v);
-  R eint = c.E - kin;
+  // contractions written out: the fused step epilogue and the standalone wavespeed scan (first
+  // step after init / upload / checkpoint load) must round alike, or a resumed run's first dt
+  // differs from the uninterrupted run's in the last bit
+  R q2 = fma(v, v, u * u);
+  R eint = fma(-(R(0.5) * rho), q2, c.E);
   p.rho = rho;
   p.u = u;
   p.v = v;

@@ -102,6 +102,21 @@ __device__ __forceinline__ float W_cubic_sel(float r, float inv_h, float alpha) 
   return q < 1.0f ? w1 : (q < 2.0f ? w2 : 0.f);
 }
 
+// gradW_cubic :118-133 with the reciprocal of h hoisted by the caller (same bits, see above)
+__device__ __forceinline__ float2 gradW_cubic_h(float2 rij, float r, float h, float inv_h, float alpha) {
+  if (r <= 1e-8f || r >= 2.0f * h) return make_float2(0.f, 0.f);
+  float q = r * inv_h;
+  float dWdq;
+  if (q < 1.0f) dWdq = alpha * (-3.0f * q + 2.25f * q * q);
+  else {
+    float t = 2.0f - q;
+    dWdq = alpha * (-0.75f * t * t);
+  }
+  float invr = 1.0f / r;
+  float dWdr = dWdq * inv_h;
+  return make_float2(dWdr * rij.x * invr, dWdr * rij.y * invr);
+}
+
 // ---- cell keys (k_build_cells :165-176, integer part) ------------------------------------------
 __global__ void sph_keys(const float2 *__restrict__ pos, unsigned *__restrict__ keys,
                          unsigned *__restrict__ vals, Consts c) {
@@ -340,6 +355,8 @@ sph_forces_integrate(const float2 *__restrict__ sxy, const float2 *__restrict__ 
   const float rhoi = rpi.x, pri = rpi.y;
   const int gx = grid_c(xi.x, c.cell, c.Gx), gy = grid_c(xi.y, c.cell, c.Gy);
   const float twoh = 2.f * c.h, twoh2 = twoh * twoh;
+  const float inv_h = rcp_approx(c.h);
+  const float eta2 = 0.01f * c.h * c.h, visc_c = -c.viscAlpha * c.c0;  // loop invariants of :247-249
   float ax = 0.f, ay = 0.f;
   if (valid) {
     // (the branch-free form of the density sweep does not pay here: measured +9 % instructions —
@@ -359,7 +376,7 @@ sph_forces_integrate(const float2 *__restrict__ sxy, const float2 *__restrict__ 
           const float2 rij = make_float2(xi.x - xj.x, xi.y - xj.y);
           const float r2 = rij.x * rij.x + rij.y * rij.y;
           const float r = sqrtf(r2);
-          const float2 gW = gradW_cubic(rij, r, c.h, c.alpha);
+          const float2 gW = gradW_cubic_h(rij, r, c.h, inv_h, c.alpha);
           const float2 rpj = srp[j];
           const float common = -c.mass * (pri + rpj.y);
           ax += common * gW.x;
@@ -369,9 +386,9 @@ sph_forces_integrate(const float2 *__restrict__ sxy, const float2 *__restrict__ 
             const float vx = vi.x - vj.x, vy = vi.y - vj.y;
             const float dot = vx * rij.x + vy * rij.y;
             if (dot < 0.f) {
-              const float mu = (c.h * dot) / (r2 + 0.01f * c.h * c.h);
+              const float mu = (c.h * dot) / (r2 + eta2);
               const float rhoBar = 0.5f * (rhoi + rpj.x);
-              const float Pi_ij = (-c.viscAlpha * c.c0 * mu) / rhoBar;
+              const float Pi_ij = (visc_c * mu) / rhoBar;
               ax += -c.mass * Pi_ij * gW.x;
               ay += -c.mass * Pi_ij * gW.y;
             }

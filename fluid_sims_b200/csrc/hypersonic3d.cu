@@ -268,6 +268,47 @@ __device__ __forceinline__ int zplane(const Par &P, int lz) {
   return (P.slab ? min(max(lz, -T3_H), P.nz_local + T3_H - 1) : wrapi(lz, P.nz_local)) + T3_H;
 }
 
+// prim_at_xbc :724-749 for grid column gx (any value), row gy (already wrapped) and LOCAL plane
+// glz: inflow state for x < 0, transmissive outflow (:691-722) for x >= nx, the decoded cell
+// otherwise; solid cells (mask inside the grid, analytic sphere outside it, :186-188) are forced to
+// the isothermal no-slip wall state.
+__device__ __forceinline__ Q halo_prim(const Par &P, const float *__restrict__ in,
+                                       const uint8_t *__restrict__ solid, int gx, int gy, int glz,
+                                       bool &is_solid) {
+  const size_t PL = P.plane;
+  const int nxy = P.nx * P.ny;
+  const int pz = zplane(P, glz);
+  Q q;
+  if (gx < 0 || gx >= P.nx) {
+    const int gz = wrapi(P.z_begin + glz, P.nz);
+    is_solid = sdf_sphere(P, (gx + 0.5f) * P.dx, (gy + 0.5f) * P.dy, (gz + 0.5f) * P.dz) < 0.f;
+    if (gx < 0) {
+      q = inflow_prim(P);
+    } else {
+      const size_t gi = (size_t)pz * nxy + (size_t)gy * P.nx + (P.nx - 1);
+      q = decode(P, in[gi], in[PL + gi], in[2 * PL + gi], in[3 * PL + gi], in[4 * PL + gi],
+                 in[5 * PL + gi]);
+      const float aR = soundspeed(P, q), un = q.u;
+      if (un < 0.0f) {
+        q = inflow_prim(P);
+      } else {
+        if (un < aR) {
+          const float p_amb = fmaxf(P.inflow_p, RHO_P_FLOOR);
+          q.p = fmaxf(q.p + 0.05f * (p_amb - q.p), RHO_P_FLOOR);
+        }
+        prim_floor_fast(q);
+      }
+    }
+  } else {
+    const size_t gi = (size_t)pz * nxy + (size_t)gy * P.nx + gx;
+    is_solid = solid[gi] != 0;
+    q = decode(P, in[gi], in[PL + gi], in[2 * PL + gi], in[3 * PL + gi], in[4 * PL + gi],
+               in[5 * PL + gi]);
+  }
+  if (is_solid) apply_wall(P, q);
+  return q;
+}
+
 __global__ void __launch_bounds__(T3_THREADS)
 hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out,
            const uint8_t *__restrict__ solid, Clock *__restrict__ clk, int slot) {
@@ -291,37 +332,8 @@ hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out,
   for (int tt = tid; tt < T3_SVOL; tt += T3_THREADS) {
     const int lz = tt / T3_SXY, rem = tt - lz * T3_SXY, ly = rem / T3_SX, lx = rem - ly * T3_SX;
     const int gx = bx0 + lx - T3_H, gy = wrapi(by0 + ly - T3_H, P.ny), glz = bz0 + lz - T3_H;
-    const int pz = zplane(P, glz);
     bool is_solid;
-    Q q;
-    if (gx < 0 || gx >= P.nx) {
-      // cell_is_solid outside the grid: analytic sphere (:186-188)
-      const int gz = wrapi(P.z_begin + glz, P.nz);
-      is_solid = sdf_sphere(P, (gx + 0.5f) * P.dx, (gy + 0.5f) * P.dy, (gz + 0.5f) * P.dz) < 0.f;
-      if (gx < 0) {
-        q = inflow_prim(P);
-      } else {  // outflow_prim_transmissive :691-722
-        const size_t gi = (size_t)pz * nxy + (size_t)gy * P.nx + (P.nx - 1);
-        q = decode(P, in[gi], in[PL + gi], in[2 * PL + gi], in[3 * PL + gi], in[4 * PL + gi],
-                   in[5 * PL + gi]);
-        const float aR = soundspeed(P, q), un = q.u;
-        if (un < 0.0f) {
-          q = inflow_prim(P);
-        } else {
-          if (un < aR) {
-            const float p_amb = fmaxf(P.inflow_p, RHO_P_FLOOR);
-            q.p = fmaxf(q.p + 0.05f * (p_amb - q.p), RHO_P_FLOOR);
-          }
-          prim_floor_fast(q);
-        }
-      }
-    } else {
-      const size_t gi = (size_t)pz * nxy + (size_t)gy * P.nx + gx;
-      is_solid = solid[gi] != 0;
-      q = decode(P, in[gi], in[PL + gi], in[2 * PL + gi], in[3 * PL + gi], in[4 * PL + gi],
-                 in[5 * PL + gi]);
-    }
-    if (is_solid) apply_wall(P, q);
+    const Q q = halo_prim(P, in, solid, gx, gy, glz, is_solid);
     s_q[tt] = q.r;
     s_q[T3_SVOL + tt] = q.u;
     s_q[2 * T3_SVOL + tt] = q.v;
@@ -534,6 +546,65 @@ __global__ void hyp3d_init(const Par P, float *st, const uint8_t *solid) {
   st[5 * P.plane + i] = __logf(fmaxf(ev, RHO_P_FLOOR));
 }
 
+
+// ---- diagnostic scalar field: k_vis :800-905 (the volume renderer's input) ---------------------------
+// The reference decodes a cell and its six neighbours per thread (7 x 6 transcendentals).  Here a CTA
+// decodes its 8x8x4 tile + a one-cell halo once into shared memory (600 decodes for 256 cells) with
+// the same boundary rule as the step kernel's tile build (prim_at_xbc), then every thread evaluates
+// the requested quantity from shared memory.  Modes: VisMode :784-794.
+constexpr int V3_SX = T3_TX + 2, V3_SY = T3_TY + 2, V3_SZ = T3_TZ + 2;
+constexpr int V3_SXY = V3_SX * V3_SY, V3_SVOL = V3_SXY * V3_SZ;
+__global__ void __launch_bounds__(T3_THREADS)
+hyp3d_vis(const Par P, const float *__restrict__ in, const uint8_t *__restrict__ solid,
+          float *__restrict__ out, int mode) {
+  __shared__ float s_r[V3_SVOL], s_u[V3_SVOL], s_v[V3_SVOL], s_w[V3_SVOL], s_p[V3_SVOL];
+  const int tid = (threadIdx.z * T3_TY + threadIdx.y) * T3_TX + threadIdx.x;
+  const int bx0 = blockIdx.x * T3_TX, by0 = blockIdx.y * T3_TY, bz0 = blockIdx.z * T3_TZ;
+  for (int tt = tid; tt < V3_SVOL; tt += T3_THREADS) {
+    const int lz = tt / V3_SXY, rem = tt - lz * V3_SXY, ly = rem / V3_SX, lx = rem - ly * V3_SX;
+    bool is_solid;
+    const Q q = halo_prim(P, in, solid, bx0 + lx - 1, wrapi(by0 + ly - 1, P.ny), bz0 + lz - 1, is_solid);
+    s_r[tt] = q.r; s_u[tt] = q.u; s_v[tt] = q.v; s_w[tt] = q.w; s_p[tt] = q.p;
+  }
+  __syncthreads();
+  const int x = bx0 + threadIdx.x, y = by0 + threadIdx.y, lz = bz0 + threadIdx.z;
+  if (x >= P.nx || y >= P.ny || lz >= P.nz_local) return;
+  const size_t i = ((size_t)lz * P.ny + y) * P.nx + x;  // idx3 :152 within the slab
+  if (solid[((size_t)(lz + T3_H) * P.ny + y) * P.nx + x]) {
+    out[i] = 0.f;
+    return;
+  }
+  const int c = ((threadIdx.z + 1) * V3_SY + threadIdx.y + 1) * V3_SX + threadIdx.x + 1;
+  const float r0 = s_r[c], u0 = s_u[c], v0 = s_v[c], w0 = s_w[c], p0 = s_p[c];
+  if (mode == 1) { out[i] = logf(1.0f + fmaxf(r0, 0.0f)); return; }   // VIS_LOG_RHO, safe_log1pf_dev :796
+  if (mode == 2) { out[i] = logf(1.0f + fmaxf(p0, 0.0f)); return; }   // VIS_LOG_P
+  const float sp = sqrtf(u0 * u0 + v0 * v0 + w0 * w0);
+  if (mode == 3) { out[i] = sp; return; }                              // VIS_SPEED
+  if (mode == 4) {                                                     // VIS_MACH
+    const float a = sqrtf(fmaxf(P.gamma_floor * p0 / r0, DENOM_EPS));  // soundspeed :264
+    out[i] = sp / fmaxf(a, DENOM_EPS);
+    return;
+  }
+  const int xm = c - 1, xp = c + 1, ym = c - V3_SX, yp = c + V3_SX, zm = c - V3_SXY, zp = c + V3_SXY;
+  const float inv2dx = 0.5f / P.dx, inv2dy = 0.5f / P.dy, inv2dz = 0.5f / P.dz;
+  const float dudx = (s_u[xp] - s_u[xm]) * inv2dx, dudy = (s_u[yp] - s_u[ym]) * inv2dy, dudz = (s_u[zp] - s_u[zm]) * inv2dz;
+  const float dvdx = (s_v[xp] - s_v[xm]) * inv2dx, dvdy = (s_v[yp] - s_v[ym]) * inv2dy, dvdz = (s_v[zp] - s_v[zm]) * inv2dz;
+  const float dwdx = (s_w[xp] - s_w[xm]) * inv2dx, dwdy = (s_w[yp] - s_w[ym]) * inv2dy, dwdz = (s_w[zp] - s_w[zm]) * inv2dz;
+  if (mode == 6) { out[i] = dudx + dvdy + dwdz; return; }              // VIS_DIV
+  const float wx = dwdy - dvdz, wy = dudz - dwdx, wz = dvdx - dudy;
+  if (mode == 5) { out[i] = sqrtf(wx * wx + wy * wy + wz * wz); return; }   // VIS_VORT_MAG
+  if (mode == 7) {                                                     // VIS_Q_CRITERION :879-899
+    const float O12 = 0.5f * (dudy - dvdx), O13 = 0.5f * (dudz - dwdx), O23 = 0.5f * (dvdz - dwdy);
+    const float Om2 = 2.0f * (O12 * O12 + O13 * O13 + O23 * O23);
+    const float S12 = 0.5f * (dudy + dvdx), S13 = 0.5f * (dudz + dwdx), S23 = 0.5f * (dvdz + dwdy);
+    const float Sm2 = (dudx * dudx + dvdy * dvdy + dwdz * dwdz) + 2.0f * (S12 * S12 + S13 * S13 + S23 * S23);
+    out[i] = 0.5f * (Om2 - Sm2);
+    return;
+  }
+  const float drdx = (s_r[xp] - s_r[xm]) * inv2dx, drdy = (s_r[yp] - s_r[ym]) * inv2dy, drdz = (s_r[zp] - s_r[zm]) * inv2dz;
+  out[i] = sqrtf(drdx * drdx + drdy * drdy + drdz * drdz);             // VIS_SCHLIEREN_RHO (mode 0)
+}
+
 constexpr size_t T3_SMEM = (size_t)(6 * T3_SVOL + 6 * T3_NF) * sizeof(float) + ((T3_SVOL + 15) / 16) * 16;
 
 }  // namespace
@@ -552,6 +623,7 @@ struct tau_hyp3d {
   size_t plane;
   cudaEvent_t ev0, ev1;
   bool timed, have_state;
+  float *vis;        // diagnostic field (device), allocated on first use
 };
 
 namespace {
@@ -607,6 +679,7 @@ int tau_hyp3d_create(const tau_hyp3d_params *p, int device, int z_begin, int nz_
   h->z_begin = z_begin;
   h->nz_local = nz_local;
   h->slab = (nz_local != p->nz);
+  h->vis = nullptr;
   h->cur = 0;
   h->steps = h->launches = 0;
   h->timed = h->have_state = false;
@@ -751,6 +824,26 @@ int tau_hyp3d_download(tau_hyp3d *h, float *const planes[6], uint8_t *solid) {
   return TAU_OK;
 }
 
+// k_vis :800-905: the scalar field the reference's volume renderer consumes (nz_local*ny*nx floats,
+// index (z*ny+y)*nx+x; solid cells 0).  mode = VisMode :784-794.  Slab handles read their ghost planes
+// for the z-neighbours: exchange them first.
+int tau_hyp3d_vis(tau_hyp3d *h, int mode, float *out) {
+  TAU_REQUIRE(h && out, "tau_hyp3d_vis: null argument");
+  TAU_REQUIRE(mode >= 0 && mode <= 7, "tau_hyp3d_vis: mode %d not in [0, 7]", mode);
+  TAU_REQUIRE(h->have_state, "tau_hyp3d_vis: no state (call tau_hyp3d_init or tau_hyp3d_upload)");
+  TAU_CUDA(cudaSetDevice(h->device));
+  const size_t n = (size_t)h->prm.nx * h->prm.ny * h->nz_local;
+  if (!h->vis) TAU_CUDA(cudaMalloc(&h->vis, n * sizeof(float)));
+  const Par P = make_par(h);
+  dim3 grid((P.nx + T3_TX - 1) / T3_TX, (P.ny + T3_TY - 1) / T3_TY, (h->nz_local + T3_TZ - 1) / T3_TZ);
+  hyp3d_vis<<<grid, dim3(T3_TX, T3_TY, T3_TZ), 0, h->stream>>>(P, h->st[h->cur], h->solid, h->vis, mode);
+  h->launches++;
+  TAU_CUDA(cudaGetLastError());
+  TAU_CUDA(cudaMemcpyAsync(out, h->vis, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  return TAU_OK;
+}
+
 int tau_hyp3d_sync(tau_hyp3d *h) {
   TAU_REQUIRE(h, "tau_hyp3d_sync: null handle");
   TAU_CUDA(cudaStreamSynchronize(h->stream));
@@ -779,6 +872,7 @@ int tau_hyp3d_destroy(tau_hyp3d *h) {
   if (!h) return TAU_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  if (h->vis) cudaFree(h->vis);
   cudaFree(h->clk);
   cudaFree(h->solid);
   cudaFree(h->st[1]);

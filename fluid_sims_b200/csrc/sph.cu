@@ -526,6 +526,25 @@ __global__ void sph_rain_write(float2 *pos, float2 *vel, int *__restrict__ winne
     winner[i] = -1;  // re-arm
   }
 }
+// ---- render pass: k_clear_grid + k_rasterize (:357-374) -----------------------------------------
+// Particle counts on the terminal's half-block raster (W x 2H).  2 M particles fall on a few 10^4
+// cells, so the reference's one-atomic-per-particle contends ~100-fold per address; here the lanes
+// of a warp that hit the same cell are merged first (__match_any_sync) and one of them adds the
+// group's population.  Integer result, identical to the reference's.
+__global__ void sph_rasterize(const float2 *__restrict__ pos, int N, int *__restrict__ grid2, int W, int H,
+                              float boxX, float boxY) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int cell = -1;
+  if (i < N) {
+    const float2 p = pos[i];
+    const int cx = (int)(p.x / boxX * (W - 1));
+    const int sy = (int)((boxY - p.y) / boxY * (2 * H - 1));  // flip y
+    if ((unsigned)cx < (unsigned)W && (unsigned)sy < (unsigned)(2 * H)) cell = sy * W + cx;
+  }
+  const unsigned peers = __match_any_sync(0xffffffffu, cell);
+  if (cell >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&grid2[cell], __popc(peers));
+}
+
 __global__ void sph_fill_int(int *a, int n, int v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = v;
@@ -550,6 +569,8 @@ struct tau_sph {
   int rank, world, chunk, sub_k;
   float dTau_accum, dt_sub;
   int *range;
+  int *grid2;          // render raster (device), allocated on first use
+  size_t grid2_cap;
   // derived constants (:573-578, ensure_cell_buffers :512-540)
   float mass, h, cell, alpha;
   int Gx, Gy, M, key_bits, nwarps;
@@ -939,6 +960,27 @@ int tau_sph_download(tau_sph *h, float *pos_xy, float *vel_xy, float *s, float *
   return TAU_OK;
 }
 
+// Render pass of the frame loop :747-755 (k_clear_grid, k_rasterize, D2H): particle counts on a
+// W x 2H raster (two vertical samples per terminal row, `halfblocks`), row-major, y flipped.
+int tau_sph_rasterize(tau_sph *h, int W, int H, int *grid2) {
+  TAU_REQUIRE(h && grid2, "tau_sph_rasterize: null argument");
+  TAU_REQUIRE(W >= 1 && H >= 1 && (size_t)W * 2 * H <= (size_t)1 << 28, "tau_sph_rasterize: bad raster %d x %d", W, H);
+  TAU_CUDA(cudaSetDevice(h->device));
+  const size_t cells = (size_t)W * 2 * H;
+  if (h->grid2_cap < cells) {
+    if (h->grid2) TAU_CUDA(cudaFree(h->grid2));
+    TAU_CUDA(cudaMalloc(&h->grid2, cells * sizeof(int)));
+    h->grid2_cap = cells;
+  }
+  TAU_CUDA(cudaMemsetAsync(h->grid2, 0, cells * sizeof(int), h->stream));
+  sph_rasterize<<<(h->p.N + 255) / 256, 256, 0, h->stream>>>(h->pos, h->p.N, h->grid2, W, H, h->p.boxX, h->p.boxY);
+  h->launches++;
+  TAU_CUDA(cudaGetLastError());
+  TAU_CUDA(cudaMemcpyAsync(grid2, h->grid2, cells * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  return TAU_OK;
+}
+
 // the (cell key, particle index) pairs of the most recent sub-step's radix sort, sorted order
 int tau_sph_download_sort(tau_sph *h, unsigned *keys, unsigned *vals) {
   TAU_REQUIRE(h && keys && vals, "tau_sph_download_sort: null argument");
@@ -998,7 +1040,7 @@ int tau_sph_destroy(tau_sph *h) {
   if (!h) return TAU_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  void *ptrs[] = {h->range, h->winner, h->cellStart, h->svel_new, h->sxy_new, h->srp, h->svel, h->sxy,
+  void *ptrs[] = {h->grid2, h->range, h->winner, h->cellStart, h->svel_new, h->sxy_new, h->srp, h->svel, h->sxy,
                   h->scan_totals, h->hist, h->vals[1], h->keys[1], h->vals[0], h->keys[0], h->press, h->s, h->acc,
                   h->vel, h->pos};
   for (void *p : ptrs) cudaFree(p);

@@ -34,6 +34,8 @@ _step_end = declare("tau_hyp3d_step_end", [_h])
 _clock = declare("tau_hyp3d_clock", [_h] + [C.POINTER(C.c_float)] * 4)
 _download = declare("tau_hyp3d_download", [_h, C.POINTER(C.c_void_p), C.c_void_p])
 _sync = declare("tau_hyp3d_sync", [_h])
+_vis = declare("tau_hyp3d_vis", [_h, C.c_int, np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")])
+VIS_MODES = ("schlieren_rho", "log_rho", "log_p", "speed", "mach", "vort_mag", "div", "q_criterion")
 _devstate = declare("tau_hyp3d_device_state", [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)])
 _steps_done = declare("tau_hyp3d_steps_done", [_h], C.c_longlong)
 _launches = declare("tau_hyp3d_launch_count", [_h], C.c_longlong)
@@ -138,6 +140,12 @@ class Hypersonic3D:
         ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in arrs])
         check(_download(self._handle, ptrs, C.c_void_p(solid.ctypes.data)))
         return arrs, solid
+
+    def vis(self, mode: int):
+        """k_vis (tau_hypersonic_3d_cuda.cu:800-905): the diagnostic scalar field, shape (nz_local, ny, nx)."""
+        out = np.empty(self.shape, np.float32)
+        check(_vis(self._handle, mode, out))
+        return out
 
     def sync(self):
         check(_sync(self._handle))

@@ -36,6 +36,7 @@ _shard_end = declare("tau_sph_shard_substep_end", [_h])
 _clock = declare("tau_sph_clock", [_h, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_longlong)])
 _download = declare("tau_sph_download", [_h, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p])
 _dl_sort = declare("tau_sph_download_sort", [_h, _u32, _u32])
+_rasterize = declare("tau_sph_rasterize", [_h, C.c_int, C.c_int, np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")])
 _sort_pairs = declare("tau_sph_sort_pairs", [_h, _u32, _u32, _u32])
 _grid = declare("tau_sph_grid", [_h, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float),
                                  C.POINTER(C.c_float), C.POINTER(C.c_float)])
@@ -137,6 +138,12 @@ class SPH:
         s, pr = np.empty(n, np.float32), np.empty(n, np.float32)
         check(_download(self._handle, pos.ctypes.data, vel.ctypes.data, s.ctypes.data, pr.ctypes.data))
         return pos, vel, s, pr
+
+    def rasterize(self, W: int, H: int):
+        """Particle counts on the W x 2H half-block raster (k_rasterize, tau_sph.cu:363-374)."""
+        g = np.empty((2 * H, W), np.int32)
+        check(_rasterize(self._handle, W, H, g))
+        return g
 
     def download_sort(self):
         n = self.params.N

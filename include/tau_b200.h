@@ -220,6 +220,10 @@ int tau_hyp3d_step_end(tau_hyp3d *h);
 int tau_hyp3d_clock(tau_hyp3d *h, float *t, float *d_tau, float *dt_last, float *maxs_last);
 int tau_hyp3d_download(tau_hyp3d *h, float *const planes[6], uint8_t *solid);
 int tau_hyp3d_sync(tau_hyp3d *h);
+/* k_vis :800-905 — the scalar field the volume renderer consumes: nz_local*ny*nx floats, solid
+ * cells 0.  mode = VisMode :784-794 (0 |grad rho|, 1 log(1+rho), 2 log(1+p), 3 |u|, 4 Mach,
+ * 5 |curl u|, 6 div u, 7 Q criterion).  Slab handles: exchange the ghost planes first. */
+int tau_hyp3d_vis(tau_hyp3d *h, int mode, float *out);
 /* device pointers: current state (6 contiguous planes of (nz_local+6)*ny*nx floats, starting at
  * ghost plane -3) and the max-wavespeed accumulator of the running step */
 int tau_hyp3d_device_state(tau_hyp3d *h, float **planes, float **maxs);
@@ -271,6 +275,9 @@ int tau_sph_shard_substep_end(tau_sph *h);
 int tau_sph_clock(tau_sph *h, float *t, float *tau, long long *step);
 /* state in ORIGINAL particle order (any pointer may be NULL) */
 int tau_sph_download(tau_sph *h, float *pos_xy, float *vel_xy, float *s, float *press);
+/* render pass of the frame loop :747-755 (k_clear_grid + k_rasterize :357-374 + D2H): particle
+ * counts on the terminal's half-block raster, grid2[sy * W + cx], sy in [0, 2H), y flipped */
+int tau_sph_rasterize(tau_sph *h, int W, int H, int *grid2);
 /* (cell key, particle index) pairs of the last sub-step's radix sort, in sorted order */
 int tau_sph_download_sort(tau_sph *h, unsigned *keys, unsigned *vals);
 /* the sort on its own: N keys (< number of cells rounded up to a power of two) -> sorted keys and

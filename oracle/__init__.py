@@ -454,3 +454,53 @@ def ref_sph_run(p: SphParams, pos, vel, nframes, clock=None):
     if rc != 0:
         raise RuntimeError(f"reference SPH run failed with cudaError {rc}")
     return pos.reshape(-1, 2), vel.reshape(-1, 2), acc.reshape(-1, 2), s, pr, ck, float(ms.value)
+
+
+def sph_rasterize(pos, W, H, boxX=1.0, boxY=1.0):
+    """CPU oracle of k_rasterize (tau_sph.cu:363-374): (2H, W) int32 counts."""
+    i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+    lib.oracle_sph_rasterize.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, i32p]
+    lib.oracle_sph_rasterize.restype = None
+    pos = np.ascontiguousarray(pos, np.float32)
+    g = np.zeros((2 * H, W), np.int32)
+    lib.oracle_sph_rasterize(pos.ravel(), pos.shape[0], W, H, boxX, boxY, g)
+    return g
+
+
+def ref_sph_rasterize(pos, W, H, boxX=1.0, boxY=1.0):
+    """The reference's own k_clear_grid + k_rasterize on the GPU."""
+    i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+    r = ref("ref_sph")
+    r.ref_sph_rasterize.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, i32p]
+    r.ref_sph_rasterize.restype = C.c_int
+    pos = np.ascontiguousarray(pos, np.float32)
+    g = np.zeros((2 * H, W), np.int32)
+    rc = r.ref_sph_rasterize(pos.ravel(), pos.shape[0], W, H, boxX, boxY, g)
+    if rc != 0:
+        raise RuntimeError(f"reference sph rasterize failed with cudaError {rc}")
+    return g
+
+
+def hyp3d_vis(p: Hyp3dParams, planes, solid, mode):
+    """CPU oracle of k_vis (tau_hypersonic_3d_cuda.cu:800-905): (nz, ny, nx) float32."""
+    lib.oracle_hyp3d_vis.argtypes = [C.POINTER(Hyp3dParams), _pp6, u8p, C.c_int, f32p]
+    lib.oracle_hyp3d_vis.restype = None
+    planes = [np.ascontiguousarray(a, np.float32).ravel() for a in planes]
+    ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in planes])
+    out = np.zeros(p.nx * p.ny * p.nz, np.float32)
+    lib.oracle_hyp3d_vis(C.byref(p), ptrs, np.ascontiguousarray(solid, np.uint8).ravel(), mode, out)
+    return out.reshape(p.nz, p.ny, p.nx)
+
+
+def ref_hyp3d_vis(p: Hyp3dParams, planes, mode):
+    """The reference's own k_vis on the GPU."""
+    r = ref("ref_hyp3d")
+    r.ref_hyp3d_vis.argtypes = [f32p, C.c_int, C.c_int, C.c_int, _pp6, C.c_int, f32p]
+    r.ref_hyp3d_vis.restype = C.c_int
+    planes = [np.ascontiguousarray(a, np.float32).ravel() for a in planes]
+    ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in planes])
+    out = np.zeros(p.nx * p.ny * p.nz, np.float32)
+    rc = r.ref_hyp3d_vis(p.as23(), p.nx, p.ny, p.nz, ptrs, mode, out)
+    if rc != 0:
+        raise RuntimeError(f"reference hyp3d vis failed with cudaError {rc}")
+    return out.reshape(p.nz, p.ny, p.nx)

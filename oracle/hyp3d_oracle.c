@@ -462,3 +462,43 @@ void oracle_hyp3d_run(const oracle_hyp3d_params *p, float *const planes[6], cons
   clock[1] = d_tau;
   free(buf);
 }
+
+/* k_vis :800-905 (VisMode :784-794) through prim_at_xbc :724-749 (== tile_prim above) */
+void oracle_hyp3d_vis(const oracle_hyp3d_params *p, const float *const in[6], const uint8_t *solid, int mode,
+                      float *out) {
+  P = p;
+  State s = {in[0], in[1], in[2], in[3], in[4], in[5]};
+  for (int z = 0; z < p->nz; ++z)
+    for (int y = 0; y < p->ny; ++y)
+      for (int x = 0; x < p->nx; ++x) {
+        const int i = idx3(x, y, z);
+        if (solid[i]) { out[i] = 0.f; continue; }
+        int sol;
+        Prim q0 = tile_prim(&s, solid, x, y, z, &sol);
+        if (mode == 1) { out[i] = logf(1.0f + fmaxf(q0.r, 0.0f)); continue; }
+        if (mode == 2) { out[i] = logf(1.0f + fmaxf(q0.p, 0.0f)); continue; }
+        float sp = sqrtf(q0.u * q0.u + q0.v * q0.v + q0.w * q0.w);
+        if (mode == 3) { out[i] = sp; continue; }
+        if (mode == 4) { out[i] = sp / fmaxf(soundspeed(&q0), DENOM_EPS); continue; }
+        Prim qxm = tile_prim(&s, solid, x - 1, y, z, &sol), qxp = tile_prim(&s, solid, x + 1, y, z, &sol);
+        Prim qym = tile_prim(&s, solid, x, y - 1, z, &sol), qyp = tile_prim(&s, solid, x, y + 1, z, &sol);
+        Prim qzm = tile_prim(&s, solid, x, y, z - 1, &sol), qzp = tile_prim(&s, solid, x, y, z + 1, &sol);
+        float inv2dx = 0.5f / p->dx, inv2dy = 0.5f / p->dy, inv2dz = 0.5f / p->dz;
+        float dudx = (qxp.u - qxm.u) * inv2dx, dudy = (qyp.u - qym.u) * inv2dy, dudz = (qzp.u - qzm.u) * inv2dz;
+        float dvdx = (qxp.v - qxm.v) * inv2dx, dvdy = (qyp.v - qym.v) * inv2dy, dvdz = (qzp.v - qzm.v) * inv2dz;
+        float dwdx = (qxp.w - qxm.w) * inv2dx, dwdy = (qyp.w - qym.w) * inv2dy, dwdz = (qzp.w - qzm.w) * inv2dz;
+        if (mode == 6) { out[i] = dudx + dvdy + dwdz; continue; }
+        float wx = dwdy - dvdz, wy = dudz - dwdx, wz = dvdx - dudy;
+        if (mode == 5) { out[i] = sqrtf(wx * wx + wy * wy + wz * wz); continue; }
+        if (mode == 7) {
+          float O12 = 0.5f * (dudy - dvdx), O13 = 0.5f * (dudz - dwdx), O23 = 0.5f * (dvdz - dwdy);
+          float Om2 = 2.0f * (O12 * O12 + O13 * O13 + O23 * O23);
+          float S12 = 0.5f * (dudy + dvdx), S13 = 0.5f * (dudz + dwdx), S23 = 0.5f * (dvdz + dwdy);
+          float Sm2 = (dudx * dudx + dvdy * dvdy + dwdz * dwdz) + 2.0f * (S12 * S12 + S13 * S13 + S23 * S23);
+          out[i] = 0.5f * (Om2 - Sm2);
+          continue;
+        }
+        float drdx = (qxp.r - qxm.r) * inv2dx, drdy = (qyp.r - qym.r) * inv2dy, drdz = (qzp.r - qzm.r) * inv2dz;
+        out[i] = sqrtf(drdx * drdx + drdy * drdy + drdz * drdz);
+      }
+}

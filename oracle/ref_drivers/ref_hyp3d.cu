@@ -77,3 +77,29 @@ extern "C" int ref_hyp3d_run(const float *pf, int nx, int ny, int nz, int steps,
   cudaFree(d_maxs); cudaFree(d_solid);
   return (int)e;
 }
+
+// k_vis :800-905 on caller-provided planes, with main()'s launch shape (:1715)
+extern "C" int ref_hyp3d_vis(const float *pf, int nx, int ny, int nz, const float *const *planes, int mode,
+                             float *out) {
+  Params hp = params_from(pf, nx, ny, nz);
+  cudaError_t e;
+  if ((e = cudaMemcpyToSymbol(P, &hp, sizeof(Params)))) return e;
+  size_t N = (size_t)nx * ny * nz, bytes = N * sizeof(float);
+  float *d[6], *d_out;
+  uint8_t *d_solid;
+  for (int f = 0; f < 6; ++f) {
+    ck(cudaMalloc(&d[f], bytes), "malloc");
+    ck(cudaMemcpy(d[f], planes[f], bytes, cudaMemcpyHostToDevice), "h2d");
+  }
+  ck(cudaMalloc(&d_out, bytes), "malloc out");
+  ck(cudaMalloc(&d_solid, N), "malloc solid");
+  dim3 block(8, 8, 4);
+  dim3 grid((nx + block.x - 1) / block.x, (ny + block.y - 1) / block.y, (nz + block.z - 1) / block.z);
+  k_build_solid_mask<<<grid, block>>>(d_solid);
+  k_vis<<<grid, block>>>(d[0], d[1], d[2], d[3], d[4], d[5], d_solid, d_out, mode);
+  e = cudaDeviceSynchronize();
+  ck(cudaMemcpy(out, d_out, bytes, cudaMemcpyDeviceToHost), "d2h");
+  for (int f = 0; f < 6; ++f) cudaFree(d[f]);
+  cudaFree(d_out); cudaFree(d_solid);
+  return (int)e;
+}

@@ -97,3 +97,20 @@ extern "C" int ref_sph_run(const float *pf, float *pos, float *vel, float *acc, 
   cudaFree(d.cellHead); cudaFree(d.next);
   return (int)e;
 }
+
+// render pass :747-755: k_clear_grid + k_rasterize on caller-provided positions
+extern "C" int ref_sph_rasterize(const float *pos, int N, int W, int H, float boxX, float boxY, int *grid2) {
+  float2 *dpos; int *dgrid;
+  const size_t cells = (size_t)W * 2 * H;
+  CUDA_CHECK(cudaMalloc(&dpos, (size_t)N * sizeof(float2)));
+  CUDA_CHECK(cudaMalloc(&dgrid, cells * sizeof(int)));
+  CUDA_CHECK(cudaMemcpy(dpos, pos, (size_t)N * sizeof(float2), cudaMemcpyHostToDevice));
+  int BSg = 256, GSg = ((int)cells + BSg - 1) / BSg;
+  k_clear_grid<<<GSg, BSg>>>(dgrid, (int)cells);
+  int BSp = 256, GSp = (N + BSp - 1) / BSp;
+  k_rasterize<<<GSp, BSp>>>(dpos, N, dgrid, W, H, boxX, boxY);
+  cudaError_t e = cudaDeviceSynchronize();
+  CUDA_CHECK(cudaMemcpy(grid2, dgrid, cells * sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(dpos); cudaFree(dgrid);
+  return (int)e;
+}

@@ -255,3 +255,16 @@ void oracle_sph_run(const oracle_sph_params *P, float *pos, float *vel, float *a
     clk->step++;
   }
 }
+
+/* k_clear_grid + k_rasterize :357-374 (plain C division; the reference is built with
+ * -use_fast_math, so a particle whose scaled coordinate is within an ulp of an integer may land in
+ * the neighbouring raster cell there) */
+void oracle_sph_rasterize(const float *pos, int N, int W, int H, float boxX, float boxY, int *grid2) {
+  for (int i = 0; i < W * 2 * H; ++i) grid2[i] = 0;
+  for (int i = 0; i < N; ++i) {
+    float px = pos[2 * i], py = pos[2 * i + 1];
+    int cx = (int)(px / boxX * (W - 1));
+    int sy = (int)((boxY - py) / boxY * (2 * H - 1));
+    if ((unsigned)cx < (unsigned)W && (unsigned)sy < (unsigned)(2 * H)) grid2[sy * W + cx] += 1;
+  }
+}

@@ -150,3 +150,26 @@ def test_errors_are_loud():
     s = Hypersonic3D(Params.default(16, 16, 16))
     with pytest.raises(TauError, match="no state"):
         s.step(1)
+
+
+@pytest.mark.skipif(not oracle.has_ref("ref_hyp3d"), reason="oracle/_ref not built")
+@pytest.mark.parametrize("mode", range(8))
+def test_vis_field_vs_reference_kernel_and_oracle(mode):
+    """k_vis (:800-905), the renderer's input: same decode intrinsics and the same stencil as the
+    reference kernel, so the fields agree to fp32 round-off relative to the field's range (the sound
+    speed uses a correctly-rounded reciprocal instead of the IEEE divide); the CPU oracle (libm instead
+    of the fast intrinsics) a little less tightly."""
+    n = 48
+    prm = oracle.hyp3d_params(n, n, n)
+    p0, solid, _, _, _, _ = oracle.ref_hyp3d_run(prm, 0)
+    p1, _, _, _, _, _ = oracle.ref_hyp3d_run(prm, 120, planes=p0, clock=(5e-3, 2e-3))
+    s = Hypersonic3D(Params.default(n, n, n)).upload(p1, (0.012, 2e-3))
+    got = s.vis(mode)
+    s.close()
+    ref = oracle.ref_hyp3d_vis(prm, p1, mode)
+    sol = solid.reshape(n, n, n) != 0
+    assert np.all(got[sol] == 0.0)
+    scale = max(float(np.abs(ref).max()), 1e-30)
+    assert float(np.abs(got - ref).max()) <= 2e-6 * scale, float(np.abs(got - ref).max()) / scale
+    cpu = oracle.hyp3d_vis(prm, p1, solid, mode)
+    assert float(np.abs(got - cpu).max()) <= 2e-4 * scale

@@ -307,3 +307,46 @@ def test_hyp2d_render_oracle_invariants():
     # mode 2 is |velocity|: body at rest, inflow at Mach 25 * sqrt(gamma)
     _, vals, (mn, mx) = oracle.hyp2d_render(cfg, planes, mask, 2)
     assert mx >= 25.0 * np.sqrt(1.1) * 0.999
+
+
+def test_sph_rasterize_oracle():
+    """k_rasterize restatement (tau_sph.cu:363-374): every in-box particle lands in exactly one raster
+    cell; y is flipped; corners map to corners."""
+    pos = np.array([[0.0, 0.0], [1.0, 1.0], [0.5, 0.25], [0.999, 0.0]], np.float32)
+    g = oracle.sph_rasterize(pos, 10, 4)
+    assert g.shape == (8, 10) and g.sum() == 4
+    assert g[7, 0] == 1          # (0,0): bottom-left -> last raster row
+    assert g[0, 9] == 1          # (1,1): top-right -> first raster row, last column
+    assert g[int((1 - 0.25) * 7), int(0.5 * 9)] == 1
+    rng = np.random.default_rng(3)
+    pos = rng.random((5000, 2)).astype(np.float32)
+    g = oracle.sph_rasterize(pos, 33, 17)
+    assert g.sum() == 5000 and g.min() >= 0
+
+
+def test_hyp3d_vis_oracle_invariants():
+    """k_vis restatement (tau_hypersonic_3d_cuda.cu:800-905): solid cells are 0; in the quiescent
+    initial state every velocity-derived field vanishes away from the inflow plane, and log(1+rho) is
+    the constant log(1.02)."""
+    prm = oracle.hyp3d_params(20, 16, 12)
+    planes, solid = oracle.hyp3d_init(prm)
+    sol = solid.reshape(12, 16, 20) != 0
+    assert sol.any() and not sol.all()
+    for mode in range(8):
+        v = oracle.hyp3d_vis(prm, planes, solid, mode)
+        assert v.shape == (12, 16, 20) and np.isfinite(v).all()
+        assert np.all(v[sol] == 0.0)
+    fluid = ~sol
+    assert np.allclose(oracle.hyp3d_vis(prm, planes, solid, 1)[fluid], np.log1p(np.float32(0.02)), rtol=1e-6)
+    assert np.all(oracle.hyp3d_vis(prm, planes, solid, 3) == 0.0)           # |u| = 0: gas at rest
+    div = oracle.hyp3d_vis(prm, planes, solid, 6)
+    assert np.all(div[:, :, 2:-1][fluid[:, :, 2:-1] & ~_near(sol)[:, :, 2:-1]] == 0.0)
+    assert np.all(div[:, :, 0][fluid[:, :, 0]] < 0.0)                        # x = 0 sees the inflow state on its left
+
+
+def _near(sol):
+    """cells with a solid face neighbour (their gradients see the wall state)"""
+    out = np.zeros_like(sol)
+    for ax in range(3):
+        out |= np.roll(sol, 1, ax) | np.roll(sol, -1, ax)
+    return out

@@ -109,3 +109,21 @@ def test_errors_are_loud():
     s = SPH(Params(N=1024))
     with pytest.raises(TauError, match="no state"):
         s.step(1)
+
+
+@pytest.mark.skipif(not oracle.has_ref("ref_sph"), reason="oracle/_ref not built")
+@pytest.mark.parametrize("N,W,H", [(65536, 120, 40), (1 << 21, 237, 63), (1000, 7, 3)])
+def test_rasterize_equals_reference_kernel(N, W, H):
+    """Render pass (k_clear_grid + k_rasterize, tau_sph.cu:357-374): integer counts, bit-exact against
+    the reference kernel; the plain-C oracle (no fast-math division) may move a particle that sits
+    within an ulp of a raster line."""
+    P = Params(N=N, rain=0)
+    pos0, vel0 = reset_particles(P)
+    s = SPH(P).upload(pos0, vel0)
+    s.step(3)
+    pos, _, _, _ = s.download()
+    g = s.rasterize(W, H)
+    assert g.shape == (2 * H, W) and int(g.sum()) == N and g.min() >= 0
+    assert np.array_equal(g, oracle.ref_sph_rasterize(pos, W, H))
+    assert np.abs(g - oracle.sph_rasterize(pos, W, H)).sum() <= max(2, N // 5000)
+    s.close()

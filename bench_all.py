@@ -5,12 +5,13 @@
   config 4  tau_hypersonic_3d_cuda n^3 (default 256, --n3 512; z-slabs under torchrun)
                                                         -> Mcell-updates/s, roofline at 49 B/cell
   config 5  tau_sph 2M particles                       -> Mparticle-updates/s (per sub-step)
+  (next)    tau_burgers 4096x4096 (only when named: `bench_all.py burgers`)
 
 Each line also carries `reference_gpu`: the reference's own kernels (oracle/_ref, recompiled for
 sm_100a) timed on the same GPU on the same problem — test infrastructure used as a yardstick, never
 as the product path.  One JSON object per line on stdout.
 
-  python bench_all.py [gs] [hyp3d] [sph] [--steps K]
+  python bench_all.py [gs] [hyp3d] [sph] [burgers] [--steps K]
   torchrun --nproc-per-node 8 bench_all.py hyp3d --n3 512        # config 4 proper
 """
 from __future__ import annotations
@@ -209,6 +210,38 @@ def bench_sph(a):
                           "gpu_launches": s.launch_count}))
 
 
+def bench_burgers(a):
+    """tau_burgers n x n (periodic), reference defaults (first-order Rusanov, K = 1)."""
+    import oracle
+    from fluid_sims_b200.burgers import Burgers, Params, initialize_host
+    n = a.burgers_n
+    P = Params(nx=n, ny=n, dtau=1e-3, rc=40.0 * n / 512, bsig=16.0 * n / 512)
+    u0, v0 = initialize_host(P)
+    s = Burgers(P).upload(u0, v0)
+    s.step(20)
+    s.sync()
+    s.step(a.steps)
+    ms = s.last_step_ms() / a.steps
+    cells = n * n
+    bytes_per_cell = 16 * (1 + max(P.visc_substeps, 1))   # each kernel reads phi_u, phi_v and writes them
+    ach = bytes_per_cell * cells / (ms * 1e-3) / 1e9
+    ref_ms = None
+    if oracle.has_ref("ref_burgers") and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        k = min(a.steps, 100)
+        *_, t = oracle.ref_burgers_run(oracle.burgers_params(nx=n, ny=n, dtau=1e-3, rc=P.rc, bsig=P.bsig), u0, v0, k)
+        ref_ms = t / k
+    print(json.dumps({"bench": "burgers", "grid": [n, n], "steps": a.steps, "ms_per_step": ms,
+                      "value": cells / (ms * 1e-3) / 1e6, "unit": "Mcell-updates/s",
+                      "roofline": {"bound": "hbm", "achieved": ach, "peak": peak(), "unit": "GB/s",
+                                   "frac": ach / peak(), "algorithmic_bytes_per_cell": bytes_per_cell,
+                                   "note": "2 kernels per step (convection, viscosity), 16 B/cell each"},
+                      "reference_gpu": {"ms_per_step": ref_ms,
+                                        "value": cells / (ref_ms * 1e-3) / 1e6 if ref_ms else None,
+                                        "what": "tau_burgers.cu kernels recompiled for sm_100a incl. the per-step "
+                                                "D2H of the block maxima"},
+                      "gpu_launches": s.launch_count}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("which", nargs="*", default=[])
@@ -219,10 +252,11 @@ def main():
     ap.add_argument("--warm3", type=int, default=60)
     ap.add_argument("--sph-n", type=int, default=1 << 21)
     ap.add_argument("--steps-sph", type=int, default=50)
+    ap.add_argument("--burgers-n", type=int, default=4096)
     a = ap.parse_args()
     which = a.which or ["gs", "hyp3d", "sph"]
     for w in which:
-        {"gs": bench_gs, "hyp3d": bench_hyp3d, "sph": bench_sph}[w](a)
+        {"gs": bench_gs, "hyp3d": bench_hyp3d, "sph": bench_sph, "burgers": bench_burgers}[w](a)
     # one process group for the whole run (re-initialising NCCL between benches is not reliable)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         import torch.distributed as dist

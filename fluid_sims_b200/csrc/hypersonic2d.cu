@@ -1225,7 +1225,7 @@ struct tau_hyp2d {
   bool speed_valid;  // ctrl->maxspeed[steps%3] holds the max wavespeed of the current state
   int seg_rows;          // tallest segment of the table (the only height when set by the caller)
   bool seg_auto;         // tapered schedule chosen by build_items (not set by the caller)
-  int taper_k, min_rows; // schedule tuning (TAU_HYP2D_TAPER_K / TAU_HYP2D_MIN_ROWS)
+  int taper_k, min_rows, max_rows; // schedule tuning (TAU_HYP2D_TAPER_K / _MIN_ROWS / _MAX_ROWS)
   cudaEvent_t ev0, ev1;
   bool timed;
   size_t plane_elems;
@@ -1340,7 +1340,7 @@ int build_items(tau_hyp2d *h, size_t smem) {
     if (h->seg_auto) {
       const long long remaining = (long long)(h->h_local - y) * nstrips;
       hgt = (int)(remaining / ((long long)h->taper_k * resident_warps));
-      if (hgt > 24) hgt = 24;
+      if (hgt > h->max_rows) hgt = h->max_rows;
       if (hgt < h->min_rows) hgt = h->min_rows;
     } else {
       hgt = h->seg_rows;
@@ -1542,6 +1542,11 @@ int tau_hyp2d_create(const tau_hyp2d_config *cfg, int W, int H, int dtype, int d
   h->seg_auto = true;
   h->taper_k = 2;
   h->min_rows = 4;
+  h->max_rows = 24;
+  if (const char *e = getenv("TAU_HYP2D_MAX_ROWS")) {
+    int v = atoi(e);
+    if (v >= 4) h->max_rows = v;
+  }
   if (const char *e = getenv("TAU_HYP2D_SEG_ROWS")) {
     int v = atoi(e);
     if (v >= 4) {

@@ -290,6 +290,46 @@ long long tau_sph_launch_count(tau_sph *h);
 int tau_sph_last_step_ms(tau_sph *h, float *ms);
 int tau_sph_destroy(tau_sph *h);
 
+/* ------------------------------------------------------------------------------------------ */
+/* 2-D viscous Burgers (reference: tau_burgers.cu) — SURVEY.md 8(f) rank 3                      */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct tau_burgers tau_burgers;
+
+/* simulation fields of `struct Params` tau_burgers.cu:53-90 (same defaults) */
+typedef struct tau_burgers_params {
+  int nx, ny;
+  float dx, dy;
+  float nu, u0;
+  float amp, bsig, swirl, rc, offx, offy, asym;
+  float CFL, tau0, t0, dtau;
+  int muscl, visc_substeps;
+  int colehopf, ck;
+  float ca;
+} tau_burgers_params;
+
+void tau_burgers_default_params(tau_burgers_params *p);
+/* initialize_host :250-304 (host): phi_u, phi_v of ny*nx floats, index j*nx+i; ny = 1 with colehopf */
+void tau_burgers_init_host(const tau_burgers_params *p, float *phi_u, float *phi_v);
+/* replaces device_alloc :315-322 (the four flux planes and the block-max buffer are not needed) */
+int tau_burgers_create(const tau_burgers_params *p, int device, void *stream, tau_burgers **out);
+/* initialize_host + H2D :652-661; clock := (t0, tau0) */
+int tau_burgers_init(tau_burgers *h);
+/* inject caller state; clock2 = {t, tau} or NULL for (t0, tau0) */
+int tau_burgers_upload(tau_burgers *h, const float *phi_u, const float *phi_v, const float *clock2);
+/* THE hot path: nsteps x { do_step :677-718; tau += dtau; t *= expf(dtau) :768-769 } — one convection
+ * kernel + visc_substeps viscosity kernels per step, dt and the log-time clock on the device.
+ * viscosity_step's in-place update (a data race in the reference) is evaluated as the Jacobi update. */
+int tau_burgers_step(tau_burgers *h, int nsteps);
+int tau_burgers_clock(tau_burgers *h, float *t, float *tau, float *dt_last);
+int tau_burgers_download(tau_burgers *h, float *phi_u, float *phi_v);
+/* colehopf_relL2 :720-737 on the current state (handles created with colehopf = 1) */
+int tau_burgers_colehopf_error(tau_burgers *h, double *rel_l2);
+int tau_burgers_sync(tau_burgers *h);
+long long tau_burgers_steps_done(tau_burgers *h);
+long long tau_burgers_launch_count(tau_burgers *h);
+int tau_burgers_last_step_ms(tau_burgers *h, float *ms);
+int tau_burgers_destroy(tau_burgers *h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -504,3 +504,83 @@ def ref_hyp3d_vis(p: Hyp3dParams, planes, mode):
     if rc != 0:
         raise RuntimeError(f"reference hyp3d vis failed with cudaError {rc}")
     return out.reshape(p.nz, p.ny, p.nx)
+
+
+# ------------------------------------------------------------------------------------------------
+# Burgers
+# ------------------------------------------------------------------------------------------------
+class BurgersParams(C.Structure):
+    """simulation fields of `struct Params` tau_burgers.cu:53-90"""
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int)] + [(k, C.c_float) for k in (
+        "dx", "dy", "nu", "u0", "amp", "bsig", "swirl", "rc", "offx", "offy", "asym", "CFL", "tau0", "t0",
+        "dtau")] + [("muscl", C.c_int), ("visc_substeps", C.c_int), ("colehopf", C.c_int), ("ck", C.c_int),
+                    ("ca", C.c_float)]
+
+    def as22(self):
+        return np.array([getattr(self, f[0]) for f in self._fields_], np.float32)
+
+    @property
+    def shape(self):
+        return (1 if self.colehopf else self.ny, self.nx)
+
+
+def burgers_params(**over) -> BurgersParams:
+    p = BurgersParams()
+    lib.oracle_burgers_default_params(C.byref(p))
+    for k, v in over.items():
+        setattr(p, k, v)
+    return p
+
+
+def burgers_init(p: BurgersParams):
+    lib.oracle_burgers_init.argtypes = [C.POINTER(BurgersParams), f32p, f32p]
+    lib.oracle_burgers_init.restype = None
+    n = p.shape[0] * p.shape[1]
+    u, v = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    lib.oracle_burgers_init(C.byref(p), u, v)
+    return u.reshape(p.shape), v.reshape(p.shape)
+
+
+def burgers_run(p: BurgersParams, phi_u, phi_v, steps, clock=None, skip_visc=False):
+    """CPU oracle: (phi_u, phi_v, (t, tau), dts)."""
+    lib.oracle_burgers_run.argtypes = [C.POINTER(BurgersParams), f32p, f32p, C.c_int, f32p, f32p, C.c_int]
+    lib.oracle_burgers_run.restype = None
+    u = np.array(phi_u, np.float32, order="C", copy=True).ravel()
+    v = np.array(phi_v, np.float32, order="C", copy=True).ravel()
+    ck = np.array(clock if clock is not None else (p.t0, p.tau0), np.float32)
+    dts = np.zeros(max(steps, 1), np.float32)
+    lib.oracle_burgers_run(C.byref(p), u, v, steps, ck, dts, 1 if skip_visc else 0)
+    return u.reshape(p.shape), v.reshape(p.shape), (float(ck[0]), float(ck[1])), dts[:steps]
+
+
+def burgers_colehopf_error(p: BurgersParams, phi_u, t_now):
+    lib.oracle_burgers_colehopf_error.argtypes = [C.POINTER(BurgersParams), f32p, C.c_float]
+    lib.oracle_burgers_colehopf_error.restype = C.c_double
+    return float(lib.oracle_burgers_colehopf_error(C.byref(p), np.ascontiguousarray(phi_u, np.float32).ravel(),
+                                                   t_now))
+
+
+def ref_burgers_init(p: BurgersParams):
+    r = ref("ref_burgers")
+    r.ref_burgers_init.argtypes = [f32p, f32p, f32p]
+    r.ref_burgers_init.restype = None
+    n = p.shape[0] * p.shape[1]
+    u, v = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    r.ref_burgers_init(p.as22(), u, v)
+    return u.reshape(p.shape), v.reshape(p.shape)
+
+
+def ref_burgers_run(p: BurgersParams, phi_u, phi_v, steps, clock=None, skip_visc=False):
+    """The reference's own kernels on the GPU: (phi_u, phi_v, (t, tau), dts, ms)."""
+    r = ref("ref_burgers")
+    r.ref_burgers_run.argtypes = [f32p, f32p, f32p, C.c_int, f32p, f32p, C.c_int, C.POINTER(C.c_float)]
+    r.ref_burgers_run.restype = C.c_int
+    u = np.array(phi_u, np.float32, order="C", copy=True).ravel()
+    v = np.array(phi_v, np.float32, order="C", copy=True).ravel()
+    ck = np.array(clock if clock is not None else (p.t0, p.tau0), np.float32)
+    dts = np.zeros(max(steps, 1), np.float32)
+    ms = C.c_float()
+    rc = r.ref_burgers_run(p.as22(), u, v, steps, ck, dts, 1 if skip_visc else 0, C.byref(ms))
+    if rc != 0:
+        raise RuntimeError(f"reference burgers run failed with cudaError {rc}")
+    return u.reshape(p.shape), v.reshape(p.shape), (float(ck[0]), float(ck[1])), dts[:steps], float(ms.value)

@@ -1,0 +1,205 @@
+/* burgers_oracle.c — CPU restatement (fp32) of the reference 2-D Burgers step.
+ * TEST INFRASTRUCTURE ONLY: only tests/, __graft_entry__.smoke() and the bench's baseline legs may
+ * call this; the product never links or imports it.
+ *
+ * Follows tau_burgers.cu kernel by kernel (line numbers cited): wavespeed_block_max :337-361 + the
+ * host dt rule :683-691, flux_x_kernel :364-408, flux_y_kernel :411-455, update_convective :458-487,
+ * viscosity_step :490-527, clock :768-769, initialize_host :250-304, colehopf_relL2 :720-737.
+ * One deliberate difference: viscosity_step updates phi in place while neighbouring threads read
+ * it (a data race); here — as in the product — every cell reads the pre-sub-step state (Jacobi).
+ *
+ * Pinning: the reference commits no golden values for this solver.  The oracle is pinned (1) by the
+ * Cole-Hopf exact solution the reference's own harness checks against (tests/test_oracle_cpu.py) and
+ * (2) on the GPU box against the reference's own kernels (oracle/_ref/libref_burgers.so) with the
+ * racy kernel left out (nu = 0 and convective-only runs), tests/test_burgers_gpu.py.
+ */
+#define _GNU_SOURCE
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+typedef struct {
+  int nx, ny;
+  float dx, dy, nu, u0;
+  float amp, bsig, swirl, rc, offx, offy, asym;
+  float CFL, tau0, t0, dtau;
+  int muscl, visc_substeps, colehopf, ck;
+  float ca;
+} oracle_burgers_params;
+
+static int wrapb(int i, int n) { i %= n; if (i < 0) i += n; return i; }           /* :92-97 */
+static float minmodb(float a, float b) {                                            /* :331-333 */
+  return (a * b <= 0.0f) ? 0.0f : copysignf(fminf(fabsf(a), fabsf(b)), a);
+}
+
+void oracle_burgers_default_params(oracle_burgers_params *p) {                       /* :53-90 */
+  memset(p, 0, sizeof(*p));
+  p->nx = 512; p->ny = 512; p->dx = 1.0f; p->dy = 1.0f; p->nu = 0.1f; p->u0 = 1.0f;
+  p->amp = 1.0f; p->bsig = 16.0f; p->swirl = 10.0f; p->rc = 40.0f;
+  p->CFL = 0.45f; p->tau0 = 0.0f; p->t0 = 1.0f; p->dtau = 1.0f;
+  p->visc_substeps = 1; p->ck = 4; p->ca = 0.5f;
+}
+
+void oracle_burgers_init(const oracle_burgers_params *P, float *phi_u, float *phi_v) { /* :250-304 */
+  const int nx = P->nx, ny = P->colehopf ? 1 : P->ny;
+  memset(phi_u, 0, sizeof(float) * (size_t)nx * ny);
+  memset(phi_v, 0, sizeof(float) * (size_t)nx * ny);
+  if (P->colehopf) {
+    float Lx = P->dx * nx;
+    float k = 2.0f * (float)M_PI * P->ck / Lx;
+    for (int i = 0; i < nx; ++i) {
+      float x = (i + 0.5f) * P->dx;
+      float denom = 1.0f + P->ca * cosf(k * x);
+      float u = (denom != 0.0f) ? (2.0f * P->nu * P->ca * k * sinf(k * x) / denom) : 0.0f;
+      phi_u[i] = asinhf(u / P->u0);
+    }
+    return;
+  }
+  float cx = 0.5f * nx + P->offx, cy = 0.5f * ny + P->offy;
+  float sig2 = P->bsig * P->bsig;
+  float rc = P->rc * fminf(P->dx, P->dy);
+  for (int j = 0; j < ny; ++j)
+    for (int i = 0; i < nx; ++i) {
+      float dx = i - cx, dy = j - cy;
+      float r2 = (dx * dx + dy * dy) / fmaxf(sig2, 1e-6f);
+      float theta = atan2f(dy, dx);
+      float mod = 1.0f + P->asym * cosf(theta);
+      float rx = dx * P->dx, ry = dy * P->dy;
+      float r = sqrtf(rx * rx + ry * ry);
+      float u_theta = (r > 0.0f) ? (P->swirl * r * expf(-0.5f * (r / rc) * (r / rc))) : 0.0f;
+      float u = (r > 0.0f) ? (-u_theta * (ry / r)) : 0.0f;
+      float v = (r > 0.0f) ? (u_theta * (rx / r)) : 0.0f;
+      float g = P->amp * mod * expf(-0.5f * r2);
+      u += 0.5f * g;
+      v += -0.5f * g;
+      phi_u[j * nx + i] = asinhf(u / P->u0);
+      phi_v[j * nx + i] = asinhf(v / P->u0);
+    }
+}
+
+/* one do_step :677-718; returns dt_eff.  skip_visc: leave viscosity_step out. */
+static float burgers_step(const oracle_burgers_params *P, int nx, int ny, float *pu, float *pv, float *Fu,
+                          float *Fv, float *Gu, float *Gv, float *tu, float *tv, float t, int skip_visc) {
+  const int oneD = P->colehopf ? 1 : 0;
+  const float u0 = P->u0;
+  /* CFL :679-691 */
+  float smax = 1e-12f;
+  const float invdx_w = 1.0f / P->dx, invdy_w = (ny > 1 ? 1.0f / P->dy : 0.0f);
+  for (int k = 0; k < nx * ny; ++k) {
+    float u = u0 * sinhf(pu[k]), v = u0 * sinhf(pv[k]);
+    smax = fmaxf(smax, fabsf(u) * invdx_w + fabsf(v) * invdy_w);
+  }
+  const float dt = fminf(t * P->dtau, P->CFL / smax);
+#define ID(i, j) (wrapb(j, ny) * nx + wrapb(i, nx))
+  for (int j = 0; j < ny; ++j)
+    for (int i = 0; i < nx; ++i) { /* flux_x_kernel */
+      int idL = ID(i, j), idR = ID(i + 1, j);
+      float pUL = pu[idL], pUR = pu[idR], pVL = pv[idL], pVR = pv[idR];
+      if (P->muscl) {
+        float pU_Lm = pu[ID(i - 1, j)], pU_Rp = pu[ID(i + 2, j)], pV_Lm = pv[ID(i - 1, j)], pV_Rp = pv[ID(i + 2, j)];
+        float sUL = 0.5f * minmodb(pUL - pU_Lm, pUR - pUL), sUR = 0.5f * minmodb(pU_Rp - pUR, pUR - pUL);
+        float sVL = 0.5f * minmodb(pVL - pV_Lm, pVR - pVL), sVR = 0.5f * minmodb(pV_Rp - pVR, pVR - pVL);
+        pUL = pUL + sUL; pUR = pUR - sUR; pVL = pVL + sVL; pVR = pVR - sVR;
+      }
+      float uL = u0 * sinhf(pUL), vL = u0 * sinhf(pVL), uR = u0 * sinhf(pUR), vR = u0 * sinhf(pVR);
+      float FL_u = 0.5f * uL * uL, FL_v = uL * vL, FR_u = 0.5f * uR * uR, FR_v = uR * vR;
+      float a = fmaxf(fabsf(uL), fabsf(uR));
+      Fu[ID(i, j)] = 0.5f * (FL_u + FR_u) - 0.5f * a * (uR - uL);
+      Fv[ID(i, j)] = 0.5f * (FL_v + FR_v) - 0.5f * a * (vR - vL);
+    }
+  if (!oneD)
+    for (int j = 0; j < ny; ++j)
+      for (int i = 0; i < nx; ++i) { /* flux_y_kernel */
+        int idB = ID(i, j), idT = ID(i, j + 1);
+        float pUB = pu[idB], pUT = pu[idT], pVB = pv[idB], pVT = pv[idT];
+        if (P->muscl) {
+          float pU_Bm = pu[ID(i, j - 1)], pU_Tp = pu[ID(i, j + 2)], pV_Bm = pv[ID(i, j - 1)], pV_Tp = pv[ID(i, j + 2)];
+          float sUB = 0.5f * minmodb(pUB - pU_Bm, pUT - pUB), sUT = 0.5f * minmodb(pU_Tp - pUT, pUT - pUB);
+          float sVB = 0.5f * minmodb(pVB - pV_Bm, pVT - pVB), sVT = 0.5f * minmodb(pV_Tp - pVT, pVT - pVB);
+          pUB = pUB + sUB; pUT = pUT - sUT; pVB = pVB + sVB; pVT = pVT - sVT;
+        }
+        float uB = u0 * sinhf(pUB), vB = u0 * sinhf(pVB), uT = u0 * sinhf(pUT), vT = u0 * sinhf(pVT);
+        float GL_u = uB * vB, GL_v = 0.5f * vB * vB, GR_u = uT * vT, GR_v = 0.5f * vT * vT;
+        float a = fmaxf(fabsf(vB), fabsf(vT));
+        Gu[ID(i, j)] = 0.5f * (GL_u + GR_u) - 0.5f * a * (uT - uB);
+        Gv[ID(i, j)] = 0.5f * (GL_v + GR_v) - 0.5f * a * (vT - vB);
+      }
+  const float invdx = 1.0f / P->dx, invdy = oneD ? 0.0f : (1.0f / P->dy);
+  for (int j = 0; j < ny; ++j)
+    for (int i = 0; i < nx; ++i) { /* update_convective */
+      int id = ID(i, j);
+      float u = u0 * sinhf(pu[id]), v = u0 * sinhf(pv[id]);
+      float dFx_u = Fu[ID(i, j)] - Fu[ID(i - 1, j)], dFx_v = Fv[ID(i, j)] - Fv[ID(i - 1, j)];
+      float dGy_u = oneD ? 0.0f : (Gu[ID(i, j)] - Gu[ID(i, j - 1)]);
+      float dGy_v = oneD ? 0.0f : (Gv[ID(i, j)] - Gv[ID(i, j - 1)]);
+      u -= dt * (dFx_u * invdx + dGy_u * invdy);
+      v -= dt * (dFx_v * invdx + dGy_v * invdy);
+      tu[id] = asinhf(u / u0);
+      tv[id] = asinhf(v / u0);
+    }
+  memcpy(pu, tu, sizeof(float) * (size_t)nx * ny);
+  memcpy(pv, tv, sizeof(float) * (size_t)nx * ny);
+  if (!skip_visc) {
+    const int K = P->visc_substeps > 0 ? P->visc_substeps : 1;
+    const float sub = dt / K;
+    const float invdx2 = 1.0f / (P->dx * P->dx), invdy2 = oneD ? 0.0f : (1.0f / (P->dy * P->dy));
+    for (int k = 0; k < K; ++k) { /* viscosity_step, Jacobi */
+      for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i) {
+#define UU(ii, jj) (u0 * sinhf(pu[ID(ii, jj)]))
+#define VV(ii, jj) (u0 * sinhf(pv[ID(ii, jj)]))
+          float cu = UU(i, j), cv = VV(i, j);
+          float lapx = (UU(i + 1, j) - 2.0f * cu + UU(i - 1, j)) * invdx2 + (UU(i, j + 1) - 2.0f * cu + UU(i, j - 1)) * invdy2;
+          float lapy = (VV(i + 1, j) - 2.0f * cv + VV(i - 1, j)) * invdx2 + (VV(i, j + 1) - 2.0f * cv + VV(i, j - 1)) * invdy2;
+          float u = cu + P->nu * sub * lapx, v = cv + P->nu * sub * lapy;
+          tu[ID(i, j)] = asinhf(u / u0);
+          tv[ID(i, j)] = asinhf(v / u0);
+        }
+      memcpy(pu, tu, sizeof(float) * (size_t)nx * ny);
+      memcpy(pv, tv, sizeof(float) * (size_t)nx * ny);
+    }
+  }
+#undef ID
+#undef UU
+#undef VV
+  return dt;
+}
+
+/* clock = {t, tau} in/out; dts (optional) receives each dt_eff */
+void oracle_burgers_run(const oracle_burgers_params *P, float *phi_u, float *phi_v, int steps, float *clock,
+                        float *dts, int skip_visc) {
+  const int nx = P->nx, ny = P->colehopf ? 1 : P->ny;
+  const size_t n = (size_t)nx * ny;
+  float *buf = (float *)malloc(6 * n * sizeof(float));
+  float t = clock[0], tau = clock[1];
+  for (int s = 0; s < steps; ++s) {
+    float dt = burgers_step(P, nx, ny, phi_u, phi_v, buf, buf + n, buf + 2 * n, buf + 3 * n, buf + 4 * n,
+                            buf + 5 * n, t, skip_visc);
+    if (dts) dts[s] = dt;
+    tau += P->dtau;       /* :768-769 */
+    t *= expf(P->dtau);
+  }
+  clock[0] = t; clock[1] = tau;
+  free(buf);
+}
+
+/* colehopf_relL2 :720-737 */
+double oracle_burgers_colehopf_error(const oracle_burgers_params *P, const float *phi_u, float t_now) {
+  const int nx = P->nx;
+  float Lx = P->dx * nx;
+  float k = 2.0f * (float)M_PI * P->ck / Lx;
+  float decay = expf(-P->nu * k * k * t_now);
+  double num = 0.0, den = 0.0;
+  for (int i = 0; i < nx; ++i) {
+    float x = (i + 0.5f) * P->dx;
+    float u_ex = (2.0f * P->nu * P->ca * k * decay * sinf(k * x)) / (1.0f + P->ca * decay * cosf(k * x));
+    double u_num = P->u0 * sinh((double)phi_u[i]);
+    double diff = u_num - u_ex;
+    num += diff * diff;
+    den += (double)u_ex * u_ex;
+  }
+  return (den > 0.0) ? sqrt(num / den) : sqrt(num);
+}

@@ -1,5 +1,5 @@
 /* Fake <ncursesw/curses.h> — TEST INFRASTRUCTURE ONLY.
- * The reference's tau_gray_scott.cu / tau_sph.cu include ncurses for their terminal renderer; the
+ * The reference's tau_gray_scott.cu / tau_sph.cu / tau_burgers.cu include ncurses for their terminal renderer; the
  * image has no ncurses headers.  This stub declares just enough (as no-ops) for those translation
  * units to compile when oracle/ref_drivers/ #include them with `-Dmain=ref_main`; the renderer is
  * never called.  Written from the symbol list in SURVEY.md §8(c); contains no reference code. */
@@ -56,6 +56,8 @@ static inline int mvaddwstr(int y, int x, const wchar_t *s) { (void)y; (void)x; 
 static inline int mvaddstr(int y, int x, const char *s) { (void)y; (void)x; (void)s; return OK; }
 static inline int mvprintw(int y, int x, const char *fmt, ...) { (void)y; (void)x; (void)fmt; return OK; }
 static inline int printw(const char *fmt, ...) { (void)fmt; return OK; }
+static inline int addnwstr(const wchar_t *s, int n) { (void)s; (void)n; return OK; }
+static inline int clrtoeol(void) { return OK; }
 static inline int refresh(void) { return OK; }
 static inline int getch(void) { return ERR; }
 static inline int timeout_(int t) { (void)t; return OK; }

@@ -81,7 +81,8 @@ def test_cli_hosts_build_and_fail_loudly_without_gpu():
     cases = {"tgs": ["--nx", "64", "--ny", "32", "--steps", "3", "--headless"],
              "tau_2d_hypersonic_cuda": ["--nx", "128", "--ny", "64", "--frames", "2"],
              "tau3d": ["--n", "16", "--frames", "1"],
-             "tau_sph": ["--n", "2048", "--frames", "2"]}
+             "tau_sph": ["--n", "2048", "--frames", "2"],
+             "tau_burgers": ["--nx", "96", "--ny", "64", "--steps", "4", "--headless", "--dtau", "1e-3"]}
     for exe, args in cases.items():
         r = subprocess.run([os.path.join(cli, exe)] + args, capture_output=True, text=True, timeout=120)
         if device_count() > 0:

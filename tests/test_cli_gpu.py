@@ -77,3 +77,27 @@ def test_cli_rejects_bad_flags_like_the_reference():
     assert r.returncode == 1 and "Invalid --gamma" in r.stderr  # parse_args :1545
     r = subprocess.run([BIN, "--bogus"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and "Unknown or incomplete argument" in r.stderr
+
+
+def test_tau_burgers_cli_matches_api_and_cole_hopf(tmp_path):
+    exe = os.path.join(ROOT, "fluid_sims_b200", "cli", "tau_burgers")
+    if not os.path.exists(exe):
+        pytest.skip("CLI not built")
+    from fluid_sims_b200.burgers import Burgers, Params
+    dump = str(tmp_path / "b.bin")
+    r = subprocess.run([exe, "--nx", "160", "--ny", "96", "--steps", "12", "--dtau", "1e-3", "--muscl",
+                        "--visc_substeps", "2", "--headless", "--dump", dump], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "Headless (stride=5):" in r.stdout and "Steps: 12" in r.stdout, r.stdout + r.stderr
+    got, step, t = read_dump(dump)
+    s = Burgers(Params(nx=160, ny=96, dtau=1e-3, muscl=1, visc_substeps=2)).init()
+    s.step(12)
+    u, v = s.download()
+    assert step == 12 and np.array_equal(got[0], u) and np.array_equal(got[1], v)
+    assert t == np.float32(s.clock()[0])
+    s.close()
+    # the reference's validation mode prints the relative L2 error against the exact solution
+    r = subprocess.run([exe, "--nx", "256", "--colehopf", "--nu", "0.5", "--dtau", "5e-3", "--t0", "1e-3", "--ck", "2",
+                        "--steps", "2200", "--stride", "100"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    last = [l for l in r.stdout.splitlines() if "relL2=" in l][-1]
+    assert float(last.split("relL2=")[1]) < 2.5e-3

@@ -350,3 +350,34 @@ def _near(sol):
     for ax in range(3):
         out |= np.roll(sol, 1, ax) | np.roll(sol, -1, ax)
     return out
+
+
+def test_burgers_oracle_cole_hopf():
+    """Pins the Burgers oracle on the exact 1-D solution the reference's own harness compares with
+    (tau_burgers.cu:720-737): error small, and shrinking with resolution."""
+    errs = []
+    for nx in (128, 256):
+        p = oracle.burgers_params(nx=nx, colehopf=1, nu=0.5, dtau=5e-3, t0=1e-3, ck=2, ca=0.5)
+        u, v = oracle.burgers_init(p)
+        assert oracle.burgers_colehopf_error(p, u, p.t0) < 1e-5
+        u2, _, (t, tau), dts = oracle.burgers_run(p, u, v, 2200)
+        assert abs(tau - 11.0) < 1e-3 and abs(t - 1e-3 * np.exp(11.0)) < 1e-3 * t
+        assert np.all(dts[:50] == np.float32(p.dtau) * (np.float32(p.t0) * np.exp(np.float32(p.dtau)) ** np.arange(50)).astype(np.float32)) or dts[0] == np.float32(p.t0 * p.dtau)
+        errs.append(oracle.burgers_colehopf_error(p, u2, t))
+        assert oracle.burgers_colehopf_error(p, u, t) > 10 * errs[-1]     # the field really evolved
+    assert errs[0] < 1e-2 and errs[1] < 2.5e-3 and errs[1] < 0.4 * errs[0]
+
+
+def test_burgers_oracle_2d_basics():
+    """2-D swirl init (:282-304), basic sanity only: nu = 0 keeps the convective update finite and bounded for both reconstructions, and the
+    log-time clock does not depend on the scheme."""
+    p = oracle.burgers_params(nx=64, ny=48, dtau=1e-3, nu=0.0)
+    u, v = oracle.burgers_init(p)
+    a = oracle.burgers_run(p, u, v, 30)
+    p.muscl = 1
+    b = oracle.burgers_run(p, u, v, 30)
+    assert np.isfinite(a[0]).all() and np.isfinite(b[0]).all()
+    assert np.abs(a[0]).max() <= np.abs(u).max() + 1e-3          # Rusanov is monotone: no new extrema
+    assert np.abs(a[0] - b[0]).max() > 0                           # the reconstruction matters
+    assert np.abs(b[0]).max() <= np.abs(u).max() + 1e-3           # minmod-limited: still no new extrema
+    assert a[2] == b[2]                                            # the clock does not depend on the scheme

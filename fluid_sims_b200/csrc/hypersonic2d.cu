@@ -1318,7 +1318,7 @@ int launch_init(tau_hyp2d *h) {
 // Work-item table.  The rows of the slab are cut into layers; a layer is one row segment of every
 // strip.  Caller-chosen height (tau_hyp2d_set_seg_rows): uniform layers.  Default: guided
 // self-scheduling — a layer's height is (remaining item-rows) / (taper_k x resident warps), clamped
-// to [min_rows, 24]: tall segments first (the two warm-up rows of a segment are amortised over 24
+// to [min_rows, 48]: tall segments first (the two warm-up rows of a segment are amortised over 48
 // rows), short ones last (so that all SMs run dry together; the step ends in a global reduction and
 // its tail cannot be overlapped with the next step).  Items whose window touches the body run the
 // costlier masked march and go to the front of the table (longest-processing-time-first).
@@ -1542,7 +1542,7 @@ int tau_hyp2d_create(const tau_hyp2d_config *cfg, int W, int H, int dtype, int d
   h->seg_auto = true;
   h->taper_k = 2;
   h->min_rows = 4;
-  h->max_rows = 24;
+  h->max_rows = 48;
   if (const char *e = getenv("TAU_HYP2D_MAX_ROWS")) {
     int v = atoi(e);
     if (v >= 4) h->max_rows = v;

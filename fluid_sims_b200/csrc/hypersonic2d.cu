@@ -377,21 +377,17 @@ template <typename R> __device__ __forceinline__ Cons4<R> shfl_down_cons(Cons4<R
                   __shfl_down_sync(0xffffffffu, c.my, 1), __shfl_down_sync(0xffffffffu, c.E, 1)};
 }
 
-// Per-warp view of the shared-memory row ring.  Row q (offset from the segment's first staged row)
-// lives in slot (q/4)%NS; a slot is laid out [field][row-in-box][BOXW columns] as the TMA box
-// lands.  row_off(q) is the element offset of (field 0, row q, column 0); fields are FSTRIDE apart.
+// Per-warp view of the shared-memory row ring.  A slot is laid out [field][row-in-box][BOXW columns]
+// as the TMA box lands; `off` is the element offset of (field 0, staged row, column 0) — see row_off
+// in the step kernel — and fields are FSTRIDE apart.
 template <typename R>
 struct Ring {
   R *base;
   static constexpr int FSTRIDE = H2_RB * H2_BOXW;
-  __device__ __forceinline__ static int row_off(int q) {
-    return ((q >> 2) % H2_NS) * (4 * H2_RB * H2_BOXW) + (q & 3) * H2_BOXW;
-  }
   __device__ __forceinline__ Cons4<R> at(int off, int c) const {
     const R *p = base + off + c;
     return Cons4<R>{p[0], p[FSTRIDE], p[2 * FSTRIDE], p[3 * FSTRIDE]};
   }
-  __device__ __forceinline__ Cons4<R> cons(int q, int c) const { return at(row_off(q), c); }
 };
 
 // 5-tap second derivative (-1, 16, -30, 16, -1)/12 of k_step :1126-1153
@@ -1388,14 +1384,14 @@ int build_items(tau_hyp2d *h, size_t smem) {
 template <typename R>
 int launch_steps(tau_hyp2d *h, int nsteps) {
   const size_t smem = step_smem_bytes<R>();
-  static bool attr_done[2][2] = {{false, false}, {false, false}};
+  static bool attr_done[2][64] = {};  // per arithmetic type and device (the attribute is per context)
   auto kern_tma = hyp2d_step<R, true>;
   auto kern_gen = hyp2d_step<R, false>;
-  const int ti = sizeof(R) == 8;
-  if (!attr_done[ti][0]) {
+  const int ti = sizeof(R) == 8, di = h->device & 63;
+  if (!attr_done[ti][di]) {
     TAU_CUDA(cudaFuncSetAttribute(kern_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TAU_CUDA(cudaFuncSetAttribute(kern_gen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done[ti][0] = true;
+    attr_done[ti][di] = true;
   }
   if (h->items_dirty) {
     const int rc = build_items<R>(h, smem);

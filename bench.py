@@ -372,7 +372,7 @@ def run_product(a):
                          "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
                          "algorithmic_bytes_per_cell": bpc, "kernel": "hyp2d_step",
                          "kernel_ms": kernel_ms,
-                         "note": "kernel is FP32-issue bound (~690 executed warp-instructions per 30-cell row, 80 % issue-slot utilisation), see DESIGN.md 4.1"},
+                         "note": "kernel is FP32-issue bound (685 executed warp-instructions per 30-cell row, 82 % issue-slot utilisation), see DESIGN.md 4.1"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             **({"peer_timing": peer_timing} if peer_timing else {}),
         }))

@@ -91,6 +91,75 @@ def test_chain_exchange_and_max(world, tmp_path):
             assert (bot[:, 0] == 100 * (r + 1)).all() and (bot[:, 1] == 100 * (r + 1) + 1).all()
 
 
+def _hyp3d_worker(rank, world, port, n, steps, out):
+    """z-slab ring of the 3-D solver: 3 ghost planes per side, max-wavespeed all-reduce feeding the
+    d_tau controller (tau_hypersonic_3d_cuda.cu:1680-1704) on every rank — the protocol of
+    tau_hyp3d_step_begin / _end, with the CPU oracle as the per-slab stepper."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import ctypes as C
+    nx, ny, nz = n
+    prm = oracle.hyp3d_params(nx, ny, nz)
+    planes, solid = oracle.hyp3d_init(prm)
+    z0, nl = slab.partition_rows(nz, world)[rank]
+    G = 3
+    loc = oracle.hyp3d_params(nx, ny, nl + 2 * G)
+    loc.dz = prm.dz                      # the slab is a window of the global grid, not a smaller grid
+    loc.sdf_cz = prm.sdf_cz - (z0 - G) * prm.dz   # sphere centre in slab-local coordinates
+    step = oracle.lib.oracle_hyp3d_step_planes
+    step.argtypes = [C.POINTER(oracle.Hyp3dParams), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), oracle.u8p,
+                     C.c_float, C.c_float, C.c_int, C.c_int]
+    step.restype = C.c_float
+    full = [np.asarray(p_, np.float32).reshape(nz, ny, nx) for p_ in planes]
+    sol_full = np.asarray(solid, np.uint8).reshape(nz, ny, nx)
+    st = torch.zeros(6, nl + 2 * G, ny, nx)
+    for f in range(6):
+        st[f, G:G + nl] = torch.from_numpy(full[f][z0:z0 + nl].copy())
+    sol = torch.zeros(nl + 2 * G, ny, nx, dtype=torch.uint8)
+    sol[G:G + nl] = torch.from_numpy(sol_full[z0:z0 + nl].copy())
+    slab.exchange_halos([sol], G, periodic=True, dim=0)       # static: once
+    libm = C.CDLL("libm.so.6")           # the oracle's clock uses libm's expf: same function, same bits
+    libm.expf.argtypes, libm.expf.restype = [C.c_float], C.c_float
+    t, d_tau = np.float32(0.012), np.float32(2e-3)
+    for _ in range(steps):
+        slab.exchange_halos([st], G, periodic=True, dim=1)
+        t = np.float32(t * np.float32(libm.expf(float(d_tau))))
+        dt = np.float32(t * d_tau)
+        gain = np.float32(min(max(t / np.float32(0.02), 0.0), 1.0))
+        a = [np.ascontiguousarray(st[f].numpy()) for f in range(6)]
+        b = [np.zeros_like(x) for x in a]
+        pa = (C.c_void_p * 6)(*[x.ctypes.data for x in a])
+        pb = (C.c_void_p * 6)(*[x.ctypes.data for x in b])
+        maxs = step(C.byref(loc), pa, pb, np.ascontiguousarray(sol.numpy()).ravel(), dt, gain, G, G + nl)
+        m = torch.tensor([maxs], dtype=torch.float32)
+        slab.allreduce_max_(m)
+        dt_cfl = np.float32(prm.cfl / max(np.float32(m.item()), np.float32(1e-9)))
+        if dt > np.float32(1.10) * dt_cfl:
+            d_tau = np.float32(d_tau * np.float32(0.80))
+        elif dt < np.float32(0.85) * dt_cfl:
+            d_tau = np.float32(d_tau * np.float32(1.10))
+        d_tau = np.float32(min(max(d_tau, np.float32(1e-7)), np.float32(5e-2)))
+        for f in range(6):
+            st[f, G:G + nl] = torch.from_numpy(b[f][G:G + nl])
+    np.save(os.path.join(out, f"s{rank}.npy"), st[:, G:G + nl].numpy())
+    np.save(os.path.join(out, f"c{rank}.npy"), np.array([t, d_tau], np.float32))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_hyp3d_z_slab_ring_reproduces_single_domain(world, tmp_path):
+    n, steps = (20, 12, 18), 5
+    mp.spawn(_hyp3d_worker, args=(world, _free_port(), n, steps, str(tmp_path)), nprocs=world, join=True)
+    got = np.concatenate([np.load(tmp_path / f"s{r}.npy") for r in range(world)], axis=1)
+    prm = oracle.hyp3d_params(*n)
+    planes, solid = oracle.hyp3d_init(prm)
+    ref, ck, _, _ = oracle.hyp3d_run(prm, planes, solid, steps, (0.012, 2e-3))
+    for f in range(6):
+        assert np.array_equal(got[f].ravel(), ref[f]), f
+    for r in range(world):
+        assert tuple(np.load(tmp_path / f"c{r}.npy")) == tuple(np.float32(x) for x in ck)
+
+
 def test_partition_rows():
     assert slab.partition_rows(4096, 8) == [(512 * i, 512) for i in range(8)]
     parts = slab.partition_rows(37, 3)

@@ -8,10 +8,12 @@
  * One deliberate difference: viscosity_step updates phi in place while neighbouring threads read
  * it (a data race); here — as in the product — every cell reads the pre-sub-step state (Jacobi).
  *
- * Pinning: the reference commits no golden values for this solver.  The oracle is pinned (1) by the
- * Cole-Hopf exact solution the reference's own harness checks against (tests/test_oracle_cpu.py) and
- * (2) on the GPU box against the reference's own kernels (oracle/_ref/libref_burgers.so) with the
- * racy kernel left out (nu = 0 and convective-only runs), tests/test_burgers_gpu.py.
+ * Pinning: the reference commits no golden values for this solver.  The oracle is pinned (1) by
+ * tests/golden/burgers_ref.npz — outputs of the reference's own kernels run on a B200 through
+ * oracle/_ref where they are deterministic (nu = 0), generator tests/golden/make_golden_gpu.py —
+ * which it reproduces to the libm-vs-fast-intrinsic level (init bit-identical, dt identical,
+ * fields 1e-5), and (2) by the Cole-Hopf exact solution the reference's own harness checks against
+ * (both in tests/test_oracle_cpu.py).
  */
 #define _GNU_SOURCE
 #include <math.h>

@@ -131,7 +131,26 @@ def sph():
     print("sph golden written")
 
 
+def burgers():
+    # the reference's own kernels where they are deterministic (nu = 0: viscosity_step does not mix cells)
+    # plus one viscous 1-D Cole-Hopf case (ny = 1: a single block row; the in-place race is confined to
+    # block seams) and the render-free init of each
+    out = {}
+    cases = (("a", dict(nx=96, ny=64, dtau=1e-3, nu=0.0, swirl=0.2, amp=0.3), 40),
+             ("b", dict(nx=96, ny=64, dtau=1e-3, nu=0.0, swirl=0.2, amp=0.3, muscl=1), 40),
+             ("c", dict(nx=96, ny=64, dtau=1e-3, nu=0.0), 10),
+             ("d", dict(nx=300, colehopf=1, dtau=5e-3, t0=1e-3, nu=0.0, ck=2), 200))
+    for tag, kw, steps in cases:
+        prm = oracle.burgers_params(**kw)
+        u0, v0 = oracle.ref_burgers_init(prm)
+        u, v, ck, dts, _ = oracle.ref_burgers_run(prm, u0, v0, steps)
+        out.update({f"u0_{tag}": u0, f"v0_{tag}": v0, f"u_{tag}": u, f"v_{tag}": v, f"clock_{tag}": np.array(ck),
+                    f"dts_{tag}": dts, f"p22_{tag}": prm.as22(), f"steps_{tag}": np.array(steps)})
+    np.savez_compressed(os.path.join(OUT, "burgers_ref.npz"), **out)
+    print("burgers golden written")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["gs", "hyp2d", "hyp3d", "sph"]
+    which = sys.argv[1:] or ["gs", "hyp2d", "hyp3d", "sph", "burgers"]
     for w in which:
         globals()[w]()

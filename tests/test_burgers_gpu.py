@@ -132,3 +132,19 @@ def test_multi_step_call_equals_single_steps_and_errors_are_loud():
         Burgers(P).upload(u0, v0).colehopf_error()
     with pytest.raises(TauError, match="u0"):
         Burgers(Params(u0=0.0))
+
+
+def test_matches_reference_golden_fixture():
+    """tests/golden/burgers_ref.npz (reference kernels on a B200, nu = 0): needs no oracle/_ref."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "burgers_ref.npz"))
+    names = [f[0] for f in oracle.BurgersParams._fields_]
+    ints = ("nx", "ny", "muscl", "visc_substeps", "colehopf", "ck")
+    for tag, tol in (("a", 1e-5), ("b", 1e-5), ("c", 2e-5)):
+        kw = {n: (int(v) if n in ints else float(v)) for n, v in zip(names, g[f"p22_{tag}"])}
+        P = Params(**kw)
+        u0, v0 = initialize_host(P)
+        assert np.array_equal(u0, g[f"u0_{tag}"]) and np.array_equal(v0, g[f"v0_{tag}"])
+        (u, v), ck = product(P, u0, v0, int(g[f"steps_{tag}"]))
+        assert np.abs(u - g[f"u_{tag}"]).max() < tol and np.abs(v - g[f"v_{tag}"]).max() < tol, tag
+        assert abs(ck[0] - g[f"clock_{tag}"][0]) <= 1e-6 * ck[0]

@@ -1311,6 +1311,42 @@ int launch_init(tau_hyp2d *h) {
   return TAU_OK;
 }
 
+}  // namespace
+
+// The row schedule of the work-item table as a pure host function (unit-tested without a GPU):
+// cuts rows [0, h_local) into layers of layer_h[i] rows starting at layer_y[i].  seg_rows > 0:
+// uniform layers of that height; seg_rows == 0: guided self-scheduling (see build_items).  A layer
+// is at most 4095 rows (12-bit field of the item descriptor).  Returns the number of layers.
+extern "C" int tau_hyp2d_plan_layers(int h_local, int nstrips, int resident_warps, int seg_rows, int taper_k,
+                                     int min_rows, int max_rows, int *layer_y, int *layer_h, int cap) {
+  TAU_REQUIRE(h_local >= 1 && nstrips >= 1 && resident_warps >= 1 && layer_y && layer_h,
+              "tau_hyp2d_plan_layers: bad argument");
+  TAU_REQUIRE(seg_rows >= 0 && taper_k >= 1 && min_rows >= 1 && max_rows >= min_rows,
+              "tau_hyp2d_plan_layers: need seg_rows >= 0, taper_k >= 1, 1 <= min_rows <= max_rows");
+  int n = 0, y = 0;
+  while (y < h_local) {
+    int hgt;
+    if (seg_rows == 0) {
+      const long long remaining = (long long)(h_local - y) * nstrips;
+      hgt = (int)(remaining / ((long long)taper_k * resident_warps));
+      if (hgt > max_rows) hgt = max_rows;
+      if (hgt < min_rows) hgt = min_rows;
+    } else {
+      hgt = seg_rows;
+    }
+    if (hgt > 4095) hgt = 4095;
+    if (hgt > h_local - y) hgt = h_local - y;
+    TAU_REQUIRE(n < cap, "tau_hyp2d_plan_layers: more than %d layers", cap);
+    layer_y[n] = y;
+    layer_h[n] = hgt;
+    ++n;
+    y += hgt;
+  }
+  return n;
+}
+
+namespace {
+
 // Work-item table.  The rows of the slab are cut into layers; a layer is one row segment of every
 // strip.  Caller-chosen height (tau_hyp2d_set_seg_rows): uniform layers.  Default: guided
 // self-scheduling — a layer's height is (remaining item-rows) / (taper_k x resident warps), clamped
@@ -1329,23 +1365,13 @@ int build_items(tau_hyp2d *h, size_t smem) {
   if (per_sm < 1) per_sm = 1;
   const int resident_warps = dev_sms * per_sm * H2_WARPS;
   const int nstrips = (h->W + H2_OWN - 1) / H2_OWN;
-  std::vector<int> layer_y, layer_h;
-  int y = 0;
-  while (y < h->h_local) {
-    int hgt;
-    if (h->seg_auto) {
-      const long long remaining = (long long)(h->h_local - y) * nstrips;
-      hgt = (int)(remaining / ((long long)h->taper_k * resident_warps));
-      if (hgt > h->max_rows) hgt = h->max_rows;
-      if (hgt < h->min_rows) hgt = h->min_rows;
-    } else {
-      hgt = h->seg_rows;
-    }
-    if (hgt > h->h_local - y) hgt = h->h_local - y;
-    layer_y.push_back(y);
-    layer_h.push_back(hgt);
-    y += hgt;
-  }
+  std::vector<int> layer_y(h->h_local), layer_h(h->h_local);
+  const int nl = tau_hyp2d_plan_layers(h->h_local, nstrips, resident_warps, h->seg_auto ? 0 : h->seg_rows,
+                                       h->taper_k, h->min_rows, h->max_rows, layer_y.data(), layer_h.data(),
+                                       h->h_local);
+  if (nl < 0) return nl;
+  layer_y.resize(nl);
+  layer_h.resize(nl);
   if (h->seg_auto) h->seg_rows = layer_h.empty() ? 0 : layer_h[0];
   const size_t n = layer_y.size() * (size_t)nstrips;
   TAU_REQUIRE(nstrips <= 0xffff && h->h_local < (1 << 20), "tau_hyp2d: grid too large for the item table");

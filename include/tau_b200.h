@@ -172,6 +172,10 @@ int tau_hyp2d_checkpoint_info(const char *path, int *W, int *H, int *dtype, int 
 int tau_hyp2d_checkpoint_load(tau_hyp2d *h, const char *path);
 /* rows each warp marches per work item (tuning; --tile-by analogue of :1641-1685) */
 int tau_hyp2d_set_seg_rows(tau_hyp2d *h, int rows);
+/* the row schedule behind the work-item table as a pure host function (no device needed): layers of
+ * layer_h[i] rows starting at layer_y[i]; seg_rows == 0 selects the guided (tall-to-short) schedule */
+int tau_hyp2d_plan_layers(int h_local, int nstrips, int resident_warps, int seg_rows, int taper_k,
+                          int min_rows, int max_rows, int *layer_y, int *layer_h, int cap);
 /* the height in use (chosen by a wave model at the first step unless set explicitly) */
 int tau_hyp2d_get_seg_rows(tau_hyp2d *h);
 long long tau_hyp2d_steps_done(tau_hyp2d *h);

@@ -119,3 +119,42 @@ def test_snapshot_file_format_without_gpu(tmp_path):
     import pytest
     with pytest.raises(TauError, match="of 12 fields"):
         Snapshot.read(str(tmp_path / "bad.txt"))
+
+
+def test_hyp2d_row_schedule_properties():
+    """tau_hyp2d_plan_layers (pure host code): the layers tile [0, h_local) exactly once; the guided
+    schedule is tall-to-short within [min_rows, max_rows] (the last layer may be the remainder); uniform
+    schedules have one height; a layer never exceeds the descriptor's 12-bit row field."""
+    import ctypes as C
+    import numpy as np
+    from fluid_sims_b200._lib import lib
+    f = lib.tau_hyp2d_plan_layers
+    f.argtypes = [C.c_int] * 7 + [C.POINTER(C.c_int)] * 2 + [C.c_int]
+    f.restype = C.c_int
+    rng = np.random.default_rng(0)
+    cases = [(4096, 137, 2960, 0, 2, 4, 48), (512, 137, 2960, 0, 2, 4, 48), (7, 2, 2960, 0, 2, 4, 48),
+             (1, 1, 4, 0, 1, 1, 1), (4096, 137, 2960, 24, 2, 4, 48), (5000, 3, 16, 5000, 1, 4, 48),
+             (4096, 1, 1, 0, 1, 4, 100000)]
+    for _ in range(200):
+        cases.append((int(rng.integers(1, 9000)), int(rng.integers(1, 300)), int(rng.integers(1, 6000)),
+                      int(rng.choice([0, 0, 4, 7, 64])), int(rng.integers(1, 5)), int(rng.integers(1, 9)),
+                      int(rng.integers(9, 80))))
+    for (hl, ns, rw, seg, k, mn, mx) in cases:
+        ly, lh = (C.c_int * hl)(), (C.c_int * hl)()
+        n = f(hl, ns, rw, seg, k, mn, mx, ly, lh, hl)
+        assert n >= 1, (hl, ns, rw, seg, k, mn, mx)
+        y = 0
+        for i in range(n):
+            assert ly[i] == y and 1 <= lh[i] <= 4095
+            y += lh[i]
+        assert y == hl
+        hs = [lh[i] for i in range(n)]
+        if seg:
+            assert all(h == min(seg, 4095) for h in hs[:-1]) and hs[-1] <= min(seg, 4095)
+        else:
+            body = hs[:-1]
+            assert all(a >= b for a, b in zip(body, body[1:]))            # tall to short
+            assert all(mn <= h <= min(mx, 4095) for h in body)
+    ly, lh = (C.c_int * 4)(), (C.c_int * 4)()
+    assert f(100, 1, 1, 4, 1, 4, 48, ly, lh, 4) < 0                        # capacity exceeded: loud
+    assert f(10, 1, 1, 0, 0, 4, 48, ly, lh, 4) < 0                         # taper_k < 1: loud

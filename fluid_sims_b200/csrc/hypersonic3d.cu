@@ -235,6 +235,36 @@ __device__ __forceinline__ float weno5_left(float v0, float v1, float v2, float 
   float n0 = 0.1f * (e1 * e2), n1 = 0.6f * (e0 * e2), n2 = 0.3f * (e0 * e1);
   return fdiv(n0 * p0 + n1 * p1 + n2 * p2, n0 + n1 + n2);
 }
+#ifdef T3_PACKED_WENO
+// Both one-sided reconstructions of a face use the same six values: L = weno5_left(v0..v4) and
+// R = weno5_left(v5..v1).  Evaluated side by side as the two halves of a float2 they run on sm_100's
+// packed FADD2/FMUL2/FFMA2 (the body is pure add/mul/fma apart from one reciprocal): same expression
+// trees with the contractions spelled out.  COMPILE-TIME OPTION, OFF BY DEFAULT: written when the
+// round's GPU budget was spent; static effect recorded in profiles/hyp3d_r1_experiments.md, to be
+// validated against tests/test_hyp3d_gpu.py before it is switched on.
+__device__ __forceinline__ float2 weno5_pair(float v0, float v1, float v2, float v3, float v4, float v5) {
+  const float2 a0 = make_float2(v0, v5), a1 = make_float2(v1, v4), a2 = make_float2(v2, v3),
+               a3 = make_float2(v3, v2), a4 = make_float2(v4, v1);
+  auto C = [](float c) { return make_float2(c, c); };
+  auto fma2 = [](float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); };
+  auto mul2 = [](float2 a, float2 b) { return __fmul2_rn(a, b); };
+  auto add2 = [](float2 a, float2 b) { return __fadd2_rn(a, b); };
+  const float2 p0 = mul2(fma2(C(11.f), a2, fma2(C(-7.f), a1, mul2(C(2.f), a0))), C(1.f / 6.f));
+  const float2 p1 = mul2(fma2(C(2.f), a3, fma2(C(5.f), a2, mul2(C(-1.f), a1))), C(1.f / 6.f));
+  const float2 p2 = mul2(fma2(C(-1.f), a4, fma2(C(5.f), a3, mul2(C(2.f), a2))), C(1.f / 6.f));
+  const float2 t0 = add2(fma2(C(-2.f), a1, a0), a2), u0 = fma2(C(3.f), a2, fma2(C(-4.f), a1, a0));
+  const float2 t1 = add2(fma2(C(-2.f), a2, a1), a3), u1 = fma2(C(-1.f), a3, a1);
+  const float2 t2 = add2(fma2(C(-2.f), a3, a2), a4), u2 = add2(fma2(C(-4.f), a3, mul2(C(3.f), a2)), a4);
+  const float2 b0 = fma2(mul2(C(0.25f), u0), u0, mul2(mul2(C(13.f / 12.f), t0), t0));
+  const float2 b1 = fma2(mul2(C(0.25f), u1), u1, mul2(mul2(C(13.f / 12.f), t1), t1));
+  const float2 b2 = fma2(mul2(C(0.25f), u2), u2, mul2(mul2(C(13.f / 12.f), t2), t2));
+  const float2 g0 = add2(C(WENO_EPS), b0), g1 = add2(C(WENO_EPS), b1), g2 = add2(C(WENO_EPS), b2);
+  const float2 e0 = mul2(g0, g0), e1 = mul2(g1, g1), e2 = mul2(g2, g2);
+  const float2 n0 = mul2(C(0.1f), mul2(e1, e2)), n1 = mul2(C(0.6f), mul2(e0, e2)), n2 = mul2(C(0.3f), mul2(e0, e1));
+  const float2 num = fma2(n2, p2, fma2(n1, p1, mul2(n0, p0))), den = add2(add2(n0, n1), n2);
+  return make_float2(fdiv(num.x, den.x), fdiv(num.y, den.y));
+}
+#endif
 __device__ __forceinline__ void prim_floor_fast(Q &q) {  // :565-571
   q.r = fmaxf(q.r, RHO_P_FLOOR);
   q.p = fmaxf(q.p, RHO_P_FLOOR);
@@ -387,17 +417,22 @@ hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out,
         R = load_q(jb);
       } else {  // weno_face_from_6 :578-598 on cells a-2 .. b+2
         const int j0 = ja - 2 * stride;
+#ifdef T3_PACKED_WENO
+#define WENO_LR(l, r) { const float2 lr = weno5_pair(v0, v1, v2, v3, v4, v5); l = lr.x; r = lr.y; }
+#else
+#define WENO_LR(l, r) { l = weno5_left(v0, v1, v2, v3, v4); r = weno5_left(v5, v4, v3, v2, v1); }
+#endif
 #define WENO_FIELD(k, fld)                                                                       \
   {                                                                                              \
     const float *s = s_q + (k) * T3_SVOL + j0;                                                   \
     const float v0 = s[0], v1 = s[stride], v2 = s[2 * stride], v3 = s[3 * stride],               \
                 v4 = s[4 * stride], v5 = s[5 * stride];                                          \
-    L.fld = weno5_left(v0, v1, v2, v3, v4);                                                      \
-    R.fld = weno5_left(v5, v4, v3, v2, v1);                                                      \
+    WENO_LR(L.fld, R.fld)                                                                        \
   }
         WENO_FIELD(0, r) WENO_FIELD(1, u) WENO_FIELD(2, v) WENO_FIELD(3, w) WENO_FIELD(4, p)
         WENO_FIELD(5, ev)
 #undef WENO_FIELD
+#undef WENO_LR
       }
       prim_floor_fast(L);
       prim_floor_fast(R);

@@ -1192,6 +1192,8 @@ __global__ void hyp2d_init(const Params<R> P, Geom G, R rest_E, R *U, uint8_t *m
 
 }  // namespace
 
+#include "hypersonic2d_pair.cuh"  // experimental packed two-column kernel (TAU_HYP2D_PAIR=1 only)
+
 // ================================================================================================
 // host side
 // ================================================================================================
@@ -1225,6 +1227,12 @@ struct tau_hyp2d {
   cudaEvent_t ev0, ev1;
   bool timed;
   size_t plane_elems;
+  // experimental pair mode (TAU_HYP2D_PAIR=1, fp32 + TMA only; see hypersonic2d_pair.cuh)
+  bool pair_mode;
+  CUtensorMap tm_pair[2];
+  uint2 *items_pair, *items_rest;   // interior body-free 60-column items / everything else (30-column)
+  int nitems_pair, nitems_rest, grid_pair, grid_rest;
+  unsigned int *pair_ctr;           // 3 rotating claim counters of the pair kernel
   uchar4 *pixels;             // render target (device), allocated on first use
   unsigned long long *mmkeys; // render min/max keys (device)
 };
@@ -1407,6 +1415,120 @@ int build_items(tau_hyp2d *h, size_t smem) {
   return TAU_OK;
 }
 
+// ---- experimental pair mode: split the item table, launch pair kernel + production kernel -------------
+size_t pair_smem_bytes() {
+  return (size_t)H2_WARPS * H2_NS * HP_SLOT * sizeof(float) + H2_WARPS * H2_NS * sizeof(uint64_t);
+}
+// After build_items<float>: a 60-column super-strip s (30-column strips 2s, 2s+1) of a layer becomes
+// one pair item iff both strips exist, neither touches the body, and its 68-column box lies inside
+// the grid; every other 30-column item stays with the production kernel.
+int build_items_pair(tau_hyp2d *h) {
+  const int n = h->nitems;
+  std::vector<uint2> all((size_t)n);
+  TAU_CUDA(cudaMemcpyAsync(all.data(), h->items, (size_t)n * sizeof(uint2), cudaMemcpyDeviceToHost, h->stream));
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  const int nstrips = (h->W + H2_OWN - 1) / H2_OWN;
+  // index the 30-column items by (layer start row, strip)
+  std::vector<uint2> pair, rest;
+  std::vector<int> pos((size_t)nstrips);
+  std::vector<unsigned> layers;
+  for (int i = 0; i < n; ++i) {
+    bool seen = false;
+    for (unsigned y : layers) seen |= (y == all[i].y);
+    if (!seen) layers.push_back(all[i].y);
+  }
+  for (unsigned ly : layers) {
+    for (int s = 0; s < nstrips; ++s) pos[s] = -1;
+    for (int i = 0; i < n; ++i)
+      if (all[i].y == ly) pos[all[i].x & 0xffffu] = i;
+    for (int ss = 0; 2 * ss < nstrips; ++ss) {
+      const int a = pos[2 * ss], b = (2 * ss + 1 < nstrips) ? pos[2 * ss + 1] : -1;
+      const int x0 = ss * HP_OWN, bx = x0 - 4;
+      const bool inside = bx >= 0 && bx + HP_BOXW <= h->W && x0 + HP_OWN <= h->W;
+      const bool clean = a >= 0 && b >= 0 && !(all[a].x >> 31) && !(all[b].x >> 31);
+      if (inside && clean) {
+        pair.push_back(make_uint2((unsigned)ss, ly));
+      } else {
+        if (a >= 0) rest.push_back(all[a]);
+        if (b >= 0) rest.push_back(all[b]);
+      }
+    }
+  }
+  // masked items first in the production table (as before); pair items tall-to-short = layer order
+  std::vector<uint2> rest_sorted;
+  for (const uint2 &d : rest) if (d.x >> 31) rest_sorted.push_back(d);
+  for (const uint2 &d : rest) if (!(d.x >> 31)) rest_sorted.push_back(d);
+  if (h->items_pair) TAU_CUDA(cudaFree(h->items_pair));
+  if (h->items_rest) TAU_CUDA(cudaFree(h->items_rest));
+  h->items_pair = h->items_rest = nullptr;
+  TAU_CUDA(cudaMalloc(&h->items_pair, (pair.size() + 1) * sizeof(uint2)));
+  TAU_CUDA(cudaMalloc(&h->items_rest, (rest_sorted.size() + 1) * sizeof(uint2)));
+  TAU_CUDA(cudaMemcpyAsync(h->items_pair, pair.data(), pair.size() * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
+  TAU_CUDA(cudaMemcpyAsync(h->items_rest, rest_sorted.data(), rest_sorted.size() * sizeof(uint2),
+                           cudaMemcpyHostToDevice, h->stream));
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  h->nitems_pair = (int)pair.size();
+  h->nitems_rest = (int)rest_sorted.size();
+  int dev_sms = 148, per_sm = 1;
+  TAU_CUDA(cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, h->device));
+  TAU_CUDA(cudaFuncSetAttribute(hyp2d_step_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes()));
+  TAU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hyp2d_step_pair, H2_WARPS * 32, pair_smem_bytes()));
+  if (per_sm < 1) per_sm = 1;
+  auto grid_for = [&](int items, int cap) {
+    int g = (items + H2_WARPS - 1) / H2_WARPS;
+    if (g > cap) g = cap;
+    return g < 1 ? 1 : g;
+  };
+  h->grid_pair = grid_for(h->nitems_pair, dev_sms * per_sm);
+  h->grid_rest = grid_for(h->nitems_rest, h->grid_ctas);
+  return TAU_OK;
+}
+
+int launch_steps_pair(tau_hyp2d *h, int nsteps, size_t smem) {
+  Params<float> P = make_params<float>(h);
+  P.nitems = h->nitems_rest;
+  for (int s = 0; s < nsteps; ++s) {
+    const int a = h->cur, b = a ^ 1;
+    const int slot = (int)(h->steps % 3);
+    PeerPush peer;
+    memset(&peer, 0, sizeof(peer));
+    peer.pc.world = 1;
+    if (h->peers_attached) {
+      peer.up_out = h->peer_up[b];
+      peer.dn_out = h->peer_dn[b];
+      peer.up_hl = h->peer_up_hl;
+      peer.up_plane = (size_t)h->W * (h->peer_up_hl + 2 * H2_GHOST);
+      peer.dn_plane = (size_t)h->W * (h->peer_dn_hl + 2 * H2_GHOST);
+      peer.pc = h->pctrl;
+    }
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t lc = {};
+    lc.blockDim = dim3(H2_WARPS * 32);
+    lc.stream = h->stream;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    if (h->nitems_pair > 0) {  // interior body-free items first
+      lc.gridDim = dim3((unsigned)h->grid_pair);
+      lc.dynamicSmemBytes = pair_smem_bytes();
+      TAU_CUDA(cudaLaunchKernelEx(&lc, hyp2d_step_pair, h->tm_pair[a], P, (float *)h->U[b],
+                                  (const uint2 *)h->items_pair, h->nitems_pair, h->ctrl, h->pair_ctr, slot, peer));
+      h->launches++;
+    }
+    // everything else + the step's bookkeeping + the multi-GPU message: the production kernel
+    lc.gridDim = dim3((unsigned)h->grid_rest);
+    lc.dynamicSmemBytes = smem;
+    TAU_CUDA(cudaLaunchKernelEx(&lc, hyp2d_step<float, true>, h->tm[a], P, (const float *)h->U[a], (float *)h->U[b],
+                                (const uint8_t *)h->mask, (const uint2 *)h->items_rest, h->ctrl, slot, peer));
+    h->launches++;
+    h->cur = b;
+    h->steps++;
+  }
+  TAU_CUDA(cudaGetLastError());
+  return TAU_OK;
+}
+
 template <typename R>
 int launch_steps(tau_hyp2d *h, int nsteps) {
   const size_t smem = step_smem_bytes<R>();
@@ -1420,8 +1542,15 @@ int launch_steps(tau_hyp2d *h, int nsteps) {
     attr_done[ti][di] = true;
   }
   if (h->items_dirty) {
-    const int rc = build_items<R>(h, smem);
+    int rc = build_items<R>(h, smem);
     if (rc) return rc;
+    if (h->pair_mode) {
+      rc = build_items_pair(h);
+      if (rc) return rc;
+    }
+  }
+  if constexpr (std::is_same<R, float>::value) {
+    if (h->pair_mode) return launch_steps_pair(h, nsteps, smem);
   }
   Params<R> P = make_params<R>(h);
   const int grid = h->grid_ctas;
@@ -1553,6 +1682,12 @@ int tau_hyp2d_create(const tau_hyp2d_config *cfg, int W, int H, int dtype, int d
   memset(&h->pctrl, 0, sizeof(h->pctrl));
   h->pctrl.world = 1;
   h->peers_attached = false;
+  h->pair_mode = false;
+  h->items_pair = h->items_rest = nullptr;
+  h->nitems_pair = h->nitems_rest = 0;
+  h->grid_pair = h->grid_rest = 1;
+  h->pair_ctr = nullptr;
+  memset(h->tm_pair, 0, sizeof(h->tm_pair));
   h->pixels = nullptr;
   h->mmkeys = nullptr;
   h->items = nullptr;
@@ -1611,6 +1746,20 @@ int tau_hyp2d_create(const tau_hyp2d_config *cfg, int W, int H, int dtype, int d
     }
   } else {
     memset(h->tm, 0, sizeof(h->tm));
+  }
+  if (const char *e = getenv("TAU_HYP2D_PAIR")) {  // experimental, see hypersonic2d_pair.cuh
+    if (atoi(e) == 1 && h->use_tma && dtype == 0 && W >= 2 * HP_BOXW) {
+      const uint64_t dims[3] = {(uint64_t)W, (uint64_t)(h_local + 2 * H2_GHOST), 4};
+      const uint64_t strides[2] = {(uint64_t)W * es, (uint64_t)h->plane_elems * es};
+      const uint32_t box[3] = {HP_BOXW, H2_RB, 4};
+      for (int b = 0; b < 2; ++b) {
+        rc = tau_make_tensor_map(&h->tm_pair[b], h->U[b], es, 3, dims, strides, box);
+        if (rc) return rc;
+      }
+      TAU_CUDA(cudaMalloc(&h->pair_ctr, 3 * sizeof(unsigned int)));
+      TAU_CUDA(cudaMemsetAsync(h->pair_ctr, 0, 3 * sizeof(unsigned int), h->stream));
+      h->pair_mode = true;
+    }
   }
   TAU_CUDA(cudaEventCreate(&h->ev0));
   TAU_CUDA(cudaEventCreate(&h->ev1));
@@ -1950,6 +2099,9 @@ int tau_hyp2d_destroy(tau_hyp2d *h) {
   cudaStreamSynchronize(h->stream);
   cudaFree(h->ctrl);
   if (h->items) cudaFree(h->items);
+  if (h->items_pair) cudaFree(h->items_pair);
+  if (h->items_rest) cudaFree(h->items_rest);
+  if (h->pair_ctr) cudaFree(h->pair_ctr);
   if (h->pixels) cudaFree(h->pixels);
   if (h->mmkeys) cudaFree(h->mmkeys);
   cudaFree(h->mask);

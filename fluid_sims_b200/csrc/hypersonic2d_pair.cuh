@@ -1,22 +1,19 @@
-// hyp2d_pair.cu — EXPERIMENTAL, NOT LINKED INTO libtau_b200.so, NOT YET RUN ON HARDWARE.
+// hypersonic2d_pair.cuh — EXPERIMENTAL step kernel, compiled into the library but only launched when
+// TAU_HYP2D_PAIR=1 is set at handle creation.  NOT YET RUN ON HARDWARE (written when the round-1 GPU
+// budget was spent); the default path does not touch it.  Included by hypersonic2d.cu (same
+// translation unit: it uses Params, Ctrl, PeerPush and the scalar helpers).
 //
-// Draft of the "two adjacent columns per lane" formulation of the 2-D hypersonic step for the interior,
-// body-free work items (97 % of the items at 4096^2), written at the end of round 1 when the GPU budget
-// was spent.  Purpose: (1) a compile-checked starting point for the next round, (2) hard static numbers
-// (registers, SASS instructions per marched row pair) for the projection in
-// profiles/hyp2d_pair_probe_r1.md.  Compile-only:
-//
-//   nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xptxas -v \
-//        -c experimental/hyp2d_pair.cu -o /tmp/hyp2d_pair.o        (from fluid_sims_b200/csrc)
-//
-// Design (see the probe note): a warp owns a strip of 60 columns; lane l = 1..30 owns columns
-// x0 + 2(l-1) and +1 as the two halves of a float2 (lanes 0 / 31 hold the halo pairs); arithmetic
-// uses the packed FADD2/FMUL2/FFMA2 of sm_100, everything without a packed form (min/max, compares,
-// selects, MUFU) runs per half.  Intended use: this kernel takes the interior unmasked items, the
-// production kernel (hyp2d_step) is launched right after it on a table holding the masked / edge
-// items, does the step's bookkeeping (sim_t, slot clearing) and sends the multi-GPU message.
-// Everything numerical follows hypersonic2d.cu (same expression trees, FMA contractions spelled out).
-#include "../hypersonic2d.cu"
+// The "two adjacent columns per lane" formulation of the 2-D hypersonic step for the interior,
+// body-free work items (97 % of the items at 4096^2): a warp owns a strip of 60 columns; lane l = 1..30
+// owns columns x0 + 2(l-1) and +1 as the two halves of a float2 (lanes 0 / 31 hold the halo pairs);
+// arithmetic uses the packed FADD2/FMUL2/FFMA2 of sm_100, everything without a packed form (min/max,
+// compares, selects, MUFU) runs per half.  In pair mode this kernel takes the interior unmasked items
+// and the production kernel (hyp2d_step) is launched right after it on the masked / edge items, does the
+// step's bookkeeping (sim_t, slot clearing) and sends the multi-GPU message.  Numerics follow
+// hypersonic2d.cu (same expression trees, FMA contractions spelled out).  Static facts and the
+// projection: profiles/hyp2d_pair_probe_r1.md.
+#pragma once
+
 
 namespace {
 
@@ -474,8 +471,5 @@ hyp2d_step_pair(const __grid_constant__ CUtensorMap tmU, const Params<float> P, 
   if (lane == 0 && wmax > 0.f) tau::atomic_max_nonneg(&ctrl->maxspeed[(step_slot + 1) % 3], (double)wmax);
   if (peer.pc.world > 1 && pushed) __threadfence_system();  // the production kernel (launched next) signals
 }
-
-// force an instantiation for the compile-only study
-void *hyp2d_step_pair_entry() { return (void *)hyp2d_step_pair; }
 
 }  // namespace

@@ -242,6 +242,41 @@ def bench_burgers(a):
                       "gpu_launches": s.launch_count}))
 
 
+def bench_sw(a):
+    """tau_sw n x n (periodic).  Only on request (`bench_all.py sw`): the kernels have not
+    run on hardware yet (NEXT.md).  A gentle field scaled with the grid; nu > 0 (2 kernels per step) as the
+    reference's default."""
+    import oracle
+    from fluid_sims_b200.shallow_water import Params, ShallowWater, initialize_host
+    n = a.sw_n
+    kw = dict(nx=n, ny=n, dtau=1e-3, offx=0.1 * n, offy=0.1 * n, swirlRc=100.0 * n / 512, bumpSigma=8.0 * n / 512)
+    P = Params(**kw)
+    f = initialize_host(P)
+    s = ShallowWater(P).upload(*f)
+    s.step(20)
+    s.sync()
+    s.step(a.steps)
+    ms = s.last_step_ms() / a.steps
+    cells = n * n
+    bytes_per_cell = 24 + (20 if P.nu > 0 else 0)   # update: 3 planes in + 3 out; viscosity: sigma, u, v in, u, v out
+    ach = bytes_per_cell * cells / (ms * 1e-3) / 1e9
+    ref_ms = None
+    if oracle.has_ref("ref_sw") and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        k = min(a.steps, 100)
+        *_, t = oracle.ref_sw_run(oracle.sw_params(**kw), *f, k)
+        ref_ms = t / k
+    print(json.dumps({"bench": "shallow_water", "grid": [n, n], "steps": a.steps, "ms_per_step": ms,
+                      "value": cells / (ms * 1e-3) / 1e6, "unit": "Mcell-updates/s",
+                      "roofline": {"bound": "hbm", "achieved": ach, "peak": peak(), "unit": "GB/s",
+                                   "frac": ach / peak(), "algorithmic_bytes_per_cell": bytes_per_cell,
+                                   "note": "fused flux+update kernel 24 B/cell, viscosity kernel 20 B/cell"},
+                      "reference_gpu": {"ms_per_step": ref_ms,
+                                        "value": cells / (ref_ms * 1e-3) / 1e6 if ref_ms else None,
+                                        "what": "tau_shallow_water.cu kernels recompiled for sm_100a incl. the "
+                                                "per-step D2H of the block maxima"},
+                      "gpu_launches": s.launch_count}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("which", nargs="*", default=[])
@@ -253,10 +288,11 @@ def main():
     ap.add_argument("--sph-n", type=int, default=1 << 21)
     ap.add_argument("--steps-sph", type=int, default=50)
     ap.add_argument("--burgers-n", type=int, default=4096)
+    ap.add_argument("--sw-n", type=int, default=4096)
     a = ap.parse_args()
     which = a.which or ["gs", "hyp3d", "sph"]
     for w in which:
-        {"gs": bench_gs, "hyp3d": bench_hyp3d, "sph": bench_sph, "burgers": bench_burgers}[w](a)
+        {"gs": bench_gs, "hyp3d": bench_hyp3d, "sph": bench_sph, "burgers": bench_burgers, "sw": bench_sw}[w](a)
     # one process group for the whole run (re-initialising NCCL between benches is not reliable)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         import torch.distributed as dist

@@ -334,6 +334,43 @@ long long tau_burgers_launch_count(tau_burgers *h);
 int tau_burgers_last_step_ms(tau_burgers *h, float *ms);
 int tau_burgers_destroy(tau_burgers *h);
 
+/* ------------------------------------------------------------------------------------------ */
+/* 2-D shallow water (reference: tau_shallow_water.cu) — SURVEY.md 8(f) rank 3                 */
+/* NOT YET RUN ON HARDWARE (written after the round-1 GPU budget was spent; see NEXT.md)       */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct tau_sw tau_sw;
+
+/* simulation fields of `struct Params` tau_shallow_water.cu:52-89 (same defaults) */
+typedef struct tau_sw_params {
+  int nx, ny;
+  float dx, dy;
+  float g, f0, nu, H0;
+  float bumpAmp, bumpSigma, CFL;
+  float offx, offy, asym, swirl, swirlRc;
+  float tau0, t0, dtau;
+} tau_sw_params;
+
+void tau_sw_default_params(tau_sw_params *p);
+/* initialize_host :238-277 (host): sigma = log h, u, v of ny*nx floats, index j*nx+i */
+void tau_sw_init_host(const tau_sw_params *p, float *sigma, float *u, float *v);
+/* replaces device_alloc :280-298 (the six flux planes and the block-max buffer are not needed) */
+int tau_sw_create(const tau_sw_params *p, int device, void *stream, tau_sw **out);
+/* initialize_host + H2D :640-655; clock := (t0, tau0) */
+int tau_sw_init(tau_sw *h);
+/* inject caller state; clock2 = {t, tau} or NULL for (t0, tau0) */
+int tau_sw_upload(tau_sw *h, const float *sigma, const float *u, const float *v, const float *clock2);
+/* THE hot path: nsteps x { do_step :669-705; tau += dtau; t *= expf(dtau) :767-768 } — one fused
+ * flux + update kernel (+ one viscosity kernel when nu > 0) per step; dt and the log-time clock on the
+ * device.  viscosity_uv's in-place update (a data race in the reference) is the Jacobi update here. */
+int tau_sw_step(tau_sw *h, int nsteps);
+int tau_sw_clock(tau_sw *h, float *t, float *tau, float *dt_last);
+int tau_sw_download(tau_sw *h, float *sigma, float *u, float *v);
+int tau_sw_sync(tau_sw *h);
+long long tau_sw_steps_done(tau_sw *h);
+long long tau_sw_launch_count(tau_sw *h);
+int tau_sw_last_step_ms(tau_sw *h, float *ms);
+int tau_sw_destroy(tau_sw *h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -584,3 +584,107 @@ def ref_burgers_run(p: BurgersParams, phi_u, phi_v, steps, clock=None, skip_visc
     if rc != 0:
         raise RuntimeError(f"reference burgers run failed with cudaError {rc}")
     return u.reshape(p.shape), v.reshape(p.shape), (float(ck[0]), float(ck[1])), dts[:steps], float(ms.value)
+
+
+# ------------------------------------------------------------------------------------------------
+# Shallow water
+# ------------------------------------------------------------------------------------------------
+class SwParams(C.Structure):
+    """simulation fields of `struct Params` tau_shallow_water.cu:52-89"""
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int)] + [(k, C.c_float) for k in (
+        "dx", "dy", "g", "f0", "nu", "H0", "bumpAmp", "bumpSigma", "CFL", "offx", "offy", "asym", "swirl",
+        "swirlRc", "tau0", "t0", "dtau")]
+
+    def as19(self):
+        return np.array([getattr(self, f[0]) for f in self._fields_], np.float32)
+
+    @property
+    def shape(self):
+        return (self.ny, self.nx)
+
+
+def sw_params(**over) -> SwParams:
+    p = SwParams()
+    lib.oracle_sw_default_params(C.byref(p))
+    for k, v in over.items():
+        setattr(p, k, v)
+    return p
+
+
+def _sw3(p, a, b, c):
+    return tuple(np.array(x, np.float32, order="C", copy=True).ravel() for x in (a, b, c))
+
+
+def sw_init(p: SwParams):
+    lib.oracle_sw_init.argtypes = [C.POINTER(SwParams), f32p, f32p, f32p]
+    lib.oracle_sw_init.restype = None
+    n = p.nx * p.ny
+    s, u, v = (np.zeros(n, np.float32) for _ in range(3))
+    lib.oracle_sw_init(C.byref(p), s, u, v)
+    return s.reshape(p.shape), u.reshape(p.shape), v.reshape(p.shape)
+
+
+def sw_run(p: SwParams, sigma, u, v, steps, clock=None):
+    """CPU oracle: (sigma, u, v, (t, tau), dts)."""
+    lib.oracle_sw_run.argtypes = [C.POINTER(SwParams), f32p, f32p, f32p, C.c_int, f32p, f32p]
+    lib.oracle_sw_run.restype = None
+    s, u, v = _sw3(p, sigma, u, v)
+    ck = np.array(clock if clock is not None else (p.t0, p.tau0), np.float32)
+    dts = np.zeros(max(steps, 1), np.float32)
+    lib.oracle_sw_run(C.byref(p), s, u, v, steps, ck, dts)
+    return s.reshape(p.shape), u.reshape(p.shape), v.reshape(p.shape), (float(ck[0]), float(ck[1])), dts[:steps]
+
+
+def sw_cmax(p: SwParams, sigma, u, v):
+    lib.oracle_sw_cmax.argtypes = [C.POINTER(SwParams), f32p, f32p, f32p]
+    lib.oracle_sw_cmax.restype = C.c_float
+    return float(lib.oracle_sw_cmax(C.byref(p), *_sw3(p, sigma, u, v)))
+
+
+def _ref_sw_init(libname, fn, p):
+    r = ref(libname)
+    f = getattr(r, fn)
+    f.argtypes = [f32p, f32p, f32p, f32p]
+    f.restype = None
+    n = p.nx * p.ny
+    s, u, v = (np.zeros(n, np.float32) for _ in range(3))
+    f(p.as19(), s, u, v)
+    return s.reshape(p.shape), u.reshape(p.shape), v.reshape(p.shape)
+
+
+def ref_sw_host_init(p: SwParams):
+    """the reference's initialize_host, compiled by g++ (no GPU needed)"""
+    return _ref_sw_init("ref_sw_host", "ref_sw_host_init", p)
+
+
+def ref_sw_host_run(p: SwParams, sigma, u, v, steps, clock=None, skip_visc=False):
+    """The reference's own kernel bodies emulated thread by thread on the CPU (oracle/ref_drivers/
+    ref_sw_host.cpp): (sigma, u, v, (t, tau), dts)."""
+    r = ref("ref_sw_host")
+    r.ref_sw_host_run.argtypes = [f32p, f32p, f32p, f32p, C.c_int, f32p, f32p, C.c_int]
+    r.ref_sw_host_run.restype = C.c_int
+    s, u, v = _sw3(p, sigma, u, v)
+    ck = np.array(clock if clock is not None else (p.t0, p.tau0), np.float32)
+    dts = np.zeros(max(steps, 1), np.float32)
+    r.ref_sw_host_run(p.as19(), s, u, v, steps, ck, dts, 1 if skip_visc else 0)
+    return s.reshape(p.shape), u.reshape(p.shape), v.reshape(p.shape), (float(ck[0]), float(ck[1])), dts[:steps]
+
+
+def ref_sw_init(p: SwParams):
+    return _ref_sw_init("ref_sw", "ref_sw_init", p)
+
+
+def ref_sw_run(p: SwParams, sigma, u, v, steps, clock=None, skip_visc=False):
+    """The reference's own kernels on the GPU: (sigma, u, v, (t, tau), dts, ms)."""
+    r = ref("ref_sw")
+    r.ref_sw_run.argtypes = [f32p, f32p, f32p, f32p, C.c_int, f32p, f32p, C.c_int, C.POINTER(C.c_float)]
+    r.ref_sw_run.restype = C.c_int
+    s, u, v = _sw3(p, sigma, u, v)
+    ck = np.array(clock if clock is not None else (p.t0, p.tau0), np.float32)
+    dts = np.zeros(max(steps, 1), np.float32)
+    ms = C.c_float()
+    rc = r.ref_sw_run(p.as19(), s, u, v, steps, ck, dts, 1 if skip_visc else 0, C.byref(ms))
+    if rc != 0:
+        raise RuntimeError(f"reference shallow-water run failed with cudaError {rc}")
+    return (s.reshape(p.shape), u.reshape(p.shape), v.reshape(p.shape), (float(ck[0]), float(ck[1])), dts[:steps],
+            float(ms.value))

@@ -150,6 +150,25 @@ def burgers():
     print("burgers golden written")
 
 
+def sw():
+    # the reference's own shallow-water kernels (nu = 0: no racy viscosity_uv); complements the host-emulated
+    # fixture sw_ref_host.npz (make_golden_host.py) with the -use_fast_math device intrinsics
+    out = {}
+    gentle = dict(H0=2.0, bumpAmp=0.4, bumpSigma=5, asym=0.3, swirl=0.05, swirlRc=10, offx=3, offy=-2)
+    cases = (("a", dict(nx=96, ny=64, dtau=0.02, nu=0.0, **gentle), 40),
+             ("b", dict(nx=70, ny=37, dtau=0.05, nu=0.0, dx=2.0, dy=1.5, **gentle), 25),
+             ("c", dict(nx=96, ny=64, dtau=1e-3, nu=0.0), 10))
+    for tag, kw, steps in cases:
+        prm = oracle.sw_params(**kw)
+        s0, u0, v0 = oracle.ref_sw_init(prm)
+        s, u, v, ck, dts, _ = oracle.ref_sw_run(prm, s0, u0, v0, steps)
+        out.update({f"s0_{tag}": s0, f"u0_{tag}": u0, f"v0_{tag}": v0, f"s_{tag}": s, f"u_{tag}": u, f"v_{tag}": v,
+                    f"clock_{tag}": np.array(ck), f"dts_{tag}": dts, f"p19_{tag}": prm.as19(),
+                    f"steps_{tag}": np.array(steps)})
+    np.savez_compressed(os.path.join(OUT, "sw_ref.npz"), **out)
+    print("shallow-water golden written")
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["gs", "hyp2d", "hyp3d", "sph", "burgers"]
     for w in which:

@@ -82,8 +82,11 @@ def test_cli_hosts_build_and_fail_loudly_without_gpu():
              "tau_2d_hypersonic_cuda": ["--nx", "128", "--ny", "64", "--frames", "2"],
              "tau3d": ["--n", "16", "--frames", "1"],
              "tau_sph": ["--n", "2048", "--frames", "2"],
-             "tau_burgers": ["--nx", "96", "--ny", "64", "--steps", "4", "--headless", "--dtau", "1e-3"]}
+             "tau_burgers": ["--nx", "96", "--ny", "64", "--steps", "4", "--headless", "--dtau", "1e-3"],
+             "tau_sw": ["--nx", "96", "--ny", "64", "--steps", "4", "--headless", "--dtau", "1e-3"]}
     for exe, args in cases.items():
+        if exe == "tau_sw" and device_count() > 0 and os.environ.get("TAU_TEST_SW") != "1":
+            continue    # kernels not yet validated on hardware (tests/test_sw_gpu.py)
         r = subprocess.run([os.path.join(cli, exe)] + args, capture_output=True, text=True, timeout=120)
         if device_count() > 0:
             assert r.returncode == 0, (exe, r.stderr)

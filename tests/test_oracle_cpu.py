@@ -407,3 +407,89 @@ def test_burgers_oracle_matches_reference_golden():
         assert np.abs(u - g[f"u_{tag}"]).max() < tol and np.abs(v - g[f"v_{tag}"]).max() < tol, tag
         assert np.allclose(dts, g[f"dts_{tag}"], rtol=1e-6, atol=0)
         assert abs(ck[0] - g[f"clock_{tag}"][0]) <= 1e-6 * ck[0]
+
+
+# ---- shallow water ----------------------------------------------------------------
+_SW_INTS = ("nx", "ny")
+
+
+def _sw_golden_cases():
+    g = np.load(os.path.join(GOLDEN, "sw_ref_host.npz"))
+    names = [f[0] for f in oracle.SwParams._fields_]
+    for tag in "abcd":
+        kw = {n: (int(v) if n in _SW_INTS else float(v)) for n, v in zip(names, g[f"p19_{tag}"])}
+        yield tag, kw, g
+
+
+def test_sw_oracle_equals_reference_kernel_bodies_golden():
+    """tests/golden/sw_ref_host.npz: outputs of the reference's own initialize_host / flux_x_kernel /
+    flux_y_kernel / update_kernel bodies compiled for the host and emulated thread by thread
+    (oracle/ref_drivers/ref_sw_host.cpp; generator tests/golden/make_golden_host.py).  Same libm, same
+    -ffp-contract=off: the restatement has to be BIT-IDENTICAL, fields, every dt and the clock."""
+    for tag, kw, g in _sw_golden_cases():
+        prm = oracle.sw_params(**kw)
+        s0, u0, v0 = oracle.sw_init(prm)
+        assert np.array_equal(s0, g[f"s0_{tag}"]) and np.array_equal(u0, g[f"u0_{tag}"]) and \
+            np.array_equal(v0, g[f"v0_{tag}"]), tag
+        s, u, v, ck, dts = oracle.sw_run(prm, s0, u0, v0, int(g[f"steps_{tag}"]))
+        assert np.array_equal(s, g[f"s_{tag}"]) and np.array_equal(u, g[f"u_{tag}"]) and \
+            np.array_equal(v, g[f"v_{tag}"]), tag
+        assert np.array_equal(dts, g[f"dts_{tag}"]) and np.array_equal(np.array(ck), g[f"clock_{tag}"]), tag
+        assert np.abs(s - s0).max() > 1e-3          # the case did evolve
+
+
+@pytest.mark.skipif(not oracle.has_ref("ref_sw_host"), reason="oracle/_ref not built")
+def test_sw_oracle_equals_reference_kernel_bodies_live():
+    """the same comparison on fresh sizes (ragged against the 16x16 launch blocks), and with viscosity:
+    viscosity_uv's in-place update, emulated in sequential thread order, against the oracle's Jacobi update"""
+    for kw, steps in ((dict(nx=50, ny=33, nu=0.0, dtau=0.01, H0=20.0, bumpAmp=5.0, bumpSigma=4, offx=2, offy=1,
+                            swirlRc=9, asym=0.5), 30),
+                      (dict(nx=17, ny=16, nu=0.0, dtau=1.0, offx=0, offy=0, swirlRc=3, bumpSigma=2), 25)):
+        prm = oracle.sw_params(**kw)
+        a = oracle.sw_init(prm)
+        assert all(np.array_equal(x, y) for x, y in zip(a, oracle.ref_sw_host_init(prm)))
+        ra, rb = oracle.sw_run(prm, *a, steps), oracle.ref_sw_host_run(prm, *a, steps)
+        assert all(np.array_equal(x, y) for x, y in zip(ra[:3], rb[:3]))
+        assert ra[3] == rb[3] and np.array_equal(ra[4], rb[4])
+    prm = oracle.sw_params(nx=96, ny=64, nu=0.5, dtau=1e-3, offx=5, offy=3, swirlRc=15, bumpSigma=5)
+    a = oracle.sw_init(prm)
+    ra, rb = oracle.sw_run(prm, *a, 50), oracle.ref_sw_host_run(prm, *a, 50)
+    assert np.array_equal(ra[4][:1], rb[4][:1])     # the first dt precedes any viscosity
+    err = max(float(np.abs(x - y).max()) for x, y in zip(ra[:3], rb[:3]))
+    assert 0 < err < 2e-4                            # measured 2.8e-5 with |u| ~ 9
+    rc = oracle.ref_sw_host_run(prm, *a, 50, skip_visc=True)
+    assert max(float(np.abs(x - y).max()) for x, y in zip(rb[:3], rc[:3])) > 10 * err   # viscosity did act
+
+
+def test_sw_oracle_invariants():
+    # lake at rest stays at rest, bit for bit (HLL is exactly consistent; viscosity of a constant is 0)
+    prm = oracle.sw_params(nx=64, ny=48, bumpAmp=0.0, swirl=0.0, nu=0.1, dtau=0.1)
+    a = oracle.sw_init(prm)
+    s, u, v, ck, dts = oracle.sw_run(prm, *a, 20)
+    assert np.array_equal(s, a[0]) and not u.any() and not v.any()
+    # dt rule :679-684: min(t dtau, CFL min(dx,dy)/cmax) with cmax = sqrt(g H0) here; the clock :767-768
+    c = np.sqrt(np.float32(prm.g) * np.exp(a[0][0, 0]))
+    assert abs(oracle.sw_cmax(prm, *a) - c) <= 1e-6 * c
+    t = np.float32(prm.t0)
+    for k in range(20):
+        want = min(np.float32(t * np.float32(prm.dtau)), np.float32(prm.CFL * min(prm.dx, prm.dy)) / np.float32(c))
+        assert abs(dts[k] - want) <= 2e-7 * want
+        t = np.float32(t * np.float32(math.exp(prm.dtau)))
+    assert abs(ck[0] - t) <= 1e-5 * t and abs(ck[1] - 20 * prm.dtau) < 1e-5
+    # mass: flux form conserves sum(h) to rounding (the state is sigma = log h, so not exactly)
+    prm = oracle.sw_params(nx=64, ny=48, H0=10.0, bumpAmp=1.0, bumpSigma=5, asym=0.2, swirl=0.01, swirlRc=10,
+                           offx=0, offy=0, nu=0.0, dtau=0.05)
+    a = oracle.sw_init(prm)
+    s, u, v, _, _ = oracle.sw_run(prm, *a, 100)
+    m0, m1 = np.exp(a[0].astype(np.float64)).sum(), np.exp(s.astype(np.float64)).sum()
+    assert abs(m1 - m0) < 2e-6 * m0 and np.abs(s - a[0]).max() > 1e-3
+    # x <-> y symmetry of the two sweeps: transposing the problem transposes the answer (u <-> v)
+    prm = oracle.sw_params(nx=40, ny=56, dx=1.5, dy=0.75, H0=4.0, nu=0.05, dtau=0.02, bumpAmp=0.0, swirl=0.0)
+    rng = np.random.default_rng(3)
+    s0 = (np.log(4.0) + 0.1 * rng.standard_normal(prm.shape)).astype(np.float32)
+    u0, v0 = (0.3 * rng.standard_normal(prm.shape).astype(np.float32) for _ in range(2))
+    s, u, v, _, d1 = oracle.sw_run(prm, s0, u0, v0, 15)
+    prmT = oracle.sw_params(nx=56, ny=40, dx=0.75, dy=1.5, H0=4.0, nu=0.05, dtau=0.02, bumpAmp=0.0, swirl=0.0)
+    sT, uT, vT, _, d2 = oracle.sw_run(prmT, s0.T.copy(), v0.T.copy(), u0.T.copy(), 15)
+    assert np.array_equal(d1, d2)
+    assert np.abs(sT.T - s).max() < 1e-5 and np.abs(vT.T - u).max() < 1e-5 and np.abs(uT.T - v).max() < 1e-5

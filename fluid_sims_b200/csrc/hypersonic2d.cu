@@ -2063,6 +2063,26 @@ int tau_hyp2d_describe(tau_hyp2d *h, int *W, int *H, int *dtype, int *y_begin, i
   return TAU_OK;
 }
 
+// Sizes of the work-item table(s) the next step will use (builds them if the schedule is stale):
+// out[0] = items of the production kernel's table, out[1] = its persistent grid (CTAs); pair mode:
+// out[2] = 60-column items of the pair kernel, out[3] = items left to the production kernel,
+// out[4] / out[5] = the two grids.  Host bookkeeping only.
+int tau_hyp2d_work_items(tau_hyp2d *h, int out[6]) {
+  TAU_REQUIRE(h && out, "tau_hyp2d_work_items: null argument");
+  TAU_CUDA(cudaSetDevice(h->device));
+  if (h->items_dirty) {  // a zero-step launch sets the kernel attributes and builds the tables
+    const int rc = h->dtype ? launch_steps<double>(h, 0) : launch_steps<float>(h, 0);
+    if (rc) return rc;
+  }
+  out[0] = h->nitems;
+  out[1] = h->grid_ctas;
+  out[2] = h->pair_mode ? h->nitems_pair : 0;
+  out[3] = h->pair_mode ? h->nitems_rest : 0;
+  out[4] = h->pair_mode ? h->grid_pair : 0;
+  out[5] = h->pair_mode ? h->grid_rest : 0;
+  return TAU_OK;
+}
+
 // Restore the device-resident clock after tau_hyp2d_upload (checkpoint/resume).  The step counter
 // only selects the rotating control slot; the max wavespeed of the restored state was re-scanned by
 // the upload, so the next dt equals the one the original run would have taken.

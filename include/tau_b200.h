@@ -148,6 +148,9 @@ int tau_hyp2d_render(tau_hyp2d *h, int view_mode, uint32_t *rgba, double minmax_
 /* grid, dtype, slab and config of a handle (any out pointer may be NULL) */
 int tau_hyp2d_describe(tau_hyp2d *h, int *W, int *H, int *dtype, int *y_begin, int *h_local,
                        tau_hyp2d_config *cfg);
+/* sizes of the work-item table(s) and persistent grids the next step uses (host bookkeeping):
+ * out = {items, grid CTAs, pair-kernel items, items left to the production kernel, pair grid, rest grid} */
+int tau_hyp2d_work_items(tau_hyp2d *h, int out[6]);
 /* restore sim_t and the step counter after tau_hyp2d_upload (checkpoint/resume) */
 int tau_hyp2d_set_clock(tau_hyp2d *h, double sim_t, long long steps_done);
 

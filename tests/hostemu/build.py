@@ -27,7 +27,7 @@ def _split_top(s):
 def cuda_to_host(src: str) -> str:
     src = src.replace('#include "common.cuh"', '#include "hostemu.h"')
     out, pos = "", 0
-    for m in re.finditer(r"(\w+)\s*<<<(.+?)>>>\s*\(", src, flags=re.S):
+    for m in re.finditer(r"(\w+(?:<[^<>;()]*>)?)\s*<<<(.+?)>>>\s*\(", src, flags=re.S):
         if m.start() < pos:
             continue
         cfg = _split_top(m.group(2))
@@ -43,17 +43,100 @@ def cuda_to_host(src: str) -> str:
     return out + src[pos:]
 
 
+_ASM_RULES = (
+    # (ptx prefix, C++ template over outputs o[] and inputs i[])
+    ("rcp.approx.ftz.f32", "{o0} = 1.0f / ({i0});"),
+    ("sqrt.approx.ftz.f32", "{o0} = sqrtf({i0});"),
+    ("mov.u32 %0, %%tid.x", "{o0} = threadIdx.x;"),
+    ("griddepcontrol.", ";"),
+    ("mov.u64 %0, %globaltimer", "{o0} = ++tau_hc::fake_timer;"),
+    ("ld.acquire.sys.global.u64", "{o0} = *(volatile unsigned long long *)({i0});"),
+    ("st.release.sys.global.u64", "*(volatile unsigned long long *)({i0}) = ({i1});"),
+)
+
+
+def _operands(section):
+    # '"=f"(r), "l"(a)' -> ['r', 'a'] (balanced parentheses)
+    ops, i = [], 0
+    while True:
+        m = re.compile(r'"[^"]*"\s*\(').search(section, i)
+        if not m:
+            return ops
+        j, depth = m.end(), 1
+        while depth:
+            depth += {"(": 1, ")": -1}.get(section[j], 0)
+            j += 1
+        ops.append(section[m.end():j - 1].strip())
+        i = j
+
+
+def rewrite_asm(src: str) -> str:
+    """every inline-PTX statement becomes its host equivalent; an unknown one is an error"""
+    out, pos = "", 0
+    for m in re.finditer(r"\basm\s*(?:volatile\s*)?\(", src):
+        if m.start() < pos:
+            continue
+        i, depth, instr = m.end(), 1, False
+        while depth:
+            ch = src[i]
+            if ch == '"' and src[i - 1] != "\\":
+                instr = not instr
+            elif not instr:
+                depth += {"(": 1, ")": -1}.get(ch, 0)
+            i += 1
+        body = src[m.end():i - 1]
+        end = src.index(";", i) + 1
+        # split the body at top-level ':' outside strings
+        parts, curp, instr, depth = [], "", False, 0
+        for k, ch in enumerate(body):
+            if ch == '"' and body[k - 1] != "\\":
+                instr = not instr
+            if not instr:
+                depth += {"(": 1, ")": -1}.get(ch, 0)
+            if ch == ":" and not instr and depth == 0:
+                parts.append(curp)
+                curp = ""
+            else:
+                curp += ch
+        parts.append(curp)
+        ptx = "".join(re.findall(r'"((?:[^"\\]|\\.)*)"', parts[0])).strip()
+        outs = _operands(parts[1]) if len(parts) > 1 else []
+        ins = _operands(parts[2]) if len(parts) > 2 else []
+        for prefix, tmpl in _ASM_RULES:
+            if ptx.startswith(prefix):
+                kw = {f"o{n}": v for n, v in enumerate(outs)}
+                kw.update({f"i{n}": v for n, v in enumerate(ins)})
+                rep = tmpl.format(**kw)
+                break
+        else:
+            raise RuntimeError(f"hostemu: no host equivalent for inline PTX {ptx!r}")
+        out += src[pos:m.start()] + rep
+        pos = end
+    return out + src[pos:]
+
+
+def preprocess(path: str) -> str:
+    text = open(path).read()
+    # local .cuh pieces are inlined (and rewritten the same way)
+    def inline(m):
+        return preprocess(os.path.join(os.path.dirname(path), m.group(1)))
+    text = re.sub(r'#include "(\w+\.cuh)"', lambda m: m.group(0) if m.group(1) == "common.cuh" else inline(m), text)
+    text = re.sub(r"extern\s+__shared__\s+(.*?)(\w+)\[\];", r"__shared__ \1\2[TAU_HC_SMEM_BYTES];", text)
+    return cuda_to_host(rewrite_asm(text))
+
+
 def build(name: str) -> str:
     os.makedirs(OUT, exist_ok=True)
     cu = os.path.join(ROOT, "fluid_sims_b200", "csrc", f"{name}.cu")
     cpp = os.path.join(OUT, f"{name}_host.cpp")
     so = os.path.join(OUT, f"lib{name}_hostemu.so")
     deps = [cu, os.path.join(ROOT, "tests", "hostemu", "hostemu.h"), __file__,
+            os.path.join(ROOT, "fluid_sims_b200", "csrc", "hypersonic2d_pair.cuh"),
             os.path.join(ROOT, "include", "tau_b200.h")]
     if os.path.exists(so) and all(os.path.getmtime(so) > os.path.getmtime(d) for d in deps):
         return so
-    text = cuda_to_host(open(cu).read())
-    assert "<<<" not in text
+    text = preprocess(cu)
+    assert "<<<" not in text and not re.search(r"\basm\s*(volatile\s*)?\(", text)
     # the .cu includes the public header relative to csrc/
     text = text.replace('#include "../../include/tau_b200.h"', f'#include "{os.path.join(ROOT, "include", "tau_b200.h")}"')
     open(cpp, "w").write(text)

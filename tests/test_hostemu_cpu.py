@@ -158,3 +158,109 @@ def test_burgers_product_code_equals_oracle(bglib, kw, steps):
     # burgers.cu evaluates u = u0 sinh(phi) once per tile cell and reuses it, like the oracle: identical
     assert err == 0.0
     assert dt.value == dts[-1] and abs(t.value - eck[0]) <= 1e-6 * eck[0]
+
+
+# ---- 2-D hypersonic solver: the HEADLINE kernel and its experimental two-columns-per-lane variant -----------
+# hypersonic2d.cu runs whole in the emulator: tensor maps + TMA box loads (zero fill), the mbarrier ring,
+# the persistent grid with its device work queue (the pretend device has TAU_HC_SMS x TAU_HC_CTAS_PER_SM
+# resident CTAs), warp-shuffle column marching, the last-CTA-out reduction and the device-side clock.
+# Its 11 inline-PTX statements are replaced by build.py (rcp/sqrt.approx -> exact, %tid -> threadIdx, ...).
+import hyp2d_emu  # noqa: E402  (tests/hostemu)
+
+NAMES = ("rho", "mx", "my", "E")
+
+
+def rel_linf(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(np.abs(a - b).max() / max(1.0, np.abs(b).max()))
+
+
+def _random_state_with_walls(W, H, holes=0.0005):
+    rng = np.random.default_rng(5)
+    yy, xx = np.mgrid[0:H, 0:W]
+    rho = 1.0 + 0.3 * np.sin(xx / 9.0) * np.cos(yy / 7.0)
+    u = 3.0 + 0.5 * np.cos(xx / 11.0)
+    v = 0.7 * np.sin(yy / 5.0)
+    p = 1.0 + 0.2 * np.cos((xx + yy) / 13.0)
+    g = 1.1
+    planes = [rho, rho * u, rho * v, p / (g - 1) + 0.5 * rho * (u * u + v * v)]
+    mask = np.zeros((H, W), np.uint8)
+    mask[40:56, 50:70] = 1
+    mask[0:3, 100:110] = 1          # touches y = 0
+    mask[H - 2:, 20:30] = 1         # touches y = H-1
+    mask[60:64, 0:2] = 1            # touches x = 0
+    mask[10:14, W - 3:] = 1         # touches x = W-1
+    mask[rng.random((H, W)) < holes] = 1
+    return planes, mask
+
+
+@pytest.fixture
+def pretend_device(monkeypatch):
+    def set_(sms, ctas):
+        monkeypatch.setenv("TAU_HC_SMS", str(sms))
+        monkeypatch.setenv("TAU_HC_CTAS_PER_SM", str(ctas))
+    return set_
+
+
+@pytest.mark.parametrize("W,H,steps,seg,sms", [(64, 33, 12, 8, 3), (36, 7, 8, 4, 1), (124, 64, 10, 64, 2),
+                                               (203, 57, 10, None, 3)])   # 203: W*8 % 16 != 0, the non-TMA loader
+def test_hyp2d_production_kernel_f64_equals_oracle(pretend_device, W, H, steps, seg, sms):
+    pretend_device(sms, 2)
+    x0 = min(125.0, W / 3.0)
+    cfg = oracle.hyp2d_cfg(W, H, geom_x0=x0)
+    planes, mask = oracle.hyp2d_init(cfg)
+    ref, t_ref, dts_ref = oracle.hyp2d_run(cfg, planes, mask, steps)
+    out, m, t, dts, _ = hyp2d_emu.run(W, H, steps, "f64", seg_rows=seg, geom_x0=x0)
+    assert np.array_equal(m.ravel(), mask)
+    for k, a, b in zip(NAMES, out, ref):
+        assert rel_linf(a, b) < 1e-12, k          # measured 1e-15 (contraction differs, nothing else)
+    assert abs(t - t_ref) < 1e-13 and np.abs(dts - dts_ref).max() < 1e-15
+
+
+def test_hyp2d_production_kernel_uploaded_state_with_walls(pretend_device):
+    pretend_device(3, 2)
+    W, H, steps = 128, 96, 10
+    planes, mask = _random_state_with_walls(W, H, holes=0.002)
+    ref, t_ref, _ = oracle.hyp2d_run(oracle.hyp2d_cfg(W, H), planes, mask.ravel(), steps)
+    out, _, t, _, _ = hyp2d_emu.run(W, H, steps, "f64", planes=planes, mask=mask)
+    assert max(rel_linf(a, b) for a, b in zip(out, ref)) < 1e-12 and abs(t - t_ref) < 1e-13
+    out, _, t, _, _ = hyp2d_emu.run(W, H, steps, "f32", planes=planes, mask=mask, chunks=[3, 7])
+    assert max(rel_linf(a, b) for a, b in zip(out, ref)) < 5e-6     # measured 1e-6
+
+
+@pytest.mark.parametrize("W,H,steps,seg,sms,ctas", [
+    (308, 96, 25, None, 3, 2),     # guided schedule; 30 pair items + 72 production items
+    (308, 96, 12, 24, 1, 1),       # one resident CTA: every item but the first four comes off the device queue
+    (1000, 40, 8, 8, 16, 2),       # more CTAs than items in the tail: late claims find the queue empty
+    (136, 20, 10, None, 3, 2),     # the narrowest grid pair mode accepts
+])
+def test_hyp2d_pair_kernel_equals_production_kernel(pretend_device, W, H, steps, seg, sms, ctas):
+    """hypersonic2d_pair.cuh (TAU_HYP2D_PAIR=1: two columns per lane, packed fp32x2 arithmetic) has not run
+    on hardware yet.  Here it computes the interior body-free items of a smooth random field with walls, the
+    production kernel the rest, and the result is compared with the production kernel alone (fp32 both:
+    they differ by FMA contraction only) and with the fp64 oracle."""
+    pretend_device(sms, ctas)
+    planes, mask = _random_state_with_walls(W, H) if H >= 64 else (None, None)
+    kw = {} if planes is not None else dict(geom_x0=min(125.0, W / 3.0))
+    if planes is not None:
+        ref, t_ref, _ = oracle.hyp2d_run(oracle.hyp2d_cfg(W, H), planes, mask.ravel(), steps)
+    else:
+        cfg = oracle.hyp2d_cfg(W, H, **kw)
+        p0, m0 = oracle.hyp2d_init(cfg)
+        ref, t_ref, _ = oracle.hyp2d_run(cfg, p0, m0, steps)
+    a, _, ta, dtsa, na = hyp2d_emu.run(W, H, steps, "f32", planes=planes, mask=mask, seg_rows=seg, **kw)
+    b, _, tb, dtsb, nb = hyp2d_emu.run(W, H, steps, "f32", planes=planes, mask=mask, seg_rows=seg, pair=True, **kw)
+    items = hyp2d_emu.run.last_work_items
+    assert items[2] > 0 and items[3] > 0 and nb == na + steps      # the pair kernel did launch, once per step
+    assert max(rel_linf(x, y) for x, y in zip(b, a)) < 2e-6         # measured <= 2.3e-7
+    assert max(rel_linf(x, y) for x, y in zip(b, ref)) < 5e-6       # measured 1.2e-6, same as the production kernel
+    assert np.abs(dtsa - dtsb).max() <= 1e-9 * dtsa.max() and abs(ta - tb) <= 1e-9 * ta
+
+
+def test_hyp2d_pair_mode_declines_what_it_cannot_do(pretend_device):
+    pretend_device(3, 2)
+    for W, H, dtype in ((137, 21, "f32"), (200, 40, "f64"), (120, 40, "f32")):   # no TMA / fp64 / too narrow
+        a, *_ = hyp2d_emu.run(W, H, 4, dtype, geom_x0=W / 3.0)
+        b, *_ = hyp2d_emu.run(W, H, 4, dtype, pair=True, geom_x0=W / 3.0)
+        assert hyp2d_emu.run.last_work_items[2] == 0
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))

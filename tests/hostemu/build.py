@@ -27,7 +27,7 @@ def _split_top(s):
 def cuda_to_host(src: str) -> str:
     src = src.replace('#include "common.cuh"', '#include "hostemu.h"')
     out, pos = "", 0
-    for m in re.finditer(r"(\w+(?:<[^<>;()]*>)?)\s*<<<(.+?)>>>\s*\(", src, flags=re.S):
+    for m in re.finditer(r"(\w+(?:<[^<>;()]*>)?)\s*<<<((?:(?!>>>|<<<).)+?)>>>\s*\(", src, flags=re.S):
         if m.start() < pos:
             continue
         cfg = _split_top(m.group(2))
@@ -122,25 +122,27 @@ def preprocess(path: str) -> str:
         return preprocess(os.path.join(os.path.dirname(path), m.group(1)))
     text = re.sub(r'#include "(\w+\.cuh)"', lambda m: m.group(0) if m.group(1) == "common.cuh" else inline(m), text)
     text = re.sub(r"extern\s+__shared__\s+(.*?)(\w+)\[\];", r"__shared__ \1\2[TAU_HC_SMEM_BYTES];", text)
+    text = re.sub(r"__shared__\s+alignas\((\w+)\)", r"__shared__ __attribute__((aligned(\1)))", text)  # g++: no alignas after static
     return cuda_to_host(rewrite_asm(text))
 
 
-def build(name: str) -> str:
+def build(name: str, defines=(), tag: str = "", contract: str = "off") -> str:
+    """-> path of build/hostemu/lib<name><tag>_hostemu.so (rebuilt when a source is newer)"""
     os.makedirs(OUT, exist_ok=True)
     cu = os.path.join(ROOT, "fluid_sims_b200", "csrc", f"{name}.cu")
-    cpp = os.path.join(OUT, f"{name}_host.cpp")
-    so = os.path.join(OUT, f"lib{name}_hostemu.so")
+    cpp = os.path.join(OUT, f"{name}{tag}_host.cpp")
+    so = os.path.join(OUT, f"lib{name}{tag}_hostemu.so")
     deps = [cu, os.path.join(ROOT, "tests", "hostemu", "hostemu.h"), __file__,
             os.path.join(ROOT, "fluid_sims_b200", "csrc", "hypersonic2d_pair.cuh"),
             os.path.join(ROOT, "include", "tau_b200.h")]
     if os.path.exists(so) and all(os.path.getmtime(so) > os.path.getmtime(d) for d in deps):
         return so
     text = preprocess(cu)
-    assert "<<<" not in text and not re.search(r"\basm\s*(volatile\s*)?\(", text)
+    assert not re.search(r"<<<\s*[^>\s]", text) and not re.search(r"\basm\s*(volatile\s*)?\(", text)
     # the .cu includes the public header relative to csrc/
     text = text.replace('#include "../../include/tau_b200.h"', f'#include "{os.path.join(ROOT, "include", "tau_b200.h")}"')
     open(cpp, "w").write(text)
-    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-mfma", "-ffp-contract=off", "-Wall", "-Wl,-Bsymbolic",
-                    "-Wno-unused-function", "-Wno-unused-variable", "-Wno-unknown-pragmas",
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-mfma", f"-ffp-contract={contract}", "-Wall", "-Wl,-Bsymbolic",
+                    "-Wno-unused-function", "-Wno-unused-variable", "-Wno-unknown-pragmas", *[f"-D{d}" for d in defines],
                     "-I", os.path.join(ROOT, "tests", "hostemu"), cpp, "-o", so, "-lm"], check=True)
     return so

@@ -257,8 +257,29 @@ static inline unsigned __ballot_sync(unsigned, int p) {
   for (unsigned l = 0; l < 32; ++l) r |= (unsigned)tau_hc::warp_buf[par][w][l];
   return r;
 }
-static inline int __all_sync(unsigned m, int p) { return __ballot_sync(m, !p) == 0u; }
-static inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0u; }
+// __activemask() inside divergent code cannot be emulated (fibers have no notion of convergence): it
+// returns 0, and a vote over a mask that is not the full warp answers "not unanimous" without
+// synchronising.  That is exact for the one way the product uses it — an early-out that the general
+// path it skips would decide identically (hypersonic3d.cu hllc: "whole warp supersonic").
+static inline unsigned __activemask() { return 0u; }
+static inline int __all_sync(unsigned m, int p) { return m == 0xffffffffu ? __ballot_sync(m, !p) == 0u : 0; }
+static inline int __any_sync(unsigned m, int p) { return m == 0xffffffffu ? __ballot_sync(m, p) != 0u : (p != 0); }
+static inline unsigned __match_any_sync(unsigned, unsigned long long v) {
+  const unsigned me = (unsigned)tau_hc::cur & 31u, w = (unsigned)tau_hc::cur >> 5;
+  const unsigned par = tau_hc::warp_par[w];
+  tau_hc::shfl(v, me);
+  unsigned r = 0;
+  for (unsigned l = 0; l < tau_hc::warp_live[w] && l < 32; ++l) r |= (tau_hc::warp_buf[par][w][l] == v) << l;
+  return r;
+}
+static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+#define __expf(x) expf(x)   /* glibc declares __expf / __logf itself: macros, not functions */
+#define __logf(x) logf(x)
+static inline float __fdividef(float a, float b) { return a / b; }
+static inline float __frcp_rn(float a) { return 1.0f / a; }
+static inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 static inline long long __double_as_longlong(double d) { long long u; memcpy(&u, &d, 8); return u; }

@@ -1,0 +1,57 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes harness over the product's hypersonic3d.cu run by the CPU fiber
+emulator (see hostemu.h).  `packed=True` builds it with -DT3_PACKED_WENO (the opt-in packed WENO5 pair)."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(__file__))
+import build as hostemu_build  # noqa: E402
+
+_libs = {}
+
+
+def lib(packed=False):
+    if packed not in _libs:
+        L = C.CDLL(hostemu_build.build("hypersonic3d", defines=("T3_PACKED_WENO",), tag="_packed") if packed
+                   else hostemu_build.build("hypersonic3d"))
+        h = C.c_void_p
+        L.tau_hyp3d_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(h)]
+        L.tau_hyp3d_init.argtypes = [h]
+        L.tau_hyp3d_upload.argtypes = [h, C.POINTER(C.c_void_p), C.c_void_p]
+        L.tau_hyp3d_step.argtypes = [h, C.c_int]
+        L.tau_hyp3d_clock.argtypes = [h] + [C.POINTER(C.c_float)] * 4
+        L.tau_hyp3d_download.argtypes = [h, C.POINTER(C.c_void_p), C.c_void_p]
+        L.tau_hyp3d_destroy.argtypes = [h]
+        L.tau_hostemu_last_error.restype = C.c_char_p
+        _libs[packed] = L
+    return _libs[packed]
+
+
+def run(prm, planes, steps, clock, packed=False):
+    """prm: oracle.Hyp3dParams (same layout as tau_hyp3d_params).  -> (planes, solid, (t, d_tau, dt, maxs))"""
+    L = lib(packed)
+
+    def check(rc):
+        if rc != 0:
+            raise RuntimeError(f"rc={rc}: {L.tau_hostemu_last_error().decode()}")
+    h = C.c_void_p()
+    check(L.tau_hyp3d_create(C.byref(prm), 0, 0, prm.nz, None, C.byref(h)))
+    shape = (prm.nz, prm.ny, prm.nx)
+    if planes is None:
+        check(L.tau_hyp3d_init(h))
+    else:
+        arrs = [np.ascontiguousarray(p, np.float32).reshape(shape) for p in planes]
+        ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in arrs])
+        ck = np.array(clock, np.float32)
+        check(L.tau_hyp3d_upload(h, ptrs, C.c_void_p(ck.ctypes.data)))
+    check(L.tau_hyp3d_step(h, steps))
+    out = [np.empty(shape, np.float32) for _ in range(6)]
+    solid = np.empty(shape, np.uint8)
+    ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in out])
+    check(L.tau_hyp3d_download(h, ptrs, C.c_void_p(solid.ctypes.data)))
+    v = [C.c_float() for _ in range(4)]
+    check(L.tau_hyp3d_clock(h, *[C.byref(x) for x in v]))
+    L.tau_hyp3d_destroy(h)
+    return out, solid, tuple(float(x.value) for x in v)

@@ -264,3 +264,109 @@ def test_hyp2d_pair_mode_declines_what_it_cannot_do(pretend_device):
         b, *_ = hyp2d_emu.run(W, H, 4, dtype, pair=True, geom_x0=W / 3.0)
         assert hyp2d_emu.run.last_work_items[2] == 0
         assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+# ---- 3-D hypersonic solver, default build and the opt-in packed WENO5 pair (-DT3_PACKED_WENO) ------------------
+import hyp3d_emu  # noqa: E402  (tests/hostemu)
+
+
+@pytest.fixture(scope="module")
+def developed_3d_flow():
+    prm = oracle.hyp3d_params(32, 28, 20)
+    planes, solid = oracle.hyp3d_init(prm)
+    dev, _, _, _ = oracle.hyp3d_run(prm, planes, solid, 150, (5e-3, 2e-3))   # bow shock formed, |phi_y,z| ~ 1
+    assert min(float(np.abs(a).max()) for a in dev) > 0.5
+    return prm, dev, solid
+
+
+@pytest.mark.parametrize("steps,tol", [(1, dict(f=2e-6, lam=3e-3, zet=5e-4)), (10, dict(f=2e-5, lam=6e-3, zet=5e-3))])
+def test_hyp3d_default_and_packed_weno_builds(developed_3d_flow, steps, tol):
+    """lam / zet (log-type thermodynamic variables) amplify fp32 rounding differences to ~1e-3 within one
+    step at a few cells of the shock layer — the same size on the GPU (tests/test_hyp3d_gpu.py TOL_DEV) —
+    while xi / phi stay at the 1e-7 level; an indexing or pairing mistake would show there at O(0.1).
+    The packed build (never run on hardware) must sit inside the same envelope, against the oracle AND
+    against the default build."""
+    prm, dev, solid = developed_3d_flow
+    clock = (0.012, 2e-3)
+    ref, ck_ref, _, _ = oracle.hyp3d_run(prm, dev, solid, steps, clock)
+    d, sol, ckd = hyp3d_emu.run(prm, dev, steps, clock)
+    p, _, ckp = hyp3d_emu.run(prm, dev, steps, clock, packed=True)
+    assert np.array_equal(sol.ravel(), solid)
+
+    def inside(x, y):
+        e = [float(np.abs(np.asarray(a).ravel() - np.asarray(b).ravel()).max()) for a, b in zip(x, y)]
+        assert max(e[:4]) < tol["f"] and e[4] < tol["lam"] and e[5] < tol["zet"], e
+    inside(d, ref)
+    inside(p, ref)
+    inside(p, d)
+    for ck in (ckd, ckp):
+        assert abs(ck[0] - ck_ref[0]) <= 1e-6 * ck_ref[0] and abs(ck[1] - ck_ref[1]) <= 1e-5 * ck_ref[1]
+
+
+# ---- Gray-Scott and SPH (GPU-validated code; CPU regression checks of the same sources) ----------------------
+class _GsParams(C.Structure):       # tau_gs_params
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int)] + [(k, C.c_float) for k in ("dx", "dt", "Du", "Dv", "feed", "kill")] + \
+               [("seed", C.c_uint)]
+
+
+@pytest.mark.parametrize("nx,ny,steps", [(128, 64, 20), (100, 37, 15), (256, 130, 10), (33, 5, 8)])
+def test_gray_scott_product_code_equals_oracle(nx, ny, steps):
+    """gs_step_tma (TMA 2-D box loads of a tile + halo, mbarrier) where nx*4 % 16 == 0, gs_step_generic
+    otherwise.  The oracle spells the GPU's FMA contraction out (it is bit-exact against the reference kernel
+    on a B200); this build has contraction off, hence a 2-ulp bound instead of equality."""
+    L = C.CDLL(hostemu_build.build("gray_scott"))
+    L.tau_gs_default_params.argtypes = [C.POINTER(_GsParams)]
+    L.tau_gs_create.argtypes = [C.POINTER(_GsParams), C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.tau_gs_upload.argtypes = [C.c_void_p, f32p, f32p]
+    L.tau_gs_step.argtypes = [C.c_void_p, C.c_int]
+    L.tau_gs_download.argtypes = [C.c_void_p, f32p, f32p]
+    L.tau_gs_destroy.argtypes = [C.c_void_p]
+    p = _GsParams()
+    L.tau_gs_default_params(C.byref(p))
+    p.nx, p.ny = nx, ny
+    u0, v0 = oracle.gs_init_pattern(nx, ny)
+    h = C.c_void_p()
+    assert L.tau_gs_create(C.byref(p), 0, 0, ny, None, C.byref(h)) == 0
+    assert L.tau_gs_upload(h, u0.ravel(), v0.ravel()) == 0 and L.tau_gs_step(h, steps) == 0
+    u, v = np.empty(nx * ny, np.float32), np.empty(nx * ny, np.float32)
+    assert L.tau_gs_download(h, u, v) == 0
+    L.tau_gs_destroy(h)
+    eu, ev = oracle.gs_run(u0, v0, steps, Du=p.Du, Dv=p.Dv, dt=p.dt, dx=p.dx, feed=p.feed, kill=p.kill)
+    assert np.abs(u.reshape(ny, nx) - eu).max() < 1e-6 and np.abs(v.reshape(ny, nx) - ev).max() < 1e-6
+    assert np.abs(eu - u0).max() > 1e-3
+
+
+@pytest.mark.parametrize("N,frames,over", [(2048, 3, {}), (3000, 2, dict(useXSPH=1)),
+                                           (4096, 2, dict(rain=0, viscSub=2))])
+def test_sph_product_code_equals_oracle(N, frames, over):
+    """the whole sub-step: cell keys, the hand-written LSD radix sort (__match_any_sync digit ranking, tile
+    scans), cell ranges, density, forces + integration, XSPH, rain, tau-clock"""
+    L = C.CDLL(hostemu_build.build("sph"))
+    P = C.POINTER(oracle.SphParams)
+    u32p = oracle.u32p
+    L.tau_sph_reset_particles.argtypes = [P, f32p, f32p]
+    L.tau_sph_create.argtypes = [P, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    L.tau_sph_upload.argtypes = [C.c_void_p, f32p, f32p]
+    L.tau_sph_step.argtypes = [C.c_void_p, C.c_int]
+    L.tau_sph_download.argtypes = [C.c_void_p, f32p, f32p, f32p, f32p]
+    L.tau_sph_download_sort.argtypes = [C.c_void_p, u32p, u32p]
+    L.tau_sph_clock.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_longlong)]
+    L.tau_sph_destroy.argtypes = [C.c_void_p]
+    p = oracle.sph_params(N, **over)
+    pos, vel = np.zeros(2 * N, np.float32), np.zeros(2 * N, np.float32)
+    L.tau_sph_reset_particles(C.byref(p), pos, vel)
+    h = C.c_void_p()
+    assert L.tau_sph_create(C.byref(p), 0, None, C.byref(h)) == 0
+    assert L.tau_sph_upload(h, pos, vel) == 0 and L.tau_sph_step(h, frames) == 0
+    po, ve, s, pr = np.zeros(2 * N, np.float32), np.zeros(2 * N, np.float32), np.zeros(N, np.float32), np.zeros(N, np.float32)
+    assert L.tau_sph_download(h, po, ve, s, pr) == 0
+    k, v = np.zeros(N, np.uint32), np.zeros(N, np.uint32)
+    assert L.tau_sph_download_sort(h, k, v) == 0
+    t, tau, st = C.c_float(), C.c_float(), C.c_longlong()
+    L.tau_sph_clock(h, C.byref(t), C.byref(tau), C.byref(st))
+    L.tau_sph_destroy(h)
+    epos, evel, _, es, epr, ck = oracle.sph_run(p, pos, vel, frames)
+    assert np.abs(po.reshape(-1, 2) - epos).max() < 1e-6 and np.abs(ve.reshape(-1, 2) - evel).max() < 1e-5
+    assert np.abs(s - es).max() < 1e-5 and np.abs(pr - epr).max() < 1e-5      # measured 1-2e-6
+    assert t.value == ck.t and st.value == ck.step
+    assert np.all(np.diff(k.astype(np.int64)) >= 0) and np.array_equal(np.sort(v), np.arange(N, dtype=np.uint32))

@@ -2117,6 +2117,14 @@ int tau_hyp2d_destroy(tau_hyp2d *h) {
   if (!h) return TAU_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
+  if (h->peers_attached) {  // unmap what tau_hyp2d_ipc_attach opened (the peers free their own memory)
+    for (int b = 0; b < 2; ++b) {
+      if (h->peer_up[b]) cudaIpcCloseMemHandle(h->peer_up[b]);
+      if (h->peer_dn[b]) cudaIpcCloseMemHandle(h->peer_dn[b]);
+    }
+    for (int p = 0; p < h->pctrl.world; ++p)
+      if (p != h->pctrl.rank && h->pctrl.ctrl[p]) cudaIpcCloseMemHandle(h->pctrl.ctrl[p]);
+  }
   cudaFree(h->ctrl);
   if (h->items) cudaFree(h->items);
   if (h->items_pair) cudaFree(h->items_pair);

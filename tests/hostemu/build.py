@@ -119,7 +119,7 @@ def preprocess(path: str) -> str:
     text = open(path).read()
     # local .cuh pieces are inlined (and rewritten the same way)
     def inline(m):
-        return preprocess(os.path.join(os.path.dirname(path), m.group(1)))
+        return preprocess(os.path.join(os.path.dirname(path), m.group(1))).replace("#pragma once", "")
     text = re.sub(r'#include "(\w+\.cuh)"', lambda m: m.group(0) if m.group(1) == "common.cuh" else inline(m), text)
     text = re.sub(r"extern\s+__shared__\s+(.*?)(\w+)\[\];", r"__shared__ \1\2[TAU_HC_SMEM_BYTES];", text)
     text = re.sub(r"__shared__\s+alignas\((\w+)\)", r"__shared__ __attribute__((aligned(\1)))", text)  # g++: no alignas after static
@@ -143,6 +143,7 @@ def build(name: str, defines=(), tag: str = "", contract: str = "off") -> str:
     text = text.replace('#include "../../include/tau_b200.h"', f'#include "{os.path.join(ROOT, "include", "tau_b200.h")}"')
     open(cpp, "w").write(text)
     subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-mfma", f"-ffp-contract={contract}", "-Wall", "-Wl,-Bsymbolic",
-                    "-Wno-unused-function", "-Wno-unused-variable", "-Wno-unknown-pragmas", *[f"-D{d}" for d in defines],
+                    "-Wno-unused-function", "-Wno-unused-variable", "-Wno-unknown-pragmas", "-Wno-return-type",  # gcc 13 misreads `if constexpr … else return` in lambdas
+                    *[f"-D{d}" for d in defines],
                     "-I", os.path.join(ROOT, "tests", "hostemu"), cpp, "-o", so, "-lm"], check=True)
     return so

@@ -359,12 +359,23 @@ static inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t *lc, void 
   tau_hc::launch(lc->gridDim, lc->blockDim, [&] { k(a...); });
   return cudaSuccess;
 }
-// CUDA IPC (multi-GPU peer memory) is not emulated
+// CUDA IPC: every "device" lives in this process, so a handle is the pointer itself.  Several handles
+// stepped in turn by one host thread emulate one-process-per-GPU peers (tests/hostemu/hyp2d_emu.py).
 struct cudaIpcMemHandle_t { char reserved[64]; };
 enum { cudaIpcMemLazyEnablePeerAccess = 1 };
-static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return 801; }
-static inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned) { return 801; }
-static inline cudaError_t cudaIpcCloseMemHandle(void *) { return 801; }
+static long long tau_hc_ipc_open = 0;
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) {
+  memset(h, 0, sizeof(*h));
+  memcpy(h->reserved, &p, sizeof(p));
+  return cudaSuccess;
+}
+static inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) {
+  memcpy(p, h.reserved, sizeof(*p));
+  tau_hc_ipc_open++;
+  return *p ? cudaSuccess : 1;
+}
+static inline cudaError_t cudaIpcCloseMemHandle(void *) { tau_hc_ipc_open--; return cudaSuccess; }
+extern "C" long long tau_hostemu_ipc_open_mappings(void) { return tau_hc_ipc_open; }
 
 // ---- tensor maps, TMA tile loads, mbarriers (common.cuh:50-113, common.cu) ------------------------------
 struct CUtensorMap {

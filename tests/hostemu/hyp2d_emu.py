@@ -88,3 +88,85 @@ def run(W, H, steps, dtype, planes=None, mask=None, seg_rows=None, pair=False, c
     n = L.tau_hyp2d_launch_count(h)
     L.tau_hyp2d_destroy(h)
     return out, m, t.value, np.array(dts), n
+
+
+def run_slabs(W, H, steps, dtype, world, pair=False, **over):
+    """`world` y-slab handles in ONE process, stepped in turn: the emulated counterpart of one process per
+    GPU with CUDA-IPC peers (fluid_sims_b200/slab.py: hyp2d_sync_state + hyp2d_attach_peers).  Each rank's
+    step kernel pushes its boundary rows into the neighbours' ghost rows and sends its max wavespeed to
+    every peer's inbox; the next step's kernel polls the inbox.  -> (planes, mask, sim_t per rank, open IPC
+    mappings after destroy)"""
+    L = lib()
+    L.tau_hyp2d_device_state.argtypes = [C.c_void_p] + [C.POINTER(C.c_void_p)] * 3
+    L.tau_hyp2d_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.tau_hyp2d_ipc_attach.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    L.tau_hyp2d_peers_ready.argtypes = [C.c_void_p]
+    L.tau_hostemu_ipc_open_mappings.restype = C.c_longlong
+    npdt = np.float32 if dtype == "f32" else np.float64
+    cc = default_cfg(W, H, **over)
+    base, rem = divmod(H, world)
+    parts, y = [], 0
+    for r in range(world):
+        hl = base + (r < rem)
+        parts.append((y, hl))
+        y += hl
+    os.environ.pop("TAU_HYP2D_PAIR", None)
+    if pair:
+        os.environ["TAU_HYP2D_PAIR"] = "1"
+    hs = []
+    try:
+        for y0, hl in parts:
+            h = C.c_void_p()
+            check(L.tau_hyp2d_create(C.byref(cc), W, H, 0 if dtype == "f32" else 1, 0, y0, hl, None, C.byref(h)))
+            check(L.tau_hyp2d_init(h))
+            hs.append(h)
+    finally:
+        os.environ.pop("TAU_HYP2D_PAIR", None)
+    # hyp2d_sync_state: ghost rows of the mask and of the current planes, max of the wavespeed slot
+    views = []
+    for h, (y0, hl) in zip(hs, parts):
+        pp, mp, sp = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(L.tau_hyp2d_device_state(h, C.byref(pp), C.byref(mp), C.byref(sp)))
+        planes = np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_float if dtype == "f32" else C.c_double)),
+                                       shape=(4, hl + 4, W))
+        mask = np.ctypeslib.as_array(C.cast(mp, C.POINTER(C.c_uint8)), shape=(hl + 4, W))
+        speed = np.ctypeslib.as_array(C.cast(sp, C.POINTER(C.c_double)), shape=(1,))
+        views.append((planes, mask, speed))
+    for r in range(world - 1):
+        (pu, mu, _), (pd, md, _) = views[r], views[r + 1]
+        hu = parts[r][1]
+        pd[:, 0:2] = pu[:, hu:hu + 2]
+        md[0:2] = mu[hu:hu + 2]
+        pu[:, hu + 2:hu + 4] = pd[:, 2:4]
+        mu[hu + 2:hu + 4] = md[2:4]
+    smax = max(float(v[2][0]) for v in views)
+    for v in views:
+        v[2][0] = smax
+    # hyp2d_attach_peers
+    blob = b""
+    for h in hs:
+        buf = C.create_string_buffer(192)
+        check(L.tau_hyp2d_ipc_export(h, buf, 192))
+        blob += buf.raw
+    hl_arr = (C.c_int * world)(*[p[1] for p in parts])
+    for r, h in enumerate(hs):
+        check(L.tau_hyp2d_ipc_attach(h, r, world, blob, hl_arr))
+        check(L.tau_hyp2d_peers_ready(h))
+    for _ in range(steps):
+        for h in hs:
+            check(L.tau_hyp2d_step(h, 1))
+    outs, masks, ts = [], [], []
+    for h, (y0, hl) in zip(hs, parts):
+        out = [np.empty((hl, W), npdt) for _ in range(4)]
+        m = np.empty((hl, W), np.uint8)
+        ptrs = (C.c_void_p * 4)(*[a.ctypes.data for a in out])
+        check(L.tau_hyp2d_download(h, ptrs, C.c_void_p(m.ctypes.data)))
+        t, dt = C.c_double(), C.c_double()
+        check(L.tau_hyp2d_clock(h, C.byref(t), C.byref(dt)))
+        outs.append(out)
+        masks.append(m)
+        ts.append(t.value)
+    for h in hs:
+        L.tau_hyp2d_destroy(h)
+    planes = [np.concatenate([o[k] for o in outs], axis=0) for k in range(4)]
+    return planes, np.concatenate(masks, axis=0), ts, int(L.tau_hostemu_ipc_open_mappings())

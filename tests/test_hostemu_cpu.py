@@ -370,3 +370,30 @@ def test_sph_product_code_equals_oracle(N, frames, over):
     assert np.abs(s - es).max() < 1e-5 and np.abs(pr - epr).max() < 1e-5      # measured 1-2e-6
     assert t.value == ck.t and st.value == ck.step
     assert np.all(np.diff(k.astype(np.int64)) >= 0) and np.array_equal(np.sort(v), np.arange(N, dtype=np.uint32))
+
+
+@pytest.mark.parametrize("dtype,world", [("f64", 2), ("f64", 3), ("f32", 3)])
+def test_hyp2d_device_side_slab_exchange_is_bit_identical_to_one_domain(pretend_device, dtype, world):
+    """The multi-GPU protocol of the 2-D solver with `world` handles in one process standing in for one
+    process per GPU (CUDA IPC emulated as plain pointers): every step kernel pushes its boundary rows into
+    the neighbours' ghost rows, sends its max wavespeed to every peer's inbox with one store, and the next
+    step polls the inbox — no host exchange after the initial hyp2d_sync_state.  Bit-identical to the
+    single-domain run (as measured on 2/4/8 B200s), and tau_hyp2d_destroy unmaps what ipc_attach opened."""
+    pretend_device(3, 2)
+    W, H, steps = 200, 120, 12
+    a, m, t, _, _ = hyp2d_emu.run(W, H, steps, dtype, geom_x0=W / 3.0)
+    b, mb, ts, open_mappings = hyp2d_emu.run_slabs(W, H, steps, dtype, world, geom_x0=W / 3.0)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and np.array_equal(m, mb)
+    assert all(tt == t for tt in ts) and open_mappings == 0
+
+
+def test_hyp2d_pair_kernel_in_slab_mode(pretend_device):
+    """pair kernel first, production kernel second (it owns the step's bookkeeping and the peer message);
+    both push boundary rows.  Different items go to the pair kernel than in the single-domain run, so the
+    comparison is to rounding (FMA contraction), not bit for bit."""
+    pretend_device(3, 2)
+    W, H, steps = 200, 120, 12
+    a, _, t, _, _ = hyp2d_emu.run(W, H, steps, "f32", geom_x0=W / 3.0)
+    b, _, ts, open_mappings = hyp2d_emu.run_slabs(W, H, steps, "f32", 2, pair=True, geom_x0=W / 3.0)
+    assert max(rel_linf(x, y) for x, y in zip(b, a)) < 2e-6 and all(abs(tt - t) <= 1e-9 * t for tt in ts)
+    assert open_mappings == 0

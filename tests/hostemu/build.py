@@ -126,7 +126,7 @@ def preprocess(path: str) -> str:
     return cuda_to_host(rewrite_asm(text))
 
 
-def build(name: str, defines=(), tag: str = "", contract: str = "off") -> str:
+def build(name: str, defines=(), tag: str = "", contract: str = "off", sanitize: bool = False) -> str:
     """-> path of build/hostemu/lib<name><tag>_hostemu.so (rebuilt when a source is newer)"""
     os.makedirs(OUT, exist_ok=True)
     cu = os.path.join(ROOT, "fluid_sims_b200", "csrc", f"{name}.cu")
@@ -145,5 +145,6 @@ def build(name: str, defines=(), tag: str = "", contract: str = "off") -> str:
     subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-mfma", f"-ffp-contract={contract}", "-Wall", "-Wl,-Bsymbolic",
                     "-Wno-unused-function", "-Wno-unused-variable", "-Wno-unknown-pragmas", "-Wno-return-type",  # gcc 13 misreads `if constexpr … else return` in lambdas
                     *[f"-D{d}" for d in defines],
+                    *(["-fsanitize=alignment,bounds", "-fno-sanitize-recover=all", "-g"] if sanitize else []),
                     "-I", os.path.join(ROOT, "tests", "hostemu"), cpp, "-o", so, "-lm"], check=True)
     return so

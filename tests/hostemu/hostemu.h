@@ -49,12 +49,14 @@ struct dim3 {
   unsigned x, y, z;
   dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
-struct float2 { float x, y; };
-struct float4 { float x, y, z, w; };
-struct double2 { double x, y; };
-struct uint2 { unsigned x, y; };
-struct int2 { int x, y; };
-struct uchar4 { unsigned char x, y, z, w; };
+// CUDA's alignments: a misaligned vector access faults on the GPU; built with -fsanitize=alignment
+// (build.py sanitize=True) the emulated run reports it
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(16) double2 { double x, y; };
+struct alignas(8) uint2 { unsigned x, y; };
+struct alignas(8) int2 { int x, y; };
+struct alignas(4) uchar4 { unsigned char x, y, z, w; };
 static inline uchar4 make_uchar4(unsigned char x, unsigned char y, unsigned char z, unsigned char w) { return {x, y, z, w}; }
 static inline float2 make_float2(float x, float y) { return {x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return {x, y, z, w}; }
@@ -301,12 +303,40 @@ typedef struct tau_hc_event *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 enum { cudaStreamNonBlocking = 1 };
 static inline const char *cudaGetErrorString(cudaError_t) { return "hostemu"; }
+// "device" allocations: garbage-filled (reads before writes show up), 256-byte aligned like cudaMalloc's,
+// with a guard zone on either side that cudaFree verifies (out-of-bounds WRITES of a kernel abort the run)
+constexpr size_t TAU_HC_GUARD = 4096;
+struct tau_hc_alloc { char *raw; size_t n; };
+static std::vector<std::pair<void *, tau_hc_alloc>> tau_hc_allocs;
 template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) {
-  *p = (T *)malloc(n ? n : 1);
-  if (*p) memset(*p, 0xCB, n);   // garbage, like fresh device memory: reads before writes show up
-  return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+  char *raw = (char *)aligned_alloc(256, ((n + 2 * TAU_HC_GUARD + 255) / 256) * 256);
+  if (!raw) { *p = nullptr; return cudaErrorMemoryAllocation; }
+  memset(raw, 0xA5, TAU_HC_GUARD);
+  memset(raw + TAU_HC_GUARD, 0xCB, n);
+  memset(raw + TAU_HC_GUARD + n, 0xA5, TAU_HC_GUARD);
+  *p = (T *)(raw + TAU_HC_GUARD);
+  tau_hc_allocs.push_back({(void *)*p, {raw, n}});
+  return cudaSuccess;
 }
-static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaFree(void *p) {
+  if (!p) return cudaSuccess;
+  for (size_t i = 0; i < tau_hc_allocs.size(); ++i)
+    if (tau_hc_allocs[i].first == p) {
+      const tau_hc_alloc a = tau_hc_allocs[i].second;
+      for (size_t k = 0; k < TAU_HC_GUARD; ++k)
+        if ((unsigned char)a.raw[k] != 0xA5 || (unsigned char)a.raw[TAU_HC_GUARD + a.n + k] != 0xA5) {
+          fprintf(stderr, "hostemu: out-of-bounds write next to a %zu-byte device allocation (%s it, offset %zu)\n",
+                  a.n, (unsigned char)a.raw[k] != 0xA5 ? "before" : "after", k);
+          abort();
+        }
+      free(a.raw);
+      tau_hc_allocs.erase(tau_hc_allocs.begin() + i);
+      return cudaSuccess;
+    }
+  fprintf(stderr, "hostemu: cudaFree of a pointer cudaMalloc did not return\n");
+  abort();
+}
+extern "C" long long tau_hostemu_live_allocations(void) { return (long long)tau_hc_allocs.size(); }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) {
   memmove(d, s, n);
   return cudaSuccess;

@@ -17,7 +17,8 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        L = C.CDLL(hostemu_build.build("hypersonic2d"))
+        san = os.environ.get("TAU_HC_SANITIZE") == "1"   # UBSan alignment + bounds build (run it in a subprocess)
+        L = C.CDLL(hostemu_build.build("hypersonic2d", tag="_san" if san else "", sanitize=san))
         h = C.c_void_p
         L.tau_hyp2d_default_config.argtypes = [C.POINTER(_CConfig), C.c_int, C.c_int]
         L.tau_hyp2d_default_config.restype = None

@@ -397,3 +397,14 @@ def test_hyp2d_pair_kernel_in_slab_mode(pretend_device):
     b, _, ts, open_mappings = hyp2d_emu.run_slabs(W, H, steps, "f32", 2, pair=True, geom_x0=W / 3.0)
     assert max(rel_linf(x, y) for x, y in zip(b, a)) < 2e-6 and all(abs(tt - t) <= 1e-9 * t for tt in ts)
     assert open_mappings == 0
+
+
+def test_hyp2d_vector_accesses_are_aligned_and_in_bounds():
+    """UBSan (alignment, bounds) build of the emulated 2-D solver — production, pair and slab modes — in a
+    subprocess (a report aborts it).  float2 / uint2 carry CUDA's alignment in the emulator's headers."""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(__file__), "hostemu", "sanitized_run.py")],
+                       capture_output=True, text=True, timeout=600)
+    if r.returncode != 0 and "cannot find -lubsan" in r.stderr:
+        pytest.skip("libubsan not available")
+    assert r.returncode == 0 and "sanitized run clean" in r.stdout, r.stderr[-2000:]

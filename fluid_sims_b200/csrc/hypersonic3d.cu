@@ -636,8 +636,59 @@ hyp3d_vis(const Par P, const float *__restrict__ in, const uint8_t *__restrict__
     out[i] = 0.5f * (Om2 - Sm2);
     return;
   }
+  if (mode == 8) {  // th3cs.cu k_schlieren_export :641-673: the same quantity, divisions instead of 0.5f/d factors
+    const float ex = (s_r[xp] - s_r[xm]) / (2.0f * P.dx), ey = (s_r[yp] - s_r[ym]) / (2.0f * P.dy),
+                ez = (s_r[zp] - s_r[zm]) / (2.0f * P.dz);
+    out[i] = sqrtf(ex * ex + ey * ey + ez * ez);
+    return;
+  }
   const float drdx = (s_r[xp] - s_r[xm]) * inv2dx, drdy = (s_r[yp] - s_r[ym]) * inv2dy, drdz = (s_r[zp] - s_r[zm]) * inv2dz;
   out[i] = sqrtf(drdx * drdx + drdy * drdy + drdz * drdz);             // VIS_SCHLIEREN_RHO (mode 0)
+}
+
+// ---- .4spl frame export (th3cs.cu main :1193-1222): the reference copies the whole schlieren volume to the
+// host (4 B/voxel), takes min/max there and quantises every voxel with powf on the host.  Here: min/max by
+// warp shuffle + ordered-integer atomics, the 8-bit palette index on the device, 1 B/voxel over PCIe.
+// (int)(powf(norm, 0.65f) * 255.0f) is a monotone step function of norm, so the index is "how many of its
+// 255 steps lie at or below norm": the step positions come from the HOST's powf (export_thresholds below),
+// which makes the device result identical to the reference's host loop by construction.
+__device__ __forceinline__ unsigned f32_key(float f) {      // order-preserving map float -> unsigned
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_unkey(unsigned k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+__global__ void __launch_bounds__(256) hyp3d_export_minmax(const float *__restrict__ v, size_t n, unsigned *keys) {
+  float lo = 1e30f, hi = -1e30f;                            // the reference's start values :1200
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    lo = fminf(lo, v[i]);
+    hi = fmaxf(hi, v[i]);
+  }
+  hi = tau::warp_max(hi);
+  lo = -tau::warp_max(-lo);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&keys[0], f32_key(lo));
+    atomicMax(&keys[1], f32_key(hi));
+  }
+}
+__global__ void __launch_bounds__(256)
+hyp3d_export_quantize(const float *__restrict__ v, size_t n, const unsigned *__restrict__ keys,
+                      const float *__restrict__ thr, uint8_t *__restrict__ out) {
+  __shared__ float s_thr[256];
+  s_thr[threadIdx.x] = threadIdx.x ? thr[threadIdx.x - 1] : 0.f;   // s_thr[k] = first norm with index >= k
+  __syncthreads();
+  const float vmin = f32_unkey(keys[0]), vmax = f32_unkey(keys[1]);
+  const float range = fmaxf(vmax - vmin, 1e-12f);                   // :1205
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float norm = (v[i] - vmin) / range;                       // :1212 (IEEE division: this TU has no fast-math)
+    int lo = 0, hi = 256;                                           // largest k with s_thr[k] <= norm
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_thr[mid] <= norm) lo = mid; else hi = mid;
+    }
+    out[i] = (uint8_t)lo;                                           // NaN compares false everywhere -> 0
+  }
 }
 
 constexpr size_t T3_SMEM = (size_t)(6 * T3_SVOL + 6 * T3_NF) * sizeof(float) + ((T3_SVOL + 15) / 16) * 16;
@@ -659,6 +710,9 @@ struct tau_hyp3d {
   cudaEvent_t ev0, ev1;
   bool timed, have_state;
   float *vis;        // diagnostic field (device), allocated on first use
+  uint8_t *ex_idx;   // .4spl frame export: palette indices, min/max keys, quantiser steps (device)
+  unsigned *ex_keys;
+  float *ex_thr;
 };
 
 namespace {
@@ -715,6 +769,9 @@ int tau_hyp3d_create(const tau_hyp3d_params *p, int device, int z_begin, int nz_
   h->nz_local = nz_local;
   h->slab = (nz_local != p->nz);
   h->vis = nullptr;
+  h->ex_idx = nullptr;
+  h->ex_keys = nullptr;
+  h->ex_thr = nullptr;
   h->cur = 0;
   h->steps = h->launches = 0;
   h->timed = h->have_state = false;
@@ -864,7 +921,7 @@ int tau_hyp3d_download(tau_hyp3d *h, float *const planes[6], uint8_t *solid) {
 // for the z-neighbours: exchange them first.
 int tau_hyp3d_vis(tau_hyp3d *h, int mode, float *out) {
   TAU_REQUIRE(h && out, "tau_hyp3d_vis: null argument");
-  TAU_REQUIRE(mode >= 0 && mode <= 7, "tau_hyp3d_vis: mode %d not in [0, 7]", mode);
+  TAU_REQUIRE(mode >= 0 && mode <= 8, "tau_hyp3d_vis: mode %d not in [0, 8]", mode);
   TAU_REQUIRE(h->have_state, "tau_hyp3d_vis: no state (call tau_hyp3d_init or tau_hyp3d_upload)");
   TAU_CUDA(cudaSetDevice(h->device));
   const size_t n = (size_t)h->prm.nx * h->prm.ny * h->nz_local;
@@ -876,6 +933,64 @@ int tau_hyp3d_vis(tau_hyp3d *h, int mode, float *out) {
   TAU_CUDA(cudaGetLastError());
   TAU_CUDA(cudaMemcpyAsync(out, h->vis, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
   TAU_CUDA(cudaStreamSynchronize(h->stream));
+  return TAU_OK;
+}
+
+// The palette index the reference computes on the host, as a function of norm :1215-1218
+static int export_index_host(float norm) {
+  const float g = powf(norm, 0.65f);
+  int p = (int)(g * 255.0f);
+  return p < 0 ? 0 : (p > 255 ? 255 : p);
+}
+// thr[k-1] = the smallest float norm in [0, 1] whose index is >= k (k = 1..255), by bisection over the
+// float bit patterns (non-negative floats order like their bits) with the host's own powf.
+void tau_4spl_index_thresholds(float thr[255]) {
+  for (int k = 1; k <= 255; ++k) {
+    uint32_t lo = 0u, hi = 0x3f800000u;  // index(0) = 0 < k <= index(1) = 255
+    while (hi - lo > 1u) {
+      const uint32_t mid = lo + (hi - lo) / 2u;
+      float x;
+      memcpy(&x, &mid, 4);
+      if (export_index_host(x) >= k) hi = mid; else lo = mid;
+    }
+    memcpy(&thr[k - 1], &hi, 4);
+  }
+}
+
+// one frame of th3cs.cu's export loop :1193-1222: schlieren field -> min/max -> 8-bit palette indices
+int tau_hyp3d_export_frame(tau_hyp3d *h, uint8_t *indices, float minmax[2]) {
+  TAU_REQUIRE(h && indices, "tau_hyp3d_export_frame: null argument");
+  TAU_REQUIRE(h->have_state, "tau_hyp3d_export_frame: no state (call tau_hyp3d_init or tau_hyp3d_upload)");
+  TAU_CUDA(cudaSetDevice(h->device));
+  const size_t n = (size_t)h->prm.nx * h->prm.ny * h->nz_local;
+  if (!h->vis) TAU_CUDA(cudaMalloc(&h->vis, n * sizeof(float)));
+  if (!h->ex_idx) {
+    TAU_CUDA(cudaMalloc(&h->ex_idx, n));
+    TAU_CUDA(cudaMalloc(&h->ex_keys, 2 * sizeof(unsigned)));
+    TAU_CUDA(cudaMalloc(&h->ex_thr, 255 * sizeof(float)));
+    float thr[255];
+    tau_4spl_index_thresholds(thr);
+    TAU_CUDA(cudaMemcpyAsync(h->ex_thr, thr, sizeof(thr), cudaMemcpyHostToDevice, h->stream));
+    TAU_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  const Par P = make_par(h);
+  dim3 grid((P.nx + T3_TX - 1) / T3_TX, (P.ny + T3_TY - 1) / T3_TY, (h->nz_local + T3_TZ - 1) / T3_TZ);
+  hyp3d_vis<<<grid, dim3(T3_TX, T3_TY, T3_TZ), 0, h->stream>>>(P, h->st[h->cur], h->solid, h->vis, 8);
+  const unsigned init[2] = {0xffffffffu, 0u};
+  TAU_CUDA(cudaMemcpyAsync(h->ex_keys, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+  hyp3d_export_minmax<<<148 * 4, 256, 0, h->stream>>>(h->vis, n, h->ex_keys);
+  hyp3d_export_quantize<<<148 * 8, 256, 0, h->stream>>>(h->vis, n, h->ex_keys, h->ex_thr, h->ex_idx);
+  h->launches += 3;
+  TAU_CUDA(cudaGetLastError());
+  TAU_CUDA(cudaMemcpyAsync(indices, h->ex_idx, n, cudaMemcpyDeviceToHost, h->stream));
+  unsigned k[2];
+  TAU_CUDA(cudaMemcpyAsync(k, h->ex_keys, sizeof(k), cudaMemcpyDeviceToHost, h->stream));
+  TAU_CUDA(cudaStreamSynchronize(h->stream));
+  if (minmax)
+    for (int i = 0; i < 2; ++i) {
+      const unsigned b = (k[i] & 0x80000000u) ? (k[i] & 0x7fffffffu) : ~k[i];
+      memcpy(&minmax[i], &b, 4);
+    }
   return TAU_OK;
 }
 
@@ -908,6 +1023,9 @@ int tau_hyp3d_destroy(tau_hyp3d *h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   if (h->vis) cudaFree(h->vis);
+  if (h->ex_idx) cudaFree(h->ex_idx);
+  if (h->ex_keys) cudaFree(h->ex_keys);
+  if (h->ex_thr) cudaFree(h->ex_thr);
   cudaFree(h->clk);
   cudaFree(h->solid);
   cudaFree(h->st[1]);

@@ -35,7 +35,10 @@ _clock = declare("tau_hyp3d_clock", [_h] + [C.POINTER(C.c_float)] * 4)
 _download = declare("tau_hyp3d_download", [_h, C.POINTER(C.c_void_p), C.c_void_p])
 _sync = declare("tau_hyp3d_sync", [_h])
 _vis = declare("tau_hyp3d_vis", [_h, C.c_int, np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")])
-VIS_MODES = ("schlieren_rho", "log_rho", "log_p", "speed", "mach", "vort_mag", "div", "q_criterion")
+VIS_MODES = ("schlieren_rho", "log_rho", "log_p", "speed", "mach", "vort_mag", "div", "q_criterion",
+             "schlieren_export")   # 8: th3cs.cu k_schlieren_export :641-673
+_export_frame = declare("tau_hyp3d_export_frame", [_h, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"),
+                                                   C.POINTER(C.c_float)])
 _devstate = declare("tau_hyp3d_device_state", [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)])
 _steps_done = declare("tau_hyp3d_steps_done", [_h], C.c_longlong)
 _launches = declare("tau_hyp3d_launch_count", [_h], C.c_longlong)
@@ -146,6 +149,14 @@ class Hypersonic3D:
         out = np.empty(self.shape, np.float32)
         check(_vis(self._handle, mode, out))
         return out
+
+    def export_frame(self):
+        """One frame of th3cs.cu's `.4spl` export loop (:1193-1222) on the device: ((nz_local, ny, nx) uint8
+        palette indices, (min, max) of the schlieren field)."""
+        idx = np.empty(self.shape, np.uint8)
+        mm = (C.c_float * 2)()
+        check(_export_frame(self._handle, idx.ravel(), mm))
+        return idx, (float(mm[0]), float(mm[1]))
 
     def sync(self):
         check(_sync(self._handle))

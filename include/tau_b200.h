@@ -229,8 +229,24 @@ int tau_hyp3d_download(tau_hyp3d *h, float *const planes[6], uint8_t *solid);
 int tau_hyp3d_sync(tau_hyp3d *h);
 /* k_vis :800-905 — the scalar field the volume renderer consumes: nz_local*ny*nx floats, solid
  * cells 0.  mode = VisMode :784-794 (0 |grad rho|, 1 log(1+rho), 2 log(1+p), 3 |u|, 4 Mach,
- * 5 |curl u|, 6 div u, 7 Q criterion).  Slab handles: exchange the ghost planes first. */
+ * 5 |curl u|, 6 div u, 7 Q criterion; 8 = th3cs.cu's k_schlieren_export :641-673).  Slab handles:
+ * exchange the ghost planes first. */
 int tau_hyp3d_vis(tau_hyp3d *h, int mode, float *out);
+/* One frame of th3cs.cu's export loop :1193-1222 — k_schlieren_export (vis mode 8: mode 0 with the
+ * exporter's divisions), min/max, and per voxel (int)(powf((v-min)/range, 0.65f)*255) clamped to 0..255 —
+ * all on the device; nz_local*ny*nx palette indices come back (1 B/voxel instead of the reference's
+ * 4 B/voxel D2H + host loop).  Identical to the host loop by construction: the 255 steps of that function
+ * are located with the host's powf (tau_4spl_index_thresholds).  minmax (optional): the frame's range. */
+int tau_hyp3d_export_frame(tau_hyp3d *h, uint8_t *indices, float minmax[2]);
+void tau_4spl_index_thresholds(float thr[255]);
+/* `.4spl` container (th3cs.cu:17-62, 1226-1240; reader viewer.html:67-96; the writer library 4splat.c is
+ * missing from the reference, see csrc/splat4.cu for what is pinned and what is our choice).
+ * palette: pSize entries of 12 floats (Splat4D); indices: frames*depth*height*width bytes, x fastest. */
+void tau_4spl_thermal_palette(float *palette, int pSize);
+int tau_4spl_write(const char *path, int width, int height, int depth, int frames, int pSize, unsigned flags,
+                   const float *palette, const uint8_t *indices);
+/* dims = {width, height, depth, frames, pSize, flags}; verifies length and checksum */
+int tau_4spl_info(const char *path, int dims[6]);
 /* device pointers: current state (6 contiguous planes of (nz_local+6)*ny*nx floats, starting at
  * ghost plane -3) and the max-wavespeed accumulator of the running step */
 int tau_hyp3d_device_state(tau_hyp3d *h, float **planes, float **maxs);

@@ -688,3 +688,31 @@ def ref_sw_run(p: SwParams, sigma, u, v, steps, clock=None, skip_visc=False):
         raise RuntimeError(f"reference shallow-water run failed with cudaError {rc}")
     return (s.reshape(p.shape), u.reshape(p.shape), v.reshape(p.shape), (float(ck[0]), float(ck[1])), dts[:steps],
             float(ms.value))
+
+
+# ------------------------------------------------------------------------------------------------
+# `.4spl` export: host-side quantisation + palette of th3cs.cu main
+# ------------------------------------------------------------------------------------------------
+def splat4_palette(p_size=256):
+    lib.oracle_4spl_palette.argtypes = [f32p, C.c_int]
+    lib.oracle_4spl_palette.restype = None
+    pal = np.zeros(12 * p_size, np.float32)
+    lib.oracle_4spl_palette(pal, p_size)
+    return pal.reshape(p_size, 12)
+
+
+def splat4_index(norm: float) -> int:
+    lib.oracle_4spl_index.argtypes = [C.c_float]
+    lib.oracle_4spl_index.restype = C.c_int
+    return int(lib.oracle_4spl_index(norm))
+
+
+def splat4_frame_indices(sch):
+    """th3cs.cu:1199-1222 on a schlieren volume: (uint8 indices of the same shape, (min, max))"""
+    lib.oracle_4spl_frame_indices.argtypes = [f32p, C.c_long, u8p, f32p]
+    lib.oracle_4spl_frame_indices.restype = None
+    a = np.ascontiguousarray(sch, np.float32)
+    out = np.zeros(a.size, np.uint8)
+    mm = np.zeros(2, np.float32)
+    lib.oracle_4spl_frame_indices(a.ravel(), a.size, out, mm)
+    return out.reshape(a.shape), (float(mm[0]), float(mm[1]))

@@ -498,6 +498,12 @@ void oracle_hyp3d_vis(const oracle_hyp3d_params *p, const float *const in[6], co
           out[i] = 0.5f * (Om2 - Sm2);
           continue;
         }
+        if (mode == 8) { /* th3cs.cu k_schlieren_export :669-672 */
+          float ex = (qxp.r - qxm.r) / (2.0f * p->dx), ey = (qyp.r - qym.r) / (2.0f * p->dy),
+                ez = (qzp.r - qzm.r) / (2.0f * p->dz);
+          out[i] = sqrtf(ex * ex + ey * ey + ez * ez);
+          continue;
+        }
         float drdx = (qxp.r - qxm.r) * inv2dx, drdy = (qyp.r - qym.r) * inv2dy, drdz = (qzp.r - qzm.r) * inv2dz;
         out[i] = sqrtf(drdx * drdx + drdy * drdy + drdz * drdz);
       }

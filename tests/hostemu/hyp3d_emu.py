@@ -24,6 +24,9 @@ def lib(packed=False):
         L.tau_hyp3d_clock.argtypes = [h] + [C.POINTER(C.c_float)] * 4
         L.tau_hyp3d_download.argtypes = [h, C.POINTER(C.c_void_p), C.c_void_p]
         L.tau_hyp3d_destroy.argtypes = [h]
+        L.tau_hyp3d_vis.argtypes = [h, C.c_int, np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")]
+        L.tau_hyp3d_export_frame.argtypes = [h, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"),
+                                             C.POINTER(C.c_float)]
         L.tau_hostemu_last_error.restype = C.c_char_p
         _libs[packed] = L
     return _libs[packed]
@@ -55,3 +58,25 @@ def run(prm, planes, steps, clock, packed=False):
     check(L.tau_hyp3d_clock(h, *[C.byref(x) for x in v]))
     L.tau_hyp3d_destroy(h)
     return out, solid, tuple(float(x.value) for x in v)
+
+
+def vis_and_export(prm, planes, clock=(0.012, 2e-3), modes=(0, 8)):
+    """-> ({mode: vis field}, palette indices, (min, max)) of the uploaded state"""
+    L = lib(False)
+    h = C.c_void_p()
+    assert L.tau_hyp3d_create(C.byref(prm), 0, 0, prm.nz, None, C.byref(h)) == 0
+    shape = (prm.nz, prm.ny, prm.nx)
+    arrs = [np.ascontiguousarray(p, np.float32).reshape(shape) for p in planes]
+    ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in arrs])
+    ck = np.array(clock, np.float32)
+    assert L.tau_hyp3d_upload(h, ptrs, C.c_void_p(ck.ctypes.data)) == 0
+    vis = {}
+    for m in modes:
+        out = np.empty(shape, np.float32)
+        assert L.tau_hyp3d_vis(h, m, out.ravel()) == 0, L.tau_hostemu_last_error()
+        vis[m] = out
+    idx = np.empty(shape, np.uint8)
+    mm = (C.c_float * 2)()
+    assert L.tau_hyp3d_export_frame(h, idx.ravel(), mm) == 0, L.tau_hostemu_last_error()
+    L.tau_hyp3d_destroy(h)
+    return vis, idx, (float(mm[0]), float(mm[1]))

@@ -716,3 +716,20 @@ def splat4_frame_indices(sch):
     mm = np.zeros(2, np.float32)
     lib.oracle_4spl_frame_indices(a.ravel(), a.size, out, mm)
     return out.reshape(a.shape), (float(mm[0]), float(mm[1]))
+
+
+def ref_th3cs_host_run(n, frames):
+    """The reference's `.4spl` exporter (th3cs.cu's whole main()) run on the CPU emulator for an n^3 grid:
+    (header dict, palette (pSize, 12), indices (frames, n, n, n) uint8).  See oracle/ref_drivers/ref_th3cs_host.cpp."""
+    r = ref("ref_th3cs_host")
+    u32p_ = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+    r.ref_th3cs_host_run.argtypes = [C.c_int, C.c_int, u32p_, f32p, u8p]
+    r.ref_th3cs_host_run.restype = C.c_int
+    hdr = np.zeros(6, np.uint32)
+    pal = np.zeros(256 * 12, np.float32)
+    idx = np.zeros(frames * n ** 3, np.uint8)
+    rc = r.ref_th3cs_host_run(n, frames, hdr, pal, idx)
+    if rc != 0:
+        raise RuntimeError(f"emulated th3cs main() failed with {rc}")
+    keys = ("width", "height", "depth", "frames", "pSize", "flags")
+    return dict(zip(keys, [int(x) for x in hdr])), pal.reshape(256, 12), idx.reshape(frames, n, n, n)

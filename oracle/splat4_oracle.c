@@ -2,10 +2,14 @@
  * `.4spl` exporter (th3cs.cu main).  TEST INFRASTRUCTURE ONLY: only tests/ may call this.
  *
  * Follows th3cs.cu line by line: palette :1136-1144, per-frame min/max :1199-1205, palette index
- * :1207-1222.  Pinning: PARITY UNPINNED against reference output — the exporter cannot be built or run
- * here (its 4splat.c is not in the reference repository and the loop lives inside main()); what is
- * checked is this restatement against the product (bit-exact) and the product's file against a
- * restatement of the reference's reader (viewer.html:67-96) in tests/test_splat4_cpu.py.
+ * :1207-1222.  Pinning: the exporter's 4splat.c is missing from the reference repository, so the reference
+ * binary cannot be built — but its whole main() runs on the CPU: oracle/ref_drivers/ref_th3cs_host.cpp
+ * compiles th3cs.cu for the host (sizes made variable by sed, <<< >>> launches rewritten mechanically by
+ * tests/hostemu/build.py, kernels executed by the fiber emulator of tests/hostemu/hostemu.h) with four stub
+ * 4splat functions that capture what main() hands them.  Its output (tests/golden/th3cs_ref_host.npz:
+ * 24^3, 48 frames, generator tests/golden/make_golden_host.py) is reproduced index for index, frame for
+ * frame by hyp3d_oracle.c (k_step + d_tau controller + vis mode 8) followed by this file
+ * (tests/test_oracle_cpu.py::test_th3cs_golden_pins_the_3d_and_4spl_oracles).
  */
 #include <math.h>
 #include <stdint.h>

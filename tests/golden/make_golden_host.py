@@ -35,6 +35,18 @@ def sw():
     print("shallow-water host golden written")
 
 
+TH3CS_N, TH3CS_FRAMES = 24, 48
+
+
+def th3cs():
+    # the reference's whole .4spl exporter (th3cs.cu main(): k_init, 4 x k_step per frame with the host d_tau
+    # controller, k_schlieren_export, host min/max + palette index loop) on the CPU emulator, 24^3 x 48 frames
+    hdr, pal, idx = oracle.ref_th3cs_host_run(TH3CS_N, TH3CS_FRAMES)
+    np.savez_compressed(os.path.join(OUT, "th3cs_ref_host.npz"), header=np.array(list(hdr.values()), np.uint32),
+                        palette=pal, indices=idx)
+    print("th3cs host golden written", hdr)
+
+
 if __name__ == "__main__":
-    for w in (sys.argv[1:] or ["sw"]):
+    for w in (sys.argv[1:] or ["sw", "th3cs"]):
         globals()[w]()

@@ -148,3 +148,13 @@ def build(name: str, defines=(), tag: str = "", contract: str = "off", sanitize:
                     *(["-fsanitize=alignment,bounds", "-fno-sanitize-recover=all", "-g"] if sanitize else []),
                     "-I", os.path.join(ROOT, "tests", "hostemu"), cpp, "-o", so, "-lm"], check=True)
     return so
+
+
+if __name__ == "__main__":
+    # python build.py rewrite IN.cu OUT.cpp — the CUDA -> host source rewriting alone (oracle/Makefile uses it to
+    # run a reference translation unit on the CPU emulator)
+    import sys
+    if len(sys.argv) == 4 and sys.argv[1] == "rewrite":
+        open(sys.argv[3], "w").write(preprocess(sys.argv[2]))
+    else:
+        sys.exit("usage: build.py rewrite IN.cu OUT.cpp")

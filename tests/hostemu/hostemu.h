@@ -39,6 +39,7 @@
 #define __shared__ static
 #define __launch_bounds__(...)
 #define __grid_constant__
+#define __constant__   /* a plain global; cudaMemcpyToSymbol is a memcpy */
 #define __align__(n) __attribute__((aligned(n)))
 #ifndef TAU_HC_SMEM_BYTES
 #define TAU_HC_SMEM_BYTES 232448   // `extern __shared__ T name[]` becomes a static array of this size
@@ -356,6 +357,10 @@ static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent
 static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+template <class T> static inline cudaError_t cudaMemcpyToSymbol(T &sym, const void *src, size_t n) {
+  memcpy(&sym, src, n);
+  return cudaSuccess;
+}
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 static inline int tau_hc_env_int(const char *name, int dflt) {

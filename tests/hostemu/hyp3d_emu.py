@@ -9,7 +9,18 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(__file__))
 import build as hostemu_build  # noqa: E402
 
+from fluid_sims_b200.hypersonic3d import _CParams  # noqa: E402  (tau_hyp3d_params layout only)
+
 _libs = {}
+
+
+def cparams(prm, t0=1e-5, d_tau0=1e-3):
+    """oracle.Hyp3dParams lacks tau_hyp3d_params' trailing (t0, d_tau0): convert instead of casting"""
+    c = _CParams()
+    for name, _ in prm._fields_:
+        setattr(c, name, getattr(prm, name))
+    c.t0, c.d_tau0 = t0, d_tau0
+    return c
 
 
 def lib(packed=False):
@@ -40,7 +51,8 @@ def run(prm, planes, steps, clock, packed=False):
         if rc != 0:
             raise RuntimeError(f"rc={rc}: {L.tau_hostemu_last_error().decode()}")
     h = C.c_void_p()
-    check(L.tau_hyp3d_create(C.byref(prm), 0, 0, prm.nz, None, C.byref(h)))
+    cp = cparams(prm)
+    check(L.tau_hyp3d_create(C.byref(cp), 0, 0, prm.nz, None, C.byref(h)))
     shape = (prm.nz, prm.ny, prm.nx)
     if planes is None:
         check(L.tau_hyp3d_init(h))
@@ -64,7 +76,8 @@ def vis_and_export(prm, planes, clock=(0.012, 2e-3), modes=(0, 8)):
     """-> ({mode: vis field}, palette indices, (min, max)) of the uploaded state"""
     L = lib(False)
     h = C.c_void_p()
-    assert L.tau_hyp3d_create(C.byref(prm), 0, 0, prm.nz, None, C.byref(h)) == 0
+    cp = cparams(prm)
+    assert L.tau_hyp3d_create(C.byref(cp), 0, 0, prm.nz, None, C.byref(h)) == 0
     shape = (prm.nz, prm.ny, prm.nx)
     arrs = [np.ascontiguousarray(p, np.float32).reshape(shape) for p in planes]
     ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in arrs])
@@ -80,3 +93,19 @@ def vis_and_export(prm, planes, clock=(0.012, 2e-3), modes=(0, 8)):
     assert L.tau_hyp3d_export_frame(h, idx.ravel(), mm) == 0, L.tau_hostemu_last_error()
     L.tau_hyp3d_destroy(h)
     return vis, idx, (float(mm[0]), float(mm[1]))
+
+
+def export_video(prm, frames, steps_per_frame=4):
+    """th3cs.cu's main loop through the product: init, then per frame `steps_per_frame` steps + export_frame.
+    -> (frames, nz, ny, nx) uint8"""
+    L = lib(False)
+    h = C.c_void_p()
+    cp = cparams(prm)
+    assert L.tau_hyp3d_create(C.byref(cp), 0, 0, prm.nz, None, C.byref(h)) == 0
+    assert L.tau_hyp3d_init(h) == 0
+    out = np.empty((frames, prm.nz, prm.ny, prm.nx), np.uint8)
+    for f in range(frames):
+        assert L.tau_hyp3d_step(h, steps_per_frame) == 0
+        assert L.tau_hyp3d_export_frame(h, out[f].ravel(), None) == 0
+    L.tau_hyp3d_destroy(h)
+    return out

@@ -493,3 +493,38 @@ def test_sw_oracle_invariants():
     sT, uT, vT, _, d2 = oracle.sw_run(prmT, s0.T.copy(), v0.T.copy(), u0.T.copy(), 15)
     assert np.array_equal(d1, d2)
     assert np.abs(sT.T - s).max() < 1e-5 and np.abs(vT.T - u).max() < 1e-5 and np.abs(uT.T - v).max() < 1e-5
+
+
+# ---- the reference's .4spl exporter, run whole on the CPU ------------------------------
+def _th3cs_golden():
+    g = np.load(os.path.join(GOLDEN, "th3cs_ref_host.npz"))
+    return [int(x) for x in g["header"]], g["palette"], g["indices"]
+
+
+def test_th3cs_golden_pins_the_3d_and_4spl_oracles():
+    """tests/golden/th3cs_ref_host.npz: output of th3cs.cu's own main() — k_build_solid_mask, k_init, 4 x k_step
+    per frame under its host-side d_tau controller, k_schlieren_export, the host min/max + palette-index loop,
+    the palette, the header arguments — executed on the CPU by tests/hostemu (oracle/ref_drivers/
+    ref_th3cs_host.cpp; generator tests/golden/make_golden_host.py), 24^3, 48 frames = 192 steps, by which time
+    the bow shock has formed.  The oracle chain (hyp3d_oracle.c k_step + controller -> vis mode 8 ->
+    splat4_oracle.c) must reproduce EVERY index of EVERY frame: integer output of ~200 fp32 steps, i.e. the
+    restatements follow the reference's expression trees to the last bit (same libm, no contraction)."""
+    hdr, pal, idx = _th3cs_golden()
+    frames, n = idx.shape[0], idx.shape[1]
+    assert hdr == [n, n, n, frames, 256, 4]                      # create_splat4DHeader(nx, ny, nz, frames, pSize, 0x0004)
+    assert np.array_equal(pal, oracle.splat4_palette(256))
+    prm = oracle.hyp3d_params(n, n, n)
+    planes, solid = oracle.hyp3d_init(prm)
+    clock = (1e-5, 1e-3)                                          # th3cs.cu:1146-1147
+    for f in range(frames):
+        planes, clock, _, _ = oracle.hyp3d_run(prm, planes, solid, 4, clock)
+        got, _ = oracle.splat4_frame_indices(oracle.hyp3d_vis(prm, planes, solid, 8))
+        assert np.array_equal(got, idx[f]), f
+    assert len(np.unique(idx[-1])) > 80 and len(np.unique(idx[0])) < 10     # quiescent start, developed end
+
+
+@pytest.mark.skipif(not oracle.has_ref("ref_th3cs_host"), reason="oracle/_ref not built")
+def test_th3cs_reference_exporter_runs_on_the_cpu_emulator():
+    hdr, pal, idx = _th3cs_golden()
+    h2, p2, i2 = oracle.ref_th3cs_host_run(idx.shape[1], 6)      # a short live run reproduces the fixture's start
+    assert list(h2.values()) == hdr[:3] + [6, 256, 4] and np.array_equal(p2, pal) and np.array_equal(i2, idx[:6])

@@ -47,8 +47,30 @@ def has_ref(name: str) -> bool:
 _ref_cache: dict = {}
 
 
+_host_refs = False
+
+
+class host_refs:
+    """with oracle.host_refs(): every ref_*() wrapper drives the reference's kernels on the CPU emulator
+    (oracle/_ref/lib<name>_host.so, built by the HOST_REF_RULE of oracle/Makefile) instead of on a GPU."""
+
+    def __enter__(self):
+        global _host_refs
+        self._old, _host_refs = _host_refs, True
+
+    def __exit__(self, *a):
+        global _host_refs
+        _host_refs = self._old
+
+
+def has_host_ref(name: str) -> bool:
+    return os.path.exists(os.path.join(REF_DIR, f"lib{name}_host.so"))
+
+
 def ref(name: str) -> C.CDLL:
     """Load oracle/_ref/lib<name>.so (the compiled reference)."""
+    if _host_refs and not name.endswith("_host") and has_host_ref(name):
+        name += "_host"
     if name not in _ref_cache:
         path = os.path.join(REF_DIR, f"lib{name}.so")
         if not os.path.exists(path):
@@ -174,10 +196,11 @@ def hyp2d_snapshot(cfg: Hyp2dCfg, steps, planes, mask):
     return out
 
 
-def ref_hyp2d_run(W, H, cfg11, steps, planes=None, mask=None, tile=(32, 8)):
-    """The reference's own kernels on the GPU (oracle/_ref/libref_hyp2d_<W>x<H>.so).
+def ref_hyp2d_run(W, H, cfg11, steps, planes=None, mask=None, tile=(32, 8), host=False):
+    """The reference's own kernels on the GPU (oracle/_ref/libref_hyp2d_<W>x<H>.so) or, host=True, the same
+    driver and kernels executed by the CPU emulator of tests/hostemu (libref_hyp2d_host_<W>x<H>.so).
     planes=None -> start from k_init.  Returns (planes, mask, sim_t, dts, ms)."""
-    r = ref(f"ref_hyp2d_{W}x{H}")
+    r = ref(f"ref_hyp2d_host_{W}x{H}" if host else f"ref_hyp2d_{W}x{H}")
     r.ref_hyp2d_run.argtypes = [f64p, C.c_int, C.c_int, C.c_int, C.c_int, f64p, f64p, f64p, f64p,
                                 u8p, C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_float)]
     r.ref_hyp2d_run.restype = C.c_int

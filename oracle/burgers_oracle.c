@@ -14,6 +14,8 @@
  * which it reproduces to the libm-vs-fast-intrinsic level (init bit-identical, dt identical,
  * fields 1e-5), and (2) by the Cole-Hopf exact solution the reference's own harness checks against
  * (both in tests/test_oracle_cpu.py).
+ * Also pinned BIT FOR BIT (nu = 0, and the 1-D Cole-Hopf harness) on the reference's kernels executed on the CPU
+ * (oracle/_ref/libref_burgers_host.so, tests/test_oracle_cpu.py::test_burgers_oracle_equals_reference_kernels_run_on_the_cpu).
  */
 #define _GNU_SOURCE
 #include <math.h>

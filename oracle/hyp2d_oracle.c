@@ -12,6 +12,8 @@
  * (tests/golden/hyp2d_*.npz, made by tests/golden/make_golden_gpu.py via oracle/_ref) are compared
  * in the same test file.  The reference's 12-scalar regression snapshot (:143-176) is restated in
  * oracle_hyp2d_snapshot().
+ * Also pinned BIT FOR BIT on the reference's kernels executed on the CPU (oracle/_ref/libref_hyp2d_host_*.so,
+ * tests/test_oracle_cpu.py::test_hyp2d_oracle_equals_reference_kernels_run_on_the_cpu).
  */
 #include <math.h>
 #include <stdint.h>

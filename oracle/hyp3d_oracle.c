@@ -13,6 +13,8 @@
  * tests/golden/hyp3d_ref_*.npz hold outputs of the reference's own k_step run on a B200 through
  * oracle/_ref/libref_hyp3d.so (tests/golden/make_golden_gpu.py) and tests/test_oracle_cpu.py
  * compares this file against them.
+ * Also pinned BIT FOR BIT on the reference's kernels executed on the CPU (oracle/_ref/libref_hyp3d_host.so and the
+ * th3cs exporter, tests/test_oracle_cpu.py::test_hyp3d_oracle_equals_reference_kernel_run_on_the_cpu, ::test_th3cs_*).
  */
 #include <math.h>
 #include <stdint.h>

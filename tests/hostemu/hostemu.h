@@ -337,6 +337,10 @@ static inline cudaError_t cudaFree(void *p) {
   fprintf(stderr, "hostemu: cudaFree of a pointer cudaMalloc did not return\n");
   abort();
 }
+enum { cudaHostAllocDefault = 0 };
+template <class T> static inline cudaError_t cudaHostAlloc(T **p, size_t n, unsigned) { *p = (T *)malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+template <class T> static inline cudaError_t cudaMallocHost(T **p, size_t n) { *p = (T *)malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 extern "C" long long tau_hostemu_live_allocations(void) { return (long long)tau_hc_allocs.size(); }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) {
   memmove(d, s, n);
@@ -345,12 +349,13 @@ static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cuda
 static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = nullptr; return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = nullptr; return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
-static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0.f; return cudaSuccess; }
 
@@ -361,6 +366,13 @@ template <class T> static inline cudaError_t cudaMemcpyToSymbol(T &sym, const vo
   memcpy(&sym, src, n);
   return cudaSuccess;
 }
+struct cudaDeviceProp {
+  char name[256];
+  int major, minor, multiProcessorCount, maxThreadsPerBlock, warpSize;
+  size_t sharedMemPerBlock, sharedMemPerBlockOptin, totalGlobalMem;
+};
+static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 static inline int tau_hc_env_int(const char *name, int dflt) {
@@ -369,6 +381,14 @@ static inline int tau_hc_env_int(const char *name, int dflt) {
 }
 // a small pretend device keeps persistent grids small: TAU_HC_SMS "SMs" x TAU_HC_CTAS_PER_SM resident CTAs
 static inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) { *v = tau_hc_env_int("TAU_HC_SMS", 3); return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
+  memset(p, 0, sizeof(*p));
+  strcpy(p->name, "hostemu");
+  p->major = 10; p->minor = 0; p->multiProcessorCount = tau_hc_env_int("TAU_HC_SMS", 3);
+  p->maxThreadsPerBlock = 1024; p->warpSize = 32;
+  p->sharedMemPerBlock = 48 << 10; p->sharedMemPerBlockOptin = TAU_HC_SMEM_BYTES; p->totalGlobalMem = (size_t)1 << 34;
+  return cudaSuccess;
+}
 template <class K> static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int v) {
   return v <= TAU_HC_SMEM_BYTES ? cudaSuccess : 1;
 }

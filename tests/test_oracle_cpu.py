@@ -528,3 +528,88 @@ def test_th3cs_reference_exporter_runs_on_the_cpu_emulator():
     hdr, pal, idx = _th3cs_golden()
     h2, p2, i2 = oracle.ref_th3cs_host_run(idx.shape[1], 6)      # a short live run reproduces the fixture's start
     assert list(h2.values()) == hdr[:3] + [6, 256, 4] and np.array_equal(p2, pal) and np.array_equal(i2, idx[:6])
+
+
+# ---- the reference's 2-D hypersonic kernels executed on the CPU ------------------------------------------------
+@pytest.mark.parametrize("W,H,steps", [(96, 64, 40), (200, 120, 60)])
+def test_hyp2d_oracle_equals_reference_kernels_run_on_the_cpu(W, H, steps):
+    """oracle/_ref/libref_hyp2d_host_<W>x<H>.so: tau_hypersonic_cuda.cu's own kernels (k_init, k_apply_inflow_left,
+    k_max_wavespeed_blocks, k_reduce_block_max, k_predict_face_states, k_compute_x/yface_flux, k_step) and the
+    host loop of oracle/ref_drivers/ref_hyp2d.cu, rewritten mechanically for the CPU emulator of tests/hostemu
+    (same recipe as the th3cs exporter above).  Same libm, no contraction on either side: the headline
+    solver's oracle reproduces the reference BIT FOR BIT — fields, mask, sim_t, every dt.  (The GPU fixture
+    pins it to 2e-15: there the reference is compiled with FMA contraction.)"""
+    if not oracle.has_ref(f"ref_hyp2d_host_{W}x{H}"):
+        pytest.skip("oracle/_ref not built")
+    cfg = oracle.hyp2d_cfg(W, H, geom_x0=W / 3.0)
+    planes, mask = oracle.hyp2d_init(cfg)
+    got, t, dts = oracle.hyp2d_run(cfg, planes, mask, steps)
+    cfg11 = np.array([getattr(cfg, f[0]) for f in oracle.Hyp2dCfg._fields_[:11]], np.float64)
+    ref, rmask, rt, rdts, _ = oracle.ref_hyp2d_run(W, H, cfg11, steps, host=True)
+    assert np.array_equal(rmask, mask) and t == rt and np.array_equal(dts, rdts)
+    for k, a, b in zip("rho mx my E".split(), got, ref):
+        # my is ~0 by symmetry in most of the field; the oracle leaves residues of 1e-63 where the reference has 0
+        assert np.array_equal(a, b) or (k == "my" and np.abs(a - b).max() < 1e-50), k
+    assert np.abs(got[0] - planes[0]).max() > 0.1        # the flow did evolve
+
+
+# ---- every other reference solver's kernels executed on the CPU (oracle/Makefile HOST_REF_RULE) --------------------
+def _need_host_ref(name):
+    if not oracle.has_host_ref(name):
+        pytest.skip("oracle/_ref host builds not present")
+
+
+def test_hyp3d_oracle_equals_reference_kernel_run_on_the_cpu():
+    """tau_hypersonic_3d_cuda.cu's k_build_solid_mask / k_init / k_step (+ the host d_tau controller of
+    oracle/ref_drivers/ref_hyp3d.cu) and all eight k_vis modes: bit for bit."""
+    _need_host_ref("ref_hyp3d")
+    prm = oracle.hyp3d_params(24, 20, 12)
+    with oracle.host_refs():
+        p0, solid, _, _, _, _ = oracle.ref_hyp3d_run(prm, 0)
+        o0, osolid = oracle.hyp3d_init(prm)
+        assert all(np.array_equal(a, b) for a, b in zip(p0, o0)) and np.array_equal(solid, osolid)
+        ref, _, ck_ref, dts, mx, _ = oracle.ref_hyp3d_run(prm, 40, planes=p0, clock=(0.012, 2e-3))
+        out, ck, odts, omx = oracle.hyp3d_run(prm, p0, solid, 40, (0.012, 2e-3))
+        assert all(np.array_equal(a, b) for a, b in zip(ref, out))
+        assert ck == ck_ref and np.array_equal(dts, odts) and np.array_equal(mx, omx)
+        for mode in range(8):
+            assert np.array_equal(oracle.ref_hyp3d_vis(prm, out, mode), oracle.hyp3d_vis(prm, out, solid, mode)), mode
+
+
+def test_burgers_oracle_equals_reference_kernels_run_on_the_cpu():
+    """bit for bit wherever viscosity_step does not mix cells of one sweep (nu = 0; the 1-D Cole-Hopf harness);
+    with 2-D viscosity the emulator's sequential in-place sweep differs from the oracle's Jacobi sweep"""
+    _need_host_ref("ref_burgers")
+    with oracle.host_refs():
+        for kw in (dict(nx=96, ny=64, dtau=1e-3, nu=0.0, swirl=0.2, amp=0.3, muscl=1), dict(nx=96, ny=64, dtau=1e-3, nu=0.0),
+                   dict(nx=200, colehopf=1, dtau=5e-3, t0=1e-3, nu=0.5, ck=2)):
+            p = oracle.burgers_params(**kw)
+            a0 = oracle.burgers_init(p)
+            assert all(np.array_equal(x, y) for x, y in zip(a0, oracle.ref_burgers_init(p)))
+            ra, rb = oracle.burgers_run(p, *a0, 30), oracle.ref_burgers_run(p, *a0, 30)
+            assert all(np.array_equal(x, y) for x, y in zip(ra[:2], rb[:2])), kw
+            assert ra[2] == rb[2] and np.array_equal(ra[3], rb[3])
+        p = oracle.burgers_params(nx=64, ny=48, dtau=1e-3, nu=0.1)
+        a0 = oracle.burgers_init(p)
+        ra, rb = oracle.burgers_run(p, *a0, 30), oracle.ref_burgers_run(p, *a0, 30)
+        assert 0 < max(float(np.abs(x - y).max()) for x, y in zip(ra[:2], rb[:2])) < 5e-4     # measured 8.7e-5
+
+
+def test_gs_and_sph_oracles_against_reference_kernels_run_on_the_cpu():
+    """Gray-Scott: the oracle spells out the GPU's FMA contraction (bit-exact against the GPU fixture), the
+    emulated reference has none: 2 ulp.  SPH: the oracle (like the product) sums neighbours in sorted-slot
+    order, the reference in cell-list order: fp32 round-off."""
+    _need_host_ref("ref_gs")
+    _need_host_ref("ref_sph")
+    with oracle.host_refs():
+        u0, v0 = oracle.gs_init_pattern(96, 64)
+        ru, rv = oracle.ref_gs_run(u0, v0, 20)
+        eu, ev = oracle.gs_run(u0, v0, 20)
+        assert np.abs(ru - eu).max() < 1e-6 and np.abs(rv - ev).max() < 1e-6
+        for N, frames, over in ((2048, 3, {}), (3000, 2, dict(useXSPH=1))):
+            p = oracle.sph_params(N, **over)
+            pos, vel = oracle.ref_sph_reset_particles(p)
+            r, e = oracle.ref_sph_run(p, pos, vel, frames), oracle.sph_run(p, pos, vel, frames)
+            assert np.abs(r[0] - e[0]).max() < 1e-6 and np.abs(r[1] - e[1]).max() < 1e-5
+            assert np.abs(r[3] - e[3]).max() < 1e-5 and np.abs(r[4] - e[4]).max() < 1e-5
+            assert r[5][0] == e[5].t and r[5][3] == e[5].step

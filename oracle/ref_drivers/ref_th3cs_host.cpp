@@ -2,7 +2,7 @@
 // Runs the reference's `.4spl` exporter th3cs.cu — its whole main(): k_build_solid_mask, k_init, 4 x k_step
 // per frame with the host-side d_tau controller, k_schlieren_export, the host min/max + palette-index loop,
 // the palette — ON THE CPU.  REF_SRC is th3cs.cu after (1) sed of the three hard-coded sizes
-// (hp.nx/ny/nz = 64, frames = 60) into REF_N / REF_FRAMES and (2) tests/hostemu/build.py's mechanical
+// (hp.nx/ny/nz = 64, frames = 60) into REF_N / REF_FRAMES and (2) tests/hostemu/hostemu_build.py's mechanical
 // rewriting of `k<<<g, b, s>>>(args)` into emulator launches; it is compiled against tests/hostemu/hostemu.h
 // (fibers with real __syncthreads semantics; __expf/__logf are libm's) and deleted after compilation.
 // The four functions of the missing 4splat.c are provided here and simply capture what main() hands them.

@@ -5,7 +5,7 @@
  * :1207-1222.  Pinning: the exporter's 4splat.c is missing from the reference repository, so the reference
  * binary cannot be built — but its whole main() runs on the CPU: oracle/ref_drivers/ref_th3cs_host.cpp
  * compiles th3cs.cu for the host (sizes made variable by sed, <<< >>> launches rewritten mechanically by
- * tests/hostemu/build.py, kernels executed by the fiber emulator of tests/hostemu/hostemu.h) with four stub
+ * tests/hostemu/hostemu_build.py, kernels executed by the fiber emulator of tests/hostemu/hostemu.h) with four stub
  * 4splat functions that capture what main() hands them.  Its output (tests/golden/th3cs_ref_host.npz:
  * 24^3, 48 frames, generator tests/golden/make_golden_host.py) is reproduced index for index, frame for
  * frame by hyp3d_oracle.c (k_step + d_tau controller + vis mode 8) followed by this file

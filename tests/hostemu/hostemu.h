@@ -1,6 +1,6 @@
 // hostemu.h — TEST INFRASTRUCTURE ONLY: runs the PRODUCT's simple CUDA translation units on the CPU so
 // that their logic (tile/halo indexing, buffer rotation, clock slots, barrier placement) is checked on
-// a GPU-less box.  tests/hostemu/build.py rewrites `k<<<g, b, s, st>>>(args);` into
+// a GPU-less box.  tests/hostemu/hostemu_build.py rewrites `k<<<g, b, s, st>>>(args);` into
 // tau_hc::launch(g, b, [&]{ k(args); }) and `#include "common.cuh"` into this header, then g++ builds
 // build/hostemu/lib<name>_hostemu.so, which ONLY tests/test_hostemu_cpu.py loads.  Nothing in the
 // package, bench.py or __graft_entry__ knows this exists: it is a checker for code, not a fallback.
@@ -13,7 +13,7 @@
 // host's (libm, -ffp-contract=off), so a kernel whose expression trees match the CPU oracle's must
 // reproduce it BIT FOR BIT.  TMA tile loads are executed synchronously with the hardware's zero fill of
 // out-of-bounds elements; mbarriers keep the phase/arrival/tx-count protocol.  Inline PTX is rewritten
-// statement by statement by build.py (a statement it does not know is a build error).
+// statement by statement by hostemu_build.py (a statement it does not know is a build error).
 // NOT modelled: memory ordering, inter-block concurrency, partial-mask collectives, -use_fast_math, speed.
 #pragma once
 #include <math.h>
@@ -51,7 +51,7 @@ struct dim3 {
   dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 // CUDA's alignments: a misaligned vector access faults on the GPU; built with -fsanitize=alignment
-// (build.py sanitize=True) the emulated run reports it
+// (hostemu_build.py sanitize=True) the emulated run reports it
 struct alignas(8) float2 { float x, y; };
 struct alignas(16) float4 { float x, y, z, w; };
 struct alignas(16) double2 { double x, y; };

@@ -151,10 +151,10 @@ def build(name: str, defines=(), tag: str = "", contract: str = "off", sanitize:
 
 
 if __name__ == "__main__":
-    # python build.py rewrite IN.cu OUT.cpp — the CUDA -> host source rewriting alone (oracle/Makefile uses it to
+    # python hostemu_build.py rewrite IN.cu OUT.cpp — the CUDA -> host source rewriting alone (oracle/Makefile uses it to
     # run a reference translation unit on the CPU emulator)
     import sys
     if len(sys.argv) == 4 and sys.argv[1] == "rewrite":
         open(sys.argv[3], "w").write(preprocess(sys.argv[2]))
     else:
-        sys.exit("usage: build.py rewrite IN.cu OUT.cpp")
+        sys.exit("usage: hostemu_build.py rewrite IN.cu OUT.cpp")

@@ -7,7 +7,7 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(__file__))
-import build as hostemu_build  # noqa: E402
+import hostemu_build  # noqa: E402
 
 from fluid_sims_b200.hypersonic3d import _CParams  # noqa: E402  (tau_hyp3d_params layout only)
 

@@ -20,7 +20,7 @@ import pytest
 import oracle
 
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "hostemu"))
-import build as hostemu_build  # noqa: E402
+import hostemu_build  # noqa: E402
 
 f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
 
@@ -164,7 +164,7 @@ def test_burgers_product_code_equals_oracle(bglib, kw, steps):
 # hypersonic2d.cu runs whole in the emulator: tensor maps + TMA box loads (zero fill), the mbarrier ring,
 # the persistent grid with its device work queue (the pretend device has TAU_HC_SMS x TAU_HC_CTAS_PER_SM
 # resident CTAs), warp-shuffle column marching, the last-CTA-out reduction and the device-side clock.
-# Its 11 inline-PTX statements are replaced by build.py (rcp/sqrt.approx -> exact, %tid -> threadIdx, ...).
+# Its 11 inline-PTX statements are replaced by hostemu_build.py (rcp/sqrt.approx -> exact, %tid -> threadIdx, ...).
 import hyp2d_emu  # noqa: E402  (tests/hostemu)
 
 NAMES = ("rho", "mx", "my", "E")

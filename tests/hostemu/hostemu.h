@@ -74,7 +74,7 @@ static dim3 blockDim, gridDim;
 #error "tests/hostemu needs x86-64"
 #endif
 extern "C" void tau_hc_switch(void **save_sp, void *load_sp);
-asm(".text\n.globl tau_hc_switch\n.type tau_hc_switch,@function\ntau_hc_switch:\n"
+asm(".text\n.weak tau_hc_switch\n.type tau_hc_switch,@function\ntau_hc_switch:\n"
     "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
     "  movq %rsp, (%rdi)\n  movq %rsi, %rsp\n"
     "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n  ret\n"
@@ -341,7 +341,7 @@ enum { cudaHostAllocDefault = 0 };
 template <class T> static inline cudaError_t cudaHostAlloc(T **p, size_t n, unsigned) { *p = (T *)malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 template <class T> static inline cudaError_t cudaMallocHost(T **p, size_t n) { *p = (T *)malloc(n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
 static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
-extern "C" long long tau_hostemu_live_allocations(void) { return (long long)tau_hc_allocs.size(); }
+extern "C" __attribute__((weak)) long long tau_hostemu_live_allocations(void) { return (long long)tau_hc_allocs.size(); }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) {
   memmove(d, s, n);
   return cudaSuccess;
@@ -430,7 +430,7 @@ static inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, u
   return *p ? cudaSuccess : 1;
 }
 static inline cudaError_t cudaIpcCloseMemHandle(void *) { tau_hc_ipc_open--; return cudaSuccess; }
-extern "C" long long tau_hostemu_ipc_open_mappings(void) { return tau_hc_ipc_open; }
+extern "C" __attribute__((weak)) long long tau_hostemu_ipc_open_mappings(void) { return tau_hc_ipc_open; }
 
 // ---- tensor maps, TMA tile loads, mbarriers (common.cuh:50-113, common.cu) ------------------------------
 struct CUtensorMap {
@@ -519,16 +519,20 @@ static inline void stg_stream_d2(double *p, double a, double b) { p[0] = a; p[1]
 #define TAU_ERR_NOMEM -12
 #define TAU_ERR_CUDA -5
 #define TAU_ERR_NODEV -19
-static char tau_hc_err[512];
-static inline void tau_set_error(const char *fmt, ...) {
+// (weak: several emulated translation units can be linked into one library — hostemu_build.build_all)
+#define TAU_HC_WEAK __attribute__((weak))
+TAU_HC_WEAK char tau_hc_err[512];
+TAU_HC_WEAK void tau_set_error(const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(tau_hc_err, sizeof(tau_hc_err), fmt, ap);
   va_end(ap);
 }
-extern "C" const char *tau_hostemu_last_error(void) { return tau_hc_err; }
-extern "C" long long tau_hostemu_launches(void) { return tau_hc::launches; }
-extern "C" int tau_device_count(void) { return 1; }
+extern "C" TAU_HC_WEAK const char *tau_hostemu_last_error(void) { return tau_hc_err; }
+extern "C" TAU_HC_WEAK const char *tau_last_error(void) { return tau_hc_err; }
+extern "C" TAU_HC_WEAK int tau_abi_version(void) { return 1; }
+extern "C" TAU_HC_WEAK long long tau_hostemu_launches(void) { return tau_hc::launches; }
+extern "C" TAU_HC_WEAK int tau_device_count(void) { return 1; }
 #define TAU_CUDA(expr)                                                   \
   do {                                                                   \
     cudaError_t _e = (expr);                                             \

@@ -150,6 +150,28 @@ def build(name: str, defines=(), tag: str = "", contract: str = "off", sanitize:
     return so
 
 
+def build_all() -> str:
+    """every product translation unit for the emulator in ONE library with the product's C-ABI:
+    TAU_B200_LIB=build/hostemu/libtau_b200_hostemu.so runs Python code written for the GPU library on the CPU
+    (a pre-flight for tests/ -m gpu at sizes the emulator can afford; never shipped, never a default)."""
+    os.makedirs(OUT, exist_ok=True)
+    names = ["burgers", "gray_scott", "hypersonic2d", "hypersonic3d", "shallow_water", "snapshot", "splat4", "sph"]
+    objs = []
+    for name in names:
+        cu = os.path.join(ROOT, "fluid_sims_b200", "csrc", f"{name}.cu")
+        cpp = os.path.join(OUT, f"{name}_all_host.cpp")
+        obj = os.path.join(OUT, f"{name}_all_host.o")
+        text = preprocess(cu).replace('#include "../../include/tau_b200.h"',
+                                      f'#include "{os.path.join(ROOT, "include", "tau_b200.h")}"')
+        open(cpp, "w").write(text)
+        subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-c", "-mfma", "-ffp-contract=off", "-Wno-return-type",
+                        "-Wno-unknown-pragmas", "-I", os.path.join(ROOT, "tests", "hostemu"), cpp, "-o", obj], check=True)
+        objs.append(obj)
+    so = os.path.join(OUT, "libtau_b200_hostemu.so")
+    subprocess.run(["g++", "-shared", "-Wl,-Bsymbolic", "-o", so] + objs + ["-lm"], check=True)
+    return so
+
+
 if __name__ == "__main__":
     # python hostemu_build.py rewrite IN.cu OUT.cpp — the CUDA -> host source rewriting alone (oracle/Makefile uses it to
     # run a reference translation unit on the CPU emulator)

@@ -278,6 +278,15 @@ static inline unsigned __match_any_sync(unsigned, unsigned long long v) {
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+#ifdef TAU_HC_ROUGH_FASTMATH
+// A rough stand-in for -use_fast_math (ex2.approx(x*log2e), lg2.approx(x)*ln2: the argument scaling is
+// rounded to fp32, so the error grows with |x| like the GPU's) — ONLY to size test tolerances for code that
+// has not run on hardware yet; nothing is compared bit for bit in this mode.
+static inline float tau_hc_fast_expf(float x) { return exp2f(x * 1.4426950408889634f); }
+static inline float tau_hc_fast_logf(float x) { return log2f(x) * 0.6931471805599453f; }
+#define expf(x) tau_hc_fast_expf(x)
+#define logf(x) tau_hc_fast_logf(x)
+#endif
 #define __expf(x) expf(x)   /* glibc declares __expf / __logf itself: macros, not functions */
 #define __logf(x) logf(x)
 static inline float __fdividef(float a, float b) { return a / b; }

@@ -4,8 +4,10 @@ against the reference's own kernels on the same device (oracle/_ref/libref_sw.so
 
 OPT-IN (TAU_TEST_SW=1): shallow_water.cu was written after the round-1 GPU budget was spent and has not
 run on hardware yet; a never-run kernel must not be able to take the validated suite down with it.  The
-bounds below are first estimates (fp32, -use_fast_math expf/logf/division on the GPU sides, libm in the
-oracle), to be replaced by ~4x the measured values on the first run — see NEXT.md.
+bounds below are estimates (fp32, -use_fast_math expf/logf/division on the GPU sides, libm in the oracle);
+with a rough stand-in for the fast intrinsics in the CPU emulator (hostemu.h TAU_HC_ROUGH_FASTMATH) the
+errors are 2e-7 ... 9e-7 for the gentle fields and 3e-5 for the default field, i.e. the bounds have a 20-60x
+margin; replace them by ~4x the measured values on the first run — see NEXT.md.
 """
 import os
 
@@ -65,7 +67,10 @@ def test_lake_at_rest_and_mass():
     P = Params(nx=128, ny=96, bumpAmp=0.0, swirl=0.0, nu=0.1, dtau=0.1)
     a = initialize_host(P)
     (s, u, v), _, _ = product(P, *a, 30)
-    assert np.abs(s - a[0]).max() < 1e-6 and np.abs(u).max() < 1e-4 and np.abs(v).max() < 1e-4
+    # every cell computes the same numbers, so no gradient can appear (u, v stay 0); sigma itself may drift
+    # uniformly by the log(exp(sigma)) round trip of the fast intrinsics, a few ulp of 6.9 per step
+    assert np.abs(s - a[0]).max() < 1e-4 and np.abs(u).max() < 1e-4 and np.abs(v).max() < 1e-4
+    assert np.ptp(s) == 0.0
     P = Params(nx=128, ny=96, dtau=0.05, nu=0.0, **GENTLE)
     a = initialize_host(P)
     (s, _, _), _, _ = product(P, *a, 200)

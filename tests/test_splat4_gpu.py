@@ -1,7 +1,7 @@
 """GPU side of the `.4spl` export: tau_hyp3d_export_frame and the th3cs host program.
 
-OPT-IN (TAU_TEST_4SPL=1): written after the round-1 GPU budget was spent; the new kernels have run in the CPU
-emulator only (tests/test_hostemu_cpu.py: bit-identical to the reference's host loop) — see NEXT.md."""
+Written after the round-1 GPU budget was spent; the new kernels have run in the CPU emulator only
+(tests/test_hostemu_cpu.py: bit-identical to the reference's host loop) — see pytestmark below and NEXT.md."""
 import os
 import subprocess
 
@@ -12,9 +12,12 @@ import oracle
 from fluid_sims_b200 import splat4
 from fluid_sims_b200.hypersonic3d import Hypersonic3D, Params
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("TAU_TEST_4SPL") != "1",
-                                 reason=".4spl export kernels not yet validated on hardware (TAU_TEST_4SPL=1)")]
+# First contact with hardware: the tests RUN, but until a pass has been seen on a B200 (TAU_TEST_4SPL=1 makes them
+# ordinary tests) a failure is reported as xfailed instead of stopping the validated suite (`-x`), and a pass as
+# xpassed.  The kernels have no polling loops (nothing can hang), and these files sort last, after every
+# validated GPU test.
+pytestmark = [pytest.mark.gpu] + ([] if os.environ.get("TAU_TEST_4SPL") == "1" else [
+    pytest.mark.xfail(strict=False, reason=".4spl export kernels: first run on hardware (verified in the CPU emulator only)")])
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
@@ -28,7 +31,7 @@ def test_export_frame_equals_the_reference_host_loop():
         assert np.array_equal(idx, want) and mm == want_mm
         assert len(np.unique(idx)) > 8     # 120 steps: the shock layer is forming (14 levels in the emulator)
         ref = oracle.hyp3d_vis(oracle.hyp3d_params(n, n, n), s.download()[0], s.download()[1], 8)
-        assert np.abs(sch - ref).max() <= 1e-4 * np.abs(ref).max()
+        assert np.abs(sch - ref).max() <= 2e-4 * np.abs(ref).max()     # the bound tests/test_hyp3d_gpu.py holds on hardware
         s.close()
 
 

@@ -2,8 +2,8 @@
 is bit-identical to the reference's kernel bodies compiled for the host, tests/test_oracle_cpu.py) and
 against the reference's own kernels on the same device (oracle/_ref/libref_sw.so).
 
-OPT-IN (TAU_TEST_SW=1): shallow_water.cu was written after the round-1 GPU budget was spent and has not
-run on hardware yet; a never-run kernel must not be able to take the validated suite down with it.  The
+shallow_water.cu was written after the round-1 GPU budget was spent and has not run on hardware yet; a
+never-run kernel must not be able to take the validated suite down with it (see pytestmark below).  The
 bounds below are estimates (fp32, -use_fast_math expf/logf/division on the GPU sides, libm in the oracle);
 with a rough stand-in for the fast intrinsics in the CPU emulator (hostemu.h TAU_HC_ROUGH_FASTMATH) the
 errors are 2e-7 ... 9e-7 for the gentle fields and 3e-5 for the default field, i.e. the bounds have a 20-60x
@@ -17,9 +17,12 @@ import pytest
 import oracle
 from fluid_sims_b200.shallow_water import Params, ShallowWater, initialize_host
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("TAU_TEST_SW") != "1",
-                                 reason="shallow-water kernels not yet validated on hardware (TAU_TEST_SW=1)")]
+# First contact with hardware: the tests RUN, but until a pass has been seen on a B200 (TAU_TEST_SW=1 makes them
+# ordinary tests) a failure is reported as xfailed instead of stopping the validated suite (`-x`), and a pass as
+# xpassed.  The kernels have no polling loops (nothing can hang), and these files sort last, after every
+# validated GPU test.
+pytestmark = [pytest.mark.gpu] + ([] if os.environ.get("TAU_TEST_SW") == "1" else [
+    pytest.mark.xfail(strict=False, reason="shallow-water kernels: first run on hardware (verified in the CPU emulator only)")])
 
 GENTLE = dict(H0=2.0, bumpAmp=0.4, bumpSigma=5, asym=0.3, swirl=0.05, swirlRc=10, offx=3, offy=-2)
 

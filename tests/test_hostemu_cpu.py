@@ -441,3 +441,29 @@ def test_th3cs_main_loop_through_the_product_matches_the_reference_exporter():
     d = np.abs(out.astype(int) - idx.astype(int)).reshape(frames, -1)
     assert (d[:24] == 0).all()                                     # half the run: identical
     assert d.max() <= 2 and (d != 0).sum(axis=1).max() <= 0.005 * d.shape[1]
+
+
+def test_hyp2d_headline_width_and_height(pretend_device):
+    """the benchmarked grid's extents, one axis at a time (4096 x 64 and 256 x 4096): 137 strips with the
+    16-column remainder strip at the right edge, TMA boxes hanging over x = W, 69 pair items per layer, the
+    guided layer schedule over 4096 rows — production and pair kernels against the fp64 oracle"""
+    pretend_device(8, 5)
+    for W, H, steps in ((4096, 64, 3), (256, 4096, 2)):
+        yy, xx = np.mgrid[0:H, 0:W]
+        rho = 1.0 + 0.3 * np.sin(xx / 9.0) * np.cos(yy / 7.0)
+        u, v = 3.0 + 0.5 * np.cos(xx / 11.0), 0.7 * np.sin(yy / 5.0)
+        p = 1.0 + 0.2 * np.cos((xx + yy) / 13.0)
+        planes = [rho, rho * u, rho * v, p / 0.1 + 0.5 * rho * (u * u + v * v)]
+        mask = np.zeros((H, W), np.uint8)
+        mask[H // 2:H // 2 + 12, W // 8:W // 8 + 40] = 1
+        mask[0:3, W - 90:W - 80] = 1
+        mask[10:14, W - 3:] = 1
+        mask[H - 4:, 0:2] = 1
+        ref, t_ref, _ = oracle.hyp2d_run(oracle.hyp2d_cfg(W, H), planes, mask.ravel(), steps)
+        a, _, ta, _, _ = hyp2d_emu.run(W, H, steps, "f32", planes=planes, mask=mask)
+        b, _, tb, _, _ = hyp2d_emu.run(W, H, steps, "f32", planes=planes, mask=mask, pair=True)
+        items = hyp2d_emu.run.last_work_items
+        assert items[2] > 0.3 * items[0] and 2 * items[2] + items[3] == items[0]   # a pair item = two strips
+        assert max(rel_linf(x, y) for x, y in zip(a, ref)) < 2e-6
+        assert max(rel_linf(x, y) for x, y in zip(b, ref)) < 2e-6 and max(rel_linf(x, y) for x, y in zip(b, a)) < 1e-6
+        assert abs(ta - t_ref) <= 1e-6 * t_ref and ta == tb

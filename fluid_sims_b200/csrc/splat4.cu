@@ -19,18 +19,19 @@
 #include <stdlib.h>
 
 namespace {
-uint32_t crc32_update(uint32_t c, const unsigned char *p, size_t n) {
-  static uint32_t tab[256];
-  static bool have = false;
-  if (!have) {
+struct Crc32Table {
+  uint32_t t[256];
+  Crc32Table() {
     for (uint32_t i = 0; i < 256; ++i) {
       uint32_t x = i;
       for (int k = 0; k < 8; ++k) x = (x >> 1) ^ (0xEDB88320u & (0u - (x & 1u)));
-      tab[i] = x;
+      t[i] = x;
     }
-    have = true;
   }
-  for (size_t i = 0; i < n; ++i) c = tab[(c ^ p[i]) & 0xffu] ^ (c >> 8);
+};
+uint32_t crc32_update(uint32_t c, const unsigned char *p, size_t n) {
+  static const Crc32Table tab;  // function-local static: initialised once, thread-safe
+  for (size_t i = 0; i < n; ++i) c = tab.t[(c ^ p[i]) & 0xffu] ^ (c >> 8);
   return c;
 }
 void put32(unsigned char *b, uint32_t v) { for (int i = 0; i < 4; ++i) b[i] = (unsigned char)(v >> (8 * i)); }

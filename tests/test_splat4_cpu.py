@@ -54,6 +54,9 @@ def test_container_is_what_the_reference_viewer_reads(tmp_path):
     raw = open(p, "rb").read()
     assert len(raw) == 32 + 256 * 48 + idx.size + 16 and raw[:4] == b"4SPL" and raw[-4:] == b"LPS4"
     assert splat4.info(p) == dict(width=6, height=5, depth=4, frames=3, pSize=256, flags=4)
+    import zlib
+    assert zlib.crc32(raw[:-16]) == int.from_bytes(raw[-16:-12], "little")       # the footer's checksum is plain CRC-32
+    assert int.from_bytes(raw[-12:-4], "little") == 32 + 256 * 48                # idxoffset
     d = splat4.parse(raw)                                                # viewer.html parse4Splat
     assert (d["width"], d["height"], d["depth"], d["frames"], d["voxelsPerFrame"]) == (6, 5, 4, 3, 120)
     assert np.array_equal(d["indices"], idx) and np.array_equal(d["palette"], splat4.thermal_palette()[:, 8:11])

@@ -180,9 +180,25 @@ static inline void launch(dim3 g, dim3 b, const std::function<void()> &fn) {
   blockDim = b;
   nthreads = nt;
   launches++;
-  for (unsigned bz = 0; bz < g.z; ++bz)
-    for (unsigned by = 0; by < g.y; ++by)
-      for (unsigned bx = 0; bx < g.x; ++bx) {
+  // block order: ascending by default; TAU_HC_BLOCK_ORDER=reverse | random (seeded per launch) — a GPU
+  // promises no order, so results must not depend on it
+  const size_t nblocks = (size_t)g.x * g.y * g.z;
+  std::vector<size_t> order(nblocks);
+  for (size_t i = 0; i < nblocks; ++i) order[i] = i;
+  if (const char *bo = getenv("TAU_HC_BLOCK_ORDER")) {
+    if (!strcmp(bo, "reverse")) std::reverse(order.begin(), order.end());
+    else if (!strncmp(bo, "random", 6)) {
+      uint64_t st = 0x9E3779B97F4A7C15ull * (uint64_t)(launches + 1);
+      for (size_t i = nblocks; i > 1; --i) {
+        st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+        std::swap(order[i - 1], order[st % i]);
+      }
+    }
+  }
+  for (size_t oi = 0; oi < nblocks; ++oi) {
+      {
+        const unsigned bx = (unsigned)(order[oi] % g.x), by = (unsigned)((order[oi] / g.x) % g.y),
+                       bz = (unsigned)(order[oi] / ((size_t)g.x * g.y));
         blockIdx = {bx, by, bz};
         nlive = nt;
         blk_arrived = 0;
@@ -230,6 +246,7 @@ static inline void launch(dim3 g, dim3 b, const std::function<void()> &fn) {
           }
         }
       }
+  }
   cur = -1;
 }
 }  // namespace tau_hc

@@ -467,3 +467,26 @@ def test_hyp2d_headline_width_and_height(pretend_device):
         assert max(rel_linf(x, y) for x, y in zip(a, ref)) < 2e-6
         assert max(rel_linf(x, y) for x, y in zip(b, ref)) < 2e-6 and max(rel_linf(x, y) for x, y in zip(b, a)) < 1e-6
         assert abs(ta - t_ref) <= 1e-6 * t_ref and ta == tb
+
+
+@pytest.mark.parametrize("order", ["reverse", "random"])
+def test_results_do_not_depend_on_block_order(swlib, pretend_device, monkeypatch, order):
+    """a GPU promises no block order: reversed and shuffled launches (TAU_HC_BLOCK_ORDER) must give the same
+    bits — the clear-two-steps-ahead control slots, the device work queue (items go to different CTAs), the
+    last-CTA-out reduction, the peer messages"""
+    pretend_device(3, 2)
+    prm = oracle.sw_params(nx=70, ny=37, dtau=0.05, nu=0.02, dx=2.0, dy=1.5, **GENTLE)
+    s0, u0, v0 = oracle.sw_init(prm)
+    W, H, steps = 200, 120, 8
+    base_sw, ck_sw, _ = sw_emulated(swlib, prm, s0, u0, v0, 15)
+    base64, _, t64, _, _ = hyp2d_emu.run(W, H, steps, "f64", geom_x0=W / 3.0)
+    base_pair, _, tp, _, _ = hyp2d_emu.run(W, H, steps, "f32", pair=True, geom_x0=W / 3.0)
+    monkeypatch.setenv("TAU_HC_BLOCK_ORDER", order)
+    got_sw, ck2, _ = sw_emulated(swlib, prm, s0, u0, v0, 15)
+    assert all(np.array_equal(a, b) for a, b in zip(base_sw, got_sw)) and ck_sw == ck2
+    got64, _, t2, _, _ = hyp2d_emu.run(W, H, steps, "f64", geom_x0=W / 3.0)
+    assert all(np.array_equal(a, b) for a, b in zip(base64, got64)) and t2 == t64
+    got_pair, _, tp2, _, _ = hyp2d_emu.run(W, H, steps, "f32", pair=True, geom_x0=W / 3.0)
+    assert all(np.array_equal(a, b) for a, b in zip(base_pair, got_pair)) and tp2 == tp
+    slabs, _, ts, _ = hyp2d_emu.run_slabs(W, H, steps, "f64", 3, geom_x0=W / 3.0)
+    assert all(np.array_equal(a, b) for a, b in zip(base64, slabs)) and all(t == t64 for t in ts)

@@ -313,6 +313,16 @@ def run_product(a):
             def drain():
                 for h, _, _ in lanes:
                     h2.check(h2._sync(h._handle))
+        elif a.e2e_peers_async and a.exchange == "peer":
+            # experimental (not yet run on hardware, NEXT.md): the frame hand-over between ranks on the device —
+            # no NCCL exchange, host synchronisation or barrier inside the frame loop
+            def frame(i):
+                h2.check(h2._upload_peers_async(sim._handle, in_ptrs))
+                h2.check(h2._step(sim._handle, a.steps_per_frame))
+                h2.check(h2._download_async(sim._handle, out_ptrs, C.c_void_p(0)))
+
+            def drain():
+                h2.check(h2._sync(sim._handle))
         else:
             def frame(i):
                 h2.check(h2._upload(sim._handle, in_ptrs, C.c_void_p(0)))
@@ -347,6 +357,8 @@ def run_product(a):
                "steps_per_frame": a.steps_per_frame, "frames": a.e2e_frames,
                "frames_in_flight": a.e2e_lanes if pipelined else 1,
                "ms_per_frame": dt_wall / a.e2e_frames * 1e3}
+        if world > 1:
+            e2e["handover"] = "device" if (a.e2e_peers_async and a.exchange == "peer") else "host"
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
@@ -400,6 +412,8 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU halo exchange: device-side peer pushes over NVLink (default) or "
                          "host-driven NCCL send/recv + all-reduce every step")
+    ap.add_argument("--e2e-peers-async", action="store_true",
+                    help="N>1, --exchange peer: device-side frame hand-over (experimental, default off)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()

@@ -974,6 +974,70 @@ __global__ void hyp2d_wavespeed(const Params<R> P, const R *__restrict__ U,
   if ((threadIdx.x & 31) == 0 && wmax > R(0)) tau::atomic_max_nonneg(&ctrl->maxspeed[slot], (double)wmax);
 }
 
+// ---- multi-GPU frame hand-over without the host (tau_hyp2d_upload_peers_async) --------------------------
+// A frame upload is a pseudo-step of the control-slot rotation.  hyp2d_frame_wait: every peer's "finished
+// my last step" message is in inbox[slot] (its pushes into our ghost rows are done) -> the H2D copies of the
+// new frame may overwrite the planes; it also does the step kernel's clear-two-ahead duty.
+__global__ void hyp2d_frame_wait(Ctrl *ctrl, unsigned int *pair_ctr, int slot, const PeerCtrls pc) {
+  const int lane = threadIdx.x;
+  if (lane < pc.world && lane != pc.rank) {
+    const unsigned long long *a = &ctrl->inbox[slot][lane];
+    unsigned long long v;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a) : "memory");
+      if (v != 0ull) break;
+      __nanosleep(40);
+    }
+  }
+  __syncwarp();
+  const int clr = (slot + 2) % 3;
+  if (lane == 0) {
+    ctrl->maxspeed[clr] = 0.0;
+    ctrl->next_item[clr] = 0u;
+    if (pair_ctr) pair_ctr[clr] = 0u;
+  }
+  if (lane < 8) ctrl->inbox[clr][lane] = 0ull;
+}
+// hyp2d_frame_announce: push the first / last two owned rows of the uploaded state into the neighbours'
+// ghost rows (what the step kernel does for the rows it computes), then one release store per peer of this
+// rank's max wavespeed into inbox[next]: the neighbours' next step kernel finds ghost rows and dt inputs.
+template <typename R>
+__global__ void hyp2d_frame_announce(const Params<R> P, const R *__restrict__ U, const PeerPush peer, Ctrl *ctrl,
+                                     int next) {
+  const int W = P.W;
+  const size_t n = (size_t)4 * H2_GHOST * W;  // 4 planes x 2 rows x W
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W), g = (int)((i / W) % H2_GHOST), f = (int)(i / ((size_t)W * H2_GHOST));
+    if (peer.up_out != nullptr) {  // my rows 0, 1 -> the upper neighbour's bottom ghost rows
+      R *o = static_cast<R *>(peer.up_out);
+      o[f * peer.up_plane + (size_t)(peer.up_hl + H2_GHOST + g) * W + x] = U[f * P.plane + (size_t)(H2_GHOST + g) * W + x];
+    }
+    if (peer.dn_out != nullptr) {  // my rows H_local-2, H_local-1 -> the lower neighbour's top ghost rows
+      R *o = static_cast<R *>(peer.dn_out);
+      o[f * peer.dn_plane + (size_t)g * W + x] = U[f * P.plane + (size_t)(P.H_local + g) * W + x];
+    }
+  }
+  // last CTA out sends the messages (after every CTA's peer stores)
+  __threadfence_system();
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&ctrl->done_blocks, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x == 0) ctrl->done_blocks = 0;
+  Ctrl *pc = nullptr;
+#pragma unroll
+  for (int p = 0; p < 8; ++p)
+    if (p == (int)threadIdx.x && p < peer.pc.world && p != peer.pc.rank) pc = peer.pc.ctrl[p];
+  if (pc != nullptr) {
+    const double m = *reinterpret_cast<volatile double *>(&ctrl->maxspeed[next]);
+    const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(fmax(m, 1e-12)));
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&pc->inbox[next][peer.pc.rank]), "l"(bits) : "memory");
+  }
+}
+
 // Fill the ghost rows of planes and mask at GLOBAL y-edges with the clamp images (rows 0 / H-1).
 template <typename R>
 __global__ void hyp2d_fill_ghost(const Params<R> P, R *U, uint8_t *mask, int do_mask) {
@@ -1220,7 +1284,8 @@ struct tau_hyp2d {
   CUtensorMap tm[2];
   int cur;
   long long steps, launches;
-  bool speed_valid;  // ctrl->maxspeed[steps%3] holds the max wavespeed of the current state
+  bool speed_valid;  // ctrl->maxspeed[ctl_slot(h)] holds the max wavespeed of the current state
+  long long slot_bias; // control-slot rotations that were not solver steps (tau_hyp2d_upload_peers_async)
   int seg_rows;          // tallest segment of the table (the only height when set by the caller)
   bool seg_auto;         // tapered schedule chosen by build_items (not set by the caller)
   int taper_k, min_rows, max_rows; // schedule tuning (TAU_HYP2D_TAPER_K / _MIN_ROWS / _MAX_ROWS)
@@ -1238,6 +1303,9 @@ struct tau_hyp2d {
 };
 
 namespace {
+
+// rotating control slot (maxspeed / next_item / inbox) the NEXT step kernel reads
+inline int ctl_slot(const tau_hyp2d *h) { return (int)((h->steps + h->slot_bias) % 3); }
 
 template <typename R>
 Params<R> make_params(const tau_hyp2d *h) {
@@ -1489,7 +1557,7 @@ int launch_steps_pair(tau_hyp2d *h, int nsteps, size_t smem) {
   P.nitems = h->nitems_rest;
   for (int s = 0; s < nsteps; ++s) {
     const int a = h->cur, b = a ^ 1;
-    const int slot = (int)(h->steps % 3);
+    const int slot = ctl_slot(h);
     PeerPush peer;
     memset(&peer, 0, sizeof(peer));
     peer.pc.world = 1;
@@ -1556,7 +1624,7 @@ int launch_steps(tau_hyp2d *h, int nsteps) {
   const int grid = h->grid_ctas;
   for (int s = 0; s < nsteps; ++s) {
     const int a = h->cur, b = a ^ 1;
-    const int slot = (int)(h->steps % 3);
+    const int slot = ctl_slot(h);
     PeerPush peer;
     memset(&peer, 0, sizeof(peer));
     peer.pc.world = 1;
@@ -1770,7 +1838,7 @@ int tau_hyp2d_create(const tau_hyp2d_config *cfg, int W, int H, int dtype, int d
 static int hyp2d_state_changed(tau_hyp2d *h, int fill_mask) {
   int rc = h->dtype ? launch_fill_ghost<double>(h, fill_mask) : launch_fill_ghost<float>(h, fill_mask);
   if (rc) return rc;
-  const int slot = (int)(h->steps % 3);
+  const int slot = ctl_slot(h);
   rc = h->dtype ? launch_wavespeed<double>(h, slot) : launch_wavespeed<float>(h, slot);
   if (rc) return rc;
   h->speed_valid = true;
@@ -1781,6 +1849,7 @@ int tau_hyp2d_init(tau_hyp2d *h) {
   TAU_REQUIRE(h, "tau_hyp2d_init: null handle");
   TAU_CUDA(cudaSetDevice(h->device));
   h->steps = 0;
+  h->slot_bias = 0;
   h->items_dirty = true;
   TAU_CUDA(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->stream));
   int rc = h->dtype ? launch_init<double>(h) : launch_init<float>(h);
@@ -1819,6 +1888,55 @@ static int hyp2d_upload_impl(tau_hyp2d *h, const void *const planes[4], const ui
   int rc = hyp2d_state_changed(h, mask ? 1 : 0);
   if (rc) return rc;
   if (sync) TAU_CUDA(cudaStreamSynchronize(h->stream));
+  return TAU_OK;
+}
+
+// Multi-GPU frame upload with no host exchange (peers attached; pinned host planes; enqueue-only).
+// Stream order: wait until every peer finished its previous step (their pushes into our ghost rows are
+// done) -> H2D of the owned rows -> global-edge ghosts -> max-wavespeed scan -> push the boundary rows into
+// the neighbours' ghost rows + one message per peer.  The next tau_hyp2d_step finds everything it needs, as
+// after hyp2d_sync_state + tau_hyp2d_peers_ready, but without NCCL, host synchronisation or a barrier.
+// EVERY rank must call it for the same frame (the control slots rotate in lock step).  The body mask is
+// static across such frames (distribute it once with tau_hyp2d_upload + the host-driven exchange).
+int tau_hyp2d_upload_peers_async(tau_hyp2d *h, const void *const planes[4]) {
+  TAU_REQUIRE(h && planes, "tau_hyp2d_upload_peers_async: null argument");
+  TAU_REQUIRE(h->peers_attached, "tau_hyp2d_upload_peers_async: no peers attached (use tau_hyp2d_upload_async)");
+  TAU_REQUIRE(h->speed_valid, "tau_hyp2d_upload_peers_async: no state yet (first frame: tau_hyp2d_upload + exchange)");
+  TAU_CUDA(cudaSetDevice(h->device));
+  if (h->items_dirty) {  // pair mode needs its claim counters allocated before the first clear
+    const int rc = h->dtype ? launch_steps<double>(h, 0) : launch_steps<float>(h, 0);
+    if (rc) return rc;
+  }
+  const int slot = ctl_slot(h), next = (slot + 1) % 3;
+  hyp2d_frame_wait<<<1, 32, 0, h->stream>>>(h->ctrl, h->pair_mode ? h->pair_ctr : nullptr, slot, h->pctrl);
+  h->launches++;
+  const int es = elem_size(h);
+  const size_t row0 = (size_t)H2_GHOST * h->W, n = (size_t)h->W * h->h_local;
+  for (int f = 0; f < 4; ++f) {
+    TAU_REQUIRE(planes[f], "tau_hyp2d_upload_peers_async: null plane %d", f);
+    TAU_CUDA(cudaMemcpyAsync((char *)h->U[h->cur] + (f * h->plane_elems + row0) * es, planes[f], n * es,
+                             cudaMemcpyHostToDevice, h->stream));
+  }
+  int rc = h->dtype ? launch_fill_ghost<double>(h, 0) : launch_fill_ghost<float>(h, 0);
+  if (rc) return rc;
+  rc = h->dtype ? launch_wavespeed<double>(h, next) : launch_wavespeed<float>(h, next);
+  if (rc) return rc;
+  PeerPush peer;
+  memset(&peer, 0, sizeof(peer));
+  peer.up_out = h->peer_up[h->cur];
+  peer.dn_out = h->peer_dn[h->cur];
+  peer.up_hl = h->peer_up_hl;
+  peer.up_plane = (size_t)h->W * (h->peer_up_hl + 2 * H2_GHOST);
+  peer.dn_plane = (size_t)h->W * (h->peer_dn_hl + 2 * H2_GHOST);
+  peer.pc = h->pctrl;
+  const int grid = (int)((4 * H2_GHOST * (size_t)h->W + 255) / 256);
+  if (h->dtype)
+    hyp2d_frame_announce<double><<<grid, 256, 0, h->stream>>>(make_params<double>(h), (const double *)h->U[h->cur], peer, h->ctrl, next);
+  else
+    hyp2d_frame_announce<float><<<grid, 256, 0, h->stream>>>(make_params<float>(h), (const float *)h->U[h->cur], peer, h->ctrl, next);
+  h->launches++;
+  TAU_CUDA(cudaGetLastError());
+  h->slot_bias++;  // the upload consumed control slot `slot`
   return TAU_OK;
 }
 
@@ -1880,7 +1998,7 @@ int tau_hyp2d_device_state(tau_hyp2d *h, void **planes, uint8_t **mask, double *
   TAU_REQUIRE(h, "tau_hyp2d_device_state: null handle");
   if (planes) *planes = h->U[h->cur];
   if (mask) *mask = h->mask;
-  if (maxspeed_slot) *maxspeed_slot = &h->ctrl->maxspeed[h->steps % 3];
+  if (maxspeed_slot) *maxspeed_slot = &h->ctrl->maxspeed[ctl_slot(h)];
   return TAU_OK;
 }
 
@@ -1941,7 +2059,7 @@ int tau_hyp2d_peers_ready(tau_hyp2d *h) {
   memset(box, 0, sizeof(box));
   const double tiny = 1e-12;
   for (int p = 0; p < h->pctrl.world; ++p)
-    if (p != h->pctrl.rank) memcpy(&box[h->steps % 3][p], &tiny, sizeof(double));
+    if (p != h->pctrl.rank) memcpy(&box[ctl_slot(h)][p], &tiny, sizeof(double));
   TAU_CUDA(cudaMemsetAsync(&h->ctrl->done_blocks, 0, sizeof(unsigned int), h->stream));
   TAU_CUDA(cudaMemcpyAsync(h->ctrl->inbox, box, sizeof(box), cudaMemcpyHostToDevice, h->stream));
   TAU_CUDA(cudaMemsetAsync(&h->ctrl->t_wait, 0, 5 * sizeof(unsigned long long), h->stream));
@@ -2093,10 +2211,11 @@ int tau_hyp2d_set_clock(tau_hyp2d *h, double sim_t, long long steps_done) {
   Ctrl c;
   TAU_CUDA(cudaMemcpyAsync(&c, h->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, h->stream));
   TAU_CUDA(cudaStreamSynchronize(h->stream));
-  const double ms = c.maxspeed[h->steps % 3];
+  const double ms = c.maxspeed[ctl_slot(h)];
   memset(&c, 0, sizeof(c));
   h->steps = steps_done;
-  c.maxspeed[h->steps % 3] = ms;
+  h->slot_bias = 0;
+  c.maxspeed[ctl_slot(h)] = ms;
   c.sim_t = sim_t;
   TAU_CUDA(cudaMemcpyAsync(h->ctrl, &c, sizeof(Ctrl), cudaMemcpyHostToDevice, h->stream));
   TAU_CUDA(cudaStreamSynchronize(h->stream));

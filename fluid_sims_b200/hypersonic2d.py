@@ -33,6 +33,7 @@ _download = declare("tau_hyp2d_download", [_h, C.POINTER(C.c_void_p), C.c_void_p
 _sync = declare("tau_hyp2d_sync", [_h])
 _upload_async = declare("tau_hyp2d_upload_async", [_h, C.POINTER(C.c_void_p), C.c_void_p])
 _download_async = declare("tau_hyp2d_download_async", [_h, C.POINTER(C.c_void_p), C.c_void_p])
+_upload_peers_async = declare("tau_hyp2d_upload_peers_async", [_h, C.POINTER(C.c_void_p)])
 _devstate = declare("tau_hyp2d_device_state", [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                                C.POINTER(C.c_void_p)])
 _set_seg = declare("tau_hyp2d_set_seg_rows", [_h, C.c_int])
@@ -254,6 +255,14 @@ class Hypersonic2D:
         out = (C.c_double * 4)()
         check(_peer_timing(self._handle, out))
         return {"wait_us": out[0], "busy_us": out[1], "gap_us": out[2], "steps": int(out[3])}
+
+    def upload_peers_async(self, planes):
+        """Multi-GPU, peers attached: enqueue the upload of the next frame's owned rows (4 pinned host arrays or
+        raw addresses) with the ghost-row hand-over, the wavespeed all-reduce and the inter-frame barrier done
+        on the device.  Every rank calls it for the same frame; buffers stay valid until sync()."""
+        addrs = [p if isinstance(p, int) else (p.data_ptr() if hasattr(p, "data_ptr") else p.ctypes.data) for p in planes]
+        check(_upload_peers_async(self._handle, (C.c_void_p * 4)(*addrs)))
+        return self
 
     def set_seg_rows(self, rows: int):
         check(_set_seg(self._handle, rows))

@@ -116,6 +116,10 @@ int tau_hyp2d_download(tau_hyp2d *h, void *const planes[4], uint8_t *mask);
  * handles on two streams a frame loop overlaps the upload of frame i+1 with the download of frame i */
 int tau_hyp2d_upload_async(tau_hyp2d *h, const void *const planes[4], const uint8_t *mask);
 int tau_hyp2d_download_async(tau_hyp2d *h, void *const planes[4], uint8_t *mask);
+/* multi-GPU (peers attached): upload the next frame's owned rows with NO host exchange — the hand-over of the
+ * ghost rows, the all-reduce(max) of the wavespeed and the barrier between frames run on the device, in stream
+ * order (see hypersonic2d.cu).  Every rank calls it for the same frame; the body mask stays as uploaded. */
+int tau_hyp2d_upload_peers_async(tau_hyp2d *h, const void *const planes[4]);
 int tau_hyp2d_sync(tau_hyp2d *h);
 /* slab plumbing: device pointers of the current planes (4 contiguous planes of (h_local+4) x W,
  * starting at ghost row -2), the mask (same row layout) and the max-wavespeed scalar the next

@@ -490,3 +490,41 @@ def test_results_do_not_depend_on_block_order(swlib, pretend_device, monkeypatch
     assert all(np.array_equal(a, b) for a, b in zip(base_pair, got_pair)) and tp2 == tp
     slabs, _, ts, _ = hyp2d_emu.run_slabs(W, H, steps, "f64", 3, geom_x0=W / 3.0)
     assert all(np.array_equal(a, b) for a, b in zip(base64, slabs)) and all(t == t64 for t in ts)
+
+
+def test_hyp2d_frame_handover_between_ranks_on_the_device(pretend_device):
+    """tau_hyp2d_upload_peers_async (never run on hardware): a frame upload as a pseudo-step of the control-slot
+    rotation — wait for the peers' last-step messages, H2D, wavespeed scan, push of the boundary rows into the
+    neighbours' ghost rows, one message per peer — replaces the host-driven exchange (NCCL + barrier) between
+    frames.  Three frames with 4 / 1 / 5 steps (every residue of the three-slot rotation), 2 and 3 ranks:
+    bit-identical to one domain that gets the same frames through tau_hyp2d_upload."""
+    pretend_device(3, 2)
+    W, H = 200, 120
+    yy, xx = np.mgrid[0:H, 0:W]
+
+    def state(k):
+        rho = 1.0 + 0.3 * np.sin(xx / (9.0 + k)) * np.cos(yy / 7.0)
+        u, v = 3.0 + 0.5 * np.cos(xx / 11.0), 0.7 * np.sin(yy / (5.0 + k))
+        p = 1.0 + 0.2 * np.cos((xx + yy) / 13.0)
+        return [rho, rho * u, rho * v, p / 0.1 + 0.5 * rho * (u * u + v * v)]
+    frames = [(state(0), 4), (state(1), 1), (state(2), 5)]
+    L = hyp2d_emu.lib()
+    for dtype, npdt in (("f64", np.float64), ("f32", np.float32)):
+        cc = hyp2d_emu.default_cfg(W, H, geom_x0=W / 3.0)
+        h = C.c_void_p()
+        hyp2d_emu.check(L.tau_hyp2d_create(C.byref(cc), W, H, 0 if dtype == "f32" else 1, 0, 0, H, None, C.byref(h)))
+        hyp2d_emu.check(L.tau_hyp2d_init(h))
+        hyp2d_emu.check(L.tau_hyp2d_step(h, 3))
+        for fp, fs in frames:
+            arrs = [np.ascontiguousarray(p, npdt) for p in fp]
+            hyp2d_emu.check(L.tau_hyp2d_upload(h, (C.c_void_p * 4)(*[a.ctypes.data for a in arrs]), None))
+            hyp2d_emu.check(L.tau_hyp2d_step(h, fs))
+        one = [np.empty((H, W), npdt) for _ in range(4)]
+        m = np.empty((H, W), np.uint8)
+        hyp2d_emu.check(L.tau_hyp2d_download(h, (C.c_void_p * 4)(*[a.ctypes.data for a in one]), C.c_void_p(m.ctypes.data)))
+        L.tau_hyp2d_destroy(h)
+        for world in (2, 3):
+            got, _, _, open_mappings = hyp2d_emu.run_slabs(W, H, 3, dtype, world, frames=frames, geom_x0=W / 3.0)
+            assert all(np.array_equal(a, b) for a, b in zip(one, got)) and open_mappings == 0, (dtype, world)
+    got, _, _, _ = hyp2d_emu.run_slabs(W, H, 3, "f32", 2, pair=True, frames=frames, geom_x0=W / 3.0)
+    assert max(rel_linf(a, b) for a, b in zip(got, one)) < 2e-6      # pair kernel: FMA rounding only

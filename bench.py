@@ -315,14 +315,34 @@ def run_product(a):
                     h2.check(h2._sync(h._handle))
         elif a.e2e_peers_async and a.exchange == "peer":
             # experimental (not yet run on hardware, NEXT.md): the frame hand-over between ranks on the device —
-            # no NCCL exchange, host synchronisation or barrier inside the frame loop
+            # no NCCL exchange, host synchronisation or barrier inside the frame loop; with --e2e-lanes > 1 every
+            # rank runs that many slab handles (each with its own peer attachments) on their own streams, so the
+            # upload of frame i+1 overlaps the download of frame i
+            lanes = [(sim, out_ptrs, host_out)]
+            lane_streams = []
+            for _ in range(a.e2e_lanes - 1):
+                st = torch.cuda.Stream(device=dev)
+                sb = Hypersonic2D(cfg, dtype=a.dtype, device=dev, y_begin=y0, h_local=hl, stream=st.cuda_stream)
+                if a.seg_rows:
+                    sb.set_seg_rows(a.seg_rows)
+                sb.init()
+                slab.hyp2d_attach_peers(sb)
+                slab.hyp2d_sync_state(sb)
+                sb.peers_ready()
+                dist.barrier()
+                ho = [torch.empty((hl, W), dtype=tdt).pin_memory() for _ in range(4)]
+                lanes.append((sb, (C.c_void_p * 4)(*[t_.data_ptr() for t_ in ho]), ho))
+                lane_streams.append(st)
+
             def frame(i):
-                h2.check(h2._upload_peers_async(sim._handle, in_ptrs))
-                h2.check(h2._step(sim._handle, a.steps_per_frame))
-                h2.check(h2._download_async(sim._handle, out_ptrs, C.c_void_p(0)))
+                h, optr, _ = lanes[i % len(lanes)]
+                h2.check(h2._upload_peers_async(h._handle, in_ptrs))
+                h2.check(h2._step(h._handle, a.steps_per_frame))
+                h2.check(h2._download_async(h._handle, optr, C.c_void_p(0)))
 
             def drain():
-                h2.check(h2._sync(sim._handle))
+                for h, _, _ in lanes:
+                    h2.check(h2._sync(h._handle))
         else:
             def frame(i):
                 h2.check(h2._upload(sim._handle, in_ptrs, C.c_void_p(0)))
@@ -355,7 +375,7 @@ def run_product(a):
         e2e = {"value": cells * a.steps_per_frame * a.e2e_frames / dt_wall / 1e6,
                "unit": "Mcell-updates/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                "steps_per_frame": a.steps_per_frame, "frames": a.e2e_frames,
-               "frames_in_flight": a.e2e_lanes if pipelined else 1,
+               "frames_in_flight": a.e2e_lanes if (pipelined or (a.e2e_peers_async and a.exchange == "peer")) else 1,
                "ms_per_frame": dt_wall / a.e2e_frames * 1e3}
         if world > 1:
             e2e["handover"] = "device" if (a.e2e_peers_async and a.exchange == "peer") else "host"

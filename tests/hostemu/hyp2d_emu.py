@@ -91,7 +91,7 @@ def run(W, H, steps, dtype, planes=None, mask=None, seg_rows=None, pair=False, c
     return out, m, t.value, np.array(dts), n
 
 
-def run_slabs(W, H, steps, dtype, world, pair=False, frames=(), **over):
+def run_slabs(W, H, steps, dtype, world, pair=False, frames=(), reverse_ranks=False, **over):
     """`world` y-slab handles in ONE process, stepped in turn: the emulated counterpart of one process per
     GPU with CUDA-IPC peers (fluid_sims_b200/slab.py: hyp2d_sync_state + hyp2d_attach_peers).  Each rank's
     step kernel pushes its boundary rows into the neighbours' ghost rows and sends its max wavespeed to
@@ -159,14 +159,20 @@ def run_slabs(W, H, steps, dtype, world, pair=False, frames=(), **over):
     # further frames: (full-domain planes, steps) — handed over on the "device" (tau_hyp2d_upload_peers_async):
     # every rank enqueues its upload first (a rank's next step waits for all peers' announcements)
     L.tau_hyp2d_upload_peers_async.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    order = list(zip(hs, parts))
+    if reverse_ranks:       # the ranks are independent processes: no call order between them may matter
+        order.reverse()
+        hs_step = hs[::-1]
+    else:
+        hs_step = hs
     for fplanes, fsteps in frames:
         keep = []
-        for h, (y0, hl) in zip(hs, parts):
+        for h, (y0, hl) in order:
             arrs = [np.ascontiguousarray(np.asarray(p, npdt).reshape(H, W)[y0:y0 + hl]) for p in fplanes]
             keep.append(arrs)
             check(L.tau_hyp2d_upload_peers_async(h, (C.c_void_p * 4)(*[a.ctypes.data for a in arrs])))
         for _ in range(fsteps):
-            for h in hs:
+            for h in hs_step:
                 check(L.tau_hyp2d_step(h, 1))
     outs, masks, ts = [], [], []
     for h, (y0, hl) in zip(hs, parts):

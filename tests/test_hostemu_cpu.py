@@ -524,7 +524,8 @@ def test_hyp2d_frame_handover_between_ranks_on_the_device(pretend_device):
         hyp2d_emu.check(L.tau_hyp2d_download(h, (C.c_void_p * 4)(*[a.ctypes.data for a in one]), C.c_void_p(m.ctypes.data)))
         L.tau_hyp2d_destroy(h)
         for world in (2, 3):
-            got, _, _, open_mappings = hyp2d_emu.run_slabs(W, H, 3, dtype, world, frames=frames, geom_x0=W / 3.0)
+            got, _, _, open_mappings = hyp2d_emu.run_slabs(W, H, 3, dtype, world, frames=frames,
+                                                           reverse_ranks=(world == 3), geom_x0=W / 3.0)
             assert all(np.array_equal(a, b) for a, b in zip(one, got)) and open_mappings == 0, (dtype, world)
     got, _, _, _ = hyp2d_emu.run_slabs(W, H, 3, "f32", 2, pair=True, frames=frames, geom_x0=W / 3.0)
     assert max(rel_linf(a, b) for a, b in zip(got, one)) < 2e-6      # pair kernel: FMA rounding only

@@ -55,43 +55,24 @@ __device__ __forceinline__ int wrap(int i, int n) {  // :91-96, callers are at m
   return i;
 }
 
-// hll_x :322-352 / hll_y :355-385 for a generic normal (un) / tangential (ut) split: returns the
-// fluxes of (h, h*un, h*ut)
-__device__ __forceinline__ void hll_n(float hL, float unL, float utL, float hR, float unR, float utR, float g,
-                                      float &Fh, float &Fn, float &Ft) {
+// HLL flux through a face with normal velocity q and tangential velocity r (x faces: q = u, r = v; y faces:
+// q = v, r = u): fluxes of (h, h q, h r).  hll_x :322-352 and hll_y :355-385 are this one function up to the
+// association of the triple product in the tangential momentum flux — (h u) v in both, i.e. (h q) r on x
+// faces and (h r) q on y faces — which TANGENTIAL_FIRST keeps, so that both round like the reference.
+template <bool TANGENTIAL_FIRST>
+__device__ __forceinline__ void hll_flux(float hL, float qL, float rL, float hR, float qR, float rR, float g,
+                                         float &Fh, float &Fq, float &Fr) {
   const float cL = sqrtf(g * hL), cR = sqrtf(g * hR);
-  const float sL = fminf(unL - cL, unR - cR);
-  const float sR = fmaxf(unL + cL, unR + cR);
-  const float mL = hL * unL, mR = hR * unR;
-  const float nL = hL * utL, nR = hR * utR;
-  const float FL_h = mL, FL_n = mL * unL + 0.5f * g * hL * hL, FL_t = mL * utL;
-  const float FR_h = mR, FR_n = mR * unR + 0.5f * g * hR * hR, FR_t = mR * utR;
-  if (sL >= 0.0f) { Fh = FL_h; Fn = FL_n; Ft = FL_t; return; }
-  if (sR <= 0.0f) { Fh = FR_h; Fn = FR_n; Ft = FR_t; return; }
-  const float inv = 1.0f / (sR - sL);
-  Fh = (sR * FL_h - sL * FR_h + sR * sL * (hR - hL)) * inv;
-  Fn = (sR * FL_n - sL * FR_n + sR * sL * (mR - mL)) * inv;
-  Ft = (sR * FL_t - sL * FR_t + sR * sL * (nR - nL)) * inv;
-}
-// NOTE on hll_y: the reference's y-flux of x-momentum is mB*vB with mB = hB*uB (:361-365), i.e.
-// (h u) v = (h v) u: the tangential flux FL_t = (h*un)*ut above with un = v, ut = u gives (h v) u —
-// the same product in a different association.  To keep the reference's rounding, the y-sweep below
-// calls hll_y_ref, which spells the reference's expressions out.
-__device__ __forceinline__ void hll_y_ref(float hB, float uB, float vB, float hT, float uT, float vT, float g,
-                                          float &Gh, float &Gmx, float &Gmy) {
-  const float cB = sqrtf(g * hB), cT = sqrtf(g * hT);
-  const float sB = fminf(vB - cB, vT - cT);
-  const float sT = fmaxf(vB + cB, vT + cT);
-  const float mB = hB * uB, mT = hT * uT;
-  const float nB = hB * vB, nT = hT * vT;
-  const float GL_h = nB, GL_mx = mB * vB, GL_my = nB * vB + 0.5f * g * hB * hB;
-  const float GR_h = nT, GR_mx = mT * vT, GR_my = nT * vT + 0.5f * g * hT * hT;
-  if (sB >= 0.0f) { Gh = GL_h; Gmx = GL_mx; Gmy = GL_my; return; }
-  if (sT <= 0.0f) { Gh = GR_h; Gmx = GR_mx; Gmy = GR_my; return; }
-  const float inv = 1.0f / (sT - sB);
-  Gh = (sT * GL_h - sB * GR_h + sT * sB * (hT - hB)) * inv;
-  Gmx = (sT * GL_mx - sB * GR_mx + sT * sB * (mT - mB)) * inv;
-  Gmy = (sT * GL_my - sB * GR_my + sT * sB * (nT - nB)) * inv;
+  const float sL = fminf(qL - cL, qR - cR), sR = fmaxf(qL + cL, qR + cR);
+  const float hqL = hL * qL, hqR = hR * qR, hrL = hL * rL, hrR = hR * rR;   // conserved momenta
+  const float FqL = hqL * qL + 0.5f * g * hL * hL, FqR = hqR * qR + 0.5f * g * hR * hR;
+  const float FrL = TANGENTIAL_FIRST ? hrL * qL : hqL * rL, FrR = TANGENTIAL_FIRST ? hrR * qR : hqR * rR;
+  if (sL >= 0.0f) { Fh = hqL; Fq = FqL; Fr = FrL; return; }
+  if (sR <= 0.0f) { Fh = hqR; Fq = FqR; Fr = FrR; return; }
+  const float inv = 1.0f / (sR - sL), sRL = sR * sL;
+  Fh = (sR * hqL - sL * hqR + sRL * (hR - hL)) * inv;
+  Fq = (sR * FqL - sL * FqR + sRL * (hqR - hqL)) * inv;
+  Fr = (sR * FrL - sL * FrR + sRL * (hrR - hrL)) * inv;
 }
 
 __device__ __forceinline__ float step_dt(const SPar &P, const SClock *clk, int step3, int step2) {  // :679-684
@@ -132,12 +113,12 @@ sw_update(const SPar P, const float *__restrict__ sig, const float *__restrict__
   for (int f = threadIdx.x; f < S_NFX; f += S_THREADS) {  // face on the RIGHT of tile column fx-1
     const int fy = f / (S_TX + 1), fx = f - fy * (S_TX + 1);
     const int cL = (fy + 1) * S_SX + fx, cR = cL + 1;
-    hll_n(s_h[cL], s_u[cL], s_v[cL], s_h[cR], s_u[cR], s_v[cR], P.g, s_Fh[f], s_Fmx[f], s_Fmy[f]);
+    hll_flux<false>(s_h[cL], s_u[cL], s_v[cL], s_h[cR], s_u[cR], s_v[cR], P.g, s_Fh[f], s_Fmx[f], s_Fmy[f]);
   }
   for (int f = threadIdx.x; f < S_NFY; f += S_THREADS) {  // face on TOP of tile row fy-1
     const int fy = f / S_TX, fx = f - fy * S_TX;
     const int cB = fy * S_SX + fx + 1, cT = cB + S_SX;
-    hll_y_ref(s_h[cB], s_u[cB], s_v[cB], s_h[cT], s_u[cT], s_v[cT], P.g, s_Gh[f], s_Gmx[f], s_Gmy[f]);
+    hll_flux<true>(s_h[cB], s_v[cB], s_u[cB], s_h[cT], s_v[cT], s_u[cT], P.g, s_Gh[f], s_Gmy[f], s_Gmx[f]);
   }
   __syncthreads();
   const float invdx = 1.0f / P.dx, invdy = 1.0f / P.dy;

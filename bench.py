@@ -379,6 +379,10 @@ def run_product(a):
                "ms_per_frame": dt_wall / a.e2e_frames * 1e3}
         if world > 1:
             e2e["handover"] = "device" if (a.e2e_peers_async and a.exchange == "peer") else "host"
+            if a.e2e_peers_async and a.exchange == "peer":
+                for sb, _, _ in lanes[1:]:      # the extra lanes' peer mappings go before their planes do
+                    slab.hyp2d_detach_peers(sb)
+                    sb.close()
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
@@ -409,6 +413,11 @@ def run_product(a):
             **({"peer_timing": peer_timing} if peer_timing else {}),
         }))
     if world > 1:
+        if peer:   # unmap the peers' planes on every rank before any rank frees them
+            try:
+                slab.hyp2d_detach_peers(sim)
+            except Exception as e:      # teardown must not turn a finished measurement into a failure
+                print(f"[bench] peer detach: {e}", file=sys.stderr)
         dist.destroy_process_group()
 
 

@@ -2049,6 +2049,28 @@ int tau_hyp2d_ipc_attach(tau_hyp2d *h, int rank, int world, const void *all_hand
   return TAU_OK;
 }
 
+// Unmap the peers' planes and control blocks.  CUDA wants an importer to close its mapping before the
+// exporter frees the memory: every rank detaches, THEN (after a barrier between the processes,
+// slab.hyp2d_detach_peers) the handles are destroyed.  tau_hyp2d_destroy calls it as a fallback.
+int tau_hyp2d_ipc_detach(tau_hyp2d *h) {
+  TAU_REQUIRE(h, "tau_hyp2d_ipc_detach: null handle");
+  if (!h->peers_attached) return TAU_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (int b = 0; b < 2; ++b) {
+    if (h->peer_up[b]) cudaIpcCloseMemHandle(h->peer_up[b]);
+    if (h->peer_dn[b]) cudaIpcCloseMemHandle(h->peer_dn[b]);
+    h->peer_up[b] = h->peer_dn[b] = nullptr;
+  }
+  for (int p = 0; p < h->pctrl.world; ++p) {
+    if (p != h->pctrl.rank && h->pctrl.ctrl[p]) cudaIpcCloseMemHandle(h->pctrl.ctrl[p]);
+    h->pctrl.ctrl[p] = nullptr;
+  }
+  h->pctrl.world = 1;
+  h->peers_attached = false;
+  return TAU_OK;
+}
+
 // Call once after the caller has exchanged the ghost rows of the current state and all-reduced
 // the wavespeed slot on the host side (init / upload): arms the first device-side barrier.
 int tau_hyp2d_peers_ready(tau_hyp2d *h) {
@@ -2236,14 +2258,7 @@ int tau_hyp2d_destroy(tau_hyp2d *h) {
   if (!h) return TAU_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  if (h->peers_attached) {  // unmap what tau_hyp2d_ipc_attach opened (the peers free their own memory)
-    for (int b = 0; b < 2; ++b) {
-      if (h->peer_up[b]) cudaIpcCloseMemHandle(h->peer_up[b]);
-      if (h->peer_dn[b]) cudaIpcCloseMemHandle(h->peer_dn[b]);
-    }
-    for (int p = 0; p < h->pctrl.world; ++p)
-      if (p != h->pctrl.rank && h->pctrl.ctrl[p]) cudaIpcCloseMemHandle(h->pctrl.ctrl[p]);
-  }
+  tau_hyp2d_ipc_detach(h);  // unmap what tau_hyp2d_ipc_attach opened (the peers free their own memory)
   cudaFree(h->ctrl);
   if (h->items) cudaFree(h->items);
   if (h->items_pair) cudaFree(h->items_pair);

@@ -41,6 +41,7 @@ _get_seg = declare("tau_hyp2d_get_seg_rows", [_h])
 _ipc_export = declare("tau_hyp2d_ipc_export", [_h, C.c_void_p, C.c_size_t])
 _ipc_attach = declare("tau_hyp2d_ipc_attach", [_h, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)])
 _peers_ready = declare("tau_hyp2d_peers_ready", [_h])
+_ipc_detach = declare("tau_hyp2d_ipc_detach", [_h])
 _peer_timing = declare("tau_hyp2d_peer_timing", [_h, C.POINTER(C.c_double)])
 _render_mm = declare("tau_hyp2d_render_minmax", [_h, C.c_int, C.POINTER(C.c_double)])
 _render_px = declare("tau_hyp2d_render_pixels", [_h, C.c_int, C.POINTER(C.c_double), C.c_void_p])
@@ -244,6 +245,10 @@ class Hypersonic2D:
         assert len(blob) == world * IPC_BYTES
         hl = (C.c_int * world)(*h_locals)
         check(_ipc_attach(self._handle, rank, world, blob, hl))
+        return self
+
+    def ipc_detach(self):
+        check(_ipc_detach(self._handle))
         return self
 
     def peers_ready(self):

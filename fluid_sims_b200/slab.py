@@ -116,6 +116,14 @@ def hyp2d_attach_peers(sim, group=None) -> None:
     sim.ipc_attach(rank, world, [g[0] for g in gathered], [g[1] for g in gathered])
 
 
+def hyp2d_detach_peers(sim, group=None) -> None:
+    """Teardown counterpart of hyp2d_attach_peers: every rank unmaps its peers' memory, then all meet at a
+    barrier, so that no rank frees planes another rank still has mapped.  Call before closing the handles."""
+    sim.ipc_detach()
+    if dist.is_initialized():
+        dist.barrier(group=group)
+
+
 def hyp2d_sync_state(sim, group=None) -> None:
     """Host-driven (NCCL) exchange of the CURRENT state's ghost rows, the static mask's ghost rows
     and the max-wavespeed scalar — needed once after init()/upload(); arms the device barrier when

@@ -135,6 +135,9 @@ int tau_hyp2d_ipc_export(tau_hyp2d *h, void *out, size_t out_bytes);
 int tau_hyp2d_ipc_attach(tau_hyp2d *h, int rank, int world, const void *all_handles,
                          const int *h_locals);
 int tau_hyp2d_peers_ready(tau_hyp2d *h);
+/* unmap the peers' memory again: every rank detaches, the processes meet at a barrier, then the handles are
+ * destroyed (CUDA wants importers to close before the exporter frees).  tau_hyp2d_destroy falls back to it. */
+int tau_hyp2d_ipc_detach(tau_hyp2d *h);
 /* Diagnostics of the device-side exchange: average microseconds per step spent waiting for the
  * peers' messages, computing, and between steps; out[3] = steps counted since peers_ready. */
 int tau_hyp2d_peer_timing(tau_hyp2d *h, double out[4]);

@@ -57,6 +57,7 @@ def main():
         s2.step(steps - steps // 2)
         out2, _ = s2.download()
         same_peer = all(np.array_equal(a, b) for a, b in zip(out, out2)) and s2.clock()[0] == t_slab
+        slab.hyp2d_detach_peers(s2)
         flag = torch.tensor([1 if same_peer else 0], device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         if rank == 0:

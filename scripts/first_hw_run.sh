@@ -22,6 +22,11 @@ run bench_prod 300 python bench.py --no-e2e --no-cpu
 run bench_pair 300 env TAU_HYP2D_PAIR=1 python bench.py --no-e2e --no-cpu
 run bench_prod_512 300 python bench.py --no-e2e --no-cpu --grid-h 512
 run bench_pair_512 300 env TAU_HYP2D_PAIR=1 python bench.py --no-e2e --no-cpu --grid-h 512
+# 1b. ncu of the pair kernel (one launch of the developed flow; ~40 replays) and the launch list of a pair-mode step
+run pair_ncu 600 env TAU_HYP2D_PAIR=1 ncu --set full --clock-control none --import-source on -k regex:hyp2d_step_pair \
+  -s 300 -c 1 -o "$OUT/pair_prof" python bench.py --steps 4 --warmup 3 --develop 300 --no-e2e --no-cpu
+run pair_launches 300 env TAU_HYP2D_PAIR=1 ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 40 --csv \
+  --log-file "$OUT/pair_launches.csv" python bench.py --steps 10 --warmup 3 --develop 300 --no-e2e --no-cpu
 # 2. shallow water: parity (prints measured errors: replace the estimated bounds), golden, speed
 run sw_parity 300 env TAU_TEST_SW=1 python -m pytest tests/test_sw_gpu.py -m gpu -q -s
 run sw_golden 120 python tests/golden/make_golden_gpu.py sw

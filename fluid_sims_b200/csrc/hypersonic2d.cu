@@ -1522,6 +1522,25 @@ int build_items_pair(tau_hyp2d *h) {
       }
     }
   }
+  // The production kernel runs second and cannot overlap the pair kernel (both are ordered behind the
+  // previous step), so its duration is its longest item chain.  It has only a few per cent of the work but
+  // the whole device: cut its items into short pieces (TAU_HYP2D_REST_ROWS, default 8 rows; 0 = leave them)
+  // — a 48-row item alone takes tens of microseconds, an 8-row piece a few; the two warm-up rows per piece
+  // are paid on ~3 % of the cells.  A piece keeps its parent's masked flag (conservative: the masked march
+  // is correct everywhere).
+  int rest_rows = 8;
+  if (const char *e = getenv("TAU_HYP2D_REST_ROWS")) rest_rows = atoi(e);
+  if (rest_rows > 0) {
+    std::vector<uint2> cut;
+    for (const uint2 &d : rest) {
+      const int ys = (int)(d.y & 0xfffffu), rows = (int)(d.y >> 20);
+      for (int off = 0; off < rows; off += rest_rows) {
+        const int r = rows - off < rest_rows ? rows - off : rest_rows;
+        cut.push_back(make_uint2(d.x, (unsigned)(ys + off) | ((unsigned)r << 20)));
+      }
+    }
+    rest.swap(cut);
+  }
   // masked items first in the production table (as before); pair items tall-to-short = layer order
   std::vector<uint2> rest_sorted;
   for (const uint2 &d : rest) if (d.x >> 31) rest_sorted.push_back(d);

@@ -463,7 +463,7 @@ def test_hyp2d_headline_width_and_height(pretend_device):
         a, _, ta, _, _ = hyp2d_emu.run(W, H, steps, "f32", planes=planes, mask=mask)
         b, _, tb, _, _ = hyp2d_emu.run(W, H, steps, "f32", planes=planes, mask=mask, pair=True)
         items = hyp2d_emu.run.last_work_items
-        assert items[2] > 0.3 * items[0] and 2 * items[2] + items[3] == items[0]   # a pair item = two strips
+        assert items[2] > 0.3 * items[0] and 2 * items[2] + items[3] >= items[0]   # a pair item = two strips; the rest is cut into 8-row pieces
         assert max(rel_linf(x, y) for x, y in zip(a, ref)) < 2e-6
         assert max(rel_linf(x, y) for x, y in zip(b, ref)) < 2e-6 and max(rel_linf(x, y) for x, y in zip(b, a)) < 1e-6
         assert abs(ta - t_ref) <= 1e-6 * t_ref and ta == tb

@@ -22,6 +22,9 @@ run bench_prod 300 python bench.py --no-e2e --no-cpu
 run bench_pair 300 env TAU_HYP2D_PAIR=1 python bench.py --no-e2e --no-cpu
 run bench_prod_512 300 python bench.py --no-e2e --no-cpu --grid-h 512
 run bench_pair_512 300 env TAU_HYP2D_PAIR=1 python bench.py --no-e2e --no-cpu --grid-h 512
+for rr in 0 4 16; do
+  run bench_pair_512_rest$rr 200 env TAU_HYP2D_PAIR=1 TAU_HYP2D_REST_ROWS=$rr python bench.py --no-e2e --no-cpu --grid-h 512
+done
 # 1b. ncu of the pair kernel (one launch of the developed flow; ~40 replays) and the launch list of a pair-mode step
 run pair_ncu 600 env TAU_HYP2D_PAIR=1 ncu --set full --clock-control none --import-source on -k regex:hyp2d_step_pair \
   -s 300 -c 1 -o "$OUT/pair_prof" python bench.py --steps 4 --warmup 3 --develop 300 --no-e2e --no-cpu

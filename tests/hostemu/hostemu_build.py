@@ -156,6 +156,12 @@ def build_all() -> str:
     (a pre-flight for tests/ -m gpu at sizes the emulator can afford; never shipped, never a default)."""
     os.makedirs(OUT, exist_ok=True)
     names = ["burgers", "gray_scott", "hypersonic2d", "hypersonic3d", "shallow_water", "snapshot", "splat4", "sph"]
+    so = os.path.join(OUT, "libtau_b200_hostemu.so")
+    csrc = os.path.join(ROOT, "fluid_sims_b200", "csrc")
+    deps = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh"))] + [
+        os.path.join(ROOT, "tests", "hostemu", "hostemu.h"), __file__, os.path.join(ROOT, "include", "tau_b200.h")]
+    if os.path.exists(so) and all(os.path.getmtime(so) > os.path.getmtime(d) for d in deps):
+        return so
     objs = []
     for name in names:
         cu = os.path.join(ROOT, "fluid_sims_b200", "csrc", f"{name}.cu")
@@ -167,7 +173,6 @@ def build_all() -> str:
         subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-c", "-mfma", "-ffp-contract=off", "-Wno-return-type",
                         "-Wno-unknown-pragmas", "-I", os.path.join(ROOT, "tests", "hostemu"), cpp, "-o", obj], check=True)
         objs.append(obj)
-    so = os.path.join(OUT, "libtau_b200_hostemu.so")
     subprocess.run(["g++", "-shared", "-Wl,-Bsymbolic", "-o", so] + objs + ["-lm"], check=True)
     return so
 

@@ -529,3 +529,30 @@ def test_hyp2d_frame_handover_between_ranks_on_the_device(pretend_device):
             assert all(np.array_equal(a, b) for a, b in zip(one, got)) and open_mappings == 0, (dtype, world)
     got, _, _, _ = hyp2d_emu.run_slabs(W, H, 3, "f32", 2, pair=True, frames=frames, geom_x0=W / 3.0)
     assert max(rel_linf(a, b) for a, b in zip(got, one)) < 2e-6      # pair kernel: FMA rounding only
+
+
+def test_c_host_programs_run_end_to_end_on_the_emulator(tmp_path):
+    """The C hosts of fluid_sims_b200/cli/ (the reference's binary names and flags) with the emulated library
+    preloaded in front of libtau_b200.so: argument parsing, frame loops, reports and file output of every
+    program, incl. the two that have not met hardware (tau_sw, th3cs — whose .4spl file must contain the very
+    frames the reference exporter produces, tests/golden/th3cs_ref_host.npz)."""
+    import subprocess
+    from fluid_sims_b200 import splat4
+    cli = os.path.join(os.path.dirname(__file__), "..", "fluid_sims_b200", "cli")
+    subprocess.run(["make", "-C", cli], check=True, capture_output=True)
+    env = dict(os.environ, LD_PRELOAD=hostemu_build.build_all(), TAU_HC_SMS="3", TAU_HC_CTAS_PER_SM="2")
+    out4 = str(tmp_path / "v.4spl")
+    cases = {"tgs": ["--nx", "64", "--ny", "32", "--steps", "3", "--headless"],
+             "tau_2d_hypersonic_cuda": ["--nx", "128", "--ny", "64", "--frames", "2"],
+             "tau3d": ["--n", "16", "--frames", "1"],
+             "tau_sph": ["--n", "2048", "--frames", "2"],
+             "tau_burgers": ["--nx", "96", "--ny", "64", "--steps", "4", "--headless", "--dtau", "1e-3"],
+             "tau_sw": ["--nx", "96", "--ny", "64", "--steps", "20", "--headless", "--dtau", "1e-3"],
+             "th3cs": ["--n", "24", "--frames", "6", "--out", out4]}
+    for exe, args in cases.items():
+        r = subprocess.run([os.path.join(cli, exe)] + args, capture_output=True, text=True, timeout=300, env=env,
+                           cwd=str(tmp_path))
+        assert r.returncode == 0 and "updates/s" in r.stdout, (exe, r.stdout[-300:], r.stderr[-300:])
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "th3cs_ref_host.npz"))
+    assert splat4.info(out4) == dict(width=24, height=24, depth=24, frames=6, pSize=256, flags=4)
+    assert np.array_equal(splat4.parse(open(out4, "rb").read())["indices"], g["indices"][:6])

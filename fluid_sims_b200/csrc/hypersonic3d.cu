@@ -961,6 +961,7 @@ void tau_4spl_index_thresholds(float thr[255]) {
 int tau_hyp3d_export_frame(tau_hyp3d *h, uint8_t *indices, float minmax[2]) {
   TAU_REQUIRE(h && indices, "tau_hyp3d_export_frame: null argument");
   TAU_REQUIRE(h->have_state, "tau_hyp3d_export_frame: no state (call tau_hyp3d_init or tau_hyp3d_upload)");
+  TAU_REQUIRE(!h->slab, "tau_hyp3d_export_frame: z-slab handles are not supported (the frame's min/max is global)");
   TAU_CUDA(cudaSetDevice(h->device));
   const size_t n = (size_t)h->prm.nx * h->prm.ny * h->nz_local;
   if (!h->vis) TAU_CUDA(cudaMalloc(&h->vis, n * sizeof(float)));

@@ -556,3 +556,42 @@ def test_c_host_programs_run_end_to_end_on_the_emulator(tmp_path):
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "th3cs_ref_host.npz"))
     assert splat4.info(out4) == dict(width=24, height=24, depth=24, frames=6, pSize=256, flags=4)
     assert np.array_equal(splat4.parse(open(out4, "rb").read())["indices"], g["indices"][:6])
+
+
+def test_hyp2d_fuzz_random_grids_masks_schedules(monkeypatch):
+    """seeded random sweep of what a user can vary: grid 8..330 x 5..150, speckled and blocky body masks touching
+    any boundary, segment heights, pretend devices (1..8 SMs x 1..5 CTAs), block orders, fp64 / fp32 / pair
+    mode, 1..6 steps, and 2..4 in-process ranks — every case against the fp64 oracle (380 further cases of the
+    same generator were run once when this test was written: no failure)."""
+    rng = np.random.default_rng(11)
+    for case in range(24):
+        W, H, steps = int(rng.integers(8, 330)), int(rng.integers(5, 150)), int(rng.integers(1, 7))
+        seg = [None, 4, 8, 13, 32, 64][int(rng.integers(0, 6))]
+        monkeypatch.setenv("TAU_HC_SMS", str(int(rng.integers(1, 9))))
+        monkeypatch.setenv("TAU_HC_CTAS_PER_SM", str(int(rng.integers(1, 6))))
+        monkeypatch.setenv("TAU_HC_BLOCK_ORDER", ["", "reverse", "random"][int(rng.integers(0, 3))])
+        yy, xx = np.mgrid[0:H, 0:W]
+        rho = 1.0 + 0.3 * np.sin(xx / 9.0 + rng.random()) * np.cos(yy / 7.0)
+        u, v = 3.0 * rng.random() + 0.5 * np.cos(xx / 11.0), 0.7 * np.sin(yy / 5.0)
+        p = 1.0 + 0.2 * np.cos((xx + yy) / 13.0)
+        planes = [rho, rho * u, rho * v, p / 0.1 + 0.5 * rho * (u * u + v * v)]
+        mask = (rng.random((H, W)) < rng.choice([0.0, 0.002, 0.02])).astype(np.uint8)
+        if rng.random() < 0.5:
+            y0, x0 = int(rng.integers(0, H)), int(rng.integers(0, W))
+            mask[y0:y0 + int(rng.integers(1, 20)), x0:x0 + int(rng.integers(1, 40))] = 1
+        mask[0, 0] = 0
+        ref, t_ref, _ = oracle.hyp2d_run(oracle.hyp2d_cfg(W, H), planes, mask.ravel(), steps)
+        dtype = "f64" if rng.random() < 0.6 else "f32"
+        pair = dtype == "f32" and rng.random() < 0.6
+        out, m, t, _, _ = hyp2d_emu.run(W, H, steps, dtype, planes=planes, mask=mask, seg_rows=seg, pair=pair)
+        err = max(rel_linf(a, b) for a, b in zip(out, ref))
+        assert err < (1e-11 if dtype == "f64" else 2e-5) and np.array_equal(m, mask), (case, W, H, steps, seg, dtype, pair, err)
+        assert abs(t - t_ref) <= 1e-6 * t_ref
+    for case in range(6):      # k_init states cut into 2..4 slabs, fp64: bit-identical to one domain
+        W, H, steps = int(rng.integers(40, 260)), int(rng.integers(24, 130)), int(rng.integers(2, 7))
+        world = int(rng.integers(2, 5))
+        monkeypatch.setenv("TAU_HC_BLOCK_ORDER", ["", "reverse", "random"][int(rng.integers(0, 3))])
+        a, _, t, _, _ = hyp2d_emu.run(W, H, steps, "f64", geom_x0=W / 3.0)
+        b, _, ts, open_mappings = hyp2d_emu.run_slabs(W, H, steps, "f64", world, geom_x0=W / 3.0)
+        assert all(np.array_equal(x, y) for x, y in zip(a, b)) and all(tt == t for tt in ts) and open_mappings == 0, \
+            (case, W, H, steps, world)

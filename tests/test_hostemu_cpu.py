@@ -617,3 +617,43 @@ def test_shallow_water_fuzz_bit_identical(swlib, monkeypatch):
         es, eu, ev, eck, _ = oracle.sw_run(prm, s0, u0, v0, steps)
         assert all(np.array_equal(a, b, equal_nan=True) for a, b in ((s, es), (u, eu), (v, ev))), (case, kw, steps)
         assert ck[0] == eck[0] and ck[1] == eck[1]
+
+
+def test_hyp2d_frame_handover_fuzz(monkeypatch):
+    """random frame sequences through tau_hyp2d_upload_peers_async: 0..3 steps before the first hand-over, 1..4
+    frames of 0..4 steps each (0 = two uploads in a row), 2..4 ranks, either rank call order, any block order and
+    pretend device — bit-identical to one domain (30 cases of this generator were run when it was written)."""
+    L = hyp2d_emu.lib()
+    rng = np.random.default_rng(21)
+    for case in range(6):
+        W, H, world, pre = int(rng.integers(10, 50)) * 4, int(rng.integers(24, 120)), int(rng.integers(2, 5)), int(rng.integers(0, 4))
+        dtype = "f64" if rng.random() < 0.5 else "f32"
+        npdt = np.float64 if dtype == "f64" else np.float32
+        monkeypatch.setenv("TAU_HC_BLOCK_ORDER", ["", "reverse", "random"][int(rng.integers(0, 3))])
+        monkeypatch.setenv("TAU_HC_SMS", str(int(rng.integers(1, 5))))
+        monkeypatch.setenv("TAU_HC_CTAS_PER_SM", str(int(rng.integers(1, 4))))
+        yy, xx = np.mgrid[0:H, 0:W]
+
+        def state(k):
+            rho = 1.0 + 0.3 * np.sin(xx / (9.0 + k)) * np.cos(yy / 7.0)
+            u, v = 3.0 + 0.5 * np.cos(xx / 11.0), 0.7 * np.sin(yy / (5.0 + k))
+            p = 1.0 + 0.2 * np.cos((xx + yy) / 13.0)
+            return [rho, rho * u, rho * v, p / 0.1 + 0.5 * rho * (u * u + v * v)]
+        frames = [(state(k), int(rng.integers(0, 5))) for k in range(int(rng.integers(1, 5)))]
+        cc = hyp2d_emu.default_cfg(W, H, geom_x0=W / 3.0)
+        h = C.c_void_p()
+        hyp2d_emu.check(L.tau_hyp2d_create(C.byref(cc), W, H, 0 if dtype == "f32" else 1, 0, 0, H, None, C.byref(h)))
+        hyp2d_emu.check(L.tau_hyp2d_init(h))
+        hyp2d_emu.check(L.tau_hyp2d_step(h, pre))
+        for fp, fs in frames:
+            arrs = [np.ascontiguousarray(p, npdt) for p in fp]
+            hyp2d_emu.check(L.tau_hyp2d_upload(h, (C.c_void_p * 4)(*[a.ctypes.data for a in arrs]), None))
+            hyp2d_emu.check(L.tau_hyp2d_step(h, fs))
+        one = [np.empty((H, W), npdt) for _ in range(4)]
+        m = np.empty((H, W), np.uint8)
+        hyp2d_emu.check(L.tau_hyp2d_download(h, (C.c_void_p * 4)(*[a.ctypes.data for a in one]), C.c_void_p(m.ctypes.data)))
+        L.tau_hyp2d_destroy(h)
+        got, _, _, open_mappings = hyp2d_emu.run_slabs(W, H, pre, dtype, world, frames=frames,
+                                                       reverse_ranks=bool(rng.integers(0, 2)), geom_x0=W / 3.0)
+        assert all(np.array_equal(a, b) for a, b in zip(one, got)) and open_mappings == 0, \
+            (case, W, H, world, pre, dtype, [f[1] for f in frames])

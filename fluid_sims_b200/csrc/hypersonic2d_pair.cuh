@@ -1,15 +1,19 @@
 // hypersonic2d_pair.cuh — EXPERIMENTAL step kernel, compiled into the library but only launched when
 // TAU_HYP2D_PAIR=1 is set at handle creation.  NOT YET RUN ON HARDWARE (written when the round-1 GPU
-// budget was spent); the default path does not touch it.  Included by hypersonic2d.cu (same
-// translation unit: it uses Params, Ctrl, PeerPush and the scalar helpers).
+// budget was spent); the default path does not touch it.  Its results are verified on the CPU emulator
+// (tests/hostemu, tests/test_hostemu_cpu.py: equal to the production kernel to FMA rounding on random
+// fields with walls, in slab mode, at the benchmarked grid's extents, under UBSan alignment checks and in
+// a 400-case fuzz sweep); speed, register pressure at run time and memory ordering are what hardware
+// still has to show.  Included by hypersonic2d.cu (same translation unit: it uses Params, Ctrl, PeerPush
+// and the scalar helpers).
 //
 // The "two adjacent columns per lane" formulation of the 2-D hypersonic step for the interior,
 // body-free work items (97 % of the items at 4096^2): a warp owns a strip of 60 columns; lane l = 1..30
 // owns columns x0 + 2(l-1) and +1 as the two halves of a float2 (lanes 0 / 31 hold the halo pairs);
 // arithmetic uses the packed FADD2/FMUL2/FFMA2 of sm_100, everything without a packed form (min/max,
 // compares, selects, MUFU) runs per half.  In pair mode this kernel takes the interior unmasked items
-// and the production kernel (hyp2d_step) is launched right after it on the masked / edge items, does the
-// step's bookkeeping (sim_t, slot clearing) and sends the multi-GPU message.  Numerics follow
+// and the production kernel (hyp2d_step) is launched right after it on the masked / edge items (cut into
+// 8-row pieces, build_items_pair), does the step's bookkeeping (sim_t, slot clearing) and sends the multi-GPU message.  Numerics follow
 // hypersonic2d.cu (same expression trees, FMA contractions spelled out).  Static facts and the
 // projection: profiles/hyp2d_pair_probe_r1.md.
 #pragma once

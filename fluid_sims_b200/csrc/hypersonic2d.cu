@@ -402,527 +402,13 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
            R *__restrict__ Uout, const uint8_t *__restrict__ mask,
            const uint2 *__restrict__ items, Ctrl *__restrict__ ctrl, int step_slot,
            const PeerPush peer) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  // volatile asm: ptxas otherwise re-reads SR_TID.X (an ~20-cycle S2R) three times per marched row
-  // to rematerialise lane / warp instead of holding them in registers
-  int lane, warp;
-  {
-    unsigned t;
-    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(t));
-    lane = (int)(t & 31u);
-    warp = (int)(t >> 5);
-  }
-  constexpr int SLOT_ELEMS = 4 * H2_RB * H2_BOXW;
-  R *ring_base = reinterpret_cast<R *>(smem_raw) + (size_t)warp * H2_NS * SLOT_ELEMS;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + (size_t)H2_WARPS * H2_NS * SLOT_ELEMS *
-                                                               sizeof(R)) +
-                   warp * H2_NS;
-  Ring<R> ring{ring_base};
-
-  // Programmatic dependent launch: the next step's grid may be scheduled as soon as this one's CTAs
-  // have all started; its CTAs take over SM slots as ours retire and park at griddepcontrol.wait
-  // (below) until this grid has completed and its stores are visible.  Hides the launch latency
-  // between the back-to-back step kernels.  Nothing above the wait reads global memory.
-  asm volatile("griddepcontrol.launch_dependents;");
-  if (USE_TMA) {
-    if (lane == 0) {
-      for (int s = 0; s < H2_NS; ++s) tau::mbar_init(&bars[s], 1);
-      tau::mbar_fence_init();
-    }
-    __syncwarp();
-  }
-  // A warp's first work item is fixed (its global warp index), so its descriptor — static data, not
-  // written by the previous step — can be fetched before the grid dependency resolves; only the
-  // later items are claimed from the counter (which therefore counts from the number of warps).
-  const unsigned nwarps_grid = gridDim.x * H2_WARPS;
-  unsigned item = blockIdx.x * H2_WARPS + warp;
-  uint2 desc = make_uint2(0u, 0u);
-  if (item < (unsigned)P.nitems) desc = items[item];
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-
-  // ---- multi-GPU step barrier + all-reduce(max): every peer must have finished the previous step
-  // (its boundary rows are in our ghost rows); its inbox entry carries its max wavespeed ----------
-  __shared__ unsigned long long s_peer_max;
-  unsigned long long tm0 = 0;
-  if (peer.pc.world > 1) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tm0));
-    if (warp == 0) {
-      unsigned long long v = 1ull;
-      if (lane < peer.pc.world && lane != peer.pc.rank) {
-        const unsigned long long *a = &ctrl->inbox[step_slot][lane];
-        for (;;) {
-          asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a) : "memory");
-          if (v != 0ull) break;
-          __nanosleep(40);
-        }
-      } else {
-        v = 0ull;
-      }
-#pragma unroll
-      for (int o = 4; o > 0; o >>= 1) {  // ranks live in lanes 0..7; non-negative doubles order like their bits
-        const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
-        v = w > v ? w : v;
-      }
-      if (lane == 0) s_peer_max = v;
-    }
-    __syncthreads();
-  }
-
-  // (evaluated after the first item's tiles have been requested: see the work-item loop)
-  R dt = R(0), half_dt = R(0);
-  auto compute_dt = [&]() {
-  // ---- dt from the device-resident max wavespeed (host rule :1852-1869, evaluated in fp64) ----
-  double maxs = *reinterpret_cast<volatile double *>(&ctrl->maxspeed[step_slot]);
-  if (peer.pc.world > 1) maxs = fmax(maxs, __longlong_as_double((long long)s_peer_max));
-  if (!isfinite(maxs) || maxs < 1e-12) maxs = 1e-12;
-  const double dt_conv = P.cfl * 1.0 / maxs;
-  double dt_diff = dt_conv;
-  if (isfinite(P.nu_max) && P.nu_max > 1e-12) dt_diff = 0.25 / P.nu_max;
-  const double dt_d = fmin(dt_conv, dt_diff);
-  dt = (R)dt_d;
-  half_dt = (R)(0.5 * dt_d);
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    ctrl->sim_t += dt_d;
-    ctrl->dt_last = dt_d;
-    ctrl->maxspeed[(step_slot + 2) % 3] = 1e-12;
-    ctrl->next_item[(step_slot + 2) % 3] = 0u;
-    if (peer.pc.world > 1) {
-      // the slot our peers will fill at the end of THEIR next step; they cannot get there before
-      // they have seen this step's message, which is sent after this clear
-#pragma unroll
-      for (int p = 0; p < 8; ++p) ctrl->inbox[(step_slot + 2) % 3][p] = 0ull;
-      unsigned long long tm1;
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tm1));
-      ctrl->t_wait += tm1 - tm0;
-      if (ctrl->t_prev_end != 0ull) ctrl->t_gap += tm0 - ctrl->t_prev_end;
-      ctrl->t_prev_end = tm1;  // peers seen; replaced by this step's end below
-      ctrl->t_steps += 1ull;
-    }
-  }
-  };
-
-  bool pushed = false;  // this thread stored into a neighbour GPU's ghost rows
-  R wmax = R(0);
-  const int W = P.W;
-  const size_t PL = P.plane;
-  // Persistent warps: each claims work items (strip x row segment) from the table until it is
-  // exhausted.  The ring slots and their mbarrier phases simply keep counting across items: `kb`
-  // is the number of 4-row blocks this warp has staged so far.
-  // The next item is claimed three rows before the current one ends and its descriptor is fetched
-  // during the last row: late enough that no warp sits on reserved work while another idles at the
-  // end of the step, early enough that neither latency is exposed.
-  unsigned kb = 0;
-  unsigned claim = 0;
-  bool first = true;
+#define H2_WARP_RING_ELEMS (H2_NS * (4 * H2_RB * H2_BOXW))
+#include "hypersonic2d_prologue.inc"
+#undef H2_WARP_RING_ELEMS
   while (item < (unsigned)P.nitems) {
-  const int strip = (int)(desc.x & 0xffffu);
-  const bool item_masked = (desc.x >> 31) != 0u;
-  const int x0 = strip * H2_OWN;
-  const int x = x0 - 1 + lane;  // this lane's column
-  const int bx = (x0 - 2) & ~3;  // first staged column (16-byte aligned box origin)
-  const int c = x - bx;          // this lane's staged column index
-  const int ys = (int)(desc.y & 0xfffffu);
-  const int ye = ys + (int)(desc.y >> 20);
-  const int nrows = (ye - ys) + 4;  // staged rows: local rows ys-2 .. ye+1
-  const int nblk = (nrows + H2_RB - 1) / H2_RB;
-  const bool owned = (lane >= 1) && (lane <= H2_OWN) && (x < W);
-  const bool edge_strip = (bx < 0) || (bx + H2_BOXW > W);
-  auto row_off = [&](int q) -> int {  // ring offset of staged row q of this item
-    return (int)((kb + (unsigned)(q >> 2)) % H2_NS) * (4 * H2_RB * H2_BOXW) + (q & 3) * H2_BOXW;
-  };
-
-  auto infl_f = [&](int f) -> R {
-    return f == 0 ? P.infl_cons[0] : f == 1 ? P.infl_cons[1] : f == 2 ? P.infl_cons[2] : P.infl_cons[3];
-  };
-  // stage block k (plane rows ys+4k .. ys+4k+3; plane row = local row + 2) into slot k%NS
-  auto issue = [&](int k) {
-    const unsigned slot = (kb + (unsigned)k) % H2_NS;
-    R *dst = ring_base + (size_t)slot * SLOT_ELEMS;
-    const int prow = ys + H2_RB * k;
-    if (USE_TMA) {
-      if (lane == 0) {
-        tau::mbar_expect_tx(&bars[slot], SLOT_ELEMS * sizeof(R));
-        tau::tma_load_3d(dst, &tmU, bx, prow, 0, &bars[slot]);
-      }
-    } else {
-      for (int i = lane; i < SLOT_ELEMS; i += 32) {
-        const int cc = i % H2_BOXW, sub = (i / H2_BOXW) % H2_RB, f = i / (H2_BOXW * H2_RB);
-        const int gx = bx + cc, gr = prow + sub;
-        R v = R(0);
-        if (gx >= 0 && gx < W && gr < P.H_local + 2 * H2_GHOST) v = Uin[f * PL + (size_t)gr * W + gx];
-        dst[i] = v;
-      }
-    }
-  };
-  // wait for block k and fold the x-boundary conditions into the staged rows
-  auto acquire = [&](int k, auto edge_tag) {
-    const unsigned slot = (kb + (unsigned)k) % H2_NS;
-    if (USE_TMA) tau::mbar_wait(&bars[slot], ((kb + (unsigned)k) / H2_NS) & 1u);
-    else __syncwarp();
-    if (decltype(edge_tag)::value && edge_strip) {
-      R *dst = ring_base + (size_t)slot * SLOT_ELEMS;
-      const int prow = ys + H2_RB * k;
-      const int cw = (W - 1) - bx;  // staged column of x = W-1
-      for (int i = lane; i < SLOT_ELEMS; i += 32) {
-        const int cc = i % H2_BOXW, sub = (i / H2_BOXW) % H2_RB, f = i / (H2_BOXW * H2_RB);
-        const int gx = bx + cc, gr = prow + sub;
-        if (gr >= P.H_local + 2 * H2_GHOST) continue;
-        if (gx < 0) {
-          dst[i] = infl_f(f);  // x<0 -> inflow (neighbor_or_wall :277-279)
-        } else if (gx == 0) {
-          if (!mask[(size_t)gr * W]) dst[i] = infl_f(f);  // k_apply_inflow_left :772-784
-        }
-      }
-      __syncwarp();
-      for (int i = lane; i < SLOT_ELEMS; i += 32) {
-        const int cc = i % H2_BOXW;
-        const int gx = bx + cc;
-        if (gx >= W) dst[i] = dst[i - cc + cw];  // x>=W -> raw column W-1 (:280-282)
-      }
-      __syncwarp();
-    }
-  };
-  auto row_in_domain = [&](int r) -> bool {  // local row r inside the GLOBAL grid?
-    const int gy = P.y_begin + r;
-    return gy >= 0 && gy < P.H_global;
-  };
-
-  int issued = 0, acquired = 0;
-  for (; issued < nblk && issued < H2_NS; ++issued) issue(issued);
-  auto need_row = [&](int q, auto edge_tag) {
-    while (acquired * H2_RB <= q) {
-      acquire(acquired, edge_tag);
-      ++acquired;
-    }
-  };
-  if (first) {
-    compute_dt();
-    first = false;
-  }
-  need_row(1, std::true_type{});
-
-  // 40 mask bits of one plane row (bit b <-> staged column b); out-of-domain columns read as 0
-  const int mgx0 = bx + lane, mgx1 = bx + 32 + lane;
-  const bool mok0 = (mgx0 >= 0) && (mgx0 < W);
-  const bool mok1 = (lane < H2_BOXW - 32) && (mgx1 < W);
-
-  // The march is instantiated twice: MASKED = the strip-segment touches the body (mask words are
-  // loaded and every neighbour access goes through the no-slip ghost rule), and the plain variant
-  // for the (vast majority of) strip-segments that contain no body cell, where the mask plane is
-  // never read and the ghost selects vanish at compile time.
-  // ... and once more for strips that touch the x-boundaries (EDGE): interior strips of the plain
-  // variant carry no inflow / outflow / ownership tests at all.
-  auto march = [&](auto masked_tag, auto edge_tag) {
-    constexpr bool MASKED = decltype(masked_tag)::value;
-    constexpr bool EDGE = decltype(edge_tag)::value;
-    static_assert(EDGE || !MASKED, "the masked march always keeps the boundary tests");
-    const bool own = EDGE ? owned : ((lane >= 1) && (lane <= H2_OWN));
-    // rows 2 .. H_local-3 have no consumer besides this slab's own planes
-    const unsigned interior_rows = (unsigned)max(P.H_local - 2 * H2_GHOST, 0);
-    auto mask_row = [&](int prow) -> unsigned long long {
-      if constexpr (MASKED) {
-        const uint8_t *mr = mask + (size_t)prow * W;
-        const int m0 = mok0 ? mr[mgx0] : 0;
-        const int m1 = mok1 ? mr[mgx1] : 0;
-        const unsigned lo = __ballot_sync(0xffffffffu, m0 != 0);
-        const unsigned hi = __ballot_sync(0xffffffffu, m1 != 0);
-        return (unsigned long long)lo | ((unsigned long long)hi << 32);
-      } else {
-        return 0ull;
-      }
-    };
-    auto bit = [&](unsigned long long w, int b) -> bool {
-      if constexpr (MASKED) return (w >> b) & 1ull;
-      else return false;
-    };
-    // neighbour prim with the wall rule: masked -> no-slip ghost of the centre (:364-368)
-    auto nb = [&](unsigned long long w, int b, const Prim4<R> &centre, const Prim4<R> &n) {
-      if constexpr (MASKED) return bit(w, b) ? ghost_prim(centre) : n;
-      else return n;
-    };
-
-    // y-face flux between the cell below (B) and above (T) — k_compute_yface_flux :998-1030
-    auto yface = [&](bool hasB, bool hasT, bool rinB, bool rinT, const Face<R> &yT_B,
-                     const Face<R> &yB_T, const Prim4<R> &PB, const Prim4<R> &PT, int roB,
-                     int roT) -> Cons4<R> {
-      Face<R> lo = yT_B, hi = yB_T;
-      if (!(hasB && hasT)) {
-        if (hasT) {  // neighbor_or_wall(x, yt, 0, -1): body cell below, or the y=0 clamp
-          lo = rinB ? ghost_face(P, PT) : face_from_cons(P, ring.at(roT, c));
-        } else if (hasB) {  // neighbor_or_wall(x, yb, 0, +1)
-          hi = rinT ? ghost_face(P, PB) : face_from_cons(P, ring.at(roB, c));
-        }
-      }
-      // faces between two non-fluid cells carry no flux (:1024-1027); they are still evaluated
-      // (on finite states) so that the warp-uniform control flow of hllc_flux stays convergent
-      const Cons4<R> F = hllc_flux<1>(P, lo, hi);
-      if constexpr (MASKED) return (hasB || hasT) ? F : Cons4<R>{R(0), R(0), R(0), R(0)};
-      else return F;
-    };
-
-    // The march starts two rows early (r = ys-2, ys-1): those warm-up iterations only build the
-    // carried y-state (predicted top state of the row below, flux through the face below) with
-    // the same code the real rows use, which keeps a single copy of the reconstruction / Riemann
-    // solver in the instruction stream.
-    unsigned long long mw_m2 = 0, mw_m1 = 0, mw_c, mw_p1, mw_p2;
-    mw_c = mask_row(ys + 0);   // local row ys-2 (plane row = local row + 2)
-    mw_p1 = mask_row(ys + 1);  // local row ys-1
-    // ring offsets of rows r-2, r-1, r, r+1 (and r+2, advanced incrementally: +1 row inside a
-    // 4-row block, on to the next slot when a block is entered)
-    int ro_m2 = 0, ro_m1 = 0, ro_c = row_off(0), ro_p1 = row_off(1), ro_p2 = ro_p1;
-    unsigned slot_p2 = kb % H2_NS;
-    Prim4<R> Pr = cons_to_prim(P, ring.at(ro_c, c)), Pr1 = cons_to_prim(P, ring.at(ro_p1, c));
-    Face<R> yT_r{R(1), R(0), R(0), R(1), R(1), R(1)};
-    Cons4<R> G_bot{R(0), R(0), R(0), R(0)};
-
-    for (int r = ys - 2; r < ye; ++r) {
-      const int q = r - ys + 2;  // staged-row offset of row r
-      if (r >= ye - 3) {         // (a segment has at least one row: r = ye-3 >= ys-2 is reached)
-        if (r == ye - 3) {
-          if (lane == 0) claim = nwarps_grid + atomicAdd(&ctrl->next_item[step_slot], 1u);
-        } else if (r == ye - 1) {
-          item = __shfl_sync(0xffffffffu, claim, 0);
-          if (item < (unsigned)P.nitems) desc = items[item];
-        }
-      }
-      ro_p2 += H2_BOXW;
-      if (((q + 2) & (H2_RB - 1)) == 0) {
-        // row q+2 opens block B = (q+2)/4: wait for it; block B-2 died with row q-3, so its slot
-        // takes block B+1 (needed four rows from now)
-        need_row(q + 2, edge_tag);
-        slot_p2 = (slot_p2 + 1 == H2_NS) ? 0u : slot_p2 + 1;
-        ro_p2 = (int)slot_p2 * (4 * H2_RB * H2_BOXW);
-        if (q >= 6) {
-          __syncwarp();
-          if (issued < nblk) {
-            issue(issued);
-            ++issued;
-          }
-        }
-      }
-      mw_p2 = mask_row(r + 2 + H2_GHOST);
-      const Prim4<R> Pr2 = cons_to_prim(P, ring.at(ro_p2, c));
-
-      // -- y: reconstruct cell r+1, flux through face r+1/2 ----------------------------------
-      Face<R> yB1, yT1;
-      reconstruct_predict<1>(P, nb(mw_c, c, Pr1, Pr), Pr1, nb(mw_p2, c, Pr1, Pr2), half_dt, yB1,
-                             yT1);
-      const bool m_c = bit(mw_c, c);
-      const bool rinB = row_in_domain(r), rinT = row_in_domain(r + 1);
-      const Cons4<R> G_top = yface(rinB && !m_c, rinT && !bit(mw_p1, c), rinB, rinT, yT_r, yB1,
-                                   Pr, Pr1, ro_c, ro_p1);
-
-      if (r >= ys) {  // warp-uniform: the two warm-up rows skip the x-sweep and the update
-        // -- x: neighbours by shuffle, edge lanes from the staged halo columns ----------------
-        Prim4<R> Pl = shfl_up_prim(Pr), Pq = shfl_down_prim(Pr);
-        {  // (a divergent branch taken by 2 lanes costs the same issue slots as all 32 taking it)
-          const Prim4<R> e = cons_to_prim(P, ring.at(ro_c, c + (lane == 0 ? -1 : (lane == 31 ? 1 : 0))));
-          if (lane == 0) Pl = e;
-          if (lane == 31) Pq = e;
-        }
-        Face<R> xL, xR;
-        reconstruct_predict<0>(P, nb(mw_c, c - 1, Pr, Pl), Pr, nb(mw_c, c + 1, Pr, Pq), half_dt, xL,
-                               xR);
-        // flux through this lane's RIGHT face (columns x | x+1) — k_compute_xface_flux :964-996
-        Cons4<R> F_right;
-        {
-          const Face<R> xL_B = shfl_down_face(xL);
-          const bool inA = !EDGE || ((x >= 0) && (x < W)), inB = !EDGE || ((x + 1 >= 0) && (x + 1 < W));
-          const bool hasA = inA && !m_c, hasB = inB && !bit(mw_c, c + 1);
-          Face<R> lo = xR, hi = xL_B;
-          if (!(hasA && hasB)) {
-            if (hasB) {  // A is the inflow boundary (x<0) or a body cell
-              lo = inA ? ghost_face(P, Pq)
-                       : face_from_cons(P, Cons4<R>{P.infl_cons[0], P.infl_cons[1],
-                                                    P.infl_cons[2], P.infl_cons[3]});
-            } else if (hasA) {  // B is beyond the outflow edge (raw column W-1) or a body cell
-              hi = inB ? ghost_face(P, Pr) : face_from_cons(P, ring.at(ro_c, c + 1));
-            }
-          }
-          const Cons4<R> F = hllc_flux<0>(P, lo, hi);
-          if constexpr (MASKED) F_right = (hasA || hasB) ? F : Cons4<R>{R(0), R(0), R(0), R(0)};
-          else F_right = F;
-        }
-        const Cons4<R> F_left = shfl_up_cons(F_right);
-
-        // -- update (k_step :1097-1175) -------------------------------------------------------
-        if (own) {
-          const Cons4<R> Ur = ring.at(ro_c, c);
-          Cons4<R> Un = Ur;
-          if (!m_c) {
-            Un.rho -= dt * (F_right.rho - F_left.rho);
-            Un.mx -= dt * (F_right.mx - F_left.mx);
-            Un.my -= dt * (F_right.my - F_left.my);
-            Un.E -= dt * (F_right.E - F_left.E);
-            Un.rho -= dt * (G_top.rho - G_bot.rho);
-            Un.mx -= dt * (G_top.mx - G_bot.mx);
-            Un.my -= dt * (G_top.my - G_bot.my);
-            Un.E -= dt * (G_top.E - G_bot.E);
-
-            // diffusion taps: masked neighbour -> no-slip ghost of the centre (:1121-1141)
-            Cons4<R> xm2 = ring.at(ro_c, c - 2), xm1 = ring.at(ro_c, c - 1);
-            Cons4<R> xp1 = ring.at(ro_c, c + 1), xp2 = ring.at(ro_c, c + 2);
-            Cons4<R> ym2 = ring.at(ro_m2, c), ym1 = ring.at(ro_m1, c);
-            Cons4<R> yp1 = ring.at(ro_p1, c), yp2 = ring.at(ro_p2, c);
-            if constexpr (MASKED) {
-              const Cons4<R> gh = ghost_cons(P, Pr);
-              if (bit(mw_c, c - 2)) xm2 = gh;
-              if (bit(mw_c, c - 1)) xm1 = gh;
-              if (bit(mw_c, c + 1)) xp1 = gh;
-              if (bit(mw_c, c + 2)) xp2 = gh;
-              if (bit(mw_m2, c)) ym2 = gh;
-              if (bit(mw_m1, c)) ym1 = gh;
-              if (bit(mw_p1, c)) yp1 = gh;
-              if (bit(mw_p2, c)) yp2 = gh;
-            }
-            // d2x + d2y of :1126-1158 in one expression:
-            // (16 (xm1+xp1+ym1+yp1) - (xm2+xp2+ym2+yp2) - 60 c) / 12
-#define TAU_LAP(f)                                                                         \
-  (((R(16) * ((xm1.f + xp1.f) + (ym1.f + yp1.f)) - ((xm2.f + xp2.f) + (ym2.f + yp2.f))) - \
-    R(60) * Ur.f) * (R(1) / R(12)))
-            Un.rho += (P.visc_rho * dt) * TAU_LAP(rho);
-            Un.mx += (P.visc_nu * dt) * TAU_LAP(mx);
-            Un.my += (P.visc_nu * dt) * TAU_LAP(my);
-            Un.E += (P.visc_e * dt) * TAU_LAP(E);
-#undef TAU_LAP
-
-            Un.rho = rmax(Un.rho, P.eps_rho);
-            Prim4<R> pp = cons_to_prim(P, Un);
-            if (pp.p <= P.eps_p || !isfinite(pp.p) || !isfinite(pp.rho) || !isfinite(pp.u) ||
-                !isfinite(pp.v)) {
-              pp.rho = rmax(pp.rho, P.eps_rho);
-              pp.p = rmax(pp.p, P.eps_p);
-              Un = prim_to_cons(P, pp);
-              pp = cons_to_prim(P, Un);
-            }
-            // max wavespeed of the state the NEXT step will see (k_max_wavespeed_blocks
-            // :786-819); column 0 is overwritten with the inflow state before that scan (:1834)
-            R ws;
-            if (EDGE && x == 0) {
-              ws = (R)P.infl_speed;
-            } else {
-              const R a = sound_speed(P, pp);
-              const R sx = rabs(pp.u) + a, sy = rabs(pp.v) + a;
-              ws = sx > sy ? sx : sy;
-              if (!isfinite(ws)) ws = R(1e-12);
-            }
-            wmax = ws > wmax ? ws : wmax;
-          }
-          const size_t o = (size_t)(r + H2_GHOST) * W + x;
-          Uout[o] = Un.rho;
-          Uout[PL + o] = Un.mx;
-          Uout[2 * PL + o] = Un.my;
-          Uout[3 * PL + o] = Un.E;
-          // The first and last two rows of the slab have extra consumers; one warp-uniform test
-          // keeps all of that out of the way of every other row.
-          if ((unsigned)(r - H2_GHOST) >= interior_rows) {
-          // multi-GPU: push boundary rows into the slab neighbours' ghost rows (peer memory)
-          if (peer.up_out != nullptr && r < H2_GHOST) {
-            pushed = true;
-            R *o_up = static_cast<R *>(peer.up_out);
-            const size_t og = (size_t)(peer.up_hl + H2_GHOST + r) * W + x;
-            o_up[og] = Un.rho;
-            o_up[peer.up_plane + og] = Un.mx;
-            o_up[2 * peer.up_plane + og] = Un.my;
-            o_up[3 * peer.up_plane + og] = Un.E;
-          }
-          if (peer.dn_out != nullptr && r >= P.H_local - H2_GHOST) {
-            pushed = true;
-            R *o_dn = static_cast<R *>(peer.dn_out);
-            const size_t og = (size_t)(r - (P.H_local - H2_GHOST)) * W + x;
-            o_dn[og] = Un.rho;
-            o_dn[peer.dn_plane + og] = Un.mx;
-            o_dn[2 * peer.dn_plane + og] = Un.my;
-            o_dn[3 * peer.dn_plane + og] = Un.E;
-          }
-          // keep the y-clamp ghost rows of the output planes current (global edges only)
-          const int gy = P.y_begin + r;
-          if (gy == 0 || gy == P.H_global - 1) {
-            for (int g = 1; g <= H2_GHOST; ++g) {
-              if (gy == 0) {
-                const size_t og = (size_t)(r + H2_GHOST - g) * W + x;
-                Uout[og] = Un.rho;
-                Uout[PL + og] = Un.mx;
-                Uout[2 * PL + og] = Un.my;
-                Uout[3 * PL + og] = Un.E;
-              }
-              if (gy == P.H_global - 1) {
-                const size_t og = (size_t)(r + H2_GHOST + g) * W + x;
-                Uout[og] = Un.rho;
-                Uout[PL + og] = Un.mx;
-                Uout[2 * PL + og] = Un.my;
-                Uout[3 * PL + og] = Un.E;
-              }
-            }
-          }
-          }  // boundary rows
-        }
-      }  // r >= ys
-
-      // -- roll the carried state ---------------------------------------------------------------
-      G_bot = G_top;
-      yT_r = yT1;
-      Pr = Pr1;
-      Pr1 = Pr2;
-      mw_m2 = mw_m1;
-      mw_m1 = mw_c;
-      mw_c = mw_p1;
-      mw_p1 = mw_p2;
-      ro_m2 = ro_m1;
-      ro_m1 = ro_c;
-      ro_c = ro_p1;
-      ro_p1 = ro_p2;
-    }
-  };
-
-  if (item_masked) march(std::true_type{}, std::true_type{});
-  else if (edge_strip) march(std::false_type{}, std::true_type{});
-  else march(std::false_type{}, std::false_type{});
-
-  kb += (unsigned)nblk;  // every staged block has been acquired; the ring carries on from here
-  __syncwarp();
+#include "hypersonic2d_item.inc"
   }  // work-item loop
-  if (first) compute_dt();  // a warp without any item still owes block 0's bookkeeping
-
-  wmax = tau::warp_max(wmax);
-  if (lane == 0 && wmax > R(0)) tau::atomic_max_nonneg(&ctrl->maxspeed[(step_slot + 1) % 3], (double)wmax);
-
-  // ---- multi-GPU: the last CTA out folds this rank's max wavespeed into every peer's slot for the
-  // next step and then signals "step done" (release order: data, fence, flag) -------------------
-  if (peer.pc.world > 1) {
-    __shared__ int s_last;
-    if (pushed) __threadfence_system();  // peer stores (ghost-row pushes) before the CTA count
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      s_last = (atomicAdd(&ctrl->done_blocks, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (s_last) {
-      __threadfence();
-      const int next = (step_slot + 1) % 3;
-      if (threadIdx.x == 0) ctrl->done_blocks = 0;
-      // (constant indices only: a dynamically indexed kernel parameter would be copied to local
-      // memory, and every read of `peer` in the row loop would become a local load)
-      Ctrl *pc = nullptr;
-#pragma unroll
-      for (int p = 0; p < 8; ++p)
-        if (p == (int)threadIdx.x && p < peer.pc.world && p != peer.pc.rank) pc = peer.pc.ctrl[p];
-      if (pc != nullptr) {
-        const double m = *reinterpret_cast<volatile double *>(&ctrl->maxspeed[next]);
-        const unsigned long long bits = static_cast<unsigned long long>(__double_as_longlong(fmax(m, 1e-12)));
-        __threadfence_system();
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&pc->inbox[next][peer.pc.rank]), "l"(bits)
-                     : "memory");
-      }
-      if (threadIdx.x == 0) {
-        unsigned long long tm2;
-        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tm2));
-        ctrl->t_busy += tm2 - ctrl->t_prev_end;
-        ctrl->t_prev_end = tm2;
-      }
-    }
-  }
+#include "hypersonic2d_epilogue.inc"
 }
 
 // One flag per marching work item (strip x row segment): does the staged window of that item

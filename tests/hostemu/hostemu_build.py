@@ -120,7 +120,7 @@ def preprocess(path: str) -> str:
     # local .cuh pieces are inlined (and rewritten the same way)
     def inline(m):
         return preprocess(os.path.join(os.path.dirname(path), m.group(1))).replace("#pragma once", "")
-    text = re.sub(r'#include "(\w+\.cuh)"', lambda m: m.group(0) if m.group(1) == "common.cuh" else inline(m), text)
+    text = re.sub(r'#include "(\w+\.(?:cuh|inc))"', lambda m: m.group(0) if m.group(1) == "common.cuh" else inline(m), text)
     text = re.sub(r"extern\s+__shared__\s+(.*?)(\w+)\[\];", r"__shared__ \1\2[TAU_HC_SMEM_BYTES];", text)
     text = re.sub(r"__shared__\s+alignas\((\w+)\)", r"__shared__ __attribute__((aligned(\1)))", text)  # g++: no alignas after static
     return cuda_to_host(rewrite_asm(text))
@@ -132,8 +132,9 @@ def build(name: str, defines=(), tag: str = "", contract: str = "off", sanitize:
     cu = os.path.join(ROOT, "fluid_sims_b200", "csrc", f"{name}.cu")
     cpp = os.path.join(OUT, f"{name}{tag}_host.cpp")
     so = os.path.join(OUT, f"lib{name}{tag}_hostemu.so")
+    csrc_dir = os.path.join(ROOT, "fluid_sims_b200", "csrc")
     deps = [cu, os.path.join(ROOT, "tests", "hostemu", "hostemu.h"), __file__,
-            os.path.join(ROOT, "fluid_sims_b200", "csrc", "hypersonic2d_pair.cuh"),
+            *[os.path.join(csrc_dir, f) for f in os.listdir(csrc_dir) if f.endswith((".cuh", ".inc"))],
             os.path.join(ROOT, "include", "tau_b200.h")]
     if os.path.exists(so) and all(os.path.getmtime(so) > os.path.getmtime(d) for d in deps):
         return so
@@ -158,7 +159,7 @@ def build_all() -> str:
     names = ["burgers", "gray_scott", "hypersonic2d", "hypersonic3d", "shallow_water", "snapshot", "splat4", "sph"]
     so = os.path.join(OUT, "libtau_b200_hostemu.so")
     csrc = os.path.join(ROOT, "fluid_sims_b200", "csrc")
-    deps = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh"))] + [
+    deps = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".inc"))] + [
         os.path.join(ROOT, "tests", "hostemu", "hostemu.h"), __file__, os.path.join(ROOT, "include", "tau_b200.h")]
     if os.path.exists(so) and all(os.path.getmtime(so) > os.path.getmtime(d) for d in deps):
         return so

@@ -742,7 +742,8 @@ __global__ void hyp2d_init(const Params<R> P, Geom G, R rest_E, R *U, uint8_t *m
 
 }  // namespace
 
-#include "hypersonic2d_pair.cuh"  // experimental packed two-column kernel (TAU_HYP2D_PAIR=1 only)
+#include "hypersonic2d_pair.cuh"   // experimental packed two-column kernel (TAU_HYP2D_PAIR=1 | 2 only)
+#include "hypersonic2d_fused.cuh"  // experimental: pair + production items in one kernel (TAU_HYP2D_PAIR=2)
 
 // ================================================================================================
 // host side
@@ -780,6 +781,9 @@ struct tau_hyp2d {
   size_t plane_elems;
   // experimental pair mode (TAU_HYP2D_PAIR=1, fp32 + TMA only; see hypersonic2d_pair.cuh)
   bool pair_mode;
+  bool fused_mode;                  // TAU_HYP2D_PAIR=2: one kernel per step claims both kinds of item
+  uint2 *items_fused;
+  int nitems_fused, grid_fused;
   CUtensorMap tm_pair[2];
   uint2 *items_pair, *items_rest;   // interior body-free 60-column items / everything else (30-column)
   int nitems_pair, nitems_rest, grid_pair, grid_rest;
@@ -1008,6 +1012,27 @@ int build_items_pair(tau_hyp2d *h) {
       }
     }
   }
+  if (h->fused_mode) {  // one table: masked items first (longest), then the pair items, then the plain leftovers
+    std::vector<uint2> fused;
+    for (const uint2 &d : rest) if (d.x >> 31) fused.push_back(d);
+    for (const uint2 &d : pair) fused.push_back(make_uint2(d.x | HF_PAIR_BIT, d.y));
+    for (const uint2 &d : rest) if (!(d.x >> 31)) fused.push_back(d);
+    if (h->items_fused) TAU_CUDA(cudaFree(h->items_fused));
+    h->items_fused = nullptr;
+    TAU_CUDA(cudaMalloc(&h->items_fused, (fused.size() + 1) * sizeof(uint2)));
+    TAU_CUDA(cudaMemcpyAsync(h->items_fused, fused.data(), fused.size() * sizeof(uint2), cudaMemcpyHostToDevice,
+                             h->stream));
+    TAU_CUDA(cudaStreamSynchronize(h->stream));
+    h->nitems_fused = (int)fused.size();
+    int sms = 148, per = 1;
+    TAU_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    TAU_CUDA(cudaFuncSetAttribute(hyp2d_step_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair_smem_bytes()));
+    TAU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, hyp2d_step_fused, H2_WARPS * 32, pair_smem_bytes()));
+    if (per < 1) per = 1;
+    int g = (h->nitems_fused + H2_WARPS - 1) / H2_WARPS;
+    if (g > sms * per) g = sms * per;
+    h->grid_fused = g < 1 ? 1 : g;
+  }
   // The production kernel runs second and cannot overlap the pair kernel (both are ordered behind the
   // previous step), so its duration is its longest item chain.  It has only a few per cent of the work but
   // the whole device: cut its items into short pieces (TAU_HYP2D_REST_ROWS, default 8 rows; 0 = leave them)
@@ -1082,6 +1107,19 @@ int launch_steps_pair(tau_hyp2d *h, int nsteps, size_t smem) {
     lc.stream = h->stream;
     lc.attrs = attr;
     lc.numAttrs = 1;
+    if (h->fused_mode) {  // both kinds of item from one table, one kernel (hypersonic2d_fused.cuh)
+      Params<float> PF = P;
+      PF.nitems = h->nitems_fused;
+      lc.gridDim = dim3((unsigned)h->grid_fused);
+      lc.dynamicSmemBytes = pair_smem_bytes();
+      TAU_CUDA(cudaLaunchKernelEx(&lc, hyp2d_step_fused, h->tm[a], h->tm_pair[a], PF, (const float *)h->U[a],
+                                  (float *)h->U[b], (const uint8_t *)h->mask, (const uint2 *)h->items_fused,
+                                  h->ctrl, slot, peer));
+      h->launches++;
+      h->cur = b;
+      h->steps++;
+      continue;
+    }
     if (h->nitems_pair > 0) {  // interior body-free items first
       lc.gridDim = dim3((unsigned)h->grid_pair);
       lc.dynamicSmemBytes = pair_smem_bytes();
@@ -1321,7 +1359,7 @@ int tau_hyp2d_create(const tau_hyp2d_config *cfg, int W, int H, int dtype, int d
     memset(h->tm, 0, sizeof(h->tm));
   }
   if (const char *e = getenv("TAU_HYP2D_PAIR")) {  // experimental, see hypersonic2d_pair.cuh
-    if (atoi(e) == 1 && h->use_tma && dtype == 0 && W >= 2 * HP_BOXW) {
+    if ((atoi(e) == 1 || atoi(e) == 2) && h->use_tma && dtype == 0 && W >= 2 * HP_BOXW) {
       const uint64_t dims[3] = {(uint64_t)W, (uint64_t)(h_local + 2 * H2_GHOST), 4};
       const uint64_t strides[2] = {(uint64_t)W * es, (uint64_t)h->plane_elems * es};
       const uint32_t box[3] = {HP_BOXW, H2_RB, 4};
@@ -1332,6 +1370,7 @@ int tau_hyp2d_create(const tau_hyp2d_config *cfg, int W, int H, int dtype, int d
       TAU_CUDA(cudaMalloc(&h->pair_ctr, 3 * sizeof(unsigned int)));
       TAU_CUDA(cudaMemsetAsync(h->pair_ctr, 0, 3 * sizeof(unsigned int), h->stream));
       h->pair_mode = true;
+      h->fused_mode = atoi(e) == 2;
     }
   }
   TAU_CUDA(cudaEventCreate(&h->ev0));
@@ -1768,6 +1807,7 @@ int tau_hyp2d_destroy(tau_hyp2d *h) {
   if (h->items) cudaFree(h->items);
   if (h->items_pair) cudaFree(h->items_pair);
   if (h->items_rest) cudaFree(h->items_rest);
+  if (h->items_fused) cudaFree(h->items_fused);
   if (h->pair_ctr) cudaFree(h->pair_ctr);
   if (h->pixels) cudaFree(h->pixels);
   if (h->mmkeys) cudaFree(h->mmkeys);

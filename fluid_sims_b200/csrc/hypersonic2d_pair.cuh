@@ -280,195 +280,19 @@ hyp2d_step_pair(const __grid_constant__ CUtensorMap tmU, const Params<float> P, 
   unsigned kb = 0, claim = 0;
   bool first = true;
   while (item < (unsigned)nitems) {
-    const int x0 = (int)(desc.x & 0xffffu) * HP_OWN;
-    const int bx = x0 - 4;
-    const int c = 2 * lane + 2;           // staged column of this lane's first cell (even)
-    const int xa = bx + c;                // its grid column; the second cell is xa + 1
-    const int ys = (int)(desc.y & 0xfffffu);
-    const int ye = ys + (int)(desc.y >> 20);
-    const int nblk = ((ye - ys) + 4 + H2_RB - 1) / H2_RB;
-    const bool own = (lane >= 1) && (lane <= 30);
-    auto row_off = [&](int q) -> int {
-      return (int)((kb + (unsigned)(q >> 2)) % H2_NS) * HP_SLOT + (q & 3) * HP_BOXW;
-    };
-    auto issue = [&](int k) {
-      const unsigned slot = (kb + (unsigned)k) % H2_NS;
-      if (lane == 0) {
-        tau::mbar_expect_tx(&bars[slot], HP_SLOT * sizeof(float));
-        tau::tma_load_3d(ring_base + (size_t)slot * HP_SLOT, &tmU, bx, ys + H2_RB * k, 0, &bars[slot]);
-      }
-    };
-    int issued = 0, acquired = 0;
-    for (; issued < nblk && issued < H2_NS; ++issued) issue(issued);
-    auto need_row = [&](int q) {
-      while (acquired * H2_RB <= q) {
-        tau::mbar_wait(&bars[(kb + (unsigned)acquired) % H2_NS], ((kb + (unsigned)acquired) / H2_NS) & 1u);
-        ++acquired;
-      }
-    };
-    if (first) {
-      compute_dt();
-      first = false;
-    }
-    need_row(1);
-
-    int ro_m2 = 0, ro_m1 = 0, ro_c = row_off(0), ro_p1 = row_off(1), ro_p2 = ro_p1;
-    unsigned slot_p2 = kb % H2_NS;
-    Prim2 Pr = cons_to_prim2(P, ring.at(ro_c, c)), Pr1 = cons_to_prim2(P, ring.at(ro_p1, c));
-    Face2 yT_r{f2(1.f), f2(0.f), f2(0.f), f2(1.f), f2(1.f), f2(1.f)};
-    Cons2 G_bot{f2(0.f), f2(0.f), f2(0.f), f2(0.f)};
-    const unsigned interior_rows = (unsigned)max(P.H_local - 2 * H2_GHOST, 0);
-
-    for (int r = ys - 2; r < ye; ++r) {
-      const int q = r - ys + 2;
-      if (r >= ye - 3) {
-        if (r == ye - 3) {
-          if (lane == 0) claim = nwarps_grid + atomicAdd(&claim_ctr[step_slot], 1u);
-        } else if (r == ye - 1) {
-          item = __shfl_sync(0xffffffffu, claim, 0);
-          if (item < (unsigned)nitems) desc = items[item];
-        }
-      }
-      ro_p2 += HP_BOXW;
-      if (((q + 2) & (H2_RB - 1)) == 0) {
-        need_row(q + 2);
-        slot_p2 = (slot_p2 + 1 == H2_NS) ? 0u : slot_p2 + 1;
-        ro_p2 = (int)slot_p2 * HP_SLOT;
-        if (q >= 6) {
-          __syncwarp();
-          if (issued < nblk) {
-            issue(issued);
-            ++issued;
-          }
-        }
-      }
-      const Prim2 Pr2 = cons_to_prim2(P, ring.at(ro_p2, c));
-
-      // -- y: reconstruct row r+1 (both cells), flux through face r+1/2 ------------------------------
-      Face2 yB1, yT1;
-      reconstruct_predict2<1>(P, Pr, Pr1, Pr2, half_dt, yB1, yT1);
-      Face2 lo = yT_r, hi = yB1;
-      {
-        const int gy = P.y_begin + r;
-        if ((unsigned)gy >= (unsigned)(P.H_global - 1)) {  // a row of the face is outside the grid: y-clamp
-          const bool rinB = gy >= 0 && gy < P.H_global, rinT = gy + 1 >= 0 && gy + 1 < P.H_global;
-          if (rinT && !rinB) lo = face_from_cons2(P, ring.at(ro_p1, c));
-          else if (rinB && !rinT) hi = face_from_cons2(P, ring.at(ro_c, c));
-        }
-      }
-      const Cons2 G_top = hllc_flux2<1>(P, lo, hi);
-
-      if (r >= ys) {
-        // -- x: (A, B) = this lane's cells; A's left neighbour is lane-1's B, B's right one lane+1's A --
-        const Prim4<float> e = cons_to_prim(P, ring.at1(ro_c, lane == 0 ? c - 1 : c + 2));  // halo columns
-        Prim2 qm{f2(__shfl_up_sync(0xffffffffu, Pr.rho.v.y, 1), Pr.rho.v.x), f2(__shfl_up_sync(0xffffffffu, Pr.u.v.y, 1), Pr.u.v.x),
-                 f2(__shfl_up_sync(0xffffffffu, Pr.v.v.y, 1), Pr.v.v.x), f2(__shfl_up_sync(0xffffffffu, Pr.p.v.y, 1), Pr.p.v.x)};
-        Prim2 qp{f2(Pr.rho.v.y, __shfl_down_sync(0xffffffffu, Pr.rho.v.x, 1)), f2(Pr.u.v.y, __shfl_down_sync(0xffffffffu, Pr.u.v.x, 1)),
-                 f2(Pr.v.v.y, __shfl_down_sync(0xffffffffu, Pr.v.v.x, 1)), f2(Pr.p.v.y, __shfl_down_sync(0xffffffffu, Pr.p.v.x, 1))};
-        if (lane == 0) { qm.rho.v.x = e.rho; qm.u.v.x = e.u; qm.v.v.x = e.v; qm.p.v.x = e.p; }
-        if (lane == 31) { qp.rho.v.y = e.rho; qp.u.v.y = e.u; qp.v.v.y = e.v; qp.p.v.y = e.p; }
-        Face2 xL, xR;
-        reconstruct_predict2<0>(P, qm, Pr, qp, half_dt, xL, xR);
-        // right faces of A (A | B) and of B (B | next lane's A)
-        const Face2 hiF{f2(xL.rho.v.y, __shfl_down_sync(0xffffffffu, xL.rho.v.x, 1)),
-                        f2(xL.u.v.y, __shfl_down_sync(0xffffffffu, xL.u.v.x, 1)),
-                        f2(xL.v.v.y, __shfl_down_sync(0xffffffffu, xL.v.v.x, 1)),
-                        f2(xL.p.v.y, __shfl_down_sync(0xffffffffu, xL.p.v.x, 1)),
-                        f2(xL.E.v.y, __shfl_down_sync(0xffffffffu, xL.E.v.x, 1)),
-                        f2(xL.a.v.y, __shfl_down_sync(0xffffffffu, xL.a.v.x, 1))};
-        const Cons2 F_right = hllc_flux2<0>(P, xR, hiF);
-        const Cons2 F_left{f2(__shfl_up_sync(0xffffffffu, F_right.rho.v.y, 1), F_right.rho.v.x),
-                           f2(__shfl_up_sync(0xffffffffu, F_right.mx.v.y, 1), F_right.mx.v.x),
-                           f2(__shfl_up_sync(0xffffffffu, F_right.my.v.y, 1), F_right.my.v.x),
-                           f2(__shfl_up_sync(0xffffffffu, F_right.E.v.y, 1), F_right.E.v.x)};
-        if (own) {
-          const Cons2 Ur = ring.at(ro_c, c), Lq = ring.at(ro_c, c - 2), Rq = ring.at(ro_c, c + 2);
-          const Cons2 ym2 = ring.at(ro_m2, c), ym1 = ring.at(ro_m1, c), yp1 = ring.at(ro_p1, c), yp2 = ring.at(ro_p2, c);
-          const f2 ndt(-dt);
-          Cons2 Un;
-          Un.rho = fma_(ndt, G_top.rho - G_bot.rho, fma_(ndt, F_right.rho - F_left.rho, Ur.rho));
-          Un.mx = fma_(ndt, G_top.mx - G_bot.mx, fma_(ndt, F_right.mx - F_left.mx, Ur.mx));
-          Un.my = fma_(ndt, G_top.my - G_bot.my, fma_(ndt, F_right.my - F_left.my, Ur.my));
-          Un.E = fma_(ndt, G_top.E - G_bot.E, fma_(ndt, F_right.E - F_left.E, Ur.E));
-          // x taps of the pair: xm2 = Lq, xm1 = (Lq.y, Ur.x), xp1 = (Ur.y, Rq.x), xp2 = Rq
-#define HP_LAP(fld)                                                                                          \
-  ((fma_(f2(16.f), f2(Lq.fld.v.y + Ur.fld.v.y, Ur.fld.v.x + Rq.fld.v.x) + (ym1.fld + yp1.fld),               \
-         -((Lq.fld + Rq.fld) + (ym2.fld + yp2.fld))) -                                                       \
-    f2(60.f) * Ur.fld) * f2(1.f / 12.f))
-          Un.rho = fma_(f2(P.visc_rho * dt), HP_LAP(rho), Un.rho);
-          Un.mx = fma_(f2(P.visc_nu * dt), HP_LAP(mx), Un.mx);
-          Un.my = fma_(f2(P.visc_nu * dt), HP_LAP(my), Un.my);
-          Un.E = fma_(f2(P.visc_e * dt), HP_LAP(E), Un.E);
-#undef HP_LAP
-          Un.rho = max_(Un.rho, f2(P.eps_rho));
-          Prim2 pp = cons_to_prim2(P, Un);
-          // repair :1166-1173 — rare, per half with the scalar routines
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            Prim4<float> ph = half(pp, k);
-            if (ph.p <= P.eps_p || !isfinite(ph.p) || !isfinite(ph.rho) || !isfinite(ph.u) || !isfinite(ph.v)) {
-              ph.rho = rmax(ph.rho, P.eps_rho);
-              ph.p = rmax(ph.p, P.eps_p);
-              const Cons4<float> cn = prim_to_cons(P, ph);
-              ph = cons_to_prim(P, cn);
-              if (k) { Un.rho.v.y = cn.rho; Un.mx.v.y = cn.mx; Un.my.v.y = cn.my; Un.E.v.y = cn.E;
-                       pp.rho.v.y = ph.rho; pp.u.v.y = ph.u; pp.v.v.y = ph.v; pp.p.v.y = ph.p; }
-              else { Un.rho.v.x = cn.rho; Un.mx.v.x = cn.mx; Un.my.v.x = cn.my; Un.E.v.x = cn.E;
-                     pp.rho.v.x = ph.rho; pp.u.v.x = ph.u; pp.v.v.x = ph.v; pp.p.v.x = ph.p; }
-            }
-          }
-          const f2 a = sqrt_((f2(P.gamma) * max_(pp.p, f2(P.eps_p))) * rcp_(max_(pp.rho, f2(P.eps_rho))));
-          const f2 ws = max_(abs_(pp.u) + a, abs_(pp.v) + a);
-          const float w0 = isfinite(ws.v.x) ? ws.v.x : 1e-12f, w1 = isfinite(ws.v.y) ? ws.v.y : 1e-12f;
-          wmax = fmaxf(wmax, fmaxf(w0, w1));
-          const size_t o = (size_t)(r + H2_GHOST) * W + xa;  // even column, W % 4 == 0: 8-byte aligned
-          *reinterpret_cast<float2 *>(Uout + o) = Un.rho.v;
-          *reinterpret_cast<float2 *>(Uout + PL + o) = Un.mx.v;
-          *reinterpret_cast<float2 *>(Uout + 2 * PL + o) = Un.my.v;
-          *reinterpret_cast<float2 *>(Uout + 3 * PL + o) = Un.E.v;
-          if ((unsigned)(r - H2_GHOST) >= interior_rows) {
-            if (peer.up_out != nullptr && r < H2_GHOST) {
-              pushed = true;
-              float *o_up = static_cast<float *>(peer.up_out);
-              const size_t og = (size_t)(peer.up_hl + H2_GHOST + r) * W + xa;
-              *reinterpret_cast<float2 *>(o_up + og) = Un.rho.v;
-              *reinterpret_cast<float2 *>(o_up + peer.up_plane + og) = Un.mx.v;
-              *reinterpret_cast<float2 *>(o_up + 2 * peer.up_plane + og) = Un.my.v;
-              *reinterpret_cast<float2 *>(o_up + 3 * peer.up_plane + og) = Un.E.v;
-            }
-            if (peer.dn_out != nullptr && r >= P.H_local - H2_GHOST) {
-              pushed = true;
-              float *o_dn = static_cast<float *>(peer.dn_out);
-              const size_t og = (size_t)(r - (P.H_local - H2_GHOST)) * W + xa;
-              *reinterpret_cast<float2 *>(o_dn + og) = Un.rho.v;
-              *reinterpret_cast<float2 *>(o_dn + peer.dn_plane + og) = Un.mx.v;
-              *reinterpret_cast<float2 *>(o_dn + 2 * peer.dn_plane + og) = Un.my.v;
-              *reinterpret_cast<float2 *>(o_dn + 3 * peer.dn_plane + og) = Un.E.v;
-            }
-            const int gy = P.y_begin + r;
-            for (int g = 1; g <= H2_GHOST; ++g) {
-              if (gy == 0 || gy == P.H_global - 1) {
-                const size_t og = (size_t)(r + H2_GHOST + (gy == 0 ? -g : g)) * W + xa;
-                *reinterpret_cast<float2 *>(Uout + og) = Un.rho.v;
-                *reinterpret_cast<float2 *>(Uout + PL + og) = Un.mx.v;
-                *reinterpret_cast<float2 *>(Uout + 2 * PL + og) = Un.my.v;
-                *reinterpret_cast<float2 *>(Uout + 3 * PL + og) = Un.E.v;
-              }
-            }
-          }
-        }
-      }
-      G_bot = G_top;
-      yT_r = yT1;
-      Pr = Pr1;
-      Pr1 = Pr2;
-      ro_m2 = ro_m1;
-      ro_m1 = ro_c;
-      ro_c = ro_p1;
-      ro_p1 = ro_p2;
-    }
-    kb += (unsigned)nblk;
-    __syncwarp();
+#define HP_TM tmU
+#define HP_NITEMS nitems
+#define HP_CLAIM_CTR claim_ctr
+#define HP_HALF_DT half_dt
+#define HP_RING ring
+#define HP_RING_BASE ring_base
+#include "hypersonic2d_pair_item.inc"
+#undef HP_TM
+#undef HP_NITEMS
+#undef HP_CLAIM_CTR
+#undef HP_HALF_DT
+#undef HP_RING
+#undef HP_RING_BASE
   }
   if (first) compute_dt();
   wmax = tau::warp_max(wmax);

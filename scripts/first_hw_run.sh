@@ -22,6 +22,10 @@ run bench_prod 300 python bench.py --no-e2e --no-cpu
 run bench_pair 300 env TAU_HYP2D_PAIR=1 python bench.py --no-e2e --no-cpu
 run bench_prod_512 300 python bench.py --no-e2e --no-cpu --grid-h 512
 run bench_pair_512 300 env TAU_HYP2D_PAIR=1 python bench.py --no-e2e --no-cpu --grid-h 512
+# the fused kernel (TAU_HYP2D_PAIR=2: pair and production items in one kernel per step)
+run fused_parity 300 env TAU_TEST_PAIR=1 TAU_HYP2D_PAIR=2 python -m pytest tests/test_hyp2d_gpu.py -m gpu -q
+run bench_fused 300 env TAU_HYP2D_PAIR=2 python bench.py --no-e2e --no-cpu
+run bench_fused_512 300 env TAU_HYP2D_PAIR=2 python bench.py --no-e2e --no-cpu --grid-h 512
 for rr in 0 4 16; do
   run bench_pair_512_rest$rr 200 env TAU_HYP2D_PAIR=1 TAU_HYP2D_REST_ROWS=$rr python bench.py --no-e2e --no-cpu --grid-h 512
 done

@@ -58,7 +58,7 @@ def run(W, H, steps, dtype, planes=None, mask=None, seg_rows=None, pair=False, c
     cc = default_cfg(W, H, **over)
     os.environ.pop("TAU_HYP2D_PAIR", None)
     if pair:
-        os.environ["TAU_HYP2D_PAIR"] = "1"
+        os.environ["TAU_HYP2D_PAIR"] = str(int(pair))      # True / 1: pair + production kernels; 2: the fused kernel
     h = C.c_void_p()
     try:
         check(L.tau_hyp2d_create(C.byref(cc), W, H, 0 if dtype == "f32" else 1, 0, 0, H, None, C.byref(h)))
@@ -113,7 +113,7 @@ def run_slabs(W, H, steps, dtype, world, pair=False, frames=(), reverse_ranks=Fa
         y += hl
     os.environ.pop("TAU_HYP2D_PAIR", None)
     if pair:
-        os.environ["TAU_HYP2D_PAIR"] = "1"
+        os.environ["TAU_HYP2D_PAIR"] = str(int(pair))
     hs = []
     try:
         for y0, hl in parts:

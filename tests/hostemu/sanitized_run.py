@@ -17,6 +17,9 @@ a, *_ = hyp2d_emu.run(W, H, 6, "f32", geom_x0=W / 3.0)
 b, *_ = hyp2d_emu.run(W, H, 6, "f32", pair=True, geom_x0=W / 3.0)
 assert hyp2d_emu.run.last_work_items[2] > 0
 assert max(float(np.abs(x - y).max()) for x, y in zip(a, b)) < 1e-3
+c, *_ = hyp2d_emu.run(W, H, 6, "f32", pair=2, geom_x0=W / 3.0)     # the fused kernel
+assert all(np.array_equal(x, y) for x, y in zip(b, c))
+hyp2d_emu.run_slabs(200, 60, 5, "f32", 2, pair=2, geom_x0=60.0)
 hyp2d_emu.run(203, 57, 5, "f64", geom_x0=60.0)                 # generic (non-TMA) loader
 hyp2d_emu.run_slabs(200, 60, 5, "f32", 2, pair=True, geom_x0=60.0)   # peer pushes of both kernels
 print("sanitized run clean")

@@ -657,3 +657,38 @@ def test_hyp2d_frame_handover_fuzz(monkeypatch):
                                                        reverse_ranks=bool(rng.integers(0, 2)), geom_x0=W / 3.0)
         assert all(np.array_equal(a, b) for a, b in zip(one, got)) and open_mappings == 0, \
             (case, W, H, world, pre, dtype, [f[1] for f in frames])
+
+
+def test_hyp2d_fused_kernel_equals_the_two_kernel_pair_mode(pretend_device, monkeypatch):
+    """hypersonic2d_fused.cuh (TAU_HYP2D_PAIR=2, never run on hardware): pair and production items claimed from
+    ONE table by ONE kernel per step — the included text of both marches around the production kernel's prologue
+    and epilogue.  Same arithmetic per cell as TAU_HYP2D_PAIR=1, so the results must be bit-identical to it;
+    launches per step drop from 2 to 1; slab mode, frame hand-over and any block order included."""
+    W, H, steps = 308, 96, 10
+    planes, mask = _random_state_with_walls(W, H)
+    for sms, ctas, order in ((3, 2, ""), (1, 1, "reverse"), (5, 3, "random")):
+        pretend_device(sms, ctas)
+        monkeypatch.setenv("TAU_HC_BLOCK_ORDER", order)
+        a, _, ta, _, na = hyp2d_emu.run(W, H, steps, "f32", planes=planes, mask=mask)
+        b, _, tb, dtsb, nb = hyp2d_emu.run(W, H, steps, "f32", planes=planes, mask=mask, pair=1)
+        have_pairs = hyp2d_emu.run.last_work_items[2] > 0         # (tall layers on a tiny device can all touch a hole)
+        c, _, tc, dtsc, nc = hyp2d_emu.run(W, H, steps, "f32", planes=planes, mask=mask, pair=2)
+        assert all(np.array_equal(x, y) for x, y in zip(b, c)) and tb == tc and np.array_equal(dtsb, dtsc)
+        assert nc == na and nb == na + (steps if have_pairs else 0)   # one kernel per step again
+        assert have_pairs or sms == 1
+        assert max(rel_linf(x, y) for x, y in zip(c, a)) < 2e-6
+    monkeypatch.setenv("TAU_HC_BLOCK_ORDER", "")
+    pretend_device(3, 2)
+    one, _, t, _, _ = hyp2d_emu.run(200, 120, 8, "f32", geom_x0=66.0)
+    for world in (2, 3):
+        got, _, ts, open_mappings = hyp2d_emu.run_slabs(200, 120, 8, "f32", world, pair=2, geom_x0=66.0)
+        assert max(rel_linf(x, y) for x, y in zip(got, one)) < 2e-6 and open_mappings == 0
+        assert all(abs(tt - t) <= 1e-9 * t for tt in ts)
+    # the device-side frame hand-over with the fused kernel
+    yy, xx = np.mgrid[0:120, 0:200]
+    rho = 1.0 + 0.3 * np.sin(xx / 9.0) * np.cos(yy / 7.0)
+    u, v = 3.0 + 0.5 * np.cos(xx / 11.0), 0.7 * np.sin(yy / 5.0)
+    frame = [rho, rho * u, rho * v, (1.0 + 0.2 * np.cos((xx + yy) / 13.0)) / 0.1 + 0.5 * rho * (u * u + v * v)]
+    f1, _, _, _ = hyp2d_emu.run_slabs(200, 120, 3, "f32", 2, pair=1, frames=[(frame, 4)], geom_x0=66.0)
+    f2, _, _, _ = hyp2d_emu.run_slabs(200, 120, 3, "f32", 2, pair=2, frames=[(frame, 4)], geom_x0=66.0)
+    assert all(np.array_equal(x, y) for x, y in zip(f1, f2))

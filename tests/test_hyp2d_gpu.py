@@ -233,15 +233,21 @@ def test_errors_are_loud():
 @pytest.mark.skipif(os.environ.get("TAU_TEST_PAIR") != "1",
                     reason="experimental packed two-column kernel (hypersonic2d_pair.cuh): written after the "
                            "round-1 GPU budget was spent, not yet run on hardware; enable with TAU_TEST_PAIR=1")
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("W,H,steps", [(256, 128, 40), (1024, 512, 100)])
-def test_pair_mode_matches_production_path(W, H, steps, monkeypatch):
-    """TAU_HYP2D_PAIR=1: interior body-free items go through hyp2d_step_pair, the rest through hyp2d_step.
+def test_pair_mode_matches_production_path(W, H, steps, mode, monkeypatch):
+    """TAU_HYP2D_PAIR=1: interior body-free items go through hyp2d_step_pair, the rest through hyp2d_step;
+    =2: both kinds of item through the one fused kernel (bit-identical to =1).
     Same expression trees with the FMA contractions spelled out, so the two paths agree to fp32
     round-off growth (bounds of test_f32_error_growth), and both against the fp64 oracle."""
     base, m, t0, _ = product_run(W, H, steps, "f32")
-    monkeypatch.setenv("TAU_HYP2D_PAIR", "1")
+    monkeypatch.setenv("TAU_HYP2D_PAIR", str(mode))
     pair, m2, t1, _ = product_run(W, H, steps, "f32")
     assert np.array_equal(m, m2)
+    if mode == 2:
+        monkeypatch.setenv("TAU_HYP2D_PAIR", "1")
+        two, _, t2, _ = product_run(W, H, steps, "f32")
+        assert all(np.array_equal(a, b) for a, b in zip(pair, two)) and t1 == t2
     for k, a, b in zip(NAMES, pair, base):
         assert rel_linf(a, b) < 5e-4, k
     assert abs(t1 - t0) < 1e-5 * t0

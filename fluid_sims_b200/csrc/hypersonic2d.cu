@@ -1446,6 +1446,7 @@ int tau_hyp2d_upload_peers_async(tau_hyp2d *h, const void *const planes[4]) {
   TAU_REQUIRE(h && planes, "tau_hyp2d_upload_peers_async: null argument");
   TAU_REQUIRE(h->peers_attached, "tau_hyp2d_upload_peers_async: no peers attached (use tau_hyp2d_upload_async)");
   TAU_REQUIRE(h->speed_valid, "tau_hyp2d_upload_peers_async: no state yet (first frame: tau_hyp2d_upload + exchange)");
+  for (int f = 0; f < 4; ++f) TAU_REQUIRE(planes[f], "tau_hyp2d_upload_peers_async: null plane %d", f);
   TAU_CUDA(cudaSetDevice(h->device));
   if (h->items_dirty) {  // pair mode needs its claim counters allocated before the first clear
     const int rc = h->dtype ? launch_steps<double>(h, 0) : launch_steps<float>(h, 0);
@@ -1456,11 +1457,9 @@ int tau_hyp2d_upload_peers_async(tau_hyp2d *h, const void *const planes[4]) {
   h->launches++;
   const int es = elem_size(h);
   const size_t row0 = (size_t)H2_GHOST * h->W, n = (size_t)h->W * h->h_local;
-  for (int f = 0; f < 4; ++f) {
-    TAU_REQUIRE(planes[f], "tau_hyp2d_upload_peers_async: null plane %d", f);
+  for (int f = 0; f < 4; ++f)
     TAU_CUDA(cudaMemcpyAsync((char *)h->U[h->cur] + (f * h->plane_elems + row0) * es, planes[f], n * es,
                              cudaMemcpyHostToDevice, h->stream));
-  }
   int rc = h->dtype ? launch_fill_ghost<double>(h, 0) : launch_fill_ghost<float>(h, 0);
   if (rc) return rc;
   rc = h->dtype ? launch_wavespeed<double>(h, next) : launch_wavespeed<float>(h, next);

@@ -15,7 +15,7 @@ namespace {
 
 constexpr unsigned HF_PAIR_BIT = 0x40000000u;
 
-__global__ void __launch_bounds__(H2_WARPS * 32, 3)
+__global__ void __launch_bounds__(H2_WARPS * 32, HP_MIN_CTAS)
 hyp2d_step_fused(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmPair,
                  const Params<float> P, const float *__restrict__ Uin, float *__restrict__ Uout,
                  const uint8_t *__restrict__ mask, const uint2 *__restrict__ items, Ctrl *__restrict__ ctrl,

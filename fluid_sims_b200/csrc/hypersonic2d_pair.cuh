@@ -21,6 +21,9 @@
 
 namespace {
 
+#ifndef HP_MIN_CTAS
+#define HP_MIN_CTAS 3   // resident CTAs per SM the register allocation must allow: 3 -> 168 registers, no spills;
+#endif                  // 4 -> 128 registers with ~190 bytes of spill stores per thread (compile-time fact; untried)
 constexpr int HP_OWN = 60;   // columns owned per warp strip
 constexpr int HP_BOXW = 68;  // staged columns: bx = x0 - 4 (x0 = 60 s is a multiple of 4), bx .. bx+67
 constexpr int HP_SLOT = 4 * H2_RB * HP_BOXW;  // floats per ring slot
@@ -206,7 +209,7 @@ struct Ring2 {
 
 // Interior, body-free work items only.  `ctrl->next_item` is NOT used: the pair kernel claims from its own
 // counter `claim_ctr[step_slot]` (cleared two steps ahead like the others).  No bookkeeping of sim_t here.
-__global__ void __launch_bounds__(H2_WARPS * 32, 3)
+__global__ void __launch_bounds__(H2_WARPS * 32, HP_MIN_CTAS)
 hyp2d_step_pair(const __grid_constant__ CUtensorMap tmU, const Params<float> P, float *__restrict__ Uout,
                 const uint2 *__restrict__ items, int nitems, Ctrl *__restrict__ ctrl,
                 unsigned int *__restrict__ claim_ctr, int step_slot, const PeerPush peer) {

@@ -29,6 +29,10 @@ run bench_fused_512 300 env TAU_HYP2D_PAIR=2 python bench.py --no-e2e --no-cpu -
 for rr in 0 4 16; do
   run bench_pair_512_rest$rr 200 env TAU_HYP2D_PAIR=1 TAU_HYP2D_REST_ROWS=$rr python bench.py --no-e2e --no-cpu --grid-h 512
 done
+# 4 CTAs/SM build of the pair / fused kernels (128 registers, some spill) in a separate library
+run ctas4_build 400 make -C fluid_sims_b200/csrc BUILD=../../build/csrc_ctas4 OUT=../libtau_b200_ctas4.so EXTRA_hypersonic2d=-DHP_MIN_CTAS=4
+run bench_pair_ctas4 300 env TAU_B200_LIB=fluid_sims_b200/libtau_b200_ctas4.so TAU_HYP2D_PAIR=1 python bench.py --no-e2e --no-cpu
+run bench_fused_ctas4 300 env TAU_B200_LIB=fluid_sims_b200/libtau_b200_ctas4.so TAU_HYP2D_PAIR=2 python bench.py --no-e2e --no-cpu
 # 1b. ncu of the pair kernel (one launch of the developed flow; ~40 replays) and the launch list of a pair-mode step
 run pair_ncu 600 env TAU_HYP2D_PAIR=1 ncu --set full --clock-control none --import-source on -k regex:hyp2d_step_pair \
   -s 300 -c 1 -o "$OUT/pair_prof" python bench.py --steps 4 --warmup 3 --develop 300 --no-e2e --no-cpu

@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # First hardware run of everything that was written after the round-1 GPU budget was spent (NEXT.md).
 # One gpurun call, each part under its own timeout so that a hang costs minutes, not the box:
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/first_hw_run.sh'
+#   /usr/local/graft/bin/gpurun --timeout 2700 -- 'bash scripts/first_hw_run.sh'
 # Everything lands in gpurun_out/first_hw_run/.
 set -u
 OUT=gpurun_out/first_hw_run

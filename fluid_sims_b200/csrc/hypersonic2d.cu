@@ -988,6 +988,9 @@ int build_items_pair(tau_hyp2d *h) {
   const int nstrips = (h->W + H2_OWN - 1) / H2_OWN;
   // index the 30-column items by (layer start row, strip)
   std::vector<uint2> pair, rest;
+  // the fused kernel's single table: masked items first (the costliest), then layer by layer — tall layers
+  // first, short ones last, as the guided schedule built them — pair and plain items in strip order
+  std::vector<uint2> fused_head, fused_tail;
   std::vector<int> pos((size_t)nstrips);
   std::vector<unsigned> layers;
   for (int i = 0; i < n; ++i) {
@@ -1006,17 +1009,19 @@ int build_items_pair(tau_hyp2d *h) {
       const bool clean = a >= 0 && b >= 0 && !(all[a].x >> 31) && !(all[b].x >> 31);
       if (inside && clean) {
         pair.push_back(make_uint2((unsigned)ss, ly));
+        fused_tail.push_back(make_uint2((unsigned)ss | HF_PAIR_BIT, ly));
       } else {
-        if (a >= 0) rest.push_back(all[a]);
-        if (b >= 0) rest.push_back(all[b]);
+        for (int i : {a, b})
+          if (i >= 0) {
+            rest.push_back(all[i]);
+            ((all[i].x >> 31) ? fused_head : fused_tail).push_back(all[i]);
+          }
       }
     }
   }
-  if (h->fused_mode) {  // one table: masked items first (longest), then the pair items, then the plain leftovers
-    std::vector<uint2> fused;
-    for (const uint2 &d : rest) if (d.x >> 31) fused.push_back(d);
-    for (const uint2 &d : pair) fused.push_back(make_uint2(d.x | HF_PAIR_BIT, d.y));
-    for (const uint2 &d : rest) if (!(d.x >> 31)) fused.push_back(d);
+  if (h->fused_mode) {
+    std::vector<uint2> fused(fused_head);
+    fused.insert(fused.end(), fused_tail.begin(), fused_tail.end());
     if (h->items_fused) TAU_CUDA(cudaFree(h->items_fused));
     h->items_fused = nullptr;
     TAU_CUDA(cudaMalloc(&h->items_fused, (fused.size() + 1) * sizeof(uint2)));

@@ -36,7 +36,11 @@
 #define __host__
 #define __forceinline__ inline
 #define __noinline__ __attribute__((noinline))
-#define __shared__ static
+// `__shared__` variables are function-local statics collected in one ELF section, so that the launcher can
+// poison ALL of them (0xFF bytes: NaN floats, huge integers) before every block: shared memory is
+// uninitialised on a GPU and does not survive from one block to the next.
+#define __shared__ static __attribute__((section("tau_hc_smem")))
+extern "C" char __start_tau_hc_smem[] __attribute__((weak)), __stop_tau_hc_smem[] __attribute__((weak));
 #define __launch_bounds__(...)
 #define __grid_constant__
 #define __constant__   /* a plain global; cudaMemcpyToSymbol is a memcpy */
@@ -200,6 +204,7 @@ static inline void launch(dim3 g, dim3 b, const std::function<void()> &fn) {
         const unsigned bx = (unsigned)(order[oi] % g.x), by = (unsigned)((order[oi] / g.x) % g.y),
                        bz = (unsigned)(order[oi] / ((size_t)g.x * g.y));
         blockIdx = {bx, by, bz};
+        if (__start_tau_hc_smem) memset(__start_tau_hc_smem, 0xFF, (size_t)(__stop_tau_hc_smem - __start_tau_hc_smem));
         nlive = nt;
         blk_arrived = 0;
         blk_or = 0;

@@ -21,6 +21,19 @@ pytestmark = [pytest.mark.gpu] + ([] if os.environ.get("TAU_TEST_4SPL") == "1" e
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
+def _require_healthy_cuda_context():
+    """The reference drivers exit() on a CUDA error (the reference's CUDA_CHECK policy).  If an earlier failure of
+    never-run code left a sticky error in this process, skip instead of letting them end the whole test run."""
+    from fluid_sims_b200.gray_scott import GrayScott, Params as GsParams
+    try:
+        g = GrayScott(GsParams(nx=32, ny=32)).init()
+        g.step(1)
+        g.download()
+        g.close()
+    except Exception as e:      # noqa: BLE001
+        pytest.skip(f"CUDA context unusable after an earlier failure: {e}")
+
+
 def test_export_frame_equals_the_reference_host_loop():
     for n in (64, 40):                       # 40: dx = 1/40 is not a power of two (mode 8 != mode 0 in the last bit)
         s = Hypersonic3D(Params.default(n, n, n)).init()
@@ -41,6 +54,7 @@ def test_schlieren_mode_8_vs_reference_k_vis_on_the_exporters_grid():
     s = Hypersonic3D(Params.default(64, 64, 64)).init()
     s.step(100)
     planes, _ = s.download()
+    _require_healthy_cuda_context()
     ref = oracle.ref_hyp3d_vis(oracle.hyp3d_params(64, 64, 64), planes, 0)
     assert np.abs(s.vis(8) - ref).max() <= 2e-5 * np.abs(ref).max()
     s.close()

@@ -27,6 +27,19 @@ pytestmark = [pytest.mark.gpu] + ([] if os.environ.get("TAU_TEST_SW") == "1" els
 GENTLE = dict(H0=2.0, bumpAmp=0.4, bumpSigma=5, asym=0.3, swirl=0.05, swirlRc=10, offx=3, offy=-2)
 
 
+def _require_healthy_cuda_context():
+    """The reference drivers exit() on a CUDA error (the reference's CUDA_CHECK policy).  If an earlier failure of
+    never-run code left a sticky error in this process, skip instead of letting them end the whole test run."""
+    from fluid_sims_b200.gray_scott import GrayScott, Params as GsParams
+    try:
+        g = GrayScott(GsParams(nx=32, ny=32)).init()
+        g.step(1)
+        g.download()
+        g.close()
+    except Exception as e:      # noqa: BLE001
+        pytest.skip(f"CUDA context unusable after an earlier failure: {e}")
+
+
 def product(P, s0, u0, v0, steps, chunks=1):
     h = ShallowWater(P).upload(s0, u0, v0)
     for _ in range(chunks):
@@ -89,6 +102,7 @@ def test_vs_reference_kernels_where_they_are_deterministic(kw, steps, tol):
     P, op = Params(**kw), oracle.sw_params(**kw)
     a = initialize_host(P)
     (s, u, v), ck, _ = product(P, *a, steps)
+    _require_healthy_cuda_context()
     rs, ru, rv, rck, dts, _ = oracle.ref_sw_run(op, *a, steps)
     err = max(float(np.abs(s - rs).max()), float(np.abs(u - ru).max()), float(np.abs(v - rv).max()))
     print(f"\nsw vs reference kernels {kw} x{steps}: {err:.3e} (bound {tol:g})")
@@ -102,6 +116,7 @@ def test_vs_reference_kernels_with_viscosity():
     P, op = Params(**kw), oracle.sw_params(**kw)
     a = initialize_host(P)
     (s, u, v), ck, _ = product(P, *a, 60)
+    _require_healthy_cuda_context()
     r1, r2 = oracle.ref_sw_run(op, *a, 60), oracle.ref_sw_run(op, *a, 60)
     scatter = max(float(np.abs(x - y).max()) for x, y in zip(r1[:3], r2[:3]))      # the race, run to run
     err = max(float(np.abs(x - y).max()) for x, y in zip((s, u, v), r1[:3]))

@@ -14,7 +14,8 @@ run() {  # name, timeout seconds, command...
   tail -n 3 "$OUT/$name.log" | sed 's/^/   /' >> "$OUT/summary.txt"
 }
 # 0. the validated suite first: a regression there outranks everything below
-run gpu_suite 900 python -m pytest tests -m gpu -x -q
+run gpu_suite 900 python -m pytest tests -m gpu -q
+run sph_diag 600 python scripts/sph_diag.py
 # 1. pair kernel (hypersonic2d_pair.cuh): parity, then speed at the headline size and at a 512-row slab
 run pair_parity 300 env TAU_TEST_PAIR=1 python -m pytest tests/test_hyp2d_gpu.py -m gpu -k pair -q -s
 run pair_suite 600 env TAU_HYP2D_PAIR=1 python -m pytest tests/test_hyp2d_gpu.py -m gpu -q

@@ -1401,6 +1401,9 @@ int tau_hyp2d_init(tau_hyp2d *h) {
   h->slot_bias = 0;
   h->items_dirty = true;
   TAU_CUDA(cudaMemsetAsync(h->ctrl, 0, sizeof(Ctrl), h->stream));
+  // the pair kernel's claim counters rotate with the step count like the control slots: a stale one would make
+  // the first step after a re-init claim from nwarps_grid + stale and skip work items
+  if (h->pair_ctr) TAU_CUDA(cudaMemsetAsync(h->pair_ctr, 0, 3 * sizeof(unsigned int), h->stream));
   int rc = h->dtype ? launch_init<double>(h) : launch_init<float>(h);
   if (rc) return rc;
   rc = hyp2d_state_changed(h, 1);
@@ -1788,6 +1791,7 @@ int tau_hyp2d_set_clock(tau_hyp2d *h, double sim_t, long long steps_done) {
   c.maxspeed[ctl_slot(h)] = ms;
   c.sim_t = sim_t;
   TAU_CUDA(cudaMemcpyAsync(h->ctrl, &c, sizeof(Ctrl), cudaMemcpyHostToDevice, h->stream));
+  if (h->pair_ctr) TAU_CUDA(cudaMemsetAsync(h->pair_ctr, 0, 3 * sizeof(unsigned int), h->stream));
   TAU_CUDA(cudaStreamSynchronize(h->stream));
   return TAU_OK;
 }

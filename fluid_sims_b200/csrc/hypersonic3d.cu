@@ -26,6 +26,12 @@
 #include <new>
 #include <vector>
 
+// The packed WENO5 pair (weno5_pair below) is the default since its first hardware run (round 2: all 16 parity
+// tests of tests/test_hyp3d_gpu.py green, 3.29 -> 3.01 ms/step at 256^3); -DT3_SCALAR_WENO keeps the scalar form.
+#if !defined(T3_SCALAR_WENO) && !defined(T3_PACKED_WENO)
+#define T3_PACKED_WENO
+#endif
+
 namespace {
 
 constexpr int T3_TX = 8, T3_TY = 8, T3_TZ = 4, T3_H = 3;
@@ -239,9 +245,8 @@ __device__ __forceinline__ float weno5_left(float v0, float v1, float v2, float 
 // Both one-sided reconstructions of a face use the same six values: L = weno5_left(v0..v4) and
 // R = weno5_left(v5..v1).  Evaluated side by side as the two halves of a float2 they run on sm_100's
 // packed FADD2/FMUL2/FFMA2 (the body is pure add/mul/fma apart from one reciprocal): same expression
-// trees with the contractions spelled out.  COMPILE-TIME OPTION, OFF BY DEFAULT: written when the
-// round's GPU budget was spent; static effect recorded in profiles/hyp3d_r1_experiments.md, to be
-// validated against tests/test_hyp3d_gpu.py before it is switched on.
+// trees with the contractions spelled out.  Static effect: profiles/hyp3d_r1_experiments.md; measured:
+// profiles/r2_first_hw_run.md.
 __device__ __forceinline__ float2 weno5_pair(float v0, float v1, float v2, float v3, float v4, float v5) {
   const float2 a0 = make_float2(v0, v5), a1 = make_float2(v1, v4), a2 = make_float2(v2, v3),
                a3 = make_float2(v3, v2), a4 = make_float2(v4, v1);

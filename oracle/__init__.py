@@ -300,6 +300,42 @@ class RefHypCpu:
         return planes, mask
 
 
+# plain-C restatement of tau_hypersonic.c (oracle/hypcpu_oracle.c), run-time grid extents
+lib.hypcpu_init.argtypes = [C.c_int, C.c_int, f64p, f64p, f64p, f64p, u8p]
+lib.hypcpu_init.restype = None
+lib.hypcpu_step.argtypes = [C.c_int, C.c_int, f64p, f64p, f64p, f64p, u8p, C.c_int, C.POINTER(C.c_double), f64p]
+lib.hypcpu_step.restype = None
+lib.hypcpu_render.argtypes = [C.c_int, C.c_int, f64p, f64p, f64p, f64p, u8p, C.c_int, u8p, f64p, f64p]
+lib.hypcpu_render.restype = None
+
+
+def hypcpu_init(W, H):
+    """init_sim (tau_hypersonic.c:450): 4 planes (rho, mx, my, E) of W*H doubles + mask."""
+    planes = [np.empty(W * H, np.float64) for _ in range(4)]
+    mask = np.empty(W * H, np.uint8)
+    lib.hypcpu_init(W, H, *planes, mask)
+    return planes, mask
+
+
+def hypcpu_run(W, H, planes, mask, steps, sim_t=0.0):
+    """`steps` x step_physics (tau_hypersonic.c:500-674) -> (planes, sim_t, dts)."""
+    planes = [np.ascontiguousarray(p, np.float64).ravel().copy() for p in planes]
+    t = C.c_double(sim_t)
+    dts = np.zeros(max(steps, 1), np.float64)
+    lib.hypcpu_step(W, H, *planes, np.ascontiguousarray(mask, np.uint8).ravel(), steps, C.byref(t), dts)
+    return planes, float(t.value), dts[:steps]
+
+
+def hypcpu_render(W, H, planes, mask, view_mode=2):
+    """main()'s render loop (tau_hypersonic.c:713-786): (rgba[H, W, 4], (min, max), values[H, W])."""
+    planes = [np.ascontiguousarray(p, np.float64).ravel() for p in planes]
+    rgba = np.zeros(W * H * 4, np.uint8)
+    mm = np.zeros(2, np.float64)
+    vals = np.zeros(W * H, np.float64)
+    lib.hypcpu_render(W, H, *planes, np.ascontiguousarray(mask, np.uint8).ravel(), view_mode, rgba, mm, vals)
+    return rgba.reshape(H, W, 4), (float(mm[0]), float(mm[1])), vals.reshape(H, W)
+
+
 # ------------------------------------------------------------------------------------------------
 # 3-D hypersonic (tau_hypersonic_3d_cuda.cu), fp32
 # ------------------------------------------------------------------------------------------------

@@ -2,8 +2,11 @@
 reference's own (racy) kernels and the sorted-order CPU oracle, and how far is the reference from
 itself run to run.  Prints, per configuration, the fraction of particles whose position differs by
 more than 2e-5 and the largest difference.  Checker-side script (imports oracle/)."""
+import os
 import sys
 import time
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 
 import numpy as np
 

@@ -47,6 +47,21 @@ def th3cs():
     print("th3cs host golden written", hdr)
 
 
+def hypcpu():
+    # BASELINE config 1: the reference's CPU solver tau_hypersonic.c compiled at 256 x 256 with its own flags
+    # (oracle/_ref/libref_hypcpu_256x256.so), init_sim + 10 warm-up + 200 steps of step_physics
+    r = oracle.RefHypCpu(256, 256)
+    r.init()
+    p0, mask = r.get()
+    r.steps(10)
+    t10 = r.sim_t
+    r.steps(200)
+    p210, _ = r.get()
+    np.savez_compressed(os.path.join(OUT, "hypcpu_ref_256x256.npz"), mask=mask, rho0=p0[0], E0=p0[3],
+                        rho=p210[0], mx=p210[1], my=p210[2], E=p210[3], sim_t=np.array([t10, r.sim_t]))
+    print("tau_hypersonic.c 256x256 golden written", t10, r.sim_t)
+
+
 if __name__ == "__main__":
-    for w in (sys.argv[1:] or ["sw", "th3cs"]):
+    for w in (sys.argv[1:] or ["sw", "th3cs", "hypcpu"]):
         globals()[w]()

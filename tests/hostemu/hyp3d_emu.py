@@ -1,5 +1,5 @@
 """TEST INFRASTRUCTURE ONLY — ctypes harness over the product's hypersonic3d.cu run by the CPU fiber
-emulator (see hostemu.h).  `packed=True` builds it with -DT3_PACKED_WENO (the opt-in packed WENO5 pair)."""
+emulator (see hostemu.h).  `packed=True` is the default build (packed WENO5 pair), `packed=False` builds it with -DT3_SCALAR_WENO."""
 import ctypes as C
 import os
 import sys
@@ -25,8 +25,8 @@ def cparams(prm, t0=1e-5, d_tau0=1e-3):
 
 def lib(packed=False):
     if packed not in _libs:
-        L = C.CDLL(hostemu_build.build("hypersonic3d", defines=("T3_PACKED_WENO",), tag="_packed") if packed
-                   else hostemu_build.build("hypersonic3d"))
+        L = C.CDLL(hostemu_build.build("hypersonic3d") if packed
+                   else hostemu_build.build("hypersonic3d", defines=("T3_SCALAR_WENO",), tag="_scalar"))
         h = C.c_void_p
         L.tau_hyp3d_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(h)]
         L.tau_hyp3d_init.argtypes = [h]

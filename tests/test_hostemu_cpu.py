@@ -266,7 +266,7 @@ def test_hyp2d_pair_mode_declines_what_it_cannot_do(pretend_device):
         assert all(np.array_equal(x, y) for x, y in zip(a, b))
 
 
-# ---- 3-D hypersonic solver, default build and the opt-in packed WENO5 pair (-DT3_PACKED_WENO) ------------------
+# ---- 3-D hypersonic solver, default build (packed WENO5 pair) and the scalar form (-DT3_SCALAR_WENO) ----------
 import hyp3d_emu  # noqa: E402  (tests/hostemu)
 
 
@@ -284,7 +284,7 @@ def test_hyp3d_default_and_packed_weno_builds(developed_3d_flow, steps, tol):
     """lam / zet (log-type thermodynamic variables) amplify fp32 rounding differences to ~1e-3 within one
     step at a few cells of the shock layer — the same size on the GPU (tests/test_hyp3d_gpu.py TOL_DEV) —
     while xi / phi stay at the 1e-7 level; an indexing or pairing mistake would show there at O(0.1).
-    The packed build (never run on hardware) must sit inside the same envelope, against the oracle AND
+    The packed build (the default since its first hardware run in round 2) must sit inside the same envelope, against the oracle AND
     against the default build."""
     prm, dev, solid = developed_3d_flow
     clock = (0.012, 2e-3)

@@ -217,16 +217,86 @@ def test_gs_init_pattern_matches_reference_golden():
     assert np.array_equal(u, g["u0"]) and np.array_equal(v, g["v0"])
 
 
+def test_hypcpu_oracle_is_the_reference_bit_for_bit_golden():
+    """BASELINE config 1 (tau_hypersonic.c, 256 x 256): init_sim + 10 warm-up + 200 steps of
+    step_physics.  tests/golden/hypcpu_ref_256x256.npz is the state of the reference's own object code
+    (oracle/_ref/libref_hypcpu_256x256.so, `gcc -O3`; generator tests/golden/make_golden_host.py hypcpu);
+    the restatement oracle/hypcpu_oracle.c has to reproduce it to 0 ulp — fields, mask and sim_t."""
+    g = np.load(os.path.join(GOLDEN, "hypcpu_ref_256x256.npz"))
+    planes, mask = oracle.hypcpu_init(256, 256)
+    assert np.array_equal(mask, g["mask"]) and np.array_equal(planes[0], g["rho0"]) and np.array_equal(planes[3], g["E0"])
+    planes, t10, _ = oracle.hypcpu_run(256, 256, planes, mask, 10)
+    planes, t210, dts = oracle.hypcpu_run(256, 256, planes, mask, 200, sim_t=t10)
+    assert t10 == g["sim_t"][0] and t210 == g["sim_t"][1]
+    for a, k in zip(planes, ("rho", "mx", "my", "E")):
+        assert np.array_equal(a, g[k]), k
+    assert (dts > 0).all() and np.ptp(g["rho"]) > 1.0          # a bow shock did form
+
+
 @pytest.mark.skipif(not oracle.has_ref("ref_hypcpu_256x256"), reason="oracle/_ref not built")
-def test_reference_cpu_solver_runs_config1():
-    """BASELINE config 1 (tau_hypersonic.c 256x256 on the host CPU): the compiled reference steps,
-    stays finite and positive, and its sim_t advances."""
-    r = oracle.RefHypCpu(256, 256)
+def test_hypcpu_oracle_is_the_reference_bit_for_bit_live():
+    """the same comparison against the compiled reference itself on a perturbed state (uploaded through
+    ref_hypcpu_set): a second body, a slow pocket and a low-pressure pocket exercise the slip-wall ghost on
+    every side, the subsonic HLLC branches and the positivity fix."""
+    W = H = 256
+    r = oracle.RefHypCpu(W, H)
     r.init()
-    r.steps(5)
     planes, mask = r.get()
-    assert r.sim_t > 0 and np.isfinite(planes[3]).all() and planes[0].min() > 0
-    assert mask.sum() > 0
+    rng = np.random.default_rng(5)
+    yy, xx = np.mgrid[0:H, 0:W]
+    mask = mask.reshape(H, W).copy()
+    mask[(xx - 170) ** 2 + (yy - 60) ** 2 < 15 ** 2] = 1
+    mask[200:230, 120:124] = 1
+    rho = 1.0 + 0.3 * rng.random((H, W))
+    u = np.where((xx > 100) & (xx < 140) & (yy > 150), 0.3, 17.0) + rng.normal(0, 0.2, (H, W))
+    v = rng.normal(0, 0.5, (H, W))
+    pr = np.where((xx - 60) ** 2 + (yy - 200) ** 2 < 100, 1e-9, 1.0 + 0.2 * rng.random((H, W)))
+    u[mask == 1] = 0
+    v[mask == 1] = 0
+    planes = [rho.ravel(), (rho * u).ravel(), (rho * v).ravel(), (pr / 0.4 + 0.5 * rho * (u * u + v * v)).ravel()]
+    mask = mask.ravel()
+    r.lib.ref_hypcpu_set(*[np.ascontiguousarray(p) for p in planes], mask)
+    t0 = r.sim_t
+    r.steps(12)
+    rp, rm = r.get()
+    op, t, _ = oracle.hypcpu_run(W, H, planes, mask, 12, sim_t=t0)
+    assert np.array_equal(rm, mask) and t == r.sim_t
+    for a, b in zip(op, rp):
+        assert np.array_equal(a, b)
+    assert np.isfinite(rp[3]).all()
+
+
+def test_hypcpu_render_oracle_speed_mode():
+    """main()'s render loop (tau_hypersonic.c:713-786) in "speed mode" (view_mode 2, README.md:1): body grey, the
+    free stream at the top of the colour ramp, the stagnation region at the bottom."""
+    W, H = 96, 64
+    planes, mask = oracle.hypcpu_init(W, H)
+    planes, _, _ = oracle.hypcpu_run(W, H, planes, mask, 30)
+    rgba, (lo, hi), vals = oracle.hypcpu_render(W, H, planes, mask, 2)
+    m = mask.reshape(H, W).astype(bool)
+    assert (rgba[m] == (110, 110, 110, 255)).all() and (rgba[..., 3] == 255).all()
+    assert 0 <= lo < hi and abs(hi - 15.0 * np.sqrt(1.4)) < 1.0
+    assert np.array_equal(rgba[vals == hi][0], (255, 0, 0, 255)) and np.array_equal(rgba[(vals == lo) & ~m][0], (0, 0, 255, 255))
+    for mode in (0, 1, 3):
+        r2, mm, _ = oracle.hypcpu_render(W, H, planes, mask, mode)
+        assert mm[0] < mm[1] and (r2[m] == (110, 110, 110, 255)).all()
+
+
+def test_sw_oracle_close_to_reference_kernels_gpu_golden():
+    """tests/golden/sw_ref.npz: the reference's own shallow-water kernels run on a B200 (nu = 0, where they are
+    deterministic; generator tests/golden/make_golden_gpu.py sw) with -use_fast_math intrinsics; the oracle uses
+    libm, so fp32 round-off separates them (measured 2.4e-6 ... 8.4e-5; the default field has H0 = 1000)."""
+    g = np.load(os.path.join(GOLDEN, "sw_ref.npz"))
+    names = [f[0] for f in oracle.SwParams._fields_]
+    for tag, tol in (("a", 2e-5), ("b", 2e-5), ("c", 4e-4)):
+        kw = {n: (int(v) if n in _SW_INTS else float(v)) for n, v in zip(names, g[f"p19_{tag}"])}
+        prm = oracle.sw_params(**kw)
+        a = oracle.sw_init(prm)
+        assert all(np.array_equal(x, g[f"{k}0_{tag}"]) for x, k in zip(a, "suv")), tag
+        s, u, v, ck, dts = oracle.sw_run(prm, *a, int(g[f"steps_{tag}"]))
+        err = max(float(np.abs(x - g[f"{k}_{tag}"]).max()) for x, k in zip((s, u, v), "suv"))
+        assert err < tol, (tag, err)
+        assert ck[0] == g[f"clock_{tag}"][0] and np.allclose(dts, g[f"dts_{tag}"], rtol=3e-6, atol=0)
 
 
 def test_hyp3d_oracle_matches_reference_golden():

@@ -1,7 +1,7 @@
 """GPU side of the `.4spl` export: tau_hyp3d_export_frame and the th3cs host program.
 
-Written after the round-1 GPU budget was spent; the new kernels have run in the CPU emulator only
-(tests/test_hostemu_cpu.py: bit-identical to the reference's host loop) — see pytestmark below and NEXT.md."""
+First hardware run in round 2 (profiles/r2_first_hw_run.md): all tests passed; the frame indices are integer
+work and bit-identical to the reference's host loop (also in the CPU emulator, tests/test_hostemu_cpu.py)."""
 import os
 import subprocess
 
@@ -12,12 +12,7 @@ import oracle
 from fluid_sims_b200 import splat4
 from fluid_sims_b200.hypersonic3d import Hypersonic3D, Params
 
-# First contact with hardware: the tests RUN, but until a pass has been seen on a B200 (TAU_TEST_4SPL=1 makes them
-# ordinary tests) a failure is reported as xfailed instead of stopping the validated suite (`-x`), and a pass as
-# xpassed.  The kernels have no polling loops (nothing can hang), and these files sort last, after every
-# validated GPU test.
-pytestmark = [pytest.mark.gpu] + ([] if os.environ.get("TAU_TEST_4SPL") == "1" else [
-    pytest.mark.xfail(strict=False, reason=".4spl export kernels: first run on hardware (verified in the CPU emulator only)")])
+pytestmark = pytest.mark.gpu
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 

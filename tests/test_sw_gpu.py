@@ -2,12 +2,11 @@
 is bit-identical to the reference's kernel bodies compiled for the host, tests/test_oracle_cpu.py) and
 against the reference's own kernels on the same device (oracle/_ref/libref_sw.so).
 
-shallow_water.cu was written after the round-1 GPU budget was spent and has not run on hardware yet; a
-never-run kernel must not be able to take the validated suite down with it (see pytestmark below).  The
-bounds below are estimates (fp32, -use_fast_math expf/logf/division on the GPU sides, libm in the oracle);
-with a rough stand-in for the fast intrinsics in the CPU emulator (hostemu.h TAU_HC_ROUGH_FASTMATH) the
-errors are 2e-7 ... 9e-7 for the gentle fields and 3e-5 for the default field, i.e. the bounds have a 20-60x
-margin; replace them by ~4x the measured values on the first run — see NEXT.md.
+First hardware run (round 2, profiles/r2_first_hw_run.md): all tests passed; measured errors (fp32,
+-use_fast_math expf/logf/division on the GPU sides, libm in the oracle): 1.8e-6 ... 5.8e-6 for the gentle
+fields against the CPU oracle, 3.4e-5 for the default (H0 = 1000) field, 6.5e-7 / 2.7e-5 against the
+reference kernels, 7.0e-7 with viscosity where the reference's own run-to-run scatter is 5.8e-7.  The
+bounds below are ~4x those.
 """
 import os
 
@@ -17,12 +16,7 @@ import pytest
 import oracle
 from fluid_sims_b200.shallow_water import Params, ShallowWater, initialize_host
 
-# First contact with hardware: the tests RUN, but until a pass has been seen on a B200 (TAU_TEST_SW=1 makes them
-# ordinary tests) a failure is reported as xfailed instead of stopping the validated suite (`-x`), and a pass as
-# xpassed.  The kernels have no polling loops (nothing can hang), and these files sort last, after every
-# validated GPU test.
-pytestmark = [pytest.mark.gpu] + ([] if os.environ.get("TAU_TEST_SW") == "1" else [
-    pytest.mark.xfail(strict=False, reason="shallow-water kernels: first run on hardware (verified in the CPU emulator only)")])
+pytestmark = pytest.mark.gpu
 
 GENTLE = dict(H0=2.0, bumpAmp=0.4, bumpSigma=5, asym=0.3, swirl=0.05, swirlRc=10, offx=3, offy=-2)
 
@@ -62,8 +56,8 @@ def test_initialize_host_equals_reference():
     (dict(nx=96, ny=64, dtau=0.02, nu=0.0, **GENTLE), 40, 2e-5),
     (dict(nx=96, ny=64, dtau=0.02, nu=0.05, **GENTLE), 40, 2e-5),     # Jacobi viscosity on both sides
     (dict(nx=70, ny=37, dtau=0.05, nu=0.02, dx=2.0, dy=1.5, **GENTLE), 25, 2e-5),   # ragged against 32x16 tiles
-    (dict(nx=33, ny=5, dtau=0.02, nu=0.0, **GENTLE), 20, 2e-5),       # narrower than one tile + halo
-    (dict(nx=96, ny=64, dtau=1e-3), 5, 2e-3),                         # default (violent, H0 = 1000) field
+    (dict(nx=33, ny=5, dtau=0.02, nu=0.0, **GENTLE), 20, 1e-5),       # narrower than one tile + halo
+    (dict(nx=96, ny=64, dtau=1e-3), 5, 1.5e-4),                         # default (violent, H0 = 1000) field
 ])
 def test_matches_cpu_oracle(kw, steps, tol):
     P, op = Params(**kw), oracle.sw_params(**kw)
@@ -95,8 +89,8 @@ def test_lake_at_rest_and_mass():
 
 
 @pytest.mark.skipif(not oracle.has_ref("ref_sw"), reason="oracle/_ref not built")
-@pytest.mark.parametrize("kw,steps,tol", [(dict(nx=512, ny=512, dtau=1e-3, nu=0.0), 5, 2e-3),
-                                          (dict(nx=512, ny=384, dtau=0.02, nu=0.0, **GENTLE), 60, 1e-5)])
+@pytest.mark.parametrize("kw,steps,tol", [(dict(nx=512, ny=512, dtau=1e-3, nu=0.0), 5, 1.2e-4),
+                                          (dict(nx=512, ny=384, dtau=0.02, nu=0.0, **GENTLE), 60, 3e-6)])
 def test_vs_reference_kernels_where_they_are_deterministic(kw, steps, tol):
     """nu = 0: no viscosity_uv, the reference is deterministic and the same intrinsics run on both sides"""
     P, op = Params(**kw), oracle.sw_params(**kw)
@@ -121,7 +115,7 @@ def test_vs_reference_kernels_with_viscosity():
     scatter = max(float(np.abs(x - y).max()) for x, y in zip(r1[:3], r2[:3]))      # the race, run to run
     err = max(float(np.abs(x - y).max()) for x, y in zip((s, u, v), r1[:3]))
     print(f"\nsw nu=0.05: |product - reference| = {err:.3e}; reference run-to-run scatter = {scatter:.3e}")
-    assert err < 1e-4
+    assert err < max(4e-6, 6 * scatter)
 
 
 def test_multi_step_call_equals_single_steps_and_errors_are_loud():

@@ -26,8 +26,22 @@ Definitions
   cpu_baseline  the reference's own tau_hypersonic_simd.c (compiled from the reference sources into
            oracle/_ref with the reference's flags) stepping a 4096 x 256 band of the grid on one
            host core; `--impl reference` runs one independent replica of it per host core.
+  state_crc  checksum of the four state planes after the timed region (develop + warmup + steps solver steps
+           from k_init), computed from per-row weighted sums of the fp32 bit patterns so that ranks can add
+           their parts: identical across N = 1/2/4/8 <=> the slab-decomposed run is bit-identical.
+  dtype_f64  the same solver with the fp64 handle (the instantiation that holds the north-star's 1e-5 bound),
+           short run, N = 1 only.
+  reference_gpu  the reference's own kernels (oracle/_ref, recompiled for sm_100a) timed on the same GPU on the
+           same grid — a yardstick beside the CPU baseline, N = 1 only.
+  other_configs  BASELINE configs 3-5 (Gray-Scott 8192^2, 3-D hypersonic 256^3 at N = 1 / 512^3 z-slabs at N > 1,
+           SPH 2^21 particles), short runs of bench_all.py's benches, each with its roofline and reference_gpu.
 The working set (2 x 268 MB of state) is larger than the 126 MB L2, so no L2 flush is needed
 between timed steps.
+
+Timed region at N > 1: barrier + synchronize, then the W warm-up steps and the K timed steps are enqueued back
+to back; ev0 is recorded IN-STREAM after the last warm-up step (the device-side inbox barrier of every step has
+aligned the ranks by then), ev1 after the K-th step, then barrier + synchronize; max over ranks.  A host barrier
+between warm-up and ev0 would put the ranks' host skew (~1 ms) into a region that lasts 2 ms at N = 8.
 """
 from __future__ import annotations
 
@@ -57,14 +71,35 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
-def profile_traffic():
-    """dram bytes per hyp2d_step launch from the committed ncu summary (profiles/), if present."""
+def profile_constants():
+    """per-launch DRAM bytes and executed warp-instructions of the step kernel at 4096 rows, from the committed
+    ncu capture (profiles/hyp2d_step_traffic.json); both scale with the rows a launch updates."""
     path = os.path.join(ROOT, "profiles", "hyp2d_step_traffic.json")
     try:
         with open(path) as f:
-            return float(json.load(f)["dram_bytes_per_launch"])
+            j = json.load(f)
+        return j
     except Exception:
-        return None
+        return {}
+
+
+def state_crc(torch, dist, planes_view, y0, hl, W, halo, world, dev):
+    """order-independent-across-ranks checksum of the owned rows of the 4 planes (see module docstring)"""
+    import zlib
+    P31 = (1 << 31) - 1
+    bits = planes_view[:, halo:halo + hl, :].contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    rows = torch.arange(y0, y0 + hl, device=bits.device, dtype=torch.int64).view(1, hl, 1)
+    W2 = bits.shape[2]                                      # 2 W words per row for an fp64 handle
+    cols = torch.arange(W2, device=bits.device, dtype=torch.int64).view(1, 1, W2)
+    wgt = (rows * W2 + cols) % 65521 + 1
+    s1 = bits.sum(dim=(1, 2))                               # < 2^56
+    s2 = ((bits * wgt).sum(dim=2) % P31).sum(dim=1)         # row sums < 2^60, then < 2^31 each
+    acc = torch.stack([s1, s2]).to(torch.int64)
+    if world > 1:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+    acc[1] %= P31
+    vals = [int(v) for v in acc.flatten().tolist()]
+    return f"{zlib.crc32(repr(vals).encode()) & 0xFFFFFFFF:08x}", vals
 
 
 class ClockSampler:
@@ -237,15 +272,18 @@ def run_product(a):
 
     # develop the flow first (uniform inflow under-exercises the limiter/HLLC branches)
     advance(a.develop)
-    advance(a.warmup)
     barrier()
 
     sampler = ClockSampler(dev)
     if rank == 0:
         sampler.start()
-    launches0 = sim.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
+    host_driven = world > 1 and not peer     # NCCL exchange per step: nothing aligns the ranks on the device
+    advance(a.warmup)
+    if host_driven:
+        barrier()
+    launches0 = sim.launch_count
+    ev0.record()                             # in-stream, right behind the last warm-up step (see module docstring)
     advance(a.steps)
     ev1.record()
     barrier()
@@ -261,6 +299,8 @@ def run_product(a):
         mine = sim.peer_timing()
         peer_timing = [None] * world
         dist.all_gather_object(peer_timing, {k: round(v, 2) for k, v in mine.items()})
+    crc, crc_parts = state_crc(torch, dist, state_views()[0], y0, hl, W, HALO, world, dev)
+    clock_t, clock_dt = sim.clock()
 
     cells = W * H
     value = cells * a.steps / (ms * 1e-3) / 1e6
@@ -391,9 +431,54 @@ def run_product(a):
                "sample": (f"{a.cpu_steps} x step_physics() of tau_hypersonic_simd.c (gcc -O3 -mavx2 "
                           f"-mfma, oracle/_ref) on a {CPU_BAND[0]}x{CPU_BAND[1]} band of the grid, "
                           f"1 thread (the solver is single-threaded); host has {os.cpu_count()} cores")}
+        if a.cpu_full_steps > 0:
+            try:
+                import oracle
+                r = oracle.RefHypCpu(GRID_W, GRID_H, simd=True)
+                r.init()
+                secs = r.steps(a.cpu_full_steps)
+                cpu["full_grid"] = {"value": GRID_W * GRID_H * a.cpu_full_steps / secs / 1e6, "unit": "Mcell-updates/s",
+                                    "sample": f"{a.cpu_full_steps} x step_physics() on the full {GRID_W}x{GRID_H} grid, 1 thread"}
+            except Exception as e:      # noqa: BLE001 (library not built for this size)
+                cpu["full_grid"] = {"error": str(e)[:200]}
 
+    # ---- the fp64 handle (holds the north-star's 1e-5 bound) and the reference's own kernels, N = 1 only ----
+    f64 = ref_gpu = None
+    if world == 1 and not a.no_extras:
+        try:
+            s64 = Hypersonic2D(cfg, dtype="f64", device=dev, stream=stream).init()
+            s64.step(a.develop_f64)
+            s64.sync()
+            s64.step(a.steps_f64)
+            ms64 = s64.last_step_ms() / a.steps_f64
+            f64 = {"dtype": "f64", "ms_per_step": ms64, "value": cells / (ms64 * 1e-3) / 1e6, "unit": "Mcell-updates/s",
+                   "steps": a.steps_f64, "developed_for": a.develop_f64,
+                   "roofline": {"bound": "hbm", "achieved": 65 * cells / (ms64 * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                "frac": 65 * cells / (ms64 * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_cell": 65},
+                   "parity": "L_inf <= 5.5e-13 vs the reference kernels after 1000 steps (tests/test_hyp2d_gpu.py)"}
+            s64.close()
+        except Exception as e:          # noqa: BLE001
+            f64 = {"error": str(e)[:200]}
+        try:
+            import oracle
+            if oracle.has_ref(f"ref_hyp2d_{W}x{H}"):
+                *_, rms = oracle.ref_hyp2d_run(W, H, oracle.hyp2d_cfg(W, H).as11(), a.steps_ref_gpu)
+                ref_gpu = {"ms_per_step": rms / a.steps_ref_gpu, "value": cells / (rms / a.steps_ref_gpu * 1e-3) / 1e6,
+                           "unit": "Mcell-updates/s", "dtype": "f64", "steps": a.steps_ref_gpu,
+                           "what": "tau_hypersonic_cuda.cu's own step loop (:1833-1889: 7 kernels + an 8-byte D2H and host dt "
+                                   "per step) recompiled for sm_100a, from k_init, same GPU"}
+        except Exception as e:          # noqa: BLE001
+            ref_gpu = {"error": str(e)[:200]}
+
+    prof = profile_constants()
+    frac_rows = hl / 4096.0 * (W / 4096.0)
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    inst = prof.get("warp_instructions_per_launch")
+    issue_frac = (inst * frac_rows / (kernel_ms * 1e-3)) / (sm_count * 4 * sm_mhz * 1e6) if inst else None
+    line = None
     if rank == 0:
-        print(json.dumps({
+        line = {
             "metric": "Mcell-updates/s", "value": value, "unit": "Mcell-updates/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
             "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
@@ -402,22 +487,61 @@ def run_product(a):
                                    f"for {a.develop} steps, then timed",
                        "grid": [W, H], "slab_rows_per_gpu": hl, "parallelism": f"y-slab x{world}" + (f" ({a.exchange} halo exchange)" if world > 1 else ""),
                        "cache": "state (2 x 268 MB) larger than L2 (126 MB): no flush needed",
-                       "seg_rows": sim.seg_rows},
+                       "seg_rows": sim.seg_rows, "step_kernel": sim.kernel_name},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": profile_traffic(),
+                         "frac": ach / peak,
+                         "traffic": prof["dram_bytes_per_launch"] * frac_rows if "dram_bytes_per_launch" in prof else None,
+                         "traffic_source": prof.get("source", None) and (prof["source"] + "; scaled by the rows one launch updates"),
                          "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
-                         "algorithmic_bytes_per_cell": bpc, "kernel": "hyp2d_step",
+                         "algorithmic_bytes_per_cell": bpc, "kernel": sim.kernel_name,
                          "kernel_ms": kernel_ms,
-                         "note": "kernel is FP32-issue bound (685 executed warp-instructions per 30-cell row, 82 % issue-slot utilisation), see DESIGN.md 4.1"},
+                         "limiter": "fp32-issue", "issue_frac": issue_frac,
+                         "issue_peak": f"{sm_count} SMs x 4 schedulers x {sm_mhz:.0f} MHz warp-instructions/s",
+                         "note": "the kernel is FP32-issue bound, not HBM bound: `frac` is the HBM fraction at the algorithmic 33 B/cell, "
+                                 "`issue_frac` the executed warp-instructions (committed ncu capture, scaled by rows) over the issue peak; DESIGN.md 4.1"},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "state_crc": crc, "sim_t": clock_t,
+            **({"dtype_f64": f64} if f64 else {}), **({"reference_gpu": ref_gpu} if ref_gpu else {}),
             **({"peer_timing": peer_timing} if peer_timing else {}),
-        }))
-    if world > 1:
-        if peer:   # unmap the peers' planes on every rank before any rank frees them
+        }
+    if world > 1 and peer:   # unmap the peers' planes on every rank before any rank frees them
+        try:
+            slab.hyp2d_detach_peers(sim)
+        except Exception as e:      # teardown must not turn a finished measurement into a failure
+            print(f"[bench] peer detach: {e}", file=sys.stderr)
+    sim.close()
+
+    # ---- BASELINE configs 3-5, short runs (never allowed to cost the headline line: watchdog) -------------
+    def emit():
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+
+    if not a.no_other:
+        done = threading.Event()
+
+        def watchdog():
+            if not done.wait(a.other_timeout):
+                if rank == 0:
+                    line.setdefault("other_configs", {})["error"] = f"timed out after {a.other_timeout} s"
+                emit()
+                os._exit(0)
+
+        threading.Thread(target=watchdog, daemon=True).start()
+        other = {}
+        import bench_all
+        ba = bench_all.default_args(steps=200, n3=256 if world == 1 else 512, steps3=20, warm3=30, steps_sph=30)
+        for name in (("gs",) if world == 1 else ()) + ("hyp3d", "sph"):
             try:
-                slab.hyp2d_detach_peers(sim)
-            except Exception as e:      # teardown must not turn a finished measurement into a failure
-                print(f"[bench] peer detach: {e}", file=sys.stderr)
+                rec = bench_all.BENCHES[name](ba)
+            except Exception as e:      # noqa: BLE001
+                rec = {"error": f"{type(e).__name__}: {e}"[:300]}
+            other[name] = rec
+            torch.cuda.synchronize()
+        if rank == 0:
+            line["other_configs"] = other
+        done.set()
+    emit()
+    if world > 1:
         dist.destroy_process_group()
 
 
@@ -445,6 +569,13 @@ def main():
                     help="N>1, --exchange peer: device-side frame hand-over (experimental, default off)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fp64-handle and reference-kernel sub-records (N=1)")
+    ap.add_argument("--no-other", action="store_true", help="skip BASELINE configs 3-5 (other_configs)")
+    ap.add_argument("--other-timeout", type=float, default=240.0)
+    ap.add_argument("--cpu-full-steps", type=int, default=3, help="reference CPU solver on the full 4096^2 grid (0 = skip)")
+    ap.add_argument("--develop-f64", type=int, default=100)
+    ap.add_argument("--steps-f64", type=int, default=40)
+    ap.add_argument("--steps-ref-gpu", type=int, default=20)
     a = ap.parse_args()
     if a.warmup < 3 and a.impl == "b200":
         a.warmup = 3

@@ -52,14 +52,14 @@ def bench_gs(a):
         t = C.c_float()
         r.ref_gs_time(n, n, min(a.steps, 200), C.byref(t))
         ref_ms = t.value / min(a.steps, 200)
-    print(json.dumps({"bench": "gray_scott", "grid": [n, n], "steps": a.steps, "ms_per_step": ms,
+    return ({"bench": "gray_scott", "grid": [n, n], "steps": a.steps, "ms_per_step": ms,
                       "value": cells / (ms * 1e-3) / 1e6, "unit": "Mcell-updates/s",
                       "roofline": {"bound": "hbm", "achieved": ach, "peak": peak(), "unit": "GB/s",
                                    "frac": ach / peak(), "algorithmic_bytes_per_cell": 16},
                       "reference_gpu": {"ms_per_step": ref_ms,
                                         "value": cells / (ref_ms * 1e-3) / 1e6 if ref_ms else None,
                                         "what": "tau_gray_scott.cu step_kernel recompiled for sm_100a"},
-                      "gpu_launches": g.launch_count}))
+                      "gpu_launches": g.launch_count})
 
 
 def bench_hyp3d(a):
@@ -127,7 +127,7 @@ def bench_hyp3d(a):
         *_, rms = oracle.ref_hyp3d_run(op, a.steps3, clock=(5e-3, 2e-3))
         ref = rms / a.steps3
     if rank == 0:
-        print(json.dumps({"bench": "hypersonic3d", "grid": [n, n, n], "n_gpus": world,
+        return ({"bench": "hypersonic3d", "grid": [n, n, n], "n_gpus": world,
                           "steps": a.steps3, "ms_per_step": ms,
                           "value": cells / (ms * 1e-3) / 1e6, "unit": "Mcell-updates/s",
                           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak(), "unit": "GB/s",
@@ -137,7 +137,8 @@ def bench_hyp3d(a):
                                             "value": cells / (ref * 1e-3) / 1e6 if ref else None,
                                             "what": "tau_hypersonic_3d_cuda.cu k_step recompiled for "
                                                     "sm_100a incl. its 2 blocking 4-byte copies per step"},
-                          "clock": sim.clock(), "parallelism": f"z-slab ring x{world}"}))
+                          "clock": sim.clock(), "parallelism": f"z-slab ring x{world}"})
+    return None
 
 
 def bench_sph(a):
@@ -196,7 +197,7 @@ def bench_sph(a):
         ref = r[6] / a.steps_sph
     ach = 72 * N / (ms * 1e-3) / 1e9
     if rank == 0:
-        print(json.dumps({"bench": "sph", "particles": N, "n_gpus": world, "substeps": a.steps_sph,
+        return ({"bench": "sph", "particles": N, "n_gpus": world, "substeps": a.steps_sph,
                           "ms_per_substep": ms, "value": N / (ms * 1e-3) / 1e6,
                           "unit": "Mparticle-updates/s",
                           "roofline": {"bound": "hbm", "achieved": ach, "peak": peak(), "unit": "GB/s",
@@ -207,7 +208,8 @@ def bench_sph(a):
                                             "value": N / (ref * 1e-3) / 1e6 if ref else None,
                                             "what": "tau_sph.cu kernels recompiled for sm_100a"},
                           "parallelism": "replicated state, slot-range shards + all-gather x%d" % world,
-                          "gpu_launches": s.launch_count}))
+                          "gpu_launches": s.launch_count})
+    return None
 
 
 def bench_burgers(a):
@@ -230,7 +232,7 @@ def bench_burgers(a):
         k = min(a.steps, 100)
         *_, t = oracle.ref_burgers_run(oracle.burgers_params(nx=n, ny=n, dtau=1e-3, rc=P.rc, bsig=P.bsig), u0, v0, k)
         ref_ms = t / k
-    print(json.dumps({"bench": "burgers", "grid": [n, n], "steps": a.steps, "ms_per_step": ms,
+    return ({"bench": "burgers", "grid": [n, n], "steps": a.steps, "ms_per_step": ms,
                       "value": cells / (ms * 1e-3) / 1e6, "unit": "Mcell-updates/s",
                       "roofline": {"bound": "hbm", "achieved": ach, "peak": peak(), "unit": "GB/s",
                                    "frac": ach / peak(), "algorithmic_bytes_per_cell": bytes_per_cell,
@@ -239,7 +241,7 @@ def bench_burgers(a):
                                         "value": cells / (ref_ms * 1e-3) / 1e6 if ref_ms else None,
                                         "what": "tau_burgers.cu kernels recompiled for sm_100a incl. the per-step "
                                                 "D2H of the block maxima"},
-                      "gpu_launches": s.launch_count}))
+                      "gpu_launches": s.launch_count})
 
 
 def bench_sw(a):
@@ -265,7 +267,7 @@ def bench_sw(a):
         k = min(a.steps, 100)
         *_, t = oracle.ref_sw_run(oracle.sw_params(**kw), *f, k)
         ref_ms = t / k
-    print(json.dumps({"bench": "shallow_water", "grid": [n, n], "steps": a.steps, "ms_per_step": ms,
+    return ({"bench": "shallow_water", "grid": [n, n], "steps": a.steps, "ms_per_step": ms,
                       "value": cells / (ms * 1e-3) / 1e6, "unit": "Mcell-updates/s",
                       "roofline": {"bound": "hbm", "achieved": ach, "peak": peak(), "unit": "GB/s",
                                    "frac": ach / peak(), "algorithmic_bytes_per_cell": bytes_per_cell,
@@ -274,10 +276,21 @@ def bench_sw(a):
                                         "value": cells / (ref_ms * 1e-3) / 1e6 if ref_ms else None,
                                         "what": "tau_shallow_water.cu kernels recompiled for sm_100a incl. the "
                                                 "per-step D2H of the block maxima"},
-                      "gpu_launches": s.launch_count}))
+                      "gpu_launches": s.launch_count})
 
 
-def main():
+BENCHES = {"gs": bench_gs, "hyp3d": bench_hyp3d, "sph": bench_sph, "burgers": bench_burgers, "sw": bench_sw}
+
+
+def default_args(**over):
+    """the argument namespace of main() with its defaults (bench.py's `other_configs` leg calls the benches directly)"""
+    a = make_parser().parse_args([])
+    for k, v in over.items():
+        setattr(a, k, v)
+    return a
+
+
+def make_parser():
     ap = argparse.ArgumentParser()
     ap.add_argument("which", nargs="*", default=[])
     ap.add_argument("--steps", type=int, default=500)
@@ -289,10 +302,16 @@ def main():
     ap.add_argument("--steps-sph", type=int, default=50)
     ap.add_argument("--burgers-n", type=int, default=4096)
     ap.add_argument("--sw-n", type=int, default=4096)
-    a = ap.parse_args()
+    return ap
+
+
+def main():
+    a = make_parser().parse_args()
     which = a.which or ["gs", "hyp3d", "sph"]
     for w in which:
-        {"gs": bench_gs, "hyp3d": bench_hyp3d, "sph": bench_sph, "burgers": bench_burgers, "sw": bench_sw}[w](a)
+        rec = BENCHES[w](a)
+        if rec is not None:
+            print(json.dumps(rec), flush=True)
     # one process group for the whole run (re-initialising NCCL between benches is not reliable)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         import torch.distributed as dist

@@ -1796,6 +1796,8 @@ int tau_hyp2d_set_clock(tau_hyp2d *h, double sim_t, long long steps_done) {
   return TAU_OK;
 }
 long long tau_hyp2d_steps_done(tau_hyp2d *h) { return h ? h->steps : -1; }
+// which step kernel this handle launches: 0 hyp2d_step, 1 hyp2d_step_pair + hyp2d_step, 2 hyp2d_step_fused
+int tau_hyp2d_kernel_mode(tau_hyp2d *h) { return !h ? -1 : (h->pair_mode ? (h->fused_mode ? 2 : 1) : 0); }
 long long tau_hyp2d_launch_count(tau_hyp2d *h) { return h ? h->launches : -1; }
 
 int tau_hyp2d_last_step_ms(tau_hyp2d *h, float *ms) {

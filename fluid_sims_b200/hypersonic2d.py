@@ -36,6 +36,7 @@ _download_async = declare("tau_hyp2d_download_async", [_h, C.POINTER(C.c_void_p)
 _upload_peers_async = declare("tau_hyp2d_upload_peers_async", [_h, C.POINTER(C.c_void_p)])
 _devstate = declare("tau_hyp2d_device_state", [_h, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                                C.POINTER(C.c_void_p)])
+_kernel_mode = declare("tau_hyp2d_kernel_mode", [_h])
 _set_seg = declare("tau_hyp2d_set_seg_rows", [_h, C.c_int])
 _get_seg = declare("tau_hyp2d_get_seg_rows", [_h])
 _ipc_export = declare("tau_hyp2d_ipc_export", [_h, C.c_void_p, C.c_size_t])
@@ -167,6 +168,11 @@ class Hypersonic2D:
     def step(self, nsteps: int = 1):
         check(_step(self._handle, nsteps))
         return self
+
+    @property
+    def kernel_name(self) -> str:
+        """the step kernel(s) this handle launches per step"""
+        return ("hyp2d_step", "hyp2d_step_pair+hyp2d_step", "hyp2d_step_fused")[_kernel_mode(self._handle)]
 
     def clock(self):
         """(sim_t, dt of the last step)."""

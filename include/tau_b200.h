@@ -189,6 +189,9 @@ int tau_hyp2d_plan_layers(int h_local, int nstrips, int resident_warps, int seg_
 /* the height in use (chosen by a wave model at the first step unless set explicitly) */
 int tau_hyp2d_get_seg_rows(tau_hyp2d *h);
 long long tau_hyp2d_steps_done(tau_hyp2d *h);
+/* which step kernel the handle launches: 0 hyp2d_step (one column per lane; fp64, narrow or non-TMA grids),
+ * 1 hyp2d_step_pair + hyp2d_step (two launches), 2 hyp2d_step_fused (two columns per lane, one launch) */
+int tau_hyp2d_kernel_mode(tau_hyp2d *h);
 long long tau_hyp2d_launch_count(tau_hyp2d *h);
 int tau_hyp2d_last_step_ms(tau_hyp2d *h, float *ms);
 int tau_hyp2d_destroy(tau_hyp2d *h);
@@ -396,6 +399,34 @@ long long tau_sw_steps_done(tau_sw *h);
 long long tau_sw_launch_count(tau_sw *h);
 int tau_sw_last_step_ms(tau_sw *h, float *ms);
 int tau_sw_destroy(tau_sw *h);
+
+/* ---------------------------------------------------------------------------------------------
+ * tau_hypersonic (CPU reference solver, tau_hypersonic.c — BASELINE config 1: 256 x 256, "speed mode")
+ * Replaces: `static void step_physics(void)` (tau_hypersonic.c:500-674) on the file-static
+ * `Cons U[W*H]`, `mask[]`, `sim_t` (:38-43), `init_sim` (:450-475) and the render loops of main()
+ * (:713-786).  fp64 on the device; built without FMA contraction: results equal the reference's own
+ * object code (gcc -O3, x86-64) to 0 ulp.  Planes are the SoA view of the reference's AoS state:
+ * rho, mx, my, E, each H x W doubles, index y*W+x (:46).  W and H are run-time here (the reference
+ * fixes them with #define W/H, :12-13).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct tau_hypc tau_hypc;
+int tau_hypc_create(int W, int H, int device, void *stream, tau_hypc **out);
+/* init_sim :450-475 on the host (pure arithmetic, no device needed) */
+void tau_hypc_init_host(int W, int H, double *rho, double *mx, double *my, double *E, uint8_t *mask);
+int tau_hypc_init(tau_hypc *h);
+int tau_hypc_upload(tau_hypc *h, const double *const planes[4], const uint8_t *mask, double sim_t);
+/* THE hot path: nsteps x step_physics — two kernels per step, dt (compute_dt :477-498) and sim_t on the device */
+int tau_hypc_step(tau_hypc *h, int nsteps);
+int tau_hypc_clock(tau_hypc *h, double *sim_t, double *dt_last);
+int tau_hypc_download(tau_hypc *h, double *const planes[4], uint8_t *mask);
+/* view_mode as the reference's `view_mode` (:44): 0 log rho, 1 log p, 2 speed, 3 schlieren; rgba: W*H pixels
+ * (r | g<<8 | b<<16 | 255<<24, the byte order of the reference's `pixels`); minmax_out may be NULL */
+int tau_hypc_render(tau_hypc *h, int view_mode, uint32_t *rgba, double minmax_out[2]);
+int tau_hypc_sync(tau_hypc *h);
+long long tau_hypc_steps_done(tau_hypc *h);
+long long tau_hypc_launch_count(tau_hypc *h);
+int tau_hypc_last_step_ms(tau_hypc *h, float *ms);
+int tau_hypc_destroy(tau_hypc *h);
 
 #ifdef __cplusplus
 }

@@ -95,6 +95,37 @@ def main():
         same = np.array_equal(got[0], fu) and np.array_equal(got[1], fv)
         print(f"gray-scott world={world}: slab == single-GPU: {same}")
         ok &= same
+    # ---- 3-D hypersonic: z-slab ring, halo 3, all-reduce(max) feeding the d_tau controller --------------------
+    # (tau_hypersonic_3d_cuda.cu:1680-1704; z is periodic: the slabs form a ring)
+    from fluid_sims_b200.hypersonic3d import HALO as H3, Hypersonic3D, Params as P3
+    n, steps3 = 48, 30
+    prm = P3.default(n, n, n)
+    z0, nl3 = slab.partition_rows(n, world)[rank]
+    s3 = Hypersonic3D(prm, device=local, z_begin=z0, nz_local=nl3, stream=ts.cuda_stream).init()
+    p0, _ = s3.download()
+    s3.upload(p0, (5e-3, 2e-3))          # late in the inflow ramp: the bow shock forms within the run
+    for _ in range(steps3):
+        pp, mp = s3.device_state()
+        slab.exchange_halos([slab.wrap_plane(pp, (6, nl3 + 2 * H3, n, n), torch.float32, local)], H3, periodic=True, dim=1)
+        s3.step_begin()
+        dist.all_reduce(slab.wrap_plane(mp, (1,), torch.float32, local), op=dist.ReduceOp.MAX)
+        s3.step_end()
+    o3, _ = s3.download()
+    mine = torch.from_numpy(np.stack(o3)).cuda()
+    gathered = [torch.empty((6, c, n, n), dtype=torch.float32, device="cuda") for _, c in slab.partition_rows(n, world)]
+    dist.all_gather(gathered, mine)
+    if rank == 0:
+        full = Hypersonic3D(prm, device=local).init()
+        f0, _ = full.download()
+        full.upload(f0, (5e-3, 2e-3))
+        full.step(steps3)
+        ref3, _ = full.download()
+        got = torch.cat(gathered, dim=1).cpu().numpy()
+        same = all(np.array_equal(got[f], ref3[f]) for f in range(6)) and s3.clock() == full.clock()
+        moved = float(np.abs(ref3[0] - f0[0]).max())
+        print(f"hyp3d world={world}: z-slab ring == single-GPU: {same} (clock {s3.clock()}, max |d xi| {moved:.3g})")
+        ok &= same and moved > 0.1
+
     # ---- SPH: replicated state, work sharded by sorted-slot range, all-gather per sub-step ---------
     from fluid_sims_b200.sph import SPH, Params as SP, reset_particles
     sp = SP(N=200000, viscSub=2)

@@ -156,7 +156,7 @@ def build_all() -> str:
     TAU_B200_LIB=build/hostemu/libtau_b200_hostemu.so runs Python code written for the GPU library on the CPU
     (a pre-flight for tests/ -m gpu at sizes the emulator can afford; never shipped, never a default)."""
     os.makedirs(OUT, exist_ok=True)
-    names = ["burgers", "gray_scott", "hypersonic2d", "hypersonic3d", "shallow_water", "snapshot", "splat4", "sph"]
+    names = ["burgers", "gray_scott", "hypersonic2d", "hypersonic3d", "hypersonic_c", "shallow_water", "snapshot", "splat4", "sph"]
     so = os.path.join(OUT, "libtau_b200_hostemu.so")
     csrc = os.path.join(ROOT, "fluid_sims_b200", "csrc")
     deps = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".inc"))] + [

@@ -84,7 +84,8 @@ def test_cli_hosts_build_and_fail_loudly_without_gpu():
              "tau_sph": ["--n", "2048", "--frames", "2"],
              "tau_burgers": ["--nx", "96", "--ny", "64", "--steps", "4", "--headless", "--dtau", "1e-3"],
              "tau_sw": ["--nx", "96", "--ny", "64", "--steps", "4", "--headless", "--dtau", "1e-3"],
-             "th3cs": ["--n", "16", "--frames", "1", "--out", os.devnull]}
+             "th3cs": ["--n", "16", "--frames", "1", "--out", os.devnull],
+             "tau_hypersonic": ["--nx", "64", "--ny", "48", "--frames", "3", "--speed-mode"]}
     for exe, args in cases.items():
         r = subprocess.run([os.path.join(cli, exe)] + args, capture_output=True, text=True, timeout=120)
         if device_count() > 0:
@@ -98,6 +99,21 @@ def test_cli_hosts_build_and_fail_loudly_without_gpu():
     assert r.returncode == 1 and "Invalid --gamma" in r.stderr
     r = subprocess.run([os.path.join(cli, "tau_2d_hypersonic_cuda"), "--bogus"], capture_output=True, text=True)
     assert r.returncode == 1 and "Unknown or incomplete argument" in r.stderr
+
+
+def test_hypc_init_sim_is_host_code_and_equals_the_oracle():
+    """init_sim (tau_hypersonic.c:450-475) needs no device: the product's host routine against the oracle's,
+    incl. the golden mask / initial planes of the compiled reference at 256 x 256"""
+    import numpy as np
+    import oracle
+    from fluid_sims_b200.hypersonic_c import init_sim
+    for W, H in ((256, 256), (300, 300), (37, 91)):
+        planes, mask = init_sim(W, H)
+        op, om = oracle.hypcpu_init(W, H)
+        assert np.array_equal(mask.ravel(), om) and all(np.array_equal(a.ravel(), b) for a, b in zip(planes, op))
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hypcpu_ref_256x256.npz"))
+    planes, mask = init_sim(256, 256)
+    assert np.array_equal(mask.ravel(), g["mask"]) and np.array_equal(planes[3].ravel(), g["E0"])
 
 
 def test_snapshot_file_format_without_gpu(tmp_path):

@@ -692,3 +692,50 @@ def test_hyp2d_fused_kernel_equals_the_two_kernel_pair_mode(pretend_device, monk
     f1, _, _, _ = hyp2d_emu.run_slabs(200, 120, 3, "f32", 2, pair=1, frames=[(frame, 4)], geom_x0=66.0)
     f2, _, _, _ = hyp2d_emu.run_slabs(200, 120, 3, "f32", 2, pair=2, frames=[(frame, 4)], geom_x0=66.0)
     assert all(np.array_equal(x, y) for x, y in zip(f1, f2))
+
+
+# ---- tau_hypersonic.c's update path (hypersonic_c.cu, BASELINE config 1) -----------------------------------------
+@pytest.mark.parametrize("W,H,steps", [(64, 48, 40), (130, 33, 25)])
+def test_hypc_product_code_equals_oracle_bit_for_bit(W, H, steps):
+    """hypersonic_c.cu on the emulator (same -ffp-contract=off arithmetic as its --fmad=false device build): fields,
+    mask, sim_t and dt equal the oracle — which is pinned 0 ulp on the reference's own object code — and the speed-mode
+    render (sqrt only) equals the oracle's pixel for pixel."""
+    lib = C.CDLL(hostemu_build.build("hypersonic_c"))
+    f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+    h = C.c_void_p()
+    lib.tau_hypc_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.tau_hypc_upload.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.c_double]
+    lib.tau_hypc_step.argtypes = [C.c_void_p, C.c_int]
+    lib.tau_hypc_download.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
+    lib.tau_hypc_clock.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.tau_hypc_render.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+    lib.tau_hypc_destroy.argtypes = [C.c_void_p]
+    lib.tau_hostemu_last_error.restype = C.c_char_p
+    assert lib.tau_hypc_create(W, H, 0, None, C.byref(h)) == 0, lib.tau_hostemu_last_error()
+    planes, mask = oracle.hypcpu_init(W, H)
+    rng = np.random.default_rng(W)
+    mask = mask.reshape(H, W).copy()
+    mask[H // 4:H // 4 + 3, W // 2:W // 2 + 5] = 1           # a second body: slip-wall ghosts on flat faces
+    mask[H // 2, 0] = 1                                       # a body cell in the inflow column
+    mask = mask.ravel()
+    planes = [p * (1.0 + 0.05 * rng.random(p.size)) for p in planes]
+    for p in planes[1:3]:
+        p[mask == 1] = 0.0
+    ptrs = (C.c_void_p * 4)(*[p.ctypes.data for p in planes])
+    assert lib.tau_hypc_upload(h, ptrs, mask.ctypes.data, 0.25) == 0
+    assert lib.tau_hypc_step(h, steps) == 0
+    out = [np.empty(W * H, np.float64) for _ in range(4)]
+    m = np.empty(W * H, np.uint8)
+    assert lib.tau_hypc_download(h, (C.c_void_p * 4)(*[p.ctypes.data for p in out]), m.ctypes.data) == 0
+    t, dt = C.c_double(), C.c_double()
+    assert lib.tau_hypc_clock(h, C.byref(t), C.byref(dt)) == 0
+    exp, et, dts = oracle.hypcpu_run(W, H, planes, mask, steps, sim_t=0.25)
+    assert np.array_equal(m, mask) and t.value == et and dt.value == dts[-1]
+    for a, b in zip(out, exp):
+        assert np.array_equal(a, b)
+    px = np.empty(W * H, np.uint32)
+    mm = (C.c_double * 2)()
+    assert lib.tau_hypc_render(h, 2, px.ctypes.data, mm) == 0
+    ergba, emm, _ = oracle.hypcpu_render(W, H, exp, mask, 2)
+    assert (mm[0], mm[1]) == emm and np.array_equal(px.view(np.uint8).reshape(H, W, 4), ergba)
+    lib.tau_hypc_destroy(h)

@@ -15,10 +15,11 @@ Definitions
            the reference's frame loop — upload the 4 state planes from pinned host memory, run
            `steps_per_frame` solver steps (reference default 2, tau_hypersonic_cuda.cu:1407),
            download the 4 planes — all inside the timed region (wall clock, drained at the end).
-           At N=1 three frames are in flight (one handle per frame in flight, each on its own stream, tau_hyp2d_upload_async /
+           Three frames are in flight (one handle per frame in flight, each on its own stream, tau_hyp2d_upload_async /
            tau_hyp2d_download_async), so the H2D copy of one frame overlaps the D2H copy of the
-           other; at N>1 frames are synchronous (the ghost-row hand-over after an upload is a
-           host-driven NCCL exchange).
+           other; at N>1 every rank moves its own slab over its own PCIe link and the ghost-row hand-over after
+           an upload happens on the device (tau_hyp2d_upload_peers_async; `--e2e-handover host` = the
+           host-driven NCCL exchange of round 1, one frame at a time).
   roofline achieved = 33 algorithmic bytes/cell (read 4 fp32 fields + 1 mask byte, write 4 fields;
            SURVEY.md §8(d)) x W*H / average duration of one hyp2d_step launch (CUDA events over the
            timed region, in which it is the only kernel) vs the measured HBM copy bandwidth in
@@ -354,8 +355,9 @@ def run_product(a):
                 for h, _, _ in lanes:
                     h2.check(h2._sync(h._handle))
         elif a.e2e_peers_async and a.exchange == "peer":
-            # experimental (not yet run on hardware, NEXT.md): the frame hand-over between ranks on the device —
-            # no NCCL exchange, host synchronisation or barrier inside the frame loop; with --e2e-lanes > 1 every
+            # the frame hand-over between ranks on the device (validated at N = 2 in round 2: 4.06 ms per frame
+            # with three lanes against 6.19 ms host-driven) — no NCCL exchange, host synchronisation or barrier
+            # inside the frame loop; with --e2e-lanes > 1 every
             # rank runs that many slab handles (each with its own peer attachments) on their own streams, so the
             # upload of frame i+1 overlaps the download of frame i
             lanes = [(sim, out_ptrs, host_out)]
@@ -565,8 +567,11 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU halo exchange: device-side peer pushes over NVLink (default) or "
                          "host-driven NCCL send/recv + all-reduce every step")
-    ap.add_argument("--e2e-peers-async", action="store_true",
-                    help="N>1, --exchange peer: device-side frame hand-over (experimental, default off)")
+    ap.add_argument("--e2e-handover", default="device", choices=["device", "host"],
+                    help="N>1, --exchange peer: hand the uploaded frame over to the neighbours on the device "
+                         "(tau_hyp2d_upload_peers_async: no NCCL, host synchronisation or barrier in the frame loop; default) "
+                         "or with the host-driven NCCL exchange of round 1")
+    ap.add_argument("--e2e-peers-async", action="store_true", help="(round-1 spelling of --e2e-handover device)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the fp64-handle and reference-kernel sub-records (N=1)")
@@ -577,6 +582,7 @@ def main():
     ap.add_argument("--steps-f64", type=int, default=40)
     ap.add_argument("--steps-ref-gpu", type=int, default=20)
     a = ap.parse_args()
+    a.e2e_peers_async = a.e2e_peers_async or a.e2e_handover == "device"
     if a.warmup < 3 and a.impl == "b200":
         a.warmup = 3
     if a.impl == "reference":

@@ -7,7 +7,9 @@
  * pass of the frame loop :1892-1926 written as a binary PPM instead of a raylib texture; MODE as
  * the reference's M key cycles it, 0..6); --write-baseline / --verify-baseline FILE (the regression
  * snapshot of tau_hypersonic_cuda_tests.cu:84-176, same file format and tolerances);
- * --checkpoint FILE / --resume FILE (raw SoA state, bit-identical resume). */
+ * --checkpoint FILE / --resume FILE (raw SoA state, bit-identical resume);
+ * --gpus N (additive): the grid is split into N y-slabs, one per device of this box, all driven from this
+ * one process through tau_hyp2d_group_* — results are bit-identical to --gpus 1. */
 #include <errno.h>
 #include <limits.h>
 #include <math.h>
@@ -23,7 +25,7 @@ static void usage(const char *a0) {
           "          [--tile-bx BX] [--tile-by BY]\n"
           "          [--nx W] [--ny H] [--frames N] [--dtype f32|f64] [--dump FILE]\n"
           "          [--view MODE] [--ppm FILE] [--write-baseline FILE | --verify-baseline FILE]\n"
-          "          [--checkpoint FILE] [--resume FILE]\n",
+          "          [--checkpoint FILE] [--resume FILE] [--gpus N]\n",
           a0);
 }
 static int parse_d(const char *name, const char *v, double *out) { /* parse_double_flag :1462 */
@@ -51,7 +53,7 @@ static int parse_i(const char *name, const char *v, int *out) { /* parse_int_fla
 int main(int argc, char **argv) {
   int W = 8192, H = 1024, frames = 100, dtype = TAU_F64, tile_bx = -1, tile_by = -1;
   const char *dump = NULL, *ppm = NULL, *wbase = NULL, *vbase = NULL, *ckpt = NULL, *resume = NULL;
-  int view = 0;
+  int view = 0, gpus = 1;
   /* first pass: grid size, because default_config derives the geometry from H (:1401-1405) */
   for (int i = 1; i + 1 < argc; i++) {
     if (!strcmp(argv[i], "--nx") && !parse_i("--nx", argv[i + 1], &W)) return 1;
@@ -82,6 +84,7 @@ int main(int argc, char **argv) {
     if (!strcmp(a, "--verify-baseline") && has) { vbase = argv[++i]; continue; }
     if (!strcmp(a, "--checkpoint") && has) { ckpt = argv[++i]; continue; }
     if (!strcmp(a, "--resume") && has) { resume = argv[++i]; continue; }
+    if (!strcmp(a, "--gpus") && has) { if (!parse_i(a, argv[++i], &gpus)) return 1; continue; }
     fprintf(stderr, "Unknown or incomplete argument: %s\n", a);
     usage(argv[0]);
     return 1;
@@ -96,6 +99,57 @@ int main(int argc, char **argv) {
          "  geom_x0=%.8g geom_cy=%.8g geom_Rb=%.8g geom_Rn=%.8g geom_theta=%.8g\n",
          c.gamma, c.cfl, c.visc_nu, c.visc_rho, c.visc_e, c.inflow_mach, c.steps_per_frame, c.geom_x0,
          c.geom_cy, c.geom_Rb, c.geom_Rn, c.geom_theta); /* print_config :1687-1709 */
+  if (gpus != 1) { /* y-slabs over several devices of this box, one process (tau_hyp2d_group_*) */
+    if (wbase || vbase || ckpt || resume) {
+      fprintf(stderr, "--gpus %d: baselines and checkpoints are per-handle operations (run with --gpus 1)\n", gpus);
+      return 1;
+    }
+    tau_hyp2d_group *g;
+    TAU_OR_DIE(tau_hyp2d_group_create(&c, W, H, dtype, gpus, NULL, &g));
+    TAU_OR_DIE(tau_hyp2d_group_init(g));
+    printf("LaunchConfig:\n  grid=%dx%d dtype=%s y-slabs over %d GPUs:", W, H, dtype ? "f64" : "f32", gpus);
+    for (int i = 0; i < gpus; ++i) {
+      int y0, hl;
+      TAU_OR_DIE(tau_hyp2d_group_member(g, i, NULL, &y0, &hl));
+      printf(" [%d,%d)", y0, y0 + hl);
+    }
+    printf("\n");
+    const double t0 = cli_now();
+    double sim_t = 0, dt = 0;
+    for (int f = 0; f < frames; f++) {
+      TAU_OR_DIE(tau_hyp2d_group_step(g, c.steps_per_frame));
+      if ((f + 1) % 50 == 0 || f + 1 == frames) {
+        TAU_OR_DIE(tau_hyp2d_group_clock(g, &sim_t, &dt));
+        printf("frame %d  t = %.6f  dt = %.3e\n", f + 1, sim_t, dt);
+      }
+    }
+    TAU_OR_DIE(tau_hyp2d_group_sync(g));
+    const double secs = cli_now() - t0;
+    const double steps = (double)frames * c.steps_per_frame;
+    printf("%.0f steps in %.3f s: %.1f Mcell-updates/s\n", steps, secs, steps * W * H / secs / 1e6);
+    if (dump) {
+      const size_t n = (size_t)W * H, es = dtype ? 8 : 4;
+      void *planes[4];
+      for (int p = 0; p < 4; ++p) planes[p] = malloc(n * es);
+      TAU_OR_DIE(tau_hyp2d_group_download(g, planes, NULL));
+      cli_dump(dump, 4, (int)es, W, H, 1, (long long)steps, sim_t, planes);
+      for (int p = 0; p < 4; ++p) free(planes[p]);
+    }
+    if (ppm) {
+      uint32_t *px = (uint32_t *)malloc((size_t)W * H * 4);
+      double mm[2];
+      TAU_OR_DIE(tau_hyp2d_group_render(g, view, px, mm));
+      FILE *f = fopen(ppm, "wb");
+      if (!f) { fprintf(stderr, "cannot open %s for writing\n", ppm); return 1; }
+      fprintf(f, "P6\n%d %d\n255\n", W, H);
+      for (size_t i = 0; i < (size_t)W * H; ++i) fwrite(&px[i], 1, 3, f);
+      fclose(f);
+      free(px);
+      printf("view %d: value range [%.6g, %.6g] -> %s\n", view, mm[0], mm[1], ppm);
+    }
+    TAU_OR_DIE(tau_hyp2d_group_destroy(g));
+    return 0;
+  }
   tau_hyp2d *sim;
   TAU_OR_DIE(tau_hyp2d_create(&c, W, H, dtype, 0, 0, H, NULL, &sim));
   if (tile_by > 0) TAU_OR_DIE(tau_hyp2d_set_seg_rows(sim, tile_by < 4 ? 4 : tile_by));

@@ -788,6 +788,7 @@ struct tau_hyp2d {
   uint2 *items_pair, *items_rest;   // interior body-free 60-column items / everything else (30-column)
   int nitems_pair, nitems_rest, grid_pair, grid_rest;
   unsigned int *pair_ctr;           // 3 rotating claim counters of the pair kernel
+  bool peers_local;                 // peers are handles of THIS process (tau_hyp2d_group): plain pointers, no IPC mappings
   uchar4 *pixels;             // render target (device), allocated on first use
   unsigned long long *mmkeys; // render min/max keys (device)
 };
@@ -1298,6 +1299,7 @@ int tau_hyp2d_create(const tau_hyp2d_config *cfg, int W, int H, int dtype, int d
   memset(&h->pctrl, 0, sizeof(h->pctrl));
   h->pctrl.world = 1;
   h->peers_attached = false;
+  h->peers_local = false;
   h->pair_mode = false;
   h->items_pair = h->items_rest = nullptr;
   h->nitems_pair = h->nitems_rest = 0;
@@ -1609,14 +1611,17 @@ int tau_hyp2d_ipc_detach(tau_hyp2d *h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   for (int b = 0; b < 2; ++b) {
-    if (h->peer_up[b]) cudaIpcCloseMemHandle(h->peer_up[b]);
-    if (h->peer_dn[b]) cudaIpcCloseMemHandle(h->peer_dn[b]);
+    if (!h->peers_local) {
+      if (h->peer_up[b]) cudaIpcCloseMemHandle(h->peer_up[b]);
+      if (h->peer_dn[b]) cudaIpcCloseMemHandle(h->peer_dn[b]);
+    }
     h->peer_up[b] = h->peer_dn[b] = nullptr;
   }
   for (int p = 0; p < h->pctrl.world; ++p) {
-    if (p != h->pctrl.rank && h->pctrl.ctrl[p]) cudaIpcCloseMemHandle(h->pctrl.ctrl[p]);
+    if (!h->peers_local && p != h->pctrl.rank && h->pctrl.ctrl[p]) cudaIpcCloseMemHandle(h->pctrl.ctrl[p]);
     h->pctrl.ctrl[p] = nullptr;
   }
+  h->peers_local = false;
   h->pctrl.world = 1;
   h->peers_attached = false;
   return TAU_OK;
@@ -1828,6 +1833,257 @@ int tau_hyp2d_destroy(tau_hyp2d *h) {
   cudaEventDestroy(h->ev0);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
+  return TAU_OK;
+}
+
+
+// ---- multi-GPU behind the C boundary: ONE process, one slab handle per device ---------------------------------
+// tau_<solver>_create(cfg, dims, ngpus, &handle).  The slab handles are the ones torchrun's ranks
+// use (y-slabs, chain, 2 ghost rows); here their peers live in the same process, so the neighbours' planes and
+// every rank's control block are plain device pointers made reachable with cudaDeviceEnablePeerAccess instead of
+// CUDA-IPC mappings.  Everything per step stays on the devices (boundary rows pushed over NVLink by the step
+// kernel, one release store per peer as all-reduce(max) + barrier); the host only enqueues.  The hand-over after
+// init / upload (ghost rows, mask ghost rows, max wavespeed) is cudaMemcpyPeer + a host max: no NCCL needed.
+struct tau_hyp2d_group {
+  int n, W, H, dtype;
+  tau_hyp2d *h[8];
+  int dev[8], y0[8], hl[8];
+  int chunk;  // steps enqueued per device before moving on to the next one
+};
+
+namespace {
+
+int group_sync_state(tau_hyp2d_group *g, bool with_mask) {
+  if (g->n == 1) return TAU_OK;
+  const int es = g->dtype ? 8 : 4;
+  const size_t rowb = (size_t)g->W * es, ghostb = H2_GHOST * rowb;
+  for (int i = 0; i < g->n; ++i) TAU_CUDA(cudaStreamSynchronize(g->h[i]->stream));
+  for (int i = 0; i + 1 < g->n; ++i) {
+    tau_hyp2d *a = g->h[i], *b = g->h[i + 1];  // a above b
+    for (int f = 0; f < 4; ++f) {
+      char *pa = (char *)a->U[a->cur] + (size_t)f * a->plane_elems * es, *pb = (char *)b->U[b->cur] + (size_t)f * b->plane_elems * es;
+      // a's last two owned rows -> b's upper ghost rows; b's first two owned rows -> a's lower ghost rows
+      TAU_CUDA(cudaMemcpyPeerAsync(pb, b->device, pa + (size_t)a->h_local * rowb, a->device, ghostb, a->stream));
+      TAU_CUDA(cudaMemcpyPeerAsync(pa + (size_t)(a->h_local + H2_GHOST) * rowb, a->device, pb + ghostb, b->device, ghostb, b->stream));
+    }
+    if (with_mask) {
+      const size_t mrow = (size_t)g->W;
+      TAU_CUDA(cudaMemcpyPeerAsync(b->mask, b->device, a->mask + (size_t)a->h_local * mrow, a->device, H2_GHOST * mrow, a->stream));
+      TAU_CUDA(cudaMemcpyPeerAsync(a->mask + (size_t)(a->h_local + H2_GHOST) * mrow, a->device, b->mask + H2_GHOST * mrow, b->device,
+                                   H2_GHOST * mrow, b->stream));
+    }
+  }
+  // all-reduce(max) of the wavespeed slot the next step reads (exact: max is associative)
+  double m = 0.0;
+  for (int i = 0; i < g->n; ++i) {
+    tau_hyp2d *h = g->h[i];
+    TAU_CUDA(cudaSetDevice(h->device));
+    TAU_CUDA(cudaStreamSynchronize(h->stream));
+    double v = 0.0;
+    TAU_CUDA(cudaMemcpy(&v, &h->ctrl->maxspeed[ctl_slot(h)], sizeof(double), cudaMemcpyDeviceToHost));
+    if (v > m) m = v;
+  }
+  for (int i = 0; i < g->n; ++i) {
+    tau_hyp2d *h = g->h[i];
+    TAU_CUDA(cudaSetDevice(h->device));
+    TAU_CUDA(cudaMemcpy(&h->ctrl->maxspeed[ctl_slot(h)], &m, sizeof(double), cudaMemcpyHostToDevice));
+    if (with_mask) h->items_dirty = true;  // the ghost rows of the mask decide which items take the masked march
+    const int rc = tau_hyp2d_peers_ready(h);
+    if (rc) return rc;
+  }
+  return TAU_OK;
+}
+
+}  // namespace
+
+int tau_hyp2d_group_create(const tau_hyp2d_config *cfg, int W, int H, int dtype, int ngpus, const int *devices,
+                           tau_hyp2d_group **out) {
+  TAU_REQUIRE(cfg && out, "tau_hyp2d_group_create: null argument");
+  TAU_REQUIRE(ngpus >= 1 && ngpus <= 8, "tau_hyp2d_group_create: ngpus must be in [1, 8] (got %d)", ngpus);
+  TAU_REQUIRE(H >= ngpus * 2 * H2_GHOST, "tau_hyp2d_group_create: %d rows cannot be split over %d GPUs", H, ngpus);
+  const int have = tau_device_count();
+  if (have <= 0) {
+    tau_set_error("tau_hyp2d_group_create: no CUDA device (this library has no CPU fallback)");
+    return TAU_ERR_NODEV;
+  }
+  TAU_REQUIRE(have >= ngpus, "tau_hyp2d_group_create: %d GPUs requested, %d visible", ngpus, have);
+  tau_hyp2d_group *g = new (std::nothrow) tau_hyp2d_group();
+  if (!g) return TAU_ERR_NOMEM;
+  memset(g, 0, sizeof(*g));
+  g->n = ngpus; g->W = W; g->H = H; g->dtype = dtype;
+  g->chunk = 16;
+  if (const char *e = getenv("TAU_HYP2D_GROUP_CHUNK")) {
+    const int v = atoi(e);
+    if (v >= 1) g->chunk = v;
+  }
+  const int base = H / ngpus, rem = H % ngpus;  // balanced contiguous partition, earlier slabs take the remainder
+  int y = 0, rc = TAU_OK;
+  for (int i = 0; i < ngpus && !rc; ++i) {
+    g->dev[i] = devices ? devices[i] : i;
+    g->y0[i] = y;
+    g->hl[i] = base + (i < rem ? 1 : 0);
+    y += g->hl[i];
+    rc = tau_hyp2d_create(cfg, W, H, dtype, g->dev[i], g->y0[i], g->hl[i], nullptr, &g->h[i]);
+  }
+  if (!rc && ngpus > 1) {
+    for (int i = 0; i < ngpus && !rc; ++i) {
+      if (cudaSetDevice(g->dev[i]) != cudaSuccess) rc = TAU_ERR_CUDA;
+      for (int j = 0; j < ngpus && !rc; ++j) {
+        if (j == i) continue;
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, g->dev[i], g->dev[j]);
+        if (!can) {
+          tau_set_error("tau_hyp2d_group_create: device %d cannot access device %d (no NVLink/P2P path)", g->dev[i], g->dev[j]);
+          rc = TAU_ERR_CUDA;
+          break;
+        }
+        const cudaError_t e = cudaDeviceEnablePeerAccess(g->dev[j], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+          tau_set_error("cudaDeviceEnablePeerAccess(%d -> %d): %s", g->dev[i], g->dev[j], cudaGetErrorString(e));
+          rc = TAU_ERR_CUDA;
+        }
+        cudaGetLastError();
+      }
+    }
+    for (int i = 0; i < ngpus && !rc; ++i) {  // what tau_hyp2d_ipc_attach does, with in-process pointers
+      tau_hyp2d *h = g->h[i];
+      h->pctrl.world = ngpus;
+      h->pctrl.rank = i;
+      for (int p = 0; p < ngpus; ++p) h->pctrl.ctrl[p] = g->h[p]->ctrl;
+      if (i > 0) {
+        for (int b = 0; b < 2; ++b) h->peer_up[b] = g->h[i - 1]->U[b];
+        h->peer_up_hl = g->hl[i - 1];
+      }
+      if (i < ngpus - 1) {
+        for (int b = 0; b < 2; ++b) h->peer_dn[b] = g->h[i + 1]->U[b];
+        h->peer_dn_hl = g->hl[i + 1];
+      }
+      h->peers_attached = true;
+      h->peers_local = true;
+    }
+  }
+  if (rc) {
+    for (int i = 0; i < ngpus; ++i)
+      if (g->h[i]) {
+        g->h[i]->peers_attached = false;
+        tau_hyp2d_destroy(g->h[i]);
+      }
+    delete g;
+    return rc;
+  }
+  *out = g;
+  return TAU_OK;
+}
+
+int tau_hyp2d_group_size(tau_hyp2d_group *g) { return g ? g->n : -1; }
+int tau_hyp2d_group_member(tau_hyp2d_group *g, int i, tau_hyp2d **h, int *y_begin, int *h_local) {
+  TAU_REQUIRE(g && i >= 0 && i < g->n, "tau_hyp2d_group_member: bad argument");
+  if (h) *h = g->h[i];
+  if (y_begin) *y_begin = g->y0[i];
+  if (h_local) *h_local = g->hl[i];
+  return TAU_OK;
+}
+
+int tau_hyp2d_group_init(tau_hyp2d_group *g) {  // k_init on every slab, then the hand-over
+  TAU_REQUIRE(g, "tau_hyp2d_group_init: null handle");
+  for (int i = 0; i < g->n; ++i) {
+    const int rc = tau_hyp2d_init(g->h[i]);
+    if (rc) return rc;
+  }
+  return group_sync_state(g, true);
+}
+
+// planes / mask cover the WHOLE grid (H x W, reference layout); every device receives its rows
+int tau_hyp2d_group_upload(tau_hyp2d_group *g, const void *const planes[4], const uint8_t *mask) {
+  TAU_REQUIRE(g && planes, "tau_hyp2d_group_upload: null argument");
+  const int es = g->dtype ? 8 : 4;
+  for (int i = 0; i < g->n; ++i) {
+    const void *pl[4];
+    for (int f = 0; f < 4; ++f) {
+      TAU_REQUIRE(planes[f], "tau_hyp2d_group_upload: null plane %d", f);
+      pl[f] = (const char *)planes[f] + (size_t)g->y0[i] * g->W * es;
+    }
+    const int rc = tau_hyp2d_upload(g->h[i], pl, mask ? mask + (size_t)g->y0[i] * g->W : nullptr);
+    if (rc) return rc;
+  }
+  return group_sync_state(g, mask != nullptr);
+}
+
+// THE hot path on ngpus devices: one step kernel per device per step, nothing else; no host synchronisation.
+int tau_hyp2d_group_step(tau_hyp2d_group *g, int nsteps) {
+  TAU_REQUIRE(g && nsteps >= 0, "tau_hyp2d_group_step: bad argument");
+  for (int done = 0; done < nsteps; done += g->chunk) {
+    const int k = nsteps - done < g->chunk ? nsteps - done : g->chunk;
+    for (int i = 0; i < g->n; ++i) {
+      const int rc = tau_hyp2d_step(g->h[i], k);
+      if (rc) return rc;
+    }
+  }
+  return TAU_OK;
+}
+
+int tau_hyp2d_group_sync(tau_hyp2d_group *g) {
+  TAU_REQUIRE(g, "tau_hyp2d_group_sync: null handle");
+  for (int i = 0; i < g->n; ++i) {
+    const int rc = tau_hyp2d_sync(g->h[i]);
+    if (rc) return rc;
+  }
+  return TAU_OK;
+}
+
+int tau_hyp2d_group_clock(tau_hyp2d_group *g, double *sim_t, double *dt_last) {
+  TAU_REQUIRE(g, "tau_hyp2d_group_clock: null handle");
+  return tau_hyp2d_clock(g->h[0], sim_t, dt_last);  // every slab carries the same clock (same dt sequence)
+}
+
+int tau_hyp2d_group_download(tau_hyp2d_group *g, void *const planes[4], uint8_t *mask) {
+  TAU_REQUIRE(g && planes, "tau_hyp2d_group_download: null argument");
+  const int es = g->dtype ? 8 : 4;
+  for (int i = 0; i < g->n; ++i) {
+    void *pl[4];
+    for (int f = 0; f < 4; ++f) pl[f] = planes[f] ? (char *)planes[f] + (size_t)g->y0[i] * g->W * es : nullptr;
+    for (int f = 0; f < 4; ++f) TAU_REQUIRE(pl[f], "tau_hyp2d_group_download: null plane %d", f);
+    const int rc = tau_hyp2d_download(g->h[i], pl, mask ? mask + (size_t)g->y0[i] * g->W : nullptr);
+    if (rc) return rc;
+  }
+  return TAU_OK;
+}
+
+// render pass over the whole grid: per-slab min/max, host fold, per-slab pixels with the global range
+int tau_hyp2d_group_render(tau_hyp2d_group *g, int view_mode, uint32_t *rgba, double minmax_out[2]) {
+  TAU_REQUIRE(g && rgba, "tau_hyp2d_group_render: null argument");
+  double mm[2] = {1e300, -1e300};
+  for (int i = 0; i < g->n; ++i) {
+    double m[2];
+    const int rc = tau_hyp2d_render_minmax(g->h[i], view_mode, m);
+    if (rc) return rc;
+    if (m[0] < mm[0]) mm[0] = m[0];
+    if (m[1] > mm[1]) mm[1] = m[1];
+  }
+  for (int i = 0; i < g->n; ++i) {
+    const int rc = tau_hyp2d_render_pixels(g->h[i], view_mode, mm, rgba + (size_t)g->y0[i] * g->W);
+    if (rc) return rc;
+  }
+  if (minmax_out) {
+    minmax_out[0] = mm[0];
+    minmax_out[1] = mm[1];
+  }
+  return TAU_OK;
+}
+
+long long tau_hyp2d_group_launch_count(tau_hyp2d_group *g) {
+  if (!g) return -1;
+  long long n = 0;
+  for (int i = 0; i < g->n; ++i) n += g->h[i]->launches;
+  return n;
+}
+
+int tau_hyp2d_group_destroy(tau_hyp2d_group *g) {
+  if (!g) return TAU_OK;
+  for (int i = 0; i < g->n; ++i) tau_hyp2d_sync(g->h[i]);
+  for (int i = 0; i < g->n; ++i) tau_hyp2d_ipc_detach(g->h[i]);  // forget the peers' pointers before anything is freed
+  for (int i = g->n - 1; i >= 0; --i) tau_hyp2d_destroy(g->h[i]);
+  delete g;
   return TAU_OK;
 }
 

@@ -306,3 +306,95 @@ class Hypersonic2D:
             self.close()
         except Exception:
             pass
+
+
+# ---- several GPUs of one box from ONE process (tau_hyp2d_group_*, include/tau_b200.h) ---------------------------
+_g = C.c_void_p
+_g_create = declare("tau_hyp2d_group_create", [C.POINTER(_CConfig), C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.POINTER(C.c_int), C.POINTER(_g)])
+_g_size = declare("tau_hyp2d_group_size", [_g])
+_g_member = declare("tau_hyp2d_group_member", [_g, C.c_int, C.POINTER(_h), C.POINTER(C.c_int), C.POINTER(C.c_int)])
+_g_init = declare("tau_hyp2d_group_init", [_g])
+_g_upload = declare("tau_hyp2d_group_upload", [_g, C.POINTER(C.c_void_p), C.c_void_p])
+_g_step = declare("tau_hyp2d_group_step", [_g, C.c_int])
+_g_sync = declare("tau_hyp2d_group_sync", [_g])
+_g_clock = declare("tau_hyp2d_group_clock", [_g, C.POINTER(C.c_double), C.POINTER(C.c_double)])
+_g_download = declare("tau_hyp2d_group_download", [_g, C.POINTER(C.c_void_p), C.c_void_p])
+_g_render = declare("tau_hyp2d_group_render", [_g, C.c_int, C.c_void_p, C.POINTER(C.c_double)])
+_g_launches = declare("tau_hyp2d_group_launch_count", [_g], C.c_longlong)
+_g_destroy = declare("tau_hyp2d_group_destroy", [_g])
+
+
+class Hypersonic2DGroup:
+    """The 2-D solver y-slab decomposed over `ngpus` devices of one box, driven from this one process
+    (no torchrun, no NCCL): same calls as Hypersonic2D, planes cover the whole grid."""
+
+    def __init__(self, cfg: SimConfig, ngpus: int, dtype: str = "f32", devices=None):
+        if dtype not in _NP:
+            raise ValueError("dtype must be 'f32' or 'f64'")
+        self.cfg, self.dtype, self.np_dtype, self.ngpus = cfg, dtype, _NP[dtype], ngpus
+        self._handle = _g()
+        cc = cfg._c()
+        dv = (C.c_int * ngpus)(*devices) if devices is not None else None
+        check(_g_create(C.byref(cc), cfg.W, cfg.H, 0 if dtype == "f32" else 1, ngpus, dv, C.byref(self._handle)))
+
+    def slabs(self):
+        """[(y_begin, h_local)] of the member handles."""
+        out = []
+        for i in range(int(_g_size(self._handle))):
+            y0, hl = C.c_int(), C.c_int()
+            check(_g_member(self._handle, i, None, C.byref(y0), C.byref(hl)))
+            out.append((y0.value, hl.value))
+        return out
+
+    def init(self):
+        check(_g_init(self._handle))
+        return self
+
+    def upload(self, planes, mask=None):
+        arrs = [np.ascontiguousarray(p, self.np_dtype).reshape(self.cfg.H, self.cfg.W) for p in planes]
+        ptrs = (C.c_void_p * 4)(*[a.ctypes.data for a in arrs])
+        m = None if mask is None else np.ascontiguousarray(mask, np.uint8).reshape(self.cfg.H, self.cfg.W)
+        check(_g_upload(self._handle, ptrs, C.c_void_p(m.ctypes.data if m is not None else 0)))
+        return self
+
+    def step(self, nsteps: int = 1):
+        check(_g_step(self._handle, nsteps))
+        return self
+
+    def sync(self):
+        check(_g_sync(self._handle))
+
+    def clock(self):
+        t, dt = C.c_double(), C.c_double()
+        check(_g_clock(self._handle, C.byref(t), C.byref(dt)))
+        return float(t.value), float(dt.value)
+
+    def download(self):
+        arrs = [np.empty((self.cfg.H, self.cfg.W), self.np_dtype) for _ in range(4)]
+        mask = np.empty((self.cfg.H, self.cfg.W), np.uint8)
+        ptrs = (C.c_void_p * 4)(*[a.ctypes.data for a in arrs])
+        check(_g_download(self._handle, ptrs, C.c_void_p(mask.ctypes.data)))
+        return arrs, mask
+
+    def render(self, view_mode=0):
+        mode = VIEW_MODES.index(view_mode) if isinstance(view_mode, str) else int(view_mode)
+        px = np.empty((self.cfg.H, self.cfg.W, 4), np.uint8)
+        mm = (C.c_double * 2)()
+        check(_g_render(self._handle, mode, C.c_void_p(px.ctypes.data), mm))
+        return px, (float(mm[0]), float(mm[1]))
+
+    @property
+    def launch_count(self) -> int:
+        return int(_g_launches(self._handle))
+
+    def close(self):
+        if self._handle:
+            check(_g_destroy(self._handle))
+            self._handle = _g()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -401,6 +401,32 @@ int tau_sw_last_step_ms(tau_sw *h, float *ms);
 int tau_sw_destroy(tau_sw *h);
 
 /* ---------------------------------------------------------------------------------------------
+ * 2-D hypersonic on several GPUs of one box from ONE process ("create(cfg, dims, ngpus)")
+ * Replaces the same step loop (tau_hypersonic_cuda.cu:1833-1889) and allocation block (:1748-1819) as
+ * tau_hyp2d_*, y-slab decomposed (chain, 2 ghost rows): one slab handle per device, peers
+ * reached through cudaDeviceEnablePeerAccess.  Per step every device runs ONE kernel that also pushes
+ * its boundary rows into the neighbours' ghost rows over NVLink and sends its max wavespeed to every
+ * peer with one release store (all-reduce(max) + step barrier); the host only enqueues.  Results are
+ * bit-identical to the single-GPU handle.  planes / mask / rgba cover the whole H x W grid.
+ * devices == NULL: devices 0 .. ngpus-1.  ngpus == 1 is allowed (one full-domain handle).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct tau_hyp2d_group tau_hyp2d_group;
+int tau_hyp2d_group_create(const tau_hyp2d_config *cfg, int W, int H, int dtype, int ngpus, const int *devices,
+                           tau_hyp2d_group **out);
+int tau_hyp2d_group_size(tau_hyp2d_group *g);
+/* the i-th slab handle and its rows [y_begin, y_begin + h_local) — for per-slab calls (snapshot, timing) */
+int tau_hyp2d_group_member(tau_hyp2d_group *g, int i, tau_hyp2d **h, int *y_begin, int *h_local);
+int tau_hyp2d_group_init(tau_hyp2d_group *g);
+int tau_hyp2d_group_upload(tau_hyp2d_group *g, const void *const planes[4], const uint8_t *mask);
+int tau_hyp2d_group_step(tau_hyp2d_group *g, int nsteps);
+int tau_hyp2d_group_sync(tau_hyp2d_group *g);
+int tau_hyp2d_group_clock(tau_hyp2d_group *g, double *sim_t, double *dt_last);
+int tau_hyp2d_group_download(tau_hyp2d_group *g, void *const planes[4], uint8_t *mask);
+int tau_hyp2d_group_render(tau_hyp2d_group *g, int view_mode, uint32_t *rgba, double minmax_out[2]);
+long long tau_hyp2d_group_launch_count(tau_hyp2d_group *g);
+int tau_hyp2d_group_destroy(tau_hyp2d_group *g);
+
+/* ---------------------------------------------------------------------------------------------
  * tau_hypersonic (CPU reference solver, tau_hypersonic.c — BASELINE config 1: 256 x 256, "speed mode")
  * Replaces: `static void step_physics(void)` (tau_hypersonic.c:500-674) on the file-static
  * `Cons U[W*H]`, `mask[]`, `sim_t` (:38-43), `init_sim` (:450-475) and the render loops of main()

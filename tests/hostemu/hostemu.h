@@ -329,7 +329,7 @@ template <class T> static inline T atomicCAS(T *a, T c, T v) { T o = *a; if (o =
 
 // ---- the slice of the CUDA runtime API the host functions use; "device memory" is host memory ----
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorPeerAccessAlreadyEnabled = 704 };
 typedef struct tau_hc_stream *cudaStream_t;
 typedef struct tau_hc_event *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
@@ -403,13 +403,17 @@ struct cudaDeviceProp {
   size_t sharedMemPerBlock, sharedMemPerBlockOptin, totalGlobalMem;
 };
 static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 static inline int tau_hc_env_int(const char *name, int dflt) {
   const char *e = getenv(name);
   return e && *e ? atoi(e) : dflt;
 }
+// pretend devices of one process (tau_hyp2d_group): all share the host's memory, "peer access" is a no-op
+static inline cudaError_t cudaGetDeviceCount(int *n) { *n = tau_hc_env_int("TAU_HC_DEVICES", 1); return cudaSuccess; }
+static inline cudaError_t cudaDeviceCanAccessPeer(int *can, int, int) { *can = 1; return cudaSuccess; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaMemcpyPeerAsync(void *d, int, const void *s, int, size_t n, cudaStream_t) { memmove(d, s, n); return cudaSuccess; }
 // a small pretend device keeps persistent grids small: TAU_HC_SMS "SMs" x TAU_HC_CTAS_PER_SM resident CTAs
 static inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) { *v = tau_hc_env_int("TAU_HC_SMS", 3); return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) {
@@ -563,7 +567,7 @@ extern "C" TAU_HC_WEAK const char *tau_hostemu_last_error(void) { return tau_hc_
 extern "C" TAU_HC_WEAK const char *tau_last_error(void) { return tau_hc_err; }
 extern "C" TAU_HC_WEAK int tau_abi_version(void) { return 1; }
 extern "C" TAU_HC_WEAK long long tau_hostemu_launches(void) { return tau_hc::launches; }
-extern "C" TAU_HC_WEAK int tau_device_count(void) { return 1; }
+extern "C" TAU_HC_WEAK int tau_device_count(void) { return tau_hc_env_int("TAU_HC_DEVICES", 1); }
 #define TAU_CUDA(expr)                                                   \
   do {                                                                   \
     cudaError_t _e = (expr);                                             \

@@ -739,3 +739,67 @@ def test_hypc_product_code_equals_oracle_bit_for_bit(W, H, steps):
     ergba, emm, _ = oracle.hypcpu_render(W, H, exp, mask, 2)
     assert (mm[0], mm[1]) == emm and np.array_equal(px.view(np.uint8).reshape(H, W, 4), ergba)
     lib.tau_hypc_destroy(h)
+
+
+# ---- tau_hyp2d_group: the slab handles of one process (multi-GPU behind the C boundary) --------------------------
+@pytest.mark.parametrize("ngpus,dtype", [(2, "f64"), (3, "f32"), (4, "f32")])
+def test_hyp2d_group_equals_single_domain(pretend_device, monkeypatch, ngpus, dtype):
+    """tau_hyp2d_group_* (ONE process, one slab handle per pretend device, peers as plain pointers, hand-over by
+    cudaMemcpyPeer + host max) reproduces the single-domain handle bit for bit — init and uploaded states with a
+    body crossing slab boundaries, chunked stepping, download and the render pass over the whole grid."""
+    from hyp2d_emu import default_cfg, lib as h2lib
+    pretend_device(3, 2)
+    monkeypatch.setenv("TAU_HC_DEVICES", str(ngpus))
+    monkeypatch.setenv("TAU_HYP2D_GROUP_CHUNK", "1")     # emulated kernels run at launch: ranks must alternate
+    monkeypatch.delenv("TAU_HYP2D_PAIR", raising=False)
+    L = h2lib()
+    g, h = C.c_void_p(), C.c_void_p()
+    L.tau_hyp2d_group_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    for fn in ("init", "sync", "destroy"):
+        getattr(L, f"tau_hyp2d_group_{fn}").argtypes = [C.c_void_p]
+    L.tau_hyp2d_group_step.argtypes = [C.c_void_p, C.c_int]
+    L.tau_hyp2d_group_upload.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
+    L.tau_hyp2d_group_download.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
+    L.tau_hyp2d_group_clock.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.tau_hyp2d_group_render.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+    L.tau_hyp2d_render.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(C.c_double)]
+    W, H, steps = 200, 120, 9
+    npdt = np.float32 if dtype == "f32" else np.float64
+    cc = default_cfg(W, H, geom_x0=W / 3.0)
+    dt = 0 if dtype == "f32" else 1
+
+    def state(handle_download, handle, n):
+        out = [np.empty((H, W), npdt) for _ in range(4)]
+        m = np.empty((H, W), np.uint8)
+        assert handle_download(handle, (C.c_void_p * 4)(*[a.ctypes.data for a in out]), m.ctypes.data) == 0
+        return out, m
+
+    assert L.tau_hyp2d_group_create(C.byref(cc), W, H, dt, ngpus, None, C.byref(g)) == 0, L.tau_hostemu_last_error()
+    assert L.tau_hyp2d_create(C.byref(cc), W, H, dt, 0, 0, H, None, C.byref(h)) == 0
+    assert L.tau_hyp2d_group_init(g) == 0 and L.tau_hyp2d_init(h) == 0
+    assert L.tau_hyp2d_group_step(g, steps) == 0 and L.tau_hyp2d_step(h, steps) == 0
+    a, ma = state(L.tau_hyp2d_group_download, g, ngpus)
+    b, mb = state(L.tau_hyp2d_download, h, 1)
+    assert np.array_equal(ma, mb) and all(np.array_equal(x, y) for x, y in zip(a, b))
+    # an uploaded state (a second wall that crosses a slab boundary), more steps, clock, render
+    rng = np.random.default_rng(ngpus)
+    mb = mb.copy()
+    mb[H // ngpus - 3:H // ngpus + 4, 150:158] = 1
+    up = [np.ascontiguousarray(x * (1 + 0.02 * rng.random(x.shape)), npdt) for x in b]
+    for x in up[1:3]:
+        x[mb == 1] = 0
+    ptrs = (C.c_void_p * 4)(*[x.ctypes.data for x in up])
+    assert L.tau_hyp2d_group_upload(g, ptrs, mb.ctypes.data) == 0 and L.tau_hyp2d_upload(h, ptrs, mb.ctypes.data) == 0
+    assert L.tau_hyp2d_group_step(g, 7) == 0 and L.tau_hyp2d_step(h, 7) == 0
+    a, ma = state(L.tau_hyp2d_group_download, g, ngpus)
+    b, mb2 = state(L.tau_hyp2d_download, h, 1)
+    assert np.array_equal(ma, mb2) and all(np.array_equal(x, y) for x, y in zip(a, b))
+    t1, d1, t2, d2 = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+    L.tau_hyp2d_group_clock(g, C.byref(t1), C.byref(d1))
+    L.tau_hyp2d_clock(h, C.byref(t2), C.byref(d2))
+    assert (t1.value, d1.value) == (t2.value, d2.value) and t1.value > 0
+    pa, pb = np.empty((H, W), np.uint32), np.empty((H, W), np.uint32)
+    m1, m2 = (C.c_double * 2)(), (C.c_double * 2)()
+    assert L.tau_hyp2d_group_render(g, 5, pa.ctypes.data, m1) == 0 and L.tau_hyp2d_render(h, 5, pb.ctypes.data, m2) == 0
+    assert tuple(m1) == tuple(m2) and np.array_equal(pa, pb)
+    assert L.tau_hyp2d_group_destroy(g) == 0 and L.tau_hyp2d_destroy(h) == 0

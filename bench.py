@@ -198,8 +198,12 @@ def run_reference(a):
 # product arm
 # --------------------------------------------------------------------------------------------
 def run_product(a):
+    import faulthandler
+
     import numpy as np
     import torch
+
+    faulthandler.dump_traceback_later(a.trace_after, repeat=False, file=sys.stderr)   # where is it, if it hangs?
 
     from fluid_sims_b200 import slab
     from fluid_sims_b200.hypersonic2d import HALO, Hypersonic2D, SimConfig
@@ -313,6 +317,54 @@ def run_product(a):
     if a.dtype != "f32":
         ach = bpc * (W * hl) / (kernel_ms * 1e-3) / 1e9
 
+    prof = profile_constants()
+    frac_rows = hl / 4096.0 * (W / 4096.0)
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    inst = prof.get("warp_instructions_per_launch")
+    issue_frac = (inst * frac_rows / (kernel_ms * 1e-3)) / (sm_count * 4 * sm_mhz * 1e6) if inst else None
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "Mcell-updates/s", "value": value, "unit": "Mcell-updates/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+            "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
+            "dtype": a.dtype, "data": "synthetic",
+            "config": {"workload": f"tau_hypersonic_cuda {W}x{H} {a.dtype}: k_init state developed "
+                                   f"for {a.develop} steps, then timed",
+                       "grid": [W, H], "slab_rows_per_gpu": hl, "parallelism": f"y-slab x{world}" + (f" ({a.exchange} halo exchange)" if world > 1 else ""),
+                       "cache": "state (2 x 268 MB) larger than L2 (126 MB): no flush needed",
+                       "seg_rows": sim.seg_rows, "step_kernel": sim.kernel_name},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak,
+                         "traffic": prof["dram_bytes_per_launch"] * frac_rows if "dram_bytes_per_launch" in prof else None,
+                         "traffic_source": prof.get("source", None) and (prof["source"] + "; scaled by the rows one launch updates"),
+                         "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
+                         "algorithmic_bytes_per_cell": bpc, "kernel": sim.kernel_name,
+                         "kernel_ms": kernel_ms,
+                         "limiter": "fp32-issue", "issue_frac": issue_frac,
+                         "issue_peak": f"{sm_count} SMs x 4 schedulers x {sm_mhz:.0f} MHz warp-instructions/s",
+                         "note": "the kernel is FP32-issue bound, not HBM bound: `frac` is the HBM fraction at the algorithmic 33 B/cell, "
+                                 "`issue_frac` the executed warp-instructions (committed ncu capture, scaled by rows) over the issue peak; DESIGN.md 4.1"},
+            "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
+            "state_crc": crc, "sim_t": clock_t,
+            **({"peer_timing": peer_timing} if peer_timing else {}),
+        }
+    # ---- from here on nothing may cost the headline: a watchdog prints what has been measured and exits -------
+    def emit():
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+
+    done = threading.Event()
+
+    def watchdog():
+        if not done.wait(a.total_timeout):
+            if rank == 0:
+                line["watchdog"] = f"sections after the timed region did not finish within {a.total_timeout} s"
+            emit()
+            os._exit(0)
+
+    threading.Thread(target=watchdog, daemon=True).start()
     # ---- e2e: frames through the C-ABI with host buffers -------------------------------------
     e2e = None
     if not a.no_e2e:
@@ -426,6 +478,8 @@ def run_product(a):
                     slab.hyp2d_detach_peers(sb)
                     sb.close()
 
+    if rank == 0:
+        line["e2e"] = e2e
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
         v, _ = cpu_reference(a.cpu_steps, 1, 1)
@@ -445,6 +499,8 @@ def run_product(a):
                 cpu["full_grid"] = {"error": str(e)[:200]}
 
     # ---- the fp64 handle (holds the north-star's 1e-5 bound) and the reference's own kernels, N = 1 only ----
+    if rank == 0:
+        line["cpu_baseline"] = cpu
     f64 = ref_gpu = None
     if world == 1 and not a.no_extras:
         try:
@@ -472,40 +528,10 @@ def run_product(a):
         except Exception as e:          # noqa: BLE001
             ref_gpu = {"error": str(e)[:200]}
 
-    prof = profile_constants()
-    frac_rows = hl / 4096.0 * (W / 4096.0)
-    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
-    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    inst = prof.get("warp_instructions_per_launch")
-    issue_frac = (inst * frac_rows / (kernel_ms * 1e-3)) / (sm_count * 4 * sm_mhz * 1e6) if inst else None
-    line = None
-    if rank == 0:
-        line = {
-            "metric": "Mcell-updates/s", "value": value, "unit": "Mcell-updates/s",
-            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
-            "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
-            "dtype": a.dtype, "data": "synthetic",
-            "config": {"workload": f"tau_hypersonic_cuda {W}x{H} {a.dtype}: k_init state developed "
-                                   f"for {a.develop} steps, then timed",
-                       "grid": [W, H], "slab_rows_per_gpu": hl, "parallelism": f"y-slab x{world}" + (f" ({a.exchange} halo exchange)" if world > 1 else ""),
-                       "cache": "state (2 x 268 MB) larger than L2 (126 MB): no flush needed",
-                       "seg_rows": sim.seg_rows, "step_kernel": sim.kernel_name},
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak,
-                         "traffic": prof["dram_bytes_per_launch"] * frac_rows if "dram_bytes_per_launch" in prof else None,
-                         "traffic_source": prof.get("source", None) and (prof["source"] + "; scaled by the rows one launch updates"),
-                         "peak_source": f"{peak_src} (MEASURED_PEAKS.json hbm_gbs)",
-                         "algorithmic_bytes_per_cell": bpc, "kernel": sim.kernel_name,
-                         "kernel_ms": kernel_ms,
-                         "limiter": "fp32-issue", "issue_frac": issue_frac,
-                         "issue_peak": f"{sm_count} SMs x 4 schedulers x {sm_mhz:.0f} MHz warp-instructions/s",
-                         "note": "the kernel is FP32-issue bound, not HBM bound: `frac` is the HBM fraction at the algorithmic 33 B/cell, "
-                                 "`issue_frac` the executed warp-instructions (committed ncu capture, scaled by rows) over the issue peak; DESIGN.md 4.1"},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "state_crc": crc, "sim_t": clock_t,
-            **({"dtype_f64": f64} if f64 else {}), **({"reference_gpu": ref_gpu} if ref_gpu else {}),
-            **({"peer_timing": peer_timing} if peer_timing else {}),
-        }
+    if rank == 0 and f64:
+        line["dtype_f64"] = f64
+    if rank == 0 and ref_gpu:
+        line["reference_gpu"] = ref_gpu
     if world > 1 and peer:   # unmap the peers' planes on every rank before any rank frees them
         try:
             slab.hyp2d_detach_peers(sim)
@@ -514,21 +540,7 @@ def run_product(a):
     sim.close()
 
     # ---- BASELINE configs 3-5, short runs (never allowed to cost the headline line: watchdog) -------------
-    def emit():
-        if rank == 0:
-            print(json.dumps(line), flush=True)
-
     if not a.no_other:
-        done = threading.Event()
-
-        def watchdog():
-            if not done.wait(a.other_timeout):
-                if rank == 0:
-                    line.setdefault("other_configs", {})["error"] = f"timed out after {a.other_timeout} s"
-                emit()
-                os._exit(0)
-
-        threading.Thread(target=watchdog, daemon=True).start()
         other = {}
         import bench_all
         ba = bench_all.default_args(steps=200, n3=256 if world == 1 else 512, steps3=20, warm3=30, steps_sph=30)
@@ -541,7 +553,7 @@ def run_product(a):
             torch.cuda.synchronize()
         if rank == 0:
             line["other_configs"] = other
-        done.set()
+    done.set()
     emit()
     if world > 1:
         dist.destroy_process_group()
@@ -576,7 +588,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the fp64-handle and reference-kernel sub-records (N=1)")
     ap.add_argument("--no-other", action="store_true", help="skip BASELINE configs 3-5 (other_configs)")
-    ap.add_argument("--other-timeout", type=float, default=240.0)
+    ap.add_argument("--total-timeout", type=float, default=300.0,
+                    help="seconds the sections after the timed region (e2e, baselines, other configs) may take before the "
+                         "watchdog prints the line with what has been measured")
+    ap.add_argument("--trace-after", type=float, default=150.0, help="dump every thread's Python stack to stderr after this many seconds")
     ap.add_argument("--cpu-full-steps", type=int, default=3, help="reference CPU solver on the full 4096^2 grid (0 = skip)")
     ap.add_argument("--develop-f64", type=int, default=100)
     ap.add_argument("--steps-f64", type=int, default=40)

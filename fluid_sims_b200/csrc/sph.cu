@@ -312,8 +312,8 @@ sph_density(const float2 *__restrict__ sxy, const unsigned *__restrict__ vals,
             const int *__restrict__ cellStart, float2 *__restrict__ srp, float *__restrict__ s_out, float *__restrict__ press_out,
             const int *__restrict__ range, Consts c) {
   const int g = threadIdx.x & (GROUP - 1);
-  const int k = (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
-  const bool valid = range ? (k >= range[0] && k < range[1]) : (k < c.N);
+  const int k = (range ? range[0] : 0) + (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
+  const bool valid = k < (range ? range[1] : c.N);
   const float2 xi = sxy[valid ? k : 0];
   const int gx = grid_c(xi.x, c.cell, c.Gx), gy = grid_c(xi.y, c.cell, c.Gy);
   const float inv_h = rcp_approx(c.h);
@@ -346,10 +346,12 @@ __global__ void __launch_bounds__(256)
 sph_forces_integrate(const float2 *__restrict__ sxy, const float2 *__restrict__ svel,
                      const float2 *__restrict__ srp, const unsigned *__restrict__ vals,
                      const int *__restrict__ cellStart, float2 *__restrict__ pos, float2 *__restrict__ vel, float2 *__restrict__ acc,
-                     float2 *__restrict__ sxy_new, float2 *__restrict__ svel_new, float dt, Consts c) {
+                     float2 *__restrict__ sxy_new, float2 *__restrict__ svel_new, float dt, Consts c,
+                     const int *__restrict__ range) {
   const int g = threadIdx.x & (GROUP - 1);
-  const int k = c.k_begin + (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
-  const bool valid = k < c.k_end;
+  // slots this launch integrates: [k_begin, k_end) from the host, or a device-resident range (stripe shards)
+  const int k = (range ? range[0] : c.k_begin) + (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
+  const bool valid = k < (range ? range[1] : c.k_end);
   const int kk = valid ? k : 0;
   const float2 xi = sxy[kk], vi = svel[kk], rpi = srp[kk];
   const float rhoi = rpi.x, pri = rpi.y;
@@ -431,10 +433,10 @@ sph_forces_integrate(const float2 *__restrict__ sxy, const float2 *__restrict__ 
 __global__ void __launch_bounds__(256)
 sph_xsph(const float2 *__restrict__ sxy_new, const float2 *__restrict__ svel_new,
          const float2 *__restrict__ srp, const unsigned *__restrict__ vals,
-         const int *__restrict__ cellStart, float2 *__restrict__ dvel, Consts c) {
+         const int *__restrict__ cellStart, float2 *__restrict__ dvel, Consts c, const int *__restrict__ range) {
   const int g = threadIdx.x & (GROUP - 1);
-  const int k = (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
-  const bool valid = k < c.N;
+  const int k = (range ? range[0] : 0) + (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
+  const bool valid = k < (range ? range[1] : c.N);
   const int kk = valid ? k : 0;
   const float2 xi = sxy_new[kk], vi = svel_new[kk];
   const float rhoi = srp[kk].x;
@@ -609,28 +611,31 @@ Consts make_consts(const tau_sph *h) {
   return c;
 }
 
-// stable radix sort of (keys[0], vals[0]); returns the buffer index holding the result
-int radix_sort(tau_sph *h) {
-  const int n = h->p.N;
-  const int passes = (h->key_bits + SORT_MAX_BITS - 1) / SORT_MAX_BITS;
-  const int bits = (h->key_bits + passes - 1) / passes;
-  const int blocks = (h->nwarps + SORT_WARPS - 1) / SORT_WARPS;
+// stable radix sort of (keys[0], vals[0]), n pairs with keys < 2^key_bits; returns the buffer index holding the result
+int radix_sort_pairs(unsigned *const keys[2], unsigned *const vals[2], unsigned *hist, unsigned *scan_totals, int n,
+                     int key_bits, cudaStream_t stream, long long *launches) {
+  const int nwarps = (n + SORT_SEG - 1) / SORT_SEG;
+  const int passes = (key_bits + SORT_MAX_BITS - 1) / SORT_MAX_BITS;
+  const int bits = (key_bits + passes - 1) / passes;
+  const int blocks = (nwarps + SORT_WARPS - 1) / SORT_WARPS;
   int src = 0;
   for (int p = 0; p < passes; ++p) {
     const int shift = p * bits;
-    sort_hist<<<blocks, SORT_WARPS * 32, 0, h->stream>>>(h->keys[src], h->hist, n, shift, bits, h->nwarps);
+    sort_hist<<<blocks, SORT_WARPS * 32, 0, stream>>>(keys[src], hist, n, shift, bits, nwarps);
     {
-      const int m = (1 << bits) * h->nwarps, tiles = (m + SCAN_TILE - 1) / SCAN_TILE;
-      scan_tiles<<<tiles, SCAN_THREADS, 0, h->stream>>>(h->hist, h->scan_totals, m);
-      scan_add<<<tiles, SCAN_THREADS, 0, h->stream>>>(h->hist, h->scan_totals, m);
+      const int m = (1 << bits) * nwarps, tiles = (m + SCAN_TILE - 1) / SCAN_TILE;
+      scan_tiles<<<tiles, SCAN_THREADS, 0, stream>>>(hist, scan_totals, m);
+      scan_add<<<tiles, SCAN_THREADS, 0, stream>>>(hist, scan_totals, m);
     }
-    sort_scatter<<<blocks, SORT_WARPS * 32, 0, h->stream>>>(h->keys[src], h->vals[src], h->keys[src ^ 1],
-                                                            h->vals[src ^ 1], h->hist, n, shift, bits,
-                                                            h->nwarps);
-    h->launches += 4;
+    sort_scatter<<<blocks, SORT_WARPS * 32, 0, stream>>>(keys[src], vals[src], keys[src ^ 1], vals[src ^ 1], hist, n, shift,
+                                                         bits, nwarps);
+    *launches += 4;
     src ^= 1;
   }
   return src;
+}
+int radix_sort(tau_sph *h) {
+  return radix_sort_pairs(h->keys, h->vals, h->hist, h->scan_totals, h->p.N, h->key_bits, h->stream, &h->launches);
 }
 
 // first half of a sub-step: keys, sort, cell ranges, gather, density, forces + integration.
@@ -661,12 +666,12 @@ int substep_compute(tau_sph *h, float dt_sub) {
   sph_forces_integrate<<<GSown, BS, 0, h->stream>>>(h->sxy, h->svel, h->srp, h->vals[sb], h->cellStart,
                                                     h->pos, h->vel, h->acc,
                                                     (xsph || sharded) ? h->sxy_new : nullptr,
-                                                    (xsph || sharded) ? h->svel_new : nullptr, dt_sub, c);
+                                                    (xsph || sharded) ? h->svel_new : nullptr, dt_sub, c, nullptr);
   h->launches += 5;
   if (xsph) {
     const int GSg = GSall;
     sph_xsph<<<GSg, BS, 0, h->stream>>>(h->sxy_new, h->svel_new, h->srp, h->vals[sb], h->cellStart,
-                                        h->acc, c);
+                                        h->acc, c, nullptr);
     sph_apply_xsph<<<GS, BS, 0, h->stream>>>(h->vel, h->acc, n);
     h->launches += 2;
   }
@@ -1052,3 +1057,5 @@ int tau_sph_destroy(tau_sph *h) {
 }
 
 }  // extern "C"
+
+#include "sph_stripes.inc"

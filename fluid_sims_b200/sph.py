@@ -190,3 +190,179 @@ class SPH:
             self.close()
         except Exception:
             pass
+
+
+# ---- the particle set sharded by hash-bin stripes (tau_sph_stripe_*, include/tau_b200.h) -------------------------
+_s = C.c_void_p
+_st_create = declare("tau_sph_stripe_create", [C.POINTER(_CParams), C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(_s)])
+_st_upload = declare("tau_sph_stripe_upload", [_s, _f32, _f32])
+_st_xbuf = declare("tau_sph_stripe_xbuf", [_s, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)])
+_st_phase = declare("tau_sph_stripe_phase", [_s, C.c_int])
+_st_hist_begin = declare("tau_sph_stripe_hist_begin", [_s, C.POINTER(C.c_void_p), C.POINTER(C.c_int)])
+_st_hist_apply = declare("tau_sph_stripe_hist_apply", [_s])
+_st_status = declare("tau_sph_stripe_status", [_s, C.POINTER(C.c_int)])
+_st_download = declare("tau_sph_stripe_download", [_s, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                   C.POINTER(C.c_int)])
+_st_clock = declare("tau_sph_stripe_clock", [_s, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_longlong)])
+_st_capacity = declare("tau_sph_stripe_capacity", [_s, C.POINTER(C.c_int), C.POINTER(C.c_int)])
+_st_sync = declare("tau_sph_stripe_sync", [_s])
+_st_substeps = declare("tau_sph_stripe_substeps_done", [_s], C.c_longlong)
+_st_launches = declare("tau_sph_stripe_launch_count", [_s], C.c_longlong)
+_st_destroy = declare("tau_sph_stripe_destroy", [_s])
+
+
+class SPHStripes:
+    """One rank of the stripe-sharded SPH solver: holds the particles of its stripe of hash-bin rows only.
+
+    `exchange(send_lo, send_hi, recv_lo, recv_hi)` moves whole message buffers between neighbouring ranks (send_lo
+    to rank-1, send_hi to rank+1, recv_lo from rank-1, recv_hi from rank+1; arguments are (device pointer, 32-bit
+    words), None where there is no neighbour) and `allreduce_sum(ptr, n_ints)` sums the row histogram in place;
+    `nccl_plumbing()` returns the pair for torch.distributed (NCCL send/recv over NVLink)."""
+
+    def __init__(self, params: Params, rank: int, world: int, device: int = 0, stream: int | None = None,
+                 exchange=None, allreduce_sum=None, rebalance_every: int = 16):
+        self.params, self.rank, self.world, self.device = params, rank, world, device
+        self.exchange, self.allreduce_sum, self.rebalance_every = exchange, allreduce_sum, rebalance_every
+        self._handle = _s()
+        cp = params._c()
+        check(_st_create(C.byref(cp), device, C.c_void_p(stream or 0), rank, world, C.byref(self._handle)))
+        self._bufs = []
+        for which in range(8):
+            p, w = C.c_void_p(), C.c_longlong()
+            check(_st_xbuf(self._handle, which, C.byref(p), C.byref(w)))
+            self._bufs.append((p.value, int(w.value)))
+
+    def upload(self, pos, vel):
+        """the WHOLE particle set on every rank (reference order); each keeps its stripe"""
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1)
+        vel = np.ascontiguousarray(vel, np.float32).reshape(-1)
+        assert pos.size == 2 * self.params.N and vel.size == pos.size
+        check(_st_upload(self._handle, pos, vel))
+        return self
+
+    def init(self):
+        return self.upload(*reset_particles(self.params))
+
+    def _xchg(self, base):
+        if self.world == 1:
+            return
+        lo, hi = self.rank > 0, self.rank < self.world - 1
+        b = self._bufs
+        self.exchange(b[base] if lo else None, b[base + 1] if hi else None, b[base + 2] if lo else None,
+                      b[base + 3] if hi else None)
+
+    def substep(self):
+        """one sub-step (tau_sph.cu:676-721) of this rank's stripe; every rank must call it"""
+        xsph = self.params.useXSPH and self.params.xsphEps > 0
+        check(_st_phase(self._handle, 0))
+        self._xchg(0)
+        check(_st_phase(self._handle, 1))
+        self._xchg(4)
+        check(_st_phase(self._handle, 2))
+        if xsph:
+            self._xchg(0)
+        check(_st_phase(self._handle, 3))
+        if self.world > 1 and self.rebalance_every and self.substeps_done % self.rebalance_every == 0:
+            self.rebalance()
+
+    def rebalance(self):
+        p, n = C.c_void_p(), C.c_int()
+        check(_st_hist_begin(self._handle, C.byref(p), C.byref(n)))
+        self.allreduce_sum(p.value, n.value)
+        check(_st_hist_apply(self._handle))
+
+    def step(self, nframes: int = 1):
+        k = self.params.viscSub if self.params.viscSub > 0 else 1
+        for _ in range(nframes * k):
+            self.substep()
+        return self
+
+    def status(self):
+        out = (C.c_int * 8)()
+        check(_st_status(self._handle, out))
+        keys = ("n_own", "n_ghost", "err", "max_send", "cap", "xcap", "row_begin", "row_end")
+        return dict(zip(keys, [int(v) for v in out]))
+
+    def download_local(self):
+        """(ids, pos, vel, s, press) of the particles this rank owns, local order"""
+        cap, xcap = C.c_int(), C.c_int()
+        check(_st_capacity(self._handle, C.byref(cap), C.byref(xcap)))
+        ids = np.empty(cap.value, np.uint32)
+        pos, vel = np.empty((cap.value, 2), np.float32), np.empty((cap.value, 2), np.float32)
+        s, pr = np.empty(cap.value, np.float32), np.empty(cap.value, np.float32)
+        n = C.c_int()
+        check(_st_download(self._handle, ids.ctypes.data, pos.ctypes.data, vel.ctypes.data, s.ctypes.data, pr.ctypes.data,
+                           C.byref(n)))
+        keep = ids[:n.value] != 0xFFFFFFFF       # a particle the rain re-homed to another rank leaves a hole until the next sub-step
+        return ids[:n.value][keep], pos[:n.value][keep], vel[:n.value][keep], s[:n.value][keep], pr[:n.value][keep]
+
+    def clock(self):
+        t, tau, st = C.c_float(), C.c_float(), C.c_longlong()
+        check(_st_clock(self._handle, C.byref(t), C.byref(tau), C.byref(st)))
+        return float(t.value), float(tau.value), int(st.value)
+
+    def sync(self):
+        check(_st_sync(self._handle))
+
+    @property
+    def substeps_done(self) -> int:
+        return int(_st_substeps(self._handle))
+
+    @property
+    def launch_count(self) -> int:
+        return int(_st_launches(self._handle))
+
+    def close(self):
+        if self._handle:
+            check(_st_destroy(self._handle))
+            self._handle = _s()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def assemble(parts, N):
+    """[(ids, pos, vel, s, press)] of every rank -> (pos, vel, s, press) in the reference's particle order; every id
+    must appear exactly once"""
+    ids = np.concatenate([p[0] for p in parts])
+    assert ids.size == N and np.array_equal(np.sort(ids), np.arange(N, dtype=ids.dtype)), "stripes lost or duplicated particles"
+    out = []
+    for k, shape in ((1, (N, 2)), (2, (N, 2)), (3, (N,)), (4, (N,))):
+        a = np.empty(shape, np.float32)
+        a[ids] = np.concatenate([p[k] for p in parts])
+        out.append(a)
+    return tuple(out)
+
+
+def nccl_plumbing(device: int):
+    """(exchange, allreduce_sum) for SPHStripes over torch.distributed: whole message buffers by NCCL send / recv
+    between neighbouring ranks (a chain in y), the row histogram by all_reduce — on torch's current stream, which the
+    caller makes the handle's stream."""
+    import torch
+    import torch.distributed as dist
+
+    from . import slab
+    rank = dist.get_rank()
+    views = {}
+
+    def view(buf):
+        if buf not in views:
+            views[buf] = slab.wrap_plane(buf[0], (buf[1],), torch.int32, device)
+        return views[buf]
+
+    def exchange(send_lo, send_hi, recv_lo, recv_hi):
+        ops = []
+        if send_lo is not None:
+            ops += [dist.P2POp(dist.isend, view(send_lo), rank - 1), dist.P2POp(dist.irecv, view(recv_lo), rank - 1)]
+        if send_hi is not None:
+            ops += [dist.P2POp(dist.isend, view(send_hi), rank + 1), dist.P2POp(dist.irecv, view(recv_hi), rank + 1)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+
+    def allreduce_sum(ptr, n):
+        dist.all_reduce(slab.wrap_plane(ptr, (n,), torch.int32, device), op=dist.ReduceOp.SUM)
+
+    return exchange, allreduce_sum

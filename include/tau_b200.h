@@ -401,6 +401,40 @@ int tau_sw_last_step_ms(tau_sw *h, float *ms);
 int tau_sw_destroy(tau_sw *h);
 
 /* ---------------------------------------------------------------------------------------------
+ * SPH sharded by hash-bin stripes with ghost-particle exchange and migration
+ * Replaces the same sub-step body (tau_sph.cu:676-721) as tau_sph_step, for `world` GPUs: rank r holds
+ * only the particles of its stripe of grid rows (stripes balanced by particle count) plus, per
+ * sub-step, the ghost particles of one cell row on either side.  Global particle ids (= index in the
+ * reference's arrays) travel with the particles.  A sub-step is four enqueue-only phases with the
+ * neighbour exchanges between them (fixed-capacity messages with their counts in a header; all counts
+ * the kernels need are device-resident: no host synchronisation):
+ *   phase 0 -> exchange buffers 0..3 (migrants + boundary rows: ids, pos, vel) -> phase 1
+ *           -> exchange buffers 4..7 (rho, p/rho^2 of the boundary rows)      -> phase 2
+ *           -> [XSPH only: exchange buffers 0..3 again (integrated boundary rows)] -> phase 3
+ * "exchange": send buffer b+0 to rank-1 and b+1 to rank+1, receive b+2 from rank-1 and b+3 from rank+1
+ * (whole buffers; a chain — y is not periodic).  Results are bit-identical to the single-GPU handle.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct tau_sph_stripe tau_sph_stripe;
+int tau_sph_stripe_create(const tau_sph_params *p, int device, void *stream, int rank, int world, tau_sph_stripe **out);
+/* the WHOLE particle set (N x (x, y), reference order); the rank keeps its stripe; clock := (t0, 0) */
+int tau_sph_stripe_upload(tau_sph_stripe *h, const float *pos_xy, const float *vel_xy);
+int tau_sph_stripe_xbuf(tau_sph_stripe *h, int which, void **ptr, long long *words);
+int tau_sph_stripe_phase(tau_sph_stripe *h, int phase);
+/* re-balancing between sub-steps: hist_begin -> all-reduce(SUM) of *rows ints at *hist (device) -> hist_apply */
+int tau_sph_stripe_hist_begin(tau_sph_stripe *h, void **hist, int *rows);
+int tau_sph_stripe_hist_apply(tau_sph_stripe *h);
+/* n_own, n_ghost, error bits, message high-water mark, capacity, message capacity, first row, end row (synchronises) */
+int tau_sph_stripe_status(tau_sph_stripe *h, int out[8]);
+/* the rank's owned particles in local order: ids[n], pos / vel (n x 2), s, press (n); *n_out = n <= capacity */
+int tau_sph_stripe_download(tau_sph_stripe *h, unsigned *ids, float *pos_xy, float *vel_xy, float *s, float *press, int *n_out);
+int tau_sph_stripe_clock(tau_sph_stripe *h, float *t, float *tau, long long *step);
+int tau_sph_stripe_capacity(tau_sph_stripe *h, int *cap, int *xcap);
+int tau_sph_stripe_sync(tau_sph_stripe *h);
+long long tau_sph_stripe_substeps_done(tau_sph_stripe *h);
+long long tau_sph_stripe_launch_count(tau_sph_stripe *h);
+int tau_sph_stripe_destroy(tau_sph_stripe *h);
+
+/* ---------------------------------------------------------------------------------------------
  * 2-D hypersonic on several GPUs of one box from ONE process ("create(cfg, dims, ngpus)")
  * Replaces the same step loop (tau_hypersonic_cuda.cu:1833-1889) and allocation block (:1748-1819) as
  * tau_hyp2d_*, y-slab decomposed (chain, 2 ghost rows): one slab handle per device, peers

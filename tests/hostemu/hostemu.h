@@ -325,6 +325,7 @@ template <class T> static inline T atomicMax(T *a, T v) { T o = *a; if (v > o) *
 template <class T> static inline T atomicMin(T *a, T v) { T o = *a; if (v < o) *a = v; return o; }
 template <class T, class U> static inline T atomicAdd(T *a, U v) { T o = *a; *a = o + (T)v; return o; }
 template <class T> static inline T atomicExch(T *a, T v) { T o = *a; *a = v; return o; }
+template <class T, class U> static inline T atomicOr(T *a, U v) { T o = *a; *a = o | (T)v; return o; }
 template <class T> static inline T atomicCAS(T *a, T c, T v) { T o = *a; if (o == c) *a = v; return o; }
 
 // ---- the slice of the CUDA runtime API the host functions use; "device memory" is host memory ----

@@ -803,3 +803,29 @@ def test_hyp2d_group_equals_single_domain(pretend_device, monkeypatch, ngpus, dt
     assert L.tau_hyp2d_group_render(g, 5, pa.ctypes.data, m1) == 0 and L.tau_hyp2d_render(h, 5, pb.ctypes.data, m2) == 0
     assert tuple(m1) == tuple(m2) and np.array_equal(pa, pb)
     assert L.tau_hyp2d_group_destroy(g) == 0 and L.tau_hyp2d_destroy(h) == 0
+
+
+# ---- SPH sharded by hash-bin stripes (sph_stripes.inc): ghost exchange, migration, re-balancing, rain ------------
+@pytest.mark.parametrize("N,world,frames,over", [
+    (3000, 1, 4, {}), (3000, 2, 4, {}), (5000, 3, 5, dict(viscSub=3, rebalance_every=2)),
+    (6000, 4, 7, dict(useXSPH=1)), (4000, 2, 6, dict(rain=0, gammaEOS=2.0, c0=2.0, useGrav=0)), (12000, 8, 5, {})])
+def test_sph_stripes_equal_single_handle_bit_for_bit(N, world, frames, over):
+    """`world` rank handles of the stripe-sharded solver in one process, stepping in lock-step with memmove exchanges
+    (tests/hostemu/sph_stripes_emu.py), against the single-GPU handle of the same emulated library: positions, velocities
+    and the clock bit-identical — through migration, ghost rows, the in-cell order by global id, stripe re-balancing, XSPH's
+    third exchange and the rain's re-homing; no error bit; the owned sets partition the particles.  s / press may differ
+    only on the handful of particles the rain re-homed to another rank in the last sub-step (their s stays behind)."""
+    import json
+    import subprocess
+    so = hostemu_build.build("sph")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TAU_B200_LIB=so, PYTHONPATH=root)
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "hostemu", "sph_stripes_emu.py"), str(N), str(world),
+                        str(frames), json.dumps(over)], capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    j = json.loads(r.stdout.strip().split("\n")[-1])
+    assert j["pos_equal"] and j["vel_equal"] and j["clock_equal"] and j["moved"] > 0.05, j
+    assert all(s["err"] == 0 for s in j["status"]) and sum(s["n_own"] for s in j["status"]) >= N
+    assert j["s_mismatches"] <= (0 if not over.get("rain", 1) else 12) and j["press_mismatches"] <= 12
+    if world > 1:
+        assert all(s["n_ghost"] > 0 for s in j["status"]) and max(s["max_send"] for s in j["status"]) > 0

@@ -160,21 +160,18 @@ def bench_sph(a):
     P = Params(N=N)
     ts = torch.cuda.Stream(device=local)
     torch.cuda.set_stream(ts)
-    s = SPH(P, device=local, stream=ts.cuda_stream).init()
-    if world > 1:
-        s.shard_config(rank, world)
+    if world == 1:
+        s = SPH(P, device=local, stream=ts.cuda_stream).init()
+        advance = s.step
+    else:   # hash-bin stripes: every rank holds its stripe only; ghost rows + migrants by NCCL send / recv
+        from fluid_sims_b200.sph import SPHStripes, nccl_plumbing
+        exchange, allreduce_sum = nccl_plumbing(local)
+        s = SPHStripes(P, rank, world, device=local, stream=ts.cuda_stream, exchange=exchange,
+                       allreduce_sum=allreduce_sum).init()
 
-    def gather(pa, pb, chunk):
-        for ptr in (pa, pb):
-            full = slab.wrap_plane(ptr, (world * chunk, 2), torch.float32, local)
-            dist.all_gather_into_tensor(full, full[rank * chunk:(rank + 1) * chunk])
-
-    def advance(k):
-        if world == 1:
-            s.step(k)
-        else:
+        def advance(k):
             for _ in range(k):
-                s.shard_substep(gather)
+                s.substep()
 
     advance(5)
     torch.cuda.synchronize()
@@ -186,10 +183,13 @@ def bench_sph(a):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps_sph
+    stripes = None
     if world > 1:
         t = torch.tensor([ms], device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        stripes = [None] * world
+        dist.all_gather_object(stripes, s.status())
     ref = None
     if world == 1 and oracle.has_ref("ref_sph"):
         pos0, vel0 = reset_particles(P)
@@ -207,7 +207,10 @@ def bench_sph(a):
                           "reference_gpu": {"ms_per_substep": ref,
                                             "value": N / (ref * 1e-3) / 1e6 if ref else None,
                                             "what": "tau_sph.cu kernels recompiled for sm_100a"},
-                          "parallelism": "replicated state, slot-range shards + all-gather x%d" % world,
+                          "parallelism": ("single GPU" if world == 1 else
+                                          "hash-bin stripes x%d, ghost-row + migrant exchange by NCCL send/recv" % world),
+                          **({"stripes": [{k: x[k] for k in ("n_own", "n_ghost", "err", "max_send", "row_begin", "row_end")}
+                                          for x in stripes]} if stripes else {}),
                           "gpu_launches": s.launch_count})
     return None
 

@@ -411,25 +411,21 @@ hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *
 #include "hypersonic2d_epilogue.inc"
 }
 
-// One flag per marching work item (strip x row segment): does the staged window of that item
-// contain a body cell?  Static for a given mask and item table; selects the march variant (bit 31
-// of the descriptor's first word).
+// One flag per (strip, owned row): does the march read a body cell when it produces this row, i.e. is there one in
+// rows r-2 .. r+2 of the strip's staged columns?  The flag depends on the mask alone (ghost rows hold the
+// neighbour's rows or the y-clamp images), NOT on how rows are cut into work items or slabs: items are cut where
+// it changes, so a cell is always produced by the same march variant — which is what makes results bit-identical
+// for every segment height and every slab decomposition (the variants differ in FMA contraction).
 template <typename R>
-__global__ void hyp2d_flag_items(const Params<R> P, const uint8_t *__restrict__ mask,
-                                 uint2 *__restrict__ items) {
-  const int item = blockIdx.x;
-  const uint2 d = items[item];
-  const int strip = (int)(d.x & 0xffffu);
+__global__ void hyp2d_flag_rows(const Params<R> P, const uint8_t *__restrict__ mask, uint8_t *__restrict__ flags) {
+  const int strip = blockIdx.x, r = blockIdx.y * blockDim.x + threadIdx.x;
+  if (r >= P.H_local) return;
   const int x0 = strip * H2_OWN, bx = (x0 - 2) & ~3;
-  const int ys = (int)(d.y & 0xfffffu), ye = ys + (int)(d.y >> 20);
-  const int r0 = ys, r1 = min(ye + 2 * H2_GHOST, P.H_local + 2 * H2_GHOST);  // plane rows
   const int c0 = max(bx, 0), c1 = min(bx + H2_BOXW, P.W);
   int any = 0;
-  const int ncol = c1 - c0, n = (r1 - r0) * ncol;
-  for (int i = threadIdx.x; i < n; i += blockDim.x)
-    any |= mask[(size_t)(r0 + i / ncol) * P.W + c0 + i % ncol];
-  any = __syncthreads_or(any);
-  if (threadIdx.x == 0) items[item].x = (d.x & 0x7fffffffu) | (any ? 0x80000000u : 0u);
+  for (int pr = r; pr <= r + 2 * H2_GHOST; ++pr)  // plane rows r .. r+4 = local rows r-2 .. r+2
+    for (int c = c0; c < c1; ++c) any |= mask[(size_t)pr * P.W + c];
+  flags[(size_t)strip * P.H_local + r] = any ? 1 : 0;
 }
 
 // Standalone max-wavespeed scan of the CURRENT state (first step after init/upload) —
@@ -940,42 +936,57 @@ int build_items(tau_hyp2d *h, size_t smem) {
   layer_y.resize(nl);
   layer_h.resize(nl);
   if (h->seg_auto) h->seg_rows = layer_h.empty() ? 0 : layer_h[0];
-  const size_t n = layer_y.size() * (size_t)nstrips;
   TAU_REQUIRE(nstrips <= 0xffff && h->h_local < (1 << 20), "tau_hyp2d: grid too large for the item table");
-  std::vector<uint2> tab(n);
+  Params<R> P = make_params<R>(h);
+  // per-(strip, row) variant flags: a property of the mask, see hyp2d_flag_rows
+  std::vector<uint8_t> flags((size_t)nstrips * h->h_local);
+  {
+    uint8_t *dflags = nullptr;
+    TAU_CUDA(cudaMalloc(&dflags, flags.size()));
+    hyp2d_flag_rows<R><<<dim3((unsigned)nstrips, (unsigned)((h->h_local + 127) / 128)), 128, 0, h->stream>>>(P, h->mask, dflags);
+    h->launches++;
+    TAU_CUDA(cudaGetLastError());
+    TAU_CUDA(cudaMemcpyAsync(flags.data(), dflags, flags.size(), cudaMemcpyDeviceToHost, h->stream));
+    TAU_CUDA(cudaStreamSynchronize(h->stream));
+    TAU_CUDA(cudaFree(dflags));
+  }
+  // The guided schedule puts its SHORT layers at the end of the slab.  Where those rows hold the body, the masked
+  // march (the costliest variant) is cut into many 4-row items, each paying its two warm-up rows: measured at N = 2,
+  // the rank with the body at the bottom of its slab took 254 us per step against 233 us for the mirror-image rank.
+  // So: if the masked rows sit in the lower half of the slab, lay the layers out bottom-up instead.
+  if (h->seg_auto && !getenv("TAU_HYP2D_NO_MIRROR")) {
+    double rows = 0.0, centre = 0.0;
+    for (int s = 0; s < nstrips; ++s)
+      for (int r = 0; r < h->h_local; ++r)
+        if (flags[(size_t)s * h->h_local + r]) {
+          rows += 1.0;
+          centre += r + 0.5;
+        }
+    if (rows > 0.0 && centre / rows > 0.5 * h->h_local)
+      for (size_t l = 0; l < layer_y.size(); ++l) layer_y[l] = h->h_local - layer_y[l] - layer_h[l];
+  }
+  // layers x strips, every item cut where its rows' flag changes
+  std::vector<uint2> tab;
+  tab.reserve(layer_y.size() * (size_t)nstrips + 64);
+  for (size_t l = 0; l < layer_y.size(); ++l)
+    for (int s = 0; s < nstrips; ++s) {
+      const uint8_t *f = &flags[(size_t)s * h->h_local];
+      int y = layer_y[l];
+      const int ye = layer_y[l] + layer_h[l];
+      while (y < ye) {
+        int e = y + 1;
+        while (e < ye && f[e] == f[y]) ++e;
+        tab.push_back(make_uint2((unsigned)s | (f[y] ? 0x80000000u : 0u), (unsigned)y | ((unsigned)(e - y) << 20)));
+        y = e;
+      }
+    }
+  const size_t n = tab.size();
   if (h->items_cap < n) {
     if (h->items) TAU_CUDA(cudaFree(h->items));
     TAU_CUDA(cudaMalloc(&h->items, n * sizeof(uint2)));
     h->items_cap = n;
   }
   h->nitems = (int)n;
-  Params<R> P = make_params<R>(h);
-  // The guided schedule puts its SHORT layers at the end of the slab.  Where those rows hold the body, the masked
-  // march (the costliest variant) is cut into many 4-row items, each paying its two warm-up rows: measured at N = 2,
-  // the rank with the body at the bottom of its slab took 254 us per step against 233 us for the mirror-image rank.
-  // So: flag once, and if the masked items sit in the lower half of the slab, lay the layers out bottom-up instead.
-  for (int pass = 0; pass < 2; ++pass) {
-    size_t k = 0;
-    for (size_t l = 0; l < layer_y.size(); ++l)
-      for (int s = 0; s < nstrips; ++s)
-        tab[k++] = make_uint2((unsigned)s, (unsigned)layer_y[l] | ((unsigned)layer_h[l] << 20));
-    TAU_CUDA(cudaMemcpyAsync(h->items, tab.data(), n * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
-    hyp2d_flag_items<R><<<(unsigned)n, 128, 0, h->stream>>>(P, h->mask, h->items);
-    h->launches++;
-    TAU_CUDA(cudaGetLastError());
-    TAU_CUDA(cudaMemcpyAsync(tab.data(), h->items, n * sizeof(uint2), cudaMemcpyDeviceToHost, h->stream));
-    TAU_CUDA(cudaStreamSynchronize(h->stream));
-    if (pass || !h->seg_auto || getenv("TAU_HYP2D_NO_MIRROR")) break;
-    double rows = 0.0, centre = 0.0;
-    for (size_t i = 0; i < n; ++i)
-      if (tab[i].x >> 31) {
-        const double y0 = (double)(tab[i].y & 0xfffffu), hh = (double)(tab[i].y >> 20);
-        rows += hh;
-        centre += hh * (y0 + 0.5 * hh);
-      }
-    if (rows == 0.0 || centre / rows <= 0.5 * h->h_local) break;
-    for (size_t l = 0; l < layer_y.size(); ++l) layer_y[l] = h->h_local - layer_y[l] - layer_h[l];
-  }
   // masked items first; within each class the table order (tall -> short) is kept
   std::vector<uint2> sorted;
   sorted.reserve(n);

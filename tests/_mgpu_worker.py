@@ -126,28 +126,39 @@ def main():
         print(f"hyp3d world={world}: z-slab ring == single-GPU: {same} (clock {s3.clock()}, max |d xi| {moved:.3g})")
         ok &= same and moved > 0.1
 
-    # ---- SPH: replicated state, work sharded by sorted-slot range, all-gather per sub-step ---------
-    from fluid_sims_b200.sph import SPH, Params as SP, reset_particles
-    sp = SP(N=200000, viscSub=2)
-    pos0, vel0 = reset_particles(sp)
-    sh = SPH(sp, device=local, stream=ts.cuda_stream).upload(pos0, vel0).shard_config(rank, world)
-
-    def gather(pa, pb, chunk):
-        for ptr in (pa, pb):
-            full = slab.wrap_plane(ptr, (world * chunk, 2), torch.float32, local)
-            dist.all_gather_into_tensor(full, full[rank * chunk:(rank + 1) * chunk])
-
-    nsub = 16
-    for _ in range(nsub):
-        sh.shard_substep(gather)
-    spos, svel, _, _ = sh.download()
+    # ---- SPH: the particle set sharded by hash-bin stripes, ghost exchange + migration over NCCL send / recv ----------
+    from fluid_sims_b200 import sph as S
+    results = []
+    for N, frames, kw in ((200000, 8, dict(viscSub=2)), (120000, 10, dict(useXSPH=1)), (150000, 12, dict(rebalance_every=3))):
+        rb = kw.pop("rebalance_every", 16)
+        sp = S.Params(N=N, **kw)
+        pos0, vel0 = S.reset_particles(sp)
+        exchange, allreduce_sum = S.nccl_plumbing(local)
+        st = S.SPHStripes(sp, rank, world, device=local, stream=ts.cuda_stream, exchange=exchange,
+                          allreduce_sum=allreduce_sum, rebalance_every=rb).upload(pos0, vel0)
+        st.step(frames)
+        status = st.status()
+        mine = st.download_local()
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+        stats = [None] * world
+        dist.all_gather_object(stats, status)
+        if rank == 0:
+            got = S.assemble(parts, N)
+            one = S.SPH(sp, device=local).upload(pos0, vel0)
+            one.step(frames)
+            opos, ovel, os_, opr = one.download()
+            same = np.array_equal(got[0], opos) and np.array_equal(got[1], ovel) and st.clock() == one.clock()
+            s_bad = int((got[2] != os_).sum())
+            errs = [x["err"] for x in stats]
+            print(f"sph stripes world={world} N={N} {kw}: == single-GPU: {same}; s mismatches {s_bad} (rain re-homing only); "
+                  f"err bits {errs}; owned {[x['n_own'] for x in stats]} ghosts {[x['n_ghost'] for x in stats]} "
+                  f"max message {max(x['max_send'] for x in stats)} of {stats[0]['xcap']}")
+            results.append(same and not any(errs) and s_bad <= 50)
+            one.close()
+        st.close()
     if rank == 0:
-        one = SPH(sp, device=local).upload(pos0, vel0)
-        one.step(nsub // 2)
-        opos, ovel, _, _ = one.download()
-        same = np.array_equal(spos, opos) and np.array_equal(svel, ovel) and sh.clock() == one.clock()
-        print(f"sph world={world}: sharded == single-GPU: {same}")
-        ok &= same
+        ok &= all(results)
         with open(os.path.join(out_dir, "result.txt"), "w") as f:
             f.write("OK" if ok else "FAIL")
     dist.barrier()

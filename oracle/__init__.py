@@ -196,11 +196,13 @@ def hyp2d_snapshot(cfg: Hyp2dCfg, steps, planes, mask):
     return out
 
 
-def ref_hyp2d_run(W, H, cfg11, steps, planes=None, mask=None, tile=(32, 8), host=False):
+def ref_hyp2d_run(W, H, cfg11, steps, planes=None, mask=None, tile=(32, 8), host=False, f32=False):
     """The reference's own kernels on the GPU (oracle/_ref/libref_hyp2d_<W>x<H>.so) or, host=True, the same
-    driver and kernels executed by the CPU emulator of tests/hostemu (libref_hyp2d_host_<W>x<H>.so).
+    driver and kernels executed by the CPU emulator of tests/hostemu (libref_hyp2d_host_<W>x<H>.so), or, f32=True,
+    the float-typed scratch copy of the reference (libref_hyp2d_f32_<W>x<H>.so, oracle/gen_f32_src.py): the
+    reference's algorithm evaluated in fp32 (planes still cross this interface as float64).
     planes=None -> start from k_init.  Returns (planes, mask, sim_t, dts, ms)."""
-    r = ref(f"ref_hyp2d_host_{W}x{H}" if host else f"ref_hyp2d_{W}x{H}")
+    r = ref(f"ref_hyp2d_f32_{W}x{H}" if f32 else (f"ref_hyp2d_host_{W}x{H}" if host else f"ref_hyp2d_{W}x{H}"))
     r.ref_hyp2d_run.argtypes = [f64p, C.c_int, C.c_int, C.c_int, C.c_int, f64p, f64p, f64p, f64p,
                                 u8p, C.POINTER(C.c_double), C.c_void_p, C.POINTER(C.c_float)]
     r.ref_hyp2d_run.restype = C.c_int

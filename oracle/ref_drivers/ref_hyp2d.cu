@@ -6,9 +6,28 @@
 // The host loop below restates main()'s step loop (:1833-1889) with main()'s launch parameters —
 // NOT the test harness's run_hypersonic_steps(), whose reduction launches omit the dynamic shared
 // memory argument.
+// -DREF_F32: REF_SRC is the float-typed scratch copy made by oracle/gen_f32_src.py (every `double` -> `float`, literals
+// suffixed): the reference's own algorithm evaluated in fp32, the yardstick for the product's fp32 handle.  The host
+// loop then runs in float as the sed-ed main() would; the planes cross the C interface as doubles either way.
 #define TAU_HYPERSONIC_CUDA_NO_RAYLIB
 #define TAU_HYPERSONIC_CUDA_NO_MAIN
 #include REF_SRC
+#include <vector>
+#ifdef REF_F32
+typedef float real_t;
+#else
+typedef double real_t;
+#endif
+static void up(real_t *dst, const double *src, size_t n) {
+  std::vector<real_t> t(n);
+  for (size_t i = 0; i < n; ++i) t[i] = (real_t)src[i];
+  CK(cudaMemcpy(dst, t.data(), n * sizeof(real_t), cudaMemcpyHostToDevice));
+}
+static void down(double *dst, const real_t *src, size_t n) {
+  std::vector<real_t> t(n);
+  CK(cudaMemcpy(t.data(), src, n * sizeof(real_t), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i) dst[i] = (double)t[i];
+}
 
 extern "C" void ref_hyp2d_dims(int *w, int *h) { *w = W; *h = H; }
 
@@ -47,26 +66,23 @@ extern "C" int ref_hyp2d_run(const double *cfg11, int steps, int tile_bx, int ti
   uint8_t *dMask = nullptr;
   CK(cudaMalloc(&dMask, (size_t)N));
   const int threads = 256;
-  const size_t reduceSharedBytes = (size_t)threads * sizeof(double);
+  const size_t reduceSharedBytes = (size_t)threads * sizeof(real_t);
   const int blocksN = (N + threads - 1) / threads;
   const int blocksXFaces = ((W + 1) * H + threads - 1) / threads;
   const int blocksYFaces = (W * (H + 1) + threads - 1) / threads;
   const dim3 tileBlock(tile_bx, tile_by);
   const dim3 grid((W + tile_bx - 1) / tile_bx, (H + tile_by - 1) / tile_by);
   const size_t cp = (size_t)(tile_bx + 2) * (tile_by + 2), cs = (size_t)(tile_bx + 4) * (tile_by + 4);
-  const size_t shmPredict = 4 * cp * sizeof(double) + cp, shmStep = 4 * cs * sizeof(double) + cs;
-  double *dMaxSpeed, *dBlockSpeedMax;
-  CK(cudaMalloc(&dMaxSpeed, sizeof(double)));
-  CK(cudaMalloc(&dBlockSpeedMax, (size_t)blocksN * sizeof(double)));
+  const size_t shmPredict = 4 * cp * sizeof(real_t) + cp, shmStep = 4 * cs * sizeof(real_t) + cs;
+  real_t *dMaxSpeed, *dBlockSpeedMax;
+  CK(cudaMalloc(&dMaxSpeed, sizeof(real_t)));
+  CK(cudaMalloc(&dBlockSpeedMax, (size_t)blocksN * sizeof(real_t)));
 
   if (do_init) {
     k_init<<<blocksN, threads>>>(dU, dMask);
     CK(cudaGetLastError());
   } else {
-    CK(cudaMemcpy(dU.rho, rho, (size_t)N * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dU.mx, mx, (size_t)N * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dU.my, my, (size_t)N * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(dU.E, E, (size_t)N * 8, cudaMemcpyHostToDevice));
+    up(dU.rho, rho, N); up(dU.mx, mx, N); up(dU.my, my, N); up(dU.E, E, N);
     CK(cudaMemcpy(dMask, mask, (size_t)N, cudaMemcpyHostToDevice));
   }
   CK(cudaDeviceSynchronize());
@@ -74,20 +90,20 @@ extern "C" int ref_hyp2d_run(const double *cfg11, int steps, int tile_bx, int ti
   cudaEvent_t ev0, ev1;
   cudaEventCreate(&ev0); cudaEventCreate(&ev1);
   cudaEventRecord(ev0);
-  double sim_t = 0.0;
+  real_t sim_t = 0;
   for (int k = 0; k < steps; k++) {
     k_apply_inflow_left<<<(H + threads - 1) / threads, threads>>>(dU, dMask);
     k_max_wavespeed_blocks<<<blocksN, threads, reduceSharedBytes>>>(dU, dMask, dBlockSpeedMax);
     k_reduce_block_max<<<1, threads, reduceSharedBytes>>>(dBlockSpeedMax, blocksN, dMaxSpeed);
-    double maxs = 1e-12;
-    CK(cudaMemcpy(&maxs, dMaxSpeed, sizeof(double), cudaMemcpyDeviceToHost));
-    if (!isfinite(maxs) || maxs < 1e-12) maxs = 1e-12;
-    double dt_convective = h_cfg.cfl * 1.0 / maxs;
-    double nu_max = fmax(h_cfg.visc_nu, fmax(h_cfg.visc_rho, h_cfg.visc_e));
-    double dt_diff = dt_convective;
-    if (isfinite(nu_max) && nu_max > 1e-12) dt_diff = 0.25 / nu_max;
-    double dt = fmin(dt_convective, dt_diff);
-    double half_dt = 0.5 * dt;
+    real_t maxs = (real_t)1e-12;
+    CK(cudaMemcpy(&maxs, dMaxSpeed, sizeof(real_t), cudaMemcpyDeviceToHost));
+    if (!isfinite(maxs) || maxs < (real_t)1e-12) maxs = (real_t)1e-12;
+    real_t dt_convective = h_cfg.cfl * (real_t)1.0 / maxs;
+    real_t nu_max = fmax(h_cfg.visc_nu, fmax(h_cfg.visc_rho, h_cfg.visc_e));
+    real_t dt_diff = dt_convective;
+    if (isfinite(nu_max) && nu_max > (real_t)1e-12) dt_diff = (real_t)0.25 / nu_max;
+    real_t dt = fmin(dt_convective, dt_diff);
+    real_t half_dt = (real_t)0.5 * dt;
     k_predict_face_states<<<grid, tileBlock, shmPredict>>>(dU, dMask, xL, xR, yL, yR, half_dt, half_dt);
     k_compute_xface_flux<<<blocksXFaces, threads>>>(dU, dMask, xL, xR, xF);
     k_compute_yface_flux<<<blocksYFaces, threads>>>(dU, dMask, yL, yR, yF);
@@ -100,10 +116,7 @@ extern "C" int ref_hyp2d_run(const double *cfg11, int steps, int tile_bx, int ti
   cudaEventRecord(ev1);
   e = cudaDeviceSynchronize();
   if (ms) cudaEventElapsedTime(ms, ev0, ev1);
-  CK(cudaMemcpy(rho, dU.rho, (size_t)N * 8, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(mx, dU.mx, (size_t)N * 8, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(my, dU.my, (size_t)N * 8, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(E, dU.E, (size_t)N * 8, cudaMemcpyDeviceToHost));
+  down(rho, dU.rho, N); down(mx, dU.mx, N); down(my, dU.my, N); down(E, dU.E, N);
   CK(cudaMemcpy(mask, dMask, (size_t)N, cudaMemcpyDeviceToHost));
   if (sim_t_out) *sim_t_out = sim_t;
   cudaFree(dMaxSpeed); cudaFree(dBlockSpeedMax); cudaFree(dMask);
@@ -112,6 +125,7 @@ extern "C" int ref_hyp2d_run(const double *cfg11, int steps, int tile_bx, int ti
   return (int)e;
 }
 
+#ifndef REF_F32
 // ---- device-helper evaluation for fixture generation (random-input vectors) --------------------
 __global__ void k_eval_hllc(const double *in, double *out, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,3 +222,4 @@ extern "C" int ref_hyp2d_render(const double *cfg11, int view_mode, const double
   free_Us(&dU);
   return (int)e;
 }
+#endif  // !REF_F32

@@ -171,6 +171,44 @@ def test_full_size_4096_vs_reference_kernels():
     assert float(out32[0].min()) > 0 and np.isfinite(out32[3]).all()
 
 
+@pytest.mark.skipif(not (oracle.has_ref("ref_hyp2d_4096x4096") and oracle.has_ref("ref_hyp2d_f32_4096x4096")),
+                    reason="oracle/_ref not built")
+def test_full_size_4096_developed_flow_vs_reference_kernels():
+    """BASELINE config 2 on a DEVELOPED flow (the bow shock exists: the state bench.py times): the fp64 handle develops
+    1500 steps from k_init; from that state the reference kernels (fp64), the float-typed reference and both product
+    handles advance another 100 steps.  fp64 handle: the north-star's 1e-5; fp32 handle: at most twice as far from the
+    fp64 reference as the float-typed reference is (per field, L-inf and L1 relative to the field's max)."""
+    W = H = 4096
+    dev, steps = 1500, 100
+    cfg = SimConfig.default(W, H)
+    cfg11 = oracle.hyp2d_cfg(W, H).as11()
+    s = Hypersonic2D(cfg, dtype="f64").init()
+    s.step(dev)
+    start, mask = s.download()
+    assert float(np.ptp(start[0])) > 5.0                      # a shock layer: rho jumps by more than a factor 6
+    ref, rmask, t_ref, _, _ = oracle.ref_hyp2d_run(W, H, cfg11, steps, planes=start, mask=mask)
+    s.step(steps)
+    out, _ = s.download()
+    s.close()
+    e64 = {k: rel_linf(a, b) for k, a, b in zip(NAMES, out, ref)}
+    r32, _, _, _, _ = oracle.ref_hyp2d_run(W, H, cfg11, steps, planes=start, mask=mask, f32=True)
+    s32 = Hypersonic2D(cfg, dtype="f32").upload(start, mask)
+    s32.step(steps)
+    out32, _ = s32.download()
+    s32.close()
+    e32 = {k: rel_linf(a, b) for k, a, b in zip(NAMES, out32, ref)}
+    eref = {k: rel_linf(a, b) for k, a, b in zip(NAMES, r32, ref)}
+    l1 = lambda a, b: float(np.abs(np.asarray(a, np.float64).ravel() - b).mean() / max(1.0, np.abs(b).max()))   # noqa: E731
+    l1_32 = {k: l1(a, b) for k, a, b in zip(NAMES, out32, ref)}
+    l1ref = {k: l1(a, b) for k, a, b in zip(NAMES, r32, ref)}
+    print(f"\n4096^2 developed flow +{steps} steps: f64 handle rel L-inf {e64}")
+    print(f"  f32 handle rel L-inf {e32} rel L1 {l1_32}\n  float-typed reference rel L-inf {eref} rel L1 {l1ref}")
+    for k in NAMES:
+        assert e64[k] < 1e-5, ("f64", k, e64[k])
+        assert e32[k] <= 2.0 * eref[k] + 1e-6, ("f32 L-inf vs float reference", k, e32[k], eref[k])
+        assert l1_32[k] <= 2.0 * l1ref[k] + 1e-8, ("f32 L1 vs float reference", k, l1_32[k], l1ref[k])
+
+
 @pytest.mark.skipif(not oracle.has_ref("ref_hyp2d_1024x512"), reason="oracle/_ref not built")
 def test_1000_steps_vs_reference_kernels():
     """BASELINE.json north_star: 'per-field L-inf error < 1e-5 vs the reference after 1000 steps'.
@@ -203,8 +241,20 @@ def test_1000_steps_vs_reference_kernels():
     assert abs(t - t_ref) < 1e-9
     for k in NAMES:
         assert l1_32[k] < 1e-4, ("f32 L1", k, l1_32[k])
-        assert np.isfinite(e32[k])
+        assert e32[k] < 2e-3, ("f32 L-inf", k, e32[k])          # measured 4-5e-4 (a few cells at the bow shock)
     assert abs(t32 - t_ref) < 1e-3 * t_ref
+    # The yardstick for fp32: the REFERENCE's own algorithm evaluated in fp32 (float-typed copy of the reference
+    # translation unit, oracle/gen_f32_src.py) against the same fp64 reference run.  It separates "fp32 rounding on a
+    # Mach-25 shock" from "what the product's fp32 path changes" (rcp.approx, closed-form limiter, merged HLLC guards,
+    # fused passes): the product may not be further from the fp64 reference than twice the float reference itself.
+    if oracle.has_ref(f"ref_hyp2d_f32_{W}x{H}"):
+        r32, _, tr32, _, _ = oracle.ref_hyp2d_run(W, H, cfg11, steps, f32=True)
+        eref = {k: rel_linf(a, b) for k, a, b in zip(NAMES, r32, ref)}
+        l1ref = {k: float(np.abs(a - b).mean() / max(1.0, np.abs(b).max())) for k, a, b in zip(NAMES, r32, ref)}
+        print(f"1000 steps {W}x{H}: float-typed REFERENCE rel L-inf {eref}  rel L1 {l1ref}  |t-t_ref|={abs(tr32 - t_ref):.3e}")
+        for k in NAMES:
+            assert e32[k] <= 2.0 * eref[k] + 1e-6, ("f32 L-inf vs float reference", k, e32[k], eref[k])
+            assert l1_32[k] <= 2.0 * l1ref[k] + 1e-8, ("f32 L1 vs float reference", k, l1_32[k], l1ref[k])
 
 
 def test_multi_step_call_equals_single_steps():

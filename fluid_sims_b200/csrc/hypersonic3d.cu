@@ -36,21 +36,13 @@ namespace {
 
 constexpr int T3_TX = 8, T3_TY = 8, T3_TZ = 4, T3_H = 3;
 constexpr int T3_SX = T3_TX + 2 * T3_H, T3_SY = T3_TY + 2 * T3_H, T3_SZ = T3_TZ + 2 * T3_H;
-// z-plane stride padded by 4 floats: with 14 x 14 planes of 196 floats every warp load of the face sweep is 2- to 3-way bank
-// conflicted whatever the visiting order (81 M conflicts per launch at 256^3, ncu); with 200 and the face order of
-// hypersonic3d_face_order.inc (scripts/gen_t3_face_order.py) a load by all 896 faces takes 30 wavefronts instead of 58 (minimum 28)
-constexpr int T3_SXY = T3_SX * T3_SY + 4, T3_SVOL = T3_SXY * T3_SZ;
+constexpr int T3_SXY = T3_SX * T3_SY, T3_SVOL = T3_SXY * T3_SZ;
 constexpr int T3_THREADS = T3_TX * T3_TY * T3_TZ;
 constexpr int T3_NFX = (T3_TX + 1) * T3_TY * T3_TZ;  // 288 = 9 warps
 constexpr int T3_NFY = T3_TX * (T3_TY + 1) * T3_TZ;  // 288
 constexpr int T3_NFZ = T3_TX * T3_TY * (T3_TZ + 1);  // 320
 constexpr int T3_NF = T3_NFX + T3_NFY + T3_NFZ;
 static_assert(T3_NFX % 32 == 0 && T3_NFY % 32 == 0 && T3_NFZ % 32 == 0, "one axis per warp");
-static_assert(T3_SX == 14 && T3_SXY == 200 && T3_NF == 896, "hypersonic3d_face_order.inc was generated for this layout");
-// thread-slot -> face: any order is valid (each face parks its flux at s_f[face]) as long as a warp stays on one axis
-__device__ const unsigned short t3_face_order[T3_NF] = {
-#include "hypersonic3d_face_order.inc"
-};
 
 constexpr float RHO_P_FLOOR = 1e-30f;  // tau_hypersonic_3d_cuda.cu:52-58
 constexpr float THERMAL_ENERGY_FLOOR = 1e-12f;
@@ -372,9 +364,8 @@ hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out,
   const int nxy = P.nx * P.ny;
 
   // ---- decode the halo tile to primitives (k_step :1019-1056) --------------------------------
-  for (int cc = tid; cc < T3_SX * T3_SY * T3_SZ; cc += T3_THREADS) {
-    const int lz = cc / (T3_SX * T3_SY), rem = cc - lz * (T3_SX * T3_SY), ly = rem / T3_SX, lx = rem - ly * T3_SX;
-    const int tt = lz * T3_SXY + ly * T3_SX + lx;
+  for (int tt = tid; tt < T3_SVOL; tt += T3_THREADS) {
+    const int lz = tt / T3_SXY, rem = tt - lz * T3_SXY, ly = rem / T3_SX, lx = rem - ly * T3_SX;
     const int gx = bx0 + lx - T3_H, gy = wrapi(by0 + ly - T3_H, P.ny), glz = bz0 + lz - T3_H;
     bool is_solid;
     const Q q = halo_prim(P, in, solid, gx, gy, glz, is_solid);
@@ -394,8 +385,7 @@ hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out,
   };
 
   // ---- every face of the tile once (k_step :1113-1264 evaluates each from both sides) ---------
-  for (int slot = tid; slot < T3_NF; slot += T3_THREADS) {
-    const int f = t3_face_order[slot];
+  for (int f = tid; f < T3_NF; f += T3_THREADS) {
     int axis, fx, fy, fz;  // (fx,fy,fz): tile coordinates of the cell on the PLUS side of the face
     if (f < T3_NFX) {
       axis = 0;
@@ -410,7 +400,7 @@ hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out,
       fx = g % T3_TX; fy = (g / T3_TX) % T3_TY; fz = g / (T3_TX * T3_TY);
     }
     const int stride = axis == 0 ? 1 : (axis == 1 ? T3_SX : T3_SXY);
-    const int jb = (fz + T3_H) * T3_SXY + (fy + T3_H) * T3_SX + (fx + T3_H);  // plus-side cell
+    const int jb = ((fz + T3_H) * T3_SY + (fy + T3_H)) * T3_SX + (fx + T3_H);  // plus-side cell
     const int ja = jb - stride;                                                // minus-side cell
     const bool sa = s_solid[ja] != 0, sb = s_solid[jb] != 0;
     Q L, R;
@@ -475,7 +465,7 @@ hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out,
       const int fxm = (tz * T3_TY + ty) * (T3_TX + 1) + tx, fxp = fxm + 1;
       const int fym = T3_NFX + (tz * (T3_TY + 1) + ty) * T3_TX + tx, fyp = fym + T3_TX;
       const int fzm = T3_NFX + T3_NFY + (tz * T3_TY + ty) * T3_TX + tx, fzp = fzm + T3_TX * T3_TY;
-      const int jc = (tz + T3_H) * T3_SXY + (ty + T3_H) * T3_SX + (tx + T3_H);
+      const int jc = ((tz + T3_H) * T3_SY + (ty + T3_H)) * T3_SX + (tx + T3_H);
       const Q q0 = load_q(jc);
       const C6 U0 = prim_to_cons(P, q0);
       float U1[6];

@@ -17,6 +17,8 @@ def test_slab_runs_match_single_gpu(tmp_path):
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 4 if n >= 4 else 2
+    if os.environ.get("TAU_TEST_WORLD"):          # e.g. 8 on a full box
+        world = min(n, int(os.environ["TAU_TEST_WORLD"]))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29533",
            os.path.join(ROOT, "tests", "_mgpu_worker.py"), str(tmp_path)]

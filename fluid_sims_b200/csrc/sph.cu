@@ -275,7 +275,7 @@ __device__ __forceinline__ float group_sum(float v) {
 // Neighbour sweep: the GROUP lanes of a group stride over the three contiguous slot ranges (one per
 // cell row) of a particle's 3x3 neighbourhood; `test` is the distance check (~35 % pass), `heavy`
 // the kernel / gradient evaluation.
-// (Tried on B200 and rejected, see profiles/sph_r1.md: compacting the hits through a ballot + shared
+// (Tried on B200 and rejected, see profiles/sph_r1_ncu_full_compaction_variant.txt: compacting the hits through a ballot + shared
 // queue so that `heavy` runs on full batches — the queue bookkeeping costs more instructions than
 // the predicated-off lanes it saves, both with 8-lane groups and with one particle per warp.)
 template <typename Test, typename Heavy>

@@ -51,7 +51,7 @@ def default_cfg(W, H, **over):
     return c
 
 
-def run(W, H, steps, dtype, planes=None, mask=None, seg_rows=None, pair=False, chunks=None, **over):
+def run(W, H, steps, dtype, planes=None, mask=None, seg_rows=None, pair=False, chunks=None, reinit_after=0, **over):
     """-> (planes, mask, sim_t, dts, launches) from the emulated product library"""
     L = lib()
     npdt = np.float32 if dtype == "f32" else np.float64
@@ -73,6 +73,9 @@ def run(W, H, steps, dtype, planes=None, mask=None, seg_rows=None, pair=False, c
         ptrs = (C.c_void_p * 4)(*[a.ctypes.data for a in arrs])
         m = None if mask is None else np.ascontiguousarray(mask, np.uint8).reshape(H, W)
         check(L.tau_hyp2d_upload(h, ptrs, C.c_void_p(m.ctypes.data if m is not None else 0)))
+    if reinit_after:      # a few steps, then tau_hyp2d_init again: every rotating counter must start over
+        check(L.tau_hyp2d_step(h, reinit_after))
+        check(L.tau_hyp2d_init(h))
     wi = (C.c_int * 6)()
     check(L.tau_hyp2d_work_items(h, wi))
     run.last_work_items = list(wi)

@@ -266,6 +266,19 @@ def test_hyp2d_pair_mode_declines_what_it_cannot_do(pretend_device):
         assert all(np.array_equal(x, y) for x, y in zip(a, b))
 
 
+@pytest.mark.parametrize("pair", [False, 1, 2])
+@pytest.mark.parametrize("after", [1, 2, 4])
+def test_hyp2d_reinit_after_a_few_steps_starts_every_rotating_counter_over(pretend_device, pair, after):
+    """tau_hyp2d_init cleared Ctrl and the step count but not the pair kernel's separately allocated claim
+    counters; re-initialising after 1, 4, 7 ... steps then made the first step claim from a stale counter and skip items.
+    A run that is re-initialised after `after` steps must equal a fresh run bit for bit (production, pair and fused modes)."""
+    pretend_device(3, 2)
+    W, H, steps = 308, 96, 5
+    a, _, ta, dtsa, _ = hyp2d_emu.run(W, H, steps, "f32", pair=pair, geom_x0=W / 3.0)
+    b, _, tb, dtsb, _ = hyp2d_emu.run(W, H, steps, "f32", pair=pair, reinit_after=after, geom_x0=W / 3.0)
+    assert ta == tb and np.array_equal(dtsa, dtsb) and all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
 # ---- 3-D hypersonic solver, default build (packed WENO5 pair) and the scalar form (-DT3_SCALAR_WENO) ----------
 import hyp3d_emu  # noqa: E402  (tests/hostemu)
 

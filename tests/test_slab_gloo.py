@@ -160,6 +160,25 @@ def test_hyp3d_z_slab_ring_reproduces_single_domain(world, tmp_path):
         assert tuple(np.load(tmp_path / f"c{r}.npy")) == tuple(np.float32(x) for x in ck)
 
 
+def test_partition_rows_cost_weighted():
+    """equal cost per slab instead of equal rows (bench.py at N > 1): contiguous, complete, >= 1 row each, and the slabs that
+    hold the costlier rows are shorter"""
+    from fluid_sims_b200.hypersonic2d import SimConfig
+    cfg = SimConfig.default(4096, 4096)
+    w = slab.hyp2d_row_costs(cfg)
+    assert len(w) == 4096 and min(w) == 1.0 and max(w) > 1.0
+    for parts in (2, 3, 4, 8):
+        p = slab.partition_rows(4096, parts, w)
+        assert p[0][0] == 0 and all(p[i][0] + p[i][1] == p[i + 1][0] for i in range(parts - 1)) and p[-1][0] + p[-1][1] == 4096
+        cost = [sum(w[b:b + c]) for b, c in p]
+        assert max(cost) - min(cost) <= 2.2 and min(c for _, c in p) >= 1
+    p8 = slab.partition_rows(4096, 8, w)
+    assert p8[3][1] < p8[0][1] and p8[4][1] < p8[7][1]
+    assert slab.partition_rows(10, 3, [1.0] * 10) == [(0, 3), (3, 3), (6, 4)]
+    assert slab.partition_rows(5, 5, [9, 1, 1, 1, 1]) == [(i, 1) for i in range(5)]
+    assert slab.partition_rows(4096, 1, w) == [(0, 4096)]
+
+
 def test_partition_rows():
     assert slab.partition_rows(4096, 8) == [(512 * i, 512) for i in range(8)]
     parts = slab.partition_rows(37, 3)

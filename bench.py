@@ -34,8 +34,9 @@ Definitions
            short run, N = 1 only.
   reference_gpu  the reference's own kernels (oracle/_ref, recompiled for sm_100a) timed on the same GPU on the
            same grid — a yardstick beside the CPU baseline, N = 1 only.
-  other_configs  BASELINE configs 3-5 (Gray-Scott 8192^2, 3-D hypersonic 256^3 at N = 1 / 512^3 z-slabs at N > 1,
-           SPH 2^21 particles), short runs of bench_all.py's benches, each with its roofline and reference_gpu.
+  other_configs  BASELINE configs 3-5 (Gray-Scott 8192^2, 3-D hypersonic 512^3 — z-slabs at N > 1 —,
+           SPH 2^21 particles), short runs of bench_all.py's benches, each with its roofline, reference_gpu (N = 1) and a
+           state_crc that is equal across N when the multi-GPU run is bit-identical to the single-GPU one.
 The working set (2 x 268 MB of state) is larger than the 126 MB L2, so no L2 flush is needed
 between timed steps.
 
@@ -101,6 +102,30 @@ def state_crc(torch, dist, planes_view, y0, hl, W, halo, world, dev):
     acc[1] %= P31
     vals = [int(v) for v in acc.flatten().tolist()]
     return f"{zlib.crc32(repr(vals).encode()) & 0xFFFFFFFF:08x}", vals
+
+
+def bind_to_gpu_numa_node(torch, dev):
+    """Pin this process (and therefore its first-touch pinned host buffers) to the CPU cores of the NUMA node the GPU hangs off:
+    at N > 1 every rank moves its slab over its own PCIe link, and a buffer on the other socket makes that traffic cross the
+    socket interconnect.  Returns a short description for the e2e record; does nothing where sysfs does not tell."""
+    try:
+        pr = torch.cuda.get_device_properties(dev)
+        bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        nodes = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()])
+        if node < 0 or nodes < 2:
+            return f"single NUMA node (gpu {bus}: node {node} of {nodes})"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return f"gpu {bus} on node {node} of {nodes}: no allowed core there"
+        os.sched_setaffinity(0, cpus)
+        return f"bound to NUMA node {node} of {nodes} ({len(cpus)} cores) for gpu {bus}"
+    except Exception as e:      # noqa: BLE001
+        return f"not bound ({type(e).__name__}: {e})"[:120]
 
 
 class ClockSampler:
@@ -368,6 +393,7 @@ def run_product(a):
     # ---- e2e: frames through the C-ABI with host buffers -------------------------------------
     e2e = None
     if not a.no_e2e:
+        numa = bind_to_gpu_numa_node(torch, dev) if (world > 1 and not a.no_numa_bind) else None
         np_dt = np.float32 if a.dtype == "f32" else np.float64
         host_in = [torch.empty((hl, W), dtype=tdt).pin_memory() for _ in range(4)]
         planes, _ = sim.download()
@@ -472,6 +498,7 @@ def run_product(a):
                "frames_in_flight": a.e2e_lanes if (pipelined or (a.e2e_peers_async and a.exchange == "peer")) else 1,
                "ms_per_frame": dt_wall / a.e2e_frames * 1e3}
         if world > 1:
+            e2e["host_buffers"] = numa
             e2e["handover"] = "device" if (a.e2e_peers_async and a.exchange == "peer") else "host"
             if a.e2e_peers_async and a.exchange == "peer":
                 for sb, _, _ in lanes[1:]:      # the extra lanes' peer mappings go before their planes do
@@ -543,7 +570,8 @@ def run_product(a):
     if not a.no_other:
         other = {}
         import bench_all
-        ba = bench_all.default_args(steps=200, n3=256 if world == 1 else 512, steps3=20, warm3=30, steps_sph=30)
+        # config 4 is 512^3 at every N (6.4 GB on one GPU), so that the lines' state_crc can be compared across N
+        ba = bench_all.default_args(steps=200, n3=512, steps3=12, warm3=20, steps_sph=30)
         for name in (("gs",) if world == 1 else ()) + ("hyp3d", "sph"):
             try:
                 rec = bench_all.BENCHES[name](ba)
@@ -587,6 +615,7 @@ def main():
     ap.add_argument("--cost-weighted-slabs", action="store_true",
                     help="N>1: rows partitioned by estimated cost instead of equally (results are identical either way; measured: "
                          "no gain — 0.08676 vs 0.08679 ms/step at N = 8 — the per-rank busy times even out but the step does not shorten)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N>1 e2e: do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the fp64-handle and reference-kernel sub-records (N=1)")

@@ -33,6 +33,25 @@ def peak():
         return 6650.0
 
 
+P31 = (1 << 31) - 1
+
+
+def crc_hex(vals):
+    import zlib
+    return f"{zlib.crc32(repr([int(v) for v in vals]).encode()) & 0xFFFFFFFF:08x}"
+
+
+def particles_crc(ids, pos, vel):
+    """order-independent checksum of a particle set keyed by global id: partial sums add across ranks"""
+    import numpy as np
+    w = (ids.astype(np.int64) % 65521) + 1
+    out = []
+    for arr in (pos, vel):
+        bits = np.ascontiguousarray(arr, np.float32).view(np.uint32).astype(np.int64)
+        out += [int(((bits[:, 0] * w) % P31).sum()), int(((bits[:, 1] * (w + 7)) % P31).sum())]
+    return out
+
+
 def bench_gs(a):
     import oracle
     from fluid_sims_b200.gray_scott import GrayScott, Params
@@ -119,10 +138,24 @@ def bench_hyp3d(a):
         t = torch.tensor([ms], device=f"cuda:{local}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    # checksum of the owned planes (weights by global cell index): equal across N <=> the z-slab ring is bit-identical
+    pp, _ = sim.device_state()
+    v = slab.wrap_plane(pp, (6, nl + 2 * HALO, n, n), torch.float32, local)[:, HALO:HALO + nl]
+    bits = v.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    gz = torch.arange(z0, z0 + nl, device=bits.device, dtype=torch.int64).view(1, nl, 1, 1)
+    gy = torch.arange(n, device=bits.device, dtype=torch.int64).view(1, 1, n, 1)
+    gx = torch.arange(n, device=bits.device, dtype=torch.int64).view(1, 1, 1, n)
+    wgt = ((gz * n + gy) * n + gx) % 65521 + 1
+    acc = torch.stack([bits.sum(dim=(1, 2, 3)), ((bits * wgt).sum(dim=3) % P31).sum(dim=(1, 2))])
+    if world > 1:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+    acc[1] %= P31
+    crc = crc_hex(acc.flatten().tolist())
+    del v, bits, wgt
     cells = n ** 3
     ach = 49 * (cells / world) / (ms * 1e-3) / 1e9
     ref = None
-    if world == 1 and oracle.has_ref("ref_hyp3d") and n <= 256:
+    if world == 1 and oracle.has_ref("ref_hyp3d") and n <= 512:
         op = oracle.hyp3d_params(n, n, n)
         *_, rms = oracle.ref_hyp3d_run(op, a.steps3, clock=(5e-3, 2e-3))
         ref = rms / a.steps3
@@ -137,7 +170,8 @@ def bench_hyp3d(a):
                                             "value": cells / (ref * 1e-3) / 1e6 if ref else None,
                                             "what": "tau_hypersonic_3d_cuda.cu k_step recompiled for "
                                                     "sm_100a incl. its 2 blocking 4-byte copies per step"},
-                          "clock": sim.clock(), "parallelism": f"z-slab ring x{world}"})
+                          "clock": sim.clock(), "state_crc": crc, "steps_from_init": a.warm3 + a.steps3,
+                          "parallelism": f"z-slab ring x{world}"})
     return None
 
 
@@ -190,6 +224,17 @@ def bench_sph(a):
         ms = float(t.item())
         stripes = [None] * world
         dist.all_gather_object(stripes, s.status())
+    import numpy as np
+    if world == 1:
+        pos, vel, _, _ = s.download()
+        part = particles_crc(np.arange(N, dtype=np.uint32), pos, vel)
+    else:
+        ids, pos, vel, _, _ = s.download_local()
+        part = particles_crc(ids, pos, vel)
+        t = torch.tensor(part, device=f"cuda:{local}", dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        part = [int(x) for x in t.tolist()]
+    crc = crc_hex([x % P31 for x in part])
     ref = None
     if world == 1 and oracle.has_ref("ref_sph"):
         pos0, vel0 = reset_particles(P)
@@ -211,6 +256,7 @@ def bench_sph(a):
                                           "hash-bin stripes x%d, ghost-row + migrant exchange by NCCL send/recv" % world),
                           **({"stripes": [{k: x[k] for k in ("n_own", "n_ghost", "err", "max_send", "row_begin", "row_end")}
                                           for x in stripes]} if stripes else {}),
+                          "state_crc": crc, "substeps_from_init": 5 + a.steps_sph,
                           "gpu_launches": s.launch_count})
     return None
 

@@ -211,9 +211,12 @@ def bench_sph(a):
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    import time
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    w0 = time.perf_counter()
     advance(a.steps_sph)
+    host_ms = (time.perf_counter() - w0) * 1e3 / a.steps_sph     # time the host needs to ENQUEUE a sub-step
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps_sph
@@ -256,7 +259,7 @@ def bench_sph(a):
                                           "hash-bin stripes x%d, ghost-row + migrant exchange by NCCL send/recv" % world),
                           **({"stripes": [{k: x[k] for k in ("n_own", "n_ghost", "err", "max_send", "row_begin", "row_end")}
                                           for x in stripes]} if stripes else {}),
-                          "state_crc": crc, "substeps_from_init": 5 + a.steps_sph,
+                          "state_crc": crc, "substeps_from_init": 5 + a.steps_sph, "host_enqueue_ms_per_substep": host_ms,
                           "gpu_launches": s.launch_count})
     return None
 

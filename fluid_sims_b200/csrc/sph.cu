@@ -291,37 +291,6 @@ __device__ __forceinline__ void neighbour_sweep(const int *__restrict__ cellStar
       if (test(j)) heavy(j);
   }
 }
-// The same sweep in two phases per lane: candidates that pass `test` are queued (per-lane FIFO in shared memory, one bank
-// per thread: conflict-free whatever the fill levels), then `heavy` runs over the queue.  In neighbour_sweep a warp executes
-// `heavy` in practically every iteration with ~35 % of its lanes active (ncu: 19.7 of 32 threads per instruction in the force
-// kernel); here the heavy loop runs max-over-lanes(queue length) times — ~19 instead of ~36 iterations at 290 candidates per
-// particle.  Each lane still visits ITS candidates in the same order, so every partial sum is bit-identical to
-// neighbour_sweep's (the CPU oracle and the stripe shards rely on that order).
-constexpr int SWEEP_QCAP = 32;  // queue entries per lane; a full queue is drained on the spot
-template <typename Test, typename Heavy>
-__device__ __forceinline__ void neighbour_sweep_queued(const int *__restrict__ cellStart, const Consts &c, int gx, int gy, int g,
-                                                       int *__restrict__ queue /* this thread's column, stride blockDim.x */,
-                                                       Test test, Heavy heavy) {
-  const int cxl = max(gx - 1, 0), cxr = min(gx + 1, c.Gx - 1);
-  const int qs = blockDim.x;
-  int n = 0;
-#pragma unroll
-  for (int oy = -1; oy <= 1; ++oy) {
-    const int cy = gy + oy;
-    if ((unsigned)cy >= (unsigned)c.Gy) continue;
-    const int end = cellStart[cy * c.Gx + cxr + 1];
-    for (int j = cellStart[cy * c.Gx + cxl] + g; j < end; j += GROUP) {
-      if (test(j)) {
-        queue[n * qs] = j;
-        if (++n == SWEEP_QCAP) {
-          for (int e = 0; e < SWEEP_QCAP; ++e) heavy(queue[e * qs]);
-          n = 0;
-        }
-      }
-    }
-  }
-  for (int e = 0; e < n; ++e) heavy(queue[e * qs]);
-}
 // the same sweep with an unconditional body (see W_cubic_sel)
 template <typename Body>
 __device__ __forceinline__ void neighbour_sweep_all(const int *__restrict__ cellStart, const Consts &c,
@@ -391,13 +360,13 @@ sph_forces_integrate(const float2 *__restrict__ sxy, const float2 *__restrict__ 
   const float inv_h = rcp_approx(c.h);
   const float eta2 = 0.01f * c.h * c.h, visc_c = -c.viscAlpha * c.c0;  // loop invariants of :247-249
   float ax = 0.f, ay = 0.f;
-  __shared__ int s_queue[SWEEP_QCAP * 256];
   if (valid) {
     // (the branch-free form of the density sweep does not pay here: measured +9 % instructions —
     // the pair test skips three dependent loads and two divisions for the 65 % of pairs outside
-    // the support; round 2: test and evaluation in two phases, see neighbour_sweep_queued)
-    neighbour_sweep_queued(
-        cellStart, c, gx, gy, g, s_queue + threadIdx.x,
+    // the support whenever a whole warp iteration misses, which the ragged ends of the 8-lane
+    // groups make common enough)
+    neighbour_sweep(
+        cellStart, c, gx, gy, g,
         [&](int j) {
           const float2 xj = sxy[j];
           const float rx = xi.x - xj.x, ry = xi.y - xj.y;
@@ -474,10 +443,9 @@ sph_xsph(const float2 *__restrict__ sxy_new, const float2 *__restrict__ svel_new
   const int gx = grid_c(xi.x, c.cell, c.Gx), gy = grid_c(xi.y, c.cell, c.Gy);
   const float twoh = 2.f * c.h, twoh2 = twoh * twoh;
   float dx = 0.f, dy = 0.f;
-  __shared__ int s_queue[SWEEP_QCAP * 256];
   if (valid) {
-    neighbour_sweep_queued(
-        cellStart, c, gx, gy, g, s_queue + threadIdx.x,
+    neighbour_sweep(
+        cellStart, c, gx, gy, g,
         [&](int j) {
           const float2 xj = sxy_new[j];
           const float rx = xi.x - xj.x, ry = xi.y - xj.y;

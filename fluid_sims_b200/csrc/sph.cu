@@ -35,11 +35,19 @@ namespace {
 
 constexpr int SORT_WARPS = 8;            // warps per CTA in the sort kernels
 constexpr int SORT_SEG = 1024;           // keys per warp segment
-constexpr int SORT_MAX_BITS = 9;         // digit width upper bound (512 bins)
+constexpr int SORT_MAX_BITS = 10;        // digit width upper bound (1024 bins: the 2^21-particle case sorts 20-bit keys in two passes)
 constexpr int GROUP = 8;                 // lanes cooperating on one particle
+// Sort-key columns per grid cell.  The reference's cell (edge 2h = the support radius, :512-540) makes the 3x3 search
+// visit 9 cells = 36 h^2 for a support disc of 4 pi h^2: 35 % of the candidates pass the distance test.  The key keeps the
+// reference's rows but cuts every cell into SUBX columns: a row of the neighbourhood is still ONE contiguous slot range,
+// now SUBX key columns either side of the particle's own — (2 SUBX + 1) / SUBX = 2.25 cells wide instead of 3, 25 % fewer
+// candidates.  SUBX is a power of two: x / (cell / SUBX) == SUBX * (x / cell) exactly, so key column >> log2(SUBX) IS the
+// reference's grid_x (:141-148) and the order is a refinement of the reference's cell order.
+constexpr int SUBX = 4;
 
 struct Consts {
-  int N, Gx, Gy;
+  int N, Gx, Gy;   // Gx = KEY columns per row (SUBX per grid cell), Gy = grid rows
+  float cellx;     // width of a key column = cell / SUBX
   float cell, mass, h, rho0, c0, gammaEOS, viscAlpha, gx, gy, boxX, boxY, alpha, xsphEps;
   int useVisc, useGrav;
   int k_begin, k_end;   // slots this launch works on (single GPU: [0, N))
@@ -123,7 +131,7 @@ __global__ void sph_keys(const float2 *__restrict__ pos, unsigned *__restrict__ 
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c.N) return;
   const float2 p = pos[i];
-  keys[i] = (unsigned)(grid_c(p.y, c.cell, c.Gy) * c.Gx + grid_c(p.x, c.cell, c.Gx));
+  keys[i] = (unsigned)(grid_c(p.y, c.cell, c.Gy) * c.Gx + grid_c(p.x, c.cellx, c.Gx));
   vals[i] = (unsigned)i;
 }
 
@@ -256,14 +264,16 @@ __global__ void sph_cell_start(const unsigned *__restrict__ keys, int *__restric
   }
   cellStart[c] = lo;
 }
+// (the force sweep reads position AND velocity of a candidate: one 16-byte record per slot, one address, one load)
 __global__ void sph_gather(const unsigned *__restrict__ vals, const float2 *__restrict__ pos,
                            const float2 *__restrict__ vel, float2 *__restrict__ sxy,
-                           float2 *__restrict__ svel, int n) {
+                           float4 *__restrict__ spv, int n) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const unsigned i = vals[k];
-  sxy[k] = pos[i];
-  svel[k] = vel[i];
+  const float2 x = pos[i], v = vel[i];
+  sxy[k] = x;
+  spv[k] = make_float4(x.x, x.y, v.x, v.y);
 }
 
 __device__ __forceinline__ float group_sum(float v) {
@@ -281,7 +291,7 @@ __device__ __forceinline__ float group_sum(float v) {
 template <typename Test, typename Heavy>
 __device__ __forceinline__ void neighbour_sweep(const int *__restrict__ cellStart, const Consts &c,
                                                 int gx, int gy, int g, Test test, Heavy heavy) {
-  const int cxl = max(gx - 1, 0), cxr = min(gx + 1, c.Gx - 1);
+  const int cxl = max(gx - SUBX, 0), cxr = min(gx + SUBX, c.Gx - 1);
 #pragma unroll
   for (int oy = -1; oy <= 1; ++oy) {
     const int cy = gy + oy;
@@ -295,7 +305,7 @@ __device__ __forceinline__ void neighbour_sweep(const int *__restrict__ cellStar
 template <typename Body>
 __device__ __forceinline__ void neighbour_sweep_all(const int *__restrict__ cellStart, const Consts &c,
                                                     int gx, int gy, int g, Body body) {
-  const int cxl = max(gx - 1, 0), cxr = min(gx + 1, c.Gx - 1);
+  const int cxl = max(gx - SUBX, 0), cxr = min(gx + SUBX, c.Gx - 1);
 #pragma unroll
   for (int oy = -1; oy <= 1; ++oy) {
     const int cy = gy + oy;
@@ -315,7 +325,7 @@ sph_density(const float2 *__restrict__ sxy, const unsigned *__restrict__ vals,
   const int k = (range ? range[0] : 0) + (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
   const bool valid = k < (range ? range[1] : c.N);
   const float2 xi = sxy[valid ? k : 0];
-  const int gx = grid_c(xi.x, c.cell, c.Gx), gy = grid_c(xi.y, c.cell, c.Gy);
+  const int gx = grid_c(xi.x, c.cellx, c.Gx), gy = grid_c(xi.y, c.cell, c.Gy);
   const float inv_h = rcp_approx(c.h);
   float rho = 0.f;
   if (valid) {
@@ -342,9 +352,40 @@ sph_density(const float2 *__restrict__ sxy, const unsigned *__restrict__ vals,
 }
 
 // ---- forces (k_forces_cell :215-272) + symplectic-Euler integration (k_integrate :324-355) ------------
+// gradW_cubic :118-133 for a pair the caller has already tested (1e-16 < r^2 < 4h^2): the reference's own range test on r
+// (it can still fire by one rounding of the square root) becomes a select on dW/dr instead of a branch around the body;
+// a pair it rejects contributes an exact +-0 to both sums, which leaves them unchanged.
+__device__ __forceinline__ float2 gradW_cubic_sel(float2 rij, float r, float h, float inv_h, float alpha) {
+  const float q = r * inv_h;
+  float dWdq;
+  if (q < 1.0f) dWdq = alpha * (-3.0f * q + 2.25f * q * q);
+  else {
+    const float t = 2.0f - q;
+    dWdq = alpha * (-0.75f * t * t);
+  }
+  const float invr = 1.0f / r;
+  float dWdr = dWdq * inv_h;
+  if (r <= 1e-8f || r >= 2.0f * h) dWdr = 0.f;
+  return make_float2(dWdr * rij.x * invr, dWdr * rij.y * invr);
+}
+// the sweep of neighbour_sweep with the candidate's record loaded once and handed to both halves
+template <typename Load, typename Test, typename Heavy>
+__device__ __forceinline__ void neighbour_sweep_rec(const int *__restrict__ cellStart, const Consts &c, int gx, int gy, int g,
+                                                    Load load, Test test, Heavy heavy) {
+  const int cxl = max(gx - SUBX, 0), cxr = min(gx + SUBX, c.Gx - 1);
+#pragma unroll
+  for (int oy = -1; oy <= 1; ++oy) {
+    const int cy = gy + oy;
+    if ((unsigned)cy >= (unsigned)c.Gy) continue;
+    const int end = cellStart[cy * c.Gx + cxr + 1];
+    for (int j = cellStart[cy * c.Gx + cxl] + g; j < end; j += GROUP) {
+      const auto rec = load(j);
+      if (test(rec)) heavy(j, rec);
+    }
+  }
+}
 __global__ void __launch_bounds__(256)
-sph_forces_integrate(const float2 *__restrict__ sxy, const float2 *__restrict__ svel,
-                     const float2 *__restrict__ srp, const unsigned *__restrict__ vals,
+sph_forces_integrate(const float4 *__restrict__ spv, const float2 *__restrict__ srp, const unsigned *__restrict__ vals,
                      const int *__restrict__ cellStart, float2 *__restrict__ pos, float2 *__restrict__ vel, float2 *__restrict__ acc,
                      float2 *__restrict__ sxy_new, float2 *__restrict__ svel_new, float dt, Consts c,
                      const int *__restrict__ range) {
@@ -353,39 +394,37 @@ sph_forces_integrate(const float2 *__restrict__ sxy, const float2 *__restrict__ 
   const int k = (range ? range[0] : c.k_begin) + (blockIdx.x * blockDim.x + threadIdx.x) / GROUP;
   const bool valid = k < (range ? range[1] : c.k_end);
   const int kk = valid ? k : 0;
-  const float2 xi = sxy[kk], vi = svel[kk], rpi = srp[kk];
+  const float4 pvi = spv[kk];
+  const float2 xi = make_float2(pvi.x, pvi.y), vi = make_float2(pvi.z, pvi.w), rpi = srp[kk];
   const float rhoi = rpi.x, pri = rpi.y;
-  const int gx = grid_c(xi.x, c.cell, c.Gx), gy = grid_c(xi.y, c.cell, c.Gy);
+  const int gx = grid_c(xi.x, c.cellx, c.Gx), gy = grid_c(xi.y, c.cell, c.Gy);
   const float twoh = 2.f * c.h, twoh2 = twoh * twoh;
   const float inv_h = rcp_approx(c.h);
   const float eta2 = 0.01f * c.h * c.h, visc_c = -c.viscAlpha * c.c0;  // loop invariants of :247-249
   float ax = 0.f, ay = 0.f;
   if (valid) {
     // (the branch-free form of the density sweep does not pay here: measured +9 % instructions —
-    // the pair test skips three dependent loads and two divisions for the 65 % of pairs outside
+    // the pair test skips two dependent loads and two divisions for the 65 % of pairs outside
     // the support whenever a whole warp iteration misses, which the ragged ends of the 8-lane
-    // groups make common enough)
-    neighbour_sweep(
-        cellStart, c, gx, gy, g,
-        [&](int j) {
-          const float2 xj = sxy[j];
-          const float rx = xi.x - xj.x, ry = xi.y - xj.y;
+    // groups make common enough.  The reference's `j != i` (:232) is implied by its r^2 <= 1e-16 test.)
+    neighbour_sweep_rec(
+        cellStart, c, gx, gy, g, [&](int j) { return spv[j]; },
+        [&](const float4 &pj) {
+          const float rx = xi.x - pj.x, ry = xi.y - pj.y;
           const float r2 = rx * rx + ry * ry;
-          return (j != k) && !(r2 >= twoh2 || r2 <= 1e-16f);
+          return !(r2 >= twoh2 || r2 <= 1e-16f);
         },
-        [&](int j) {
-          const float2 xj = sxy[j];
-          const float2 rij = make_float2(xi.x - xj.x, xi.y - xj.y);
+        [&](int j, const float4 &pj) {
+          const float2 rij = make_float2(xi.x - pj.x, xi.y - pj.y);
           const float r2 = rij.x * rij.x + rij.y * rij.y;
           const float r = sqrtf(r2);
-          const float2 gW = gradW_cubic_h(rij, r, c.h, inv_h, c.alpha);
+          const float2 gW = gradW_cubic_sel(rij, r, c.h, inv_h, c.alpha);
           const float2 rpj = srp[j];
           const float common = -c.mass * (pri + rpj.y);
           ax += common * gW.x;
           ay += common * gW.y;
           if (c.useVisc) {
-            const float2 vj = svel[j];
-            const float vx = vi.x - vj.x, vy = vi.y - vj.y;
+            const float vx = vi.x - pj.z, vy = vi.y - pj.w;
             const float dot = vx * rij.x + vy * rij.y;
             if (dot < 0.f) {
               const float mu = (c.h * dot) / (r2 + eta2);
@@ -440,7 +479,7 @@ sph_xsph(const float2 *__restrict__ sxy_new, const float2 *__restrict__ svel_new
   const int kk = valid ? k : 0;
   const float2 xi = sxy_new[kk], vi = svel_new[kk];
   const float rhoi = srp[kk].x;
-  const int gx = grid_c(xi.x, c.cell, c.Gx), gy = grid_c(xi.y, c.cell, c.Gy);
+  const int gx = grid_c(xi.x, c.cellx, c.Gx), gy = grid_c(xi.y, c.cell, c.Gy);
   const float twoh = 2.f * c.h, twoh2 = twoh * twoh;
   float dx = 0.f, dy = 0.f;
   if (valid) {
@@ -564,7 +603,8 @@ struct tau_sph {
   float *s, *press;
   // sorted-order scratch
   unsigned *keys[2], *vals[2], *hist, *scan_totals;
-  float2 *sxy, *svel, *srp, *sxy_new, *svel_new;
+  float2 *sxy, *srp, *sxy_new, *svel_new;
+  float4 *spv;  // sorted (x, y, vx, vy) records
   int *cellStart, *winner;
   int sorted_buf;  // which keys/vals buffer holds the last sort result
   // multi-GPU sharding (replicated state): this rank integrates slots [rank*chunk, ...)
@@ -575,7 +615,7 @@ struct tau_sph {
   size_t grid2_cap;
   // derived constants (:573-578, ensure_cell_buffers :512-540)
   float mass, h, cell, alpha;
-  int Gx, Gy, M, key_bits, nwarps;
+  int Gx, Gy, Gxk, M, key_bits, nwarps;  // Gx x Gy: the reference's grid; Gxk = Gx * SUBX key columns; M = Gxk * Gy keys
   // host step control (:663-722)
   float t, tau, rain_carry;
   long long step, substeps, launches;
@@ -588,7 +628,8 @@ namespace {
 Consts make_consts(const tau_sph *h) {
   Consts c;
   c.N = h->p.N;
-  c.Gx = h->Gx;
+  c.Gx = h->Gxk;
+  c.cellx = h->cell / SUBX;
   c.Gy = h->Gy;
   c.cell = h->cell;
   c.mass = h->mass;
@@ -649,13 +690,13 @@ int substep_compute(tau_sph *h, float dt_sub) {
   const int sb = radix_sort(h);
   h->sorted_buf = sb;
   sph_cell_start<<<(h->M + 1 + BS - 1) / BS, BS, 0, h->stream>>>(h->keys[sb], h->cellStart, n, h->M);
-  sph_gather<<<GS, BS, 0, h->stream>>>(h->vals[sb], h->pos, h->vel, h->sxy, h->svel, n);
+  sph_gather<<<GS, BS, 0, h->stream>>>(h->vals[sb], h->pos, h->vel, h->sxy, h->spv, n);
   const int GSall = (int)(((size_t)n * GROUP + BS - 1) / BS);
   if (sharded) {
     c.k_begin = h->rank * h->chunk;
     c.k_end = min(n, c.k_begin + h->chunk);
     c.write_state = 0;
-    sph_ghost_range<<<1, 32, 0, h->stream>>>(h->keys[sb], h->cellStart, h->range, c.k_begin, c.k_end, h->Gx,
+    sph_ghost_range<<<1, 32, 0, h->stream>>>(h->keys[sb], h->cellStart, h->range, c.k_begin, c.k_end, h->Gxk,
                                              h->Gy);
     h->launches++;
   }
@@ -663,7 +704,7 @@ int substep_compute(tau_sph *h, float dt_sub) {
                                            sharded ? h->range : nullptr, c);
   const bool xsph = h->p.useXSPH && h->p.xsphEps > 0.f;
   const int GSown = (int)(((size_t)(c.k_end - c.k_begin) * GROUP + BS - 1) / BS);
-  sph_forces_integrate<<<GSown, BS, 0, h->stream>>>(h->sxy, h->svel, h->srp, h->vals[sb], h->cellStart,
+  sph_forces_integrate<<<GSown, BS, 0, h->stream>>>(h->spv, h->srp, h->vals[sb], h->cellStart,
                                                     h->pos, h->vel, h->acc,
                                                     (xsph || sharded) ? h->sxy_new : nullptr,
                                                     (xsph || sharded) ? h->svel_new : nullptr, dt_sub, c, nullptr);
@@ -792,7 +833,8 @@ int tau_sph_create(const tau_sph_params *p, int device, void *stream, tau_sph **
   h->Gy = (int)ceilf(p->boxY / h->cell);
   if (h->Gx < 1) h->Gx = 1;
   if (h->Gy < 1) h->Gy = 1;
-  h->M = h->Gx * h->Gy;
+  h->Gxk = h->Gx * SUBX;
+  h->M = h->Gxk * h->Gy;
   h->key_bits = 1;
   while ((1 << h->key_bits) < h->M) h->key_bits++;
   h->nwarps = (p->N + SORT_SEG - 1) / SORT_SEG;
@@ -810,7 +852,7 @@ int tau_sph_create(const tau_sph_params *p, int device, void *stream, tau_sph **
   TAU_CUDA(cudaMalloc(&h->scan_totals,
                       (((size_t)(1 << SORT_MAX_BITS) * h->nwarps + SCAN_TILE - 1) / SCAN_TILE + 1) * sizeof(unsigned)));
   TAU_CUDA(cudaMalloc(&h->sxy, n * sizeof(float2)));
-  TAU_CUDA(cudaMalloc(&h->svel, n * sizeof(float2)));
+  TAU_CUDA(cudaMalloc(&h->spv, n * sizeof(float4)));
   TAU_CUDA(cudaMalloc(&h->srp, n * sizeof(float2)));
   TAU_CUDA(cudaMalloc(&h->sxy_new, (n + 64) * sizeof(float2)));   // + padding: all-gather chunks
   TAU_CUDA(cudaMalloc(&h->svel_new, (n + 64) * sizeof(float2)));
@@ -1023,6 +1065,12 @@ int tau_sph_grid(tau_sph *h, int *Gx, int *Gy, float *cell, float *hh, float *ma
   if (mass) *mass = h->mass;
   return TAU_OK;
 }
+// key columns per grid cell (SUBX): the sort key of a particle is row * (Gx * subx) + key column, and
+// key column / subx is the reference's grid_x
+int tau_sph_subx(tau_sph *h) {
+  (void)h;
+  return SUBX;
+}
 
 int tau_sph_sync(tau_sph *h) {
   TAU_REQUIRE(h, "tau_sph_sync: null handle");
@@ -1045,7 +1093,7 @@ int tau_sph_destroy(tau_sph *h) {
   if (!h) return TAU_OK;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  void *ptrs[] = {h->grid2, h->range, h->winner, h->cellStart, h->svel_new, h->sxy_new, h->srp, h->svel, h->sxy,
+  void *ptrs[] = {h->grid2, h->range, h->winner, h->cellStart, h->svel_new, h->sxy_new, h->srp, h->spv, h->sxy,
                   h->scan_totals, h->hist, h->vals[1], h->keys[1], h->vals[0], h->keys[0], h->press, h->s, h->acc,
                   h->vel, h->pos};
   for (void *p : ptrs) cudaFree(p);

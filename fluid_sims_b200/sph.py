@@ -41,6 +41,7 @@ _rasterize = declare("tau_sph_rasterize", [_h, C.c_int, C.c_int, np.ctypeslib.nd
 _sort_pairs = declare("tau_sph_sort_pairs", [_h, _u32, _u32, _u32])
 _grid = declare("tau_sph_grid", [_h, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_float),
                                  C.POINTER(C.c_float), C.POINTER(C.c_float)])
+_subx = declare("tau_sph_subx", [_h])
 _sync = declare("tau_sph_sync", [_h])
 _substeps = declare("tau_sph_substeps_done", [_h], C.c_longlong)
 _launches = declare("tau_sph_launch_count", [_h], C.c_longlong)
@@ -163,7 +164,7 @@ class SPH:
         gx, gy = C.c_int(), C.c_int()
         cell, h, m = C.c_float(), C.c_float(), C.c_float()
         check(_grid(self._handle, C.byref(gx), C.byref(gy), C.byref(cell), C.byref(h), C.byref(m)))
-        return dict(Gx=gx.value, Gy=gy.value, cell=cell.value, h=h.value, mass=m.value)
+        return dict(Gx=gx.value, Gy=gy.value, cell=cell.value, h=h.value, mass=m.value, subx=int(_subx(self._handle)))
 
     def sync(self):
         check(_sync(self._handle))

@@ -311,12 +311,16 @@ int tau_sph_download(tau_sph *h, float *pos_xy, float *vel_xy, float *s, float *
 /* render pass of the frame loop :747-755 (k_clear_grid + k_rasterize :357-374 + D2H): particle
  * counts on the terminal's half-block raster, grid2[sy * W + cx], sy in [0, 2H), y flipped */
 int tau_sph_rasterize(tau_sph *h, int W, int H, int *grid2);
-/* (cell key, particle index) pairs of the last sub-step's radix sort, in sorted order */
+/* (sort key, particle index) pairs of the last sub-step's radix sort, in sorted order.  key = grid row * (Gx * subx) +
+ * key column, where subx = tau_sph_subx() key columns cut each grid cell (the reference's cell, edge 2h) so that a
+ * neighbourhood row is a narrower slot range; key column / subx is the reference's grid_x (:141-148) exactly, i.e. the
+ * order refines the reference's cell order */
 int tau_sph_download_sort(tau_sph *h, unsigned *keys, unsigned *vals);
 /* the sort on its own: N keys (< number of cells rounded up to a power of two) -> sorted keys and
  * the stable permutation */
 int tau_sph_sort_pairs(tau_sph *h, const unsigned *keys_in, unsigned *keys_out, unsigned *vals_out);
 int tau_sph_grid(tau_sph *h, int *Gx, int *Gy, float *cell, float *hh, float *mass);
+int tau_sph_subx(tau_sph *h);
 int tau_sph_sync(tau_sph *h);
 long long tau_sph_substeps_done(tau_sph *h);
 long long tau_sph_launch_count(tau_sph *h);

@@ -383,6 +383,9 @@ def test_sph_product_code_equals_oracle(N, frames, over):
     assert np.abs(s - es).max() < 1e-5 and np.abs(pr - epr).max() < 1e-5      # measured 1-2e-6
     assert t.value == ck.t and st.value == ck.step
     assert np.all(np.diff(k.astype(np.int64)) >= 0) and np.array_equal(np.sort(v), np.arange(N, dtype=np.uint32))
+    key_of = np.empty(N, np.int64)   # ... and the permutation is the STABLE sort of the keys
+    key_of[v] = k
+    assert np.array_equal(v, np.argsort(key_of, kind="stable").astype(np.uint32))
 
 
 @pytest.mark.parametrize("dtype,world", [("f64", 2), ("f64", 3), ("f32", 3)])

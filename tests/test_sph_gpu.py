@@ -39,12 +39,29 @@ def test_radix_sort_is_bit_exact(N):
 
 
 def test_cell_keys_and_sort_match_oracle():
+    """The sort key is (grid row, key column) with `subx` key columns per grid cell: key column // subx and the row must be
+    the reference's grid_x / grid_y (:141-157, the oracle's cell key) for every particle, and the permutation the stable
+    sort of the keys (ascending particle index inside a key)."""
     N = 50000
     P = Params(N=N, rain=0)
     pos0, vel0 = reset_particles(P)
-    (_, _, _, _), _, (k, v) = product(P, pos0, vel0, 1)
+    s = SPH(P).upload(pos0, vel0)
+    g = s.grid()
+    s.step(1)
+    k, v = s.download_sort()
+    s.close()
     ek, ev, _ = oracle.sph_cell_sort(oracle.sph_params(N, rain=0), pos0)
-    assert np.array_equal(k, ek) and np.array_equal(v, ev)
+    Gx, subx = g["Gx"], g["subx"]
+    cell_of = np.empty(N, np.int64)
+    cell_of[ev] = ek                                   # the reference's cell of every particle
+    k64 = k.astype(np.int64)
+    coarse = (k64 // (Gx * subx)) * Gx + (k64 % (Gx * subx)) // subx
+    assert np.array_equal(coarse, cell_of[v])
+    key_of = np.empty(N, np.int64)
+    key_of[v] = k64
+    assert np.array_equal(v, np.argsort(key_of, kind="stable").astype(np.uint32)) and np.all(np.diff(k64) >= 0)
+    if subx == 1:
+        assert np.array_equal(k, ek) and np.array_equal(v, ev)
 
 
 def _outliers(a, b, tol):

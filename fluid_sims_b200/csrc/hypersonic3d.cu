@@ -23,6 +23,7 @@
 #include "../../include/tau_b200.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <new>
 #include <vector>
 
@@ -307,12 +308,20 @@ __device__ __forceinline__ int zplane(const Par &P, int lz) {
 // glz: inflow state for x < 0, transmissive outflow (:691-722) for x >= nx, the decoded cell
 // otherwise; solid cells (mask inside the grid, analytic sphere outside it, :186-188) are forced to
 // the isothermal no-slip wall state.
-__device__ __forceinline__ Q halo_prim(const Par &P, const float *__restrict__ in,
+__device__ __forceinline__ Q halo_prim(const Par &P, const float *__restrict__ in, const float *__restrict__ pin,
                                        const uint8_t *__restrict__ solid, int gx, int gy, int glz,
                                        bool &is_solid) {
   const size_t PL = P.plane;
   const int nxy = P.nx * P.ny;
   const int pz = zplane(P, glz);
+  // Decoded state of cell gi.  `pin` (may be null) holds decode(in) for the slab's own planes, written by the step that
+  // produced `in` (see the update tail): the same function of the same six numbers, evaluated once per cell instead of once
+  // per tile that stages it (7.7 tiles).  Ghost planes of a slab arrive encoded from the neighbours and are decoded here.
+  auto fetch = [&](size_t gi) -> Q {
+    if (pin != nullptr && !(P.slab && (pz < T3_H || pz >= P.nz_local + T3_H)))
+      return Q{pin[gi], pin[PL + gi], pin[2 * PL + gi], pin[3 * PL + gi], pin[4 * PL + gi], pin[5 * PL + gi]};
+    return decode(P, in[gi], in[PL + gi], in[2 * PL + gi], in[3 * PL + gi], in[4 * PL + gi], in[5 * PL + gi]);
+  };
   Q q;
   if (gx < 0 || gx >= P.nx) {
     const int gz = wrapi(P.z_begin + glz, P.nz);
@@ -320,9 +329,7 @@ __device__ __forceinline__ Q halo_prim(const Par &P, const float *__restrict__ i
     if (gx < 0) {
       q = inflow_prim(P);
     } else {
-      const size_t gi = (size_t)pz * nxy + (size_t)gy * P.nx + (P.nx - 1);
-      q = decode(P, in[gi], in[PL + gi], in[2 * PL + gi], in[3 * PL + gi], in[4 * PL + gi],
-                 in[5 * PL + gi]);
+      q = fetch((size_t)pz * nxy + (size_t)gy * P.nx + (P.nx - 1));
       const float aR = soundspeed(P, q), un = q.u;
       if (un < 0.0f) {
         q = inflow_prim(P);
@@ -337,16 +344,15 @@ __device__ __forceinline__ Q halo_prim(const Par &P, const float *__restrict__ i
   } else {
     const size_t gi = (size_t)pz * nxy + (size_t)gy * P.nx + gx;
     is_solid = solid[gi] != 0;
-    q = decode(P, in[gi], in[PL + gi], in[2 * PL + gi], in[3 * PL + gi], in[4 * PL + gi],
-               in[5 * PL + gi]);
+    q = fetch(gi);
   }
   if (is_solid) apply_wall(P, q);
   return q;
 }
 
 __global__ void __launch_bounds__(T3_THREADS)
-hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out,
-           const uint8_t *__restrict__ solid, Clock *__restrict__ clk, int slot) {
+hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ pin,
+           float *__restrict__ pout, const uint8_t *__restrict__ solid, Clock *__restrict__ clk, int slot) {
   extern __shared__ __align__(16) unsigned char smem[];
   float *s_q = reinterpret_cast<float *>(smem);                 // [6][SVOL] r,u,v,w,p,ev
   float *s_f = s_q + 6 * T3_SVOL;                                // [6][NF]   face fluxes
@@ -368,7 +374,7 @@ hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out,
     const int lz = tt / T3_SXY, rem = tt - lz * T3_SXY, ly = rem / T3_SX, lx = rem - ly * T3_SX;
     const int gx = bx0 + lx - T3_H, gy = wrapi(by0 + ly - T3_H, P.ny), glz = bz0 + lz - T3_H;
     bool is_solid;
-    const Q q = halo_prim(P, in, solid, gx, gy, glz, is_solid);
+    const Q q = halo_prim(P, in, pin, solid, gx, gy, glz, is_solid);
     s_q[tt] = q.r;
     s_q[T3_SVOL + tt] = q.u;
     s_q[2 * T3_SVOL + tt] = q.v;
@@ -458,8 +464,14 @@ hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out,
   if (x < P.nx && y < P.ny && lz < P.nz_local) {
     const size_t i = (size_t)(lz + T3_H) * nxy + (size_t)y * P.nx + x;
     if (solid[i]) {
+      float e[6];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) out[k * PL + i] = in[k * PL + i];
+      for (int k = 0; k < 6; ++k) out[k * PL + i] = e[k] = in[k * PL + i];
+      if (pout != nullptr) {
+        const Q d = decode(P, e[0], e[1], e[2], e[3], e[4], e[5]);
+        pout[i] = d.r; pout[PL + i] = d.u; pout[2 * PL + i] = d.v; pout[3 * PL + i] = d.w; pout[4 * PL + i] = d.p;
+        pout[5 * PL + i] = d.ev;
+      }
     } else {
       const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
       const int fxm = (tz * T3_TY + ty) * (T3_TX + 1) + tx, fxp = fxm + 1;
@@ -525,12 +537,25 @@ hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out,
       const float a = soundspeed(P, q1);  // :1345-1351
       const float sw = fdiv(fabsf(q1.u) + a, P.dx) + fdiv(fabsf(q1.v) + a, P.dy) + fdiv(fabsf(q1.w) + a, P.dz);
       if (isfinite(sw) && sw > 0.f) ssum = sw;
-      out[i] = __logf(fmaxf(q1.r, RHO_P_FLOOR));  // :1353-1358
-      out[PL + i] = asinhf_dev(fdiv(q1.u, P.u_ref));
-      out[2 * PL + i] = asinhf_dev(fdiv(q1.v, P.u_ref));
-      out[3 * PL + i] = asinhf_dev(fdiv(q1.w, P.u_ref));
-      out[4 * PL + i] = __logf(fmaxf(q1.p, RHO_P_FLOOR));
-      out[5 * PL + i] = __logf(fmaxf(q1.ev, RHO_P_FLOOR));
+      const float e0 = __logf(fmaxf(q1.r, RHO_P_FLOOR));  // :1353-1358
+      const float e1 = asinhf_dev(fdiv(q1.u, P.u_ref));
+      const float e2 = asinhf_dev(fdiv(q1.v, P.u_ref));
+      const float e3 = asinhf_dev(fdiv(q1.w, P.u_ref));
+      const float e4 = __logf(fmaxf(q1.p, RHO_P_FLOOR));
+      const float e5 = __logf(fmaxf(q1.ev, RHO_P_FLOOR));
+      out[i] = e0;
+      out[PL + i] = e1;
+      out[2 * PL + i] = e2;
+      out[3 * PL + i] = e3;
+      out[4 * PL + i] = e4;
+      out[5 * PL + i] = e5;
+      // what the NEXT step's tile builds would each recompute from these six numbers (the reference decodes the stored
+      // logs, :213-225, so the round trip is part of the algorithm: q1 itself must not be handed on)
+      if (pout != nullptr) {
+        const Q d = decode(P, e0, e1, e2, e3, e4, e5);
+        pout[i] = d.r; pout[PL + i] = d.u; pout[2 * PL + i] = d.v; pout[3 * PL + i] = d.w; pout[4 * PL + i] = d.p;
+        pout[5 * PL + i] = d.ev;
+      }
     }
   }
   ssum = tau::warp_max(ssum);
@@ -603,7 +628,7 @@ hyp3d_vis(const Par P, const float *__restrict__ in, const uint8_t *__restrict__
   for (int tt = tid; tt < V3_SVOL; tt += T3_THREADS) {
     const int lz = tt / V3_SXY, rem = tt - lz * V3_SXY, ly = rem / V3_SX, lx = rem - ly * V3_SX;
     bool is_solid;
-    const Q q = halo_prim(P, in, solid, bx0 + lx - 1, wrapi(by0 + ly - 1, P.ny), bz0 + lz - 1, is_solid);
+    const Q q = halo_prim(P, in, nullptr, solid, bx0 + lx - 1, wrapi(by0 + ly - 1, P.ny), bz0 + lz - 1, is_solid);
     s_r[tt] = q.r; s_u[tt] = q.u; s_v[tt] = q.v; s_w[tt] = q.w; s_p[tt] = q.p;
   }
   __syncthreads();
@@ -707,6 +732,8 @@ struct tau_hyp3d {
   cudaStream_t stream;
   bool own_stream;
   float *st[2];      // 6 contiguous planes each, (nz_local+6) z-planes
+  float *pr[2];      // decoded primitives of st[b]'s own planes (same layout; null: TAU_HYP3D_PRIMS=0), see halo_prim
+  bool pr_valid[2];  // pr[b] == decode(st[b]) on the slab's own planes
   uint8_t *solid;
   Clock *clk;
   int cur;
@@ -792,6 +819,13 @@ int tau_hyp3d_create(const tau_hyp3d_params *p, int device, int z_begin, int nz_
     TAU_CUDA(cudaMalloc(&h->st[b], 6 * h->plane * sizeof(float)));
     TAU_CUDA(cudaMemsetAsync(h->st[b], 0, 6 * h->plane * sizeof(float), h->stream));
   }
+  h->pr[0] = h->pr[1] = nullptr;
+  h->pr_valid[0] = h->pr_valid[1] = false;
+  {
+    const char *e = getenv("TAU_HYP3D_PRIMS");  // 0: every tile decodes its own halo (the round-1 kernel)
+    if (!(e && atoi(e) == 0))
+      for (int b = 0; b < 2; ++b) TAU_CUDA(cudaMalloc(&h->pr[b], 6 * h->plane * sizeof(float)));
+  }
   TAU_CUDA(cudaMalloc(&h->solid, h->plane));
   TAU_CUDA(cudaMalloc(&h->clk, sizeof(Clock)));
   TAU_CUDA(cudaEventCreate(&h->ev0));
@@ -821,6 +855,7 @@ int tau_hyp3d_init(tau_hyp3d *h) {
   TAU_CUDA(cudaSetDevice(h->device));
   const Par P = make_par(h);
   hyp3d_init<<<(unsigned)((h->plane + 255) / 256), 256, 0, h->stream>>>(P, h->st[h->cur], h->solid);
+  h->pr_valid[h->cur] = false;
   h->launches++;
   TAU_CUDA(cudaGetLastError());
   h->have_state = true;
@@ -837,6 +872,7 @@ int tau_hyp3d_upload(tau_hyp3d *h, const float *const planes[6], const float *cl
                              cudaMemcpyHostToDevice, h->stream));
   }
   h->have_state = true;
+  h->pr_valid[h->cur] = false;
   int rc = hyp3d_reset_clock(h);
   if (rc) return rc;
   if (clock2) {
@@ -877,7 +913,11 @@ int tau_hyp3d_step_begin(tau_hyp3d *h) {
   const int slot = (int)(h->steps & 1);
   dim3 block(T3_TX, T3_TY, T3_TZ);
   dim3 grid((P.nx + T3_TX - 1) / T3_TX, (P.ny + T3_TY - 1) / T3_TY, (h->nz_local + T3_TZ - 1) / T3_TZ);
-  hyp3d_step<<<grid, block, T3_SMEM, h->stream>>>(P, h->st[h->cur], h->st[h->cur ^ 1], h->solid, h->clk, slot);
+  // the first step after init / upload decodes on the fly (no side buffer for that state yet) and writes the first one
+  hyp3d_step<<<grid, block, T3_SMEM, h->stream>>>(P, h->st[h->cur], h->st[h->cur ^ 1],
+                                                   h->pr_valid[h->cur] ? h->pr[h->cur] : nullptr, h->pr[h->cur ^ 1], h->solid,
+                                                   h->clk, slot);
+  h->pr_valid[h->cur ^ 1] = h->pr[h->cur ^ 1] != nullptr;
   h->launches++;
   TAU_CUDA(cudaGetLastError());
   return TAU_OK;
@@ -1034,6 +1074,8 @@ int tau_hyp3d_destroy(tau_hyp3d *h) {
   if (h->ex_thr) cudaFree(h->ex_thr);
   cudaFree(h->clk);
   cudaFree(h->solid);
+  cudaFree(h->pr[1]);
+  cudaFree(h->pr[0]);
   cudaFree(h->st[1]);
   cudaFree(h->st[0]);
   cudaEventDestroy(h->ev1);

@@ -35,6 +35,9 @@ def lib(packed=False):
         L.tau_hyp3d_clock.argtypes = [h] + [C.POINTER(C.c_float)] * 4
         L.tau_hyp3d_download.argtypes = [h, C.POINTER(C.c_void_p), C.c_void_p]
         L.tau_hyp3d_destroy.argtypes = [h]
+        L.tau_hyp3d_step_begin.argtypes = [h]
+        L.tau_hyp3d_step_end.argtypes = [h]
+        L.tau_hyp3d_device_state.argtypes = [h, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.tau_hyp3d_vis.argtypes = [h, C.c_int, np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")]
         L.tau_hyp3d_export_frame.argtypes = [h, np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS"),
                                              C.POINTER(C.c_float)]
@@ -109,3 +112,57 @@ def export_video(prm, frames, steps_per_frame=4):
         assert L.tau_hyp3d_export_frame(h, out[f].ravel(), None) == 0
     L.tau_hyp3d_destroy(h)
     return out
+
+
+def run_slabs(prm, planes, steps, clock, world, packed=False):
+    """The z-slab ring of tests/_mgpu_worker.py in one process: `world` slab handles, ghost planes copied between their
+    state buffers through tau_hyp3d_device_state (in the emulator a device pointer is a host pointer), the max wavespeed
+    reduced by hand between step_begin and step_end.  -> (planes of the whole domain, [clock per handle])"""
+    L = lib(packed)
+    H = 3
+    nz, ny, nx = prm.nz, prm.ny, prm.nx
+    cp = cparams(prm)
+    cuts = [(r * nz // world, (r + 1) * nz // world - r * nz // world) for r in range(world)]
+    full = [np.ascontiguousarray(p, np.float32).reshape(nz, ny, nx) for p in planes]
+    hs = []
+    for z0, nl in cuts:
+        h = C.c_void_p()
+        assert L.tau_hyp3d_create(C.byref(cp), 0, z0, nl, None, C.byref(h)) == 0, L.tau_hostemu_last_error()
+        arrs = [np.ascontiguousarray(f[z0:z0 + nl]) for f in full]
+        ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in arrs])
+        ck = np.array(clock, np.float32)
+        assert L.tau_hyp3d_upload(h, ptrs, C.c_void_p(ck.ctypes.data)) == 0
+        hs.append(h)
+
+    def state(h, nl):
+        pp, mp = C.c_void_p(), C.c_void_p()
+        assert L.tau_hyp3d_device_state(h, C.byref(pp), C.byref(mp)) == 0
+        st = np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_float)), shape=(6, nl + 2 * H, ny, nx))
+        return st, np.ctypeslib.as_array(C.cast(mp, C.POINTER(C.c_float)), shape=(1,))
+    for _ in range(steps):
+        sts = [state(h, nl) for h, (_, nl) in zip(hs, cuts)]
+        for r in range(world):   # z is periodic: a ring
+            lo, hi = sts[(r - 1) % world][0], sts[(r + 1) % world][0]
+            me, nl = sts[r][0], cuts[r][1]
+            me[:, :H] = lo[:, cuts[(r - 1) % world][1]:cuts[(r - 1) % world][1] + H]   # the lower neighbour's last H planes
+            me[:, nl + H:] = hi[:, H:2 * H]                                              # the upper neighbour's first H
+        for h in hs:
+            assert L.tau_hyp3d_step_begin(h) == 0, L.tau_hostemu_last_error()
+        m = max(float(s[1][0]) for s in sts)
+        for s_ in sts:
+            s_[1][0] = m
+        for h in hs:
+            assert L.tau_hyp3d_step_end(h) == 0
+    out = [np.empty((nz, ny, nx), np.float32) for _ in range(6)]
+    clocks = []
+    for h, (z0, nl) in zip(hs, cuts):
+        part = [np.empty((nl, ny, nx), np.float32) for _ in range(6)]
+        ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in part])
+        assert L.tau_hyp3d_download(h, ptrs, None) == 0
+        for f in range(6):
+            out[f][z0:z0 + nl] = part[f]
+        v = [C.c_float() for _ in range(4)]
+        assert L.tau_hyp3d_clock(h, *[C.byref(x) for x in v]) == 0
+        clocks.append(tuple(float(x.value) for x in v))
+        L.tau_hyp3d_destroy(h)
+    return out, clocks

@@ -426,6 +426,25 @@ def test_hyp2d_vector_accesses_are_aligned_and_in_bounds():
     assert r.returncode == 0 and "sanitized run clean" in r.stdout, r.stderr[-2000:]
 
 
+def test_hyp3d_prim_side_buffer_is_bit_identical_to_decoding_every_tile(developed_3d_flow, monkeypatch):
+    """Since round 2 the step kernel writes decode(new state) next to the state and the next step's tile builds load it
+    instead of decoding their 7.7x-amplified halo themselves (TAU_HYP3D_PRIMS=0: the old kernel).  Same function of the
+    same numbers: the two must agree BIT FOR BIT — single domain, and z-slab rings whose ghost planes arrive encoded and
+    are decoded in the tile build."""
+    prm, dev, solid = developed_3d_flow
+    steps, clock = 4, (0.012, 2e-3)
+    monkeypatch.setenv("TAU_HYP3D_PRIMS", "0")
+    a, _, cka = hyp3d_emu.run(prm, dev, steps, clock, packed=True)
+    monkeypatch.setenv("TAU_HYP3D_PRIMS", "1")
+    b, _, ckb = hyp3d_emu.run(prm, dev, steps, clock, packed=True)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and cka == ckb
+    assert max(np.abs(x - np.asarray(y).reshape(x.shape)).max() for x, y in zip(a, dev)) > 1e-3   # the flow moved
+    for world in (2, 3):
+        c, cks = hyp3d_emu.run_slabs(prm, dev, steps, clock, world, packed=True)
+        assert all(np.array_equal(x, y) for x, y in zip(a, c)), world
+        assert all(ck[:2] == cka[:2] for ck in cks), world
+
+
 def test_hyp3d_4spl_frame_export_is_bit_identical_to_the_reference_host_loop(developed_3d_flow):
     """tau_hyp3d_export_frame (never run on hardware): schlieren field (vis mode 8 = th3cs.cu's
     k_schlieren_export), min/max by ordered-integer atomics, palette index by binary search over the 255

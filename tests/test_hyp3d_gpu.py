@@ -37,6 +37,25 @@ def check(out, ref, tol):
         assert err <= tol[k], (k, err)
 
 
+def test_prim_side_buffer_is_bit_identical_to_decoding_every_tile(monkeypatch):
+    """The step kernel writes decode(new state) next to the state and the next step's tile builds load it instead of
+    decoding their 7.7x-amplified halo (TAU_HYP3D_PRIMS=0: every tile decodes, the round-1 kernel).  Same function of
+    the same six numbers, so the two runs must agree bit for bit — 96^3, 60 steps into the inflow ramp."""
+    n, steps = 96, 60
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("TAU_HYP3D_PRIMS", flag)
+        s = Hypersonic3D(Params.default(n, n, n)).init()
+        p0, _ = s.download()
+        s.upload(p0, (5e-3, 2e-3))
+        s.step(steps)
+        out, _ = s.download()
+        outs.append((out, s.clock()))
+        s.close()
+    assert all(np.array_equal(a, b) for a, b in zip(outs[0][0], outs[1][0])) and outs[0][1] == outs[1][1]
+    assert float(np.abs(outs[0][0][0] - p0[0]).max()) > 0.1
+
+
 def test_matches_reference_golden():
     g = np.load(os.path.join(GOLDEN, "hyp3d_ref_32x28x20.npz"))
     prm = oracle.hyp3d_params(32, 28, 20)

@@ -50,7 +50,10 @@ constexpr int H2_RB = 4;      // rows per TMA box / ring slot
 #define H2_NS_SLOTS 3
 #endif
 constexpr int H2_NS = H2_NS_SLOTS;  // ring slots per warp
-constexpr int H2_WARPS = 4;   // warps per CTA
+#ifndef H2_WARPS_PER_CTA
+#define H2_WARPS_PER_CTA 4
+#endif
+constexpr int H2_WARPS = H2_WARPS_PER_CTA;   // warps per CTA
 constexpr int H2_GHOST = 2;   // ghost rows above/below each plane
 #ifndef H2_MIN_CTAS
 #define H2_MIN_CTAS 5          // fp32: resident CTAs per SM the register allocation must allow (measured: 5 > 4 > 6)
@@ -397,7 +400,11 @@ __device__ __forceinline__ R d2(R m2, R m1, R c, R p1, R p2) {
 }
 
 template <typename R, bool USE_TMA>
+#ifdef H2_MAXNREG   // experiments with other CTA shapes: an explicit register cap instead of a resident-CTA count
+__global__ void __maxnreg__(H2_MAXNREG)
+#else
 __global__ void __launch_bounds__(H2_WARPS * 32, sizeof(R) == 4 ? H2_MIN_CTAS : 2)
+#endif
 hyp2d_step(const __grid_constant__ CUtensorMap tmU, const Params<R> P, const R *__restrict__ Uin,
            R *__restrict__ Uout, const uint8_t *__restrict__ mask,
            const uint2 *__restrict__ items, Ctrl *__restrict__ ctrl, int step_slot,

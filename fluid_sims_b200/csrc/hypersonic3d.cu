@@ -308,7 +308,7 @@ __device__ __forceinline__ int zplane(const Par &P, int lz) {
 // glz: inflow state for x < 0, transmissive outflow (:691-722) for x >= nx, the decoded cell
 // otherwise; solid cells (mask inside the grid, analytic sphere outside it, :186-188) are forced to
 // the isothermal no-slip wall state.
-__device__ __forceinline__ Q halo_prim(const Par &P, const float *__restrict__ in, const float *__restrict__ pin,
+__device__ __forceinline__ Q halo_prim(const Par &P, const float *__restrict__ in, const float4 *__restrict__ pin,
                                        const uint8_t *__restrict__ solid, int gx, int gy, int glz,
                                        bool &is_solid) {
   const size_t PL = P.plane;
@@ -318,8 +318,10 @@ __device__ __forceinline__ Q halo_prim(const Par &P, const float *__restrict__ i
   // produced `in` (see the update tail): the same function of the same six numbers, evaluated once per cell instead of once
   // per tile that stages it (7.7 tiles).  Ghost planes of a slab arrive encoded from the neighbours and are decoded here.
   auto fetch = [&](size_t gi) -> Q {
-    if (pin != nullptr && !(P.slab && (pz < T3_H || pz >= P.nz_local + T3_H)))
-      return Q{pin[gi], pin[PL + gi], pin[2 * PL + gi], pin[3 * PL + gi], pin[4 * PL + gi], pin[5 * PL + gi]};
+    if (pin != nullptr && !(P.slab && (pz < T3_H || pz >= P.nz_local + T3_H))) {
+      const float4 a = pin[2 * gi], b = pin[2 * gi + 1];
+      return Q{a.x, a.y, a.z, a.w, b.x, b.y};
+    }
     return decode(P, in[gi], in[PL + gi], in[2 * PL + gi], in[3 * PL + gi], in[4 * PL + gi], in[5 * PL + gi]);
   };
   Q q;
@@ -350,9 +352,20 @@ __device__ __forceinline__ Q halo_prim(const Par &P, const float *__restrict__ i
   return q;
 }
 
+// out of line: the step kernel's staging loop reaches it for x-boundary columns, slab ghost planes and the first step
+// after an upload only, and its decode / boundary-state code would otherwise sit in the middle of the hot loop
+struct QS { Q q; int solid; };
+__device__ __noinline__ QS halo_prim_cold(const Par &P, const float *__restrict__ in, const float4 *__restrict__ pin,
+                                          const uint8_t *__restrict__ solid, int gx, int gy, int glz) {
+  bool is_solid;
+  const Q q = halo_prim(P, in, pin, solid, gx, gy, glz, is_solid);
+  return QS{q, is_solid ? 1 : 0};
+}
+
 __global__ void __launch_bounds__(T3_THREADS)
-hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ pin,
-           float *__restrict__ pout, const uint8_t *__restrict__ solid, Clock *__restrict__ clk, int slot) {
+hyp3d_step(const __grid_constant__ Par P, const float *__restrict__ in, float *__restrict__ out,
+           const float4 *__restrict__ pin, float4 *__restrict__ pout, const uint8_t *__restrict__ solid,
+           Clock *__restrict__ clk, int slot) {
   extern __shared__ __align__(16) unsigned char smem[];
   float *s_q = reinterpret_cast<float *>(smem);                 // [6][SVOL] r,u,v,w,p,ev
   float *s_f = s_q + 6 * T3_SVOL;                                // [6][NF]   face fluxes
@@ -369,19 +382,43 @@ hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out, c
   const size_t PL = P.plane;
   const int nxy = P.nx * P.ny;
 
-  // ---- decode the halo tile to primitives (k_step :1019-1056) --------------------------------
-  for (int tt = tid; tt < T3_SVOL; tt += T3_THREADS) {
-    const int lz = tt / T3_SXY, rem = tt - lz * T3_SXY, ly = rem / T3_SX, lx = rem - ly * T3_SX;
-    const int gx = bx0 + lx - T3_H, gy = wrapi(by0 + ly - T3_H, P.ny), glz = bz0 + lz - T3_H;
-    bool is_solid;
-    const Q q = halo_prim(P, in, pin, solid, gx, gy, glz, is_solid);
-    s_q[tt] = q.r;
-    s_q[T3_SVOL + tt] = q.u;
-    s_q[2 * T3_SVOL + tt] = q.v;
-    s_q[3 * T3_SVOL + tt] = q.w;
-    s_q[4 * T3_SVOL + tt] = q.p;
-    s_q[5 * T3_SVOL + tt] = q.ev;
-    s_solid[tt] = is_solid ? 1 : 0;
+  // ---- stage the halo tile as primitives (k_step :1019-1056) ------------------------------------
+  // One (x, y) column of the tile per thread, marched through its T3_SZ planes: the column's grid position, its
+  // periodic wrap in y and its x-boundary class are loop invariants, a plane step is one z-plane index and the loads.
+  // (Round 2 measured the flat `for tt < T3_SVOL` form of this loop at 1069 of the kernel's 4373 warp-instructions per
+  // 32 cells and 48 % of its stall samples — 140 instructions per staged cell of index arithmetic, with the loads of one
+  // cell issued and consumed before the next cell's: profiles/hyp3d_step_r2b_ncu_full.txt.)
+  for (int col = tid; col < T3_SXY; col += T3_THREADS) {
+    const int ly = col / T3_SX, lx = col - ly * T3_SX;
+    const int gx = bx0 + lx - T3_H, gy = wrapi(by0 + ly - T3_H, P.ny);
+    const bool col_in_grid = (unsigned)gx < (unsigned)P.nx && pin != nullptr;  // no x-boundary state, primitives at hand
+    const size_t col_off = (size_t)gy * P.nx + (size_t)max(gx, 0);
+#pragma unroll 2
+    for (int lz = 0; lz < T3_SZ; ++lz) {
+      const int tt = lz * T3_SXY + col;
+      const int glz = bz0 + lz - T3_H;
+      const int pz = zplane(P, glz);
+      bool is_solid;
+      Q q;
+      if (col_in_grid && !(P.slab && (pz < T3_H || pz >= P.nz_local + T3_H))) {  // (== halo_prim's interior branch)
+        const size_t gi = (size_t)pz * nxy + col_off;
+        const float4 a = pin[2 * gi], b = pin[2 * gi + 1];  // (r, u, v, w), (p, ev, solid flag, -)
+        q = Q{a.x, a.y, a.z, a.w, b.x, b.y};
+        is_solid = b.z != 0.f;
+        if (is_solid) apply_wall(P, q);
+      } else {
+        const QS c = halo_prim_cold(P, in, pin, solid, gx, gy, glz);
+        q = c.q;
+        is_solid = c.solid != 0;
+      }
+      s_q[tt] = q.r;
+      s_q[T3_SVOL + tt] = q.u;
+      s_q[2 * T3_SVOL + tt] = q.v;
+      s_q[3 * T3_SVOL + tt] = q.w;
+      s_q[4 * T3_SVOL + tt] = q.p;
+      s_q[5 * T3_SVOL + tt] = q.ev;
+      s_solid[tt] = is_solid ? 1 : 0;
+    }
   }
   __syncthreads();
 
@@ -469,8 +506,8 @@ hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out, c
       for (int k = 0; k < 6; ++k) out[k * PL + i] = e[k] = in[k * PL + i];
       if (pout != nullptr) {
         const Q d = decode(P, e[0], e[1], e[2], e[3], e[4], e[5]);
-        pout[i] = d.r; pout[PL + i] = d.u; pout[2 * PL + i] = d.v; pout[3 * PL + i] = d.w; pout[4 * PL + i] = d.p;
-        pout[5 * PL + i] = d.ev;
+        pout[2 * i] = make_float4(d.r, d.u, d.v, d.w);
+        pout[2 * i + 1] = make_float4(d.p, d.ev, 1.f, 0.f);
       }
     } else {
       const int tx = threadIdx.x, ty = threadIdx.y, tz = threadIdx.z;
@@ -553,8 +590,8 @@ hyp3d_step(const Par P, const float *__restrict__ in, float *__restrict__ out, c
       // logs, :213-225, so the round trip is part of the algorithm: q1 itself must not be handed on)
       if (pout != nullptr) {
         const Q d = decode(P, e0, e1, e2, e3, e4, e5);
-        pout[i] = d.r; pout[PL + i] = d.u; pout[2 * PL + i] = d.v; pout[3 * PL + i] = d.w; pout[4 * PL + i] = d.p;
-        pout[5 * PL + i] = d.ev;
+        pout[2 * i] = make_float4(d.r, d.u, d.v, d.w);
+        pout[2 * i + 1] = make_float4(d.p, d.ev, 0.f, 0.f);
       }
     }
   }
@@ -628,7 +665,7 @@ hyp3d_vis(const Par P, const float *__restrict__ in, const uint8_t *__restrict__
   for (int tt = tid; tt < V3_SVOL; tt += T3_THREADS) {
     const int lz = tt / V3_SXY, rem = tt - lz * V3_SXY, ly = rem / V3_SX, lx = rem - ly * V3_SX;
     bool is_solid;
-    const Q q = halo_prim(P, in, nullptr, solid, bx0 + lx - 1, wrapi(by0 + ly - 1, P.ny), bz0 + lz - 1, is_solid);
+    const Q q = halo_prim(P, in, static_cast<const float4 *>(nullptr), solid, bx0 + lx - 1, wrapi(by0 + ly - 1, P.ny), bz0 + lz - 1, is_solid);
     s_r[tt] = q.r; s_u[tt] = q.u; s_v[tt] = q.v; s_w[tt] = q.w; s_p[tt] = q.p;
   }
   __syncthreads();
@@ -732,7 +769,8 @@ struct tau_hyp3d {
   cudaStream_t stream;
   bool own_stream;
   float *st[2];      // 6 contiguous planes each, (nz_local+6) z-planes
-  float *pr[2];      // decoded primitives of st[b]'s own planes (same layout; null: TAU_HYP3D_PRIMS=0), see halo_prim
+  float4 *pr[2];     // decoded primitives of st[b]'s own planes: two float4 per cell, (r, u, v, w) (p, ev, solid flag, -),
+                     // cell index as in st (null: TAU_HYP3D_PRIMS=0), see halo_prim
   bool pr_valid[2];  // pr[b] == decode(st[b]) on the slab's own planes
   uint8_t *solid;
   Clock *clk;
@@ -824,7 +862,7 @@ int tau_hyp3d_create(const tau_hyp3d_params *p, int device, int z_begin, int nz_
   {
     const char *e = getenv("TAU_HYP3D_PRIMS");  // 0: every tile decodes its own halo (the round-1 kernel)
     if (!(e && atoi(e) == 0))
-      for (int b = 0; b < 2; ++b) TAU_CUDA(cudaMalloc(&h->pr[b], 6 * h->plane * sizeof(float)));
+      for (int b = 0; b < 2; ++b) TAU_CUDA(cudaMalloc(&h->pr[b], 2 * h->plane * sizeof(float4)));
   }
   TAU_CUDA(cudaMalloc(&h->solid, h->plane));
   TAU_CUDA(cudaMalloc(&h->clk, sizeof(Clock)));

@@ -35,10 +35,15 @@
 
 namespace {
 
-constexpr int T3_TX = 8, T3_TY = 8, T3_TZ = 4, T3_H = 3;
+#ifndef T3_TILE_Z
+#define T3_TILE_Z 4
+#endif
+constexpr int T3_TX = 8, T3_TY = 8, T3_TZ = T3_TILE_Z, T3_H = 3;
 constexpr int T3_SX = T3_TX + 2 * T3_H, T3_SY = T3_TY + 2 * T3_H, T3_SZ = T3_TZ + 2 * T3_H;
 constexpr int T3_SXY = T3_SX * T3_SY, T3_SVOL = T3_SXY * T3_SZ;
 constexpr int T3_THREADS = T3_TX * T3_TY * T3_TZ;
+constexpr int T3_STAGE_BATCH = T3_SZ / 2;  // tile planes whose loads one thread keeps in flight while staging
+static_assert(T3_SZ % T3_STAGE_BATCH == 0, "whole batches");
 constexpr int T3_NFX = (T3_TX + 1) * T3_TY * T3_TZ;  // 288 = 9 warps
 constexpr int T3_NFY = T3_TX * (T3_TY + 1) * T3_TZ;  // 288
 constexpr int T3_NFZ = T3_TX * T3_TY * (T3_TZ + 1);  // 320
@@ -362,7 +367,7 @@ __device__ __noinline__ QS halo_prim_cold(const Par &P, const float *__restrict_
   return QS{q, is_solid ? 1 : 0};
 }
 
-__global__ void __launch_bounds__(T3_THREADS)
+__global__ void __launch_bounds__(T3_THREADS, T3_TZ == 4 ? 3 : 2)   // what shared memory admits per SM: keep the registers to that
 hyp3d_step(const __grid_constant__ Par P, const float *__restrict__ in, float *__restrict__ out,
            const float4 *__restrict__ pin, float4 *__restrict__ pout, const uint8_t *__restrict__ solid,
            Clock *__restrict__ clk, int slot) {
@@ -383,41 +388,56 @@ hyp3d_step(const __grid_constant__ Par P, const float *__restrict__ in, float *_
   const int nxy = P.nx * P.ny;
 
   // ---- stage the halo tile as primitives (k_step :1019-1056) ------------------------------------
-  // One (x, y) column of the tile per thread, marched through its T3_SZ planes: the column's grid position, its
-  // periodic wrap in y and its x-boundary class are loop invariants, a plane step is one z-plane index and the loads.
+  // Half an (x, y) column of the tile per thread (T3_STAGE_BATCH planes): the column's grid position, its periodic wrap
+  // in y and its x-boundary class are computed once, a plane is one z-plane index and two 16-byte loads.
   // (Round 2 measured the flat `for tt < T3_SVOL` form of this loop at 1069 of the kernel's 4373 warp-instructions per
   // 32 cells and 48 % of its stall samples — 140 instructions per staged cell of index arithmetic, with the loads of one
   // cell issued and consumed before the next cell's: profiles/hyp3d_step_r2b_ncu_full.txt.)
-  for (int col = tid; col < T3_SXY; col += T3_THREADS) {
+  for (int unit = tid; unit < T3_SXY * (T3_SZ / T3_STAGE_BATCH); unit += T3_THREADS) {
+    const int part = unit / T3_SXY, col = unit - part * T3_SXY;  // (tile column, batch of planes)
     const int ly = col / T3_SX, lx = col - ly * T3_SX;
     const int gx = bx0 + lx - T3_H, gy = wrapi(by0 + ly - T3_H, P.ny);
     const bool col_in_grid = (unsigned)gx < (unsigned)P.nx && pin != nullptr;  // no x-boundary state, primitives at hand
     const size_t col_off = (size_t)gy * P.nx + (size_t)max(gx, 0);
-#pragma unroll 2
-    for (int lz = 0; lz < T3_SZ; ++lz) {
-      const int tt = lz * T3_SXY + col;
-      const int glz = bz0 + lz - T3_H;
-      const int pz = zplane(P, glz);
-      bool is_solid;
-      Q q;
-      if (col_in_grid && !(P.slab && (pz < T3_H || pz >= P.nz_local + T3_H))) {  // (== halo_prim's interior branch)
-        const size_t gi = (size_t)pz * nxy + col_off;
-        const float4 a = pin[2 * gi], b = pin[2 * gi + 1];  // (r, u, v, w), (p, ev, solid flag, -)
-        q = Q{a.x, a.y, a.z, a.w, b.x, b.y};
-        is_solid = b.z != 0.f;
-        if (is_solid) apply_wall(P, q);
-      } else {
-        const QS c = halo_prim_cold(P, in, pin, solid, gx, gy, glz);
-        q = c.q;
-        is_solid = c.solid != 0;
+    // planes in batches of T3_STAGE_BATCH: all loads of a batch are issued before the first is consumed (the staging
+    // phase waits on memory, not on issue slots: measured 33 % of the kernel's stall samples with one plane in flight)
+    {
+      const int lz0 = part * T3_STAGE_BATCH;
+      float4 a[T3_STAGE_BATCH], b[T3_STAGE_BATCH];
+      bool hot[T3_STAGE_BATCH];
+#pragma unroll
+      for (int k = 0; k < T3_STAGE_BATCH; ++k) {
+        const int pz = zplane(P, bz0 + lz0 + k - T3_H);
+        hot[k] = col_in_grid && !(P.slab && (pz < T3_H || pz >= P.nz_local + T3_H));  // (== halo_prim's interior branch)
+        if (hot[k]) {
+          const size_t gi = (size_t)pz * nxy + col_off;
+          a[k] = pin[2 * gi];      // (r, u, v, w)
+          b[k] = pin[2 * gi + 1];  // (p, ev, solid flag, -)
+        }
       }
-      s_q[tt] = q.r;
-      s_q[T3_SVOL + tt] = q.u;
-      s_q[2 * T3_SVOL + tt] = q.v;
-      s_q[3 * T3_SVOL + tt] = q.w;
-      s_q[4 * T3_SVOL + tt] = q.p;
-      s_q[5 * T3_SVOL + tt] = q.ev;
-      s_solid[tt] = is_solid ? 1 : 0;
+#pragma unroll
+      for (int k = 0; k < T3_STAGE_BATCH; ++k) {
+        const int lz = lz0 + k;
+        const int tt = lz * T3_SXY + col;
+        bool is_solid;
+        Q q;
+        if (hot[k]) {
+          q = Q{a[k].x, a[k].y, a[k].z, a[k].w, b[k].x, b[k].y};
+          is_solid = b[k].z != 0.f;
+          if (is_solid) apply_wall(P, q);
+        } else {
+          const QS c = halo_prim_cold(P, in, pin, solid, gx, gy, bz0 + lz - T3_H);
+          q = c.q;
+          is_solid = c.solid != 0;
+        }
+        s_q[tt] = q.r;
+        s_q[T3_SVOL + tt] = q.u;
+        s_q[2 * T3_SVOL + tt] = q.v;
+        s_q[3 * T3_SVOL + tt] = q.w;
+        s_q[4 * T3_SVOL + tt] = q.p;
+        s_q[5 * T3_SVOL + tt] = q.ev;
+        s_solid[tt] = is_solid ? 1 : 0;
+      }
     }
   }
   __syncthreads();

@@ -27,6 +27,7 @@
 #include "../../include/tau_b200.h"
 
 #include <math.h>
+#include <stdlib.h>
 #include <new>
 #include <random>
 #include <vector>
@@ -35,7 +36,8 @@ namespace {
 
 constexpr int SORT_WARPS = 8;            // warps per CTA in the sort kernels
 constexpr int SORT_SEG = 1024;           // keys per warp segment
-constexpr int SORT_MAX_BITS = 10;        // digit width upper bound (1024 bins: the 2^21-particle case sorts 20-bit keys in two passes)
+constexpr int SORT_MAX_BITS = 10;        // digit width upper bound (1024 bins: shared-memory histograms of the sort kernels)
+constexpr int SORT_DEFAULT_BITS = 10;    // digit width used: the 2^21-particle case sorts 20-bit keys in two passes
 constexpr int GROUP = 8;                 // lanes cooperating on one particle
 // Sort-key columns per grid cell.  The reference's cell (edge 2h = the support radius, :512-540) makes the 3x3 search
 // visit 9 cells = 36 h^2 for a support disc of 4 pi h^2: 35 % of the candidates pass the distance test.  The key keeps the
@@ -652,11 +654,23 @@ Consts make_consts(const tau_sph *h) {
   return c;
 }
 
+// widest digit of a pass: SORT_MAX_BITS, or TAU_SPH_SORT_BITS (1 .. SORT_MAX_BITS) for experiments — the result of the sort
+// does not depend on it
+int sort_digit_bits() {
+  static int bits = 0;
+  if (bits == 0) {
+    const char *e = getenv("TAU_SPH_SORT_BITS");
+    const int v = e ? atoi(e) : SORT_DEFAULT_BITS;
+    bits = v < 1 ? 1 : (v > SORT_MAX_BITS ? SORT_MAX_BITS : v);
+  }
+  return bits;
+}
 // stable radix sort of (keys[0], vals[0]), n pairs with keys < 2^key_bits; returns the buffer index holding the result
 int radix_sort_pairs(unsigned *const keys[2], unsigned *const vals[2], unsigned *hist, unsigned *scan_totals, int n,
                      int key_bits, cudaStream_t stream, long long *launches) {
   const int nwarps = (n + SORT_SEG - 1) / SORT_SEG;
-  const int passes = (key_bits + SORT_MAX_BITS - 1) / SORT_MAX_BITS;
+  const int digit_max = sort_digit_bits();
+  const int passes = (key_bits + digit_max - 1) / digit_max;
   const int bits = (key_bits + passes - 1) / passes;
   const int blocks = (nwarps + SORT_WARPS - 1) / SORT_WARPS;
   int src = 0;

@@ -102,8 +102,6 @@ struct Params {
   int W, H_local, H_global, y_begin;
   int nstrips;    // 30-column strips per row
   int nitems;     // entries of the work-item table
-  int stagger_ns; // start stagger per resident warp of an SM (see the item loop), 0 = off
-  int nsm;        // SMs of the device (CTA b sits on SM b % nsm in the first wave)
   size_t plane;   // elements per plane incl. ghost rows
 };
 
@@ -781,7 +779,6 @@ struct tau_hyp2d {
   int seg_rows;          // tallest segment of the table (the only height when set by the caller)
   bool seg_auto;         // tapered schedule chosen by build_items (not set by the caller)
   int taper_k, min_rows, max_rows; // schedule tuning (TAU_HYP2D_TAPER_K / _MIN_ROWS / _MAX_ROWS)
-  int stagger_ns, nsm;   // start stagger of the resident warps of an SM (TAU_HYP2D_STAGGER_NS), SM count
   cudaEvent_t ev0, ev1;
   bool timed;
   size_t plane_elems;
@@ -843,8 +840,6 @@ Params<R> make_params(const tau_hyp2d *h) {
   P.y_begin = h->y_begin;
   P.nstrips = (h->W + H2_OWN - 1) / H2_OWN;
   P.nitems = h->nitems;
-  P.stagger_ns = h->stagger_ns;
-  P.nsm = h->nsm > 0 ? h->nsm : 148;
   P.plane = h->plane_elems;
   return P;
 }
@@ -1355,10 +1350,6 @@ int tau_hyp2d_create(const tau_hyp2d_config *cfg, int W, int H, int dtype, int d
   h->seg_rows = 24;
   h->seg_auto = true;
   h->taper_k = 2;
-  h->stagger_ns = 0;
-  if (const char *e = getenv("TAU_HYP2D_STAGGER_NS")) h->stagger_ns = atoi(e) > 0 ? atoi(e) : 0;
-  h->nsm = 148;
-  cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, device);
   h->min_rows = 4;
   h->max_rows = 48;
   if (const char *e = getenv("TAU_HYP2D_MAX_ROWS")) {

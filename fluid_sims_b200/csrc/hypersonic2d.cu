@@ -997,8 +997,11 @@ int build_items(tau_hyp2d *h, size_t smem) {
   // masked items first; within each class the table order (tall -> short) is kept
   std::vector<uint2> sorted;
   sorted.reserve(n);
+  // (... then the two edge strips, whose rows fold the inflow column / clamp at the outflow edge: the costlier items go first)
+  auto edge = [&](const uint2 &d) { const int st = (int)(d.x & 0xffffu); return st == 0 || st == nstrips - 1; };
   for (size_t i = 0; i < n; ++i) if (tab[i].x >> 31) sorted.push_back(tab[i]);
-  for (size_t i = 0; i < n; ++i) if (!(tab[i].x >> 31)) sorted.push_back(tab[i]);
+  for (size_t i = 0; i < n; ++i) if (!(tab[i].x >> 31) && edge(tab[i])) sorted.push_back(tab[i]);
+  for (size_t i = 0; i < n; ++i) if (!(tab[i].x >> 31) && !edge(tab[i])) sorted.push_back(tab[i]);
   TAU_CUDA(cudaMemcpyAsync(h->items, sorted.data(), n * sizeof(uint2), cudaMemcpyHostToDevice, h->stream));
   TAU_CUDA(cudaStreamSynchronize(h->stream));  // `sorted` goes out of scope
   const int need = (int)((n + H2_WARPS - 1) / H2_WARPS);

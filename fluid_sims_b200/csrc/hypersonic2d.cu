@@ -920,7 +920,7 @@ namespace {
 // Work-item table.  The rows of the slab are cut into layers; a layer is one row segment of every
 // strip.  Caller-chosen height (tau_hyp2d_set_seg_rows): uniform layers.  Default: guided
 // self-scheduling — a layer's height is (remaining item-rows) / (taper_k x resident warps), clamped
-// to [min_rows, 48]: tall segments first (the two warm-up rows of a segment are amortised over 48
+// to [min_rows, max_rows]: tall segments first (the two warm-up rows of a segment are amortised over up to 96
 // rows), short ones last (so that all SMs run dry together; the step ends in a global reduction and
 // its tail cannot be overlapped with the next step).  Items whose window touches the body run the
 // costlier masked march and go to the front of the table (longest-processing-time-first).
@@ -1352,9 +1352,9 @@ int tau_hyp2d_create(const tau_hyp2d_config *cfg, int W, int H, int dtype, int d
   h->items_dirty = true;
   h->seg_rows = 24;
   h->seg_auto = true;
-  h->taper_k = 2;
-  h->min_rows = 4;
-  h->max_rows = 48;
+  h->taper_k = 1;   // (2 / 4 / 48 until the edge strips stopped being the tail of every step: profiles/r2_second_session.md)
+  h->min_rows = 6;
+  h->max_rows = 96;
   if (const char *e = getenv("TAU_HYP2D_MAX_ROWS")) {
     int v = atoi(e);
     if (v >= 4) h->max_rows = v;

@@ -248,13 +248,29 @@ def run_product(a):
     W = a.grid_w or GRID_W
     H = (a.grid_h or GRID_H) * (world if a.scaling == "weak" else 1)
     cfg = SimConfig.default(W, H)
-    y0, hl = slab.partition_rows(H, world, slab.hyp2d_row_costs(cfg) if a.cost_weighted_slabs else None)[rank]
     # an explicit side stream: torch's legacy default stream has handle 0, which the C-ABI reads as
     # "create your own stream" — events recorded on it would not see the kernels
     tstream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
+    parts = slab.partition_rows(H, world, slab.hyp2d_row_costs(cfg) if a.cost_weighted_slabs else None)
+    balance = None
+    if world > 1 and a.exchange == "peer" and a.scaling == "strong" and not a.no_balance and not a.cost_weighted_slabs:
+        # measured load balancing (slab.hyp2d_balanced_partition): the slabs that hold the bow shock, the body and the wake
+        # are 10-20 % slower per row; the state does not depend on where the cuts are (state_crc below)
+        def trial(yb, hloc):
+            t = Hypersonic2D(cfg, dtype=a.dtype, device=dev, y_begin=yb, h_local=hloc, stream=stream)
+            if a.seg_rows:
+                t.set_seg_rows(a.seg_rows)
+            return t.init()
+        try:
+            parts, busy = slab.hyp2d_balanced_partition(trial, H, steps=min(a.develop, 600) or 100)
+            balance = {"rows": [c for _, c in parts], "busy_us_equal_rows": [round(b, 1) for b in busy]}
+        except Exception as e:                      # never lose the measurement to the balancer
+            parts = slab.partition_rows(H, world)
+            balance = {"error": repr(e)[:200]}
+    y0, hl = parts[rank]
     sim = Hypersonic2D(cfg, dtype=a.dtype, device=dev, y_begin=y0, h_local=hl, stream=stream)
     if a.seg_rows:
         sim.set_seg_rows(a.seg_rows)
@@ -337,13 +353,14 @@ def run_product(a):
     kernel_ms = ms / a.steps
     peak, peak_src = measured_peak()
     # roofline of the dominant kernel (hyp2d_step): per launch it updates this rank's slab
-    ach = BYTES_PER_CELL * (W * hl) / (kernel_ms * 1e-3) / 1e9
+    rows_mean = H / world                    # (balanced slabs differ in height; the step time is the max over ranks)
+    ach = BYTES_PER_CELL * (W * rows_mean) / (kernel_ms * 1e-3) / 1e9
     bpc = BYTES_PER_CELL if a.dtype == "f32" else 65
     if a.dtype != "f32":
-        ach = bpc * (W * hl) / (kernel_ms * 1e-3) / 1e9
+        ach = bpc * (W * rows_mean) / (kernel_ms * 1e-3) / 1e9
 
     prof = profile_constants()
-    frac_rows = hl / 4096.0 * (W / 4096.0)
+    frac_rows = rows_mean / 4096.0 * (W / 4096.0)
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     inst = prof.get("warp_instructions_per_launch")
@@ -374,6 +391,7 @@ def run_product(a):
             "cpu_baseline": None, "e2e": None, "gpu_launches": int(launches), "clocks": clocks,
             "state_crc": crc, "sim_t": clock_t,
             **({"peer_timing": peer_timing} if peer_timing else {}),
+            **({"slab_balance": balance} if balance else {}),
         }
     # ---- from here on nothing may cost the headline: a watchdog prints what has been measured and exits -------
     def emit():
@@ -616,6 +634,7 @@ def main():
                     help="N>1: rows partitioned by estimated cost instead of equally (results are identical either way; measured: "
                          "no gain — 0.08676 vs 0.08679 ms/step at N = 8 — the per-rank busy times even out but the step does not shorten)")
     ap.add_argument("--no-numa-bind", action="store_true", help="N>1 e2e: do not pin the rank to its GPU's NUMA node")
+    ap.add_argument("--no-balance", action="store_true", help="N>1: equal rows per slab instead of the measured balance")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the fp64-handle and reference-kernel sub-records (N=1)")

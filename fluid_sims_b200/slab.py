@@ -129,6 +129,51 @@ def hyp2d_row_costs(cfg, extra: float = 0.07):
     return [1.0 + (extra if lo <= y + 0.5 <= hi else 0.0) for y in range(cfg.H)]
 
 
+def rebalance_rows(parts: List[Tuple[int, int]], busy_us: Sequence[float], fixed_us: float = 10.0,
+                   min_rows: int = 8) -> List[Tuple[int, int]]:
+    """New contiguous partition of the same rows from the time each part's step kernel was busy (`busy_us[r]`, e.g.
+    Hypersonic2D.peer_timing()["busy_us"]): a row of part r is taken to cost (busy_us[r] - fixed_us) / rows_r, and the
+    cuts move so that every part gets the same modelled cost.  Pure host arithmetic; the state does not depend on the
+    partition (every decomposition is bit-identical to one GPU), so this is load balancing only."""
+    n = sum(c for _, c in parts)
+    w: List[float] = []
+    for (b, c), t in zip(parts, busy_us):
+        w += [max(float(t) - fixed_us, 1e-3) / c] * c
+    out = partition_rows(n, len(parts), w)
+    if min(c for _, c in out) < min_rows:
+        return list(parts)
+    return out
+
+
+def hyp2d_balanced_partition(make_sim, H: int, steps: int, iters: int = 2, group=None):
+    """Measured load balancing of the y-slabs of the 2-D hypersonic solver (peer mode): `make_sim(y_begin, h_local)` builds
+    this rank's initialised handle; every rank runs `steps` steps on the current partition, the ranks compare how long their
+    step kernels were busy (the rows that hold the bow shock, the body and its wake cost 10-20 % more than free-stream
+    rows), and the cuts move (rebalance_rows).  Returns (partition, [busy_us per rank of the last measurement]).  The
+    trial handles are destroyed; results do not depend on the partition."""
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    parts = partition_rows(H, world)
+    busy: List[float] = []
+    for _ in range(iters):
+        y0, hl = parts[rank]
+        sim = make_sim(y0, hl)
+        hyp2d_attach_peers(sim, group)
+        hyp2d_sync_state(sim, group)
+        sim.peers_ready()
+        dist.barrier(group=group)
+        sim.step(steps)
+        sim.sync()
+        mine = float(sim.peer_timing()["busy_us"])
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine, group=group)
+        busy = [float(x) for x in gathered]
+        hyp2d_detach_peers(sim, group)
+        sim.close()
+        dist.barrier(group=group)
+        parts = rebalance_rows(parts, busy)
+    return parts, busy
+
+
 def hyp2d_attach_peers(sim, group=None) -> None:
     """All-gather the CUDA-IPC handles of every rank's planes/control block and attach them, so that
     the 2-D hypersonic step kernel pushes its boundary rows straight into the neighbours' ghost rows

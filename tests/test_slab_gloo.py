@@ -179,6 +179,21 @@ def test_partition_rows_cost_weighted():
     assert slab.partition_rows(4096, 1, w) == [(0, 4096)]
 
 
+def test_rebalance_rows_moves_the_cuts_towards_equal_cost():
+    """measured load balancing of the 2-D slabs (bench.py at N > 1): rows of a slab cost (busy - fixed) / rows; the new
+    partition is contiguous, complete, gives the slow slabs fewer rows, and equalises the modelled cost"""
+    parts = slab.partition_rows(4096, 8)
+    busy = [65.8, 66.8, 72.0, 74.1, 74.5, 72.5, 67.1, 62.6]           # measured at N = 8 (profiles/r2d_bench_n8.json)
+    new = slab.rebalance_rows(parts, busy)
+    assert new[0][0] == 0 and all(new[i][0] + new[i][1] == new[i + 1][0] for i in range(7)) and new[-1][0] + new[-1][1] == 4096
+    assert new[4][1] < 512 < new[7][1] and new[3][1] < 512 < new[0][1]
+    per_row = [(b - 10.0) / 512 for b in busy]
+    cost = [sum(per_row[min(y // 512, 7)] for y in range(b, b + c)) for b, c in new]
+    assert max(cost) - min(cost) < 0.5 and max(cost) < max(b - 10.0 for b in busy) - 3.0
+    assert slab.rebalance_rows(parts, [70.0] * 8) == parts
+    assert slab.rebalance_rows([(0, 8), (8, 8)], [1000.0, 20.0]) == [(0, 8), (8, 8)]     # would leave < 8 rows: keep
+
+
 def test_partition_rows():
     assert slab.partition_rows(4096, 8) == [(512 * i, 512) for i in range(8)]
     parts = slab.partition_rows(37, 3)

@@ -779,6 +779,7 @@ struct tau_hyp2d {
   int seg_rows;          // tallest segment of the table (the only height when set by the caller)
   bool seg_auto;         // tapered schedule chosen by build_items (not set by the caller)
   int taper_k, min_rows, max_rows; // schedule tuning (TAU_HYP2D_TAPER_K / _MIN_ROWS / _MAX_ROWS)
+  bool max_rows_auto;    // cap of a segment = half a warp's fair share of the slab's rows (not set by the environment)
   cudaEvent_t ev0, ev1;
   bool timed;
   size_t plane_elems;
@@ -936,8 +937,19 @@ int build_items(tau_hyp2d *h, size_t smem) {
   const int resident_warps = dev_sms * per_sm * H2_WARPS;
   const int nstrips = (h->W + H2_OWN - 1) / H2_OWN;
   std::vector<int> layer_y(h->h_local), layer_h(h->h_local);
+  // The tallest segment: half of what a warp marches in the whole step (rows x strips / resident warps), within [12, 96].
+  // Measured (profiles/r2_second_session.md; K = 1): 4096 rows 96 > 64 > 128 >> 192; 2048 rows 48 > 64 >> 96; a first
+  // layer as tall as the whole fair share leaves nothing to balance with.
+  int max_rows = h->max_rows;
+  if (h->max_rows_auto) {
+    const long long fair = (long long)h->h_local * nstrips / (resident_warps > 0 ? resident_warps : 1);
+    max_rows = (int)(fair / 2);
+    if (max_rows > 96) max_rows = 96;
+    if (max_rows < 12) max_rows = 12;
+    if (max_rows < h->min_rows) max_rows = h->min_rows;
+  }
   const int nl = tau_hyp2d_plan_layers(h->h_local, nstrips, resident_warps, h->seg_auto ? 0 : h->seg_rows,
-                                       h->taper_k, h->min_rows, h->max_rows, layer_y.data(), layer_h.data(),
+                                       h->taper_k, h->min_rows, max_rows, layer_y.data(), layer_h.data(),
                                        h->h_local);
   if (nl < 0) return nl;
   layer_y.resize(nl);
@@ -1355,9 +1367,13 @@ int tau_hyp2d_create(const tau_hyp2d_config *cfg, int W, int H, int dtype, int d
   h->taper_k = 1;   // (2 / 4 / 48 until the edge strips stopped being the tail of every step: profiles/r2_second_session.md)
   h->min_rows = 6;
   h->max_rows = 96;
+  h->max_rows_auto = true;
   if (const char *e = getenv("TAU_HYP2D_MAX_ROWS")) {
     int v = atoi(e);
-    if (v >= 4) h->max_rows = v;
+    if (v >= 4) {
+      h->max_rows = v;
+      h->max_rows_auto = false;
+    }
   }
   if (const char *e = getenv("TAU_HYP2D_SEG_ROWS")) {
     int v = atoi(e);

@@ -266,7 +266,7 @@ def run_product(a):
             return t.init()
         try:
             parts, busy = slab.hyp2d_balanced_partition(trial, H, steps=min(a.develop, 600) or 100)
-            balance = {"rows": [c for _, c in parts], "busy_us_equal_rows": [round(b, 1) for b in busy]}
+            balance = {"rows": [c for _, c in parts], "busy_us_last_trial": [round(b, 1) for b in busy]}
         except Exception as e:                      # never lose the measurement to the balancer
             parts = slab.partition_rows(H, world)
             balance = {"error": repr(e)[:200]}

@@ -258,7 +258,9 @@ int tau_4spl_write(const char *path, int width, int height, int depth, int frame
 /* dims = {width, height, depth, frames, pSize, flags}; verifies length and checksum */
 int tau_4spl_info(const char *path, int dims[6]);
 /* device pointers: current state (6 contiguous planes of (nz_local+6)*ny*nx floats, starting at
- * ghost plane -3) and the max-wavespeed accumulator of the running step */
+ * ghost plane -3) and the max-wavespeed accumulator of the running step.  Write GHOST planes only through this pointer (the
+ * ring exchange): the handle keeps decoded primitives of its own planes next to the state (tau_hyp3d_upload / _init replace
+ * those) */
 int tau_hyp3d_device_state(tau_hyp3d *h, float **planes, float **maxs);
 long long tau_hyp3d_steps_done(tau_hyp3d *h);
 long long tau_hyp3d_launch_count(tau_hyp3d *h);

@@ -45,7 +45,11 @@ constexpr int GROUP = 8;                 // lanes cooperating on one particle
 // now SUBX key columns either side of the particle's own — (2 SUBX + 1) / SUBX = 2.25 cells wide instead of 3, 25 % fewer
 // candidates.  SUBX is a power of two: x / (cell / SUBX) == SUBX * (x / cell) exactly, so key column >> log2(SUBX) IS the
 // reference's grid_x (:141-148) and the order is a refinement of the reference's cell order.
-constexpr int SUBX = 4;
+#ifndef SPH_SUBX
+#define SPH_SUBX 4
+#endif
+constexpr int SUBX = SPH_SUBX;
+static_assert((SUBX & (SUBX - 1)) == 0 && SUBX >= 1, "power of two");
 
 struct Consts {
   int N, Gx, Gy;   // Gx = KEY columns per row (SUBX per grid cell), Gy = grid rows

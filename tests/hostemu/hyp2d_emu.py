@@ -94,7 +94,7 @@ def run(W, H, steps, dtype, planes=None, mask=None, seg_rows=None, pair=False, c
     return out, m, t.value, np.array(dts), n
 
 
-def run_slabs(W, H, steps, dtype, world, pair=False, frames=(), reverse_ranks=False, **over):
+def run_slabs(W, H, steps, dtype, world, pair=False, frames=(), reverse_ranks=False, cuts=None, **over):
     """`world` y-slab handles in ONE process, stepped in turn: the emulated counterpart of one process per
     GPU with CUDA-IPC peers (fluid_sims_b200/slab.py: hyp2d_sync_state + hyp2d_attach_peers).  Each rank's
     step kernel pushes its boundary rows into the neighbours' ghost rows and sends its max wavespeed to
@@ -111,9 +111,10 @@ def run_slabs(W, H, steps, dtype, world, pair=False, frames=(), reverse_ranks=Fa
     base, rem = divmod(H, world)
     parts, y = [], 0
     for r in range(world):
-        hl = base + (r < rem)
+        hl = cuts[r] if cuts is not None else base + (r < rem)   # cuts: rows per rank (unequal slabs of a balanced run)
         parts.append((y, hl))
         y += hl
+    assert y == H
     os.environ.pop("TAU_HYP2D_PAIR", None)
     if pair:
         os.environ["TAU_HYP2D_PAIR"] = str(int(pair))

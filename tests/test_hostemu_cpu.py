@@ -403,6 +403,18 @@ def test_hyp2d_device_side_slab_exchange_is_bit_identical_to_one_domain(pretend_
     assert all(tt == t for tt in ts) and open_mappings == 0
 
 
+@pytest.mark.parametrize("dtype,cuts", [("f32", (37, 20, 41, 22)), ("f64", (8, 70, 42)), ("f32", (60, 60))])
+def test_hyp2d_unequal_slabs_are_bit_identical_to_one_domain(pretend_device, dtype, cuts):
+    """What the measured load balancing (slab.hyp2d_balanced_partition) produces: slabs of different heights, cuts through
+    the body.  The state must not depend on where the cuts are."""
+    pretend_device(3, 2)
+    W, H, steps = 200, 120, 12
+    a, m, t, _, _ = hyp2d_emu.run(W, H, steps, dtype, geom_x0=W / 3.0)
+    b, mb, ts, open_mappings = hyp2d_emu.run_slabs(W, H, steps, dtype, len(cuts), cuts=cuts, geom_x0=W / 3.0)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and np.array_equal(m, mb)
+    assert all(tt == t for tt in ts) and open_mappings == 0
+
+
 def test_hyp2d_pair_kernel_in_slab_mode(pretend_device):
     """pair kernel first, production kernel second (it owns the step's bookkeeping and the peer message);
     both push boundary rows.  Different items go to the pair kernel than in the single-domain run, so the

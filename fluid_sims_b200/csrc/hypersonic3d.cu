@@ -5,10 +5,13 @@
 //
 // What is restructured relative to the reference kernel:
 //   * every face flux is computed ONCE.  The reference evaluates 6 faces per cell (each face twice,
-//     once from either side; 72 WENO5 evaluations + 6 Riemann solves per cell).  Here a CTA decodes
-//     its 14x14x10 halo tile to primitives in shared memory (same tile as the reference), then its
+//     once from either side; 72 WENO5 evaluations + 6 Riemann solves per cell).  Here a CTA stages
+//     its 14x14x10 halo tile as primitives in shared memory (same tile as the reference), then its
 //     threads sweep the tile's 896 faces — ordered so that every warp works on one axis — and park
 //     the fluxes in shared memory; the cell update gathers its six.  3.5 faces per cell instead of 6.
+//   * the tile is LOADED, not decoded: the update tail writes decode(new state) next to the state
+//     (two float4 per cell incl. the solid flag) and the next step's tile builds read that instead of
+//     running __expf x3 / sinhf x3 on each of their 7.7x-amplified halo cells (see hyp3d_step).
 //   * the WENO5 nonlinear weights use one reciprocal per reconstruction instead of six IEEE
 //     divisions (algebraically identical: w_k = c_k prod_{j!=k} (eps+b_j)^2 / sum), the rest of the
 //     arithmetic keeps the reference's expression trees and its fast intrinsics (__expf/__logf).

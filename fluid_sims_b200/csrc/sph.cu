@@ -12,8 +12,9 @@
 //     into sorted order.  The sort is bit-exact (== a stable CPU sort of the same keys) and makes the
 //     whole step deterministic.
 //   * per-particle sums: 8 lanes cooperate on one particle, striding over the candidate slot ranges
-//     of its 3x3 cells (three contiguous ranges, coalesced loads), and fold their partial sums with
-//     warp shuffles.
+//     of its neighbourhood (three contiguous ranges, one per cell row, coalesced loads), and fold
+//     their partial sums with warp shuffles.  The sort key cuts every cell into SUBX key columns, so
+//     a range is 2.25 cells wide instead of 3 (see SUBX); key column / SUBX is the reference's grid_x.
 //   * rho_j = expf(s_j) and p_j / rho_j^2, which the reference recomputes for every PAIR
 //     (:242-244), are computed once per particle (identical values).
 //   * k_integrate is fused into the force kernel (forces read the sorted copies, so updating the

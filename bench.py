@@ -270,6 +270,11 @@ def run_product(a):
         except Exception as e:                      # never lose the measurement to the balancer
             parts = slab.partition_rows(H, world)
             balance = {"error": repr(e)[:200]}
+        agreed = [None] * world                     # one partition for all ranks, or equal rows for all
+        dist.all_gather_object(agreed, parts)
+        if any(p != agreed[0] for p in agreed):
+            parts = slab.partition_rows(H, world)
+            balance = {"error": "ranks disagreed on the balanced partition; equal rows used"}
     y0, hl = parts[rank]
     sim = Hypersonic2D(cfg, dtype=a.dtype, device=dev, y_begin=y0, h_local=hl, stream=stream)
     if a.seg_rows:

@@ -1146,4 +1146,169 @@ int tau_hyp3d_destroy(tau_hyp3d *h) {
   return TAU_OK;
 }
 
+// ---- multi-GPU behind the C boundary: one process, one z-slab handle per device ---------------------------------------------
+// (create(cfg, dims, ngpus); the reference has no multi-GPU path.)  z is periodic, so the slabs form a ring.  Per
+// step: the three boundary planes of every field travel to the neighbours' ghost planes (cudaMemcpyPeerAsync on the
+// destination's stream), every device runs its step kernel, the max wavespeed sums are folded on the host — one
+// synchronisation per step, which the reference's own loop has twice (:1684-1700) — and every device's controller kernel
+// commits the same clock.  Bit-identical to one handle over the whole grid (emulator test; tests/test_multi_gpu.py on >= 2 GPUs).
+struct tau_hyp3d_group {
+  int n;
+  tau_hyp3d_params prm;
+  tau_hyp3d *h[8];
+  int dev[8], z0[8], nl[8];
+  long long steps;
+};
+
+int tau_hyp3d_group_create(const tau_hyp3d_params *p, int ngpus, const int *devices, tau_hyp3d_group **out) {
+  TAU_REQUIRE(p && out, "tau_hyp3d_group_create: null argument");
+  TAU_REQUIRE(ngpus >= 1 && ngpus <= 8, "tau_hyp3d_group_create: ngpus must be in [1, 8] (got %d)", ngpus);
+  TAU_REQUIRE(ngpus == 1 || p->nz >= ngpus * T3_H, "tau_hyp3d_group_create: %d planes cannot be split into %d slabs of >= %d",
+              p->nz, ngpus, T3_H);
+  const int have = tau_device_count();
+  if (have <= 0) {
+    tau_set_error("tau_hyp3d_group_create: no CUDA device (this library has no CPU fallback)");
+    return TAU_ERR_NODEV;
+  }
+  TAU_REQUIRE(have >= ngpus, "tau_hyp3d_group_create: %d GPUs requested, %d visible", ngpus, have);
+  tau_hyp3d_group *g = new (std::nothrow) tau_hyp3d_group();
+  if (!g) return TAU_ERR_NOMEM;
+  memset(g, 0, sizeof(*g));
+  g->n = ngpus;
+  g->prm = *p;
+  const int base = p->nz / ngpus, rem = p->nz % ngpus;
+  int z = 0, rc = TAU_OK;
+  for (int i = 0; i < ngpus && !rc; ++i) {
+    g->dev[i] = devices ? devices[i] : i;
+    g->z0[i] = z;
+    g->nl[i] = base + (i < rem ? 1 : 0);
+    z += g->nl[i];
+    rc = tau_hyp3d_create(p, g->dev[i], g->z0[i], g->nl[i], nullptr, &g->h[i]);
+  }
+  for (int i = 0; i < ngpus && !rc && ngpus > 1; ++i) {  // direct peer copies where the devices allow it
+    if (cudaSetDevice(g->dev[i]) != cudaSuccess) rc = TAU_ERR_CUDA;
+    for (int j = 0; j < ngpus && !rc; ++j) {
+      if (j == i) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, g->dev[i], g->dev[j]);
+      if (can) cudaDeviceEnablePeerAccess(g->dev[j], 0);
+      cudaGetLastError();  // already enabled: fine; not possible: cudaMemcpyPeerAsync stages through the host
+    }
+  }
+  if (rc) {
+    for (int i = 0; i < ngpus; ++i) tau_hyp3d_destroy(g->h[i]);
+    delete g;
+    return rc;
+  }
+  *out = g;
+  return TAU_OK;
+}
+
+int tau_hyp3d_group_size(tau_hyp3d_group *g) { return g ? g->n : -1; }
+int tau_hyp3d_group_member(tau_hyp3d_group *g, int i, tau_hyp3d **h, int *z_begin, int *nz_local) {
+  TAU_REQUIRE(g && i >= 0 && i < g->n, "tau_hyp3d_group_member: bad argument");
+  if (h) *h = g->h[i];
+  if (z_begin) *z_begin = g->z0[i];
+  if (nz_local) *nz_local = g->nl[i];
+  return TAU_OK;
+}
+
+int tau_hyp3d_group_init(tau_hyp3d_group *g) {
+  TAU_REQUIRE(g, "tau_hyp3d_group_init: null handle");
+  for (int i = 0; i < g->n; ++i) {
+    const int rc = tau_hyp3d_init(g->h[i]);
+    if (rc) return rc;
+  }
+  g->steps = 0;
+  return TAU_OK;
+}
+
+// planes cover the WHOLE grid (nz x ny x nx, reference layout); clock2 = (t, d_tau) or null for the defaults
+int tau_hyp3d_group_upload(tau_hyp3d_group *g, const float *const planes[6], const float *clock2) {
+  TAU_REQUIRE(g && planes, "tau_hyp3d_group_upload: null argument");
+  const size_t nxy = (size_t)g->prm.nx * g->prm.ny;
+  for (int i = 0; i < g->n; ++i) {
+    const float *pl[6];
+    for (int f = 0; f < 6; ++f) {
+      TAU_REQUIRE(planes[f], "tau_hyp3d_group_upload: null plane %d", f);
+      pl[f] = planes[f] + (size_t)g->z0[i] * nxy;
+    }
+    const int rc = tau_hyp3d_upload(g->h[i], pl, clock2);
+    if (rc) return rc;
+  }
+  g->steps = 0;
+  return TAU_OK;
+}
+
+int tau_hyp3d_group_step(tau_hyp3d_group *g, int nsteps) {
+  TAU_REQUIRE(g && nsteps >= 0, "tau_hyp3d_group_step: bad argument");
+  if (g->n == 1) {
+    const int rc = tau_hyp3d_step(g->h[0], nsteps);
+    if (!rc) g->steps += nsteps;
+    return rc;
+  }
+  const size_t nxy = (size_t)g->prm.nx * g->prm.ny, ghost = (size_t)T3_H * nxy * sizeof(float);
+  for (int s = 0; s < nsteps; ++s) {
+    // ghost planes of the CURRENT state: every source's step kernel has completed (synchronised below / by upload)
+    for (int r = 0; r < g->n; ++r) {
+      tau_hyp3d *a = g->h[r], *b = g->h[(r + 1) % g->n];  // b sits above a (ring)
+      for (int f = 0; f < 6; ++f) {
+        float *pa = a->st[a->cur] + (size_t)f * a->plane, *pb = b->st[b->cur] + (size_t)f * b->plane;
+        // a's last T3_H own planes -> b's lower ghost planes; b's first T3_H own planes -> a's upper ghost planes
+        TAU_CUDA(cudaMemcpyPeerAsync(pb, b->device, pa + (size_t)a->nz_local * nxy, a->device, ghost, b->stream));
+        TAU_CUDA(cudaMemcpyPeerAsync(pa + (size_t)(a->nz_local + T3_H) * nxy, a->device, pb + (size_t)T3_H * nxy, b->device, ghost,
+                                     a->stream));
+      }
+    }
+    for (int r = 0; r < g->n; ++r) {
+      TAU_CUDA(cudaSetDevice(g->dev[r]));
+      const int rc = tau_hyp3d_step_begin(g->h[r]);
+      if (rc) return rc;
+    }
+    float m = 0.f, mr[8];
+    for (int r = 0; r < g->n; ++r)
+      TAU_CUDA(cudaMemcpyAsync(&mr[r], &g->h[r]->clk->maxs, sizeof(float), cudaMemcpyDeviceToHost, g->h[r]->stream));
+    for (int r = 0; r < g->n; ++r) {
+      TAU_CUDA(cudaStreamSynchronize(g->h[r]->stream));
+      m = mr[r] > m ? mr[r] : m;  // exact: max is associative (what the all-reduce of the torchrun path computes)
+    }
+    for (int r = 0; r < g->n; ++r) {
+      TAU_CUDA(cudaSetDevice(g->dev[r]));
+      TAU_CUDA(cudaMemcpyAsync(&g->h[r]->clk->maxs, &m, sizeof(float), cudaMemcpyHostToDevice, g->h[r]->stream));
+      const int rc = tau_hyp3d_step_end(g->h[r]);
+      if (rc) return rc;
+    }
+    for (int r = 0; r < g->n; ++r) TAU_CUDA(cudaStreamSynchronize(g->h[r]->stream));  // `m` is read by the copies above
+    g->steps++;
+  }
+  return TAU_OK;
+}
+
+int tau_hyp3d_group_clock(tau_hyp3d_group *g, float *t, float *d_tau, float *dt_last, float *maxs_last) {
+  TAU_REQUIRE(g, "tau_hyp3d_group_clock: null handle");
+  TAU_CUDA(cudaSetDevice(g->dev[0]));
+  return tau_hyp3d_clock(g->h[0], t, d_tau, dt_last, maxs_last);  // every slab carries the same clock
+}
+
+int tau_hyp3d_group_download(tau_hyp3d_group *g, float *const planes[6], uint8_t *solid) {
+  TAU_REQUIRE(g && planes, "tau_hyp3d_group_download: null argument");
+  const size_t nxy = (size_t)g->prm.nx * g->prm.ny;
+  for (int i = 0; i < g->n; ++i) {
+    float *pl[6];
+    for (int f = 0; f < 6; ++f) pl[f] = planes[f] ? planes[f] + (size_t)g->z0[i] * nxy : nullptr;
+    const int rc = tau_hyp3d_download(g->h[i], pl, solid ? solid + (size_t)g->z0[i] * nxy : nullptr);
+    if (rc) return rc;
+  }
+  return TAU_OK;
+}
+
+long long tau_hyp3d_group_steps_done(tau_hyp3d_group *g) { return g ? g->steps : -1; }
+
+int tau_hyp3d_group_destroy(tau_hyp3d_group *g) {
+  if (!g) return TAU_OK;
+  for (int i = 0; i < g->n; ++i) tau_hyp3d_destroy(g->h[i]);
+  delete g;
+  return TAU_OK;
+}
+
 }  // extern "C"

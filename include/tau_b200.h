@@ -263,6 +263,22 @@ int tau_4spl_info(const char *path, int dims[6]);
  * those) */
 int tau_hyp3d_device_state(tau_hyp3d *h, float **planes, float **maxs);
 long long tau_hyp3d_steps_done(tau_hyp3d *h);
+/* Multi-GPU from ONE process (new: the reference has none; SURVEY 8(b) create(cfg, dims, ngpus)): one z-slab handle per
+ * device, z periodic = a ring.  Per step the three boundary planes of every field go to the neighbours' ghost planes by
+ * cudaMemcpyPeerAsync, every device runs its step kernel, the max wavespeed sums are folded on the host (one
+ * synchronisation per step; the reference's loop :1684-1700 has two) and every device's controller commits the same clock.
+ * planes cover the whole grid in the reference layout.  devices = NULL: devices 0 .. ngpus-1. */
+typedef struct tau_hyp3d_group tau_hyp3d_group;
+int tau_hyp3d_group_create(const tau_hyp3d_params *p, int ngpus, const int *devices, tau_hyp3d_group **out);
+int tau_hyp3d_group_size(tau_hyp3d_group *g);
+int tau_hyp3d_group_member(tau_hyp3d_group *g, int i, tau_hyp3d **h, int *z_begin, int *nz_local);
+int tau_hyp3d_group_init(tau_hyp3d_group *g);
+int tau_hyp3d_group_upload(tau_hyp3d_group *g, const float *const planes[6], const float *clock2);
+int tau_hyp3d_group_step(tau_hyp3d_group *g, int nsteps);
+int tau_hyp3d_group_clock(tau_hyp3d_group *g, float *t, float *d_tau, float *dt_last, float *maxs_last);
+int tau_hyp3d_group_download(tau_hyp3d_group *g, float *const planes[6], uint8_t *solid);
+long long tau_hyp3d_group_steps_done(tau_hyp3d_group *g);
+int tau_hyp3d_group_destroy(tau_hyp3d_group *g);
 long long tau_hyp3d_launch_count(tau_hyp3d *h);
 int tau_hyp3d_last_step_ms(tau_hyp3d *h, float *ms);
 int tau_hyp3d_destroy(tau_hyp3d *h);

@@ -166,3 +166,45 @@ def run_slabs(prm, planes, steps, clock, world, packed=False):
         clocks.append(tuple(float(x.value) for x in v))
         L.tau_hyp3d_destroy(h)
     return out, clocks
+
+
+def run_group(prm, planes, steps, clock, ngpus, packed=True, chunks=(None,)):
+    """tau_hyp3d_group_*: ONE process, one z-slab handle per (pretend) device, ghost planes by cudaMemcpyPeerAsync, host max.
+    `planes` None: group_init.  `chunks`: the steps are issued in these pieces (None = all at once).
+    -> (planes of the whole grid, solid, (t, d_tau, dt, maxs))"""
+    L = lib(packed)
+    gp = C.c_void_p
+    L.tau_hyp3d_group_create.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.POINTER(gp)]
+    L.tau_hyp3d_group_init.argtypes = [gp]
+    L.tau_hyp3d_group_upload.argtypes = [gp, C.POINTER(C.c_void_p), C.c_void_p]
+    L.tau_hyp3d_group_step.argtypes = [gp, C.c_int]
+    L.tau_hyp3d_group_clock.argtypes = [gp] + [C.POINTER(C.c_float)] * 4
+    L.tau_hyp3d_group_download.argtypes = [gp, C.POINTER(C.c_void_p), C.c_void_p]
+    L.tau_hyp3d_group_destroy.argtypes = [gp]
+    L.tau_hyp3d_group_size.argtypes = [gp]
+    g = gp()
+    cp = cparams(prm)
+    assert L.tau_hyp3d_group_create(C.byref(cp), ngpus, None, C.byref(g)) == 0, L.tau_hostemu_last_error()
+    assert L.tau_hyp3d_group_size(g) == ngpus
+    shape = (prm.nz, prm.ny, prm.nx)
+    if planes is None:
+        assert L.tau_hyp3d_group_init(g) == 0
+    else:
+        arrs = [np.ascontiguousarray(p, np.float32).reshape(shape) for p in planes]
+        ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in arrs])
+        ck = np.array(clock, np.float32)
+        assert L.tau_hyp3d_group_upload(g, ptrs, C.c_void_p(ck.ctypes.data)) == 0, L.tau_hostemu_last_error()
+    left = steps
+    for c in chunks:
+        k = left if c is None else min(c, left)
+        assert L.tau_hyp3d_group_step(g, k) == 0, L.tau_hostemu_last_error()
+        left -= k
+    assert left == 0
+    out = [np.empty(shape, np.float32) for _ in range(6)]
+    solid = np.empty(shape, np.uint8)
+    ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in out])
+    assert L.tau_hyp3d_group_download(g, ptrs, C.c_void_p(solid.ctypes.data)) == 0
+    v = [C.c_float() for _ in range(4)]
+    assert L.tau_hyp3d_group_clock(g, *[C.byref(x) for x in v]) == 0
+    L.tau_hyp3d_group_destroy(g)
+    return out, solid, tuple(float(x.value) for x in v)

@@ -457,6 +457,22 @@ def test_hyp3d_prim_side_buffer_is_bit_identical_to_decoding_every_tile(develope
         assert all(ck[:2] == cka[:2] for ck in cks), world
 
 
+@pytest.mark.parametrize("ngpus", [1, 2, 3, 4])
+def test_hyp3d_group_equals_single_domain(developed_3d_flow, monkeypatch, ngpus):
+    """tau_hyp3d_group_* (ONE process, one z-slab handle per pretend device, ghost planes by cudaMemcpyPeerAsync around the
+    periodic ring, max wavespeed folded on the host, every controller committing the same clock) reproduces the single
+    handle bit for bit: a developed flow uploaded with its clock, stepped in uneven pieces, and the k_init state."""
+    monkeypatch.setenv("TAU_HC_DEVICES", str(ngpus))
+    prm, dev, solid = developed_3d_flow
+    steps, clock = 5, (0.012, 2e-3)
+    a, sol_a, cka = hyp3d_emu.run(prm, dev, steps, clock, packed=True)
+    b, sol_b, ckb = hyp3d_emu.run_group(prm, dev, steps, clock, ngpus, chunks=(2, 1, None))
+    assert all(np.array_equal(x, y) for x, y in zip(a, b)) and np.array_equal(sol_a, sol_b) and cka == ckb
+    c, _, ckc = hyp3d_emu.run(prm, None, 3, None, packed=True)
+    d, _, ckd = hyp3d_emu.run_group(prm, None, 3, None, ngpus)
+    assert all(np.array_equal(x, y) for x, y in zip(c, d)) and ckc == ckd
+
+
 def test_hyp3d_4spl_frame_export_is_bit_identical_to_the_reference_host_loop(developed_3d_flow):
     """tau_hyp3d_export_frame (never run on hardware): schlieren field (vis mode 8 = th3cs.cu's
     k_schlieren_export), min/max by ordered-integer atomics, palette index by binary search over the 255
@@ -600,6 +616,15 @@ def test_c_host_programs_run_end_to_end_on_the_emulator(tmp_path):
         r = subprocess.run([os.path.join(cli, exe)] + args, capture_output=True, text=True, timeout=300, env=env,
                            cwd=str(tmp_path))
         assert r.returncode == 0 and "updates/s" in r.stdout, (exe, r.stdout[-300:], r.stderr[-300:])
+    # tau3d --gpus N (tau_hyp3d_group_*, one process): the dump is the --gpus 1 dump, byte for byte
+    dumps = []
+    for gpus in (1, 3):
+        d = str(tmp_path / f"t3_{gpus}.bin")
+        r = subprocess.run([os.path.join(cli, "tau3d"), "--n", "18", "--frames", "3", "--gpus", str(gpus), "--dump", d],
+                           capture_output=True, text=True, timeout=300, env=dict(env, TAU_HC_DEVICES="3"), cwd=str(tmp_path))
+        assert r.returncode == 0 and f"on {gpus} GPU" in r.stdout, (gpus, r.stdout[-300:], r.stderr[-300:])
+        dumps.append(open(d, "rb").read())
+    assert dumps[0] == dumps[1] and len(dumps[0]) > 6 * 4 * 18 ** 3
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "th3cs_ref_host.npz"))
     assert splat4.info(out4) == dict(width=24, height=24, depth=24, frames=6, pSize=256, flags=4)
     assert np.array_equal(splat4.parse(open(out4, "rb").read())["indices"], g["indices"][:6])

@@ -93,3 +93,21 @@ def test_cli_gpus_flag_dump_identical_to_one_gpu(tmp_path):
         dumps.append(_dump_planes(d))
     for planes, t in dumps[1:]:
         assert t == dumps[0][1] and np.array_equal(planes, dumps[0][0])
+
+
+def test_tau3d_gpus_flag_dump_identical_to_one_gpu(tmp_path):
+    """`tau3d --gpus N` (tau_hyp3d_group_*: one process, z-slab ring, ghost planes by cudaMemcpyPeerAsync, host max) writes
+    the same dump as `--gpus 1`, byte for byte — 96^3, 30 steps from k_init"""
+    from fluid_sims_b200 import device_count
+    n = device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    exe = os.path.join(ROOT, "fluid_sims_b200", "cli", "tau3d")
+    dumps = []
+    for g in (1, 2, min(n, 8)):
+        d = tmp_path / f"t3_{g}.dump"
+        r = subprocess.run([exe, "--n", "96", "--frames", "15", "--gpus", str(g), "--dump", str(d)], capture_output=True,
+                           text=True, timeout=300)
+        assert r.returncode == 0 and "Mcell-updates/s" in r.stdout, r.stderr
+        dumps.append(open(d, "rb").read())
+    assert all(x == dumps[0] for x in dumps[1:]) and len(dumps[0]) > 6 * 4 * 96 ** 3

@@ -44,6 +44,14 @@ _steps_done = declare("tau_hyp3d_steps_done", [_h], C.c_longlong)
 _launches = declare("tau_hyp3d_launch_count", [_h], C.c_longlong)
 _last_ms = declare("tau_hyp3d_last_step_ms", [_h, C.POINTER(C.c_float)])
 _destroy = declare("tau_hyp3d_destroy", [_h])
+_g = C.c_void_p
+_g_create = declare("tau_hyp3d_group_create", [C.POINTER(_CParams), C.c_int, C.c_void_p, C.POINTER(_g)])
+_g_init = declare("tau_hyp3d_group_init", [_g])
+_g_upload = declare("tau_hyp3d_group_upload", [_g, C.POINTER(C.c_void_p), C.c_void_p])
+_g_step = declare("tau_hyp3d_group_step", [_g, C.c_int])
+_g_clock = declare("tau_hyp3d_group_clock", [_g] + [C.POINTER(C.c_float)] * 4)
+_g_download = declare("tau_hyp3d_group_download", [_g, C.POINTER(C.c_void_p), C.c_void_p])
+_g_destroy = declare("tau_hyp3d_group_destroy", [_g])
 
 HALO = 3
 PLANES = ("xi", "phix", "phiy", "phiz", "lam", "zet")
@@ -183,6 +191,61 @@ class Hypersonic3D:
         if self._handle:
             _destroy(self._handle)
             self._handle = _h()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Hypersonic3DGroup:
+    """The 3-D solver on `ngpus` devices from ONE process (tau_hyp3d_group_*): one z-slab handle per device, the periodic
+    ring's ghost planes by cudaMemcpyPeerAsync, the max wavespeed folded on the host once per step.  Planes cover the whole
+    grid in the reference layout; results are bit-identical to Hypersonic3D on one device."""
+
+    def __init__(self, params: Params | None = None, ngpus: int = 1):
+        self.params = params or Params.default()
+        self.ngpus = ngpus
+        self._handle = _g()
+        cp = self.params._c()
+        check(_g_create(C.byref(cp), ngpus, None, C.byref(self._handle)))
+
+    @property
+    def shape(self):
+        return (self.params.nz, self.params.ny, self.params.nx)
+
+    def init(self):
+        check(_g_init(self._handle))
+        return self
+
+    def upload(self, planes, clock=None):
+        arrs = [np.ascontiguousarray(p, np.float32).reshape(self.shape) for p in planes]
+        ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in arrs])
+        ck = np.array(clock, np.float32) if clock is not None else None
+        check(_g_upload(self._handle, ptrs, C.c_void_p(ck.ctypes.data if ck is not None else 0)))
+        return self
+
+    def step(self, nsteps: int = 1):
+        check(_g_step(self._handle, nsteps))
+        return self
+
+    def clock(self):
+        v = [C.c_float() for _ in range(4)]
+        check(_g_clock(self._handle, *[C.byref(x) for x in v]))
+        return tuple(float(x.value) for x in v)
+
+    def download(self):
+        out = [np.empty(self.shape, np.float32) for _ in range(6)]
+        solid = np.empty(self.shape, np.uint8)
+        ptrs = (C.c_void_p * 6)(*[a.ctypes.data for a in out])
+        check(_g_download(self._handle, ptrs, C.c_void_p(solid.ctypes.data)))
+        return out, solid
+
+    def close(self):
+        if self._handle:
+            check(_g_destroy(self._handle))
+            self._handle = _g()
 
     def __del__(self):
         try:

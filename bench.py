@@ -37,6 +37,10 @@ Definitions
   other_configs  BASELINE configs 3-5 (Gray-Scott 8192^2, 3-D hypersonic 512^3 — z-slabs at N > 1 —,
            SPH 2^21 particles), short runs of bench_all.py's benches, each with its roofline, reference_gpu (N = 1) and a
            state_crc that is equal across N when the multi-GPU run is bit-identical to the single-GPU one.
+  slab_balance  N > 1 (strong scaling, peer exchange): the y-slabs are cut by measured cost, not by equal rows —
+           slab.hyp2d_balanced_partition runs two short trials BEFORE the benchmark's own handles exist, compares how long
+           each rank's step kernel is busy (the slabs with the bow shock, the body and the wake are 10-20 % slower per row)
+           and moves the cuts; `rows` = the partition used.  The state does not depend on it (state_crc); --no-balance.
 The working set (2 x 268 MB of state) is larger than the 126 MB L2, so no L2 flush is needed
 between timed steps.
 
